@@ -1,0 +1,97 @@
+"""ctypes mirror of include/grb.h (the C ABI). Plumbing only: no physics lives in Python.
+
+The layout is checked against the compiled library by `grb_abi_sizeof` (tests/test_abi.py)."""
+import ctypes as C
+
+GRB_ABI_VERSION = 1
+GRB_MAX_NODES = 16
+GRB_MAX_RES = 12
+GRB_MAX_VETO = 8
+GRB_MAX_DIM = 16
+GRB_MAX_TAPE = 32
+GRB_MAX_BINS = 128
+GRB_RHO_DIM = 5
+GRB_MAX_HAMP = 36
+
+GRB_OK, GRB_ERR_ARG, GRB_ERR_CUDA, GRB_ERR_UNSUPPORTED, GRB_ERR_PARSE, GRB_ERR_STATE, GRB_ERR_NCCL = (
+    0, -1, -2, -3, -4, -5, -6)
+
+GRB_PROC_YY_CON, GRB_PROC_YY_QED, GRB_PROC_PP_RES = 3, 4, 9
+GRB_PROC_PP_CONTENSOR, GRB_PROC_PP_CON, GRB_PROC_PP_CON_MINUS, GRB_PROC_PP_RES_CON = 12, 15, 16, 17
+
+GRB_FLAG_KIN, GRB_FLAG_FID, GRB_FLAG_VETO, GRB_FLAG_AMP = 1, 2, 4, 8
+GRB_FLAGS_VALID = 7
+
+GRB_MODE_BURNIN, GRB_MODE_INTEGRATE, GRB_MODE_GENERATE = 0, 1, 2
+
+DUMP_NAMES = ["t1", "t2", "s1", "s2", "m2", "Y", "Pt", "t_hat", "u_hat", "amp2", "hamp0_re", "hamp0_im"]
+GRB_DUMP_LEN = len(DUMP_NAMES)
+
+i32, f64 = C.c_int32, C.c_double
+
+
+class Node(C.Structure):
+    _fields_ = [("pdg", i32), ("spinX2", i32), ("parent", i32), ("first_child", i32), ("n_children", i32),
+                ("pad_", i32), ("mass", f64), ("width", f64)]
+
+
+class GenCut(C.Structure):
+    _fields_ = [(k, f64) for k in ("Y_min", "Y_max", "M_min", "M_max", "forward_pt_min", "forward_pt_max",
+                                   "XI_min", "XI_max")]
+
+
+class FidCut(C.Structure):
+    _fields_ = [("active", i32), ("usercuts", i32)] + [(k, f64) for k in (
+        "eta_min", "eta_max", "rap_min", "rap_max", "pt_min", "pt_max", "Et_min", "Et_max",
+        "M_min", "M_max", "Y_min", "Y_max", "Pt_min", "Pt_max",
+        "forward_t_min", "forward_t_max", "forward_M_min", "forward_M_max")]
+
+
+class VetoDomain(C.Structure):
+    _fields_ = [(k, f64) for k in ("eta_min", "eta_max", "pt_min", "pt_max")]
+
+
+class ParamSoft(C.Structure):
+    _fields_ = [(k, f64) for k in ("DELTA_P", "ALPHA_P", "gN_P", "gN_O", "g3P", "gamma", "fc1", "fc2", "fc3")] + [
+        ("odderon_on", i32), ("pad_", i32)]
+
+
+class ParamRegge(C.Structure):
+    _fields_ = [("a0", f64 * 3), ("ap", f64 * 3), ("sgn", f64 * 3), ("s0", f64), ("offshellFF", i32),
+                ("reggeize", i32), ("b_EXP", f64), ("a_OREAR", f64), ("b_OREAR", f64), ("b_POW", f64),
+                ("omega", f64), ("c", f64 * 3), ("n", i32 * 3), ("pad_", i32)]
+
+
+class ParamTensorPom(C.Structure):
+    _fields_ = [(k, f64) for k in ("delta_P", "delta_O", "delta_1R", "delta_2R", "ap_P", "ap_O", "ap_1R",
+                                   "ap_2R", "eta_O", "gPNN", "gPpipi", "gPKK")] + [
+        ("gPrhorho", f64 * 2), ("gPphiphi", f64 * 2), ("M_O", f64), ("M_1R", f64)]
+
+
+class Resonance(C.Structure):
+    _fields_ = [("pdg", i32), ("spinX2", i32), ("P", i32), ("BW", i32), ("spingen", i32), ("spindec", i32),
+                ("frame", i32), ("jmax", i32), ("mass", f64), ("width", f64), ("g_re", f64), ("g_im", f64),
+                ("g_FF", f64), ("g_decay", f64), ("BR", f64), ("g_Tensor", f64 * 8),
+                ("rho_re", f64 * (GRB_RHO_DIM * GRB_RHO_DIM)), ("rho_im", f64 * (GRB_RHO_DIM * GRB_RHO_DIM)),
+                ("T_re", f64 * 9), ("T_im", f64 * 9), ("T_rows", i32), ("T_cols", i32)]
+
+
+class ProcessDesc(C.Structure):
+    _fields_ = [(k, i32) for k in (
+        "abi_version", "ps_class", "proc", "screening", "excitation", "flatamp", "ps_active", "flatmass2",
+        "lipsdim", "n_tape", "n_nodes", "n_legs", "n_final", "n_res", "n_veto", "veto_active", "em_ff",
+        "qed_alpha", "loop_nkt", "loop_nphi")] + [(k, f64) for k in (
+            "loop_min_kt", "loop_max_kt", "s", "sqrt_s", "pbeam1_pz", "pbeam1_E", "pbeam2_pz", "pbeam2_E",
+            "beam1_mass", "beam2_mass", "S_factor", "offshell", "flat_b")] + [
+        ("nodes", Node * GRB_MAX_NODES), ("gcuts", GenCut), ("fcuts", FidCut),
+        ("veto", VetoDomain * GRB_MAX_VETO), ("soft", ParamSoft), ("regge", ParamRegge),
+        ("tpom", ParamTensorPom), ("res", Resonance * GRB_MAX_RES)]
+
+
+class Accum(C.Structure):
+    _fields_ = [(k, f64) for k in ("fsum", "f2sum", "evaluations", "n_kin_ok", "n_fid_ok", "n_veto_ok",
+                                   "n_amp_ok", "n_nan_inf", "n_accepted", "n_overflow", "maxW", "maxf")] + [
+        ("fmat", f64 * (GRB_MAX_BINS * GRB_MAX_DIM)), ("f2mat", f64 * (GRB_MAX_BINS * GRB_MAX_DIM))]
+
+
+ACCUM_NSUM = 10  # leading doubles that are sum-reduced; then maxW, maxf (max-reduced); then fmat, f2mat (sum)

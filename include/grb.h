@@ -1,0 +1,313 @@
+/* grb.h -- C ABI of the B200-native batched event-weight engine for GRANIITTI's hot path.
+ *
+ * The reference (mieskolainen/GRANIITTI v1.051) has no FFI: its "operator API" for this path is C++
+ * virtual dispatch across two seams:
+ *
+ *   seam A  double MProcess::EventWeight(const std::vector<double>& randvec, AuxIntData& aux)
+ *           reference include/Graniitti/MProcess.h:84, called per VEGAS/FLAT point from
+ *           MGraniitti::VEGASMultiThread (src/MGraniitti.cc:1341-1443) and SampleFlat (:1446-1482)
+ *   seam B  double MSubProc::GetBareAmplitude2(gra::LORENTZSCALAR&)   (include/Graniitti/MSubProc.h:605)
+ *           selected by the process string "ISTATE[CHANNEL]<class> -> final" (src/MSubProc.cc:90-156)
+ *
+ * This header is what a cgo/ctypes/C++ binding of those seams binds instead: plain pointers and sizes,
+ * no C++ or torch types, errors as negative return codes (never exceptions), all buffers caller-owned.
+ * One engine per host thread / GPU rank; an engine is not thread-safe.
+ *
+ * Every entry point names the reference interface it replaces.  INTEGRATION.md shows the reference-side
+ * stub (a patched MGraniitti::VEGAS) that a maintainer would add.
+ */
+#ifndef GRB_H
+#define GRB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRB_ABI_VERSION 1
+
+/* ---- error codes ---------------------------------------------------------------------------------- */
+enum {
+  GRB_OK              = 0,
+  GRB_ERR_ARG         = -1, /* bad argument (replaces std::invalid_argument thrown by the reference)    */
+  GRB_ERR_CUDA        = -2, /* CUDA runtime error; no CPU fallback exists by design                      */
+  GRB_ERR_UNSUPPORTED = -3, /* process / option outside the hot-path scope        */
+  GRB_ERR_PARSE       = -4, /* steering card / model file parse error                                    */
+  GRB_ERR_STATE       = -5, /* call sequence error (e.g. screening on but no eikonal table set)          */
+  GRB_ERR_NCCL        = -6
+};
+
+/* ---- limits --------------------------------------------------------------------------------------- */
+#define GRB_MAX_NODES 16   /* flattened central decay tree nodes (config 5: 2 rho + 4 pi = 6)            */
+#define GRB_MAX_RES 12     /* resonances in a coherent sum (cards use <= 8)                              */
+#define GRB_MAX_VETO 8     /* veto domains                                                               */
+#define GRB_MAX_DIM 16     /* VEGAS dimension bound (<F>: 6, +2 with N* excitation)                      */
+#define GRB_MAX_TAPE 32    /* internal uniforms per point (config 5 uses 12)                             */
+#define GRB_MAX_BINS 128   /* VEGAS bins per dimension (reference MVEGAS.h BINS default 128)             */
+#define GRB_MAX_LOOP_KT 64 /* screening loop kt nodes (Nkt+1 <= 46 for ND<=10)                           */
+#define GRB_MAX_LOOP_PHI 64
+#define GRB_RHO_DIM 5      /* spin density matrices up to J=2                                            */
+#define GRB_MAX_HAMP 36    /* helicity amplitudes per point (tensor pomeron 2xV)                         */
+
+/* ---- process ids: the reference's MSubProc registry keys (include/Graniitti/MSubProc.h PROC_n) ---- */
+enum {
+  GRB_PROC_NONE         = 0,
+  GRB_PROC_YY_CON       = 3,  /* "yy[CON]"       PROC_3  MSubProc.h:165  MG5 HELAS yy->l+l- + kt-EPA flux */
+  GRB_PROC_YY_QED       = 4,  /* "yy[QED]"       PROC_4  :175            tensor-pomeron code, QED branch   */
+  GRB_PROC_PP_RES       = 9,  /* "PP[RES]"       PROC_9                  sum of MRegge::ME3/PhotoME3       */
+  GRB_PROC_PP_CONTENSOR = 12, /* "PP[CONTENSOR]" PROC_12 :288            MTensorPomeron::ME4               */
+  GRB_PROC_PP_CON       = 15, /* "PP[CON]"       PROC_15 :361            MRegge::ME4(+1)                   */
+  GRB_PROC_PP_CON_MINUS = 16, /* "PP[CON-]"      PROC_16 :382            MRegge::ME4(-1)                   */
+  GRB_PROC_PP_RES_CON   = 17  /* "PP[RES+CON]"   PROC_17 :399            ME4 + sum of ME3/PhotoME3         */
+};
+
+/* phase-space class: "<F>" MFactorized (all BASELINE configs) */
+enum { GRB_CLASS_F = 0, GRB_CLASS_C = 1 };
+
+/* flag bits of one evaluated point = AuxIntData of the reference (include/Graniitti/MProcess.h:37-52) */
+enum {
+  GRB_FLAG_KIN  = 1, /* kinematics_ok                                                                   */
+  GRB_FLAG_FID  = 2, /* fidcuts_ok   (meaningful only if GRB_FLAG_KIN; the reference evaluates it on     */
+  GRB_FLAG_VETO = 4, /* vetocuts_ok   stale state otherwise, MFactorized.cc:146-148)                     */
+  GRB_FLAG_AMP  = 8  /* amplitude_ok = weight finite (MProcess.h:317-340 CheckInfNan)                    */
+};
+#define GRB_FLAGS_VALID (GRB_FLAG_KIN | GRB_FLAG_FID | GRB_FLAG_VETO)
+
+/* ---- flattened process description (POD twin of MProcess + LORENTZSCALAR + PARAM_* namespaces) ----- */
+
+/* one node of the flattened central decay tree (reference MDecayBranch, MParticle.h:62-93) */
+typedef struct {
+  int32_t pdg;
+  int32_t spinX2;
+  int32_t parent;      /* index of mother node, -1 for first-level legs of the central system           */
+  int32_t first_child; /* index of first daughter, -1 if final state                                    */
+  int32_t n_children;  /* 0 (final) or 2 (two-body decays only on the device path)                      */
+  int32_t pad_;
+  double  mass;        /* PDG pole mass                                                                 */
+  double  width;       /* PDG width; BW sampled when width >= 1e-40 (MProcess.cc:753-757)               */
+} grb_node;
+
+/* reference gra::GENCUT / FIDCUT / VETOCUT (include/Graniitti/MKinematics.h:1554-1625) */
+typedef struct {
+  double Y_min, Y_max;                   /* GENCUTS.<F>.Rap                                             */
+  double M_min, M_max;                   /* GENCUTS.<F>.M                                               */
+  double forward_pt_min, forward_pt_max; /* after SetTechnicalBoundaries (MProcess.cc:1369-1386)        */
+  double XI_min, XI_max;
+} grb_gencut;
+
+typedef struct {
+  int32_t active;
+  int32_t usercuts; /* USERCUTS id (MUserCuts.cc:21-215); 0, +-3, +-111 supported                        */
+  double  eta_min, eta_max, rap_min, rap_max, pt_min, pt_max, Et_min, Et_max; /* PARTICLE                */
+  double  M_min, M_max, Y_min, Y_max, Pt_min, Pt_max;                         /* SYSTEM                  */
+  double  forward_t_min, forward_t_max, forward_M_min, forward_M_max;         /* FORWARD                 */
+} grb_fidcut;
+
+typedef struct {
+  double eta_min, eta_max, pt_min, pt_max;
+} grb_vetodomain;
+
+/* PARAM_SOFT (src/MForm.cc:71-130), PARAM_REGGE (src/MRegge.cc:924-1033) */
+typedef struct {
+  double  DELTA_P, ALPHA_P, gN_P, gN_O, g3P, gamma, fc1, fc2, fc3;
+  int32_t odderon_on, pad_;
+} grb_param_soft;
+
+typedef struct {
+  double  a0[3], ap[3], sgn[3];
+  double  s0;
+  int32_t offshellFF; /* 0 exp, 1 Orear, 2 power law                                                     */
+  int32_t reggeize;
+  double  b_EXP, a_OREAR, b_OREAR, b_POW, omega;
+  double  c[3];       /* couplings of the first central leg (PARAM_PI / PARAM_K / ...)                   */
+  int32_t n[3];       /* trajectory on/off                                                               */
+  int32_t pad_;
+} grb_param_regge;
+
+/* PARAM_TENSORPOM (modeldata GENERAL.json), MTensorPomeron.h */
+typedef struct {
+  double delta_P, delta_O, delta_1R, delta_2R;
+  double ap_P, ap_O, ap_1R, ap_2R, eta_O;
+  double gPNN, gPpipi, gPKK;
+  double gPrhorho[2], gPphiphi[2];
+  double M_O, M_1R;
+} grb_param_tensorpom;
+
+/* one resonance (reference gra::PARAM_RES, include/Graniitti/MResonance.h) */
+typedef struct {
+  int32_t pdg, spinX2, P, BW;
+  int32_t spingen, spindec, frame /* 0 CM,1 HX,2 CS,3 GJ,4 PG,5 SR */, jmax;
+  double  mass, width;
+  double  g_re, g_im; /* production coupling                                                             */
+  double  g_FF;
+  double  g_decay;    /* hel.g_decay                                                                     */
+  double  BR;
+  double  g_Tensor[8];
+  double  rho_re[GRB_RHO_DIM * GRB_RHO_DIM]; /* spin density matrix, row-major, (2J+1)^2 used            */
+  double  rho_im[GRB_RHO_DIM * GRB_RHO_DIM];
+  double  T_re[9], T_im[9];                  /* decay helicity T matrix (hel.T), row-major n1 x n2       */
+  int32_t T_rows, T_cols;
+} grb_resonance;
+
+typedef struct {
+  int32_t abi_version;
+  int32_t ps_class;   /* GRB_CLASS_F                                                                     */
+  int32_t proc;       /* GRB_PROC_*                                                                      */
+  int32_t screening;  /* POMLOOP                                                                         */
+  int32_t excitation; /* NSTARS (0 only on the device path)                                              */
+  int32_t flatamp;    /* @FLATAMP (0 only)                                                               */
+  int32_t ps_active;  /* !ISOLATE ("->" true, "&>" false)                                                */
+  int32_t flatmass2;
+  int32_t lipsdim;    /* VEGAS dimension (MFactorized.cc:69-78)                                          */
+  int32_t n_tape;     /* internal uniforms consumed per point when no rejection loop repeats             */
+  int32_t n_nodes;    /* decay tree nodes                                                                */
+  int32_t n_legs;     /* first-level central legs (nodes[0..n_legs-1])                                   */
+  int32_t n_final;    /* leaves                                                                          */
+  int32_t n_res;
+  int32_t n_veto;
+  int32_t veto_active;
+  int32_t em_ff;      /* PARAM_STRUCTURE.EM: 0 DIPOLE, 1 KELLY                                           */
+  int32_t qed_alpha;  /* PARAM_STRUCTURE.QED_alpha: 0 ZERO, 1 MG                                         */
+  int32_t loop_nkt;   /* NumberLoopKT  (MEikonal.h:44-51)                                                */
+  int32_t loop_nphi;  /* NumberLoopPHI                                                                   */
+  double  loop_min_kt, loop_max_kt;
+  double  s, sqrt_s;
+  double  pbeam1_pz, pbeam1_E, pbeam2_pz, pbeam2_E;
+  double  beam1_mass, beam2_mass;
+  double  S_factor;   /* identical-particle symmetry factor (MProcess.cc:449-468)                        */
+  double  offshell;   /* OFFSHELL: number of widths in BW sampling (default 5)                           */
+  double  flat_b;     /* PARAM_FLAT::b                                                                   */
+  grb_node            nodes[GRB_MAX_NODES];
+  grb_gencut          gcuts;
+  grb_fidcut          fcuts;
+  grb_vetodomain      veto[GRB_MAX_VETO];
+  grb_param_soft      soft;
+  grb_param_regge     regge;
+  grb_param_tensorpom tpom;
+  grb_resonance       res[GRB_MAX_RES];
+} grb_process_desc;
+
+/* VEGAS accumulators of one iteration = what VEGASMultiThread adds under the mutex
+ * (src/MGraniitti.cc:1389-1419) + the NaN/Inf counters of MProcess::CheckInfNan.
+ * All doubles so that one fp64 sum all-reduce + one max all-reduce covers it.                            */
+typedef struct {
+  double fsum, f2sum;
+  double evaluations;   /* stat.evaluations                                                              */
+  double n_kin_ok, n_fid_ok, n_veto_ok, n_amp_ok; /* pass counters (stat.*_ok)                            */
+  double n_nan_inf;
+  double n_accepted;    /* hit-or-miss accepted (mode generate)                                          */
+  double n_overflow;    /* f > maxf during generation (MGraniitti.cc:1660)                                */
+  double maxW, maxf;    /* max-reduced                                                                   */
+  double fmat[GRB_MAX_BINS * GRB_MAX_DIM];  /* [bin][dim], dim fastest                                    */
+  double f2mat[GRB_MAX_BINS * GRB_MAX_DIM];
+} grb_accum;
+
+typedef struct grb_engine grb_engine;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+
+/* Build an engine from a flattened process description. Replaces `new MFactorized(process, syntax)` +
+ * `post_Constructor()` (src/MGraniitti.cc:245-309,1016-1018).                                            */
+int grb_create(const grb_process_desc *desc, int device, grb_engine **out);
+
+/* Build an engine from the reference's own steering inputs: JSON5 card (e.g. input/test.json), optional process
+ * string override (`gr -p`), optional POMLOOP override (`gr -l`; -1 = card), and the GRANIITTI base
+ * directory holding modeldata/ (NULL = built-in TUNE0 + PDG subset). Replaces MGraniitti::ReadInput
+ * (src/MGraniitti.cc:317-330) + ReadModelParam + post_Constructor.                                       */
+int grb_create_from_card(const char *card_path, const char *process_override, int pomloop_override,
+                         const char *graniitti_base, int device, grb_engine **out);
+
+/* Host-only variant of the above (no GPU needed): parse and flatten only.                                */
+int grb_parse_card(const char *card_path, const char *process_override, int pomloop_override,
+                   const char *graniitti_base, grb_process_desc *out, char *errbuf, int errbuf_len);
+
+int         grb_get_desc(const grb_engine *e, grb_process_desc *out);
+const char *grb_last_error(const grb_engine *e);
+void        grb_destroy(grb_engine *e);
+
+/* ---- eikonal screening table ---------------------------------------------------------------------- */
+
+/* Load the screening amplitude table A_eik(kt^2) (reference MEikonal::MSA, IArray1D, src/MEikonal.cc:
+ * 404-512): n+1 points on a uniform kt^2 grid. Replaces MEikonal::S3Constructor's file read
+ * (src/MEikonal.cc:46-128).  Host pointers.                                                              */
+int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const double *im, int n_points);
+
+/* Build the density (MBT) and amplitude (MSA) tables on the device from PARAM_SOFT, replacing
+ * MEikonal::S3Density/S3Screening/S3CalculateArray (src/MEikonal.cc:177-401). Optionally returns the MSA
+ * table (n_points = NumberKT2+1 each) and sigma_tot/el/inel in mb (S3CalcXS, :262-376).                  */
+int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *kt2_out, double *re_out,
+                      double *im_out, double *xs_tot_el_inel /* [3] or NULL */);
+
+/* ---- seam A x n : batched EventWeight --------------------------------------------------------------- */
+
+/* Evaluate n caller-supplied points. u is structure-of-arrays [dim][n] (VEGAS-visible coordinates, the
+ * `randvec` of EventWeight); tape is [dtape][n] (the internal uniforms the reference draws from its
+ * thread RNG inside EventWeight: BW masses, decay angles; MFactorized.cc:374, MKinematics.h:405-409).
+ * w[n] receives the weight W (0 if not Valid()), flags[n] the GRB_FLAG_* bits. dump (optional, [ndump][n],
+ * see GRB_DUMP_*) receives intermediate scalars for parity tests. Pointers may be host or device.        */
+int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
+             uint8_t *flags, double *dump);
+
+enum {
+  GRB_DUMP_T1 = 0, GRB_DUMP_T2, GRB_DUMP_S1, GRB_DUMP_S2, GRB_DUMP_M2, GRB_DUMP_Y, GRB_DUMP_PT,
+  GRB_DUMP_THAT, GRB_DUMP_UHAT, GRB_DUMP_AMP2, GRB_DUMP_HAMP0_RE, GRB_DUMP_HAMP0_IM,
+  GRB_DUMP_LEN
+};
+
+/* ---- VEGAS iteration on the device (hot loop 1) ------------------------------------------------------ */
+
+enum { GRB_MODE_BURNIN = 0, GRB_MODE_INTEGRATE = 1, GRB_MODE_GENERATE = 2 };
+
+/* One VEGAS iteration of `ncalls` points for this rank: points [first_call, first_call+ncalls) of the
+ * iteration are generated on the device by Philox4x32-10 (key = seed, counter = (iteration, global point
+ * index, draw index)), mapped through the grid xmat[bins][dim] exactly as VEGASMultiThread does
+ * (src/MGraniitti.cc:1357-1375), evaluated, and accumulated into *out (host).  Replaces the thread
+ * fan-out + mutex accumulation of src/MGraniitti.cc:1208-1214,1341-1443.  In GRB_MODE_GENERATE accepted
+ * events (hit-or-miss vs maxf, :1657-1668) are compacted into the engine's event buffer.                 */
+int grb_vegas_iterate(grb_engine *e, const double *xmat, int bins, int dim, int64_t first_call,
+                      int64_t ncalls, uint64_t seed, uint64_t iteration, int mode, double maxf,
+                      grb_accum *out);
+
+/* Same, but leaves the accumulators on the device and returns the device pointer (layout = grb_accum) so
+ * that a collective can run on it without a host round trip.  Completed by grb_vegas_fetch.              */
+int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim, int64_t first_call,
+                            int64_t ncalls, uint64_t seed, uint64_t iteration, int mode, double maxf,
+                            void **accum_device_ptr);
+int grb_vegas_fetch(grb_engine *e, grb_accum *out);
+
+/* Grid refinement, reference VEGASData::OptimizeGrid/Rebin (include/Graniitti/MVEGAS.h:87-142). Pure host
+ * function, O(bins*dim), run redundantly on every rank from the all-reduced f2mat.                        */
+int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim, double lambda);
+
+/* Accepted events of the last GRB_MODE_GENERATE iteration: 4-momenta [n_particles][4][n_events] SoA
+ * (particle 0 = central system, 1,2 = forward protons, 3.. = central final states as lts.pfinal) and the
+ * weights.  Host pointers; returns the number of events copied (<= max_events) or a negative error.       */
+int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, double *weights,
+                       int *n_particles);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------- */
+
+/* NCCL communicator bootstrap for hosts without torch.distributed (a C++ MGraniitti on each rank):
+ * rank 0 calls grb_comm_unique_id, ships the 128 bytes to the other ranks by any means, then every rank
+ * calls grb_comm_init.  grb_allreduce sums (fsum..n_overflow, fmat, f2mat) and max-reduces (maxW, maxf) the
+ * device-resident accumulators of the last grb_vegas_iterate_async; no-op for a single rank.  This is
+ * the B200 equivalent of the reference's global mutex (src/MGraniitti.cc:1389-1419).                     */
+int grb_comm_unique_id(char id_out[128]);
+int grb_comm_init(grb_engine *e, int rank, int nranks, const char id[128]);
+int grb_allreduce(grb_engine *e);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------- */
+
+/* Measured fp64 FMA peak of the device (dependent-free DFMA chains on all SMs), in TFLOP/s; this is the
+ * roofline denominator for the path (MEASURED_PEAKS.json has no fp64 figure).                            */
+int grb_measure_dfma_peak(int device, double *tflops_out);
+
+/* Device time in ms of the kernels launched by the last grb_eval / grb_vegas_iterate call (CUDA events on
+ * the engine's stream), and how many kernels that call launched.                                         */
+int grb_last_timing(const grb_engine *e, double *kernel_ms, int *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRB_H */

@@ -1,0 +1,723 @@
+/* oracle/grb_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, scalar, one-point-at-a-time CPU restatement of GRANIITTI's event-weight path
+ * (reference seam A: MFactorized::EventWeight, src/MFactorized.cc:142-184).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this file's
+ * library; the product (graniitti_b200/) never does and has no CPU fallback.
+ *
+ * It follows the reference statement by statement, in the reference's operation order, and is compiled
+ * with -ffp-contract=off so that on the same libm it reproduces the reference's rounding.  Each function
+ * cites the reference file:line it restates.  It is pinned against the compiled reference itself
+ * (oracle/_ref/gra/bin/ref_eval, built from the unmodified sources) through the golden vectors under
+ * tests/golden/ (generator: tests/golden/make_golden.py); see tests/test_oracle_golden.py.
+ *
+ * Parity status: PINNED by reference-generated golden vectors (the reference's own test-suite holds no
+ * vector for this path).
+ */
+#include "grb_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* reference include/Graniitti/MMath.h:30 (long double literal rounded to double) */
+#define O_PI 3.141592653589793238462643383279502884197169399375105820974944
+/* reference include/Graniitti/MPDG.h:64-78 */
+static const double O_GeV2barn = ((6.582119514E-25 * 2.99792458E8) * (6.582119514E-25 * 2.99792458E8)) / 1E-28;
+/* reference include/Graniitti/MProcess.h:372 */
+#define O_ZERO_EPS 1e-12
+
+typedef struct {
+  double x, y, z, e;
+} v4;
+typedef struct {
+  double re, im;
+} cx;
+
+/* ---- M4Vec algebra, reference include/Graniitti/M4Vec.h:120-160,222-236 ----------------------------- */
+static inline double msqrt(double x) { return sqrt(x > 0.0 ? x : 0.0); } /* MMath.h:250 */
+static inline double pow2(double x) { return x * x; }
+static inline v4     v4_add(v4 a, v4 b) { return (v4){a.x + b.x, a.y + b.y, a.z + b.z, a.e + b.e}; }
+static inline v4     v4_sub(v4 a, v4 b) { return (v4){a.x - b.x, a.y - b.y, a.z - b.z, a.e - b.e}; }
+static inline double v4_p3mod2(v4 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+static inline double v4_m2(v4 a) { return a.e * a.e - v4_p3mod2(a); }
+static inline double v4_m(v4 a) {
+  const double m2 = v4_m2(a);
+  return (m2 > 0.0) ? msqrt(m2) : -msqrt(-m2);
+}
+static inline double v4_pt2(v4 a) { return a.x * a.x + a.y * a.y; }
+static inline double v4_pt(v4 a) { return msqrt(v4_pt2(a)); }
+static inline double v4_p3mod(v4 a) { return msqrt(v4_p3mod2(a)); }
+static inline double v4_et(v4 a) { return msqrt(v4_m2(a) + v4_pt2(a)); }
+static inline double v4_eta(v4 a) { return 0.5 * log((v4_p3mod(a) + a.z) / (v4_p3mod(a) - a.z)); }
+static inline double v4_rap(v4 a) { return 0.5 * log((a.e + a.z) / (a.e - a.z)); }
+static inline double v4_dot(v4 a, v4 b) { return a.e * b.e - (a.x * b.x + a.y * b.y + a.z * b.z); }
+
+/* ---- std::complex<double> algebra as libstdc++ evaluates it ------------------------------------------ */
+static inline cx cx_mul(cx a, cx b) { return (cx){a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline cx cx_scale(cx a, double d) { return (cx){a.re * d, a.im * d}; }
+static inline cx cx_add(cx a, cx b) { return (cx){a.re + b.re, a.im + b.im}; }
+static inline double cx_abs2(cx a) { return pow2(hypot(a.re, a.im)); } /* MMath.h:253 abs2 = pow2(std::abs) */
+
+/* ---- per-engine state = the pieces of gra::LORENTZSCALAR the path touches (MKinematics.h:1437-1551) -- */
+typedef struct {
+  const grb_process_desc *d;
+  const grb_oracle_eikonal *eik;
+  v4     pbeam1, pbeam2, beamsum;
+  v4     pfinal[10], pfinal_orig[10];
+  v4     node_p4[GRB_MAX_NODES];
+  double node_moff[GRB_MAX_NODES];
+  double ss[10][10];
+  double s1, s2, t1, t2, t_hat, u_hat, m2, Y, Pt, x1, x2, qt1, qt2;
+  v4     q1, q2;
+  double M_MIN, M_MAX, DW;
+  cx     hamp[GRB_MAX_HAMP];
+  int    nhamp;
+  /* tape of internal uniforms (reference: thread-local MRandom, src/MRandom.cc:62-65) */
+  const double *tape;
+  int           tape_len, tape_pos, tape_overrun;
+  /* loop-invariant signature factors ReggeEta(a0,sgn), MForm.cc:382-385 */
+  cx regge_eta0[3];
+} ost;
+
+static double tape_U(ost *S, double a, double b) {
+  double v = 0.5;
+  if (S->tape_pos < S->tape_len)
+    v = S->tape[S->tape_pos];
+  else
+    S->tape_overrun = 1;
+  S->tape_pos++;
+  return a + (b - a) * v;
+}
+
+/* reference src/MRandom.cc:82-107 RelativisticBWRandom */
+static double bw_random(ost *S, double m0, double Gamma, double LIMIT, double M_MIN) {
+  if (Gamma < 1e-40) return m0;
+  const double m2    = pow2(m0);
+  const double m2max = pow2(m0 + LIMIT * Gamma);
+  const double m2min = fmax(fmax(0.0, pow2(M_MIN)), pow2(m0 - LIMIT * Gamma));
+  double       m2val = 0.0;
+  for (int it = 0; it < 100000; ++it) {
+    const double R = tape_U(S, 0, 1);
+    m2val = m2 + m0 * Gamma *
+                     tan(atan2(m2min - m2, m0 * Gamma) +
+                         R * (atan2(m2max - m2, m0 * Gamma) - atan2(m2min - m2, m0 * Gamma)));
+    if (m2val >= 0) break;
+  }
+  return msqrt(m2val);
+}
+
+/* reference src/MProcess.cc:753-812 GetOffShellMass (FLATMASS2 == false branch) */
+static double offshell_mass(ost *S, int node) {
+  const grb_process_desc *d = S->d;
+  const grb_node *        b = &d->nodes[node];
+  if (b->width < 1e-40) return b->mass;
+  double daughter_masses = 0;
+  if (b->n_children != 0) {
+    for (int i = 0; i < b->n_children; ++i) {
+      const grb_node *l = &d->nodes[b->first_child + i];
+      daughter_masses += fmax(0.0, bw_random(S, l->mass, l->width, d->offshell, 0.0));
+    }
+    daughter_masses += 1e-5;
+  }
+  /* inner loop returns at its first trial: max(dm, .) >= dm */
+  return fmax(daughter_masses, bw_random(S, b->mass, b->width, d->offshell, daughter_masses));
+}
+
+/* reference include/Graniitti/MKinematics.h:33-64 SolvePz3_A (same symbol names) */
+static double solve_pz3_A(double m3, double pt3, double pt4, double pz5, double E5, double s) {
+  const double t2  = E5 * E5;
+  const double t3  = pt3 * pt3;
+  const double t4  = pt4 * pt4;
+  const double t5  = pz5 * pz5;
+  const double t6  = m3 * m3;
+  const double t7  = sqrt(s);
+  const double t8  = s * t2 * 6.0;
+  const double t9  = pow(s, 3.0 / 2.0);
+  const double t10 = t2 * t2;
+  const double t11 = t3 * t3;
+  const double t12 = t4 * t4;
+  const double t13 = t5 * t5;
+  const double t14 = s * s;
+  const double t15 = t5 * t6 * 4.0;
+  const double t16 = t3 * t5 * 2.0;
+  const double t17 = t4 * t5 * 2.0;
+  const double t18 = E5 * t6 * t7 * 8.0;
+  const double t19 = E5 * t3 * t7 * 4.0;
+  const double t20 = E5 * t4 * t7 * 4.0;
+  const double t21 = E5 * t5 * t7 * 4.0;
+  const double t22 = t8 + t10 + t11 + t12 + t13 + t14 + t15 + t16 + t17 + t18 + t19 + t20 + t21 -
+                     E5 * t9 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 - s * t5 * 2.0 - s * t6 * 4.0 -
+                     t2 * t3 * 2.0 - t2 * t4 * 2.0 - t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 4.0 -
+                     E5 * t2 * t7 * 4.0;
+  const double t23 = sqrt(t22);
+  return pz5 * (-1.0 / 2.0) -
+         (E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0))) /
+             (s + t2 - t5 - E5 * t7 * 2.0);
+}
+
+/* reference include/Graniitti/MKinematics.h:117-160 SolvePz3_B */
+static double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5, double E5, double s) {
+  const double t2  = E5 * E5;
+  const double t3  = m3 * m3;
+  const double t4  = m4 * m4;
+  const double t5  = pt3 * pt3;
+  const double t6  = pt4 * pt4;
+  const double t7  = pz5 * pz5;
+  const double t8  = sqrt(s);
+  const double t9  = s * t2 * 6.0;
+  const double t10 = pow(s, 3.0 / 2.0);
+  const double t11 = t2 * t2;
+  const double t12 = t3 * t3;
+  const double t13 = t4 * t4;
+  const double t14 = t5 * t5;
+  const double t15 = t6 * t6;
+  const double t16 = t7 * t7;
+  const double t17 = s * s;
+  const double t18 = t3 * t5 * 2.0;
+  const double t19 = t4 * t6 * 2.0;
+  const double t20 = t3 * t7 * 2.0;
+  const double t21 = t4 * t7 * 2.0;
+  const double t22 = t5 * t7 * 2.0;
+  const double t23 = t6 * t7 * 2.0;
+  const double t24 = E5 * t3 * t8 * 4.0;
+  const double t25 = E5 * t4 * t8 * 4.0;
+  const double t26 = E5 * t5 * t8 * 4.0;
+  const double t27 = E5 * t6 * t8 * 4.0;
+  const double t28 = E5 * t7 * t8 * 4.0;
+  const double t29 = t9 + t11 + t12 + t13 + t14 + t15 + t16 + t17 + t18 + t19 + t20 + t21 + t22 + t23 +
+                     t24 + t25 + t26 + t27 + t28 - E5 * t10 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 -
+                     s * t5 * 2.0 - s * t6 * 2.0 - s * t7 * 2.0 - t2 * t3 * 2.0 - t2 * t4 * 2.0 -
+                     t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 2.0 - t2 * t7 * 2.0 - t3 * t6 * 2.0 -
+                     t4 * t5 * 2.0 - t5 * t6 * 2.0 - E5 * t2 * t8 * 4.0;
+  const double t30 = sqrt(t29);
+  return pz5 * (-1.0 / 2.0) -
+         (E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
+          pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0))) /
+             (s + t2 - t7 - E5 * t8 * 2.0);
+}
+
+/* reference MKinematics.h:220-229 SolvePz */
+static double solve_pz(double m3, double m4, double pt3, double pt4, double pz5, double E5, double s) {
+  if (fabs(m3 - m4) < 1e-9) return solve_pz3_A(m3, pt3, pt4, pz5, E5, s);
+  return solve_pz3_B(m3, m4, pt3, pt4, pz5, E5, s);
+}
+
+/* reference MMath.h:191-198 CheckEMC (note: energy difference is not abs()) */
+static int check_emc(v4 diff) {
+  const double eps = 1e-6;
+  if (fabs(diff.x) > eps || fabs(diff.y) > eps || fabs(diff.z) > eps || diff.e > eps) return 0;
+  return 1;
+}
+
+/* reference MKinematics.h:383-401 LorentzBoost; (beta*p3).sum() of libstdc++ sums from the last element */
+static v4 lorentz_boost(v4 boost, double M0, v4 p, int sign) {
+  const double b0 = sign * boost.x / boost.e, b1 = sign * boost.y / boost.e, b2 = sign * boost.z / boost.e;
+  const double gamma  = boost.e / M0;
+  double       kappa1 = b2 * p.z;
+  kappa1 += b1 * p.y;
+  kappa1 += b0 * p.x;
+  const double kappa2 = gamma * (gamma * kappa1 / (1.0 + gamma) + p.e);
+  return (v4){p.x + kappa2 * b0, p.y + kappa2 * b1, p.z + kappa2 * b2, gamma * (p.e + kappa1)};
+}
+
+/* reference MKinematics.h:294-298 DecayMomentum, :267-271 dPhi2 */
+static double decay_momentum(double x, double y, double z) {
+  return msqrt((x - y - z) * (x + y + z) * (x + y - z) * (x - y + z)) / (2.0 * x);
+}
+static double dphi2(double E, double p_norm) {
+  const double V = 2.0 * 2.0 * O_PI;
+  return V * p_norm / (16.0 * pow2(O_PI) * E);
+}
+
+/* reference MKinematics.h:403-459 FlatIsotropic + Isotropic + TwoBodyPhaseSpace */
+static double two_body(ost *S, v4 mother, double M0, double m1, double m2, v4 *p1, v4 *p2) {
+  const double pnorm    = decay_momentum(M0, m1, m2);
+  const double costheta = tape_U(S, -1.0, 1.0);
+  const double sintheta = msqrt(1.0 - pow2(costheta));
+  const double phi      = tape_U(S, 0.0, 2.0 * O_PI);
+  const double k0 = pnorm * sintheta * cos(phi), k1 = pnorm * sintheta * sin(phi), k2 = pnorm * costheta;
+  const double e0 = msqrt(pow2(m1) + pow2(pnorm)), e1 = msqrt(pow2(m2) + pow2(pnorm));
+  *p1 = lorentz_boost(mother, M0, (v4){k0, k1, k2, e0}, 1);
+  *p2 = lorentz_boost(mother, M0, (v4){-k0, -k1, -k2, e1}, 1);
+  return dphi2(M0, pnorm);
+}
+
+/* reference src/MProcess.cc:1231-1284 ConstructDecayKinematics (2-body branches) */
+static int construct_decay(ost *S, int node) {
+  const grb_node *b = &S->d->nodes[node];
+  if (b->n_children == 0) return 1;
+  if (b->n_children != 2) return 0;
+  const int c0 = b->first_child, c1 = b->first_child + 1;
+  double    m0v, m1v;
+  for (int it = 0;; ++it) {
+    m0v = offshell_mass(S, c0);
+    m1v = offshell_mass(S, c1);
+    S->node_moff[c0] = m0v;
+    S->node_moff[c1] = m1v;
+    /* std::accumulate(m.rbegin(), m.rend(), 0.0): 0 + m[last] + ... + m[0] */
+    if (v4_m(S->node_p4[node]) < (0.0 + m1v) + m0v) {
+      if (it > 100000 || S->tape_overrun) return 0;
+      continue;
+    }
+    break;
+  }
+  const double w = two_body(S, S->node_p4[node], v4_m(S->node_p4[node]), m0v, m1v, &S->node_p4[c0], &S->node_p4[c1]);
+  if (w < 0) return 0;
+  if (!construct_decay(S, c0)) return 0;
+  if (!construct_decay(S, c1)) return 0;
+  return 1;
+}
+
+/* reference src/MProcess.cc:1499-1584 GetLorentzScalars */
+static int lorentz_scalars(ost *S, int Nf) {
+  for (int i = 0; i <= Nf; ++i)
+    for (int j = 0; j <= Nf; ++j) {
+      if (i < j) S->ss[i][j] = v4_m2(v4_add(S->pfinal[i], S->pfinal[j]));
+      if (S->ss[i][j] < 0) return 0;
+    }
+  for (int i = 0; i <= Nf; ++i)
+    for (int j = i; j <= Nf; ++j)
+      if (i != j) S->ss[j][i] = S->ss[i][j];
+  S->s1 = S->ss[1][0];
+  S->s2 = S->ss[2][0];
+  if (S->s1 < 0 || S->s2 < 0) return 0;
+  S->q1 = v4_sub(S->pbeam1, S->pfinal[1]);
+  S->q2 = v4_sub(S->pbeam2, S->pfinal[2]);
+  S->t1 = v4_m2(S->q1);
+  S->t2 = v4_m2(S->q2);
+  if (S->t1 > 0 || S->t2 > 0) return 0;
+  if (S->d->n_legs == 2) {
+    S->t_hat = v4_m2(v4_sub(S->q1, S->node_p4[0]));
+    S->u_hat = v4_m2(v4_sub(S->q1, S->node_p4[1]));
+  }
+  S->x1  = (1 - S->pfinal[1].z / S->pbeam1.z);
+  S->x2  = (1 - S->pfinal[2].z / S->pbeam2.z);
+  S->qt1 = v4_pt(S->q1);
+  S->qt2 = v4_pt(S->q2);
+  S->m2  = v4_m2(S->pfinal[0]);
+  S->Y   = v4_rap(S->pfinal[0]);
+  S->Pt  = v4_pt(S->pfinal[0]);
+  return 1;
+}
+
+/* reference src/MFactorized.cc:307-412 B51BuildKin (symmetric beams: the lab boost of :333-340 is the
+ * identity; asymmetric beams are rejected at creation) */
+static int b51_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2, double yX, double m2X,
+                         double m1, double m2) {
+  const grb_process_desc *d = S->d;
+  v4 p1 = {pt1 * cos(phi1), pt1 * sin(phi1), 0, 0};
+  v4 p2 = {pt2 * cos(phi2), pt2 * sin(phi2), 0, 0};
+  v4 pX = {-(p1.x + p2.x), -(p1.y + p2.y), 0, 0};
+  const double mtX = msqrt(m2X + v4_pt2(pX));
+  pX.z = mtX * sinh(yX);
+  pX.e = mtX * cosh(yX);
+  if (pX.e > (d->sqrt_s - (m1 + m2))) return 0;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, pX.z, pX.e, d->s);
+  const double p2z = -(pX.z + p1z);
+  if (p1z < 0 || p2z > 0) return 0;
+  if (isnan(p1z)) return 0; /* NaN compares false above and would be caught by CheckEMC's comparisons? no:
+                               NaN passes all '>' tests; the reference then fails GetLorentzScalars
+                               only by luck -- see note in DESIGN.md; kept explicit here */
+  p1.z = p1z;
+  p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  p2.z = p2z;
+  p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  S->pfinal[1] = p1;
+  S->pfinal[2] = p2;
+  S->pfinal[0] = pX;
+  if (!check_emc(v4_sub(S->beamsum, v4_add(v4_add(S->pfinal[1], S->pfinal[2]), S->pfinal[0])))) return 0;
+
+  if (d->n_legs == 2) {
+    S->DW = two_body(S, S->pfinal[0], msqrt(m2X), S->node_moff[0], S->node_moff[1], &S->node_p4[0], &S->node_p4[1]);
+  } else {
+    return 0; /* 3-/N-body central systems are outside the device path */
+  }
+  if (S->DW < 0) return 0;
+  for (int i = 0; i < d->n_legs; ++i) S->pfinal[i + 3] = S->node_p4[i];
+  for (int i = 0; i < d->n_legs; ++i)
+    if (!construct_decay(S, i)) return 0;
+  return lorentz_scalars(S, d->n_legs + 2);
+}
+
+/* reference src/MFactorized.cc:245-304 B51RandomKin (EXCITATION == 0) */
+static int b51_random_kin(ost *S, const double *r) {
+  const grb_process_desc *d  = S->d;
+  const grb_gencut *      gc = &d->gcuts;
+  const double u1 = log(gc->forward_pt_min + O_ZERO_EPS) +
+                    (log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS)) * r[0];
+  const double u2 = log(gc->forward_pt_min + O_ZERO_EPS) +
+                    (log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS)) * r[1];
+  const double pt1  = exp(u1);
+  const double pt2  = exp(u2);
+  const double phi1 = 2.0 * O_PI * r[2];
+  const double phi2 = 2.0 * O_PI * r[3];
+  const double yX   = gc->Y_min + (gc->Y_max - gc->Y_min) * r[4];
+  for (int trials = 0;; ++trials) {
+    double M_sum = 0.0;
+    for (int i = 0; i < d->n_legs; ++i) {
+      S->node_moff[i] = offshell_mass(S, i);
+      M_sum += S->node_moff[i];
+    }
+    S->M_MIN = M_sum + 1e-4;
+    S->M_MAX = d->sqrt_s - (v4_m(S->pbeam1) + v4_m(S->pbeam2));
+    S->M_MIN = fmax(S->M_MIN, gc->M_min);
+    S->M_MAX = fmin(S->M_MAX, gc->M_max);
+    if (S->M_MIN < S->M_MAX) break;
+    if (trials > 100000 || S->tape_overrun) return 0;
+  }
+  const double m2X = pow2(S->M_MIN) + (pow2(S->M_MAX) - pow2(S->M_MIN)) * r[5];
+  return b51_build_kin(S, pt1, pt2, phi1, phi2, yX, m2X, d->beam1_mass, d->beam2_mass);
+}
+
+/* reference src/MFactorized.cc:84-139 LoopKinematics */
+static int loop_kinematics(ost *S, double p1px, double p1py, double p2px, double p2py) {
+  const grb_process_desc *d = S->d;
+  S->pfinal[1].x = p1px;
+  S->pfinal[1].y = p1py;
+  S->pfinal[2].x = p2px;
+  S->pfinal[2].y = p2py;
+  const double pt1 = v4_pt(S->pfinal[1]);
+  const double pt2 = v4_pt(S->pfinal[2]);
+  const double m1  = v4_m(S->pfinal_orig[1]);
+  const double m2  = v4_m(S->pfinal_orig[2]);
+  const double mX  = v4_m(S->pfinal_orig[0]);
+  const double yX  = v4_rap(S->pfinal_orig[0]);
+  S->pfinal[0].x = -(S->pfinal[1].x + S->pfinal[2].x);
+  S->pfinal[0].y = -(S->pfinal[1].y + S->pfinal[2].y);
+  const double mtX = msqrt(pow2(mX) + v4_pt2(S->pfinal[0]));
+  S->pfinal[0].z = mtX * sinh(yX);
+  S->pfinal[0].e = mtX * cosh(yX);
+  if (S->pfinal[0].e > (d->sqrt_s - (m1 + m2))) return 0;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, S->pfinal[0].z, S->pfinal[0].e, d->s);
+  const double p2z = -(S->pfinal[0].z + p1z);
+  if (isnan(p1z)) return 0;
+  if (p1z < 0 || p2z > 0) return 0;
+  S->pfinal[1].z = p1z;
+  S->pfinal[1].e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  S->pfinal[2].z = p2z;
+  S->pfinal[2].e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  if (!check_emc(v4_sub(S->beamsum, v4_add(v4_add(S->pfinal[1], S->pfinal[2]), S->pfinal[0])))) return 0;
+  return lorentz_scalars(S, d->n_legs + 2);
+}
+
+/* ---- cuts ------------------------------------------------------------------------------------------- */
+
+/* reference src/MUserCuts.cc:21-75 (ids 0, +-3, +-111) */
+static int user_cut(const ost *S, int id) {
+  if (id == 0) return 1;
+  if (id == -3) return v4_pt(v4_sub(S->pfinal[1], S->pfinal[2])) < 0.3;
+  if (id == 3) return v4_pt(v4_sub(S->pfinal[1], S->pfinal[2])) > 0.3;
+  const double dot = S->pfinal[1].x * S->pfinal[2].x + S->pfinal[1].y * S->pfinal[2].y;
+  if (id == -111) return dot < 0;
+  if (id == 111) return dot > 0;
+  return 1;
+}
+
+/* reference src/MProcess.cc:1138-1155 FindDecayCuts */
+static void find_decay_cuts(const ost *S, int node, int *ok) {
+  const grb_node *  b = &S->d->nodes[node];
+  const grb_fidcut *f = &S->d->fcuts;
+  if (b->n_children == 0) {
+    const v4 p = S->node_p4[node];
+    if (v4_pt(p) >= f->pt_min && v4_pt(p) <= f->pt_max && v4_et(p) >= f->Et_min && v4_et(p) <= f->Et_max &&
+        v4_eta(p) >= f->eta_min && v4_eta(p) <= f->eta_max && v4_rap(p) >= f->rap_min &&
+        v4_rap(p) <= f->rap_max) {
+    } else {
+      *ok = 0;
+    }
+  }
+  for (int i = 0; i < b->n_children; ++i) find_decay_cuts(S, b->first_child + i, ok);
+}
+
+/* reference src/MProcess.cc:1085-1135 CommonCuts (no N* excitation) */
+static int common_cuts(const ost *S) {
+  const grb_fidcut *f  = &S->d->fcuts;
+  int               ok = 1;
+  if (f->active) {
+    if (!user_cut(S, f->usercuts)) return 0;
+    if (fabs(S->t1) >= f->forward_t_min && fabs(S->t1) <= f->forward_t_max && fabs(S->t2) >= f->forward_t_min &&
+        fabs(S->t2) <= f->forward_t_max) {
+    } else {
+      return 0;
+    }
+    if (msqrt(S->m2) >= f->M_min && msqrt(S->m2) <= f->M_max && S->Y >= f->Y_min && S->Y <= f->Y_max &&
+        S->Pt >= f->Pt_min && S->Pt <= f->Pt_max) {
+    } else {
+      return 0;
+    }
+    for (int i = 0; i < S->d->n_legs; ++i) find_decay_cuts(S, i, &ok);
+  }
+  return ok;
+}
+
+/* reference src/MProcess.cc:1157-1175 FindVetoCuts, :1069-1083 VetoCuts (central system only: forward
+ * legs are final protons with NSTARS=0 and decayforward{1,2} hold no fragments) */
+static void find_veto_cuts(const ost *S, int node, int *ok) {
+  const grb_node *b = &S->d->nodes[node];
+  if (b->n_children == 0) {
+    const v4 p = S->node_p4[node];
+    for (int i = 0; i < S->d->n_veto; ++i) {
+      const grb_vetodomain *v = &S->d->veto[i];
+      if (v4_pt(p) >= v->pt_min && v4_pt(p) <= v->pt_max && v4_eta(p) >= v->eta_min && v4_eta(p) <= v->eta_max)
+        *ok = 0;
+    }
+  }
+  for (int i = 0; i < b->n_children; ++i) find_veto_cuts(S, b->first_child + i, ok);
+}
+static int veto_cuts(const ost *S) {
+  int ok = 1;
+  if (S->d->veto_active)
+    for (int i = 0; i < S->d->n_legs; ++i) find_veto_cuts(S, i, &ok);
+  return ok;
+}
+
+/* ---- Regge continuum amplitude ---------------------------------------------------------------------- */
+
+/* reference src/MForm.cc:382-385 ReggeEta */
+static cx regge_eta(double alpha_t, double sigma) {
+  const double denom = sin(O_PI * alpha_t);
+  /* exp(-zi*PI*alpha_t): real part of the argument is (-0.0*PI)*alpha_t = +-0 -> exp = 1 */
+  const double y = (-1.0 * O_PI) * alpha_t;
+  const cx     e = {cos(y), sin(y)};
+  const cx     v = {1.0 + sigma * e.re, sigma * e.im};
+  return (cx){-v.re / denom, -v.im / denom};
+}
+
+/* reference src/MRegge.cc:888-906 PropOnly with MForm.cc:394-396 ReggeEtaLinear */
+static cx prop_only(const ost *S, double s, double t) {
+  const grb_param_regge *R = &S->d->regge;
+  cx                     M = {0, 0};
+  for (int k = 0; k < 3; ++k) {
+    if (R->n[k]) {
+      const double alpha = R->a0[k] + R->ap[k] * t;
+      const double y     = ((-1.0 * O_PI) / 2.0 * R->ap[k]) * t;
+      const cx     ph    = {cos(y), sin(y)};
+      const cx     eta   = cx_mul(S->regge_eta0[k], ph);
+      M = cx_add(M, cx_scale(eta, pow(s / R->s0, alpha)));
+    }
+  }
+  return M;
+}
+
+/* reference src/MForm.cc:433-435 S3F */
+static double s3f(const ost *S, double t) {
+  return (1.0 / (1 - t / S->d->soft.fc1)) * (1.0 / (1 - t / S->d->soft.fc2));
+}
+
+/* reference src/MRegge.cc:1155-1218 Meson_FF (== Baryon_FF), Meson_prop */
+static double meson_ff(const ost *S, double t_hat, double M2) {
+  const grb_param_regge *R      = &S->d->regge;
+  const double           tprime = t_hat - M2;
+  switch (R->offshellFF) {
+    case 0: return exp(-R->b_EXP * fabs(tprime));
+    case 1: return exp(-R->b_OREAR * msqrt(fabs(tprime) + pow2(R->a_OREAR)) + R->a_OREAR * R->b_OREAR);
+    default: return 1.0 / (1.0 - tprime / R->b_POW);
+  }
+}
+static double meson_prop(double t_hat, double M2) { return 1.0 / (t_hat - M2); }
+
+/* reference src/MRegge.cc:394-438 ME4 (+ :637-644 PomPomProtonVertex, elastic legs) */
+static cx regge_me4(ost *S, double sign) {
+  const grb_process_desc *d   = S->d;
+  const double            M2_ = pow2(d->nodes[0].mass);
+  const double            FF_A  = d->soft.gN_P * s3f(S, S->t1);
+  const double            FF_B  = d->soft.gN_P * s3f(S, S->t2);
+  const double            gpp_P = d->regge.c[0] / d->soft.gN_P;
+  cx A_t = prop_only(S, S->ss[1][3], S->t1);
+  A_t    = cx_scale(A_t, FF_A);
+  A_t    = cx_scale(A_t, meson_ff(S, S->t_hat, M2_));
+  A_t    = cx_scale(A_t, gpp_P);
+  A_t    = cx_scale(A_t, meson_prop(S->t_hat, M2_));
+  A_t    = cx_scale(A_t, meson_ff(S, S->t_hat, M2_));
+  A_t    = cx_scale(A_t, gpp_P);
+  A_t    = cx_mul(A_t, prop_only(S, S->ss[2][4], S->t2));
+  A_t    = cx_scale(A_t, FF_B);
+  cx A_u = cx_scale(prop_only(S, S->ss[1][4], S->t1), sign);
+  A_u    = cx_scale(A_u, FF_A);
+  A_u    = cx_scale(A_u, meson_ff(S, S->u_hat, M2_));
+  A_u    = cx_scale(A_u, gpp_P);
+  A_u    = cx_scale(A_u, meson_prop(S->u_hat, M2_));
+  A_u    = cx_scale(A_u, meson_ff(S, S->u_hat, M2_));
+  A_u    = cx_scale(A_u, gpp_P);
+  A_u    = cx_mul(A_u, prop_only(S, S->ss[2][3], S->t2));
+  A_u    = cx_scale(A_u, FF_B);
+  const cx A = cx_add(A_t, A_u);
+  S->hamp[0] = A;
+  S->nhamp   = 1;
+  return A;
+}
+
+/* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
+static double bare_amp2(ost *S) {
+  switch (S->d->proc) {
+    case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
+    case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
+    default: S->nhamp = 0; return NAN;
+  }
+}
+
+/* ---- screening -------------------------------------------------------------------------------------- */
+
+/* reference src/MEikonal.cc:489-512 IArray1D::Interpolate1D (linear grid) */
+static cx interpolate1d(const grb_oracle_eikonal *E, double a) {
+  const double MIN = E->min, MAX = E->max;
+  const double STEP = (MAX - MIN) / E->n; /* IArray1D::Set, MEikonal.h:134-138 */
+  if (a < MIN) a = MIN;
+  int i = (int)floor((a - MIN) / STEP);
+  if (i < 0) i = 0;
+  if (i >= E->n) i = E->n - 1;
+  const double dx = (a - E->x[i]);
+  const double h  = (E->x[i + 1] - E->x[i]);
+  /* F[i] + (a - x_i) * ((F[i+1] - F[i]) / (x_{i+1} - x_i)), complex/real then real*complex */
+  const cx slope = {(E->re[i + 1] - E->re[i]) / h, (E->im[i + 1] - E->im[i]) / h};
+  return (cx){E->re[i] + dx * slope.re, E->im[i] + dx * slope.im};
+}
+
+/* reference include/Graniitti/MMath.h:502-516 Simpson38Weight */
+static double simpson38_w(int i, int N) {
+  if (i == 0 || i == N) return 1.0;
+  return (i % 3 == 0) ? 2.0 : 3.0;
+}
+
+/* reference src/MProcess.cc:157-288 S3ScreenedAmp2 (non-gg initial states) */
+static double screened_amp2(ost *S) {
+  const grb_process_desc *d = S->d;
+  if (!d->screening) return bare_amp2(S);
+  bare_amp2(S);
+  if (S->nhamp == 0) return NAN;
+  const int nh = S->nhamp;
+  cx        hamp_0[GRB_MAX_HAMP];
+  memcpy(hamp_0, S->hamp, sizeof(cx) * nh);
+  const double p1T[2] = {S->pfinal[1].x, S->pfinal[1].y};
+  const double p2T[2] = {S->pfinal[2].x, S->pfinal[2].y};
+  memcpy(S->pfinal_orig, S->pfinal, sizeof(S->pfinal));
+  const int    NKT = d->loop_nkt, NPHI = d->loop_nphi;
+  const double StepKT  = (d->loop_max_kt - d->loop_min_kt) / NKT;
+  const double MinPhi  = 0.0;
+  const double MaxPhi  = 2.0 * O_PI;
+  const double StepPhi = (MaxPhi - MinPhi) / NPHI;
+  cx           I[GRB_MAX_HAMP];
+  for (int h = 0; h < nh; ++h) I[h] = (cx){0, 0};
+  /* Simpson38Integral2D (MMath.h:456-472) sums W[i][j]*f[i][j] row-major; nodes whose kinematics fail
+   * keep f = 0 and add (signed) zero, so accumulating on the fly visits the same sequence of adds */
+  for (int i = 0; i < NPHI + 1; ++i) {
+    const double phi = MinPhi + i * StepPhi;
+    for (int j = 0; j < NKT + 1; ++j) {
+      const double kt    = d->loop_min_kt + j * StepKT;
+      const double kt2   = pow2(kt);
+      const cx     A_eik = interpolate1d(S->eik, kt2);
+      const double ktx = kt * cos(phi), kty = kt * sin(phi);
+      const double Wij = simpson38_w(i, NPHI) * simpson38_w(j, NKT);
+      if (!loop_kinematics(S, p1T[0] - ktx, p1T[1] - kty, p2T[0] + ktx, p2T[1] + kty)) {
+        for (int h = 0; h < nh; ++h) { I[h].re += Wij * 0.0; I[h].im += Wij * 0.0; }
+        continue;
+      }
+      bare_amp2(S);
+      for (int h = 0; h < nh; ++h) {
+        const cx f = cx_scale(cx_mul(A_eik, S->hamp[h]), kt);
+        I[h].re += Wij * f.re; /* double * complex */
+        I[h].im += Wij * f.im;
+      }
+    }
+  }
+  const double scale = 9 * (StepPhi * StepKT) / 64;
+  /* norm = zi / (8 pi^2 s): complex / double */
+  const cx norm = {0.0 / (8.0 * (O_PI * O_PI) * d->s), 1.0 / (8.0 * (O_PI * O_PI) * d->s)};
+  cx       hamp_loop[GRB_MAX_HAMP];
+  for (int h = 0; h < nh; ++h) hamp_loop[h] = cx_mul(norm, cx_scale(I[h], scale));
+  loop_kinematics(S, p1T[0], p1T[1], p2T[0], p2T[1]);
+  double amp2 = 0.0;
+  for (int h = 0; h < nh; ++h) amp2 += cx_abs2(cx_add(hamp_0[h], hamp_loop[h]));
+  if (nh != 1) amp2 /= 4;
+  memcpy(S->hamp, hamp_0, sizeof(cx) * nh); /* for the dump: born amplitudes */
+  return amp2;
+}
+
+/* ---- weight ----------------------------------------------------------------------------------------- */
+
+/* reference src/MFactorized.cc:440-450 B51PhaseSpaceWeight */
+static double b51_ps_weight(const ost *S) {
+  const double J = 1.0 / fabs(S->pfinal[1].z / S->pfinal[1].e - S->pfinal[2].z / S->pfinal[2].e);
+  const double twopi = 2.0 * O_PI;
+  const double pow5  = twopi * ((twopi * twopi) * (twopi * twopi));
+  return (1.0 / 2.0) * (1.0 / pow5) * (v4_pt(S->pfinal[1]) / (2.0 * S->pfinal[1].e)) *
+         (v4_pt(S->pfinal[2]) / (2.0 * S->pfinal[2].e)) * J;
+}
+
+/* reference src/MFactorized.cc:432-437 B51IntegralVolume + src/MProcess.cc:1390-1400 ForwardVolume */
+static double b51_integral_volume(const ost *S) {
+  const grb_gencut *gc      = &S->d->gcuts;
+  const double      PHI_vol = pow2(2.0 * O_PI);
+  const double      J_pt    = v4_pt(S->pfinal[1]) * v4_pt(S->pfinal[2]);
+  const double      PT_vol  = J_pt * pow2(log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS));
+  const double      fv      = PHI_vol * PT_vol;
+  return (pow2(S->M_MAX) - pow2(S->M_MIN)) * (gc->Y_max - gc->Y_min) * fv;
+}
+
+/* reference src/MFactorized.cc:142-184 EventWeight */
+static double event_weight(ost *S, const double *u, uint8_t *flags) {
+  const grb_process_desc *d = S->d;
+  double                  W = 0.0;
+  const int kin  = b51_random_kin(S, u);
+  const int fid  = common_cuts(S);
+  const int veto = veto_cuts(S);
+  if (kin && fid && veto) {
+    const double MatESQ  = screened_amp2(S);
+    double       C_space = 1.0;
+    if (d->n_legs != 0 && d->ps_active) {
+      C_space = S->DW / (2 * O_PI);
+      C_space *= 1.0; /* CascadePS() == 1: no amplitude on the device path sets branch.PS_active */
+    }
+    W = C_space * (1.0 / d->S_factor) * b51_ps_weight(S) * b51_integral_volume(S) * MatESQ * O_GeV2barn /
+        (2.0 * d->s);
+  }
+  int amp = 1;
+  if (isnan(W) || isinf(W)) {
+    W   = 0;
+    amp = 0;
+  }
+  *flags = (uint8_t)((kin ? GRB_FLAG_KIN : 0) | (fid ? GRB_FLAG_FID : 0) | (veto ? GRB_FLAG_VETO : 0) |
+                     (amp ? GRB_FLAG_AMP : 0));
+  return W;
+}
+
+/* ---- public entry ----------------------------------------------------------------------------------- */
+
+int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, int64_t n, const double *u,
+                    int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
+                    int32_t *tape_used) {
+  if (!d || !u || !w || !flags) return GRB_ERR_ARG;
+  if (d->ps_class != GRB_CLASS_F || d->excitation != 0 || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
+  if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
+  if (dim < d->lipsdim) return GRB_ERR_ARG;
+  ost *S = (ost *)calloc(1, sizeof(ost));
+  S->d      = d;
+  S->eik    = eik;
+  S->pbeam1 = (v4){0, 0, d->pbeam1_pz, d->pbeam1_E};
+  S->pbeam2 = (v4){0, 0, d->pbeam2_pz, d->pbeam2_E};
+  S->beamsum = v4_add(S->pbeam1, S->pbeam2);
+  if (fabs(S->beamsum.z) > 1e-6) {
+    free(S);
+    return GRB_ERR_UNSUPPORTED;
+  }
+  for (int k = 0; k < 3; ++k) S->regge_eta0[k] = regge_eta(d->regge.a0[k], d->regge.sgn[k]);
+  int rc = GRB_OK;
+  for (int64_t k = 0; k < n; ++k) {
+    S->tape         = tape ? tape + k * dtape : NULL;
+    S->tape_len     = tape ? dtape : 0;
+    S->tape_pos     = 0;
+    S->tape_overrun = 0;
+    w[k]            = event_weight(S, u + k * dim, &flags[k]);
+    if (tape_used) tape_used[k] = S->tape_overrun ? -S->tape_pos : S->tape_pos;
+    if (dump) {
+      double *D = dump + k * GRB_DUMP_LEN;
+      D[GRB_DUMP_T1] = S->t1; D[GRB_DUMP_T2] = S->t2; D[GRB_DUMP_S1] = S->s1; D[GRB_DUMP_S2] = S->s2;
+      D[GRB_DUMP_M2] = S->m2; D[GRB_DUMP_Y] = S->Y; D[GRB_DUMP_PT] = S->Pt;
+      D[GRB_DUMP_THAT] = S->t_hat; D[GRB_DUMP_UHAT] = S->u_hat; D[GRB_DUMP_AMP2] = 0.0;
+      D[GRB_DUMP_HAMP0_RE] = S->hamp[0].re; D[GRB_DUMP_HAMP0_IM] = S->hamp[0].im;
+    }
+  }
+  free(S);
+  return rc;
+}

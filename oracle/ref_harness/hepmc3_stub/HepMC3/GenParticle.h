@@ -1,0 +1,1 @@
+#include "HepMC3/GenEvent.h"

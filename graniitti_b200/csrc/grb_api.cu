@@ -1,0 +1,530 @@
+// grb_api.cu -- the C ABI of include/grb.h: engine lifecycle, constant digestion, batched evaluation and
+// the device VEGAS iteration.  No CPU fallback: every compute entry point needs a CUDA device and returns
+// GRB_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "grb_dev.cuh"
+#include "grb_host.h"
+
+using namespace grb;
+
+struct grb_engine {
+  int              device   = 0;
+  int              sm_count = 148;
+  cudaStream_t     stream   = nullptr;
+  cudaEvent_t      ev0 = nullptr, ev1 = nullptr;
+  grb_process_desc desc;
+  DevProc          dproc;
+  DevLoop          dloop;
+  bool             have_loop = false;
+  // screening work list (one chunk)
+  int64_t       chunk      = 0;
+  double *      d_items    = nullptr;
+  int32_t *     d_item_idx = nullptr;
+  uint64_t *    d_item_bins = nullptr;
+  unsigned int *d_item_count = nullptr;
+  // VEGAS
+  grb_accum *d_acc  = nullptr;
+  double *   d_xmat = nullptr;
+  // scratch for host-pointer callers
+  void * d_scratch     = nullptr;
+  size_t scratch_bytes = 0;
+  // timing of the last call
+  bool        timed = false;
+  int         last_launches = 0;
+  std::string err;
+};
+
+static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
+static thread_local std::string g_last_global_error;
+
+#define ITEM_NF 21
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      e->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return GRB_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+static double m_of_beam(double pz, double E) {  // M4Vec::M() of (0,0,pz,E), reference M4Vec.h:123-125
+  const double m2 = E * E - (0.0 * 0.0 + 0.0 * 0.0 + pz * pz);
+  return (m2 > 0.0) ? std::sqrt(std::max(0.0, m2)) : -std::sqrt(std::max(0.0, -m2));
+}
+
+// desc -> DevProc. Host libm (glibc, the reference's) evaluates the loop invariants.
+static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
+  memset(&P, 0, sizeof(P));
+  if (d.abi_version != GRB_ABI_VERSION) { err = "abi_version mismatch"; return GRB_ERR_ARG; }
+  if (d.ps_class != GRB_CLASS_F) { err = "only the <F> phase-space class is on the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.excitation != 0) { err = "NSTARS != 0 is outside the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS) {
+    err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
+  if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
+  if (d.lipsdim != 6) { err = "lipsdim must be 6 for <F> with NSTARS=0"; return GRB_ERR_ARG; }
+  if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.n_veto > GRB_MAX_VETO) { err = "too many veto domains"; return GRB_ERR_ARG; }
+  if (d.fcuts.usercuts != 0 && std::abs(d.fcuts.usercuts) != 3 && std::abs(d.fcuts.usercuts) != 111) {
+    err = "USERCUTS id not supported on the device path";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  P.proc = d.proc; P.screening = d.screening; P.n_nodes = d.n_nodes; P.n_legs = d.n_legs; P.lipsdim = d.lipsdim;
+  P.fid_active = d.fcuts.active; P.usercuts = d.fcuts.usercuts; P.veto_active = d.veto_active; P.n_veto = d.n_veto;
+  P.ps_active = d.ps_active;
+  P.s = d.s; P.sqrt_s = d.sqrt_s; P.s_pow15 = std::pow(d.s, 3.0 / 2.0);
+  P.pb1z = d.pbeam1_pz; P.pb1e = d.pbeam1_E; P.pb2z = d.pbeam2_pz; P.pb2e = d.pbeam2_E;
+  P.bsum_z = d.pbeam1_pz + d.pbeam2_pz; P.bsum_e = d.pbeam1_E + d.pbeam2_E;
+  P.mb1 = d.beam1_mass; P.mb2 = d.beam2_mass;
+  P.M_MAX0 = d.sqrt_s - (m_of_beam(d.pbeam1_pz, d.pbeam1_E) + m_of_beam(d.pbeam2_pz, d.pbeam2_E));
+  P.log_pt0 = std::log(d.gcuts.forward_pt_min + 1e-12);
+  P.dlog_pt = std::log(d.gcuts.forward_pt_max) - std::log(d.gcuts.forward_pt_min + 1e-12);
+  P.Y_min = d.gcuts.Y_min; P.dY = d.gcuts.Y_max - d.gcuts.Y_min;
+  P.gM_min = d.gcuts.M_min; P.gM_max = d.gcuts.M_max;
+  P.offshell = d.offshell;
+  const grb_fidcut &f = d.fcuts;
+  P.f_eta_min = f.eta_min; P.f_eta_max = f.eta_max; P.f_rap_min = f.rap_min; P.f_rap_max = f.rap_max;
+  P.f_pt_min = f.pt_min; P.f_pt_max = f.pt_max; P.f_Et_min = f.Et_min; P.f_Et_max = f.Et_max;
+  P.f_M_min = f.M_min; P.f_M_max = f.M_max; P.f_Y_min = f.Y_min; P.f_Y_max = f.Y_max;
+  P.f_Pt_min = f.Pt_min; P.f_Pt_max = f.Pt_max; P.f_t_min = f.forward_t_min; P.f_t_max = f.forward_t_max;
+  for (int i = 0; i < d.n_veto; ++i) P.veto[i] = d.veto[i];
+  // weight constant, reference MFactorized.cc:173-174,432-450, MProcess.cc:1390-1400, MPDG.h:64-78
+  const double PI       = GRB_PI;
+  const double GeV2barn = ((6.582119514E-25 * 2.99792458E8) * (6.582119514E-25 * 2.99792458E8)) / 1E-28;
+  const double twopi    = 2.0 * PI;
+  P.w_const = (1.0 / d.S_factor) * GeV2barn / (2.0 * d.s) * (twopi * twopi) * (P.dlog_pt * P.dlog_pt) * P.dY *
+              0.5 / (twopi * twopi * twopi * twopi * twopi) * 0.25;
+  // Regge
+  const grb_param_regge &R = d.regge;
+  for (int k = 0; k < 3; ++k) {
+    P.a0[k] = R.a0[k]; P.ap[k] = R.ap[k]; P.regge_n[k] = R.n[k];
+    // ReggeEta(a0, sgn), reference src/MForm.cc:382-385
+    const double denom = std::sin(PI * R.a0[k]);
+    const double y     = (-1.0 * PI) * R.a0[k];
+    const double vr = 1.0 + R.sgn[k] * std::cos(y), vi = R.sgn[k] * std::sin(y);
+    P.eta0_re[k] = -vr / denom; P.eta0_im[k] = -vi / denom;
+    P.phase_c[k] = ((-1.0 * PI) / 2.0 * R.ap[k]);
+  }
+  P.ln_inv_s0 = -std::log(R.s0);
+  P.offshellFF = R.offshellFF;
+  P.gN_P = d.soft.gN_P; P.fc1 = d.soft.fc1; P.fc2 = d.soft.fc2;
+  P.gpp_P = R.c[0] / d.soft.gN_P;
+  P.M2_leg0 = d.nodes[0].mass * d.nodes[0].mass;
+  P.b_EXP = R.b_EXP; P.a_OREAR = R.a_OREAR; P.b_OREAR = R.b_OREAR; P.b_POW = R.b_POW;
+  P.me4_sign = (d.proc == GRB_PROC_PP_CON_MINUS) ? -1.0 : 1.0;
+  // nodes
+  for (int i = 0; i < d.n_nodes; ++i) {
+    const grb_node &n = d.nodes[i];
+    DevNode &       o = P.nodes[i];
+    if (n.n_children != 0 && n.n_children != 2) { err = "only two-body decays are on the device path"; return GRB_ERR_UNSUPPORTED; }
+    if (n.n_children && (n.first_child <= i || n.first_child + 1 >= d.n_nodes)) { err = "bad decay tree indices"; return GRB_ERR_ARG; }
+    o.mass = n.mass; o.width = n.width; o.first_child = n.first_child; o.n_children = n.n_children;
+    o.bw_active = !(n.width < 1e-40);
+    o.m2 = n.mass * n.mass; o.m0G = n.mass * n.width;
+    const double hi = n.mass + d.offshell * n.width, lo = n.mass - d.offshell * n.width;
+    o.m2max = hi * hi; o.m2lo = lo * lo;
+    // RelativisticBWRandom constants for M_MIN = 0, reference src/MRandom.cc:82-107
+    const double m2min = std::max(std::max(0.0, 0.0), o.m2lo);
+    o.bwA0  = std::atan2(m2min - o.m2, o.m0G);
+    o.bwBA0 = std::atan2(o.m2max - o.m2, o.m0G) - std::atan2(m2min - o.m2, o.m0G);
+  }
+  // depth-first decay order (reference MProcess::ConstructDecayKinematics recursion, MProcess.cc:1231-1284)
+  P.n_decays = 0;
+  std::vector<int> stack;
+  for (int i = d.n_legs - 1; i >= 0; --i) stack.push_back(i);
+  while (!stack.empty()) {
+    const int n = stack.back();
+    stack.pop_back();
+    if (d.nodes[n].n_children) {
+      P.decay_order[P.n_decays++] = n;
+      for (int c = d.nodes[n].n_children - 1; c >= 0; --c) stack.push_back(d.nodes[n].first_child + c);
+    }
+  }
+  return GRB_OK;
+}
+
+static int ensure_constants(grb_engine *e) {
+  if (g_const_owner != e) {
+    CK(upload_proc(e->dproc, e->stream));
+    if (e->have_loop) CK(upload_loop(e->dloop, e->stream));
+    g_const_owner = e;
+  }
+  return GRB_OK;
+}
+
+extern "C" {
+
+int grb_abi_sizeof(int what) {
+  switch (what) {
+    case 0: return (int)sizeof(grb_process_desc);
+    case 1: return (int)sizeof(grb_accum);
+    case 2: return (int)sizeof(grb_resonance);
+    case 3: return (int)sizeof(grb_node);
+    default: return -1;
+  }
+}
+
+int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
+  if (!desc || !out) return GRB_ERR_ARG;
+  *out          = nullptr;
+  grb_engine *e = new grb_engine();
+  e->desc       = *desc;
+  e->device     = device;
+  int rc        = digest(*desc, e->dproc, e->err);
+  if (rc != GRB_OK) {
+    g_last_global_error = e->err;
+    delete e;
+    return rc;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
+    g_last_global_error = "no CUDA device " + std::to_string(device) + " (the engine has no CPU fallback)";
+    delete e;
+    return GRB_ERR_CUDA;
+  }
+  auto fail = [&](const char *what, cudaError_t ce) {
+    g_last_global_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    grb_destroy(e);
+    return GRB_ERR_CUDA;
+  };
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", ce);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", ce);
+  e->sm_count = prop.multiProcessorCount;
+  if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", ce);
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+  const char *env = getenv("GRB_CHUNK");
+  e->chunk        = env ? std::max<int64_t>(1024, atoll(env)) : (int64_t)1 << 21;
+  if (desc->screening) {
+    if ((ce = cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk)) != cudaSuccess) return fail("cudaMalloc items", ce);
+    if ((ce = cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
+    if ((ce = cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
+  }
+  if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 4)) != cudaSuccess) return fail("cudaMalloc", ce);
+  if ((ce = cudaMalloc(&e->d_acc, sizeof(grb_accum))) != cudaSuccess) return fail("cudaMalloc", ce);
+  if ((ce = cudaMalloc(&e->d_xmat, sizeof(double) * GRB_MAX_BINS * GRB_MAX_DIM)) != cudaSuccess) return fail("cudaMalloc", ce);
+  cudaMemsetAsync(e->d_acc, 0, sizeof(grb_accum), e->stream);
+  cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int) * 4, e->stream);
+  *out = e;
+  return GRB_OK;
+}
+
+int grb_create_from_card(const char *card_path, const char *process_override, int pomloop_override,
+                         const char *graniitti_base, int device, grb_engine **out) {
+  if (!out) return GRB_ERR_ARG;
+  grb_process_desc d;
+  char             buf[1024];
+  int rc = grb_parse_card(card_path, process_override, pomloop_override, graniitti_base, &d, buf, sizeof(buf));
+  if (rc != GRB_OK) {
+    g_last_global_error = buf;
+    return rc;
+  }
+  return grb_create(&d, device, out);
+}
+
+int grb_get_desc(const grb_engine *e, grb_process_desc *out) {
+  if (!e || !out) return GRB_ERR_ARG;
+  *out = e->desc;
+  return GRB_OK;
+}
+
+const char *grb_last_error(const grb_engine *e) { return e ? e->err.c_str() : g_last_global_error.c_str(); }
+
+void grb_destroy(grb_engine *e) {
+  if (!e) return;
+  if (g_const_owner == e) g_const_owner = nullptr;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_count);
+  cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+// Loop discretisation + A_eik(kt_j^2): everything S3ScreenedAmp2 needs that depends on (i,j) only
+// (reference src/MProcess.cc:187-231, src/MEikonal.cc:489-512, include/Graniitti/MMath.h:502-516).
+int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const double *im, int n_points) {
+  if (!e || !kt2 || !re || !im || n_points < 3) return GRB_ERR_ARG;
+  const grb_process_desc &d = e->desc;
+  const int NKT = d.loop_nkt, NPHI = d.loop_nphi;
+  if (NKT < 3 || NPHI < 3 || NKT % 3 || NPHI % 3 || NKT + 1 > GRB_MAX_LOOP_KT || NPHI + 1 > GRB_MAX_LOOP_PHI) {
+    e->err = "loop discretisation must be multiples of 3 within the compiled bounds";
+    return GRB_ERR_ARG;
+  }
+  DevLoop &Q = e->dloop;
+  memset(&Q, 0, sizeof(Q));
+  Q.nkt = NKT; Q.nphi = NPHI;
+  const int    N    = n_points - 1;
+  const double MIN = 1e-6, MAX = 25.0;  // MEikonalNumerics::MinKT2/MaxKT2, MEikonal.h:27-28
+  const double STEP = (MAX - MIN) / N;
+  const double StepKT  = (d.loop_max_kt - d.loop_min_kt) / NKT;
+  const double StepPhi = (2.0 * GRB_PI - 0.0) / NPHI;
+  auto w38 = [](int i, int n) { return (i == 0 || i == n) ? 1.0 : ((i % 3 == 0) ? 2.0 : 3.0); };
+  for (int j = 0; j <= NKT; ++j) {
+    const double kt = d.loop_min_kt + j * StepKT;
+    double       a  = kt * kt;
+    if (a < MIN) a = MIN;
+    if (a > MAX * (1 + 1e-5)) { e->err = "loop kt^2 outside the eikonal table"; return GRB_ERR_ARG; }
+    int i = (int)std::floor((a - MIN) / STEP);
+    if (i < 0) i = 0;
+    if (i >= N) i = N - 1;
+    const double dx = a - kt2[i], h = kt2[i + 1] - kt2[i];
+    Q.kt[j]      = kt;
+    Q.aeik_re[j] = re[i] + dx * ((re[i + 1] - re[i]) / h);
+    Q.aeik_im[j] = im[i] + dx * ((im[i + 1] - im[i]) / h);
+    Q.wkt[j]     = w38(j, NKT);
+  }
+  for (int i = 0; i <= NPHI; ++i) {
+    const double phi = 0.0 + i * StepPhi;
+    Q.cphi[i] = std::cos(phi);
+    Q.sphi[i] = std::sin(phi);
+    Q.wphi[i] = w38(i, NPHI);
+  }
+  Q.norm = (9 * (StepPhi * StepKT) / 64) * (1.0 / (8.0 * (GRB_PI * GRB_PI) * d.s));
+  e->have_loop = true;
+  if (g_const_owner == e) g_const_owner = nullptr;  // force re-upload
+  return GRB_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
+             uint8_t *flags, double *dump) {
+  if (!e || n < 0 || !u || !w || !flags || dim < e->desc.lipsdim || dtape < 0 || (dtape > 0 && !tape)) return GRB_ERR_ARG;
+  if (e->desc.screening && !e->have_loop) { e->err = "screening is on but no eikonal table was set"; return GRB_ERR_STATE; }
+  if (n == 0) return GRB_OK;
+  CK(cudaSetDevice(e->device));
+  const bool dev_in = is_device_ptr(u), dev_out = is_device_ptr(w);
+  if ((tape && is_device_ptr(tape) != dev_in) || is_device_ptr(flags) != dev_out || (dump && is_device_ptr(dump) != dev_out)) {
+    e->err = "inputs (u,tape) must live on the same side, and outputs (w,flags,dump) likewise";
+    return GRB_ERR_ARG;
+  }
+  // stage host buffers
+  const size_t b_u = sizeof(double) * dim * n, b_t = sizeof(double) * (size_t)dtape * n, b_w = sizeof(double) * n;
+  const size_t b_f = (size_t)((n + 7) / 8 * 8), b_d = dump ? sizeof(double) * GRB_DUMP_LEN * n : 0;
+  size_t       need = 0;
+  if (!dev_in) need += b_u + b_t;
+  if (!dev_out) need += b_w + b_f + b_d;
+  if (need > e->scratch_bytes) {
+    cudaFree(e->d_scratch);
+    e->d_scratch = nullptr;
+    e->scratch_bytes = 0;
+    CK(cudaMalloc(&e->d_scratch, need));
+    e->scratch_bytes = need;
+  }
+  char *        sp = (char *)e->d_scratch;
+  const double *du = u, *dt = tape;
+  double *      dw = w, *dd = dump;
+  uint8_t *     df = flags;
+  if (!dev_in) {
+    du = (double *)sp; sp += b_u;
+    dt = dtape ? (double *)sp : nullptr; sp += b_t;
+    CK(cudaMemcpyAsync((void *)du, u, b_u, cudaMemcpyHostToDevice, e->stream));
+    if (dtape) CK(cudaMemcpyAsync((void *)dt, tape, b_t, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (!dev_out) {
+    dw = (double *)sp; sp += b_w;
+    df = (uint8_t *)sp; sp += b_f;
+    dd = dump ? (double *)sp : nullptr;
+  }
+  int rc = ensure_constants(e);
+  if (rc != GRB_OK) return rc;
+  e->last_launches = 0;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (int64_t off = 0; off < n; off += e->chunk) {
+    PointArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = std::min<int64_t>(e->chunk, n - off);
+    a.u = du + off; a.tape = dt ? dt + off : nullptr; a.ld = n; a.dim = dim; a.dtape = dtape;
+    a.vegas = 0; a.bins = 0;
+    a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
+    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
+    a.item_cap = e->chunk; a.acc = e->d_acc;
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
+    e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
+    if (e->desc.screening) e->last_launches += launch_screen(a, e->sm_count, e->stream);
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->timed = true;
+  CK(cudaGetLastError());
+  if (!dev_out) {
+    CK(cudaMemcpyAsync(w, dw, b_w, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(flags, df, n, cudaMemcpyDeviceToHost, e->stream));
+    if (dump) CK(cudaMemcpyAsync(dump, dd, b_d, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return GRB_OK;
+}
+
+int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim, int64_t first_call,
+                            int64_t ncalls, uint64_t seed, uint64_t iteration, int mode, double maxf,
+                            void **accum_device_ptr) {
+  if (!e || !xmat || bins < 2 || bins > GRB_MAX_BINS || dim != e->desc.lipsdim || ncalls < 0) return GRB_ERR_ARG;
+  if (e->desc.screening && !e->have_loop) { e->err = "screening is on but no eikonal table was set"; return GRB_ERR_STATE; }
+  if (mode == GRB_MODE_GENERATE) { e->err = "event generation mode is not implemented yet"; return GRB_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(e->device));
+  int rc = ensure_constants(e);
+  if (rc != GRB_OK) return rc;
+  CK(cudaMemcpyAsync(e->d_xmat, xmat, sizeof(double) * bins * dim, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(e->d_acc, 0, sizeof(grb_accum), e->stream));
+  e->last_launches = 0;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  for (int64_t off = 0; off < ncalls; off += e->chunk) {
+    PointArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = std::min<int64_t>(e->chunk, ncalls - off);
+    a.ld = a.n; a.dim = dim;
+    a.vegas = 1; a.bins = bins; a.mode = mode; a.xmat = e->d_xmat; a.seed = seed; a.iter = (uint32_t)iteration;
+    a.first_call = first_call + off; a.maxf = maxf;
+    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
+    a.item_cap = e->chunk; a.acc = e->d_acc;
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
+    e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
+    if (e->desc.screening) e->last_launches += launch_screen(a, e->sm_count, e->stream);
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->timed = true;
+  CK(cudaGetLastError());
+  if (accum_device_ptr) *accum_device_ptr = e->d_acc;
+  return GRB_OK;
+}
+
+int grb_vegas_fetch(grb_engine *e, grb_accum *out) {
+  if (!e || !out) return GRB_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(out, e->d_acc, sizeof(grb_accum), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  // points that are not Valid() keep amplitude_ok = true in the reference (AuxIntData default)
+  out->n_amp_ok = out->evaluations - out->n_nan_inf;
+  return GRB_OK;
+}
+
+int grb_vegas_iterate(grb_engine *e, const double *xmat, int bins, int dim, int64_t first_call, int64_t ncalls,
+                      uint64_t seed, uint64_t iteration, int mode, double maxf, grb_accum *out) {
+  int rc = grb_vegas_iterate_async(e, xmat, bins, dim, first_call, ncalls, seed, iteration, mode, maxf, nullptr);
+  if (rc != GRB_OK) return rc;
+  return grb_vegas_fetch(e, out);
+}
+
+int grb_sync(grb_engine *e) {
+  if (!e) return GRB_ERR_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return GRB_OK;
+}
+
+// VEGAS grid refinement (Lepage 1978; the damped-redistribution scheme of reference
+// include/Graniitti/MVEGAS.h:87-142): 3-point smoothing of the per-bin <f^2>, importance
+// r_i = ((1 - d_i/D) / (ln D - ln d_i))^lambda, then bin edges are moved so every new bin holds sum(r)/bins.
+int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim, double lambda) {
+  if (!xmat || !f2mat || bins < 3 || bins > GRB_MAX_BINS || dim < 1 || dim > GRB_MAX_DIM) return GRB_ERR_ARG;
+  const double        EPS = 1.0e-30;
+  std::vector<double> d(bins), r(bins), xnew(bins);
+  for (int j = 0; j < dim; ++j) {
+    auto F = [&](int i) { return f2mat[i * GRB_MAX_DIM + j]; };
+    // smoothing
+    double total = 0.0;
+    double zo = F(0), zn = F(1);
+    d[0]  = (zo + zn) / 2.0;
+    total = d[0];
+    for (int i = 2; i < bins; ++i) {
+      const double ac = zo + zn;
+      zo = zn;
+      zn = F(i);
+      d[i - 1] = (ac + zn) / 3.0;
+      total += d[i - 1];
+    }
+    d[bins - 1] = (zo + zn) / 2.0;
+    total += d[bins - 1];
+    // importance
+    double rsum = 0.0;
+    for (int i = 0; i < bins; ++i) {
+      if (d[i] < EPS) d[i] = EPS;
+      r[i] = std::pow((1.0 - d[i] / total) / (std::log(total) - std::log(d[i]) + EPS), lambda);
+      if (std::isnan(r[i]) || std::isinf(r[i])) r[i] = EPS;
+      rsum += r[i];
+    }
+    // rebin
+    const double per = rsum / bins;
+    int          k  = 0;
+    double       dr = 0.0, xo = 0.0, xn = 0.0;
+    for (int i = 0; i < bins - 1; ++i) {
+      while (per > dr) dr += r[(++k) - 1];
+      if (k > 1) xo = xmat[(k - 2) * dim + j];
+      xn = xmat[(k - 1) * dim + j];
+      dr -= per;
+      xnew[i] = xn - (xn - xo) * dr / r[k - 1];
+    }
+    for (int i = 0; i < bins - 1; ++i) xmat[i * dim + j] = xnew[i];
+    xmat[(bins - 1) * dim + j] = 1.0;
+  }
+  return GRB_OK;
+}
+
+int64_t grb_get_events(grb_engine *e, int64_t, double *, double *, int *) {
+  if (e) e->err = "event generation mode is not implemented yet";
+  return GRB_ERR_UNSUPPORTED;
+}
+
+int grb_build_eikonal(grb_engine *e, int, int, double *, double *, double *, double *) {
+  if (e) e->err = "device eikonal table builder is not implemented yet";
+  return GRB_ERR_UNSUPPORTED;
+}
+
+int grb_comm_unique_id(char *) { return GRB_ERR_UNSUPPORTED; }
+int grb_comm_init(grb_engine *, int, int, const char *) { return GRB_ERR_UNSUPPORTED; }
+int grb_allreduce(grb_engine *) { return GRB_ERR_UNSUPPORTED; }
+
+int grb_measure_dfma_peak(int device, double *tflops_out) {
+  if (!tflops_out) return GRB_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) return GRB_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return GRB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GRB_ERR_CUDA;
+  return run_dfma_peak(prop.multiProcessorCount, tflops_out) == cudaSuccess ? GRB_OK : GRB_ERR_CUDA;
+}
+
+int grb_last_timing(const grb_engine *e, double *kernel_ms, int *n_launches) {
+  if (!e) return GRB_ERR_ARG;
+  if (kernel_ms) {
+    *kernel_ms = 0.0;
+    if (e->timed) {
+      cudaSetDevice(e->device);
+      if (cudaEventSynchronize(e->ev1) == cudaSuccess) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) *kernel_ms = ms;
+      }
+    }
+  }
+  if (n_launches) *n_launches = e->last_launches;
+  return GRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// grb_dev.cuh -- device-side building blocks of the event-weight path (sm_100a, fp64 CUDA cores).
+//
+// This translation unit is compiled with -fmad=false: every a*b+c written below is a separately rounded
+// multiply and add, exactly like the reference build (g++ -O3 without -march=native emits no FMA on
+// x86-64, reference Makefile:195-205,232-239).  That matters for the cancellation-prone kinematics
+// (t1 = (p_beam - p1)^2 formed from O(6500 GeV) components).  Where contraction is
+// harmless and pays (amplitude algebra inside the screening loop) fma() is written explicitly.
+//
+// Nothing here is a translation of reference classes: momenta live in registers as plain doubles, the
+// process is a POD in constant memory, decay trees are flattened, and every loop invariant of the
+// screening integral is hoisted to table-set time.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/grb.h"
+
+namespace grb {
+
+// reference include/Graniitti/MMath.h:30
+#define GRB_PI 3.141592653589793238462643383279502884197169399375105820974944
+
+struct v4 {
+  double x, y, z, e;
+};
+struct cx {
+  double re, im;
+};
+
+// ---- flattened, pre-digested process constants (constant memory) -------------------------------------
+struct DevNode {
+  double mass, width;
+  double m2, m0G;        // m0^2, m0*Gamma
+  double m2max, m2lo;    // (m0 + L*G)^2, (m0 - L*G)^2
+  double bwA0, bwBA0;    // atan2(m2min - m2, m0G) and (atan2(m2max - m2, m0G) - that) for M_MIN = 0
+  int    first_child, n_children, bw_active, pad_;
+};
+
+struct DevProc {
+  // process selection
+  int proc, screening, n_nodes, n_legs, n_decays, lipsdim, fid_active, usercuts, veto_active, n_veto;
+  int ps_active, offshellFF, regge_n[3], pad_;
+  int decay_order[GRB_MAX_NODES];  // nodes with daughters in the reference's depth-first order
+  // beams
+  double s, sqrt_s, s_pow15;       // s^(3/2) as the reference's std::pow(s, 3.0/2.0)
+  double pb1z, pb1e, pb2z, pb2e, bsum_z, bsum_e;
+  double mb1, mb2;                 // PDG beam masses (SampleForwardMasses, MProcess.cc:1318)
+  double M_MAX0;                   // sqrt_s - (pbeam1.M() + pbeam2.M()), MFactorized.cc:277
+  // sampling map (MFactorized.cc:245-258)
+  double log_pt0, dlog_pt, Y_min, dY, gM_min, gM_max;
+  double offshell;
+  // cuts
+  double f_eta_min, f_eta_max, f_rap_min, f_rap_max, f_pt_min, f_pt_max, f_Et_min, f_Et_max;
+  double f_M_min, f_M_max, f_Y_min, f_Y_max, f_Pt_min, f_Pt_max, f_t_min, f_t_max;
+  grb_vetodomain veto[GRB_MAX_VETO];
+  // weight: (1/S) * GeV2barn / (2 s) * (2pi)^2 * dlog_pt^2 * (Ymax-Ymin) * 1/2 * (2pi)^-5 * 1/4
+  double w_const;
+  // Regge continuum (MRegge.cc:394-438, 888-906; MForm.cc:382-396,433-435)
+  double a0[3], ap[3], ln_inv_s0, eta0_re[3], eta0_im[3], phase_c[3];  // phase_c = -pi/2 * ap
+  double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
+  DevNode nodes[GRB_MAX_NODES];
+};
+
+// screening loop discretisation + per-node eikonal amplitude (constant memory)
+struct DevLoop {
+  int    nkt, nphi;                       // intervals: nodes are nkt+1, nphi+1
+  double kt[GRB_MAX_LOOP_KT];             // kt_j = MinLoopKT + j*StepKT
+  double aeik_re[GRB_MAX_LOOP_KT];        // A_eik(kt_j^2), Interpolate1D done at table-set time
+  double aeik_im[GRB_MAX_LOOP_KT];
+  double wkt[GRB_MAX_LOOP_KT];            // Simpson 3/8 weights
+  double cphi[GRB_MAX_LOOP_PHI], sphi[GRB_MAX_LOOP_PHI], wphi[GRB_MAX_LOOP_PHI];
+  double norm;                            // 9*StepPhi*StepKT/64 / (8 pi^2 s); hamp_loop = i*norm*sum
+};
+
+// arguments of one k_points / k_screen launch (one chunk of points)
+struct PointArgs {
+  int64_t n;
+  // parity-mode inputs: SoA u[dim][ld], tape[dtape][ld], pointers pre-offset to this chunk's first point
+  const double *u, *tape;
+  int64_t       ld;
+  int           dim, dtape;
+  // VEGAS-mode inputs
+  int           vegas, bins, mode;
+  const double *xmat;  // [bins][dim] device
+  uint64_t      seed;
+  uint32_t      iter;
+  int64_t       first_call;
+  double        maxf;
+  // per-point outputs (parity mode; nullable)
+  double * w;
+  uint8_t *flags;
+  double * dump;
+  // screening work list
+  double *      items;
+  int32_t *     item_idx;
+  uint64_t *    item_bins;
+  unsigned int *item_count;
+  int64_t       item_cap;
+  // accumulators (device)
+  grb_accum *acc;
+};
+
+// launchers implemented in grb_kernels.cu
+cudaError_t upload_proc(const DevProc &p, cudaStream_t st);
+cudaError_t upload_loop(const DevLoop &l, cudaStream_t st);
+int         launch_points(const PointArgs &a, int n_nodes, int sm_count, cudaStream_t st);
+int         launch_screen(const PointArgs &a, int sm_count, cudaStream_t st);
+cudaError_t run_dfma_peak(int sm_count, double *tflops);
+
+// ---- small math ----------------------------------------------------------------------------------------
+__device__ __forceinline__ double msqrt(double x) { return sqrt(fmax(0.0, x)); }  // MMath.h:250
+__device__ __forceinline__ double pow2(double x) { return x * x; }
+__device__ __forceinline__ double m2_of(double x, double y, double z, double e) {   // M4Vec.h:123,139
+  return e * e - (x * x + y * y + z * z);
+}
+__device__ __forceinline__ double m2_of(const v4 &a) { return m2_of(a.x, a.y, a.z, a.e); }
+__device__ __forceinline__ double m_of(const v4 &a) {  // M4Vec.h:125
+  const double m2 = m2_of(a);
+  return (m2 > 0.0) ? msqrt(m2) : -msqrt(-m2);
+}
+__device__ __forceinline__ double pt2_of(const v4 &a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ double rap_of(const v4 &a) { return 0.5 * log((a.e + a.z) / (a.e - a.z)); }
+
+// reference include/Graniitti/MKinematics.h:33-64 SolvePz3_A: the t22 chain is kept in the reference's
+// association (it carries the rounding that decides the last bits of p1z); constants in s are hoisted.
+struct PzConst {
+  double s, t7, t9, t14;  // s, sqrt(s), s^(3/2), s^2
+};
+__device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4, double pz5, double E5,
+                                              const PzConst &c) {
+  const double s   = c.s;
+  const double t2  = E5 * E5;
+  const double t3  = pt3 * pt3;
+  const double t4  = pt4 * pt4;
+  const double t5  = pz5 * pz5;
+  const double t6  = m3 * m3;
+  const double t7  = c.t7;
+  const double t8  = s * t2 * 6.0;
+  const double t9  = c.t9;
+  const double t10 = t2 * t2;
+  const double t11 = t3 * t3;
+  const double t12 = t4 * t4;
+  const double t13 = t5 * t5;
+  const double t14 = c.t14;
+  const double t15 = t5 * t6 * 4.0;
+  const double t16 = t3 * t5 * 2.0;
+  const double t17 = t4 * t5 * 2.0;
+  const double t18 = E5 * t6 * t7 * 8.0;
+  const double t19 = E5 * t3 * t7 * 4.0;
+  const double t20 = E5 * t4 * t7 * 4.0;
+  const double t21 = E5 * t5 * t7 * 4.0;
+  const double t22 = t8 + t10 + t11 + t12 + t13 + t14 + t15 + t16 + t17 + t18 + t19 + t20 + t21 -
+                     E5 * t9 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 - s * t5 * 2.0 - s * t6 * 4.0 -
+                     t2 * t3 * 2.0 - t2 * t4 * 2.0 - t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 4.0 -
+                     E5 * t2 * t7 * 4.0;
+  const double t23 = sqrt(t22);
+  return pz5 * (-1.0 / 2.0) -
+         (E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0))) /
+             (s + t2 - t5 - E5 * t7 * 2.0);
+}
+
+// reference MKinematics.h:117-160 SolvePz3_B (unequal forward masses)
+static __device__ __noinline__ double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5,
+                                           double E5, const PzConst &c) {
+  const double s   = c.s;
+  const double t2  = E5 * E5;
+  const double t3  = m3 * m3;
+  const double t4  = m4 * m4;
+  const double t5  = pt3 * pt3;
+  const double t6  = pt4 * pt4;
+  const double t7  = pz5 * pz5;
+  const double t8  = c.t7;
+  const double t9  = s * t2 * 6.0;
+  const double t10 = c.t9;
+  const double t11 = t2 * t2;
+  const double t12 = t3 * t3;
+  const double t13 = t4 * t4;
+  const double t14 = t5 * t5;
+  const double t15 = t6 * t6;
+  const double t16 = t7 * t7;
+  const double t17 = c.t14;
+  const double t18 = t3 * t5 * 2.0;
+  const double t19 = t4 * t6 * 2.0;
+  const double t20 = t3 * t7 * 2.0;
+  const double t21 = t4 * t7 * 2.0;
+  const double t22 = t5 * t7 * 2.0;
+  const double t23 = t6 * t7 * 2.0;
+  const double t24 = E5 * t3 * t8 * 4.0;
+  const double t25 = E5 * t4 * t8 * 4.0;
+  const double t26 = E5 * t5 * t8 * 4.0;
+  const double t27 = E5 * t6 * t8 * 4.0;
+  const double t28 = E5 * t7 * t8 * 4.0;
+  const double t29 = t9 + t11 + t12 + t13 + t14 + t15 + t16 + t17 + t18 + t19 + t20 + t21 + t22 + t23 +
+                     t24 + t25 + t26 + t27 + t28 - E5 * t10 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 -
+                     s * t5 * 2.0 - s * t6 * 2.0 - s * t7 * 2.0 - t2 * t3 * 2.0 - t2 * t4 * 2.0 -
+                     t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 2.0 - t2 * t7 * 2.0 - t3 * t6 * 2.0 -
+                     t4 * t5 * 2.0 - t5 * t6 * 2.0 - E5 * t2 * t8 * 4.0;
+  const double t30 = sqrt(t29);
+  return pz5 * (-1.0 / 2.0) -
+         (E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
+          pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0))) /
+             (s + t2 - t7 - E5 * t8 * 2.0);
+}
+
+__device__ __forceinline__ double solve_pz(double m3, double m4, double pt3, double pt4, double pz5,
+                                           double E5, const PzConst &c) {  // MKinematics.h:220-229
+  if (fabs(m3 - m4) < 1e-9) return solve_pz3_A(m3, pt3, pt4, pz5, E5, c);
+  return solve_pz3_B(m3, m4, pt3, pt4, pz5, E5, c);
+}
+
+// reference MKinematics.h:383-401 LorentzBoost (sign = +1); libstdc++'s (beta*p3).sum() adds from the
+// last element, kept so that daughters match the reference to the last bit on equal inputs.
+__device__ __forceinline__ v4 boost_from_rest(const v4 &mother, double M0, const v4 &p) {
+  const double b0 = mother.x / mother.e, b1 = mother.y / mother.e, b2 = mother.z / mother.e;
+  const double gamma  = mother.e / M0;
+  const double kappa1 = (b2 * p.z + b1 * p.y) + b0 * p.x;
+  const double kappa2 = gamma * (gamma * kappa1 / (1.0 + gamma) + p.e);
+  v4           r;
+  r.x = p.x + kappa2 * b0;
+  r.y = p.y + kappa2 * b1;
+  r.z = p.z + kappa2 * b2;
+  r.e = gamma * (p.e + kappa1);
+  return r;
+}
+
+// reference MKinematics.h:294-298 DecayMomentum
+__device__ __forceinline__ double decay_momentum(double x, double y, double z) {
+  return msqrt((x - y - z) * (x + y + z) * (x + y - z) * (x - y + z)) / (2.0 * x);
+}
+
+// reference MKinematics.h:403-459: FlatIsotropic + Isotropic + boost; returns dPhi2 (:267-271)
+__device__ __forceinline__ double two_body(const v4 &mother, double M0, double m1, double m2, double r_cos,
+                                           double r_phi, v4 &p1, v4 &p2) {
+  const double pnorm    = decay_momentum(M0, m1, m2);
+  const double costheta = -1.0 + (1.0 - -1.0) * r_cos;          // MRandom::U(-1,1), MRandom.cc:62-65
+  const double sintheta = msqrt(1.0 - pow2(costheta));
+  const double phi      = 0.0 + (2.0 * GRB_PI - 0.0) * r_phi;   // MRandom::U(0,2pi)
+  double       sp, cp;
+  sincos(phi, &sp, &cp);
+  v4 k;
+  k.x = pnorm * sintheta * cp;
+  k.y = pnorm * sintheta * sp;
+  k.z = pnorm * costheta;
+  k.e = msqrt(pow2(m1) + pow2(pnorm));
+  p1  = boost_from_rest(mother, M0, k);
+  k.x = -k.x;
+  k.y = -k.y;
+  k.z = -k.z;
+  k.e = msqrt(pow2(m2) + pow2(pnorm));
+  p2  = boost_from_rest(mother, M0, k);
+  const double V = 2.0 * 2.0 * GRB_PI;
+  return V * pnorm / (16.0 * pow2(GRB_PI) * M0);
+}
+
+}  // namespace grb

@@ -1,0 +1,365 @@
+// grb_kernels.cu -- the two hot kernels of the event-weight path and their launchers.
+//
+//   k_points : one thread per phase-space point. Draws (caller-supplied SoA or Philox through the VEGAS
+//              grid) -> <F> kinematics -> cuts -> Born amplitude -> weight prefactor.  Unscreened
+//              processes finish here (weight + VEGAS accumulation).  Screened processes append the
+//              accepted points to a compact SoA work list (warp-aggregated atomics).
+//   k_screen : one thread per accepted point, the eikonal screening loop integral of
+//              MProcess::S3ScreenedAmp2 (reference src/MProcess.cc:157-288) with every loop invariant in
+//              constant memory; uniform trip count, so no divergence after the compaction.
+//
+// VEGAS accumulators (reference src/MGraniitti.cc:1389-1419, a mutex per point there): per-thread
+// running sums -> warp shuffle -> one global atomic per block; the [bins][dim] histograms live in shared
+// memory per block and are flushed once at block exit.
+#include <cuda_runtime.h>
+
+#include "grb_point.cuh"
+
+namespace grb {
+
+enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY, IT_P3 = 9, IT_P4 = 13,
+       IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_NF };
+
+
+// ---- block-level VEGAS accumulation ---------------------------------------------------------------------
+struct ThreadSums {
+  double fsum = 0, f2sum = 0, n_eval = 0, n_kin = 0, n_fid = 0, n_veto = 0, n_amp = 0, n_naninf = 0;
+  double maxW = 0, maxf = 0;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v) {
+  // non-negative doubles order like their bit patterns
+  atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+}
+
+__device__ void flush_sums(const ThreadSums &t, grb_accum *acc) {
+  double s[8] = {t.fsum, t.f2sum, t.n_eval, t.n_kin, t.n_fid, t.n_veto, t.n_amp, t.n_naninf};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = warp_sum(s[k]);
+  const double mw = warp_max(t.maxW), mf = warp_max(t.maxf);
+  if ((threadIdx.x & 31) == 0) {
+    double *a = &acc->fsum;  // fsum,f2sum,evaluations,n_kin_ok,n_fid_ok,n_veto_ok,n_amp_ok,n_nan_inf
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (s[k] != 0.0) atomicAdd(a + k, s[k]);
+    if (mw > 0) atomic_max_pos(&acc->maxW, mw);
+    if (mf > 0) atomic_max_pos(&acc->maxf, mf);
+  }
+}
+
+// histograms: shared fm[bins*dim], f2m[bins*dim]
+extern __shared__ double s_hist[];
+__device__ __forceinline__ void hist_clear(int nb) {
+  for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) s_hist[i] = 0.0;
+  __syncthreads();
+}
+__device__ __forceinline__ void hist_add(int nb, int dim, uint64_t packed, double f) {
+  const double f2 = f * f;
+#pragma unroll 1
+  for (int j = 0; j < dim; ++j) {
+    const int b = (int)((packed >> (8 * j)) & 0xff);
+    atomicAdd(&s_hist[b * dim + j], f);
+    atomicAdd(&s_hist[nb + b * dim + j], f2);
+  }
+}
+__device__ __forceinline__ void hist_flush(int nb, int dim, grb_accum *acc) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    const int    b = i / dim, j = i % dim;
+    const double a = s_hist[i], c = s_hist[nb + i];
+    if (a != 0.0) atomicAdd(&acc->fmat[b * GRB_MAX_DIM + j], a);
+    if (c != 0.0) atomicAdd(&acc->f2mat[b * GRB_MAX_DIM + j], c);
+  }
+}
+
+// ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
+template <int NN>
+__device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
+  ReggeIn in;
+  in.ss13 = S.ss13; in.ss24 = S.ss24; in.ss14 = S.ss14; in.ss23 = S.ss23;
+  in.t1 = S.t1; in.t2 = S.t2; in.t_hat = S.t_hat; in.u_hat = S.u_hat;
+  return regge_me4(in);
+}
+
+// weight prefactor: everything of MFactorized.cc:173-174 except |A|^2
+template <int NN>
+__device__ __forceinline__ double weight_prefactor(const PointState<NN> &S) {
+  const double J   = 1.0 / fabs(S.p1.z / S.p1.e - S.p2.z / S.p2.e);                      // :441-443
+  const double pt1 = msqrt(pt2_of(S.p1)), pt2 = msqrt(pt2_of(S.p2));
+  const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J;                               // x 1/2 (2pi)^-5 / 4
+  const double vol = (pow2(S.M_MAX) - pow2(S.M_MIN)) * (pt1 * pt2);                     // x (2pi)^2 dlog^2 dY
+  const double C   = c_proc.ps_active ? S.DW / (2 * GRB_PI) : 1.0;
+  return C * psw * vol * c_proc.w_const;
+}
+
+template <int NN, bool VEGAS>
+__global__ void __launch_bounds__(256) k_points(const PointArgs a) {
+  const DevProc &P   = c_proc;
+  const int      dim = P.lipsdim;
+  const int      nb  = a.bins * dim;
+  if (VEGAS) hist_clear(nb);
+  ThreadSums ts;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += stride) {
+    const int64_t idx    = base + threadIdx.x;
+    const bool    active = idx < a.n;
+    double        u[GRB_MAX_DIM > 8 ? 8 : GRB_MAX_DIM];
+    uint64_t      packed = 0;
+    double        vw     = 1.0;
+    PointState<NN> S;
+    bool kin = false, fid = false, veto = false, overrun = false;
+    if (active) {
+      if (VEGAS) {
+        DrawsPhilox dr;
+        const uint64_t gp = (uint64_t)(a.first_call + idx);
+        dr.g.k0 = (uint32_t)a.seed; dr.g.k1 = (uint32_t)(a.seed >> 32);
+        dr.p_lo = (uint32_t)gp; dr.p_hi = (uint32_t)(gp >> 32); dr.iter = a.iter;
+        dr.pos = 0; dr.overrun = false;
+        // reference src/MGraniitti.cc:1357-1375: bin pick + in-bin offset, vegasweight = prod zo*BINS
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < dim) {
+            const double zn  = dr.next() * a.bins + 1.0;
+            unsigned     ind = (unsigned)zn;
+            ind = max(1u, min(ind, (unsigned)a.bins));
+            double zo, ac;
+            if (ind > 1) {
+              const double x1 = a.xmat[(ind - 1) * dim + j], x0 = a.xmat[(ind - 2) * dim + j];
+              zo = x1 - x0;
+              ac = x0 + (zn - ind) * zo;
+            } else {
+              zo = a.xmat[(ind - 1) * dim + j];
+              ac = (zn - ind) * zo;
+            }
+            u[j] = 0.0 + ac * 1.0;
+            vw *= zo * a.bins;
+            packed |= (uint64_t)(ind - 1) << (8 * j);
+          }
+        kin     = point_kinematics<NN>(u, dr, S);
+        overrun = dr.overrun;
+      } else {
+        DrawsSoA dr;
+        dr.u = a.u; dr.tape = a.tape; dr.n = a.ld; dr.idx = idx; dr.dtape = a.dtape; dr.pos = 0; dr.overrun = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < dim) u[j] = dr.coord(j);
+        kin     = point_kinematics<NN>(u, dr, S);
+        overrun = dr.overrun;
+      }
+      if (kin) {  // on failure the reference evaluates the cuts on stale state: flags are don't-care
+        fid  = fiducial_cuts<NN>(S);
+        veto = veto_cuts<NN>(S);
+      }
+    }
+    const bool valid = active && kin && fid && veto && !overrun;
+    double     W = 0.0;
+    bool       amp_ok = true;
+    cx         h0 = {0.0, 0.0};
+    double     pref = 0.0;
+    if (valid) {
+      h0   = born_amplitude<NN>(S);
+      pref = weight_prefactor<NN>(S);
+      if (!P.screening) {
+        W = pref * (h0.re * h0.re + h0.im * h0.im);
+        if (isnan(W) || isinf(W)) { W = 0.0; amp_ok = false; }
+      }
+    }
+    // screened: append to the work list (warp-aggregated slot reservation)
+    if (P.screening) {
+      const unsigned m = __ballot_sync(0xffffffffu, valid);
+      if (m) {
+        const int    lane = threadIdx.x & 31;
+        const int    lead = __ffs(m) - 1;
+        unsigned int slot0 = 0;
+        if (lane == lead) slot0 = atomicAdd(a.item_count, (unsigned)__popc(m));
+        slot0 = __shfl_sync(0xffffffffu, slot0, lead);
+        if (valid) {
+          const int64_t slot = slot0 + __popc(m & ((1u << lane) - 1));
+          if (slot < a.item_cap) {
+            LoopInv L;
+            make_loop_inv<NN>(S, L);
+            double *it = a.items + slot;
+            const int64_t c = a.item_cap;
+            it[IT_P1X * c] = L.p1x; it[IT_P1Y * c] = L.p1y; it[IT_P2X * c] = L.p2x; it[IT_P2Y * c] = L.p2y;
+            it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
+            it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
+            it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
+            it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
+            it[IT_H0RE * c] = h0.re; it[IT_H0IM * c] = h0.im;
+            it[IT_PREF * c] = pref; it[IT_VW * c] = vw;
+            a.item_idx[slot]  = (int32_t)idx;
+            a.item_bins[slot] = packed;
+          }
+        }
+      }
+    }
+    if (active) {
+      const uint8_t fl = (uint8_t)((kin ? GRB_FLAG_KIN : 0) | (fid ? GRB_FLAG_FID : 0) | (veto ? GRB_FLAG_VETO : 0) |
+                                   (amp_ok ? GRB_FLAG_AMP : 0));
+      if (a.w) a.w[idx] = W;
+      if (a.flags) a.flags[idx] = fl;
+      if (a.dump) {
+        double *D = a.dump + idx;
+        const int64_t n = a.ld;
+        D[GRB_DUMP_T1 * n] = kin ? S.t1 : 0; D[GRB_DUMP_T2 * n] = kin ? S.t2 : 0;
+        D[GRB_DUMP_S1 * n] = kin ? S.s1 : 0; D[GRB_DUMP_S2 * n] = kin ? S.s2 : 0;
+        D[GRB_DUMP_M2 * n] = kin ? S.m2 : 0; D[GRB_DUMP_Y * n] = kin ? S.Y : 0; D[GRB_DUMP_PT * n] = kin ? S.Pt : 0;
+        D[GRB_DUMP_THAT * n] = kin ? S.t_hat : 0; D[GRB_DUMP_UHAT * n] = kin ? S.u_hat : 0;
+        D[GRB_DUMP_AMP2 * n] = valid ? (h0.re * h0.re + h0.im * h0.im) : 0;
+        D[GRB_DUMP_HAMP0_RE * n] = h0.re; D[GRB_DUMP_HAMP0_IM * n] = h0.im;
+      }
+      // statistics (reference stat.Accumulate(aux)); screened weights are added by k_screen
+      ts.n_eval += 1.0;
+      ts.n_kin += kin ? 1.0 : 0.0;
+      ts.n_fid += (kin && fid) ? 1.0 : 0.0;
+      ts.n_veto += (kin && veto) ? 1.0 : 0.0;
+      if (!P.screening) {
+        ts.n_amp += amp_ok ? 1.0 : 0.0;
+        ts.n_naninf += amp_ok ? 0.0 : 1.0;
+        if (VEGAS && W != 0.0) {
+          const double f = W * vw;
+          ts.fsum += f;
+          ts.f2sum += f * f;
+          ts.maxW = fmax(ts.maxW, W);
+          ts.maxf = fmax(ts.maxf, f);
+          hist_add(nb, dim, packed, f);
+        }
+      }
+    }
+  }
+  flush_sums(ts, a.acc);
+  if (VEGAS) hist_flush(nb, dim, a.acc);
+}
+
+template <bool VEGAS>
+__global__ void __launch_bounds__(128) k_screen(const PointArgs a) {
+  const DevProc &P   = c_proc;
+  const int      dim = P.lipsdim;
+  const int      nb  = a.bins * dim;
+  if (VEGAS) hist_clear(nb);
+  ThreadSums    ts;
+  const int64_t n_items = min((int64_t)*a.item_count, a.item_cap);
+  const int64_t stride  = (int64_t)gridDim.x * blockDim.x;
+  const int64_t c       = a.item_cap;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_items; s += stride) {
+    const double *it = a.items + s;
+    LoopInv       L;
+    L.p1x = it[IT_P1X * c]; L.p1y = it[IT_P1Y * c]; L.p2x = it[IT_P2X * c]; L.p2y = it[IT_P2Y * c];
+    L.m1 = it[IT_M1 * c]; L.m2 = it[IT_M2 * c]; L.mXsq = it[IT_MXSQ * c];
+    L.shY = it[IT_SHY * c]; L.chY = it[IT_CHY * c];
+    L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
+    L.emax = P.sqrt_s - (L.m1 + L.m2);
+    L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
+    L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
+    cx h0;
+    h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
+    const double pref = it[IT_PREF * c], vw = it[IT_VW * c];
+    const double amp2 = screened_amp2_h1(L, h0);
+    double       W    = pref * amp2;
+    bool         ok   = true;
+    if (isnan(W) || isinf(W)) { W = 0.0; ok = false; }
+    const int32_t idx = a.item_idx[s];
+    if (a.w) a.w[idx] = W;
+    if (a.flags && !ok) a.flags[idx] &= (uint8_t)~GRB_FLAG_AMP;
+    if (a.dump) a.dump[GRB_DUMP_AMP2 * a.ld + idx] = amp2;
+    ts.n_amp += ok ? 1.0 : 0.0;
+    ts.n_naninf += ok ? 0.0 : 1.0;
+    if (VEGAS && W != 0.0) {
+      const double f = W * vw;
+      ts.fsum += f;
+      ts.f2sum += f * f;
+      ts.maxW = fmax(ts.maxW, W);
+      ts.maxf = fmax(ts.maxf, f);
+      hist_add(nb, dim, a.item_bins[s], f);
+    }
+  }
+  flush_sums(ts, a.acc);
+  if (VEGAS) hist_flush(nb, dim, a.acc);
+}
+
+// points that were not Valid() count as amplitude_ok in the reference (aux default true): added on the host.
+
+// ---- fp64 FMA peak microbenchmark (roofline denominator) -------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ---- launchers (called from grb_api.cu) ---------------------------------------------------------------------
+cudaError_t upload_proc(const DevProc &p, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_proc, &p, sizeof(DevProc), 0, cudaMemcpyHostToDevice, st);
+}
+cudaError_t upload_loop(const DevLoop &l, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_loop, &l, sizeof(DevLoop), 0, cudaMemcpyHostToDevice, st);
+}
+
+int launch_points(const PointArgs &a, int n_nodes, int sm_count, cudaStream_t st) {
+  const int    threads = 256;
+  int64_t      blocks  = (a.n + threads - 1) / threads;
+  const int64_t cap    = (int64_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  if (n_nodes <= 2) {
+    if (a.vegas) k_points<2, true><<<(unsigned)blocks, threads, smem, st>>>(a);
+    else k_points<2, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  } else {
+    if (a.vegas) k_points<GRB_MAX_NODES, true><<<(unsigned)blocks, threads, smem, st>>>(a);
+    else k_points<GRB_MAX_NODES, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  }
+  return 1;
+}
+
+int launch_screen(const PointArgs &a, int sm_count, cudaStream_t st) {
+  const int    threads = 128;
+  const int    blocks  = sm_count * 4;
+  const size_t smem    = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  if (a.vegas) k_screen<true><<<blocks, threads, smem, st>>>(a);
+  else k_screen<false><<<blocks, threads, 0, st>>>(a);
+  return 1;
+}
+
+cudaError_t run_dfma_peak(int sm_count, double *tflops) {
+  const int blocks = sm_count * 8, threads = 256, iters = 1 << 16;
+  double *  d      = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double) * blocks * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  k_dfma_peak<<<blocks, threads>>>(d, 1024);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0);
+    k_dfma_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(t1);
+    e = cudaEventSynchronize(t1);
+    if (e != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d);
+  *tflops = best;
+  return e;
+}
+
+}  // namespace grb

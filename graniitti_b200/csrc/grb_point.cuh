@@ -1,0 +1,464 @@
+// grb_point.cuh -- one phase-space point of the <F> class on the device: sampling map, 2->3 skeleton,
+// central decay chain, Lorentz scalars, cuts, Born amplitude, and the per-node work of the screening loop.
+// See grb_dev.cuh for the arithmetic conventions (-fmad=false, explicit fma()).
+#pragma once
+#include "grb_dev.cuh"
+
+namespace grb {
+
+__constant__ DevProc c_proc;
+__constant__ DevLoop c_loop;
+
+// ---- Philox4x32-10 counter-based RNG (Salmon et al., SC'11): key = seed, counter = (point, iter, block) --
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+    uint32_t ka = k0, kb = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ ka, n1 = lo1, n2 = hi0 ^ c3 ^ kb, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      ka += 0x9E3779B9u;
+      kb += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+};
+__device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo) {
+  // 53-bit uniform in [0,1), like std::uniform_real_distribution<double> over a 64-bit engine
+  const uint64_t x = ((uint64_t)hi << 32) | lo;
+  return (double)(x >> 11) * 0x1.0p-53;
+}
+
+// Source of the VEGAS-visible coordinates u[] and of the internal draws ("tape") of one point.
+// (a) caller supplied SoA arrays (parity mode, grb_eval); (b) Philox (grb_vegas_iterate).
+struct DrawsSoA {
+  const double *u, *tape;
+  int64_t       n, idx;
+  int           dtape, pos;
+  bool          overrun;
+  __device__ __forceinline__ double coord(int j) const { return u[(int64_t)j * n + idx]; }
+  __device__ __forceinline__ double next() {
+    double v = 0.5;
+    if (pos < dtape) v = tape[(int64_t)pos * n + idx]; else overrun = true;
+    ++pos;
+    return v;
+  }
+};
+struct DrawsPhilox {
+  Philox   g;
+  uint32_t p_lo, p_hi, iter;
+  int      pos;       // next draw index (0..: coordinates first, then tape)
+  double   cached;
+  bool     overrun;
+  __device__ __forceinline__ double draw(int d) {
+    uint32_t o[4];
+    g.block(p_lo, p_hi, iter, (uint32_t)(d >> 1), o);
+    return (d & 1) ? u01_from_bits(o[3], o[2]) : u01_from_bits(o[1], o[0]);
+  }
+  __device__ __forceinline__ double next() {
+    double v;
+    if (pos & 1) {
+      v = cached;
+    } else {
+      uint32_t o[4];
+      g.block(p_lo, p_hi, iter, (uint32_t)(pos >> 1), o);
+      v      = u01_from_bits(o[1], o[0]);
+      cached = u01_from_bits(o[3], o[2]);
+    }
+    ++pos;
+    return v;
+  }
+};
+
+// ---- per-point state ------------------------------------------------------------------------------------
+template <int NN>
+struct PointState {
+  v4     p1, p2, pX;       // lts.pfinal[1], [2], [0]
+  v4     np4[NN];          // decay tree node momenta; nodes [0,n_legs) are lts.pfinal[3..]
+  double moff[NN];         // off-shell masses
+  double M_MIN, M_MAX, DW;
+  double t1, t2, s1, s2, t_hat, u_hat, m2, Y, Pt;
+  double ss13, ss14, ss23, ss24;
+};
+
+// reference src/MRandom.cc:82-107 RelativisticBWRandom; node constants are pre-digested on the host with
+// the reference's libm for the M_MIN = 0 case (final-state legs); mothers with a lower bound take atan2 here
+template <class Draws>
+__device__ __forceinline__ double bw_mass(const DevNode &nd, double M_MIN_arg, bool has_min, Draws &dr) {
+  if (!nd.bw_active) return nd.mass;
+  double A, BA;
+  if (!has_min) {
+    A  = nd.bwA0;
+    BA = nd.bwBA0;
+  } else {
+    const double m2min = fmax(fmax(0.0, pow2(M_MIN_arg)), nd.m2lo);
+    A  = atan2(m2min - nd.m2, nd.m0G);
+    BA = atan2(nd.m2max - nd.m2, nd.m0G) - A;
+  }
+  double m2val = 0.0;
+  for (int it = 0; it < 64; ++it) {
+    const double R = dr.next();
+    m2val = nd.m2 + nd.m0G * tan(A + R * BA);
+    if (m2val >= 0) break;
+  }
+  return msqrt(m2val);
+}
+
+// reference src/MProcess.cc:753-812 GetOffShellMass
+template <class Draws>
+__device__ __forceinline__ double offshell_mass(int node, Draws &dr) {
+  const DevNode &b = c_proc.nodes[node];
+  if (b.width < 1e-40) return b.mass;
+  double dm = 0.0;
+  if (b.n_children != 0) {
+    for (int i = 0; i < b.n_children; ++i)
+      dm += fmax(0.0, bw_mass(c_proc.nodes[b.first_child + i], 0.0, false, dr));
+    dm += 1e-5;
+    return fmax(dm, bw_mass(b, dm, true, dr));
+  }
+  return fmax(dm, bw_mass(b, 0.0, false, dr));
+}
+
+// Lorentz scalars needed downstream (reference src/MProcess.cc:1499-1584 computes ~60; the ss[i][j] >= 0
+// tests on the pairs not kept here cannot fire: ss >= (m_i+m_j)^2 exceeds the rounding noise by >1e3)
+template <int NN>
+__device__ __forceinline__ bool lorentz_scalars(PointState<NN> &S) {
+  const v4 &p3 = S.np4[0], &p4 = S.np4[1];
+  S.s1   = m2_of(S.p1.x + S.pX.x, S.p1.y + S.pX.y, S.p1.z + S.pX.z, S.p1.e + S.pX.e);  // ss[0][1]
+  S.s2   = m2_of(S.p2.x + S.pX.x, S.p2.y + S.pX.y, S.p2.z + S.pX.z, S.p2.e + S.pX.e);  // ss[0][2]
+  const double s12 = m2_of(S.p1.x + S.p2.x, S.p1.y + S.p2.y, S.p1.z + S.p2.z, S.p1.e + S.p2.e);
+  S.ss13 = m2_of(S.p1.x + p3.x, S.p1.y + p3.y, S.p1.z + p3.z, S.p1.e + p3.e);
+  S.ss14 = m2_of(S.p1.x + p4.x, S.p1.y + p4.y, S.p1.z + p4.z, S.p1.e + p4.e);
+  S.ss23 = m2_of(S.p2.x + p3.x, S.p2.y + p3.y, S.p2.z + p3.z, S.p2.e + p3.e);
+  S.ss24 = m2_of(S.p2.x + p4.x, S.p2.y + p4.y, S.p2.z + p4.z, S.p2.e + p4.e);
+  const double s03 = m2_of(S.pX.x + p3.x, S.pX.y + p3.y, S.pX.z + p3.z, S.pX.e + p3.e);
+  const double s04 = m2_of(S.pX.x + p4.x, S.pX.y + p4.y, S.pX.z + p4.z, S.pX.e + p4.e);
+  const double s34 = m2_of(p3.x + p4.x, p3.y + p4.y, p3.z + p4.z, p3.e + p4.e);
+  if (S.s1 < 0 || S.s2 < 0 || s12 < 0 || S.ss13 < 0 || S.ss14 < 0 || S.ss23 < 0 || S.ss24 < 0 || s03 < 0 ||
+      s04 < 0 || s34 < 0)
+    return false;
+  const double q1x = 0.0 - S.p1.x, q1y = 0.0 - S.p1.y, q1z = c_proc.pb1z - S.p1.z, q1e = c_proc.pb1e - S.p1.e;
+  const double q2x = 0.0 - S.p2.x, q2y = 0.0 - S.p2.y, q2z = c_proc.pb2z - S.p2.z, q2e = c_proc.pb2e - S.p2.e;
+  S.t1 = m2_of(q1x, q1y, q1z, q1e);
+  S.t2 = m2_of(q2x, q2y, q2z, q2e);
+  if (S.t1 > 0 || S.t2 > 0) return false;
+  S.t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  S.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  S.m2 = m2_of(S.pX);
+  S.Y  = rap_of(S.pX);
+  S.Pt = msqrt(pt2_of(S.pX));
+  return true;
+}
+
+// reference src/MFactorized.cc:245-412 B51RandomKin + B51BuildKin, src/MProcess.cc:1231-1284
+template <int NN, class Draws>
+__device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, PointState<NN> &S) {
+  const DevProc &P = c_proc;
+  const double   pt1  = exp(P.log_pt0 + P.dlog_pt * u[0]);
+  const double   pt2  = exp(P.log_pt0 + P.dlog_pt * u[1]);
+  const double   phi1 = 2.0 * GRB_PI * u[2];
+  const double   phi2 = 2.0 * GRB_PI * u[3];
+  const double   yX   = P.Y_min + P.dY * u[4];
+  // off-shell masses of the first-level legs; the M_MIN < M_MAX retry of :264-289 is bounded
+  for (int trial = 0;; ++trial) {
+    double M_sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < NN; ++i)
+      if (i < P.n_legs) {
+        S.moff[i] = offshell_mass(i, dr);
+        M_sum += S.moff[i];
+      }
+    S.M_MIN = fmax(M_sum + 1e-4, P.gM_min);
+    S.M_MAX = fmin(P.M_MAX0, P.gM_max);
+    if (S.M_MIN < S.M_MAX) break;
+    if (trial >= 32) return false;
+  }
+  const double m2X = pow2(S.M_MIN) + (pow2(S.M_MAX) - pow2(S.M_MIN)) * u[5];
+  const double m1 = P.mb1, m2 = P.mb2;
+
+  double s1, c1, s2, c2;
+  sincos(phi1, &s1, &c1);
+  sincos(phi2, &s2, &c2);
+  S.p1.x = pt1 * c1; S.p1.y = pt1 * s1;
+  S.p2.x = pt2 * c2; S.p2.y = pt2 * s2;
+  S.pX.x = -(S.p1.x + S.p2.x);
+  S.pX.y = -(S.p1.y + S.p2.y);
+  const double mtX = msqrt(m2X + pt2_of(S.pX));
+  S.pX.z = mtX * sinh(yX);
+  S.pX.e = mtX * cosh(yX);
+  if (S.pX.e > (P.sqrt_s - (m1 + m2))) return false;
+  PzConst pc;
+  pc.s = P.s; pc.t7 = P.sqrt_s; pc.t9 = P.s_pow15; pc.t14 = P.s * P.s;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, S.pX.z, S.pX.e, pc);
+  const double p2z = -(S.pX.z + p1z);
+  if (p1z < 0 || p2z > 0 || isnan(p1z)) return false;
+  S.p1.z = p1z; S.p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  S.p2.z = p2z; S.p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  // CheckEMC, MMath.h:191-198 (beamsum has px = py = 0)
+  {
+    const double dx = 0.0 - ((S.p1.x + S.p2.x) + S.pX.x), dy = 0.0 - ((S.p1.y + S.p2.y) + S.pX.y);
+    const double dz = P.bsum_z - ((S.p1.z + S.p2.z) + S.pX.z), de = P.bsum_e - ((S.p1.e + S.p2.e) + S.pX.e);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  // central two-body decay (the device path covers 2 first-level legs)
+  {
+    const double rc = dr.next();
+    const double rp = dr.next();
+    S.DW = two_body(S.pX, msqrt(m2X), S.moff[0], S.moff[1], rc, rp, S.np4[0], S.np4[1]);
+    if (S.DW < 0) return false;
+  }
+  // cascade decays in the reference's depth-first order
+  if (NN > 2) {
+    for (int k = 0; k < P.n_decays; ++k) {
+      const int      node = P.decay_order[k];
+      const DevNode &b    = P.nodes[node];
+      const int      c0 = b.first_child, c1n = b.first_child + 1;
+      const double   Mm = m_of(S.np4[node % NN]);
+      double         m0v = 0, m1v = 0;
+      for (int it = 0;; ++it) {
+        m0v = offshell_mass(c0, dr);
+        m1v = offshell_mass(c1n, dr);
+        if (Mm < (0.0 + m1v) + m0v) {
+          if (it >= 64) return false;
+          continue;
+        }
+        break;
+      }
+      S.moff[c0 % NN]  = m0v;
+      S.moff[c1n % NN] = m1v;
+      const double rc = dr.next();
+      const double rp = dr.next();
+      const double w  = two_body(S.np4[node % NN], Mm, m0v, m1v, rc, rp, S.np4[c0 % NN], S.np4[c1n % NN]);
+      if (w < 0) return false;
+    }
+  }
+  return lorentz_scalars(S);
+}
+
+// ---- cuts (reference src/MProcess.cc:1069-1175, src/MUserCuts.cc:21-75) ------------------------------------
+__device__ __forceinline__ bool leaf_fid_ok(const v4 &p) {
+  const DevProc &P    = c_proc;
+  const double   pt2  = pt2_of(p);
+  const double   pt   = msqrt(pt2);
+  const double   et   = msqrt(m2_of(p) + pt2);
+  const double   pmod = msqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+  const double   eta  = 0.5 * log((pmod + p.z) / (pmod - p.z));
+  const double   rap  = rap_of(p);
+  return pt >= P.f_pt_min && pt <= P.f_pt_max && et >= P.f_Et_min && et <= P.f_Et_max && eta >= P.f_eta_min &&
+         eta <= P.f_eta_max && rap >= P.f_rap_min && rap <= P.f_rap_max;
+}
+__device__ __forceinline__ bool leaf_veto_hit(const v4 &p) {
+  const DevProc &P    = c_proc;
+  const double   pt   = msqrt(pt2_of(p));
+  const double   pmod = msqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+  const double   eta  = 0.5 * log((pmod + p.z) / (pmod - p.z));
+  bool           hit  = false;
+  for (int i = 0; i < P.n_veto; ++i)
+    if (pt >= P.veto[i].pt_min && pt <= P.veto[i].pt_max && eta >= P.veto[i].eta_min && eta <= P.veto[i].eta_max)
+      hit = true;
+  return hit;
+}
+
+template <int NN>
+__device__ __forceinline__ bool fiducial_cuts(const PointState<NN> &S) {
+  const DevProc &P = c_proc;
+  if (!P.fid_active) return true;
+  const int id = P.usercuts;
+  if (id != 0) {
+    if (id == 3 || id == -3) {
+      const double dx = S.p1.x - S.p2.x, dy = S.p1.y - S.p2.y;
+      const double dpt = msqrt(dx * dx + dy * dy);
+      if (id == -3 && !(dpt < 0.3)) return false;
+      if (id == 3 && !(dpt > 0.3)) return false;
+    } else if (id == 111 || id == -111) {
+      const double dot = S.p1.x * S.p2.x + S.p1.y * S.p2.y;
+      if (id == -111 && !(dot < 0)) return false;
+      if (id == 111 && !(dot > 0)) return false;
+    }
+  }
+  if (!(fabs(S.t1) >= P.f_t_min && fabs(S.t1) <= P.f_t_max && fabs(S.t2) >= P.f_t_min && fabs(S.t2) <= P.f_t_max))
+    return false;
+  const double M = msqrt(S.m2);
+  if (!(M >= P.f_M_min && M <= P.f_M_max && S.Y >= P.f_Y_min && S.Y <= P.f_Y_max && S.Pt >= P.f_Pt_min &&
+        S.Pt <= P.f_Pt_max))
+    return false;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NN; ++i)
+    if (i < P.n_nodes && P.nodes[i].n_children == 0) ok = ok && leaf_fid_ok(S.np4[i]);
+  return ok;
+}
+template <int NN>
+__device__ __forceinline__ bool veto_cuts(const PointState<NN> &S) {
+  const DevProc &P = c_proc;
+  if (!P.veto_active) return true;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NN; ++i)
+    if (i < P.n_nodes && P.nodes[i].n_children == 0 && leaf_veto_hit(S.np4[i])) ok = false;
+  return ok;
+}
+
+// ---- Regge continuum amplitude (reference src/MRegge.cc:394-438 ME4) ---------------------------------------
+// A = A_t + sign*A_u, A_x = Prop(s_a,t1) FF_A ff(x)^2 gpp^2 /(x - M^2) Prop(s_b,t2) FF_B with
+// Prop(s,t) = sum_k eta_k(0) e^{-i pi/2 ap_k t} (s/s0)^{a0_k + ap_k t}.  With one active trajectory (TUNE0)
+// the phase depends on t1+t2 only and the amplitude is  eta0^2 cis(pc (t1+t2)) * real.
+struct ReggeIn {
+  double ss13, ss24, ss14, ss23, t1, t2, t_hat, u_hat;
+};
+
+__device__ __forceinline__ double meson_G(double x) {  // ff(x)^2 * prop(x), MRegge.cc:1155-1218
+  const DevProc &P  = c_proc;
+  const double   tp = x - P.M2_leg0;
+  if (P.offshellFF == 2) {
+    const double d = 1.0 - tp / P.b_POW;
+    return 1.0 / (d * d * tp);
+  } else if (P.offshellFF == 0) {
+    const double f = exp(-P.b_EXP * fabs(tp));
+    return f * f / tp;
+  } else {
+    const double f = exp(-P.b_OREAR * msqrt(fabs(tp) + pow2(P.a_OREAR)) + P.a_OREAR * P.b_OREAR);
+    return f * f / tp;
+  }
+}
+
+__device__ __forceinline__ cx regge_prop(double s, double t) {  // general PropOnly, MRegge.cc:888-906
+  const DevProc &P = c_proc;
+  cx             M = {0.0, 0.0};
+  const double   ls = log(s) + P.ln_inv_s0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (P.regge_n[k]) {
+      const double mag = exp((P.a0[k] + P.ap[k] * t) * ls);
+      double       sn, cs;
+      sincos(P.phase_c[k] * t, &sn, &cs);
+      const double er = P.eta0_re[k] * cs - P.eta0_im[k] * sn, ei = P.eta0_re[k] * sn + P.eta0_im[k] * cs;
+      M.re += er * mag;
+      M.im += ei * mag;
+    }
+  return M;
+}
+
+__device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
+  const DevProc &P   = c_proc;
+  const double   FFA = P.gN_P * ((1.0 / (1 - in.t1 / P.fc1)) * (1.0 / (1 - in.t1 / P.fc2)));  // S3F, MForm.cc:433
+  const double   FFB = P.gN_P * ((1.0 / (1 - in.t2 / P.fc1)) * (1.0 / (1 - in.t2 / P.fc2)));
+  const double   g2  = P.gpp_P * P.gpp_P * FFA * FFB;
+  const double   Gt = meson_G(in.t_hat), Gu = meson_G(in.u_hat) * P.me4_sign;
+  cx             A;
+  if (P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2]) {
+    // single trajectory: one sincos, two exp, four log
+    const double a1 = P.a0[0] + P.ap[0] * in.t1, a2 = P.a0[0] + P.ap[0] * in.t2;
+    const double Et = exp(a1 * (log(in.ss13) + P.ln_inv_s0) + a2 * (log(in.ss24) + P.ln_inv_s0));
+    const double Eu = exp(a1 * (log(in.ss14) + P.ln_inv_s0) + a2 * (log(in.ss23) + P.ln_inv_s0));
+    const double R  = g2 * (Et * Gt + Eu * Gu);
+    double       sn, cs;
+    sincos(P.phase_c[0] * (in.t1 + in.t2), &sn, &cs);
+    // eta0^2
+    const double e2r = P.eta0_re[0] * P.eta0_re[0] - P.eta0_im[0] * P.eta0_im[0];
+    const double e2i = 2.0 * P.eta0_re[0] * P.eta0_im[0];
+    A.re = (e2r * cs - e2i * sn) * R;
+    A.im = (e2r * sn + e2i * cs) * R;
+  } else {
+    const cx P13 = regge_prop(in.ss13, in.t1), P24 = regge_prop(in.ss24, in.t2);
+    const cx P14 = regge_prop(in.ss14, in.t1), P23 = regge_prop(in.ss23, in.t2);
+    const double tr = P13.re * P24.re - P13.im * P24.im, ti = P13.re * P24.im + P13.im * P24.re;
+    const double ur = P14.re * P23.re - P14.im * P23.im, ui = P14.re * P23.im + P14.im * P23.re;
+    A.re = g2 * (tr * Gt + ur * Gu);
+    A.im = g2 * (ti * Gt + ui * Gu);
+  }
+  return A;
+}
+
+// ---- screening loop: per-point invariants and per-node work -------------------------------------------------
+// reference src/MFactorized.cc:84-139 LoopKinematics: the loop re-derives m1, m2, mX, yX from the saved
+// 4-vectors (pfinal_orig) -- done once per point here -- shifts the proton pT by -/+ kt, rebuilds pX and
+// re-solves pz.  Quirk kept: the central daughters p3, p4 are NOT updated inside the loop.
+struct LoopInv {
+  double p1x, p1y, p2x, p2y;
+  double m1, m2, m1sq, m2sq, mXsq, shY, chY, emax;  // emax = sqrt_s - (m1 + m2)
+  v4     p3, p4;
+};
+
+template <int NN>
+__device__ __forceinline__ void make_loop_inv(const PointState<NN> &S, LoopInv &L) {
+  L.p1x = S.p1.x; L.p1y = S.p1.y; L.p2x = S.p2.x; L.p2y = S.p2.y;
+  L.m1 = m_of(S.p1); L.m2 = m_of(S.p2);
+  L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
+  const double mX = m_of(S.pX);
+  const double yX = rap_of(S.pX);
+  L.mXsq = pow2(mX);
+  L.shY  = sinh(yX);
+  L.chY  = cosh(yX);
+  L.emax = c_proc.sqrt_s - (L.m1 + L.m2);
+  L.p3 = S.np4[0];
+  L.p4 = S.np4[1];
+}
+
+__device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, double ktx, double kty, ReggeIn &o) {
+  const DevProc &P = c_proc;
+  const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
+  const double pt1 = msqrt(n1x * n1x + n1y * n1y), pt2 = msqrt(n2x * n2x + n2y * n2y);
+  const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
+  const double mtX = msqrt(L.mXsq + (Xx * Xx + Xy * Xy));
+  const double Xz = mtX * L.shY, Xe = mtX * L.chY;
+  if (Xe > L.emax) return false;
+  const double p1z = solve_pz(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
+  const double p2z = -(Xz + p1z);
+  if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
+  const double e1 = msqrt(L.m1sq + pow2(pt1) + pow2(p1z));
+  const double e2 = msqrt(L.m2sq + pow2(pt2) + pow2(p2z));
+  {
+    const double dx = 0.0 - ((n1x + n2x) + Xx), dy = 0.0 - ((n1y + n2y) + Xy);
+    const double dz = P.bsum_z - ((p1z + p2z) + Xz), de = P.bsum_e - ((e1 + e2) + Xe);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  const v4 &p3 = L.p3, &p4 = L.p4;
+  o.ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
+  o.ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
+  o.ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
+  o.ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
+  const double s01 = m2_of(n1x + Xx, n1y + Xy, p1z + Xz, e1 + Xe);
+  const double s02 = m2_of(n2x + Xx, n2y + Xy, p2z + Xz, e2 + Xe);
+  if (o.ss13 < 0 || o.ss14 < 0 || o.ss23 < 0 || o.ss24 < 0 || s01 < 0 || s02 < 0) return false;
+  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  o.t1 = m2_of(q1x, q1y, q1z, q1e);
+  o.t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
+  if (o.t1 > 0 || o.t2 > 0) return false;
+  o.t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  o.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  return true;
+}
+
+// reference src/MProcess.cc:157-288 S3ScreenedAmp2 for a one-amplitude process (H = 1): returns
+// |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order.
+__device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h0) {
+  const DevLoop &Q = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  double Ire = 0.0, Iim = 0.0;
+  for (int i = 0; i <= Q.nphi; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      ReggeIn      in;
+      if (!loop_node(L, pc, kt * cp, kt * sp, in)) continue;
+      const cx A = regge_me4(in);
+      // f = (A_eik * A) * kt ;  I += W_ij * f
+      const double fr = (Q.aeik_re[j] * A.re - Q.aeik_im[j] * A.im) * kt;
+      const double fi = (Q.aeik_re[j] * A.im + Q.aeik_im[j] * A.re) * kt;
+      const double w  = wi * Q.wkt[j];
+      Ire += w * fr;
+      Iim += w * fi;
+    }
+  }
+  // hamp_loop = i * norm * I
+  const double lr = -Q.norm * Iim, li = Q.norm * Ire;
+  const double ar = h0.re + lr, ai = h0.im + li;
+  return ar * ar + ai * ai;
+}
+
+}  // namespace grb

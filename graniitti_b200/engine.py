@@ -1,0 +1,199 @@
+"""ctypes binding of include/grb.h (plumbing only)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libgrb.so")
+_lib = None
+
+
+class GrbError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"grb error {rc}: {msg}")
+        self.rc = rc
+
+
+def lib():
+    """Load libgrb.so (fails loudly if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: run `python -m graniitti_b200.build` "
+                              "(or __graft_entry__.build()); the engine has no CPU fallback")
+        L = C.CDLL(_LIB_PATH)
+        vp, i64, u64, dbl, cint = C.c_void_p, C.c_int64, C.c_uint64, C.c_double, C.c_int
+        L.grb_abi_sizeof.restype = cint
+        L.grb_abi_sizeof.argtypes = [cint]
+        L.grb_create.restype = cint
+        L.grb_create.argtypes = [C.POINTER(_abi.ProcessDesc), cint, C.POINTER(vp)]
+        L.grb_create_from_card.restype = cint
+        L.grb_create_from_card.argtypes = [C.c_char_p, C.c_char_p, cint, C.c_char_p, cint, C.POINTER(vp)]
+        L.grb_parse_card.restype = cint
+        L.grb_parse_card.argtypes = [C.c_char_p, C.c_char_p, cint, C.c_char_p, C.POINTER(_abi.ProcessDesc),
+                                     C.c_char_p, cint]
+        L.grb_get_desc.restype = cint
+        L.grb_get_desc.argtypes = [vp, C.POINTER(_abi.ProcessDesc)]
+        L.grb_last_error.restype = C.c_char_p
+        L.grb_last_error.argtypes = [vp]
+        L.grb_destroy.restype = None
+        L.grb_destroy.argtypes = [vp]
+        L.grb_set_eikonal.restype = cint
+        L.grb_set_eikonal.argtypes = [vp, vp, vp, vp, cint]
+        L.grb_build_eikonal.restype = cint
+        L.grb_build_eikonal.argtypes = [vp, cint, cint, vp, vp, vp, vp]
+        L.grb_eval.restype = cint
+        L.grb_eval.argtypes = [vp, i64, vp, cint, vp, cint, vp, vp, vp]
+        L.grb_vegas_iterate.restype = cint
+        L.grb_vegas_iterate.argtypes = [vp, vp, cint, cint, i64, i64, u64, u64, cint, dbl, C.POINTER(_abi.Accum)]
+        L.grb_vegas_iterate_async.restype = cint
+        L.grb_vegas_iterate_async.argtypes = [vp, vp, cint, cint, i64, i64, u64, u64, cint, dbl, C.POINTER(vp)]
+        L.grb_vegas_fetch.restype = cint
+        L.grb_vegas_fetch.argtypes = [vp, C.POINTER(_abi.Accum)]
+        L.grb_sync.restype = cint
+        L.grb_sync.argtypes = [vp]
+        L.grb_vegas_optimize_grid.restype = cint
+        L.grb_vegas_optimize_grid.argtypes = [vp, vp, cint, cint, dbl]
+        L.grb_get_events.restype = i64
+        L.grb_get_events.argtypes = [vp, i64, vp, vp, C.POINTER(cint)]
+        L.grb_comm_unique_id.restype = cint
+        L.grb_comm_unique_id.argtypes = [C.c_char_p]
+        L.grb_comm_init.restype = cint
+        L.grb_comm_init.argtypes = [vp, cint, cint, C.c_char_p]
+        L.grb_allreduce.restype = cint
+        L.grb_allreduce.argtypes = [vp]
+        L.grb_measure_dfma_peak.restype = cint
+        L.grb_measure_dfma_peak.argtypes = [cint, C.POINTER(dbl)]
+        L.grb_last_timing.restype = cint
+        L.grb_last_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(cint)]
+        _lib = L
+    return _lib
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+def parse_card(card, process=None, pomloop=-1, base=None):
+    """Host-only: steering card (+ overrides) -> ProcessDesc. Mirrors `gr -i card -p process -l pomloop`."""
+    d = _abi.ProcessDesc()
+    buf = C.create_string_buffer(2048)
+    rc = lib().grb_parse_card(card.encode(), process.encode() if process else None, int(pomloop),
+                              base.encode() if base else None, C.byref(d), buf, len(buf))
+    if rc != 0:
+        raise GrbError(rc, buf.value.decode(errors="replace"))
+    return d
+
+
+def optimize_grid(xmat, f2mat, lam=1.5):
+    """VEGAS grid refinement (host). xmat [bins][dim] float64 C-order (updated in place),
+    f2mat [bins][GRB_MAX_DIM]."""
+    bins, dim = xmat.shape
+    assert xmat.flags.c_contiguous and f2mat.flags.c_contiguous and f2mat.shape == (bins, _abi.GRB_MAX_DIM) or \
+        f2mat.shape[1] == _abi.GRB_MAX_DIM
+    rc = lib().grb_vegas_optimize_grid(xmat.ctypes.data, f2mat.ctypes.data, bins, dim, float(lam))
+    if rc != 0:
+        raise GrbError(rc, "grb_vegas_optimize_grid")
+    return xmat
+
+
+def measure_dfma_peak(device=0):
+    v = C.c_double(0)
+    rc = lib().grb_measure_dfma_peak(device, C.byref(v))
+    if rc != 0:
+        raise GrbError(rc, "grb_measure_dfma_peak (needs a CUDA device)")
+    return v.value
+
+
+class Engine:
+    """One engine per process/GPU rank (reference: one MProcess copy per thread, MGraniitti.cc:278-309)."""
+
+    def __init__(self, desc=None, card=None, process=None, pomloop=-1, base=None, device=0):
+        self._h = C.c_void_p()
+        L = lib()
+        if desc is not None:
+            rc = L.grb_create(C.byref(desc), device, C.byref(self._h))
+        else:
+            rc = L.grb_create_from_card(card.encode(), process.encode() if process else None, int(pomloop),
+                                        base.encode() if base else None, device, C.byref(self._h))
+        if rc != 0:
+            raise GrbError(rc, L.grb_last_error(None).decode(errors="replace"))
+        self.desc = _abi.ProcessDesc()
+        L.grb_get_desc(self._h, C.byref(self.desc))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GrbError(rc, lib().grb_last_error(self._h).decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            lib().grb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_eikonal(self, kt2, re, im):
+        kt2, re, im = (np.ascontiguousarray(a, dtype=np.float64) for a in (kt2, re, im))
+        self._check(lib().grb_set_eikonal(self._h, kt2.ctypes.data, re.ctypes.data, im.ctypes.data, len(kt2)))
+
+    def eval(self, u, tape, want_dump=False):
+        """Host numpy convenience: u [dim][n], tape [dtape][n] (SoA). Returns w, flags, dump."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        tape = np.ascontiguousarray(tape, dtype=np.float64)
+        dim, n = u.shape
+        dt = tape.shape[0]
+        w = np.zeros(n)
+        flags = np.zeros(n, dtype=np.uint8)
+        dump = np.zeros((_abi.GRB_DUMP_LEN, n)) if want_dump else None
+        self._check(lib().grb_eval(self._h, n, u.ctypes.data, dim, tape.ctypes.data if dt else None, dt,
+                                   w.ctypes.data, flags.ctypes.data, _ptr(dump)))
+        return w, flags, dump
+
+    def eval_raw(self, n, u, dim, tape, dtape, w, flags, dump=None):
+        """Pointer-level call (numpy arrays or torch CUDA tensors)."""
+        self._check(lib().grb_eval(self._h, n, _ptr(u), dim, _ptr(tape), dtape, _ptr(w), _ptr(flags), _ptr(dump)))
+
+    def vegas_iterate(self, xmat, first_call, ncalls, seed, iteration, mode=_abi.GRB_MODE_INTEGRATE, maxf=0.0):
+        xmat = np.ascontiguousarray(xmat, dtype=np.float64)
+        bins, dim = xmat.shape
+        acc = _abi.Accum()
+        self._check(lib().grb_vegas_iterate(self._h, xmat.ctypes.data, bins, dim, first_call, ncalls, seed,
+                                            iteration, mode, maxf, C.byref(acc)))
+        return acc
+
+    def vegas_iterate_async(self, xmat, first_call, ncalls, seed, iteration, mode=_abi.GRB_MODE_INTEGRATE, maxf=0.0):
+        xmat = np.ascontiguousarray(xmat, dtype=np.float64)
+        bins, dim = xmat.shape
+        p = C.c_void_p()
+        self._check(lib().grb_vegas_iterate_async(self._h, xmat.ctypes.data, bins, dim, first_call, ncalls, seed,
+                                                  iteration, mode, maxf, C.byref(p)))
+        return p.value
+
+    def vegas_fetch(self):
+        acc = _abi.Accum()
+        self._check(lib().grb_vegas_fetch(self._h, C.byref(acc)))
+        return acc
+
+    def sync(self):
+        self._check(lib().grb_sync(self._h))
+
+    def last_timing(self):
+        ms, nl = C.c_double(0), C.c_int(0)
+        lib().grb_last_timing(self._h, C.byref(ms), C.byref(nl))
+        return ms.value, nl.value

@@ -1,0 +1,49 @@
+"""Generates the golden vectors under tests/golden/ from the UNMODIFIED reference compiled in this
+container (oracle/_ref/gra/bin/ref_eval, built by oracle/build_ref.sh from /root/reference).
+
+Run here (where /root/reference exists):   python tests/golden/make_golden.py
+The vectors travel with the repo; nothing at test time reads /root/reference.
+
+Per case an .npz with: u [n][dim], tape [n][dtape] (the internal uniforms), and the reference's W, flags,
+t1, t2, s1, s2, m2, t_hat, u_hat, first helicity amplitudes, and kappa = the reference's own 1-ulp
+conditioning max_k |W(u +- ulp e_k) - W|/|W|."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from helpers import GOLDEN, have_ref, make_points, ref_eval, ref_msa  # noqa: E402
+
+# name, reference card (relative to the reference tree), process override, pomloop, n, dtape, adapted
+CASES = [
+    ("c2_alice_pipi_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 1536, 8, True),
+    ("c2_alice_pipi_con_born", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, True),
+    ("c2_alice_pipi_con_born_flat", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, False),
+    ("c1_test_pipi_con_born", "./input/test.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, True),
+    ("c2_alice_kk_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 768, 8, True),
+]
+
+
+def main():
+    if not have_ref():
+        raise SystemExit("oracle/_ref is not built (needs /root/reference): run oracle/build_ref.sh")
+    hdr, eik = ref_msa("./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-")
+    np.save(os.path.join(GOLDEN, "msa_pp_13000.npy"), np.stack([eik.x, eik.re, eik.im]))
+    only = sys.argv[1:]
+    for i, (name, card, proc, pom, n, dt, adapted) in enumerate(CASES):
+        if only and name not in only:
+            continue
+        u, tape = make_points(n, 6, dt, 1000 + i, adapted=adapted)
+        r = ref_eval(card, proc, pom, u, tape, kappa=True)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u,
+                            tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
+                            s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
+                            nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :7])
+        nz = r["W"] != 0
+        print(f"{name}: n={n} nonzero={nz.sum()} kappa median={np.median(r['kappa'][nz]):.3g} "
+              f"max={r['kappa'][nz].max():.3g}")
+
+
+if __name__ == "__main__":
+    main()

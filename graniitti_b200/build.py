@@ -20,14 +20,16 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    if not force and not _stale():
+def build_lib(force=False, verbose=False, out=None, extra=()):
+    """`out`/`extra` build an experimental variant next to the product library (profiling only)."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [
+    flags = [f for f in NVCC_FLAGS if not (extra and f.startswith("-fmad"))] + list(extra)
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + [
         os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -37,7 +37,9 @@ struct grb_engine {
   // scratch for host-pointer callers
   void * d_scratch     = nullptr;
   size_t scratch_bytes = 0;
-  // timing of the last call
+  // timing of the last call: ev0/ev1 bracket all launches, evk[] bracket each k_screen launch
+  std::vector<cudaEvent_t> evk;
+  int                      n_evk = 0;
   bool        timed = false;
   int         last_launches = 0;
   std::string err;
@@ -157,6 +159,15 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   return GRB_OK;
 }
 
+static cudaEvent_t next_event(grb_engine *e) {
+  if (e->n_evk >= (int)e->evk.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->evk.push_back(ev);
+  }
+  return e->evk[e->n_evk++];
+}
+
 static int ensure_constants(grb_engine *e) {
   if (g_const_owner != e) {
     CK(upload_proc(e->dproc, e->stream));
@@ -210,7 +221,7 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
   const char *env = getenv("GRB_CHUNK");
-  e->chunk        = env ? std::max<int64_t>(1024, atoll(env)) : (int64_t)1 << 21;
+  e->chunk        = env ? std::max<int64_t>(1024, atoll(env)) : (int64_t)1 << 23;
   if (desc->screening) {
     if ((ce = cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk)) != cudaSuccess) return fail("cudaMalloc items", ce);
     if ((ce = cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
@@ -253,6 +264,7 @@ void grb_destroy(grb_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_count);
   cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch);
+  for (auto ev : e->evk) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -356,6 +368,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
   int rc = ensure_constants(e);
   if (rc != GRB_OK) return rc;
   e->last_launches = 0;
+  e->n_evk = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   for (int64_t off = 0; off < n; off += e->chunk) {
     PointArgs a;
@@ -368,7 +381,11 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
-    if (e->desc.screening) e->last_launches += launch_screen(a, e->sm_count, e->stream);
+    if (e->desc.screening) {
+      CK(cudaEventRecord(next_event(e), e->stream));
+      e->last_launches += launch_screen(a, e->sm_count, e->stream);
+      CK(cudaEventRecord(next_event(e), e->stream));
+    }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   e->timed = true;
@@ -394,6 +411,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
   CK(cudaMemcpyAsync(e->d_xmat, xmat, sizeof(double) * bins * dim, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemsetAsync(e->d_acc, 0, sizeof(grb_accum), e->stream));
   e->last_launches = 0;
+  e->n_evk = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
   for (int64_t off = 0; off < ncalls; off += e->chunk) {
     PointArgs a;
@@ -406,7 +424,11 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
-    if (e->desc.screening) e->last_launches += launch_screen(a, e->sm_count, e->stream);
+    if (e->desc.screening) {
+      CK(cudaEventRecord(next_event(e), e->stream));
+      e->last_launches += launch_screen(a, e->sm_count, e->stream);
+      CK(cudaEventRecord(next_event(e), e->stream));
+    }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   e->timed = true;
@@ -524,6 +546,26 @@ int grb_last_timing(const grb_engine *e, double *kernel_ms, int *n_launches) {
     }
   }
   if (n_launches) *n_launches = e->last_launches;
+  return GRB_OK;
+}
+
+void *grb_get_stream(grb_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int grb_last_timing_kernels(const grb_engine *e, double *ms_total, double *ms_screen, int *n_screen_launches) {
+  if (!e) return GRB_ERR_ARG;
+  double tot = 0.0, scr = 0.0;
+  if (e->timed) {
+    cudaSetDevice(e->device);
+    if (cudaEventSynchronize(e->ev1) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) tot = ms;
+      for (int i = 0; i + 1 < e->n_evk; i += 2)
+        if (cudaEventElapsedTime(&ms, e->evk[i], e->evk[i + 1]) == cudaSuccess) scr += ms;
+    }
+  }
+  if (ms_total) *ms_total = tot;
+  if (ms_screen) *ms_screen = scr;
+  if (n_screen_launches) *n_screen_launches = e->n_evk / 2;
   return GRB_OK;
 }
 

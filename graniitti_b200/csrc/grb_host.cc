@@ -1,6 +1,590 @@
+// grb_host.cc -- host-side (C++) mirror of the reference's steering interface for the hot path.
+//
+// The reference keeps its JSON steering card, the process mini-language
+//     ISTATE[CHANNEL]<class> -> final > {daughters} @CMD[target]{k:v}
+// and the model tune directory (reference src/MGraniitti.cc:317-963, src/MProcess.cc:380-468,1732-1853,
+// src/MPDG.cc:20-560, src/MRegge.cc:984-1033, src/MForm.cc:71-209).  This file reads exactly those inputs
+// and flattens them into the POD grb_process_desc that crosses the C ABI, so a steering card written for
+// `gr` drives the device engine unchanged.  Names, argument meaning and error behaviour follow the
+// reference (std::invalid_argument there -> GRB_ERR_* + message here).
 #include "grb_host.h"
+
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
-extern "C" int grb_parse_card(const char *, const char *, int, const char *, grb_process_desc *, char *errbuf, int n) {
-  if (errbuf && n > 0) snprintf(errbuf, n, "card parser not built yet");
-  return GRB_ERR_UNSUPPORTED;
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "grb_builtin_data.h"
+#include "grb_json5.h"
+
+namespace grbhost {
+
+struct Unsupported : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+static std::string read_file(const std::string &path) {
+  std::ifstream f(path);
+  if (!f.is_open()) throw std::invalid_argument("cannot open " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+static std::string trim(const std::string &s) {
+  size_t a = 0, b = s.size();
+  while (a < b && isspace((unsigned char)s[a])) ++a;
+  while (b > a && isspace((unsigned char)s[b - 1])) --b;
+  return s.substr(a, b - a);
+}
+
+static std::vector<std::string> split(const std::string &s, char sep) {
+  std::vector<std::string> out;
+  std::string              cur;
+  for (char c : s) {
+    if (c == sep) {
+      out.push_back(cur);
+      cur.clear();
+    } else {
+      cur += c;
+    }
+  }
+  out.push_back(cur);
+  return out;
+}
+
+// ---- particle table (reference src/MPDG.cc:20-440 ReadParticleData) --------------------------------------
+struct Particle {
+  int         pdg = 0, spinX2 = 0, chargeX3 = 0;
+  double      mass = 0.0, width = 0.0;
+  std::string name;
+};
+
+class ParticleTable {
+ public:
+  void add_entry(const std::vector<int> &ids, double mass, double width, const std::string &name,
+                 const std::vector<int> &charges) {
+    for (size_t k = 0; k < ids.size() && k < charges.size(); ++k) {
+      Particle p;
+      p.pdg = ids[k]; p.mass = mass; p.width = width; p.chargeX3 = charges[k]; p.name = name;
+      p.spinX2 = (p.pdg % 10) - 1;
+      const bool quark_or_nu = (p.pdg >= 1 && p.pdg <= 6) || p.pdg == 12 || p.pdg == 14 || p.pdg == 16;
+      if (p.chargeX3 == 0 && p.pdg > 100) {
+        p.name = name + "0";
+      } else if (p.chargeX3 != 0 && !quark_or_nu) {
+        p.name = name + std::string(std::abs(p.chargeX3 / 3), p.chargeX3 > 0 ? '+' : '-');
+      }
+      if (p.pdg == 21 || p.pdg == 22 || std::abs(p.pdg) == 24 || p.pdg == 23) p.spinX2 = 2;
+      if (p.pdg == 25) p.spinX2 = 0;
+      if (p.pdg >= 1 && p.pdg <= 16 && p.pdg != 9 && p.pdg != 10) p.spinX2 = 1;  // SM fermions
+      tab[p.pdg] = p;
+      const bool fermion = (p.spinX2 % 2) != 0;
+      if ((fermion && ids.size() < 3) || (p.chargeX3 != 0 && ids.size() < 3)) {
+        Particle a = p;
+        if (quark_or_nu) a.name = name + "~";
+        else if (p.chargeX3 != 0) a.name = name + std::string(std::abs(p.chargeX3 / 3), p.chargeX3 > 0 ? '-' : '+');
+        else a.name = name + "0~";
+        a.pdg = -p.pdg;
+        a.chargeX3 = -p.chargeX3;
+        tab[a.pdg] = a;
+      }
+    }
+  }
+  static std::vector<int> parse_charges(const std::string &s) {
+    std::vector<int> q;
+    for (auto &t : split(s, ',')) {
+      const std::string c = trim(t);
+      if (c.find("++") != std::string::npos) q.push_back(6);
+      else if (c.find("--") != std::string::npos) q.push_back(-6);
+      else if (c.find("-1/3") != std::string::npos) q.push_back(-1);
+      else if (c.find("+2/3") != std::string::npos) q.push_back(2);
+      else if (c.find("+") != std::string::npos) q.push_back(3);
+      else if (c.find("-") != std::string::npos) q.push_back(-3);
+      else if (c.find("0") != std::string::npos) q.push_back(0);
+    }
+    return q;
+  }
+  void load_builtin() {
+    for (auto &b : kBuiltinPDG) {
+      std::vector<int> ids = {b.pdg};
+      if (b.pdg2) ids.push_back(b.pdg2);
+      add_entry(ids, b.mass, b.width, b.name, parse_charges(b.charges));
+    }
+  }
+  // PDG "mass_width" fixed-column format: ids in columns 1-32, mass 34-51, width 71-88, name+charges 108-128
+  void load_mcd(const std::string &path) {
+    std::ifstream f(path);
+    if (!f.is_open()) throw std::invalid_argument("cannot open PDG table " + path);
+    std::string line;
+    while (std::getline(f, line)) {
+      if (line.empty() || line[0] == '*') continue;
+      if (line.size() < 108) line.resize(128, ' ');
+      std::vector<int>   ids;
+      std::istringstream si(line.substr(0, 32));
+      int                v;
+      while (si >> v)
+        if (v != 0) ids.push_back(v);
+      if (ids.empty()) continue;
+      double             mass = 0.0, width = 0.0;
+      std::istringstream sm(line.substr(33, 18)), sw(line.substr(70, 18));
+      sm >> mass;
+      sw >> width;
+      std::istringstream sn(line.substr(107));
+      std::string        name, rest;
+      sn >> name;
+      std::getline(sn, rest);
+      add_entry(ids, mass, width, name, parse_charges(rest));
+    }
+  }
+  const Particle &by_name(const std::string &n) const {
+    for (auto &kv : tab)
+      if (kv.second.name == n) return kv.second;
+    throw std::invalid_argument("MPDG::FindByPDGName: Unknown particle name: " + n);
+  }
+  const Particle &by_pdg(int pdg) const {
+    auto it = tab.find(pdg);
+    if (it == tab.end()) throw std::invalid_argument("MPDG::FindByPDG: Unknown PDG ID: " + std::to_string(pdg));
+    return it->second;
+  }
+  std::map<int, Particle> tab;
+};
+
+// ---- @ command blocks (reference src/MAux.cc:690-811 SplitCommands) -----------------------------------------
+struct OneCmd {
+  std::string                        id;
+  std::vector<std::string>           target;
+  std::map<std::string, std::string> arg;
+};
+
+static std::vector<OneCmd> split_commands(const std::string &full) {
+  std::vector<OneCmd> out;
+  size_t              pos = full.find('@');
+  while (pos != std::string::npos) {
+    const size_t next = full.find('@', pos + 1);
+    std::string  sub  = trim(full.substr(pos + 1, next == std::string::npos ? std::string::npos : next - pos - 1));
+    OneCmd       c;
+    const size_t l = sub.find('['), r = sub.find(']');
+    if ((l == std::string::npos) != (r == std::string::npos))
+      throw std::invalid_argument("SplitCommands: Incomplete @R[]{} syntax with missing [ or ]");
+    if (l != std::string::npos) {
+      const std::string t = sub.substr(l + 1, r - l - 1);
+      if (!t.empty())
+        for (auto &x : split(t, ',')) c.target.push_back(trim(x));
+      sub.erase(l, r - l + 1);
+    }
+    const size_t L = sub.find('{'), R = sub.find('}');
+    if ((L == std::string::npos) != (R == std::string::npos))
+      throw std::invalid_argument("SplitCommands: Incomplete @R[]{} syntax with missing { or }");
+    if (L == std::string::npos) {
+      auto strip = split(sub, ':');
+      c.id       = trim(strip[0]);
+      if (strip.size() == 1) c.arg["_SINGLET_"] = "true";
+      else if (strip.size() == 2) c.arg["_SINGLET_"] = trim(strip[1]);
+      else throw std::invalid_argument("gra::SplitCommands: @Syntax invalid with '" + sub + "'");
+    } else {
+      c.id = trim(sub.substr(0, L));
+      for (auto &kv : split(sub.substr(L + 1, R - L - 1), ',')) {
+        auto strip = split(kv, ':');
+        if (strip.size() != 2) throw std::invalid_argument("gra::SplitCommands: @Syntax not good with brackets {" + kv + "}");
+        c.arg[trim(strip[0])] = trim(strip[1]);
+      }
+    }
+    out.push_back(c);
+    pos = next;
+  }
+  return out;
+}
+
+// ---- decay string -> flattened tree (reference src/MPDG.cc:446-532 TokenizeProcess) -------------------------
+struct Branch {
+  Particle            p;
+  std::vector<Branch> legs;
+};
+
+static std::vector<std::string> words(const std::string &s) {
+  std::vector<std::string> w;
+  std::istringstream       ss(s);
+  std::string              t;
+  while (ss >> t) w.push_back(t);
+  return w;
+}
+
+static void tokenize(const std::string &str, const ParticleTable &pdg, std::vector<Branch> &out) {
+  size_t i = 0, start = 0;
+  while (i < str.size()) {
+    if (str[i] == '>') {
+      // particles before '>' : the last one is the mother
+      for (auto &w : words(str.substr(start, i - start))) {
+        Branch b;
+        b.p = pdg.by_name(w);
+        out.push_back(b);
+      }
+      if (out.empty()) throw std::invalid_argument("decay arrow '>' without a mother particle");
+      // matching braces
+      size_t a = str.find('{', i);
+      if (a == std::string::npos) throw std::invalid_argument("decay arrow '>' without { }");
+      int    depth = 0;
+      size_t b     = a;
+      for (; b < str.size(); ++b) {
+        if (str[b] == '{') ++depth;
+        if (str[b] == '}' && --depth == 0) break;
+      }
+      if (b >= str.size()) throw std::invalid_argument("unbalanced { } in the decay string");
+      tokenize(str.substr(a + 1, b - a - 1), pdg, out.back().legs);
+      i = start = b + 1;
+    } else {
+      ++i;
+    }
+  }
+  for (auto &w : words(str.substr(start))) {
+    Branch b;
+    b.p = pdg.by_name(w);
+    out.push_back(b);
+  }
+}
+
+// breadth-first flattening: first-level legs at [0, n_legs), daughters of one mother contiguous
+static void flatten(const std::vector<Branch> &legs, grb_process_desc &d) {
+  struct Q {
+    const Branch *b;
+    int           idx;
+  };
+  std::vector<Q> queue;
+  int            n = 0;
+  auto put = [&](const Branch &b, int parent) {
+    if (n >= GRB_MAX_NODES) throw Unsupported("decay tree exceeds GRB_MAX_NODES");
+    grb_node &o = d.nodes[n];
+    o.pdg = b.p.pdg; o.spinX2 = b.p.spinX2; o.parent = parent; o.first_child = -1;
+    o.n_children = (int)b.legs.size(); o.mass = b.p.mass; o.width = b.p.width;
+    queue.push_back({&b, n});
+    return n++;
+  };
+  for (auto &b : legs) put(b, -1);
+  for (size_t q = 0; q < queue.size(); ++q) {
+    const Branch *b = queue[q].b;
+    const int     i = queue[q].idx;
+    if (!b->legs.empty()) {
+      d.nodes[i].first_child = n;
+      for (auto &c : b->legs) put(c, i);
+    }
+  }
+  d.n_nodes = n;
+  d.n_legs  = (int)legs.size();
+  d.n_final = 0;
+  for (int i = 0; i < n; ++i)
+    if (d.nodes[i].n_children == 0) ++d.n_final;
+}
+
+static double factorial(int n) {
+  double f = 1.0;
+  for (int i = 2; i <= n; ++i) f *= i;
+  return f;
+}
+
+static void range2(const Json &j, const char *what, double &lo, double &hi) {
+  auto v = j.as_vec();
+  if (v.size() != 2) throw std::invalid_argument(std::string(what) + ": expected [min, max]");
+  if (v[0] > v[1]) throw std::invalid_argument(std::string(what) + ": min > max");
+  lo = v[0];
+  hi = v[1];
+}
+
+// ---- the flattening proper ---------------------------------------------------------------------------------
+static void parse_card_impl(const std::string &card_path, const char *process_override, int pomloop_override,
+                            const char *base, grb_process_desc &d) {
+  memset(&d, 0, sizeof(d));
+  d.abi_version = GRB_ABI_VERSION;
+  const Json card = parse_json5(read_file(card_path));
+
+  // GENERALPARAM (reference MGraniitti::ReadGeneralParam, src/MGraniitti.cc:332-358)
+  const Json &      gen        = card.at("GENERALPARAM");
+  const std::string modelparam = gen.at("MODELPARAM").as_str();
+
+  // model tune + particle table
+  ParticleTable pdg;
+  Json          tune;
+  if (base && base[0]) {
+    pdg.load_mcd(std::string(base) + "/modeldata/mass_width_2018.mcd");
+    tune = parse_json5(read_file(std::string(base) + "/modeldata/" + modelparam + "/GENERAL.json"));
+  } else {
+    if (modelparam != "TUNE0") throw Unsupported("built-in model data holds TUNE0 only; pass the GRANIITTI base directory for MODELPARAM=" + modelparam);
+    pdg.load_builtin();
+    tune = parse_json5(kBuiltinTune0);
+  }
+
+  // PROCESSPARAM (reference MGraniitti::ReadProcessParam, src/MGraniitti.cc:375-609)
+  const Json &pp   = card.at("PROCESSPARAM");
+  std::string full = (process_override && process_override[0] && std::string(process_override) != "null")
+                         ? std::string(process_override)
+                         : pp.at("PROCESS").as_str();
+  std::vector<OneCmd> syntax;
+  const size_t        at = full.find('@');
+  if (at != std::string::npos) {
+    syntax = split_commands(full.substr(at));
+    full   = full.substr(0, at);
+  }
+  std::string  process_part, decay_part;
+  const size_t p1 = full.find("->"), p2 = full.find("&>");
+  const size_t pa = (p1 != std::string::npos) ? p1 : p2;
+  if (pa != std::string::npos) {
+    process_part = trim(full.substr(0, pa));
+    decay_part   = trim(full.substr(pa + 2));
+  } else {
+    process_part = trim(full);
+  }
+  d.ps_active = (p1 == std::string::npos && p2 != std::string::npos) ? 0 : 1;  // SetISOLATE, MProcess.h:100
+
+  // @PDG[id]{M:..,W:..} overrides (reference MProcess::SetProcess, src/MProcess.cc:1740-1790)
+  for (auto &c : syntax)
+    if (c.id == "PDG") {
+      if (c.target.size() != 1) throw std::invalid_argument("@Syntax error: invalid PDG[] target");
+      const int id = std::stoi(c.target[0]);
+      pdg.by_pdg(id);
+      for (auto &kv : c.arg) {
+        if (kv.first == "M") { pdg.tab[id].mass = std::stod(kv.second); if (pdg.tab.count(-id)) pdg.tab[-id].mass = pdg.tab[id].mass; }
+        if (kv.first == "W") { pdg.tab[id].width = std::stod(kv.second); if (pdg.tab.count(-id)) pdg.tab[-id].width = pdg.tab[id].width; }
+      }
+    }
+
+  // "PP[CON]<F>" -> istate, channel, class (reference MProcess::ParseCMD, src/MProcess.cc:1817-1850)
+  std::string ps = process_part;
+  ps.erase(std::remove(ps.begin(), ps.end(), ' '), ps.end());
+  const size_t lb = ps.find('['), rb = ps.find(']'), la = ps.find('<'), ra = ps.find('>');
+  if (lb == std::string::npos || rb == std::string::npos || la == std::string::npos || ra == std::string::npos)
+    throw std::invalid_argument("MProcess::SetProcess: Unknown PROCESS: " + ps);
+  const std::string istate = ps.substr(0, lb), channel = ps.substr(lb + 1, rb - lb - 1), cls = ps.substr(la + 1, ra - la - 1);
+  if (cls == "F") d.ps_class = GRB_CLASS_F;
+  else if (cls == "C") throw Unsupported("phase-space class <C> (MContinuum) is not on the device path yet");
+  else throw Unsupported("phase-space class <" + cls + "> is outside the hot-path scope");
+  const std::string key = istate + "[" + channel + "]";
+  static const std::map<std::string, int> registry = {
+      {"yy[CON]", GRB_PROC_YY_CON}, {"yy[QED]", GRB_PROC_YY_QED}, {"PP[RES]", GRB_PROC_PP_RES},
+      {"PP[CONTENSOR]", GRB_PROC_PP_CONTENSOR}, {"PP[CON]", GRB_PROC_PP_CON}, {"PP[CON-]", GRB_PROC_PP_CON_MINUS},
+      {"PP[RES+CON]", GRB_PROC_PP_RES_CON}};
+  auto it = registry.find(key);
+  if (it == registry.end()) throw Unsupported("MSubProc: process " + key + "<" + cls + "> is outside the hot-path scope");
+  d.proc = it->second;
+
+  d.screening  = (pomloop_override >= 0) ? (pomloop_override != 0) : pp.at("POMLOOP").as_bool();
+  d.excitation = pp.at("NSTARS").as_int();
+  if (d.excitation < 0 || d.excitation > 2) throw std::invalid_argument("MProcess::SetExcitation: Not valid input (0,1,2)");
+
+  // decay mode (reference MProcess::SetDecayMode, src/MProcess.cc:380-437)
+  {
+    int L = 0, R = 0, arrows = 0;
+    for (char c : decay_part) { L += c == '{'; R += c == '}'; arrows += c == '>'; }
+    if (L != R) throw std::invalid_argument("MProces::SetDecayMode: ERROR: Decay tree has unbalanced { } brackets");
+    if (arrows != L) throw std::invalid_argument("MProces::SetDecayMode: ERROR: Decay tree syntax with arrows > not equal to { } brackets!");
+  }
+  std::vector<Branch> tree;
+  tokenize(decay_part, pdg, tree);
+  flatten(tree, d);
+  // symmetry factor over identical first-level legs (reference CalculateSymmetryFactor, MProcess.cc:449-468)
+  {
+    d.S_factor = 1.0;
+    std::vector<bool> marked(tree.size(), false);
+    for (size_t i = 0; i < tree.size(); ++i) {
+      int n = 1;
+      marked[i] = true;
+      for (size_t j = 0; j < tree.size(); ++j)
+        if (i != j && tree[i].p.pdg == tree[j].p.pdg && !marked[j]) { marked[j] = true; ++n; }
+      d.S_factor *= factorial(n);
+    }
+  }
+
+  // command syntax (reference src/MGraniitti.cc:585-596)
+  d.offshell = 5.0;  // MProcess.h OFFSHELL default
+  for (auto &c : syntax) {
+    if (c.id == "FLATAMP") d.flatamp = std::stoi(c.arg["_SINGLET_"]);
+    else if (c.id == "FLATMASS2") d.flatmass2 = c.arg["_SINGLET_"] == "true";
+    else if (c.id == "OFFSHELL") d.offshell = std::stod(c.arg["_SINGLET_"]);
+    else if (c.id == "PDG" || c.id == "RES" || c.id == "R" || c.id == "SPINGEN" || c.id == "SPINDEC" || c.id == "FRAME" || c.id == "JMAX") {}
+    else throw std::invalid_argument("unknown @ command: " + c.id);
+  }
+
+  // beams (reference MProcess::SetInitialState/SetBeamEnergies, src/MProcess.cc:291-334)
+  {
+    const Json &beam = pp.at("BEAM"), &energy = pp.at("ENERGY");
+    if (beam.arr.size() != 2 || energy.arr.size() != 2) throw std::invalid_argument("MProcess::SetInitialState: Input BEAM/ENERGY vector not dim 2!");
+    const Particle &b1 = pdg.by_name(beam.arr[0].as_str()), &b2 = pdg.by_name(beam.arr[1].as_str());
+    const double E1 = std::max(energy.arr[0].as_num(), 1.001 * b1.mass), E2 = std::max(energy.arr[1].as_num(), 1.001 * b2.mass);
+    auto msq = [](double x) { return std::sqrt(std::max(0.0, x)); };
+    d.beam1_mass = b1.mass; d.beam2_mass = b2.mass;
+    d.pbeam1_pz = msq(E1 * E1 - b1.mass * b1.mass); d.pbeam1_E = E1;
+    d.pbeam2_pz = -msq(E2 * E2 - b2.mass * b2.mass); d.pbeam2_E = E2;
+    // s = (pbeam1 + pbeam2).M2(), reference M4Vec.h:123,139
+    const double sz = d.pbeam1_pz + d.pbeam2_pz, se = d.pbeam1_E + d.pbeam2_E;
+    d.s      = se * se - (0.0 * 0.0 + 0.0 * 0.0 + sz * sz);
+    d.sqrt_s = msq(d.s);
+    if (d.sqrt_s < b1.mass + b2.mass) throw std::invalid_argument("MProcess::SetBeamEnergies: Error with input CMS energy");
+  }
+
+  // INTEGRALPARAM: loop discretisation (reference src/MGraniitti.cc:610-628, MEikonal.h:44-51)
+  {
+    const int ND = card.at("INTEGRALPARAM").at("POMLOOP").at("ND").as_int();
+    if (ND < -10 || ND > 10) throw std::invalid_argument("POMLOOP::ND out of range [-10, 10]");
+    d.loop_nkt    = std::max(3, 3 * ND + 15);
+    d.loop_nphi   = std::max(3, 3 * ND + 12);
+    d.loop_min_kt = 1E-4;
+    d.loop_max_kt = 1.75;
+  }
+
+  // GENCUTS (reference MGraniitti::ReadGenCuts, src/MGraniitti.cc:673-823) + SetTechnicalBoundaries
+  {
+    grb_gencut &g = d.gcuts;
+    g.forward_pt_min = -1.0; g.forward_pt_max = -1.0; g.XI_min = 0.0; g.XI_max = 0.05;
+    const Json &gc = card.at("GENCUTS");
+    if (!gc.has("<F>") || !gc.at("<F>").has("Rap") || !gc.at("<F>").has("M"))
+      throw std::invalid_argument("MGraniitti::ReadGenCuts: <F> phase space class requires from user: \"GENCUTS\" : { \"<F>\" : { \"Rap\" : [min, max], \"M\" : [min, max] }}");
+    const Json &F = gc.at("<F>");
+    range2(F.at("Rap"), "GENCUTS::<F>::Rap", g.Y_min, g.Y_max);
+    range2(F.at("M"), "GENCUTS::<F>::M", g.M_min, g.M_max);
+    if (F.has("Pt")) range2(F.at("Pt"), "GENCUTS::<F>::Pt", g.forward_pt_min, g.forward_pt_max);
+    if (F.has("Xi")) range2(F.at("Xi"), "GENCUTS::<F>::Xi", g.XI_min, g.XI_max);
+    if (g.forward_pt_min < 0.0) g.forward_pt_min = 0.0;                                       // MProcess.cc:1369-1386
+    if (g.forward_pt_max < 0.0) g.forward_pt_max = d.excitation == 0 ? 2.5 : (d.excitation == 1 ? 50.0 : 100.0);
+  }
+  d.lipsdim = 5 + 1 + d.excitation;  // MFactorized.cc:69-78
+
+  // FIDCUTS (reference MGraniitti::ReadFidCuts, src/MGraniitti.cc:826-907); defaults of gra::FIDCUT
+  {
+    grb_fidcut &f = d.fcuts;
+    f.active = 0; f.usercuts = 0;
+    if (card.has("FIDCUTS") && card.at("FIDCUTS").has("active")) {
+      const Json &fc = card.at("FIDCUTS");
+      f.active = fc.at("active").as_bool();
+      const Json &P = fc.at("PARTICLE"), &S = fc.at("SYSTEM"), &W = fc.at("FORWARD");
+      range2(P.at("Eta"), "FIDCUTS::PARTICLE::Eta", f.eta_min, f.eta_max);
+      range2(P.at("Rap"), "FIDCUTS::PARTICLE::Rap", f.rap_min, f.rap_max);
+      range2(P.at("Pt"), "FIDCUTS::PARTICLE::Pt", f.pt_min, f.pt_max);
+      range2(P.at("Et"), "FIDCUTS::PARTICLE::Et", f.Et_min, f.Et_max);
+      range2(S.at("M"), "FIDCUTS::SYSTEM::M", f.M_min, f.M_max);
+      range2(S.at("Rap"), "FIDCUTS::SYSTEM::Rap", f.Y_min, f.Y_max);
+      range2(S.at("Pt"), "FIDCUTS::SYSTEM::Pt", f.Pt_min, f.Pt_max);
+      range2(W.at("t"), "FIDCUTS::FORWARD::t", f.forward_t_min, f.forward_t_max);
+      range2(W.at("M"), "FIDCUTS::FORWARD::M", f.forward_M_min, f.forward_M_max);
+      const Json &uc = fc.at("USERCUTS");
+      f.usercuts = (uc.type == Json::BOOL) ? (uc.b ? 1 : 0) : uc.as_int();
+    }
+  }
+
+  // VETOCUTS (reference MGraniitti::ReadVetoCuts, src/MGraniitti.cc:910-963)
+  if (card.has("VETOCUTS") && card.at("VETOCUTS").has("active")) {
+    const Json &vc = card.at("VETOCUTS");
+    d.veto_active  = vc.at("active").as_bool();
+    for (int i = 0; i < 100; ++i) {
+      const std::string k = std::to_string(i);
+      if (!vc.has(k) || !vc.at(k).has("Eta") || !vc.at(k).has("Pt")) break;
+      if (d.n_veto >= GRB_MAX_VETO) throw Unsupported("more veto domains than GRB_MAX_VETO");
+      grb_vetodomain &v = d.veto[d.n_veto++];
+      range2(vc.at(k).at("Eta"), "VETOCUTS::Eta", v.eta_min, v.eta_max);
+      range2(vc.at(k).at("Pt"), "VETOCUTS::Pt", v.pt_min, v.pt_max);
+    }
+  }
+
+  // model parameters: PARAM_SOFT (src/MForm.cc:110-135), PARAM_FLAT, PARAM_STRUCTURE
+  {
+    const Json &S = tune.at("PARAM_SOFT");
+    grb_param_soft &o = d.soft;
+    o.DELTA_P = S.at("DELTA_P").as_num(); o.ALPHA_P = S.at("ALPHA_P").as_num();
+    o.gN_P = S.at("gN_P").as_num(); o.gN_O = S.at("gN_O").as_num();
+    o.g3P = S.at("g3P").as_num() * o.gN_P;  // convention: file holds g3P/gN_P (MForm.cc:122)
+    o.gamma = S.at("gamma").as_num();
+    o.fc1 = S.at("fc1").as_num(); o.fc2 = S.at("fc2").as_num(); o.fc3 = S.at("fc3").as_num();
+    o.odderon_on = S.at("ODDERON_ON").as_bool();
+    d.flat_b = tune.at("PARAM_FLAT").at("b").as_num();
+    const Json &T = tune.at("PARAM_STRUCTURE");
+    const std::string em = T.at("EM").as_str(), qa = T.at("QED_alpha").as_str();
+    d.em_ff     = (em == "KELLY") ? 1 : 0;
+    d.qed_alpha = (qa == "ZERO") ? 0 : 1;
+  }
+  // PARAM_REGGE + per-particle couplings chosen by the first leg (src/MRegge.cc:984-1033)
+  {
+    const Json &R = tune.at("PARAM_REGGE");
+    grb_param_regge &o = d.regge;
+    auto a0 = R.at("a0").as_vec(), ap = R.at("ap").as_vec(), sg = R.at("sgn").as_vec();
+    if (a0.size() != 3 || ap.size() != 3 || sg.size() != 3) throw std::invalid_argument("REGGE_PARAM::ReadParameters: expected 3 trajectories");
+    for (int k = 0; k < 3; ++k) { o.a0[k] = a0[k]; o.ap[k] = ap[k]; o.sgn[k] = sg[k]; }
+    o.s0 = R.at("s0").as_num(); o.offshellFF = R.at("offshellFF").as_int(); o.reggeize = R.at("reggeize").as_bool();
+    o.b_EXP = R.at("b_EXP").as_num(); o.a_OREAR = R.at("a_OREAR").as_num(); o.b_OREAR = R.at("b_OREAR").as_num();
+    o.b_POW = R.at("b_POW").as_num(); o.omega = R.at("omega").as_num();
+    const int apdg = d.n_legs > 0 ? std::abs(d.nodes[0].pdg) : 0;
+    const char *blk = "PARAM_X";
+    if (apdg == 211 || apdg == 111) blk = "PARAM_PI";
+    else if (apdg == 321 || apdg == 311) blk = "PARAM_K";
+    else if (apdg == 2212 || apdg == 2112) blk = "PARAM_P";
+    else if (apdg == 113 || apdg == 213) blk = "PARAM_RHO";
+    else if (apdg == 331) blk = "PARAM_PHI";  // (sic) the reference keys phi(1020) couplings on 331
+    else if (apdg == 9000221) blk = "PARAM_F0500";
+    auto c = tune.at(blk).at("c").as_vec();
+    const Json &n = tune.at(blk).at("n");
+    for (int k = 0; k < 3; ++k) { o.c[k] = c[k]; o.n[k] = n.arr[k].as_bool(); }
+  }
+  {
+    const Json &T = tune.at("PARAM_TENSORPOM");
+    grb_param_tensorpom &o = d.tpom;
+    o.delta_P = T.at("delta_P").as_num(); o.delta_O = T.at("delta_O").as_num();
+    o.delta_1R = T.at("delta_1R").as_num(); o.delta_2R = T.at("delta_2R").as_num();
+    o.ap_P = T.at("ap_P").as_num(); o.ap_O = T.at("ap_O").as_num(); o.ap_1R = T.at("ap_1R").as_num(); o.ap_2R = T.at("ap_2R").as_num();
+    o.eta_O = T.at("eta_O").as_num(); o.gPNN = T.at("gPNN").as_num(); o.gPpipi = T.at("gPpipi").as_num(); o.gPKK = T.at("gPKK").as_num();
+    auto rr = T.at("gPrhorho").as_vec(), ff = T.at("gPphiphi").as_vec();
+    o.gPrhorho[0] = rr[0]; o.gPrhorho[1] = rr[1]; o.gPphiphi[0] = ff[0]; o.gPphiphi[1] = ff[1];
+    o.M_O = T.at("M_O").as_num(); o.M_1R = T.at("M_1R").as_num();
+  }
+
+  if (d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON)
+    throw Unsupported("resonance processes (PP[RES], PP[RES+CON]) are not on the device path yet");
+
+  // internal uniforms consumed per point when no rejection loop repeats (for sizing tapes)
+  {
+    int nt = 0;
+    auto bw = [&](int i) { return d.nodes[i].width < 1e-40 ? 0 : 1; };
+    auto offshell_draws = [&](int i) {
+      if (!bw(i)) return 0;
+      int k = 1;
+      for (int c = 0; c < d.nodes[i].n_children; ++c) k += bw(d.nodes[i].first_child + c);
+      return k;
+    };
+    for (int i = 0; i < d.n_legs; ++i) nt += offshell_draws(i);
+    nt += 2;
+    for (int i = 0; i < d.n_nodes; ++i)
+      if (d.nodes[i].n_children) {
+        for (int c = 0; c < d.nodes[i].n_children; ++c) nt += offshell_draws(d.nodes[i].first_child + c);
+        nt += 2;
+      }
+    d.n_tape = nt;
+  }
+}
+
+}  // namespace grbhost
+
+extern "C" int grb_parse_card(const char *card_path, const char *process_override, int pomloop_override,
+                              const char *graniitti_base, grb_process_desc *out, char *errbuf, int errbuf_len) {
+  auto seterr = [&](const std::string &m) {
+    if (errbuf && errbuf_len > 0) snprintf(errbuf, errbuf_len, "%s", m.c_str());
+  };
+  if (!card_path || !out) {
+    seterr("null argument");
+    return GRB_ERR_ARG;
+  }
+  try {
+    grbhost::parse_card_impl(card_path, process_override, pomloop_override, graniitti_base, *out);
+  } catch (const grbhost::Unsupported &e) {
+    seterr(e.what());
+    return GRB_ERR_UNSUPPORTED;
+  } catch (const std::invalid_argument &e) {
+    seterr(e.what());
+    return GRB_ERR_PARSE;
+  } catch (const std::exception &e) {
+    seterr(e.what());
+    return GRB_ERR_PARSE;
+  }
+  seterr("");
+  return GRB_OK;
 }

@@ -13,6 +13,8 @@
 // memory per block and are flushed once at block exit.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "grb_point.cuh"
 
 namespace grb {
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
   if (VEGAS) hist_flush(nb, dim, a.acc);
 }
 
-template <bool VEGAS>
-__global__ void __launch_bounds__(128) k_screen(const PointArgs a) {
+template <bool VEGAS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
   const int      nb  = a.bins * dim;
@@ -325,12 +327,26 @@ int launch_points(const PointArgs &a, int n_nodes, int sm_count, cudaStream_t st
   return 1;
 }
 
-int launch_screen(const PointArgs &a, int sm_count, cudaStream_t st) {
+template <int MINB>
+static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
   const int    threads = 128;
-  const int    blocks  = sm_count * 4;
+  const int    blocks  = sm_count * MINB;  // persistent: exactly the resident CTAs
   const size_t smem    = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
-  if (a.vegas) k_screen<true><<<blocks, threads, smem, st>>>(a);
-  else k_screen<false><<<blocks, threads, 0, st>>>(a);
+  if (a.vegas) k_screen<true, MINB><<<blocks, threads, smem, st>>>(a);
+  else k_screen<false, MINB><<<blocks, threads, 0, st>>>(a);
+}
+
+int launch_screen(const PointArgs &a, int sm_count, cudaStream_t st) {
+  static const int minb = [] {
+    const char *e = getenv("GRB_SCREEN_MINB");
+    return e ? atoi(e) : 4;
+  }();
+  switch (minb) {
+    case 3: launch_screen_t<3>(a, sm_count, st); break;
+    case 5: launch_screen_t<5>(a, sm_count, st); break;
+    case 6: launch_screen_t<6>(a, sm_count, st); break;
+    default: launch_screen_t<4>(a, sm_count, st); break;
+  }
   return 1;
 }
 

@@ -7,7 +7,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libgrb.so")
+_LIB_PATH = os.environ.get("GRB_LIB", os.path.join(_HERE, "libgrb.so"))  # GRB_LIB: experimental builds only
 _lib = None
 
 
@@ -69,6 +69,10 @@ def lib():
         L.grb_measure_dfma_peak.argtypes = [cint, C.POINTER(dbl)]
         L.grb_last_timing.restype = cint
         L.grb_last_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(cint)]
+        L.grb_get_stream.restype = vp
+        L.grb_get_stream.argtypes = [vp]
+        L.grb_last_timing_kernels.restype = cint
+        L.grb_last_timing_kernels.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(cint)]
         _lib = L
     return _lib
 
@@ -192,6 +196,15 @@ class Engine:
 
     def sync(self):
         self._check(lib().grb_sync(self._h))
+
+    def stream_ptr(self):
+        return lib().grb_get_stream(self._h)
+
+    def last_timing_kernels(self):
+        """(total device ms, summed k_screen device ms, number of k_screen launches) of the last call."""
+        tot, scr, n = C.c_double(0), C.c_double(0), C.c_int(0)
+        lib().grb_last_timing_kernels(self._h, C.byref(tot), C.byref(scr), C.byref(n))
+        return tot.value, scr.value, n.value
 
     def last_timing(self):
         ms, nl = C.c_double(0), C.c_int(0)

@@ -307,6 +307,20 @@ int grb_measure_dfma_peak(int device, double *tflops_out);
  * the engine's stream), and how many kernels that call launched.                                         */
 int grb_last_timing(const grb_engine *e, double *kernel_ms, int *n_launches);
 
+/* Same, split by kernel: total device time of the call and the summed device time of its screening-loop
+ * launches (k_screen, the dominant kernel of screened processes), each bracketed by CUDA events.          */
+int grb_last_timing_kernels(const grb_engine *e, double *ms_total, double *ms_screen, int *n_screen_launches);
+
+/* The engine's CUDA stream (cudaStream_t) so that a caller can order its own work (collectives, event
+ * timing) after the engine's kernels without a host synchronisation.                                      */
+void *grb_get_stream(grb_engine *e);
+
+/* Block until the engine's stream is idle (after grb_vegas_iterate_async).                               */
+int grb_sync(grb_engine *e);
+
+/* sizeof() of the ABI structs as compiled (0 desc, 1 accum, 2 resonance, 3 node): layout check for FFI.   */
+int grb_abi_sizeof(int what);
+
 #ifdef __cplusplus
 }
 #endif

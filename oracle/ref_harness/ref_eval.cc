@@ -22,6 +22,7 @@
 // in.bin : int64 n, int64 du, int64 dt, then n*(du+dt) doubles (point-major: u[du] then tape[dt])
 // out.bin: int64 n, int64 rec, then n*rec doubles, record layout = see `struct Rec` below.
 
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdint>
@@ -174,6 +175,7 @@ int main(int argc, char **argv) {
     fclose(fi);
 
     std::vector<Rec> out(n);
+    const auto       clk0 = std::chrono::steady_clock::now();
     for (int64_t k = 0; k < n; ++k) {
       const double *   row = &in[k * (du + dt)];
       gra::AuxIntData aux;
@@ -217,6 +219,8 @@ int main(int argc, char **argv) {
         r.kappa = kap;
       }
     }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - clk0).count();
+    printf("TIME %.6f %lld\n", secs, (long long)n);  // seconds spent in the EventWeight loop (incl. kappa calls)
     FILE *  fo      = fopen(argv[6], "wb");
     int64_t ohdr[2] = {n, RECLEN};
     fwrite(ohdr, sizeof(int64_t), 2, fo);

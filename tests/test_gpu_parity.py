@@ -1,0 +1,158 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against (a) the CPU oracle on the same
+seeded inputs, (b) the committed reference golden vectors, (c) size-independent properties at full size.
+
+Tolerance (BASELINE.json north_star): integer decisions (flags) bit-exact; weights relative 1e-10 per
+point.  The reference's own weight moves by up to ~1e-10 when one input moves by 1 ulp (SURVEY.md section 7:
+t1 = (p_beam - p1)^2 is formed from O(6500 GeV) components), and CUDA's libm differs from glibc by <= 1-2
+ulp, so the documented protocol is |dW|/W <= max(1e-10, 8*kappa(u)) with kappa the reference's measured
+1-ulp conditioning of that very point (stored in the golden files); the fraction of points that need the
+kappa term is asserted to stay below 1e-3."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CARDS, GOLDEN, Eikonal, make_points, oracle_eval
+from graniitti_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json"}
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
+
+
+def engine_for(grb, msa, card, proc=None, pom=-1):
+    E = grb.Engine(card=os.path.join(CARDS, card), process=proc, pomloop=pom)
+    if E.desc.screening:
+        E.set_eikonal(msa[0], msa[1], msa[2])
+    return E
+
+
+def compare(w, fl, ref_w, ref_fl, kappa=None, rtol=RTOL):
+    kin = (ref_fl & 1) == 1
+    assert np.array_equal(fl & 1, ref_fl & 1), "kinematics_ok differs"
+    assert np.array_equal(fl[kin], ref_fl[kin]), "cut decisions differ"
+    nz = ref_w != 0
+    assert np.array_equal(w != 0, nz), "zero pattern differs"
+    rel = np.abs(w[nz] - ref_w[nz]) / np.abs(ref_w[nz])
+    if kappa is None:
+        tol = np.full(rel.shape, rtol)
+    else:
+        tol = np.maximum(rtol, 8.0 * kappa[nz])
+    bad = rel > tol
+    assert not bad.any(), f"max rel {rel.max():.3g}; {bad.sum()} points above tolerance"
+    return rel
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_device_vs_reference_golden(grb, msa, path):
+    z = np.load(path, allow_pickle=False)
+    E = engine_for(grb, msa, CARD_OF[str(z["card"])], str(z["process"]), int(z["pomloop"]))
+    w, fl, dump = E.eval(z["u"].T.copy(), z["tape"].T.copy(), want_dump=True)
+    rel = compare(w, fl, z["W"], z["flags"], kappa=z["kappa"])
+    assert np.mean(rel > RTOL) < 1e-3 + 2.0 / len(rel), "too many points needed the conditioning term"
+    assert np.median(rel) < 1e-13
+    kin = (z["flags"] & 1) == 1
+    # intermediate scalars: absolute 2e-10 on t (t = dE^2 - dpz^2 - pt^2 cancels O(6500 GeV) roundings), relative elsewhere
+    assert np.max(np.abs(dump[0][kin] - z["t1"][kin])) < 2e-10
+    assert np.max(np.abs(dump[1][kin] - z["t2"][kin])) < 2e-10
+    assert np.max(np.abs(dump[4][kin] - z["m2"][kin]) / z["m2"][kin]) < 1e-12
+    E.close()
+
+
+@pytest.mark.parametrize("proc,pom,n", [("PP[CON]<F> -> pi+ pi-", 0, 200000), ("PP[CON]<F> -> pi+ pi-", 1, 40000),
+                                        ("PP[CON-]<F> -> K+ K-", 1, 10000), ("PP[CON]<F> -> p+ p-", 0, 50000)])
+def test_device_vs_oracle_seeded(grb, msa, proc, pom, n):
+    E = engine_for(grb, msa, "c2_alice.json", proc, pom)
+    u, tape = make_points(n, 6, 8, 99 + n, adapted=True)
+    o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
+    w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
+    nz = o["w"] != 0
+    kin = (o["flags"] & 1) == 1
+    assert np.array_equal(fl & 1, o["flags"] & 1) and np.array_equal(fl[kin], o["flags"][kin])
+    assert np.array_equal(w != 0, nz)
+    rel = np.abs(w[nz] - o["w"][nz]) / np.abs(o["w"][nz])
+    # no per-point kappa here: allow the documented ill-conditioned tail (< 1e-3 of points, < 1e-8)
+    assert np.mean(rel > RTOL) < 1e-3 and rel.max() < 1e-8 and np.median(rel) < 1e-13, (rel.max(), np.mean(rel > RTOL))
+    E.close()
+
+
+def test_flat_points_and_edges(grb, msa):
+    E = engine_for(grb, msa, "c2_alice.json", None, 1)
+    # empty batch
+    w, fl, _ = E.eval(np.zeros((6, 0)), np.zeros((8, 0)))
+    assert len(w) == 0
+    # hypercube corners / ragged batch (n not a multiple of the block size) / exhausted tape
+    u = np.array([[0.0] * 6, [1.0 - 2 ** -53] * 6, [0.5] * 6, [1.0 - 2 ** -53, 0, 0, 0, 0, 0], [0.93, 0.97, 0.1, 0.6, 0.5, 0.02]])
+    tape = np.full((5, 8), 0.5)
+    o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]), u, tape)
+    w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
+    assert np.all(np.isfinite(w)) and np.array_equal(w != 0, o["w"] != 0)
+    assert np.allclose(w, o["w"], rtol=1e-9, atol=0)
+    w, fl, _ = E.eval(u.T.copy(), np.zeros((0, 5)))
+    assert np.all(w == 0)
+    E.close()
+
+
+def test_chunking_is_invisible(grb, msa, monkeypatch):
+    """Results do not depend on the internal chunk size (work-list capacity)."""
+    u, tape = make_points(30000, 6, 8, 5, adapted=True)
+    monkeypatch.setenv("GRB_CHUNK", "4096")
+    E1 = engine_for(grb, msa, "c2_alice.json", None, 1)
+    w1, f1, _ = E1.eval(u.T.copy(), tape.T.copy())
+    monkeypatch.delenv("GRB_CHUNK")
+    E2 = engine_for(grb, msa, "c2_alice.json", None, 1)
+    w2, f2, _ = E2.eval(u.T.copy(), tape.T.copy())
+    assert np.array_equal(w1, w2) and np.array_equal(f1, f2)
+    E1.close(); E2.close()
+
+
+def test_vegas_iteration_properties(grb, msa):
+    """Full-size properties of the device VEGAS iteration (2^22 points): counters add up, the histogram
+    marginals equal the scalar sums in every dimension, results are independent of how the calls are
+    split over launches/ranks (Philox is keyed by the global point index)."""
+    E = engine_for(grb, msa, "c2_alice.json", None, 1)
+    bins, dim, N = 128, 6, 1 << 22
+    xmat = np.tile(((np.arange(bins) + 1) / bins)[:, None], (1, dim))
+    a = E.vegas_iterate(xmat, 0, N, 12345678, 3)
+    assert a.evaluations == N and a.n_kin_ok <= N and a.n_fid_ok <= a.n_kin_ok
+    fm = np.frombuffer(a.fmat, dtype=np.float64).reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM)
+    f2m = np.frombuffer(a.f2mat, dtype=np.float64).reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM)
+    for j in range(dim):
+        assert abs(fm[:, j].sum() - a.fsum) <= 1e-11 * a.fsum
+        assert abs(f2m[:, j].sum() - a.f2sum) <= 1e-11 * a.f2sum
+    assert np.all(fm[:, dim:] == 0)
+    # split into two "ranks": sums agree to fp64 summation-order noise, maxima exactly
+    b1 = E.vegas_iterate(xmat, 0, N // 2, 12345678, 3)
+    b2 = E.vegas_iterate(xmat, N // 2, N - N // 2, 12345678, 3)
+    assert abs((b1.fsum + b2.fsum) - a.fsum) <= 1e-11 * a.fsum
+    assert b1.n_fid_ok + b2.n_fid_ok == a.n_fid_ok and max(b1.maxf, b2.maxf) == a.maxf
+    # a different iteration index gives different points
+    c = E.vegas_iterate(xmat, 0, N, 12345678, 4)
+    assert c.fsum != a.fsum and abs(c.fsum - a.fsum) < 0.05 * a.fsum
+    # uniform grid => vegasweight = 1 => sigma = fsum / N; flat-grid estimate of the reference's
+    # 2.311 +- 0.023 ub (ALICE cuts, screened) within MC error
+    sigma = a.fsum / N
+    err = np.sqrt(max(a.f2sum / N - sigma * sigma, 0) / N)
+    assert abs(sigma - 2.311e-6) < 5 * np.hypot(err, 0.023e-6), (sigma, err)
+    E.close()
+
+
+def test_vegas_matches_eval_on_same_points(grb, msa):
+    """The Philox/VEGAS path and the parity path are the same code: regenerate the iteration's points on the
+    host with the documented Philox layout and feed them through grb_eval."""
+    from philox_ref import philox_points
+    E = engine_for(grb, msa, "c2_alice.json", None, 0)
+    bins, dim, N = 128, 6, 4096
+    rng = np.random.default_rng(3)
+    edges = np.sort(rng.random((bins - 1, dim)), axis=0)
+    xmat = np.vstack([edges, np.ones((1, dim))])
+    a = E.vegas_iterate(xmat, 1000, N, 777, 2)
+    u, vw, tape = philox_points(xmat, 1000, N, 777, 2, ntape=8)
+    w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
+    f = w * vw
+    assert abs(f.sum() - a.fsum) <= 1e-12 * a.fsum and abs((f * f).sum() - a.f2sum) <= 1e-12 * a.f2sum
+    assert a.maxf == f.max()
+    E.close()

@@ -1,0 +1,60 @@
+"""Pins the CPU oracle (oracle/grb_oracle.c) against golden vectors produced by the UNMODIFIED reference
+compiled in the build container (tests/golden/make_golden.py).  Same libm, same operation order:
+the restatement is required to be bit-exact on W and on the flags."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CARDS, GOLDEN, Eikonal, have_ref, make_points, oracle_eval, ref_eval
+
+CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json"}
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
+
+
+def load_case(grb, path):
+    z = np.load(path, allow_pickle=False)
+    d = grb.parse_card(os.path.join(CARDS, CARD_OF[str(z["card"])]), str(z["process"]), int(z["pomloop"]))
+    return z, d
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
+def test_oracle_reproduces_reference_bit_exactly(grb, msa, path):
+    z, d = load_case(grb, path)
+    eik = Eikonal(msa[0], msa[1], msa[2]) if d.screening else None
+    o = oracle_eval(d, eik, z["u"], z["tape"])
+    kin = (z["flags"] & 1) == 1
+    assert np.array_equal(o["flags"] & 1, z["flags"] & 1)
+    assert np.array_equal(o["flags"][kin], z["flags"][kin])
+    assert np.array_equal(o["w"], z["W"]), "oracle differs from the reference"
+    assert np.array_equal(o["dump"][kin, 0], z["t1"][kin]) and np.array_equal(o["dump"][kin, 1], z["t2"][kin])
+    assert np.array_equal(o["tape_used"], z["tape_used"].astype(np.int32))
+    assert (z["W"] != 0).sum() > 100
+
+
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("proc,pom,n", [("PP[CON]<F> -> pi+ pi-", 0, 20000), ("PP[CON]<F> -> pi+ pi-", 1, 1500),
+                                        ("PP[CON-]<F> -> K+ K-", 0, 5000), ("PP[CON]<F> -> p+ p-", 0, 5000)])
+def test_oracle_vs_live_reference(grb, msa, proc, pom, n):
+    d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), proc, pom)
+    u, tape = make_points(n, 6, 8, 4242 + n, adapted=True)
+    r = ref_eval("./tests/processes/ALICECUTS.json", proc, pom, u, tape)
+    o = oracle_eval(d, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
+    kin = (r["flags"] & 1) == 1
+    assert np.array_equal(o["flags"] & 1, r["flags"] & 1) and np.array_equal(o["flags"][kin], r["flags"][kin])
+    assert np.array_equal(o["w"], r["W"])
+
+
+def test_edge_cases(grb, msa):
+    d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), None, 0)
+    # empty batch
+    o = oracle_eval(d, None, np.zeros((0, 6)), np.zeros((0, 8)))
+    assert len(o["w"]) == 0
+    # corners of the unit hypercube: never NaN, flags consistent
+    u = np.array([[0.0] * 6, [1.0 - 2 ** -53] * 6, [0.5] * 6, [1.0 - 2 ** -53, 0, 0, 0, 0, 0]])
+    o = oracle_eval(d, None, u, np.full((4, 8), 0.5))
+    assert np.all(np.isfinite(o["w"]))
+    # exhausted tape -> flagged, not crashing
+    o = oracle_eval(d, None, u, np.zeros((4, 0)))
+    assert np.all(o["tape_used"] < 0)

@@ -72,8 +72,12 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.excitation != 0) { err = "NSTARS != 0 is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
-  if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS) {
+  if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR) {
     err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  if (d.proc == GRB_PROC_PP_CONTENSOR && !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0)) {
+    err = "PP[CONTENSOR]: only pseudoscalar pairs (2xS) have a device amplitude yet";
     return GRB_ERR_UNSUPPORTED;
   }
   if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
@@ -128,6 +132,16 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.M2_leg0 = d.nodes[0].mass * d.nodes[0].mass;
   P.b_EXP = R.b_EXP; P.a_OREAR = R.a_OREAR; P.b_OREAR = R.b_OREAR; P.b_POW = R.b_POW;
   P.me4_sign = (d.proc == GRB_PROC_PP_CON_MINUS) ? -1.0 : 1.0;
+  // tensor pomeron 2xS (reference src/MTensorPomeron.cc:726-763,1388-1399,2203-2215,2288-2298)
+  {
+    const double gP = (d.nodes[0].mass < 0.2) ? d.tpom.gPpipi : d.tpom.gPKK;
+    P.tp_coupling = 36.0 * d.tpom.gPNN * d.tpom.gPNN * gP * gP;
+    P.tp_delta = d.tpom.delta_P; P.tp_ap = d.tpom.ap_P; P.tp_ln_ap = std::log(d.tpom.ap_P);
+    P.tp_phase = -GRB_PI / 2.0;
+    P.four_mp2 = (2 * 0.938272081) * (2 * 0.938272081);  // PDG::mp, reference MPDG.h:54
+    P.em_kelly = d.em_ff;
+    P.amp_kind = (d.proc == GRB_PROC_PP_CONTENSOR) ? 1 : 0;
+  }
   // nodes
   for (int i = 0; i < d.n_nodes; ++i) {
     const grb_node &n = d.nodes[i];
@@ -380,10 +394,10 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
-    e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
+    e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
-      e->last_launches += launch_screen(a, e->sm_count, e->stream);
+      e->last_launches += launch_screen(a, e->dproc.amp_kind, e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
     }
   }
@@ -423,10 +437,10 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
-    e->last_launches += launch_points(a, e->desc.n_nodes, e->sm_count, e->stream);
+    e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
-      e->last_launches += launch_screen(a, e->sm_count, e->stream);
+      e->last_launches += launch_screen(a, e->dproc.amp_kind, e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
     }
   }

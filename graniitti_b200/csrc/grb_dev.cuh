@@ -59,6 +59,9 @@ struct DevProc {
   // Regge continuum (MRegge.cc:394-438, 888-906; MForm.cc:382-396,433-435)
   double a0[3], ap[3], ln_inv_s0, eta0_re[3], eta0_im[3], phase_c[3];  // phase_c = -pi/2 * ap
   double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
+  // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
+  double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
+  int    em_kelly, amp_kind;
   DevNode nodes[GRB_MAX_NODES];
 };
 
@@ -104,8 +107,8 @@ struct PointArgs {
 // launchers implemented in grb_kernels.cu
 cudaError_t upload_proc(const DevProc &p, cudaStream_t st);
 cudaError_t upload_loop(const DevLoop &l, cudaStream_t st);
-int         launch_points(const PointArgs &a, int n_nodes, int sm_count, cudaStream_t st);
-int         launch_screen(const PointArgs &a, int sm_count, cudaStream_t st);
+int         launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st);
+int         launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st);
 cudaError_t run_dfma_peak(int sm_count, double *tflops);
 
 // ---- small math ----------------------------------------------------------------------------------------

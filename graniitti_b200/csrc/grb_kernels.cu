@@ -85,12 +85,13 @@ __device__ __forceinline__ void hist_flush(int nb, int dim, grb_accum *acc) {
 }
 
 // ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
-template <int NN>
+template <int NN, int AMP>
 __device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
-  ReggeIn in;
+  NodeKin in;
   in.ss13 = S.ss13; in.ss24 = S.ss24; in.ss14 = S.ss14; in.ss23 = S.ss23;
   in.t1 = S.t1; in.t2 = S.t2; in.t_hat = S.t_hat; in.u_hat = S.u_hat;
-  return regge_me4(in);
+  in.p1 = S.p1; in.p2 = S.p2;
+  return amplitude<AMP>(in, S.np4[0], S.np4[1]);
 }
 
 // weight prefactor: everything of MFactorized.cc:173-174 except |A|^2
@@ -104,7 +105,7 @@ __device__ __forceinline__ double weight_prefactor(const PointState<NN> &S) {
   return C * psw * vol * c_proc.w_const;
 }
 
-template <int NN, bool VEGAS>
+template <int NN, bool VEGAS, int AMP>
 __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
     cx         h0 = {0.0, 0.0};
     double     pref = 0.0;
     if (valid) {
-      h0   = born_amplitude<NN>(S);
+      h0   = born_amplitude<NN, AMP>(S);
       pref = weight_prefactor<NN>(S);
       if (!P.screening) {
         W = pref * (h0.re * h0.re + h0.im * h0.im);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
   if (VEGAS) hist_flush(nb, dim, a.acc);
 }
 
-template <bool VEGAS, int MINB>
+template <bool VEGAS, int MINB, int AMP>
 __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
     cx h0;
     h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
     const double pref = it[IT_PREF * c], vw = it[IT_VW * c];
-    const double amp2 = screened_amp2_h1(L, h0);
+    const double amp2 = screened_amp2_h1<AMP>(L, h0);
     double       W    = pref * amp2;
     bool         ok   = true;
     if (isnan(W) || isinf(W)) { W = 0.0; ok = false; }
@@ -310,42 +311,55 @@ cudaError_t upload_loop(const DevLoop &l, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_loop, &l, sizeof(DevLoop), 0, cudaMemcpyHostToDevice, st);
 }
 
-int launch_points(const PointArgs &a, int n_nodes, int sm_count, cudaStream_t st) {
-  const int    threads = 256;
-  int64_t      blocks  = (a.n + threads - 1) / threads;
-  const int64_t cap    = (int64_t)sm_count * 8;
+template <int NN, int AMP>
+static void launch_points_t(const PointArgs &a, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
+  if (a.vegas) k_points<NN, true, AMP><<<blocks, threads, smem, st>>>(a);
+  else k_points<NN, false, AMP><<<blocks, threads, 0, st>>>(a);
+}
+template <int AMP>
+static void launch_points_n(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
+  if (n_nodes <= 2) launch_points_t<2, AMP>(a, blocks, threads, smem, st);
+  else if (n_nodes <= 6) launch_points_t<6, AMP>(a, blocks, threads, smem, st);  // config 5: rho rho -> 4 pi
+  else launch_points_t<GRB_MAX_NODES, AMP>(a, blocks, threads, smem, st);
+}
+
+int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st) {
+  const int     threads = 256;
+  int64_t       blocks  = (a.n + threads - 1) / threads;
+  const int64_t cap     = (int64_t)sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
-  if (n_nodes <= 2) {
-    if (a.vegas) k_points<2, true><<<(unsigned)blocks, threads, smem, st>>>(a);
-    else k_points<2, false><<<(unsigned)blocks, threads, 0, st>>>(a);
-  } else {
-    if (a.vegas) k_points<GRB_MAX_NODES, true><<<(unsigned)blocks, threads, smem, st>>>(a);
-    else k_points<GRB_MAX_NODES, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+  switch (amp_kind) {
+    case AMP_TENSOR_2XS: launch_points_n<AMP_TENSOR_2XS>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    default: launch_points_n<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;
 }
 
-template <int MINB>
+template <int MINB, int AMP>
 static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
   const int    threads = 128;
   const int    blocks  = sm_count * MINB;  // persistent: exactly the resident CTAs
   const size_t smem    = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
-  if (a.vegas) k_screen<true, MINB><<<blocks, threads, smem, st>>>(a);
-  else k_screen<false, MINB><<<blocks, threads, 0, st>>>(a);
+  if (a.vegas) k_screen<true, MINB, AMP><<<blocks, threads, smem, st>>>(a);
+  else k_screen<false, MINB, AMP><<<blocks, threads, 0, st>>>(a);
 }
 
-int launch_screen(const PointArgs &a, int sm_count, cudaStream_t st) {
+int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st) {
   static const int minb = [] {
     const char *e = getenv("GRB_SCREEN_MINB");
     return e ? atoi(e) : 4;
   }();
+  if (amp_kind == AMP_TENSOR_2XS) {
+    launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
+    return 1;
+  }
   switch (minb) {
-    case 3: launch_screen_t<3>(a, sm_count, st); break;
-    case 5: launch_screen_t<5>(a, sm_count, st); break;
-    case 6: launch_screen_t<6>(a, sm_count, st); break;
-    default: launch_screen_t<4>(a, sm_count, st); break;
+    case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;
+    case 5: launch_screen_t<5, AMP_REGGE>(a, sm_count, st); break;
+    case 6: launch_screen_t<6, AMP_REGGE>(a, sm_count, st); break;
+    default: launch_screen_t<4, AMP_REGGE>(a, sm_count, st); break;
   }
   return 1;
 }

@@ -306,9 +306,11 @@ __device__ __forceinline__ bool veto_cuts(const PointState<NN> &S) {
 // A = A_t + sign*A_u, A_x = Prop(s_a,t1) FF_A ff(x)^2 gpp^2 /(x - M^2) Prop(s_b,t2) FF_B with
 // Prop(s,t) = sum_k eta_k(0) e^{-i pi/2 ap_k t} (s/s0)^{a0_k + ap_k t}.  With one active trajectory (TUNE0)
 // the phase depends on t1+t2 only and the amplitude is  eta0^2 cis(pc (t1+t2)) * real.
-struct ReggeIn {
+struct NodeKin {
   double ss13, ss24, ss14, ss23, t1, t2, t_hat, u_hat;
+  v4     p1, p2;  // outgoing protons lts.pfinal[1], [2] (needed by the tensor-pomeron vertices)
 };
+typedef NodeKin ReggeIn;
 
 __device__ __forceinline__ double meson_G(double x) {  // ff(x)^2 * prop(x), MRegge.cc:1155-1218
   const DevProc &P  = c_proc;
@@ -373,6 +375,73 @@ __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
   return A;
 }
 
+// ---- tensor pomeron continuum, 2 x pseudoscalar (reference src/MTensorPomeron.cc:572-763) -----------------
+// The reference contracts rank-2 vertices with rank-4 propagators through FTensor loops.  With
+//   i Delta(s,t) = 1/(4s) (-i s a')^(alpha(t)-1) [g g + g g - 1/2 g g],   i Gamma_pp = -3i g_PNN F1(t) P P  (HE limit),
+//   i Gamma_P,ps,ps(k',k) = -2i g F_M((k'-k)^2) [K K - 1/4 g K^2],  K = k' + k,
+// every vertex.propagator.vertex chain collapses to  2 (P.K)^2 - 1/2 K^2 P^2  and the amplitude is
+//   M = 36 g_PNN^2 g^2 F1(t1) F1(t2) F_M(t1) F_M(t2) e^{-i pi (a1+a2)/2}
+//       [ E13 E24 R_t ff(t^)^2/(t^ - m^2) + E14 E23 R_u ff(u^)^2/(u^ - m^2) ],   E_ij = (s_ij a')^{a}/(4 s_ij),
+// a_k = delta_P + a' t_k.  The four helicity-conserving proton combinations carry the same amplitude
+// (:658-662,762), so one complex number per point is enough (|A|^2 = 4|M|^2/4).
+__device__ __forceinline__ double mdot(const v4 &a, const v4 &b) { return a.e * b.e - (a.x * b.x + a.y * b.y + a.z * b.z); }
+
+__device__ __forceinline__ double proton_F1(double t) {  // reference src/MForm.cc:542-548,607-645
+  const DevProc &P   = c_proc;
+  const double   Q2  = fabs(t);
+  const double   tau = Q2 / P.four_mp2;
+  double         GE, GM;
+  if (P.em_kelly) {
+    GE = (1.0 - 0.24 * tau) / (1.0 + 10.98 * tau + 12.82 * (tau * tau) + 21.97 * (tau * (tau * tau)));
+    GM = 2.792847337 * (1.0 + 0.12 * tau) / (1.0 + 10.97 * tau + 18.86 * (tau * tau) + 6.55 * (tau * (tau * tau)));
+  } else {
+    GM = 2.792847337 / pow2(1.0 + Q2 / 0.71);
+    GE = GM / 2.792847337;
+  }
+  return 1.0 / (tau + 1) * GE + tau / (tau + 1) * GM;
+}
+
+__device__ __forceinline__ cx tensor_me4_2xS(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  const DevProc &P = c_proc;
+  v4 pa, pb;
+  pa.x = 0.0; pa.y = 0.0; pa.z = P.pb1z; pa.e = P.pb1e;
+  pb.x = 0.0; pb.y = 0.0; pb.z = P.pb2z; pb.e = P.pb2e;
+  v4 P1, P2, pt, pu;
+  P1.x = in.p1.x + pa.x; P1.y = in.p1.y + pa.y; P1.z = in.p1.z + pa.z; P1.e = in.p1.e + pa.e;
+  P2.x = in.p2.x + pb.x; P2.y = in.p2.y + pb.y; P2.z = in.p2.z + pb.z; P2.e = in.p2.e + pb.e;
+  pt.x = (pa.x - in.p1.x) - p3.x; pt.y = (pa.y - in.p1.y) - p3.y; pt.z = (pa.z - in.p1.z) - p3.z; pt.e = (pa.e - in.p1.e) - p3.e;
+  pu.x = (p4.x - pa.x) + in.p1.x; pu.y = (p4.y - pa.y) + in.p1.y; pu.z = (p4.z - pa.z) + in.p1.z; pu.e = (p4.e - pa.e) + in.p1.e;
+  v4 Kta, Ktb, Kua, Kub;
+  Kta.x = pt.x - p3.x; Kta.y = pt.y - p3.y; Kta.z = pt.z - p3.z; Kta.e = pt.e - p3.e;
+  Ktb.x = p4.x + pt.x; Ktb.y = p4.y + pt.y; Ktb.z = p4.z + pt.z; Ktb.e = p4.e + pt.e;
+  Kua.x = p4.x + pu.x; Kua.y = p4.y + pu.y; Kua.z = p4.z + pu.z; Kua.e = p4.e + pu.e;
+  Kub.x = pu.x - p3.x; Kub.y = pu.y - p3.y; Kub.z = pu.z - p3.z; Kub.e = pu.e - p3.e;
+  const double P1sq = m2_of(P1), P2sq = m2_of(P2);
+  const double d1t = mdot(P1, Kta), d2t = mdot(P2, Ktb), d1u = mdot(P1, Kua), d2u = mdot(P2, Kub);
+  const double Rt = (2.0 * d1t * d1t - 0.5 * m2_of(Kta) * P1sq) * (2.0 * d2t * d2t - 0.5 * m2_of(Ktb) * P2sq);
+  const double Ru = (2.0 * d1u * d1u - 0.5 * m2_of(Kua) * P1sq) * (2.0 * d2u * d2u - 0.5 * m2_of(Kub) * P2sq);
+  const double pt2 = m2_of(pt), pu2 = m2_of(pu);
+  const double a1 = P.tp_delta + P.tp_ap * in.t1, a2 = P.tp_delta + P.tp_ap * in.t2;
+  const double Et = exp(a1 * (log(in.ss13) + P.tp_ln_ap) + a2 * (log(in.ss24) + P.tp_ln_ap)) / (16.0 * in.ss13 * in.ss24);
+  const double Eu = exp(a1 * (log(in.ss14) + P.tp_ln_ap) + a2 * (log(in.ss23) + P.tp_ln_ap)) / (16.0 * in.ss14 * in.ss23);
+  const double FM12 = (1.0 / (1.0 - in.t1 / 0.5)) * (1.0 / (1.0 - in.t2 / 0.5));
+  const double pre  = P.tp_coupling * proton_F1(in.t1) * proton_F1(in.t2) * FM12;
+  const double R    = pre * (Et * Rt * meson_G(pt2) + Eu * Ru * meson_G(pu2));
+  double       sn, cs;
+  sincos(P.tp_phase * (a1 + a2), &sn, &cs);  // tp_phase = -pi/2
+  cx A;
+  A.re = cs * R;
+  A.im = sn * R;
+  return A;
+}
+
+enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1 };
+template <int AMP>
+__device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
+  return regge_me4(in);
+}
+
 // ---- screening loop: per-point invariants and per-node work -------------------------------------------------
 // reference src/MFactorized.cc:84-139 LoopKinematics: the loop re-derives m1, m2, mX, yX from the saved
 // 4-vectors (pfinal_orig) -- done once per point here -- shifts the proton pT by -/+ kt, rebuilds pX and
@@ -430,11 +499,14 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   if (o.t1 > 0 || o.t2 > 0) return false;
   o.t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
   o.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  o.p1.x = n1x; o.p1.y = n1y; o.p1.z = p1z; o.p1.e = e1;
+  o.p2.x = n2x; o.p2.y = n2y; o.p2.z = p2z; o.p2.e = e2;
   return true;
 }
 
 // reference src/MProcess.cc:157-288 S3ScreenedAmp2 for a one-amplitude process (H = 1): returns
 // |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order.
+template <int AMP>
 __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h0) {
   const DevLoop &Q = c_loop;
   PzConst        pc;
@@ -446,7 +518,7 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
       const double kt = Q.kt[j];
       ReggeIn      in;
       if (!loop_node(L, pc, kt * cp, kt * sp, in)) continue;
-      const cx A = regge_me4(in);
+      const cx A = amplitude<AMP>(in, L.p3, L.p4);
       // f = (A_eik * A) * kt ;  I += W_ij * f
       const double fr = (Q.aeik_re[j] * A.re - Q.aeik_im[j] * A.im) * kt;
       const double fi = (Q.aeik_re[j] * A.im + Q.aeik_im[j] * A.re) * kt;

@@ -548,11 +548,171 @@ static cx regge_me4(ost *S, double sign) {
   return A;
 }
 
+/* ---- tensor pomeron continuum (Ewerz-Maniatis-Nachtmann), 2 x pseudoscalar ------------------------- */
+/* Restated with explicit rank-2/rank-4 Lorentz tensors and index loops exactly as the reference builds
+ * them with FTensor (src/MTensorPomeron.cc:572-763); the device code uses the contracted closed form, so
+ * the two are independent derivations.  Index 0 = E, metric g = diag(1,-1,-1,-1) (MTensorPomeron.h). */
+static const double o_g[4][4] = {{1, 0, 0, 0}, {0, -1, 0, 0}, {0, 0, -1, 0}, {0, 0, 0, -1}};
+static inline double v4_cov(v4 a, int mu) { /* M4Vec::operator%, M4Vec.h:230-237 */
+  return mu == 0 ? a.e : (mu == 1 ? -a.x : (mu == 2 ? -a.y : -a.z));
+}
+static inline cx cx_mulr(cx a, double d) { return (cx){a.re * d, a.im * d}; }
+
+/* reference src/MForm.cc:542-645 F1 with Kelly / dipole Sachs form factors */
+static double o_mu_ratio(void) { return 2.792847337; }
+static double o_GM(const ost *S, double Q2);
+static double o_GE(const ost *S, double Q2) {
+  const double mp = 0.938272081;
+  Q2 = fabs(Q2);
+  if (S->d->em_ff == 1) {
+    const double tau = Q2 / pow2(2 * mp);
+    double num = 0.0;
+    num += 1;
+    num += -0.24 * tau;
+    double den = 1.0;
+    den += 10.98 * tau;
+    den += 12.82 * pow2(tau);
+    den += 21.97 * (tau * pow2(tau));
+    return num / den;
+  }
+  return o_GM(S, Q2) / o_mu_ratio();
+}
+static double o_GM(const ost *S, double Q2) {
+  const double mp = 0.938272081;
+  Q2 = fabs(Q2);
+  if (S->d->em_ff == 1) {
+    const double tau = Q2 / pow2(2 * mp);
+    double num = 0.0;
+    num += 1;
+    num += 0.12 * tau;
+    double den = 1.0;
+    den += 10.97 * tau;
+    den += 18.86 * pow2(tau);
+    den += 6.55 * (tau * pow2(tau));
+    return o_mu_ratio() * num / den;
+  }
+  return o_mu_ratio() / pow2(1.0 + Q2 / 0.71);
+}
+static double o_F1(const ost *S, double Q2) {
+  const double mp = 0.938272081;
+  Q2 = fabs(Q2);
+  const double tau = Q2 / pow2(2 * mp);
+  return 1.0 / (tau + 1) * o_GE(S, Q2) + tau / (tau + 1) * o_GM(S, Q2);
+}
+
+/* std::pow(complex z, double a) = exp(a * log z) as libstdc++/glibc evaluate it (polar form) */
+static cx cx_powr(cx z, double a) {
+  if (z.re == 0.0 && z.im == 0.0) return (cx){0, 0};
+  const double lr = log(hypot(z.re, z.im)), th = atan2(z.im, z.re);
+  const double m = exp(a * lr);
+  return (cx){m * cos(a * th), m * sin(a * th)};
+}
+
+/* reference src/MTensorPomeron.cc:2288-2298 iD_P: FACTOR * (g g + g g - 1/2 g g) */
+static cx tp_iDP_factor(const ost *S, double s, double t) {
+  const grb_param_tensorpom *T = &S->d->tpom;
+  const double alpha = 1.0 + T->delta_P + T->ap_P * t;
+  /* -zi * s * ap_P = ((-0,-1)*s)*ap */
+  const cx z = {-0.0 * s * T->ap_P, -1.0 * s * T->ap_P};
+  return cx_mulr(cx_powr(z, alpha - 1.0), 1.0 / (4.0 * s));
+}
+static void tp_iDP(const ost *S, double s, double t, cx D[4][4][4][4]) {
+  const cx F = tp_iDP_factor(S, s, t);
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
+      for (int k = 0; k < 4; ++k)
+        for (int l = 0; l < 4; ++l)
+          D[u][v][k][l] = cx_mulr(F, o_g[u][k] * o_g[v][l] + o_g[u][l] * o_g[v][k] - 0.5 * o_g[u][v] * o_g[k][l]);
+}
+/* :1388-1399 iG_PppHE */
+static void tp_iG_PppHE(const ost *S, v4 prime, v4 p, cx T[4][4]) {
+  const v4 psum = v4_add(prime, p);
+  const double f = 3.0 * S->d->tpom.gPNN * o_F1(S, v4_m2(v4_sub(prime, p)));
+  const cx FACTOR = {-0.0 * f, -1.0 * f};
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v) T[u][v] = cx_mulr(FACTOR, v4_cov(psum, u) * v4_cov(psum, v));
+}
+/* :2203-2215 iG_Ppsps */
+static void tp_iG_Ppsps(v4 prime, v4 p, double g1, cx T[4][4]) {
+  const v4 psum = v4_add(prime, p);
+  const double M2 = v4_m2(psum);
+  const double f = 2.0 * g1 * (1.0 / (1.0 - v4_m2(v4_sub(prime, p)) / 0.5));
+  const cx FACTOR = {-0.0 * f, -1.0 * f};
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
+      T[u][v] = cx_mulr(FACTOR, v4_cov(psum, u) * v4_cov(psum, v) - 0.25 * o_g[u][v] * M2);
+}
+/* A(mu,nu) D(mu,nu,a,b) Ga(a,b) Gb(c,d) D2(c,d,k,l) B(k,l), contracted left to right */
+static cx tp_chain(cx A[4][4], cx D1[4][4][4][4], cx Ga[4][4], cx Gb[4][4], cx D2[4][4][4][4], cx B[4][4]) {
+  cx s1 = {0, 0};
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      cx X = {0, 0};
+      for (int m = 0; m < 4; ++m)
+        for (int n = 0; n < 4; ++n) X = cx_add(X, cx_mul(A[m][n], D1[m][n][a][b]));
+      s1 = cx_add(s1, cx_mul(X, Ga[a][b]));
+    }
+  cx r = {0, 0};
+  for (int k = 0; k < 4; ++k)
+    for (int l = 0; l < 4; ++l) {
+      cx Z = {0, 0};
+      for (int c = 0; c < 4; ++c)
+        for (int e = 0; e < 4; ++e) Z = cx_add(Z, cx_mul(cx_mul(s1, Gb[c][e]), D2[c][e][k][l]));
+      r = cx_add(r, cx_mul(Z, B[k][l]));
+    }
+  return r;
+}
+
+/* reference src/MTensorPomeron.cc:572-763,892-898 ME4, SPINMODE "2xS" */
+static double tensor_me4(ost *S) {
+  const grb_process_desc *d = S->d;
+  if (!(d->nodes[0].spinX2 == 0 && d->nodes[1].spinX2 == 0)) {
+    S->nhamp = 0;
+    return NAN; /* 2xF / 2xV not restated yet */
+  }
+  const v4 pa = S->pbeam1, pb = S->pbeam2, p1 = S->pfinal[1], p2 = S->pfinal[2];
+  const v4 p3 = S->node_p4[0], p4 = S->node_p4[1];
+  const double M_ = d->nodes[0].mass;
+  const v4 pt = v4_sub(v4_sub(pa, p1), p3);
+  const v4 pu = v4_add(v4_sub(p4, pa), p1);
+  const v4 mp3 = {-p3.x, -p3.y, -p3.z, -p3.e};
+  static cx D13[4][4][4][4], D24[4][4][4][4], D14[4][4][4][4], D23[4][4][4][4];
+  cx G1a[4][4], G2b[4][4], Gta[4][4], Gtb[4][4], Gua[4][4], Gub[4][4];
+  tp_iDP(S, S->ss[1][3], S->t1, D13);
+  tp_iDP(S, S->ss[2][4], S->t2, D24);
+  tp_iDP(S, S->ss[1][4], S->t1, D14);
+  tp_iDP(S, S->ss[2][3], S->t2, D23);
+  tp_iG_PppHE(S, p1, pa, G1a);
+  tp_iG_PppHE(S, p2, pb, G2b);
+  const double gP = (d->nodes[0].mass < 0.2) ? d->tpom.gPpipi : d->tpom.gPKK;
+  tp_iG_Ppsps(pt, mp3, gP, Gta);
+  tp_iG_Ppsps(p4, pt, gP, Gtb);
+  tp_iG_Ppsps(p4, pu, gP, Gua);
+  tp_iG_Ppsps(pu, mp3, gP, Gub);
+  const cx iDMES_t = {0.0 / (v4_m2(pt) - pow2(M_)), 1.0 / (v4_m2(pt) - pow2(M_))};
+  const cx iDMES_u = {0.0 / (v4_m2(pu) - pow2(M_)), 1.0 / (v4_m2(pu) - pow2(M_))};
+  cx M_t = tp_chain(G1a, D13, Gta, Gtb, D24, G2b);
+  M_t    = cx_mul(M_t, cx_mulr(iDMES_t, pow2(meson_ff(S, v4_m2(pt), pow2(M_)))));
+  cx M_u = tp_chain(G1a, D14, Gua, Gub, D23, G2b);
+  M_u    = cx_mul(M_u, cx_mulr(iDMES_u, pow2(meson_ff(S, v4_m2(pu), pow2(M_)))));
+  const cx sum = cx_add(M_t, M_u);
+  const cx M   = cx_mul((cx){-0.0, -1.0}, sum);
+  /* four helicity-conserving proton combinations push the same amplitude (:658-662,762) */
+  S->nhamp = 4;
+  double SumAmp2 = 0.0;
+  for (int h = 0; h < 4; ++h) {
+    S->hamp[h] = M;
+    SumAmp2 += cx_abs2(M);
+  }
+  return SumAmp2 / 4;
+}
+
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
     case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
+    case GRB_PROC_PP_CONTENSOR: return tensor_me4(S);
     default: S->nhamp = 0; return NAN;
   }
 }

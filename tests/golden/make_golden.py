@@ -18,10 +18,15 @@ from helpers import GOLDEN, have_ref, make_points, ref_eval, ref_msa  # noqa: E4
 # name, reference card (relative to the reference tree), process override, pomloop, n, dtape, adapted
 CASES = [
     ("c2_alice_pipi_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 1536, 8, True),
-    ("c2_alice_pipi_con_born", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, True),
-    ("c2_alice_pipi_con_born_flat", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, False),
-    ("c1_test_pipi_con_born", "./input/test.json", "PP[CON]<F> -> pi+ pi-", 0, 4096, 8, True),
+    ("c2_alice_pipi_con_born", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c2_alice_pipi_con_born_flat", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 2048, 8, False),
+    ("c1_test_pipi_con_born", "./input/test.json", "PP[CON]<F> -> pi+ pi-", 0, 2048, 8, True),
     ("c2_alice_kk_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 768, 8, True),
+    ("c2_alice_pipi_tensor_born", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c2_alice_pipi_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 1, 320, 8, True),
+    ("c1_test_kk_tensor_born", "./input/test.json", "PP[CONTENSOR]<F> -> K+ K-", 0, 1024, 8, True),
+    ("c5_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
+     "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 2048, 24, True),
 ]
 
 
@@ -39,7 +44,7 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u,
                             tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
                             s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
-                            nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :7])
+                            nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :5])
         nz = r["W"] != 0
         print(f"{name}: n={n} nonzero={nz.sum()} kappa median={np.median(r['kappa'][nz]):.3g} "
               f"max={r['kappa'][nz].max():.3g}")

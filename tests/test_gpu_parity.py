@@ -19,7 +19,8 @@ from graniitti_b200 import _abi
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
-CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json"}
+CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json",
+           "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json"}
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
 
 

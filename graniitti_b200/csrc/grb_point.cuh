@@ -424,9 +424,17 @@ __device__ __forceinline__ cx tensor_me4_2xS(const NodeKin &in, const v4 &p3, co
   const double a1 = P.tp_delta + P.tp_ap * in.t1, a2 = P.tp_delta + P.tp_ap * in.t2;
   const double Et = exp(a1 * (log(in.ss13) + P.tp_ln_ap) + a2 * (log(in.ss24) + P.tp_ln_ap)) / (16.0 * in.ss13 * in.ss24);
   const double Eu = exp(a1 * (log(in.ss14) + P.tp_ln_ap) + a2 * (log(in.ss23) + P.tp_ln_ap)) / (16.0 * in.ss14 * in.ss23);
-  const double FM12 = (1.0 / (1.0 - in.t1 / 0.5)) * (1.0 / (1.0 - in.t2 / 0.5));
-  const double pre  = P.tp_coupling * proton_F1(in.t1) * proton_F1(in.t2) * FM12;
-  const double R    = pre * (Et * Rt * meson_G(pt2) + Eu * Ru * meson_G(pu2));
+  // F_M takes the pomeron momentum as the reference forms it at each vertex, (k'-k)^2 of iG_Ppsps(k',k):
+  // (pt+p3)^2, (p4-pt)^2, (p4-pu)^2, (pu+p3)^2.  These equal t1/t2 only up to the O(1e-11) by which the
+  // solved kinematics conserves 4-momentum, and dlnA/dt ~ 8/GeV^2 makes that visible at the 1e-10 level.
+  const double qa_t = m2_of(pt.x + p3.x, pt.y + p3.y, pt.z + p3.z, pt.e + p3.e);
+  const double qb_t = m2_of(p4.x - pt.x, p4.y - pt.y, p4.z - pt.z, p4.e - pt.e);
+  const double qa_u = m2_of(p4.x - pu.x, p4.y - pu.y, p4.z - pu.z, p4.e - pu.e);
+  const double qb_u = m2_of(pu.x + p3.x, pu.y + p3.y, pu.z + p3.z, pu.e + p3.e);
+  const double FMt  = (1.0 / (1.0 - qa_t / 0.5)) * (1.0 / (1.0 - qb_t / 0.5));
+  const double FMu  = (1.0 / (1.0 - qa_u / 0.5)) * (1.0 / (1.0 - qb_u / 0.5));
+  const double pre  = P.tp_coupling * proton_F1(in.t1) * proton_F1(in.t2);
+  const double R    = pre * (Et * Rt * FMt * meson_G(pt2) + Eu * Ru * FMu * meson_G(pu2));
   double       sn, cs;
   sincos(P.tp_phase * (a1 + a2), &sn, &cs);  // tp_phase = -pi/2
   cx A;

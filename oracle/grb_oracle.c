@@ -80,6 +80,10 @@ typedef struct {
   cx regge_eta0[3];
 } ost;
 
+/* test switch: evaluate ill-conditioned amplitude algebra in extended precision (noise measurement) */
+static int g_oracle_extended = 0;
+void grb_oracle_set_extended(int on) { g_oracle_extended = on; }
+
 static double tape_U(ost *S, double a, double b) {
   double v = 0.5;
   if (S->tape_pos < S->tape_len)
@@ -707,12 +711,81 @@ static double tensor_me4(ost *S) {
   return SumAmp2 / 4;
 }
 
+/* The same 2xS amplitude in x87 extended precision (64-bit mantissa) from the same double inputs, through
+ * the contracted closed form: used by the tests to MEASURE the rounding noise nu of the reference's
+ * double-precision FTensor contraction (terms of size (E_beam K)^2 cancel down to (P.K)^2: factor 1e3-1e5),
+ * so that device-vs-reference differences can be judged against max(1e-10, 8 kappa, 8 nu). */
+static double tensor_me4_extended(ost *S, double *re, double *im) {
+  typedef long double R;
+  const grb_process_desc *d = S->d;
+  const v4 pa = S->pbeam1, pb = S->pbeam2, p1 = S->pfinal[1], p2 = S->pfinal[2];
+  const v4 p3 = S->node_p4[0], p4 = S->node_p4[1];
+#define LV(n, X, Y, Z, E) const R n##x = (X), n##y = (Y), n##z = (Z), n##e = (E)
+#define LDOT(a, b) (a##e * b##e - (a##x * b##x + a##y * b##y + a##z * b##z))
+  LV(P1, (R)p1.x + pa.x, (R)p1.y + pa.y, (R)p1.z + pa.z, (R)p1.e + pa.e);
+  LV(P2, (R)p2.x + pb.x, (R)p2.y + pb.y, (R)p2.z + pb.z, (R)p2.e + pb.e);
+  LV(q1, (R)pa.x - p1.x, (R)pa.y - p1.y, (R)pa.z - p1.z, (R)pa.e - p1.e);
+  LV(q2, (R)pb.x - p2.x, (R)pb.y - p2.y, (R)pb.z - p2.z, (R)pb.e - p2.e);
+  LV(pt, q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  LV(pu, p4.x - q1x, p4.y - q1y, p4.z - q1z, p4.e - q1e);
+  LV(Kta, ptx - p3.x, pty - p3.y, ptz - p3.z, pte - p3.e);
+  LV(Ktb, p4.x + ptx, p4.y + pty, p4.z + ptz, p4.e + pte);
+  LV(Kua, p4.x + pux, p4.y + puy, p4.z + puz, p4.e + pue);
+  LV(Kub, pux - p3.x, puy - p3.y, puz - p3.z, pue - p3.e);
+  (void)q2x; (void)q2y; (void)q2z; (void)q2e;
+  /* invariants the reference hands to the amplitude as doubles (lts.t1, lts.ss[][], pt.M2()) stay doubles:
+   * only the tensor contraction itself is lifted to extended precision */
+  const R t1 = S->t1, t2 = S->t2;
+  const R P1sq = LDOT(P1, P1), P2sq = LDOT(P2, P2);
+  const R d1t = LDOT(P1, Kta), d2t = LDOT(P2, Ktb), d1u = LDOT(P1, Kua), d2u = LDOT(P2, Kub);
+  const R Rt = (2 * d1t * d1t - 0.5L * LDOT(Kta, Kta) * P1sq) * (2 * d2t * d2t - 0.5L * LDOT(Ktb, Ktb) * P2sq);
+  const R Ru = (2 * d1u * d1u - 0.5L * LDOT(Kua, Kua) * P1sq) * (2 * d2u * d2u - 0.5L * LDOT(Kub, Kub) * P2sq);
+  const R pt2 = v4_m2(v4_sub(v4_sub(pa, p1), p3)), pu2 = v4_m2(v4_add(v4_sub(p4, pa), p1));
+  const R s13 = S->ss[1][3], s24 = S->ss[2][4], s14 = S->ss[1][4], s23 = S->ss[2][3];
+  const R ap = d->tpom.ap_P, a1 = d->tpom.delta_P + ap * t1, a2 = d->tpom.delta_P + ap * t2;
+  const R Et = expl(a1 * logl(s13 * ap) + a2 * logl(s24 * ap)) / (16 * s13 * s24);
+  const R Eu = expl(a1 * logl(s14 * ap) + a2 * logl(s23 * ap)) / (16 * s14 * s23);
+  const R M2 = (R)d->nodes[0].mass * d->nodes[0].mass;
+  R Gt, Gu;
+  {
+    const grb_param_regge *Rg = &d->regge;
+    R tp = pt2 - M2, tu = pu2 - M2, ft, fu;
+    if (Rg->offshellFF == 2) { ft = 1 / (1 - tp / Rg->b_POW); fu = 1 / (1 - tu / Rg->b_POW); }
+    else if (Rg->offshellFF == 0) { ft = expl(-Rg->b_EXP * fabsl(tp)); fu = expl(-Rg->b_EXP * fabsl(tu)); }
+    else { ft = expl(-Rg->b_OREAR * sqrtl(fabsl(tp) + (R)Rg->a_OREAR * Rg->a_OREAR) + (R)Rg->a_OREAR * Rg->b_OREAR);
+           fu = expl(-Rg->b_OREAR * sqrtl(fabsl(tu) + (R)Rg->a_OREAR * Rg->a_OREAR) + (R)Rg->a_OREAR * Rg->b_OREAR); }
+    Gt = ft * ft / tp; Gu = fu * fu / tu;
+  }
+  const R gP = (d->nodes[0].mass < 0.2) ? d->tpom.gPpipi : d->tpom.gPKK;
+  /* F_M arguments as the reference forms them per vertex, iG_Ppsps(k',k): (k'-k)^2 (doubles) */
+  const v4 dpt = v4_sub(v4_sub(pa, p1), p3), dpu = v4_add(v4_sub(p4, pa), p1);
+  const R FMt = (1 / (1 - (R)v4_m2(v4_add(dpt, p3)) / 0.5L)) * (1 / (1 - (R)v4_m2(v4_sub(p4, dpt)) / 0.5L));
+  const R FMu = (1 / (1 - (R)v4_m2(v4_sub(p4, dpu)) / 0.5L)) * (1 / (1 - (R)v4_m2(v4_add(dpu, p3)) / 0.5L));
+  const R pre = 36 * (R)d->tpom.gPNN * d->tpom.gPNN * gP * gP * (R)o_F1(S, (double)t1) * (R)o_F1(S, (double)t2);
+  const R Rr = pre * (Et * Rt * FMt * Gt + Eu * Ru * FMu * Gu);
+  const R ph = -(R)3.141592653589793238462643383279502884L / 2 * (a1 + a2);
+  *re = (double)(cosl(ph) * Rr);
+  *im = (double)(sinl(ph) * Rr);
+#undef LV
+#undef LDOT
+  return (double)(Rr * Rr);
+}
+
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
     case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
-    case GRB_PROC_PP_CONTENSOR: return tensor_me4(S);
+    case GRB_PROC_PP_CONTENSOR: {
+      if (g_oracle_extended) {
+        double re, im;
+        const double a2 = tensor_me4_extended(S, &re, &im);
+        for (int h = 0; h < 4; ++h) S->hamp[h] = (cx){re, im};
+        S->nhamp = 4;
+        return a2;
+      }
+      return tensor_me4(S);
+    }
     default: S->nhamp = 0; return NAN;
   }
 }

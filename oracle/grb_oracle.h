@@ -24,6 +24,10 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
                     int32_t *tape_used);
 
+/* Evaluate the tensor-pomeron amplitude algebra in x87 extended precision from the same double inputs
+ * (measures the rounding noise of the reference's double-precision tensor contraction). Born level only. */
+void grb_oracle_set_extended(int on);
+
 #ifdef __cplusplus
 }
 #endif

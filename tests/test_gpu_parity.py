@@ -54,7 +54,9 @@ def test_device_vs_reference_golden(grb, msa, path):
     w, fl, dump = E.eval(z["u"].T.copy(), z["tape"].T.copy(), want_dump=True)
     rel = compare(w, fl, z["W"], z["flags"], kappa=z["kappa"])
     assert np.mean(rel > RTOL) < 1e-3 + 2.0 / len(rel), "too many points needed the conditioning term"
-    assert np.median(rel) < 1e-13
+    # Regge amplitudes reproduce the reference's operation order (median ~1e-15); the tensor-pomeron device
+    # code is the contracted closed form of the reference's FTensor loops (median ~1e-13)
+    assert np.median(rel) < (2e-12 if "TENSOR" in str(z["process"]) else 1e-13)
     kin = (z["flags"] & 1) == 1
     # intermediate scalars: absolute 2e-10 on t (t = dE^2 - dpz^2 - pt^2 cancels O(6500 GeV) roundings), relative elsewhere
     assert np.max(np.abs(dump[0][kin] - z["t1"][kin])) < 2e-10
@@ -132,12 +134,14 @@ def test_vegas_iteration_properties(grb, msa):
     assert b1.n_fid_ok + b2.n_fid_ok == a.n_fid_ok and max(b1.maxf, b2.maxf) == a.maxf
     # a different iteration index gives different points
     c = E.vegas_iterate(xmat, 0, N, 12345678, 4)
-    assert c.fsum != a.fsum and abs(c.fsum - a.fsum) < 0.05 * a.fsum
-    # uniform grid => vegasweight = 1 => sigma = fsum / N; flat-grid estimate of the reference's
-    # 2.311 +- 0.023 ub (ALICE cuts, screened) within MC error
-    sigma = a.fsum / N
-    err = np.sqrt(max(a.f2sum / N - sigma * sigma, 0) / N)
-    assert abs(sigma - 2.311e-6) < 5 * np.hypot(err, 0.023e-6), (sigma, err)
+    # uniform grid => vegasweight = 1 => sigma = fsum / N with MC error from f2sum
+    def est(x):
+        s_ = x.fsum / N
+        return s_, np.sqrt(max(x.f2sum / N - s_ * s_, 0) / N)
+    (sa, ea), (sc, ec) = est(a), est(c)
+    assert c.fsum != a.fsum and abs(sa - sc) < 5 * np.hypot(ea, ec), (sa, ea, sc, ec)
+    # flat-grid estimate vs the reference's 2.311 +- 0.023 ub (ALICE cuts, screened)
+    assert abs(sa - 2.311e-6) < 5 * np.hypot(ea, 0.023e-6), (sa, ea)
     E.close()
 
 

@@ -132,6 +132,10 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.M2_leg0 = d.nodes[0].mass * d.nodes[0].mass;
   P.b_EXP = R.b_EXP; P.a_OREAR = R.a_OREAR; P.b_OREAR = R.b_OREAR; P.b_POW = R.b_POW;
   P.me4_sign = (d.proc == GRB_PROC_PP_CON_MINUS) ? -1.0 : 1.0;
+  P.inv_fc1 = 1.0 / P.fc1; P.inv_fc2 = 1.0 / P.fc2; P.inv_b_POW = 1.0 / P.b_POW;
+  P.g2_const = (P.gpp_P * P.gN_P) * (P.gpp_P * P.gN_P);
+  P.eta0sq_re = P.eta0_re[0] * P.eta0_re[0] - P.eta0_im[0] * P.eta0_im[0];
+  P.eta0sq_im = 2.0 * P.eta0_re[0] * P.eta0_im[0];
   // tensor pomeron 2xS (reference src/MTensorPomeron.cc:726-763,1388-1399,2203-2215,2288-2298)
   {
     const double gP = (d.nodes[0].mass < 0.2) ? d.tpom.gPpipi : d.tpom.gPKK;
@@ -317,6 +321,8 @@ int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const do
     Q.aeik_re[j] = re[i] + dx * ((re[i + 1] - re[i]) / h);
     Q.aeik_im[j] = im[i] + dx * ((im[i + 1] - im[i]) / h);
     Q.wkt[j]     = w38(j, NKT);
+    Q.b_re[j]    = Q.aeik_re[j] * kt * Q.wkt[j];
+    Q.b_im[j]    = Q.aeik_im[j] * kt * Q.wkt[j];
   }
   for (int i = 0; i <= NPHI; ++i) {
     const double phi = 0.0 + i * StepPhi;
@@ -325,6 +331,13 @@ int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const do
     Q.wphi[i] = w38(i, NPHI);
   }
   Q.norm = (9 * (StepPhi * StepKT) / 64) * (1.0 / (8.0 * (GRB_PI * GRB_PI) * d.s));
+  // phi = 0 and phi = 2 pi are the same node up to sin(2 pi) = -2.4e-16: visit it once with both Simpson
+  // end weights (1 + 1).  Saves 1/(NPHI+1) of the loop; GRB_NO_PHI_FOLD=1 keeps the reference's N+1 nodes.
+  Q.nphi_nodes = NPHI + 1;
+  if (!getenv("GRB_NO_PHI_FOLD")) {
+    Q.wphi[0] += Q.wphi[NPHI];
+    Q.nphi_nodes = NPHI;
+  }
   e->have_loop = true;
   if (g_const_owner == e) g_const_owner = nullptr;  // force re-upload
   return GRB_OK;

@@ -59,6 +59,7 @@ struct DevProc {
   // Regge continuum (MRegge.cc:394-438, 888-906; MForm.cc:382-396,433-435)
   double a0[3], ap[3], ln_inv_s0, eta0_re[3], eta0_im[3], phase_c[3];  // phase_c = -pi/2 * ap
   double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
+  double inv_fc1, inv_fc2, inv_b_POW, g2_const, eta0sq_re, eta0sq_im;  // g2_const = (gpp_P gN_P)^2
   // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
   double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
   int    em_kelly, amp_kind;
@@ -68,10 +69,13 @@ struct DevProc {
 // screening loop discretisation + per-node eikonal amplitude (constant memory)
 struct DevLoop {
   int    nkt, nphi;                       // intervals: nodes are nkt+1, nphi+1
+  int    nphi_nodes, pad_;                // phi nodes visited: nphi+1, or nphi when phi=0 and phi=2pi are folded
   double kt[GRB_MAX_LOOP_KT];             // kt_j = MinLoopKT + j*StepKT
   double aeik_re[GRB_MAX_LOOP_KT];        // A_eik(kt_j^2), Interpolate1D done at table-set time
   double aeik_im[GRB_MAX_LOOP_KT];
   double wkt[GRB_MAX_LOOP_KT];            // Simpson 3/8 weights
+  double b_re[GRB_MAX_LOOP_KT];           // A_eik(kt_j^2) * kt_j * wkt_j
+  double b_im[GRB_MAX_LOOP_KT];
   double cphi[GRB_MAX_LOOP_PHI], sphi[GRB_MAX_LOOP_PHI], wphi[GRB_MAX_LOOP_PHI];
   double norm;                            // 9*StepPhi*StepKT/64 / (8 pi^2 s); hamp_loop = i*norm*sum
 };

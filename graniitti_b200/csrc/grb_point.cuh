@@ -312,26 +312,35 @@ struct NodeKin {
 };
 typedef NodeKin ReggeIn;
 
-__device__ __forceinline__ double meson_G(double x) {  // ff(x)^2 * prop(x), MRegge.cc:1155-1218
+// ff(x)^2 * prop(x) of MRegge.cc:1155-1218 as numerator / denominator (the caller divides once)
+__device__ __forceinline__ void meson_G_nd(double x, double &num, double &den) {
   const DevProc &P  = c_proc;
   const double   tp = x - P.M2_leg0;
   if (P.offshellFF == 2) {
-    const double d = 1.0 - tp / P.b_POW;
-    return 1.0 / (d * d * tp);
+    const double d = fma(-tp, P.inv_b_POW, 1.0);  // 1 - tp/b
+    num = 1.0;
+    den = d * d * tp;
   } else if (P.offshellFF == 0) {
     const double f = exp(-P.b_EXP * fabs(tp));
-    return f * f / tp;
+    num = f * f;
+    den = tp;
   } else {
     const double f = exp(-P.b_OREAR * msqrt(fabs(tp) + pow2(P.a_OREAR)) + P.a_OREAR * P.b_OREAR);
-    return f * f / tp;
+    num = f * f;
+    den = tp;
   }
+}
+__device__ __forceinline__ double meson_G(double x) {
+  double n, d;
+  meson_G_nd(x, n, d);
+  return n / d;
 }
 
 __device__ __forceinline__ cx regge_prop(double s, double t) {  // general PropOnly, MRegge.cc:888-906
   const DevProc &P = c_proc;
   cx             M = {0.0, 0.0};
   const double   ls = log(s) + P.ln_inv_s0;
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 3; ++k)
     if (P.regge_n[k]) {
       const double mag = exp((P.a0[k] + P.ap[k] * t) * ls);
@@ -344,31 +353,36 @@ __device__ __forceinline__ cx regge_prop(double s, double t) {  // general PropO
   return M;
 }
 
+// The amplitude algebra downstream of the kinematics is well conditioned and is organised for the fp64 pipe:
+// one division per evaluation (all form-factor and propagator denominators are multiplied up first),
+// contractions written as fma().
 __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
-  const DevProc &P   = c_proc;
-  const double   FFA = P.gN_P * ((1.0 / (1 - in.t1 / P.fc1)) * (1.0 / (1 - in.t1 / P.fc2)));  // S3F, MForm.cc:433
-  const double   FFB = P.gN_P * ((1.0 / (1 - in.t2 / P.fc1)) * (1.0 / (1 - in.t2 / P.fc2)));
-  const double   g2  = P.gpp_P * P.gpp_P * FFA * FFB;
-  const double   Gt = meson_G(in.t_hat), Gu = meson_G(in.u_hat) * P.me4_sign;
-  cx             A;
+  const DevProc &P = c_proc;
+  // S3F(t1) S3F(t2) = 1 / [(1-t1/fc1)(1-t1/fc2)(1-t2/fc1)(1-t2/fc2)], MForm.cc:433
+  const double dF = (fma(-in.t1, P.inv_fc1, 1.0) * fma(-in.t1, P.inv_fc2, 1.0)) *
+                    (fma(-in.t2, P.inv_fc1, 1.0) * fma(-in.t2, P.inv_fc2, 1.0));
+  double nt, dt, nu, du;
+  meson_G_nd(in.t_hat, nt, dt);
+  meson_G_nd(in.u_hat, nu, du);
+  nu *= P.me4_sign;
+  cx A;
   if (P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2]) {
     // single trajectory: one sincos, two exp, four log
-    const double a1 = P.a0[0] + P.ap[0] * in.t1, a2 = P.a0[0] + P.ap[0] * in.t2;
-    const double Et = exp(a1 * (log(in.ss13) + P.ln_inv_s0) + a2 * (log(in.ss24) + P.ln_inv_s0));
-    const double Eu = exp(a1 * (log(in.ss14) + P.ln_inv_s0) + a2 * (log(in.ss23) + P.ln_inv_s0));
-    const double R  = g2 * (Et * Gt + Eu * Gu);
+    const double a1 = fma(P.ap[0], in.t1, P.a0[0]), a2 = fma(P.ap[0], in.t2, P.a0[0]);
+    const double Et = exp(fma(a1, log(in.ss13) + P.ln_inv_s0, a2 * (log(in.ss24) + P.ln_inv_s0)));
+    const double Eu = exp(fma(a1, log(in.ss14) + P.ln_inv_s0, a2 * (log(in.ss23) + P.ln_inv_s0)));
+    // g2 (Et nt/dt + Eu nu/du) / dF
+    const double R = P.g2_const * fma(Et * nt, du, Eu * nu * dt) / (dt * du * dF);
     double       sn, cs;
     sincos(P.phase_c[0] * (in.t1 + in.t2), &sn, &cs);
-    // eta0^2
-    const double e2r = P.eta0_re[0] * P.eta0_re[0] - P.eta0_im[0] * P.eta0_im[0];
-    const double e2i = 2.0 * P.eta0_re[0] * P.eta0_im[0];
-    A.re = (e2r * cs - e2i * sn) * R;
-    A.im = (e2r * sn + e2i * cs) * R;
+    A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
+    A.im = fma(P.eta0sq_re, sn, P.eta0sq_im * cs) * R;
   } else {
     const cx P13 = regge_prop(in.ss13, in.t1), P24 = regge_prop(in.ss24, in.t2);
     const cx P14 = regge_prop(in.ss14, in.t1), P23 = regge_prop(in.ss23, in.t2);
     const double tr = P13.re * P24.re - P13.im * P24.im, ti = P13.re * P24.im + P13.im * P24.re;
     const double ur = P14.re * P23.re - P14.im * P23.im, ui = P14.re * P23.im + P14.im * P23.re;
+    const double g2 = P.g2_const / dF, Gt = nt / dt, Gu = nu / du;
     A.re = g2 * (tr * Gt + ur * Gu);
     A.im = g2 * (ti * Gt + ui * Gu);
   }
@@ -458,6 +472,7 @@ struct LoopInv {
   double p1x, p1y, p2x, p2y;
   double m1, m2, m1sq, m2sq, mXsq, shY, chY, emax;  // emax = sqrt_s - (m1 + m2)
   v4     p3, p4;
+  bool   same_mass;  // |m1 - m2| < 1e-9: SolvePz3_A branch (MKinematics.h:220-229)
 };
 
 template <int NN>
@@ -471,11 +486,15 @@ __device__ __forceinline__ void make_loop_inv(const PointState<NN> &S, LoopInv &
   L.shY  = sinh(yX);
   L.chY  = cosh(yX);
   L.emax = c_proc.sqrt_s - (L.m1 + L.m2);
+  L.same_mass = fabs(L.m1 - L.m2) < 1e-9;
   L.p3 = S.np4[0];
   L.p4 = S.np4[1];
 }
 
-__device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, double ktx, double kty, ReggeIn &o) {
+// One node of the loop.  The tests that can never fire are not evaluated: px, py, pz are conserved by
+// construction (X = -(n1+n2), p2z = -(Xz+p1z)), and ss[0][1], ss[0][2] >= (m_p + m_X)^2; the energy test of
+// CheckEMC, the direction test, ss13..ss24 >= 0 and t1, t2 <= 0 are kept.
+__device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, double ktx, double kty, NodeKin &o) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
   const double pt1 = msqrt(n1x * n1x + n1y * n1y), pt2 = msqrt(n2x * n2x + n2y * n2y);
@@ -483,24 +502,18 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   const double mtX = msqrt(L.mXsq + (Xx * Xx + Xy * Xy));
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   if (Xe > L.emax) return false;
-  const double p1z = solve_pz(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
+  const double p1z = L.same_mass ? solve_pz3_A(L.m1, pt1, pt2, Xz, Xe, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
   const double p2z = -(Xz + p1z);
   if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
   const double e1 = msqrt(L.m1sq + pow2(pt1) + pow2(p1z));
   const double e2 = msqrt(L.m2sq + pow2(pt2) + pow2(p2z));
-  {
-    const double dx = 0.0 - ((n1x + n2x) + Xx), dy = 0.0 - ((n1y + n2y) + Xy);
-    const double dz = P.bsum_z - ((p1z + p2z) + Xz), de = P.bsum_e - ((e1 + e2) + Xe);
-    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
-  }
+  if (P.bsum_e - ((e1 + e2) + Xe) > 1e-6) return false;  // CheckEMC energy component (not abs, MMath.h:191-198)
   const v4 &p3 = L.p3, &p4 = L.p4;
   o.ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
   o.ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
   o.ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
   o.ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
-  const double s01 = m2_of(n1x + Xx, n1y + Xy, p1z + Xz, e1 + Xe);
-  const double s02 = m2_of(n2x + Xx, n2y + Xy, p2z + Xz, e2 + Xe);
-  if (o.ss13 < 0 || o.ss14 < 0 || o.ss23 < 0 || o.ss24 < 0 || s01 < 0 || s02 < 0) return false;
+  if (o.ss13 < 0 || o.ss14 < 0 || o.ss23 < 0 || o.ss24 < 0) return false;
   const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
   o.t1 = m2_of(q1x, q1y, q1z, q1e);
   o.t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
@@ -513,27 +526,28 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
 }
 
 // reference src/MProcess.cc:157-288 S3ScreenedAmp2 for a one-amplitude process (H = 1): returns
-// |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order.
+// |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order
+// (phi = 2 pi folded onto phi = 0, see grb_set_eikonal).  Rejected nodes contribute 0 but keep their weight.
 template <int AMP>
 __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h0) {
   const DevLoop &Q = c_loop;
   PzConst        pc;
   pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
   double Ire = 0.0, Iim = 0.0;
-  for (int i = 0; i <= Q.nphi; ++i) {
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
     const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    double       Jre = 0.0, Jim = 0.0;
     for (int j = 0; j <= Q.nkt; ++j) {
       const double kt = Q.kt[j];
-      ReggeIn      in;
+      NodeKin      in;
       if (!loop_node(L, pc, kt * cp, kt * sp, in)) continue;
       const cx A = amplitude<AMP>(in, L.p3, L.p4);
-      // f = (A_eik * A) * kt ;  I += W_ij * f
-      const double fr = (Q.aeik_re[j] * A.re - Q.aeik_im[j] * A.im) * kt;
-      const double fi = (Q.aeik_re[j] * A.im + Q.aeik_im[j] * A.re) * kt;
-      const double w  = wi * Q.wkt[j];
-      Ire += w * fr;
-      Iim += w * fi;
+      // f = A_eik * A * kt * w_j, with b_j = A_eik(kt_j^2) kt_j w_j tabulated
+      Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
+      Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
     }
+    Ire = fma(wi, Jre, Ire);
+    Iim = fma(wi, Jim, Iim);
   }
   // hamp_loop = i * norm * I
   const double lr = -Q.norm * Iim, li = Q.norm * Ire;

@@ -24,11 +24,9 @@ for r in range(4):
 print("RESULT flags_ok=%%s med=%%.2e p99=%%.2e max=%%.2e frac>1e-10=%%.1e | ms=%%.2f screen_ms=%%.2f pts/s=%%.4g" %% (ok, np.median(rel), np.quantile(rel, .99), rel.max(), np.mean(rel > 1e-10), best, scr, N / best * 1e3))
 ''' % (ROOT, ROOT)
 configs = []
-for lib in ("libgrb.so", "libgrb_fmad.so"):
-    for minb in (3, 4, 5, 6):
-        configs.append({"GRB_LIB": os.path.join(ROOT, "graniitti_b200", lib), "GRB_SCREEN_MINB": str(minb)})
-configs.append({"GRB_LIB": os.path.join(ROOT, "graniitti_b200", "libgrb.so"), "GRB_SCREEN_MINB": "4", "GRB_CHUNK": str(1 << 21)})
-configs.append({"GRB_LIB": os.path.join(ROOT, "graniitti_b200", "libgrb.so"), "GRB_SCREEN_MINB": "4", "GRB_CHUNK": str(1 << 24)})
+L = os.path.join(ROOT, "graniitti_b200", "libgrb.so")
+for minb in (4, 3, 5, 6):
+    configs.append({"GRB_LIB": L, "GRB_SCREEN_MINB": str(minb)})
 for c in configs:
     env = dict(os.environ); env.update(c)
     r = subprocess.run([sys.executable, "-c", ONE], env=env, capture_output=True, text=True)

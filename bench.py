@@ -173,13 +173,6 @@ def run_reference(args):
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------
-class _DevArray:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -205,14 +198,10 @@ def run_ours(args):
              "fid": 0.0, "evals": 0.0}
 
     def step(it, timed):
-        ptr = E.vegas_iterate_async(state["xmat"], rank * ncalls, ncalls, seed, it)
+        ptr = E.vegas_iterate_async(state["xmat"], rank * ncalls, ncalls, seed, it)   # weak scaling: ncalls per GPU
         if world > 1:
             with torch.cuda.stream(ext):
-                t = torch.as_tensor(_DevArray(ptr, nacc), device=torch.device("cuda", local))
-                mx = t[10:12].clone()
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-                t[10:12] = mx
+                g.allreduce_accum(torch.as_tensor(g.DevArray(ptr, nacc), device=torch.device("cuda", local)))
         acc = E.vegas_fetch()                      # D2H of the accumulators (33 KB) + stream sync
         f2 = np.frombuffer(acc.f2mat, dtype=np.float64).reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM).copy()
         g.optimize_grid(state["xmat"], f2, 1.5)    # identical on every rank

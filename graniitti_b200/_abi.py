@@ -95,3 +95,19 @@ class Accum(C.Structure):
 
 
 ACCUM_NSUM = 10  # leading doubles that are sum-reduced; then maxW, maxf (max-reduced); then fmat, f2mat (sum)
+
+
+class VegasParam(C.Structure):
+    _fields_ = [("bins", i32), ("iter", i32), ("burnin_iter", i32), ("max_iter", i32), ("ncall", C.c_int64),
+                ("lambda_", f64), ("chi2max", f64), ("precision", f64), ("seed", C.c_uint64), ("debug", i32),
+                ("pad_", i32)]
+
+
+class VegasResult(C.Structure):
+    _fields_ = [(k, f64) for k in ("sigma", "sigma_err", "chi2", "maxW", "maxf", "evaluations", "n_kin_ok",
+                                   "n_fid_ok", "n_veto_ok", "n_amp_ok", "seconds", "device_ms")] + [
+        ("ncall_final", C.c_int64), ("iterations", i32), ("restarts", i32),
+        ("xmat", f64 * (GRB_MAX_BINS * GRB_MAX_DIM))]
+
+
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)

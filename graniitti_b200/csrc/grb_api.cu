@@ -2,8 +2,10 @@
 // the device VEGAS iteration.  No CPU fallback: every compute entry point needs a CUDA device and returns
 // GRB_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +39,10 @@ struct grb_engine {
   // scratch for host-pointer callers
   void * d_scratch     = nullptr;
   size_t scratch_bytes = 0;
+  // NCCL communicator (optional, loaded at run time)
+  void *nccl_comm = nullptr;
+  int   comm_rank = 0, comm_size = 1;
+  double *d_max2 = nullptr;
   // timing of the last call: ev0/ev1 bracket all launches, evk[] bracket each k_screen launch
   std::vector<cudaEvent_t> evk;
   int                      n_evk = 0;
@@ -186,6 +192,42 @@ static cudaEvent_t next_event(grb_engine *e) {
   return e->evk[e->n_evk++];
 }
 
+// ---- NCCL, resolved at run time so that the library neither links a second NCCL into a torch process nor
+// needs one for single-GPU use -------------------------------------------------------------------------------
+namespace {
+struct NcclId {  // ncclUniqueId (nccl.h: 128 opaque bytes), passed by value to ncclCommInitRank
+  char b[128];
+};
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(void *)                                                     = nullptr;
+  int (*CommInitRank)(void **, int, NcclId, int)                                 = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *)                                                     = nullptr;
+  const char *(*GetErrorString)(int)                                             = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl() {
+  static NcclApi a;
+  if (a.h) return a;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) break;
+  }
+  if (!a.h) return a;
+  a.GetUniqueId    = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+  a.CommInitRank   = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+  a.AllReduce      = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+  a.CommDestroy    = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy;
+  return a;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+constexpr int kAccSum = 10;                                   // leading sum-reduced doubles of grb_accum
+}  // namespace
+
 static int ensure_constants(grb_engine *e) {
   if (g_const_owner != e) {
     CK(upload_proc(e->dproc, e->stream));
@@ -281,7 +323,8 @@ void grb_destroy(grb_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_count);
-  cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch);
+  cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch); cudaFree(e->d_max2);
+  if (e->nccl_comm && nccl().ok) nccl().CommDestroy(e->nccl_comm);
   for (auto ev : e->evk) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -546,9 +589,165 @@ int grb_build_eikonal(grb_engine *e, int, int, double *, double *, double *, dou
   return GRB_ERR_UNSUPPORTED;
 }
 
-int grb_comm_unique_id(char *) { return GRB_ERR_UNSUPPORTED; }
-int grb_comm_init(grb_engine *, int, int, const char *) { return GRB_ERR_UNSUPPORTED; }
-int grb_allreduce(grb_engine *) { return GRB_ERR_UNSUPPORTED; }
+int grb_comm_unique_id(char id_out[128]) {
+  if (!id_out) return GRB_ERR_ARG;
+  NcclApi &n = nccl();
+  if (!n.ok) { g_last_global_error = "libnccl.so.2 not found"; return GRB_ERR_NCCL; }
+  return n.GetUniqueId(id_out) == 0 ? GRB_OK : GRB_ERR_NCCL;
+}
+
+int grb_comm_init(grb_engine *e, int rank, int nranks, const char id[128]) {
+  if (!e || !id || rank < 0 || nranks < 1 || rank >= nranks) return GRB_ERR_ARG;
+  NcclApi &n = nccl();
+  if (!n.ok) { e->err = "libnccl.so.2 not found"; return GRB_ERR_NCCL; }
+  CK(cudaSetDevice(e->device));
+  NcclId uid;
+  memcpy(uid.b, id, 128);
+  const int rc = n.CommInitRank(&e->nccl_comm, nranks, uid, rank);
+  if (rc != 0) { e->err = std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"); return GRB_ERR_NCCL; }
+  e->comm_rank = rank;
+  e->comm_size = nranks;
+  if (!e->d_max2) CK(cudaMalloc(&e->d_max2, 2 * sizeof(double)));
+  return GRB_OK;
+}
+
+// sum-reduce everything, then restore the max-reduced pair (maxW, maxf)
+int grb_allreduce(grb_engine *e) {
+  if (!e) return GRB_ERR_ARG;
+  if (!e->nccl_comm || e->comm_size <= 1) return GRB_OK;
+  NcclApi &n = nccl();
+  CK(cudaSetDevice(e->device));
+  double *acc = reinterpret_cast<double *>(e->d_acc);
+  const size_t nd = sizeof(grb_accum) / sizeof(double);
+  CK(cudaMemcpyAsync(e->d_max2, acc + kAccSum, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  int rc = n.AllReduce(acc, acc, nd, kNcclFloat64, kNcclSum, e->nccl_comm, e->stream);
+  if (rc == 0) rc = n.AllReduce(e->d_max2, e->d_max2, 2, kNcclFloat64, kNcclMax, e->nccl_comm, e->stream);
+  if (rc != 0) { e->err = std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"); return GRB_ERR_NCCL; }
+  CK(cudaMemcpyAsync(acc + kAccSum, e->d_max2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  return GRB_OK;
+}
+
+// reference VEGASData::GetLocalCalls (include/Graniitti/MVEGAS.h:59-69): floor(calls/R) each, remainder to rank 0
+int grb_local_calls(int64_t calls, int rank, int nranks, int64_t *first, int64_t *n) {
+  if (calls < 0 || nranks < 1 || rank < 0 || rank >= nranks || !first || !n) return GRB_ERR_ARG;
+  const int64_t per = calls / nranks, extra = calls - per * nranks;
+  *n     = per + (rank == 0 ? extra : 0);
+  *first = (rank == 0) ? 0 : extra + per * rank;
+  return GRB_OK;
+}
+
+// ---- the integration loop (reference MGraniitti::SampleVegas + VEGAS, src/MGraniitti.cc:1074-1339) -----------
+namespace {
+struct VegasState {
+  double sumdata = 0, sumchi2 = 0, sweight = 0;
+  double sigma = 0, sigma_err = 0, chi2 = 0;
+  double evals = 0, kin = 0, fid = 0, veto = 0, amp = 0, maxW = 0, maxf = 0, device_ms = 0;
+  int    iterations = 0;
+};
+
+// one VEGAS() call of the reference: init 0 = burn-in (fresh grid + fresh integral), 1 = keep grid, fresh integral.
+// returns 1 (done) or 10 (chi2 > 50: caller multiplies the calls by 10), negative on error
+int vegas_phase(grb_engine *e, const grb_vegas_param &par, int init, int64_t calls, int itermin, int rank, int nranks,
+                grb_reduce_fn reduce, void *ctx, std::vector<double> &xmat, uint64_t &iter_counter, VegasState &st) {
+  const int    dim = e->desc.lipsdim, bins = par.bins;
+  const double EPS = 1.0e-30;
+  if (init == 0)
+    for (int i = 0; i < bins; ++i)
+      for (int j = 0; j < dim; ++j) xmat[i * dim + j] = (i + 1.0) / bins;
+  st = VegasState();
+  int64_t my_first = 0, my_n = 0;
+  grb_local_calls(calls, rank, nranks, &my_first, &my_n);
+  const int max_iter = par.max_iter > 0 ? par.max_iter : 1000;
+  for (int iter = 0; iter < itermin; ++iter) {
+    void *dacc = nullptr;
+    int rc = grb_vegas_iterate_async(e, xmat.data(), bins, dim, my_first, my_n, par.seed, iter_counter++,
+                                     init == 0 ? GRB_MODE_BURNIN : GRB_MODE_INTEGRATE, 0.0, &dacc);
+    if (rc != GRB_OK) return rc;
+    if (nranks > 1) {
+      rc = reduce ? reduce(ctx, dacc) : grb_allreduce(e);
+      if (rc != GRB_OK) { if (reduce) e->err = "reduce callback failed"; return rc < 0 ? rc : GRB_ERR_NCCL; }
+    }
+    grb_accum acc;
+    rc = grb_vegas_fetch(e, &acc);
+    if (rc != GRB_OK) return rc;
+    double ms = 0;
+    grb_last_timing(e, &ms, nullptr);
+    st.device_ms += ms;
+    // estimates of this iteration (src/MGraniitti.cc:1222-1251)
+    double fsum = acc.fsum * (1.0 / (double)calls);
+    double f2sum = acc.f2sum * ((1.0 / (double)calls) * (1.0 / (double)calls));
+    const double I_this = fsum;
+    f2sum = std::sqrt(std::max(0.0, f2sum * calls));
+    f2sum = (f2sum - fsum) * (f2sum + fsum);
+    if (f2sum <= 0.0) f2sum = EPS;
+    const double I2_this = f2sum * 1.0 / (double)calls;
+    const double alpha = 1.0 / I2_this;
+    st.sumdata += alpha * I_this;
+    st.sumchi2 += alpha * I_this * I_this;
+    st.sweight += alpha;
+    st.sigma     = st.sumdata / st.sweight;
+    st.sigma_err = std::sqrt(std::max(0.0, 1.0 / st.sweight));
+    double chi2this = (st.sumchi2 - st.sumdata * st.sumdata / st.sweight) / (iter + 1E-5);
+    st.chi2 = chi2this < 0 ? 0.0 : chi2this;
+    st.iterations = iter + 1;
+    st.evals += acc.evaluations; st.kin += acc.n_kin_ok; st.fid += acc.n_fid_ok; st.veto += acc.n_veto_ok; st.amp += acc.n_amp_ok;
+    if (init != 0) { st.maxW = std::max(st.maxW, acc.maxW); st.maxf = std::max(st.maxf, acc.maxf); }
+    if (par.debug >= 0 && rank == 0)
+      printf("VEGAS:: local iter = %4d integral = %0.5E +- std = %0.5E \t [global integral = %0.5E +- std = %0.5E] \t chi2this = %0.2f \n",
+             iter + 1, I_this, std::sqrt(std::max(0.0, I2_this)), st.sigma, st.sigma_err, chi2this);
+    if (iter > 0) {
+      if (std::isnan(st.sigma) || std::isinf(st.sigma)) { e->err = "VEGAS:: Integral inf/nan: FATAL ERROR, cuts or parameters need fixing"; return GRB_ERR_STATE; }
+      if (st.sigma < 1e-60) { e->err = "VEGAS:: Integral < 1E-60: Check VEGAS parameters, decaymode sanity, generation and fiducial cuts!"; return GRB_ERR_STATE; }
+      if (st.chi2 > 50) return 10;
+    }
+    if (init > 0 && iter == itermin - 1 && itermin < max_iter &&
+        (st.chi2 > par.chi2max || st.sigma_err / st.sigma > par.precision))
+      ++itermin;
+    grb_vegas_optimize_grid(xmat.data(), acc.f2mat, bins, dim, par.lambda);
+  }
+  return 1;
+}
+}  // namespace
+
+int grb_integrate(grb_engine *e, const grb_vegas_param *par, int rank, int nranks, grb_reduce_fn reduce, void *ctx,
+                  grb_vegas_result *out) {
+  if (!e || !par || !out || nranks < 1 || rank < 0 || rank >= nranks) return GRB_ERR_ARG;
+  if (par->bins < 2 || par->bins > GRB_MAX_BINS || (par->bins % 2) != 0) { e->err = "VEGAS::BINS should be an even number <= 128"; return GRB_ERR_ARG; }
+  if (par->ncall < 50 || par->iter < 1 || par->lambda < 1.0 || par->lambda > 10.0) { e->err = "VEGAS parameters out of range"; return GRB_ERR_ARG; }
+  if (nranks > 1 && !reduce && !e->nccl_comm) { e->err = "multi-rank integration needs a reduce callback or grb_comm_init"; return GRB_ERR_STATE; }
+  const auto t0 = std::chrono::steady_clock::now();
+  memset(out, 0, sizeof(*out));
+  std::vector<double> xmat((size_t)par->bins * e->desc.lipsdim);
+  uint64_t   iter_counter = 0;
+  int64_t    ncall = par->ncall;
+  int        burn = par->burnin_iter > 0 ? par->burnin_iter : 3;
+  VegasState st;
+  double     device_ms = 0;
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    int factor;
+    do {  // burn-in until stable (src/MGraniitti.cc:1096-1103)
+      factor = vegas_phase(e, *par, 0, ncall, burn, rank, nranks, reduce, ctx, xmat, iter_counter, st);
+      device_ms += st.device_ms;
+      if (factor < 0) return factor;
+      if (factor != 1) { ncall *= factor; ++out->restarts; }
+    } while (factor != 1);
+    factor = vegas_phase(e, *par, 1, ncall, par->iter, rank, nranks, reduce, ctx, xmat, iter_counter, st);
+    device_ms += st.device_ms;
+    if (factor < 0) return factor;
+    if (factor == 1) break;
+    ncall *= factor;
+    burn *= 2;
+    ++out->restarts;
+  }
+  out->sigma = st.sigma; out->sigma_err = st.sigma_err; out->chi2 = st.chi2;
+  out->maxW = st.maxW; out->maxf = st.maxf;
+  out->evaluations = st.evals; out->n_kin_ok = st.kin; out->n_fid_ok = st.fid; out->n_veto_ok = st.veto; out->n_amp_ok = st.amp;
+  out->iterations = st.iterations; out->ncall_final = ncall; out->device_ms = device_ms;
+  for (int i = 0; i < par->bins; ++i)
+    for (int j = 0; j < e->desc.lipsdim; ++j) out->xmat[i * e->desc.lipsdim + j] = xmat[i * e->desc.lipsdim + j];
+  out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return GRB_OK;
+}
 
 int grb_measure_dfma_peak(int device, double *tflops_out) {
   if (!tflops_out) return GRB_ERR_ARG;

@@ -69,6 +69,11 @@ def lib():
         L.grb_measure_dfma_peak.argtypes = [cint, C.POINTER(dbl)]
         L.grb_last_timing.restype = cint
         L.grb_last_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(cint)]
+        L.grb_integrate.restype = cint
+        L.grb_integrate.argtypes = [vp, C.POINTER(_abi.VegasParam), cint, cint, _abi.REDUCE_FN, vp,
+                                    C.POINTER(_abi.VegasResult)]
+        L.grb_local_calls.restype = cint
+        L.grb_local_calls.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
         L.grb_get_stream.restype = vp
         L.grb_get_stream.argtypes = [vp]
         L.grb_last_timing_kernels.restype = cint
@@ -111,6 +116,15 @@ def optimize_grid(xmat, f2mat, lam=1.5):
     if rc != 0:
         raise GrbError(rc, "grb_vegas_optimize_grid")
     return xmat
+
+
+def local_calls(calls, rank, nranks):
+    """(first, n): the shard of one iteration that `rank` evaluates (reference MVEGAS.h:59-69)."""
+    first, n = C.c_int64(0), C.c_int64(0)
+    rc = lib().grb_local_calls(calls, rank, nranks, C.byref(first), C.byref(n))
+    if rc != 0:
+        raise GrbError(rc, "grb_local_calls")
+    return first.value, n.value
 
 
 def measure_dfma_peak(device=0):
@@ -193,6 +207,16 @@ class Engine:
         acc = _abi.Accum()
         self._check(lib().grb_vegas_fetch(self._h, C.byref(acc)))
         return acc
+
+    def integrate(self, ncall, iters=5, precision=0.01, chi2max=10.0, bins=128, lam=1.5, seed=12345678,
+                  burnin=3, rank=0, nranks=1, reduce=None, debug=-1, max_iter=0):
+        """Burn-in + integration (reference MGraniitti::Initialize -> SampleVegas). `reduce(device_ptr)` is
+        called once per iteration for nranks > 1 (e.g. a torch.distributed all-reduce on the buffer)."""
+        par = _abi.VegasParam(bins, iters, burnin, max_iter, ncall, lam, chi2max, precision, seed, debug, 0)
+        res = _abi.VegasResult()
+        cb = _abi.REDUCE_FN(lambda ctx, ptr: int(reduce(ptr) or 0)) if reduce else _abi.REDUCE_FN()
+        self._check(lib().grb_integrate(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
+        return res
 
     def sync(self):
         self._check(lib().grb_sync(self._h))

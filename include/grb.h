@@ -286,6 +286,52 @@ int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim
 int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, double *weights,
                        int *n_particles);
 
+/* ---- the integration loop (host C++, device iterations) ----------------------------------------------- */
+
+/* INTEGRALPARAM.VEGAS of the steering card (reference VEGASPARAM, include/Graniitti/MVEGAS.h:18-32) */
+typedef struct {
+  int32_t  bins;        /* BINS (even, <= GRB_MAX_BINS)                                                     */
+  int32_t  iter;        /* ITER: minimum iterations of the integration phase                               */
+  int32_t  burnin_iter; /* burn-in iterations (reference SampleVegas: 3)                                    */
+  int32_t  max_iter;    /* safety bound on the extended iteration count (0 = 1000)                         */
+  int64_t  ncall;       /* NCALL: points per iteration, summed over ranks                                  */
+  double   lambda;      /* LAMBDA                                                                          */
+  double   chi2max;     /* CHI2MAX                                                                         */
+  double   precision;   /* PRECISION: target relative error                                                */
+  uint64_t seed;        /* RNDSEED: Philox key                                                             */
+  int32_t  debug;       /* DEBUG >= 0 prints one line per iteration like the reference                     */
+  int32_t  pad_;
+} grb_vegas_param;
+
+typedef struct {
+  double  sigma, sigma_err, chi2; /* stat.sigma, stat.sigma_err, stat.chi2 (barn)                           */
+  double  maxW, maxf;             /* for the hit-or-miss generation phase                                  */
+  double  evaluations, n_kin_ok, n_fid_ok, n_veto_ok, n_amp_ok; /* integration-phase totals                */
+  double  seconds;                /* host wall time of the whole call                                      */
+  double  device_ms;              /* summed device time of all iterations on this rank                     */
+  int64_t ncall_final;            /* NCALL after the chi2 > 50 => x10 restarts                             */
+  int32_t iterations;             /* integration-phase iterations actually run                            */
+  int32_t restarts;
+  double  xmat[GRB_MAX_BINS * GRB_MAX_DIM]; /* converged grid [bins][dim]                                   */
+} grb_vegas_result;
+
+/* Called once per iteration with the DEVICE pointer of this rank's accumulators (layout grb_accum, on the
+ * stream of grb_get_stream); must leave the all-rank sums / maxima in place.  NULL = single rank, or the
+ * engine's own NCCL communicator when grb_comm_init was called.                                            */
+typedef int (*grb_reduce_fn)(void *ctx, void *device_accum);
+
+/* Burn-in + integration exactly as the reference drives them (MGraniitti::SampleVegas / VEGAS,
+ * src/MGraniitti.cc:1074-1339): grid refinement every iteration, weighted average of the iteration
+ * estimates, chi2, iteration extension until chi2 <= CHI2MAX and error <= PRECISION, x10 calls when
+ * chi2 > 50.  Rank r evaluates calls [r*n/R, (r+1)*n/R) of every iteration (remainder to rank 0,
+ * reference VEGASData::GetLocalCalls, MVEGAS.h:59-69).                                                      */
+int grb_integrate(grb_engine *e, const grb_vegas_param *par, int rank, int nranks, grb_reduce_fn reduce,
+                  void *ctx, grb_vegas_result *out);
+
+/* The shard of an iteration's calls that rank `rank` of `nranks` evaluates (reference
+ * VEGASData::GetLocalCalls, include/Graniitti/MVEGAS.h:59-69). Host-only.                                   */
+int grb_local_calls(int64_t calls, int rank, int nranks, int64_t *first, int64_t *n);
+
 /* ---- multi-GPU ------------------------------------------------------------------------------------- */
 
 /* NCCL communicator bootstrap for hosts without torch.distributed (a C++ MGraniitti on each rank):

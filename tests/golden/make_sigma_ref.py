@@ -1,0 +1,55 @@
+"""Reference cross sections for the sigma-parity tests: runs the UNMODIFIED reference CLI (oracle/_ref/gra/bin/gr,
+built by oracle/build_ref.sh) on copies of its own cards with only INTEGRALPARAM.VEGAS NCALL/PRECISION raised,
+and stores sigma +- err in tests/golden/sigma_ref.json.   python tests/golden/make_sigma_ref.py"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from helpers import GOLDEN, REF_GR, REF_TREE  # noqa: E402
+
+# name, card, process, pomloop, NCALL, PRECISION
+CASES = [
+    ("c2_alice_pipi_con_screened", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "true", 100000, 0.003),
+    ("c2_alice_pipi_con_born", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "false", 300000, 0.001),
+    ("c1_test_pipi_con_born", "input/test.json", "PP[CON]<F> -> pi+ pi-", "false", 300000, 0.001),
+    ("c1_test_pipi_tensor_born", "input/test.json", "PP[CONTENSOR]<F> -> pi+ pi-", "false", 300000, 0.001),
+    ("c2_alice_pipi_tensor_screened", "tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", "true", 20000, 0.01),
+    ("c5_cms_rhorho_4pi_con_born", "tests/processes/CMSCUTS.json",
+     "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", "false", 300000, 0.002),
+]
+
+
+def main():
+    out_path = os.path.join(GOLDEN, "sigma_ref.json")
+    res = json.load(open(out_path)) if os.path.exists(out_path) else {}
+    only = sys.argv[1:]
+    for name, card, proc, pom, ncall, prec in CASES:
+        if only and name not in only:
+            continue
+        txt = open(os.path.join(REF_TREE, card)).read()
+        txt = re.sub(r'("NCALL"\s*:\s*)\d+', r"\g<1>%d" % ncall, txt)
+        txt = re.sub(r'("VEGAS"\s*:\s*\{[^}]*?"PRECISION"\s*:\s*)[0-9.eE+-]+', r"\g<1>%g" % prec, txt, flags=re.S)
+        tmp = os.path.join(REF_TREE, "output", f"sigma_{name}.json")
+        open(tmp, "w").write(txt)
+        r = subprocess.run([REF_GR, "-i", tmp, "-p", proc, "-l", pom, "-n", "0", "-h", "0", "-c", str(os.cpu_count())],
+                           cwd=REF_TREE, capture_output=True, text=True)
+        clean = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout)
+        m = re.search(r"cross section\}:\s*\[([0-9.eE+-]+) \+- ([0-9.eE+-]+)\] barn", clean)
+        f = re.search(r"Integrand sampling frequency:\s*([0-9.eE+-]+) Hz", clean)
+        p = re.search(r"Fiducial cuts passing rate:\s*([0-9.eE+-]+)", clean)
+        if not m:
+            print(name, "FAILED", clean[-800:], r.stderr[-400:])
+            continue
+        res[name] = {"card": card, "process": proc, "pomloop": pom == "true", "sigma_barn": float(m.group(1)),
+                     "err_barn": float(m.group(2)), "ncall": ncall, "precision": prec,
+                     "ref_points_per_s": float(f.group(1)) if f else None, "fid_pass": float(p.group(1)) if p else None,
+                     "cores": os.cpu_count()}
+        print(name, res[name], flush=True)
+        json.dump(res, open(out_path, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,3 +161,31 @@ def test_vegas_matches_eval_on_same_points(grb, msa):
     assert abs(f.sum() - a.fsum) <= 1e-12 * a.fsum and abs((f * f).sum() - a.f2sum) <= 1e-12 * a.f2sum
     assert a.maxf == f.max()
     E.close()
+
+
+SIGMA_CASES = [  # name in tests/golden/sigma_ref.json, card, ncall, iters, precision
+    ("c2_alice_pipi_con_screened", "c2_alice.json", 1 << 21, 5, 0.001),
+    ("c2_alice_pipi_con_born", "c2_alice.json", 1 << 21, 5, 0.0005),
+    ("c1_test_pipi_con_born", "c1_test13.json", 1 << 21, 5, 0.0005),
+    ("c1_test_pipi_tensor_born", "c1_test13.json", 1 << 21, 5, 0.0005),
+    ("c2_alice_pipi_tensor_screened", "c2_alice.json", 1 << 20, 5, 0.002),
+    ("c5_cms_rhorho_4pi_con_born", "c5_cms_4pi.json", 1 << 21, 5, 0.001),
+]
+
+
+@pytest.mark.parametrize("name,card,ncall,iters,prec", SIGMA_CASES, ids=[c[0] for c in SIGMA_CASES])
+def test_cross_section_matches_reference(grb, msa, name, card, ncall, iters, prec):
+    """Full adaptive integration on the device (grb_integrate: burn-in, grid refinement, chi2 control) against
+    sigma +- err of the unmodified reference CLI (tests/golden/make_sigma_ref.py): agreement within the combined
+    Monte Carlo error.  The reference prints 4 significant digits, which is added to its error."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "sigma_ref.json")))[name]
+    E = engine_for(grb, msa, card, ref["process"], int(ref["pomloop"]))
+    r = E.integrate(ncall=ncall, iters=iters, precision=prec, seed=20261017)
+    err_ref = np.hypot(ref["err_barn"], 0.5e-3 * ref["sigma_barn"])
+    pull = (r.sigma - ref["sigma_barn"]) / np.hypot(r.sigma_err, err_ref)
+    assert r.chi2 < 10 and r.sigma_err / r.sigma <= prec * 1.0001
+    assert abs(pull) < 4.0, (r.sigma, r.sigma_err, ref["sigma_barn"], ref["err_barn"], pull)
+    # the reference's fiducial pass rate is a property of the converged grid, not of the RNG
+    assert abs(r.n_fid_ok / r.evaluations - ref["fid_pass"]) < 0.02
+    E.close()

@@ -33,6 +33,10 @@ struct grb_engine {
   int32_t *     d_item_idx = nullptr;
   uint64_t *    d_item_bins = nullptr;
   unsigned int *d_item_count = nullptr;
+  // event generation buffers (allocated on first GRB_MODE_GENERATE call)
+  double *      d_ev = nullptr, *d_pay = nullptr;
+  unsigned int *d_ev_count = nullptr;
+  int64_t       ev_cap = 0;
   // VEGAS
   grb_accum *d_acc  = nullptr;
   double *   d_xmat = nullptr;
@@ -324,6 +328,7 @@ void grb_destroy(grb_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_count);
   cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch); cudaFree(e->d_max2);
+  cudaFree(e->d_ev); cudaFree(e->d_pay); cudaFree(e->d_ev_count);
   if (e->nccl_comm && nccl().ok) nccl().CommDestroy(e->nccl_comm);
   for (auto ev : e->evk) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -474,8 +479,19 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
                             void **accum_device_ptr) {
   if (!e || !xmat || bins < 2 || bins > GRB_MAX_BINS || dim != e->desc.lipsdim || ncalls < 0) return GRB_ERR_ARG;
   if (e->desc.screening && !e->have_loop) { e->err = "screening is on but no eikonal table was set"; return GRB_ERR_STATE; }
-  if (mode == GRB_MODE_GENERATE) { e->err = "event generation mode is not implemented yet"; return GRB_ERR_UNSUPPORTED; }
   CK(cudaSetDevice(e->device));
+  const int npart = 3 + e->desc.n_nodes;
+  if (mode == GRB_MODE_GENERATE) {
+    if (!(maxf > 0.0)) { e->err = "generation mode needs maxf > 0 (from the integration phase)"; return GRB_ERR_ARG; }
+    if (!e->d_ev) {
+      const char *ec = getenv("GRB_EVENT_CAP");
+      e->ev_cap = ec ? std::max<int64_t>(1024, atoll(ec)) : (int64_t)1 << 22;
+      CK(cudaMalloc(&e->d_ev, sizeof(double) * (4 * npart + 2) * e->ev_cap));
+      CK(cudaMalloc(&e->d_ev_count, 2 * sizeof(unsigned int)));
+      if (e->desc.screening) CK(cudaMalloc(&e->d_pay, sizeof(double) * 4 * npart * e->chunk));
+    }
+    CK(cudaMemsetAsync(e->d_ev_count, 0, 2 * sizeof(unsigned int), e->stream));
+  }
   int rc = ensure_constants(e);
   if (rc != GRB_OK) return rc;
   CK(cudaMemcpyAsync(e->d_xmat, xmat, sizeof(double) * bins * dim, cudaMemcpyHostToDevice, e->stream));
@@ -490,6 +506,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.ld = a.n; a.dim = dim;
     a.vegas = 1; a.bins = bins; a.mode = mode; a.xmat = e->d_xmat; a.seed = seed; a.iter = (uint32_t)iteration;
     a.first_call = first_call + off; a.maxf = maxf;
+    a.ev_out = e->d_ev; a.ev_count = e->d_ev_count; a.ev_cap = e->ev_cap; a.npart = npart; a.pay = e->d_pay;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
@@ -514,6 +531,12 @@ int grb_vegas_fetch(grb_engine *e, grb_accum *out) {
   CK(cudaStreamSynchronize(e->stream));
   // points that are not Valid() keep amplitude_ok = true in the reference (AuxIntData default)
   out->n_amp_ok = out->evaluations - out->n_nan_inf;
+  if (e->d_ev_count) {
+    unsigned int c[2] = {0, 0};
+    CK(cudaMemcpy(c, e->d_ev_count, sizeof(c), cudaMemcpyDeviceToHost));
+    out->n_accepted = (double)c[0];
+    out->n_overflow = (double)c[1];
+  }
   return GRB_OK;
 }
 
@@ -579,9 +602,23 @@ int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim
   return GRB_OK;
 }
 
-int64_t grb_get_events(grb_engine *e, int64_t, double *, double *, int *) {
-  if (e) e->err = "event generation mode is not implemented yet";
-  return GRB_ERR_UNSUPPORTED;
+int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, double *weights, int *n_particles) {
+  if (!e || max_events < 0) return GRB_ERR_ARG;
+  const int npart = 3 + e->desc.n_nodes;
+  if (n_particles) *n_particles = npart;
+  if (!e->d_ev) return 0;
+  if (cudaSetDevice(e->device) != cudaSuccess) return GRB_ERR_CUDA;
+  unsigned int c[2] = {0, 0};
+  if (cudaMemcpy(c, e->d_ev_count, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return GRB_ERR_CUDA;
+  const int64_t n = std::min<int64_t>(std::min<int64_t>((int64_t)c[0], e->ev_cap), max_events);
+  if (n == 0) return 0;
+  // device rows have stride ev_cap; the caller's arrays are [npart][4][n] and [2][n] (W, f)
+  if (momenta && cudaMemcpy2D(momenta, sizeof(double) * n, e->d_ev, sizeof(double) * e->ev_cap, sizeof(double) * n,
+                              4 * npart, cudaMemcpyDeviceToHost) != cudaSuccess) return GRB_ERR_CUDA;
+  if (weights && cudaMemcpy2D(weights, sizeof(double) * n, e->d_ev + (int64_t)4 * npart * e->ev_cap,
+                              sizeof(double) * e->ev_cap, sizeof(double) * n, 2, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return GRB_ERR_CUDA;
+  return n;
 }
 
 int grb_build_eikonal(grb_engine *e, int, int, double *, double *, double *, double *) {

@@ -106,6 +106,13 @@ struct PointArgs {
   int64_t       item_cap;
   // accumulators (device)
   grb_accum *acc;
+  // event generation (mode == GRB_MODE_GENERATE): hit-or-miss accepted events, SoA [npart*4 + 2][ev_cap]
+  // rows: px,py,pz,E of lts.pfinal[0..2] then of every decay-tree node; then W and f = W * vegasweight
+  double *      ev_out;
+  unsigned int *ev_count;    // [0] accepted events written, [1] overflows (f > maxf)
+  int64_t       ev_cap;
+  int           npart;       // 3 + n_nodes
+  double *      pay;         // screened generation: per work-list slot payload [npart*4][item_cap]
 };
 
 // launchers implemented in grb_kernels.cu

@@ -84,6 +84,40 @@ __device__ __forceinline__ void hist_flush(int nb, int dim, grb_accum *acc) {
   }
 }
 
+// ---- hit-or-miss (reference MGraniitti::SaveEvent accept test, src/MGraniitti.cc:1657-1668) ------------------
+// The uniform is draw #63 of the point's Philox stream (the kinematics never reaches it), so the decision is
+// a pure function of (seed, iteration, global point index, maxf).
+__device__ __forceinline__ double hitmiss_uniform(uint64_t seed, uint32_t iter, uint64_t gp) {
+  Philox g;
+  g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+  uint32_t o[4];
+  g.block((uint32_t)gp, (uint32_t)(gp >> 32), iter, 31u, o);
+  return u01_from_bits(o[3], o[2]);
+}
+// returns the event slot (or -1): accepted iff U < f / maxf; f > maxf counts as an overflow (still accepted)
+__device__ __forceinline__ int64_t hitmiss_slot(const PointArgs &a, double f, uint64_t gp) {
+  if (!(f > 0.0)) return -1;
+  if (f > a.maxf) atomicAdd(a.ev_count + 1, 1u);
+  if (!(hitmiss_uniform(a.seed, a.iter, gp) < f / a.maxf)) return -1;
+  const unsigned int slot = atomicAdd(a.ev_count, 1u);
+  return slot < a.ev_cap ? (int64_t)slot : -1;
+}
+template <int NN>
+__device__ __forceinline__ void store_momenta(double *dst, int64_t stride, const PointState<NN> &S, int n_nodes) {
+  const v4 *three[3] = {&S.pX, &S.p1, &S.p2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dst[(4 * k + 0) * stride] = three[k]->x; dst[(4 * k + 1) * stride] = three[k]->y;
+    dst[(4 * k + 2) * stride] = three[k]->z; dst[(4 * k + 3) * stride] = three[k]->e;
+  }
+#pragma unroll
+  for (int i = 0; i < NN; ++i)
+    if (i < n_nodes) {
+      dst[(12 + 4 * i + 0) * stride] = S.np4[i].x; dst[(12 + 4 * i + 1) * stride] = S.np4[i].y;
+      dst[(12 + 4 * i + 2) * stride] = S.np4[i].z; dst[(12 + 4 * i + 3) * stride] = S.np4[i].e;
+    }
+}
+
 // ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
 template <int NN, int AMP>
 __device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
@@ -202,6 +236,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
             it[IT_PREF * c] = pref; it[IT_VW * c] = vw;
             a.item_idx[slot]  = (int32_t)idx;
             a.item_bins[slot] = packed;
+            if (VEGAS && a.mode == GRB_MODE_GENERATE) store_momenta<NN>(a.pay + slot, c, S, P.n_nodes);
           }
         }
       }
@@ -236,6 +271,14 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
           ts.maxW = fmax(ts.maxW, W);
           ts.maxf = fmax(ts.maxf, f);
           hist_add(nb, dim, packed, f);
+          if (a.mode == GRB_MODE_GENERATE) {
+            const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
+            if (es >= 0) {
+              store_momenta<NN>(a.ev_out + es, a.ev_cap, S, P.n_nodes);
+              a.ev_out[(4 * a.npart + 0) * a.ev_cap + es] = W;
+              a.ev_out[(4 * a.npart + 1) * a.ev_cap + es] = f;
+            }
+          }
         }
       }
     }
@@ -285,6 +328,14 @@ __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
       ts.maxW = fmax(ts.maxW, W);
       ts.maxf = fmax(ts.maxf, f);
       hist_add(nb, dim, a.item_bins[s], f);
+      if (a.mode == GRB_MODE_GENERATE) {
+        const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
+        if (es >= 0) {
+          for (int r = 0; r < 4 * a.npart; ++r) a.ev_out[(int64_t)r * a.ev_cap + es] = a.pay[(int64_t)r * c + s];
+          a.ev_out[(4 * a.npart + 0) * a.ev_cap + es] = W;
+          a.ev_out[(4 * a.npart + 1) * a.ev_cap + es] = f;
+        }
+      }
     }
   }
   flush_sums(ts, a.acc);

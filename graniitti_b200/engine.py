@@ -218,6 +218,20 @@ class Engine:
         self._check(lib().grb_integrate(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
         return res
 
+    def get_events(self, max_events=1 << 22):
+        """(momenta [npart][4][n], weights [2][n]) of the events accepted by the last GENERATE iteration."""
+        npart = 3 + self.desc.n_nodes
+        mom = np.zeros((npart, 4, max_events))
+        wts = np.zeros((2, max_events))
+        npp = C.c_int(0)
+        n = lib().grb_get_events(self._h, max_events, mom.ctypes.data, wts.ctypes.data, C.byref(npp))
+        if n < 0:
+            self._check(int(n))
+        # the library packs rows with stride n
+        mom = mom.reshape(-1)[:npart * 4 * n].reshape(npart, 4, n)
+        wts = wts.reshape(-1)[:2 * n].reshape(2, n)
+        return mom, wts
+
     def sync(self):
         self._check(lib().grb_sync(self._h))
 

@@ -280,9 +280,12 @@ int grb_vegas_fetch(grb_engine *e, grb_accum *out);
  * function, O(bins*dim), run redundantly on every rank from the all-reduced f2mat.                        */
 int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim, double lambda);
 
-/* Accepted events of the last GRB_MODE_GENERATE iteration: 4-momenta [n_particles][4][n_events] SoA
- * (particle 0 = central system, 1,2 = forward protons, 3.. = central final states as lts.pfinal) and the
- * weights.  Host pointers; returns the number of events copied (<= max_events) or a negative error.       */
+/* Accepted events of the last GRB_MODE_GENERATE iteration: 4-momenta [n_particles][4][n_events] SoA with
+ * n_events = the return value (particle 0 = central system, 1,2 = forward protons = lts.pfinal[0..2], then
+ * one per decay-tree node in grb_process_desc.nodes order) and weights [2][n_events] = (W, f = W*vegasweight).
+ * Host pointers; returns the number of events copied (<= max_events) or a negative error.  A point is
+ * accepted iff U < f/maxf with U = draw #63 of its Philox stream (reference SaveEvent, MGraniitti.cc:
+ * 1657-1668); grb_accum.n_accepted / n_overflow report the totals of the iteration.                        */
 int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, double *weights,
                        int *n_particles);
 

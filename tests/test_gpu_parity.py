@@ -189,3 +189,47 @@ def test_cross_section_matches_reference(grb, msa, name, card, ncall, iters, pre
     # the reference's fiducial pass rate is a property of the converged grid, not of the RNG
     assert abs(r.n_fid_ok / r.evaluations - ref["fid_pass"]) < 0.02
     E.close()
+
+
+@pytest.mark.parametrize("pom", [0, 1], ids=["born", "screened"])
+def test_event_generation_hit_or_miss(grb, msa, pom):
+    """GRB_MODE_GENERATE (reference SaveEvent accept test, MGraniitti.cc:1657-1668): the accepted set is a pure
+    function of (seed, iteration, point index, maxf); its size follows sum(f)/maxf; accepted events conserve
+    4-momentum and reproduce the weights of the integration pass."""
+    E = engine_for(grb, msa, "c2_alice.json", None, pom)
+    r = E.integrate(ncall=1 << 19, iters=3, precision=0.01, seed=5)
+    bins, dim = 128, 6
+    xmat = np.frombuffer(r.xmat, dtype=np.float64)[:bins * dim].reshape(bins, dim).copy()
+    N = 1 << 20
+    ref = E.vegas_iterate(xmat, 0, N, 99, 7)                                   # integration pass, same points
+    acc = E.vegas_iterate(xmat, 0, N, 99, 7, mode=_abi.GRB_MODE_GENERATE, maxf=r.maxf)
+    assert abs(acc.fsum - ref.fsum) <= 1e-12 * ref.fsum and acc.n_fid_ok == ref.n_fid_ok
+    mom, wts = E.get_events()
+    n = mom.shape[2]
+    assert n == int(acc.n_accepted) and n > 100
+    expected = min(acc.fsum / r.maxf, N)
+    assert abs(n - expected) < 6 * np.sqrt(expected) + acc.n_overflow, (n, expected)
+    pX, p1, p2, p3, p4 = mom[0], mom[1], mom[2], mom[3], mom[4]
+    tot = p1 + p2 + pX
+    assert np.max(np.abs(tot[:3])) < 1e-6 and np.max(np.abs(tot[3] - 13000.0)) < 1e-6
+    assert np.max(np.abs(pX - (p3 + p4))) < 1e-9
+    W, f = wts
+    assert np.all(W > 0) and np.all(f > 0) and (f > r.maxf).sum() <= acc.n_overflow
+    # every accepted pion passes the fiducial cuts of the card (|eta| < 0.9, pt > 0.15)
+    for p in (p3, p4):
+        pt = np.hypot(p[0], p[1])
+        eta = np.arcsinh(p[2] / pt)
+        assert np.all(pt >= 0.15) and np.all(np.abs(eta) <= 0.9)
+    # reproducible: the same call accepts the same events (as a set; slot order is not defined)
+    acc2 = E.vegas_iterate(xmat, 0, N, 99, 7, mode=_abi.GRB_MODE_GENERATE, maxf=r.maxf)
+    mom2, wts2 = E.get_events()
+    assert acc2.n_accepted == acc.n_accepted
+    assert np.array_equal(np.sort(wts[1]), np.sort(wts2[1]))
+    # sharding the call range accepts the same events
+    a1 = E.vegas_iterate(xmat, 0, N // 2, 99, 7, mode=_abi.GRB_MODE_GENERATE, maxf=r.maxf)
+    w1 = E.get_events()[1][1].copy()
+    a2 = E.vegas_iterate(xmat, N // 2, N - N // 2, 99, 7, mode=_abi.GRB_MODE_GENERATE, maxf=r.maxf)
+    w2 = E.get_events()[1][1].copy()
+    assert a1.n_accepted + a2.n_accepted == acc.n_accepted
+    assert np.array_equal(np.sort(np.concatenate([w1, w2])), np.sort(wts[1]))
+    E.close()

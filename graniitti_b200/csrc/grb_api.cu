@@ -26,6 +26,7 @@ struct grb_engine {
   grb_process_desc desc;
   DevProc          dproc;
   DevLoop          dloop;
+  DevRes           dres;
   bool             have_loop = false;
   // screening work list (one chunk)
   int64_t       chunk      = 0;
@@ -82,7 +83,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.excitation != 0) { err = "NSTARS != 0 is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
-  if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR) {
+  if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR &&
+      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON) {
     err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
     return GRB_ERR_UNSUPPORTED;
   }
@@ -154,7 +156,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     P.tp_phase = -GRB_PI / 2.0;
     P.four_mp2 = (2 * 0.938272081) * (2 * 0.938272081);  // PDG::mp, reference MPDG.h:54
     P.em_kelly = d.em_ff;
-    P.amp_kind = (d.proc == GRB_PROC_PP_CONTENSOR) ? 1 : 0;
+    P.amp_kind = (d.proc == GRB_PROC_PP_CONTENSOR) ? 1 : (d.proc == GRB_PROC_PP_RES ? 2 : (d.proc == GRB_PROC_PP_RES_CON ? 3 : 0));
+    P.omega = d.regge.omega;
   }
   // nodes
   for (int i = 0; i < d.n_nodes; ++i) {
@@ -232,9 +235,58 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;  // ncclDataType_t /
 constexpr int kAccSum = 10;                                   // leading sum-reduced doubles of grb_accum
 }  // namespace
 
+static double hfact(int n) {
+  double x = 1;
+  for (int i = 1; i <= n; ++i) x *= i;
+  return x;
+}
+
+// grb_resonance[] -> DevRes (host libm for the per-resonance constants)
+static int digest_res(const grb_process_desc &d, DevRes &R, std::string &err) {
+  memset(&R, 0, sizeof(R));
+  if (d.n_res < 0 || d.n_res > GRB_MAX_RES) { err = "bad n_res"; return GRB_ERR_ARG; }
+  if ((d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON) && d.n_res > 0 &&
+      !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0 && d.n_nodes == 2)) {
+    err = "resonances: only two spinless final-state daughters are on the device path";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  R.n = d.n_res;
+  for (int i = 0; i < d.n_res; ++i) {
+    const grb_resonance &s = d.res[i];
+    DevResonance &       o = R.r[i];
+    if (s.spinX2 < 0 || s.spinX2 > 4 || (s.spinX2 % 2) != 0) { err = "resonance spin must be J = 0, 1 or 2 on the device path"; return GRB_ERR_UNSUPPORTED; }
+    if (s.T_rows != 1 || s.T_cols != 1) { err = "resonance decay T matrix must be 1x1 (spinless daughters)"; return GRB_ERR_UNSUPPORTED; }
+    o.spinX2 = s.spinX2; o.P = s.P; o.BW = s.BW; o.spingen = s.spingen; o.spindec = s.spindec; o.frame = s.frame;
+    o.photo = ((int)(s.spinX2 / 2.0) == 1 && s.P == -1) ? 1 : 0;
+    o.mass = s.mass; o.width = s.width; o.M2 = s.mass * s.mass; o.g_re = s.g_re; o.g_im = s.g_im;
+    const double g2 = s.g_FF * s.g_FF;
+    o.inv_gFF4 = 1.0 / (g2 * g2);
+    o.g_decay = s.g_decay;
+    o.B0 = std::pow(std::max(0.7 * 0.7, o.M2) / 2.0, -GRB_PI / 2.0) + 3 * GRB_PI / 2.0;
+    for (int k = 0; k < 9; ++k) { o.T_re[k] = s.T_re[k]; o.T_im[k] = s.T_im[k]; }
+    for (int k = 0; k < 25; ++k) { o.rho_re[k] = s.rho_re[k]; o.rho_im[k] = s.rho_im[k]; }
+    if (o.photo) R.any_photo = 1;
+    if (o.BW == 3) R.bw3 = 1;
+  }
+  for (int J = 1; J <= 2; ++J)
+    for (int i = 0; i <= 2 * J; ++i)
+      for (int j = 0; j <= 2 * J; ++j) {
+        const int m = i - J, mp = j - J;
+        const double factor = std::sqrt(hfact(J + m) * hfact(J - m) * hfact(J + mp) * hfact(J - mp));
+        for (int k = 0; k <= 2 * J; ++k) {
+          double c = 0.0;
+          if (J - mp - k >= 0 && J + m - k >= 0 && k + mp - m >= 0)
+            c = factor * std::pow(-1.0, mp - m + k) / (hfact(J - mp - k) * hfact(J + m - k) * hfact(k + mp - m) * hfact(k));
+          R.wd[J - 1][(i * 5 + j) * 5 + k] = c;
+        }
+      }
+  return GRB_OK;
+}
+
 static int ensure_constants(grb_engine *e) {
   if (g_const_owner != e) {
     CK(upload_proc(e->dproc, e->stream));
+    CK(upload_res(e->dres, e->stream));
     if (e->have_loop) CK(upload_loop(e->dloop, e->stream));
     g_const_owner = e;
   }
@@ -260,6 +312,7 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
   e->desc       = *desc;
   e->device     = device;
   int rc        = digest(*desc, e->dproc, e->err);
+  if (rc == GRB_OK) rc = digest_res(*desc, e->dres, e->err);
   if (rc != GRB_OK) {
     g_last_global_error = e->err;
     delete e;

@@ -31,6 +31,36 @@ static const char *const kBuiltinTune0 = R"JSON({
 "PARAM_STRUCTURE": {"F2": "CKMT", "EM": "KELLY", "QED_alpha": "ZERO"}
 })JSON";
 
+// Resonance parameter sets (values of reference modeldata/TUNE0/RES_<name>.json; same keys).
+static const struct {
+  const char *name, *json;
+} kBuiltinRes[] = {
+    {"f0_500", R"J({"PARAM_RES":{"PDG":9000221,"M":0.5,"W":0.4,"J":0,"P":1,"BW":2,"g_Tensor":[0.1,0.0],"random_rho":0,"g_A":0.05,"g_phi":-3.14159,"g_FF":1.0,"rho_real":[[0]],"rho_imag":[[0]]}})J"},
+    {"f0_980", R"J({"PARAM_RES":{"PDG":9010221,"M":0.98,"W":0.08,"J":0,"P":1,"BW":2,"g_Tensor":[0.4,2.0],"random_rho":0,"g_A":0.065,"g_phi":-3.14159,"g_FF":1.0,"rho_real":[[0]],"rho_imag":[[0]]}})J"},
+    {"f0_1500", R"J({"PARAM_RES":{"PDG":9030221,"M":1.506,"W":0.112,"J":0,"P":1,"BW":2,"g_Tensor":[0.1,0.0],"random_rho":0,"g_A":0.03,"g_phi":-3.14159,"g_FF":1.0,"rho_real":[[0]],"rho_imag":[[0]]}})J"},
+    {"f0_1710", R"J({"PARAM_RES":{"PDG":10331,"M":1.704,"W":0.123,"J":0,"P":1,"BW":2,"g_Tensor":[0.45,2.6],"random_rho":0,"g_A":0.03,"g_phi":-3.14159,"g_FF":1.0,"rho_real":[[0]],"rho_imag":[[0]]}})J"},
+    {"rho_770", R"J({"PARAM_RES":{"PDG":113,"M":0.77526,"W":0.1491,"J":1,"P":-1,"BW":2,"g_Tensor":[0.7,6.2],"random_rho":0,"g_A":0.19,"g_phi":-2.36,"g_FF":1.0,"rho_real":[[0.5,0,0],[0,0,0],[0,0,0.5]],"rho_imag":[[0,0,0],[0,0,0],[0,0,0]]}})J"},
+    {"phi_1020", R"J({"PARAM_RES":{"PDG":333,"M":1.019461,"W":0.004249,"J":1,"P":-1,"BW":2,"g_Tensor":[0.49,4.27],"random_rho":0,"g_A":0.165,"g_phi":-2.36,"g_FF":1.0,"rho_real":[[0.5,0,0],[0,0,0],[0,0,0.5]],"rho_imag":[[0,0,0],[0,0,0],[0,0,0]]}})J"},
+    {"f2_1270", R"J({"PARAM_RES":{"PDG":225,"M":1.2755,"W":0.1867,"J":2,"P":1,"BW":2,"g_Tensor":[2.0,0,0,0,0,0,0],"random_rho":0,"g_A":0.7,"g_phi":-1.57,"g_FF":1.0,"rho_real":[[0.5,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0.5]],"rho_imag":[[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0]]}})J"},
+    {"f2_1525", R"J({"PARAM_RES":{"PDG":335,"M":1.525,"W":0.073,"J":2,"P":1,"BW":2,"g_Tensor":[0.0,0.5,0,0,0,0,0],"random_rho":0,"g_A":0.19,"g_phi":-1.57,"g_FF":1.0,"rho_real":[[0.5,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0.5]],"rho_imag":[[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0]]}})J"},
+    {"f2_1950", R"J({"PARAM_RES":{"PDG":9050225,"M":1.936,"W":0.464,"J":2,"P":1,"BW":2,"g_Tensor":[1.0,0.0,0,0,0,0,0],"random_rho":0,"g_A":0.1,"g_phi":-1.57,"g_FF":1.0,"rho_real":[[0.5,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0.5]],"rho_imag":[[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0],[0,0,0,0,0]]}})J"},
+};
+
+// Decay table subset (values of reference modeldata/TUNE0/BRANCHING.json; same layout): the resonances above
+// into pseudoscalar pairs.
+static const char *const kBuiltinBranching = R"JSON({
+"0":{"0":{"PDG":[-211,211],"BR":1.0,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[-321,321],"BR":1.0,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true}},
+"9000221":{"0":{"PDG":[-211,211],"BR":1.0,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[-321,321],"BR":0.01,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true}},
+"113":{"0":{"PDG":[-211,211],"BR":1.0,"alpha_ls":[[1,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[321,-321],"BR":0.0,"alpha_ls":[[1,0,1.0,0.0]],"P_conservation":true}},
+"9010221":{"0":{"PDG":[211,-211],"BR":0.5,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[321,-321],"BR":0.345,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true}},
+"333":{"0":{"PDG":[321,-321],"BR":0.489,"alpha_ls":[[1,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[130,310],"BR":0.342,"alpha_ls":[[1,0,1.0,0.0]],"P_conservation":true},"2":{"PDG":[211,-211],"BR":7.3e-05,"alpha_ls":[[1,0,1.0,0.0]],"P_conservation":true}},
+"225":{"0":{"PDG":[211,-211],"BR":0.562,"alpha_ls":[[2,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[321,-321],"BR":0.0227,"alpha_ls":[[2,0,1.0,0.0]],"P_conservation":true}},
+"9030221":{"0":{"PDG":[211,-211],"BR":0.2299,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[321,-321],"BR":0.0425,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true}},
+"335":{"0":{"PDG":[321,-321],"BR":0.4435,"alpha_ls":[[2,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[211,-211],"BR":0.00546,"alpha_ls":[[2,0,1.0,0.0]],"P_conservation":true}},
+"10331":{"0":{"PDG":[321,-321],"BR":0.18,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true},"1":{"PDG":[211,-211],"BR":0.0552,"alpha_ls":[[0,0,1.0,0.0]],"P_conservation":true}},
+"9050225":{"0":{"PDG":[211,-211],"BR":1.0,"alpha_ls":[[2,0,1.0,0.0]],"P_conservation":true}}
+})JSON";
+
 struct BuiltinParticle {
   int         pdg;
   double      mass, width;

@@ -60,10 +60,26 @@ struct DevProc {
   double a0[3], ap[3], ln_inv_s0, eta0_re[3], eta0_im[3], phase_c[3];  // phase_c = -pi/2 * ap
   double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
   double inv_fc1, inv_fc2, inv_b_POW, g2_const, eta0sq_re, eta0sq_im;  // g2_const = (gpp_P gN_P)^2
+  double omega;                                                       // PARAM_REGGE::omega (ME3 flux power)
   // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
   double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
   int    em_kelly, amp_kind;
   DevNode nodes[GRB_MAX_NODES];
+};
+
+// resonances (constant memory): pre-digested grb_resonance + Wigner small-d coefficient tables
+struct DevResonance {
+  int    spinX2, P, BW, spingen, spindec, frame, photo, pad_;
+  double mass, width, M2, g_re, g_im, inv_gFF4, g_decay, B0;  // B0: PhotoProp slope (MRegge.cc:852-853)
+  double T_re[9], T_im[9];
+  double rho_re[25], rho_im[25];
+};
+struct DevRes {
+  int          n, any_photo, bw3, pad_;
+  DevResonance r[GRB_MAX_RES];
+  // wd[J-1][(i*5+j)*5+k] = sqrt((J+m)!(J-m)!(J+mp)!(J-mp)!) (-1)^(mp-m+k) / [(J-mp-k)!(J+m-k)!(k+mp-m)! k!],
+  // m = i-J, mp = j-J (reference src/MSpin.cc:927-950); 0 where a factorial argument is negative
+  double wd[2][125];
 };
 
 // screening loop discretisation + per-node eikonal amplitude (constant memory)
@@ -118,6 +134,7 @@ struct PointArgs {
 // launchers implemented in grb_kernels.cu
 cudaError_t upload_proc(const DevProc &p, cudaStream_t st);
 cudaError_t upload_loop(const DevLoop &l, cudaStream_t st);
+cudaError_t upload_res(const DevRes &r, cudaStream_t st);
 int         launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st);
 int         launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st);
 cudaError_t run_dfma_peak(int sm_count, double *tflops);

@@ -295,6 +295,189 @@ static void range2(const Json &j, const char *what, double &lo, double &hi) {
   hi = v[1];
 }
 
+// ---- resonances (reference form::ReadResonance src/MForm.cc:214-375, MProcess::ProcessHelicityDecay
+// src/MProcess.cc:526-748, spin::InitTMatrix src/MSpin.cc:54-245) -------------------------------------------
+static double fact(int n) {  // gra::math::factorial, MMath.h:201-205
+  double x = 1;
+  for (int i = 1; i <= n; ++i) x *= i;
+  return x;
+}
+static bool is_int(double x) { return std::abs(x - std::floor(x)) < 1E-9; }
+static bool is_halfint(double x) { return std::abs(2 * x - std::floor(2 * x)) < 1E-9; }
+static bool is_eq(double x, double y) { return std::abs(x - y) < 1E-9; }
+
+// Wigner 3j by the Racah formula (reference src/MSpin.cc:800-838) with its selection rules (:841-892)
+static double w3j(double j1, double j2, double j3, double m1, double m2, double m3) {
+  if (!is_int(j1 + j2 + j3) || !is_eq(m1 + m2 + m3, 0) || !is_eq(j1 - m1, std::floor(j1 - m1)) ||
+      !is_eq(j2 - m2, std::floor(j2 - m2)) || !is_eq(j3 - m3, std::floor(j3 - m3)) || j3 > j1 + j2 ||
+      j3 < std::abs(j1 - j2) || std::abs(m1) > j1 || std::abs(m2) > j2 || std::abs(m3) > j3)
+    return 0.0;
+  const int c1 = -j2 + m1 + j3, c2 = -j1 - m2 + j3, c3 = j1 + j2 - j3, c4 = j1 - m1, c5 = j2 + m2;
+  const int lower = std::max(std::max(0, -c1), -c2), upper = std::min(std::min(c3, c4), c5);
+  double    fsum = 0;
+  for (int k = lower; k <= upper; ++k)
+    fsum += std::pow(-1.0, k) / (fact(k) * fact(c1 + k) * fact(c2 + k) * fact(c3 - k) * fact(c4 - k) * fact(c5 - k));
+  const double tri = fact(j1 + j2 - j3) * fact(j1 - j2 + j3) * fact(-j1 + j2 + j3) / fact(j1 + j2 + j3 + 1);
+  return std::pow(-1.0, j1 - j2 - m3) *
+         std::sqrt(std::max(0.0, tri * fact(j1 + m1) * fact(j1 - m1) * fact(j2 + m2) * fact(j2 - m2) * fact(j3 + m3) * fact(j3 - m3))) * fsum;
+}
+// Clebsch-Gordan <j m | j1 j2 m1 m2> (reference src/MSpin.cc:706-713, rules :734-792)
+static double clebsch(double j1, double j2, double m1, double m2, double j, double m) {
+  if (!is_halfint(j1) || !is_halfint(j2) || !is_halfint(j) || !is_int(j1 + j2 + j) || !is_halfint(m1) ||
+      !is_halfint(m2) || !is_halfint(m) || !is_eq(m1 + m2, m) || !is_eq(j1 - m1, std::floor(j1 - m1)) ||
+      !is_eq(j2 - m2, std::floor(j2 - m2)) || !is_eq(j - m, std::floor(j - m)) || j > j1 + j2 || j < std::abs(j1 - j2) ||
+      std::abs(m1) > j1 || std::abs(m2) > j2 || std::abs(m) > j)
+    return 0.0;
+  return std::pow(-1.0, m + j1 - j2) * std::sqrt(std::max(0.0, 2 * j + 1)) * w3j(j1, j2, j, m1, m2, -m);
+}
+
+static int frame_id(const std::string &f) {
+  if (f == "CM") return 0;
+  if (f == "HX") return 1;
+  if (f == "CS") return 2;
+  if (f == "GJ") return 3;
+  throw std::invalid_argument("gra::spin::GetRotation: Unknown polarization Lorentz rest FRAME chosen: " + f);
+}
+
+// parity of a decay daughter; only (pseudo)scalar mesons are supported as resonance daughters for now
+static int daughter_parity(const grb_node &n) {
+  if (n.spinX2 != 0) throw Unsupported("resonance decays into daughters with spin are not on the device path yet");
+  return -1;  // light pseudoscalar mesons (reference MPDG.cc setPCL table: n0qq1 -> 0-+)
+}
+
+static void fill_resonance(const Json &R, const Json &tune, const Json &branching, const grb_process_desc &d,
+                           const std::string &name, grb_resonance &o) {
+  memset(&o, 0, sizeof(o));
+  const Json &sp = tune.at("PARAM_SPIN");
+  o.spingen = sp.at("SPINGEN").as_bool(); o.spindec = sp.at("SPINDEC").as_bool();
+  o.frame = frame_id(sp.at("FRAME").as_str()); o.jmax = sp.at("JMAX").as_int();
+  const double g_A = R.at("g_A").as_num(), g_phi = R.at("g_phi").as_num();
+  // g_A * exp(i g_phi): libstdc++ std::exp(complex(0, x)) = (cos x, sin x)
+  o.g_re = g_A * std::cos(g_phi); o.g_im = g_A * std::sin(g_phi);
+  o.g_FF = R.at("g_FF").as_num();
+  o.pdg = R.at("PDG").as_int();
+  o.mass = R.at("M").as_num(); o.width = R.at("W").as_num();
+  if (o.mass < 0 || o.width < 0) throw std::invalid_argument("MAux:ReadResonance:: <" + name + "> Invalid M or W < 0 !");
+  const double J = R.at("J").as_num();
+  o.spinX2 = (int)(J * 2);
+  o.P = R.at("P").as_int();
+  if (!(o.P == -1 || o.P == 1)) throw std::invalid_argument("MAux:ReadResonance:: <" + name + "> Invalid P (not -1 or 1) !");
+  auto gT = R.at("g_Tensor").as_vec();
+  for (size_t i = 0; i < gT.size() && i < 8; ++i) o.g_Tensor[i] = gT[i];
+  o.BW = R.at("BW").as_int();
+  if (o.BW < 1 || o.BW > 4) throw std::invalid_argument("CBW: Unknown BW (Breit-Wigner) parameter: " + std::to_string(o.BW));
+  const int n = o.spinX2 + 1;
+  if (o.spinX2 != 0) {
+    if (n > GRB_RHO_DIM) throw Unsupported("resonance spin J > 2 exceeds GRB_RHO_DIM");
+    if (R.at("random_rho").as_num() > 0) throw Unsupported("random_rho > 0 (RNG-drawn density matrices) is not supported");
+    double tr = 0;
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b) {
+        o.rho_re[a * GRB_RHO_DIM + b] = R.at("rho_real").arr.at(a).arr.at(b).as_num();
+        o.rho_im[a * GRB_RHO_DIM + b] = R.at("rho_imag").arr.at(a).arr.at(b).as_num();
+        if (a == b) tr += o.rho_re[a * GRB_RHO_DIM + b];
+      }
+    if (std::abs(tr - 1.0) > 1e-2) throw std::invalid_argument("gra::spin::Positivity: Density matrix is not properly normalized");
+  }
+  // ---- decay side: BR, alpha_ls -> T matrix, equivalent coupling g_decay --------------------------------
+  if (d.n_legs != 2) throw Unsupported("resonances need a 2-body central final state on the device path");
+  const std::string key = std::to_string(o.pdg);
+  if (!branching.has(key))
+    throw std::invalid_argument("MProcess::ProcessHelicityDecay: Did not find any branching ratio data for resonance with PDG: " + key);
+  const Json &tab = branching.at(key);
+  std::vector<int> want = {d.nodes[0].pdg, d.nodes[1].pdg};
+  std::sort(want.begin(), want.end());
+  double BR = 1.0;
+  bool   Pcons = true, found = false;
+  std::map<std::pair<int, int>, std::pair<double, double>> alpha;  // (l,s) -> (re,im), default 1
+  std::map<std::pair<int, int>, bool> alpha_set;
+  for (auto &kv : tab.obj) {
+    if (kv.second.type != Json::OBJ || !kv.second.has("PDG")) continue;
+    std::vector<int> have;
+    for (auto &x : kv.second.at("PDG").arr) have.push_back(x.as_int());
+    std::sort(have.begin(), have.end());
+    if (have != want) continue;
+    BR = kv.second.at("BR").as_num();
+    Pcons = kv.second.at("P_conservation").as_bool();
+    if (kv.second.has("alpha_ls"))
+      for (auto &a : kv.second.at("alpha_ls").arr) {
+        const auto key2 = std::make_pair(a.arr.at(0).as_int(), a.arr.at(1).as_int());
+        alpha[key2] = {a.arr.at(2).as_num(), a.arr.at(3).as_num()};
+        alpha_set[key2] = true;
+      }
+    found = true;
+    break;
+  }
+  const bool all_set = !found;  // unknown decay mode: BR = 1, alpha_ls == 1 everywhere (reference warning branch)
+  o.BR = BR;
+  // InitTMatrix for daughters with spins s1, s2 (here 0): T[(2s1+1)][(2s2+1)]
+  const double s1 = d.nodes[0].spinX2 / 2.0, s2 = d.nodes[1].spinX2 / 2.0;
+  const int    P1 = daughter_parity(d.nodes[0]), P2 = daughter_parity(d.nodes[1]);
+  const bool   identical = d.nodes[0].pdg == d.nodes[1].pdg;
+  const int    n1 = (int)(2 * s1 + 1), n2 = (int)(2 * s2 + 1);
+  if (n1 * n2 > 9) throw Unsupported("T matrix larger than 3x3");
+  o.T_rows = n1; o.T_cols = n2;
+  std::map<std::pair<int, int>, bool> active;
+  for (int MODE = 0; MODE < 2; ++MODE) {
+    int nonzero = 0;
+    for (int s = 0; s <= (int)(s1 + s2); ++s)
+      for (int l = 0; l <= (int)(J + s); ++l)
+        for (int i = 0; i < n1; ++i)
+          for (int j = 0; j < n2; ++j) {
+            const double lambda1 = -s1 + i, lambda2 = -s2 + j, lambda = lambda1 - lambda2;
+            if (!(std::abs(lambda1 - lambda2) <= J)) continue;
+            const double NORM = std::sqrt((2.0 * l + 1.0) / (2.0 * J + 1.0));
+            const double cg1 = clebsch(l, s, 0.0, lambda, J, lambda);
+            const double cg2 = clebsch(s1, s2, lambda1, -lambda2, s, lambda);
+            if (Pcons && (int)(P1 * P2 * std::pow(-1, l)) != o.P) continue;
+            if (identical && ((l - s) % 2 != 0)) continue;  // Bose symmetry for identical bosons
+            if (std::abs(cg1 * cg2) < 1e-6) continue;
+            active[{l, s}] = true;
+            if (MODE == 0) {
+              if (!all_set && !alpha_set[{l, s}])
+                throw std::invalid_argument("gra::spin::InitTMatrix: helicity decay alpha_ls-couplings missing from BRANCHING for (l,s) = (" +
+                                            std::to_string(l) + "," + std::to_string(s) + ")");
+              ++nonzero;
+            } else {
+              auto it = alpha.find({l, s});
+              const double ar = it == alpha.end() ? 1.0 : it->second.first, ai = it == alpha.end() ? 0.0 : it->second.second;
+              o.T_re[i * n2 + j] += ar * NORM * cg1 * cg2;
+              o.T_im[i * n2 + j] += ai * NORM * cg1 * cg2;
+            }
+          }
+    if (MODE == 0) {
+      if (nonzero == 0) throw std::invalid_argument("gra::spin::InitTMatrix: Decay is impossible (spin-parity-statistics) for resonance " + name);
+      double sum = 0;
+      for (auto &kv : active) {
+        auto it = alpha.find(kv.first);
+        const double ar = it == alpha.end() ? 1.0 : it->second.first, ai = it == alpha.end() ? 0.0 : it->second.second;
+        sum += ar * ar + ai * ai;
+      }
+      if (std::abs(sum - 1.0) > 1e-6)
+        for (auto &kv : active) {
+          auto it = alpha.find(kv.first);
+          std::pair<double, double> v = it == alpha.end() ? std::make_pair(1.0, 0.0) : it->second;
+          alpha[kv.first] = {v.first / std::sqrt(sum), v.second / std::sqrt(sum)};
+        }
+    }
+  }
+  // equivalent 2-body decay coupling (reference src/MProcess.cc:680-727, PDW2body MKinematics.h:331-334)
+  auto kallen = [](double x, double y, double z) { return std::sqrt(std::max(0.0, x * x + y * y + z * z - 2.0 * (x * y + x * z + y * z))); };
+  auto pdw2 = [&](double M2) {
+    const double m = std::sqrt(std::max(0.0, M2));
+    return kallen(M2, d.nodes[0].mass * d.nodes[0].mass, d.nodes[1].mass * d.nodes[1].mass) * 1.0 / (16.0 * 3.141592653589793238462643383279502884 * 1.0 * (m * (m * m)));
+  };
+  double PS = pdw2(o.mass * o.mass);
+  if (std::abs(PS) < 1e-12)
+    for (int i = 1; i <= 3; ++i) {
+      PS = pdw2((o.mass + i * o.width) * (o.mass + i * o.width));
+      if (PS > 1e-12) break;
+    }
+  o.g_decay = std::sqrt(std::max(0.0, o.BR * o.width / PS));
+  if (std::isnan(o.g_decay) || std::isinf(o.g_decay))
+    throw std::invalid_argument("MProcess::ProcessHelicityDecay: Kinematic coupling problem with resonance " + name + " (daughters too heavy?)");
+}
+
 // ---- the flattening proper ---------------------------------------------------------------------------------
 static void parse_card_impl(const std::string &card_path, const char *process_override, int pomloop_override,
                             const char *base, grb_process_desc &d) {
@@ -538,8 +721,49 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     o.M_O = T.at("M_O").as_num(); o.M_1R = T.at("M_1R").as_num();
   }
 
-  if (d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON)
-    throw Unsupported("resonance processes (PP[RES], PP[RES+CON]) are not on the device path yet");
+  // resonances (reference src/MGraniitti.cc:452-582): card "RES" list or @RES{name:true,...}; std::map order
+  if (process_part.find("RES") != std::string::npos) {
+    std::vector<std::string> names;
+    for (auto &x : pp.at("RES").arr) names.push_back(x.as_str());
+    for (auto &c : syntax)
+      if (c.id == "RES") {
+        names.clear();
+        for (auto &kv : c.arg)
+          if (kv.second == "true" || kv.second == "1") names.push_back(kv.first);
+      }
+    std::sort(names.begin(), names.end());
+    names.erase(std::unique(names.begin(), names.end()), names.end());
+    if ((int)names.size() > GRB_MAX_RES) throw Unsupported("more resonances than GRB_MAX_RES");
+    Json branching;
+    if (base && base[0]) branching = parse_json5(read_file(std::string(base) + "/modeldata/" + modelparam + "/BRANCHING.json"));
+    else branching = parse_json5(kBuiltinBranching);
+    for (auto &nm : names) {
+      Json R;
+      if (base && base[0]) {
+        R = parse_json5(read_file(std::string(base) + "/modeldata/" + modelparam + "/RES_" + nm + ".json"));
+      } else {
+        const char *txt = nullptr;
+        for (auto &b : kBuiltinRes)
+          if (nm == b.name) txt = b.json;
+        if (!txt) throw Unsupported("built-in model data has no resonance '" + nm + "'; pass the GRANIITTI base directory");
+        R = parse_json5(txt);
+      }
+      grb_resonance &o = d.res[d.n_res++];
+      fill_resonance(R.at("PARAM_RES"), tune, branching, d, nm, o);
+      for (auto &c : syntax) {
+        if (c.id == "R" && c.target.size() == 1 && c.target[0] == nm)
+          for (auto &kv : c.arg) {
+            if (kv.first == "M") o.mass = std::stod(kv.second);
+            else if (kv.first == "W") o.width = std::stod(kv.second);
+            else throw Unsupported("@R[]{" + kv.first + "} override is not supported yet");
+          }
+        if (c.id == "SPINGEN") o.spingen = c.arg.at("_SINGLET_") == "true";
+        if (c.id == "SPINDEC") o.spindec = c.arg.at("_SINGLET_") == "true";
+        if (c.id == "FRAME") o.frame = frame_id(c.arg.at("_SINGLET_"));
+        if (c.id == "JMAX") o.jmax = std::stoi(c.arg.at("_SINGLET_"));
+      }
+    }
+  }
 
   // internal uniforms consumed per point when no rejection loop repeats (for sizing tapes)
   {

@@ -124,7 +124,7 @@ __device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
   NodeKin in;
   in.ss13 = S.ss13; in.ss24 = S.ss24; in.ss14 = S.ss14; in.ss23 = S.ss23;
   in.t1 = S.t1; in.t2 = S.t2; in.t_hat = S.t_hat; in.u_hat = S.u_hat;
-  in.p1 = S.p1; in.p2 = S.p2;
+  in.p1 = S.p1; in.p2 = S.p2; in.pX = S.pX;
   return amplitude<AMP>(in, S.np4[0], S.np4[1]);
 }
 
@@ -359,6 +359,9 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
 cudaError_t upload_proc(const DevProc &p, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_proc, &p, sizeof(DevProc), 0, cudaMemcpyHostToDevice, st);
 }
+cudaError_t upload_res(const DevRes &r, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_res, &r, sizeof(DevRes), 0, cudaMemcpyHostToDevice, st);
+}
 cudaError_t upload_loop(const DevLoop &l, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_loop, &l, sizeof(DevLoop), 0, cudaMemcpyHostToDevice, st);
 }
@@ -384,6 +387,8 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
   const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
   switch (amp_kind) {
     case AMP_TENSOR_2XS: launch_points_n<AMP_TENSOR_2XS>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_REGGE_RES: launch_points_n<AMP_REGGE_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_REGGE_RES_CON: launch_points_n<AMP_REGGE_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     default: launch_points_n<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;
@@ -403,6 +408,14 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
   if (amp_kind == AMP_TENSOR_2XS) {
     launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
+    return 1;
+  }
+  if (amp_kind == AMP_REGGE_RES) {
+    launch_screen_t<2, AMP_REGGE_RES>(a, sm_count, st);
+    return 1;
+  }
+  if (amp_kind == AMP_REGGE_RES_CON) {
+    launch_screen_t<2, AMP_REGGE_RES_CON>(a, sm_count, st);
     return 1;
   }
   switch (minb) {

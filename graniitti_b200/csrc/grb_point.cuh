@@ -9,6 +9,12 @@ namespace grb {
 __constant__ DevProc c_proc;
 __constant__ DevLoop c_loop;
 
+}  // namespace grb
+
+#include "grb_res.cuh"
+
+namespace grb {
+
 // ---- Philox4x32-10 counter-based RNG (Salmon et al., SC'11): key = seed, counter = (point, iter, block) --
 struct Philox {
   uint32_t k0, k1;
@@ -309,6 +315,7 @@ __device__ __forceinline__ bool veto_cuts(const PointState<NN> &S) {
 struct NodeKin {
   double ss13, ss24, ss14, ss23, t1, t2, t_hat, u_hat;
   v4     p1, p2;  // outgoing protons lts.pfinal[1], [2] (needed by the tensor-pomeron vertices)
+  v4     pX;      // central system lts.pfinal[0] (needed by the resonance amplitudes)
 };
 typedef NodeKin ReggeIn;
 
@@ -457,10 +464,32 @@ __device__ __forceinline__ cx tensor_me4_2xS(const NodeKin &in, const v4 &p3, co
   return A;
 }
 
-enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1 };
+// PP[RES] / PP[RES+CON]: ME4 + coherent resonance sum (reference PROC_9, PROC_17)
+__device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  const DevProc &P = c_proc;
+  ResKin K;
+  K.t1 = in.t1; K.t2 = in.t2;
+  K.pX = in.pX; K.p1 = in.p1; K.p2 = in.p2; K.d0 = p3; K.d1 = p4;
+  K.s1 = m2_of(in.p1.x + in.pX.x, in.p1.y + in.pX.y, in.p1.z + in.pX.z, in.p1.e + in.pX.e);
+  K.s2 = m2_of(in.p2.x + in.pX.x, in.p2.y + in.pX.y, in.p2.z + in.pX.z, in.p2.e + in.pX.e);
+  K.m2 = m2_of(in.pX);
+  K.q1.x = 0.0 - in.p1.x; K.q1.y = 0.0 - in.p1.y; K.q1.z = P.pb1z - in.p1.z; K.q1.e = P.pb1e - in.p1.e;
+  K.x1 = 1 - in.p1.z / P.pb1z;
+  K.x2 = 1 - in.p2.z / P.pb2z;
+  K.qt1 = msqrt(K.q1.x * K.q1.x + K.q1.y * K.q1.y);
+  K.qt2 = msqrt(in.p2.x * in.p2.x + in.p2.y * in.p2.y);
+  return resonance_sum(K);
+}
+
+enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
+  if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
+  if (AMP == AMP_REGGE_RES_CON) {
+    const cx a = regge_me4(in), b = regge_resonances(in, p3, p4);
+    return {a.re + b.re, a.im + b.im};
+  }
   return regge_me4(in);
 }
 
@@ -522,6 +551,7 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   o.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
   o.p1.x = n1x; o.p1.y = n1y; o.p1.z = p1z; o.p1.e = e1;
   o.p2.x = n2x; o.p2.y = n2y; o.p2.z = p2z; o.p2.e = e2;
+  o.pX.x = Xx; o.pX.y = Xy; o.pX.z = Xz; o.pX.e = Xe;
   return true;
 }
 

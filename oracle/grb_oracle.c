@@ -771,11 +771,261 @@ static double tensor_me4_extended(ost *S, double *re, double *im) {
   return (double)(Rr * Rr);
 }
 
+/* ---- resonances: MRegge::ME3 / PhotoME3 with Jacob-Wick spin weights --------------------------------- */
+static inline cx cx_conj(cx a) { return (cx){a.re, -a.im}; }
+/* complex / complex as libgcc __divdc3 evaluates it (what std::complex<double>::operator/= compiles to) */
+static cx cx_div(cx x, cx y) {
+  const double a = x.re, b = x.im, c = y.re, d = y.im;
+  double ratio, denom, re, im;
+  if (fabs(c) < fabs(d)) {
+    ratio = c / d; denom = (c * ratio) + d;
+    re = ((a * ratio) + b) / denom; im = ((b * ratio) - a) / denom;
+  } else {
+    ratio = d / c; denom = (d * ratio) + c;
+    re = ((b * ratio) + a) / denom; im = (b - (a * ratio)) / denom;
+  }
+  return (cx){re, im};
+}
+static double v4_theta(v4 a) { return (a.x == 0.0 && a.y == 0.0 && a.z == 0.0) ? 0.0 : atan2(v4_pt(a), a.z); }
+static double v4_phi(v4 a) { return (a.x == 0.0 && a.y == 0.0) ? 0.0 : atan2(a.y, a.x); }
+static double o_factorial(int n) {
+  double x = 1;
+  for (int i = 1; i <= n; ++i) x *= i;
+  return x;
+}
+/* reference src/MForm.cc:743-827 CBW, types 1-4 */
+static cx o_cbw(const ost *S, const grb_resonance *r) {
+  const double m2 = S->m2, M0 = r->mass, G = r->width, J = r->spinX2 / 2.0;
+  const cx mone = {-1.0, 0.0};
+  switch (r->BW) {
+    case 1: return cx_div(mone, (cx){m2 - M0 * M0 + 0.0 * M0 * G, 1.0 * M0 * G});
+    case 2: return cx_div(mone, (cx){m2 - M0 * M0 + 0.0 * sqrt(m2) * G, 1.0 * sqrt(m2) * G});
+    case 3: {
+      const double mA = v4_m(S->node_p4[0]), mB = v4_m(S->node_p4[1]);
+      const double u = msqrt((m2 - pow2(mA + mB)) * (m2 - pow2(mA - mB))) / (2 * msqrt(m2));
+      const double d = msqrt((M0 * M0 - pow2(mA + mB)) * (M0 * M0 - pow2(mA - mB))) / (2 * M0);
+      const double B = pow(u / d, 2 * (int)J + 1);
+      return cx_div(mone, (cx){m2 - M0 * M0, G * M0 * M0 / msqrt(m2) * B});
+    }
+    default: {
+      const cx den = {m2 - M0 * M0, M0 * G};
+      double num;
+      if ((int)J == 0) num = -1.0;
+      else if ((int)(J * 2) == 1) num = -2.0 * msqrt(m2);
+      else if ((int)J == 1) num = -(1.0 - m2 / (M0 * M0));
+      else if ((int)(J * 2) == 3) num = -(2.0 / 3.0) * msqrt(m2) * (1.0 - m2 / (M0 * M0));
+      else if ((int)J == 2) num = -(7.0 / 6.0 - (4.0 / 3.0) * (m2 / (M0 * M0)) + (2.0 / 3.0) * (m2 * m2) / pow2(pow2(M0)));
+      else num = -1.0;
+      return cx_div((cx){num, 0.0}, den);
+    }
+  }
+}
+/* reference src/MSpin.cc:927-970 WignerSmalld, :978-980 WignerD */
+static double o_wigner_d(double theta, double m, double mp, double J) {
+  const double factor = msqrt(o_factorial((int)(J + m)) * o_factorial((int)(J - m)) * o_factorial((int)(J + mp)) * o_factorial((int)(J - mp)));
+  double s = 0.0;
+  for (int k = 0; k <= 2 * J; ++k) {
+    double value = 0;
+    if (J - mp - k >= 0 && J + m - k >= 0 && k + mp - m >= 0 && k >= 0) {
+      const double val1 = pow(-1, mp - m + k) / (o_factorial((int)(J - mp - k)) * o_factorial((int)(J + m - k)) *
+                                                  o_factorial((int)(k + mp - m)) * o_factorial(k));
+      const double val2 = pow(cos(theta / 2.0), 2 * J + m - mp - 2 * k) * pow(sin(theta / 2.0), mp - m + 2 * k);
+      value = val1 * val2;
+    }
+    s += value;
+  }
+  return factor * s;
+}
+static cx o_wigner_D(double theta, double phi, double m, double mp, double J) {
+  const double d = o_wigner_d(theta, m, mp, J);
+  const double y = (1.0 * mp) * phi;
+  return (cx){d * cos(y), d * sin(y)};
+}
+#define OMAXJ 5 /* 2J+1 <= 5 */
+/* reference src/MSpin.cc:631-690 fMatrix: rows = final helicity pairs, cols = initial projections */
+static int o_fmatrix(const cx *T, int n1, int n2, double J, double s1, double s2, double theta, double phi, cx f[9][OMAXJ]) {
+  const int N = n1 * n2, nJ = (int)(2 * J + 1);
+  int i = 0;
+  for (int mu = 0; mu < n1; ++mu)
+    for (int nu = 0; nu < n2; ++nu) {
+      const double lambda = (-s1 + mu) - (-s2 + nu);
+      for (int j = 0; j < nJ; ++j) f[i][j] = cx_mul(o_wigner_D(theta, phi, lambda, -J + j, J), T[mu * n2 + nu]);
+      ++i;
+    }
+  return N;
+}
+/* reference src/MSpin.cc:544-601 GetRhoRotation */
+static void o_rho_rotation(const ost *S, int frame, double *th, double *ph) {
+  const v4 X = S->pfinal[0];
+  const double MX = v4_m(X);
+  if (frame == 0) { *th = 0; *ph = 0; }
+  else if (frame == 1) { *th = v4_theta(X); *ph = v4_phi(X); }
+  else if (frame == 2) {
+    const v4 a = lorentz_boost(X, MX, S->pbeam1, -1), b = lorentz_boost(X, MX, S->pbeam2, -1);
+    double na = 0.0, nb = 0.0;
+    na += pow2(hypot(a.x, 0)); na += pow2(hypot(a.y, 0)); na += pow2(hypot(a.z, 0)); na = msqrt(na);
+    nb += pow2(hypot(b.x, 0)); nb += pow2(hypot(b.y, 0)); nb += pow2(hypot(b.z, 0)); nb = msqrt(nb);
+    const double zx = a.x / na - b.x / nb, zy = a.y / na - b.y / nb, zz = a.z / na - b.z / nb;
+    double nz = 0.0;
+    nz += pow2(hypot(zx, 0)); nz += pow2(hypot(zy, 0)); nz += pow2(hypot(zz, 0)); nz = msqrt(nz);
+    const v4 bij = {zx / nz, zy / nz, zz / nz, 0.0};
+    *th = v4_theta(bij); *ph = v4_phi(bij);
+  } else {
+    const v4 q = lorentz_boost(X, MX, S->q1, -1);
+    *th = v4_theta(q); *ph = v4_phi(q);
+  }
+}
+/* NORM * sqrt(Re Tr[f (D^+ rho D) f^+]) with MMatrix's k-sequential products (MMatrix.h:234-254) */
+static double o_spin_trace(const ost *S, const grb_resonance *r, cx f[9][OMAXJ], int N) {
+  const double J = r->spinX2 / 2.0;
+  const int n = r->spinX2 + 1;
+  double th, ph;
+  o_rho_rotation(S, r->frame, &th, &ph);
+  cx D[OMAXJ][OMAXJ], rho[OMAXJ][OMAXJ], t1[OMAXJ][OMAXJ], rr[OMAXJ][OMAXJ];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      D[i][j] = o_wigner_D(th, ph, -J + i, -J + j, J);
+      rho[i][j] = (cx){r->rho_re[i * GRB_RHO_DIM + j], r->rho_im[i * GRB_RHO_DIM + j]};
+    }
+  for (int i = 0; i < n; ++i)      /* D^+ * rho */
+    for (int j = 0; j < n; ++j) {
+      cx c = {0, 0};
+      for (int k = 0; k < n; ++k) c = cx_add(c, cx_mul(cx_conj(D[k][i]), rho[k][j]));
+      t1[i][j] = c;
+    }
+  for (int i = 0; i < n; ++i)      /* (D^+ rho) * D */
+    for (int j = 0; j < n; ++j) {
+      cx c = {0, 0};
+      for (int k = 0; k < n; ++k) c = cx_add(c, cx_mul(t1[i][k], D[k][j]));
+      rr[i][j] = c;
+    }
+  cx fr[9][OMAXJ];                 /* f * rho_ROT */
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < n; ++j) {
+      cx c = {0, 0};
+      for (int k = 0; k < n; ++k) c = cx_add(c, cx_mul(f[i][k], rr[k][j]));
+      fr[i][j] = c;
+    }
+  cx tr = {0, 0};                  /* Tr[(f rho) f^+] */
+  for (int i = 0; i < N; ++i) {
+    cx c = {0, 0};
+    for (int k = 0; k < n; ++k) c = cx_add(c, cx_mul(fr[i][k], cx_conj(f[i][k])));
+    tr = cx_add(tr, c);
+  }
+  return msqrt(r->spinX2 + 1.0) * msqrt(tr.re);
+}
+/* reference src/MSpin.cc:280-400 ProdAmp */
+static cx o_prod_amp(const ost *S, const grb_resonance *r) {
+  cx A0 = {r->g_re, r->g_im};
+  if (!r->spingen) return A0;
+  if (r->spinX2 == 0 && r->P == 1) return A0;
+  if (r->spinX2 == 0 && r->P == -1) {
+    double D = v4_phi(S->pfinal[1]) - v4_phi(S->pfinal[2]);
+    while (D >= O_PI) D -= 2.0 * O_PI;
+    while (D < -O_PI) D += 2.0 * O_PI;
+    const double dphi = fabs(D);
+    const double rt = pow(fabs(S->t1), fabs(1.0) / 2.0) * pow(fabs(S->t2), fabs(1.0) / 2.0);
+    return cx_scale(cx_scale(A0, rt), sin(dphi));
+  }
+  double s1 = 0, s2 = 0;
+  cx T0[9] = {{1.0, 0.0}};
+  int n1 = 1, n2 = 1;
+  if (r->spinX2 == 2 && r->P == 1) {
+    s1 = 1; s2 = 1; n1 = 3; n2 = 3;
+    const double t[9] = {0.000, -0.500, 0.000, 0.500, 0.000, -0.500, 0.000, 0.500, 0.000};
+    for (int i = 0; i < 9; ++i) T0[i] = (cx){t[i], 0.0};
+  }
+  if (r->spinX2 == 2 && r->P == -1) {
+    s1 = 0; s2 = 1; n1 = 1; n2 = 3;
+    T0[0] = (cx){-0.697, 0}; T0[1] = (cx){-0.169, 0}; T0[2] = (cx){0.697, 0};
+  }
+  const v4 q1 = lorentz_boost(S->pfinal[0], v4_m(S->pfinal[0]), S->q1, -1);
+  cx f0[9][OMAXJ];
+  const int N = o_fmatrix(T0, n1, n2, r->spinX2 / 2.0, s1, s2, v4_theta(q1), v4_phi(q1), f0);
+  return cx_scale(A0, o_spin_trace(S, r, f0, N));
+}
+/* reference src/MSpin.cc:406-483 DecayAmp (two final-state daughters, no cascades) */
+static cx o_decay_amp(const ost *S, const grb_resonance *r) {
+  const double A0 = r->g_decay;
+  if (!r->spindec) return (cx){A0, 0.0};
+  if (S->d->n_legs != 2) return (cx){A0, 0.0};
+  if (r->spinX2 == 0) return cx_scale((cx){r->T_re[0], r->T_im[0]}, A0);
+  const double s1 = S->d->nodes[0].spinX2 / 2.0, s2 = S->d->nodes[1].spinX2 / 2.0;
+  const v4 bd = lorentz_boost(S->pfinal[0], v4_m(S->pfinal[0]), S->node_p4[0], -1);
+  cx T[9], f[9][OMAXJ];
+  for (int i = 0; i < r->T_rows * r->T_cols; ++i) T[i] = (cx){r->T_re[i], r->T_im[i]};
+  const int N = o_fmatrix(T, r->T_rows, r->T_cols, r->spinX2 / 2.0, s1, s2, v4_theta(bd), v4_phi(bd), f);
+  return (cx){A0 * o_spin_trace(S, r, f, N), 0.0};
+}
+/* reference src/MForm.cc:664-684 CohFlux (alpha_QED() = alpha_0, MQED.h:18-21) */
+static double o_coh_flux(const ost *S, double xi, double t, double pt) {
+  const double mp = 0.938272081;
+  const double pt2 = pow2(pt), xi2 = pow2(xi), mp2 = pow2(mp), Q2 = fabs(t);
+  const double PART1 = (4.0 * pow2(mp) * pow2(o_GE(S, Q2)) + Q2 * pow2(o_GM(S, Q2))) / (4.0 * pow2(mp) + Q2);
+  const double PART2 = pow2(o_GM(S, Q2));
+  const double DELTA = pt2 / (pt2 + xi2 * mp2);
+  double f = 0.0072973525693 / O_PI * ((1.0 - xi) * pow2(DELTA) * PART1 + (xi2 / 4.0) * DELTA * PART2);
+  f /= xi;
+  f /= pt2;
+  f *= 16.0 * (O_PI * O_PI);
+  return f;
+}
+/* reference src/MRegge.cc:852-882 PhotoProp (elastic leg) */
+static cx o_photo_prop(const ost *S, double s, double t, double m2) {
+  const grb_param_regge *R = &S->d->regge;
+  const double B0 = pow(fmax(pow2(0.7), m2) / 2.0, -O_PI / 2.0) + 3 * O_PI / 2.0;
+  const double W02 = pow2(1.0);
+  const double alpha = R->a0[0] + R->ap[0] * t;
+  const double y = ((-1.0 * O_PI) / 2.0 * R->ap[0]) * t;
+  const cx eta = cx_mul(S->regge_eta0[0], (cx){cos(y), sin(y)});
+  const double FF = S->d->soft.gN_P * exp(B0 * t / 2.0);
+  return cx_scale(cx_scale(eta, pow(s / W02, alpha)), FF);
+}
+/* reference src/MRegge.cc:677-706 ME3 */
+static cx regge_me3(ost *S, const grb_resonance *r) {
+  const double FF_A = S->d->soft.gN_P * s3f(S, S->t1), FF_B = S->d->soft.gN_P * s3f(S, S->t2);
+  cx A = cx_scale(prop_only(S, S->s1, S->t1), 2.0);
+  A = cx_scale(A, FF_A);
+  A = cx_mul(A, o_cbw(S, r));
+  A = cx_scale(A, exp(-pow2(S->m2 - pow2(r->mass)) / pow2(pow2(r->g_FF))));
+  A = cx_mul(A, prop_only(S, S->s2, S->t2));
+  A = cx_scale(A, FF_B);
+  const cx A_spin = cx_mul(o_prod_amp(S, r), o_decay_amp(S, r));
+  const double V = pow(1.0 / S->m2, S->d->regge.omega);
+  return cx_scale(cx_mul(A, A_spin), V);
+}
+/* reference src/MRegge.cc:781-828 PhotoME3 (pp initial state, elastic legs) */
+static cx regge_photo_me3(ost *S, const grb_resonance *r) {
+  const cx common = cx_scale(o_cbw(S, r), exp(-pow2(S->m2 - pow2(r->mass)) / pow2(pow2(r->g_FF))));
+  const double gf1 = msqrt(o_coh_flux(S, S->x1, S->t1, S->qt1) / S->x1);
+  const double gf2 = msqrt(o_coh_flux(S, S->x2, S->t2, S->qt2) / S->x2);
+  const cx A_1 = cx_mul(cx_scale(common, gf2), o_photo_prop(S, S->s1, S->t1, pow2(r->mass)));
+  const cx A_2 = cx_mul(cx_scale(common, gf1), o_photo_prop(S, S->s2, S->t2, pow2(r->mass)));
+  const cx A_prod = cx_add(A_1, A_2);
+  const cx A_spin = cx_mul(o_prod_amp(S, r), o_decay_amp(S, r));
+  return cx_mul(A_prod, A_spin);
+}
+/* reference PROC_9 / PROC_17 (include/Graniitti/MSubProc.h:233-262,399-436): coherent sum in std::map order */
+static double res_amp2(ost *S, int with_continuum) {
+  cx A = {0.0, 0.0};
+  if (with_continuum) A = regge_me4(S, 1.0);
+  for (int i = 0; i < S->d->n_res; ++i) {
+    const grb_resonance *r = &S->d->res[i];
+    const int J = (int)(r->spinX2 / 2.0);
+    A = cx_add(A, (J == 1 && r->P == -1) ? regge_photo_me3(S, r) : regge_me3(S, r));
+  }
+  S->hamp[0] = A;
+  S->nhamp = 1;
+  return cx_abs2(A);
+}
+
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
     case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
+    case GRB_PROC_PP_RES: return res_amp2(S, 0);
+    case GRB_PROC_PP_RES_CON: return res_amp2(S, 1);
     case GRB_PROC_PP_CONTENSOR: {
       if (g_oracle_extended) {
         double re, im;

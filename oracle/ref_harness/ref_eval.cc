@@ -149,6 +149,20 @@ int main(int argc, char **argv) {
         printf("INFO leg %zu pdg %d mass %.17g width %.17g nlegs %zu\n", i, b.p.pdg, b.p.mass,
                b.p.width, b.legs.size());
       }
+      for (const auto &kv : p.lts.RESONANCES) {
+        const auto &r = kv.second;
+        printf("INFO res %s pdg %d mass %.17g width %.17g spinX2 %d P %d BW %d g %.17g %.17g gFF %.17g BR %.17g gdecay %.17g "
+               "spingen %d spindec %d frame %s jmax %d T %zu %zu",
+               kv.first.c_str(), r.p.pdg, r.p.mass, r.p.width, r.p.spinX2, r.p.P, r.BW, r.g.real(), r.g.imag(), r.g_FF,
+               r.hel.BR, r.hel.g_decay, (int)r.SPINGEN, (int)r.SPINDEC, r.FRAME.c_str(), r.JMAX, r.hel.T.size_row(),
+               r.hel.T.size_col());
+        for (size_t a = 0; a < r.hel.T.size_row(); ++a)
+          for (size_t b = 0; b < r.hel.T.size_col(); ++b) printf(" %.17g %.17g", r.hel.T[a][b].real(), r.hel.T[a][b].imag());
+        printf(" rho %zu", r.rho.size_row());
+        for (size_t a = 0; a < r.rho.size_row(); ++a)
+          for (size_t b = 0; b < r.rho.size_col(); ++b) printf(" %.17g %.17g", r.rho[a][b].real(), r.rho[a][b].imag());
+        printf("\n");
+      }
       if (p.GetScreening()) {
         const auto &N = p.Eikonal.Numerics;
         printf("INFO loop nkt %u nphi %u minkt %.17g maxkt %.17g\n", N.NumberLoopKT, N.NumberLoopPHI,

@@ -25,6 +25,11 @@ CASES = [
     ("c2_alice_pipi_tensor_born", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 0, 2048, 8, True),
     ("c2_alice_pipi_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 1, 320, 8, True),
     ("c1_test_kk_tensor_born", "./input/test.json", "PP[CONTENSOR]<F> -> K+ K-", 0, 1024, 8, True),
+    ("c1_test_pipi_rescon_born", "./input/test.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c3_atlas_pipi_rescon_born", "./tests/run_atlas_multi/ATLAS.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c3_atlas_neg_pipi_rescon_born", "./tests/run_atlas_multi/ATLAS_NEG.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 1024, 8, True),
+    ("c3_atlas_kk_res_born", "./tests/run_atlas_multi/ATLAS.json", "PP[RES]<F> -> K+ K-", 0, 1024, 8, True),
+    ("c2_alice_pipi_rescon_screened", "./tests/processes/ALICECUTS.json", "PP[RES+CON]<F> -> pi+ pi-", 1, 256, 8, True),
     ("c5_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 2048, 24, True),
 ]

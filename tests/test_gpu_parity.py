@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
 CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json",
-           "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json"}
+           "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json", "./tests/run_atlas_multi/ATLAS.json": "c3_atlas.json",
+           "./tests/run_atlas_multi/ATLAS_NEG.json": "c3_atlas_neg.json"}
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
 
 
@@ -56,7 +57,9 @@ def test_device_vs_reference_golden(grb, msa, path):
     assert np.mean(rel > RTOL) < 1e-3 + 2.0 / len(rel), "too many points needed the conditioning term"
     # Regge amplitudes reproduce the reference's operation order (median ~1e-15); the tensor-pomeron device
     # code is the contracted closed form of the reference's FTensor loops (median ~1e-13)
-    assert np.median(rel) < (2e-12 if "TENSOR" in str(z["process"]) else 1e-13)
+    # ... and the resonance code replaces the reference's pow()-based Wigner functions by integer powers
+    loose = "TENSOR" in str(z["process"]) or "RES" in str(z["process"])
+    assert np.median(rel) < (2e-12 if loose else 1e-13)
     kin = (z["flags"] & 1) == 1
     # intermediate scalars: absolute 2e-10 on t (t = dE^2 - dpz^2 - pt^2 cancels O(6500 GeV) roundings), relative elsewhere
     assert np.max(np.abs(dump[0][kin] - z["t1"][kin])) < 2e-10

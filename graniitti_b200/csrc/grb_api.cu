@@ -84,9 +84,18 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR &&
-      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON) {
+      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON && d.proc != GRB_PROC_YY_CON) {
     err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
     return GRB_ERR_UNSUPPORTED;
+  }
+  if (d.proc == GRB_PROC_YY_CON) {
+    const int a = std::abs(d.nodes[0].pdg);
+    if (!(a == 11 || a == 13 || a == 15) || d.nodes[1].pdg != -d.nodes[0].pdg || d.n_nodes != 2) {
+      err = "yy[CON]: only charged lepton pairs (MG5 yy -> l+ l-) have a device amplitude";
+      return GRB_ERR_UNSUPPORTED;
+    }
+    if (d.qed_alpha != 0) { err = "yy[CON]: PARAM_STRUCTURE.QED_alpha must be ZERO on the device path"; return GRB_ERR_UNSUPPORTED; }
+    if (d.screening) { err = "yy[CON] with POMLOOP (16 helicity amplitudes in the loop) is not on the device path yet"; return GRB_ERR_UNSUPPORTED; }
   }
   if (d.proc == GRB_PROC_PP_CONTENSOR && !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0)) {
     err = "PP[CONTENSOR]: only pseudoscalar pairs (2xS) have a device amplitude yet";
@@ -157,7 +166,10 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     P.four_mp2 = (2 * 0.938272081) * (2 * 0.938272081);  // PDG::mp, reference MPDG.h:54
     P.em_kelly = d.em_ff;
     P.amp_kind = (d.proc == GRB_PROC_PP_CONTENSOR) ? 1 : (d.proc == GRB_PROC_PP_RES ? 2 : (d.proc == GRB_PROC_PP_RES_CON ? 3 : 0));
+    if (d.proc == GRB_PROC_YY_CON) P.amp_kind = 4;
     P.omega = d.regge.omega;
+    const double ee = 2. * std::sqrt(1.0 / 137.03599908) * std::sqrt(M_PI);
+    P.yy_ee4 = (ee * ee) * (ee * ee);
   }
   // nodes
   for (int i = 0; i < d.n_nodes; ++i) {

@@ -61,6 +61,7 @@ struct DevProc {
   double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
   double inv_fc1, inv_fc2, inv_b_POW, g2_const, eta0sq_re, eta0sq_im;  // g2_const = (gpp_P gN_P)^2
   double omega;                                                       // PARAM_REGGE::omega (ME3 flux power)
+  double yy_ee4;                                                      // ee^4, ee = 2 sqrt(pi alpha(0)) (MG5 GC_3)
   // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
   double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
   int    em_kelly, amp_kind;

@@ -389,6 +389,7 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
     case AMP_TENSOR_2XS: launch_points_n<AMP_TENSOR_2XS>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_RES: launch_points_n<AMP_REGGE_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_RES_CON: launch_points_n<AMP_REGGE_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_YY_LL: launch_points_n<AMP_YY_LL>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     default: launch_points_n<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;

@@ -481,9 +481,16 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
   return resonance_sum(K);
 }
 
-enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3 };
+}  // namespace grb
+
+#include "grb_yy.cuh"
+
+namespace grb {
+
+enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {

@@ -16,6 +16,7 @@
  */
 #include "grb_oracle.h"
 
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1019,11 +1020,238 @@ static double res_amp2(ost *S, int with_continuum) {
   return cx_abs2(A);
 }
 
+/* ---- gamma gamma -> l+ l- : MadGraph5/HELAS helicity amplitudes + kt-EPA fluxes ------------------------ */
+/* reference src/Amplitude/AMP_MG5_yy_ll.cc:41-255 (CalcAmp2, calculate_wavefunctions),
+ * src/Amplitude/HelAmps_sm.cc (ixxxxx :265, oxxxxx :140, vxxxxx :207, FFV1_0 :678, FFV1_1 :930, FFV1_2 :435),
+ * include/Graniitti/MKinematics.h:799-907 (OffShell2LightCone), src/MFlux.cc:22-44 (ApplyktEPAfluxes).
+ * The ALOHA vertex routines are restated in light-cone combinations V+- = V0 +- V3, Vc = V1 + i V2,
+ * Vd = V1 - i V2 (same for the real propagator momentum P), which is what the generated expressions reduce to. */
+static inline cx cx_sub(cx a, cx b) { return (cx){a.re - b.re, a.im - b.im}; }
+static inline cx cx_i(cx a) { return (cx){-a.im, a.re}; }          /* i * a */
+static inline cx cx_r(double r) { return (cx){r, 0.0}; }
+static double o_sgn(double a, double b) { return (b < 0) ? -fabs(a) : fabs(a); }
+
+/* p = (E,px,py,pz) MadGraph convention; w[0..1] momentum, w[2..5] wavefunction */
+static void o_vxxxxx(const double p[4], int nhel, int nsv, cx vc[6]) { /* massless vector */
+  const double sqh = sqrt(0.5), hel = (double)nhel;
+  vc[0] = (cx){p[0] * nsv, p[3] * nsv};
+  vc[1] = (cx){p[1] * nsv, p[2] * nsv};
+  const double pp = p[0], pt = sqrt((p[1] * p[1]) + (p[2] * p[2]));
+  vc[2] = (cx){0.0, 0.0};
+  vc[5] = (cx){hel * pt / pp * sqh, 0.0};
+  if (pt != 0.0) {
+    const double pzpt = p[3] / (pp * pt) * sqh * hel;
+    vc[3] = (cx){-p[1] * pzpt, -nsv * p[2] / pt * sqh};
+    vc[4] = (cx){-p[2] * pzpt, nsv * p[1] / pt * sqh};
+  } else {
+    vc[3] = (cx){-hel * sqh, 0.0};
+    vc[4] = (cx){0.0, nsv * o_sgn(sqh, p[3])};
+  }
+}
+static void o_ixxxxx(const double p[4], double fmass, int nhel, int nsf, cx fi[6]) {
+  cx chi[2];
+  fi[0] = (cx){-p[0] * nsf, -p[3] * nsf};
+  fi[1] = (cx){-p[1] * nsf, -p[2] * nsf};
+  const int nh = nhel * nsf;
+  if (fmass != 0.0) {
+    const double pp = fmin(p[0], sqrt(p[1] * p[1] + p[2] * p[2] + p[3] * p[3]));
+    if (pp == 0.0) {
+      double sqm[2];
+      sqm[0] = sqrt(fabs(fmass)); sqm[1] = o_sgn(sqm[0], fmass);
+      const int ip = (1 + nh) / 2, im = (1 - nh) / 2;
+      fi[2] = cx_r(ip * sqm[ip]); fi[3] = cx_r(im * nsf * sqm[ip]); fi[4] = cx_r(ip * nsf * sqm[im]); fi[5] = cx_r(im * sqm[im]);
+    } else {
+      double sf[2], omega[2], sfomega[2];
+      sf[0] = (1 + nsf + (1 - nsf) * nh) * 0.5; sf[1] = (1 + nsf - (1 - nsf) * nh) * 0.5;
+      omega[0] = sqrt(p[0] + pp); omega[1] = fmass / omega[0];
+      const int ip = (1 + nh) / 2, im = (1 - nh) / 2;
+      sfomega[0] = sf[0] * omega[ip]; sfomega[1] = sf[1] * omega[im];
+      const double pp3 = fmax(pp + p[3], 0.0);
+      chi[0] = (cx){sqrt(pp3 * 0.5 / pp), 0};
+      if (pp3 == 0.0) chi[1] = (cx){-nh, 0};
+      else { const double dn = sqrt(2.0 * pp * pp3); chi[1] = (cx){nh * p[1] / dn, p[2] / dn}; }
+      fi[2] = cx_scale(chi[im], sfomega[0]); fi[3] = cx_scale(chi[ip], sfomega[0]);
+      fi[4] = cx_scale(chi[im], sfomega[1]); fi[5] = cx_scale(chi[ip], sfomega[1]);
+    }
+  } else {
+    double sqp0p3;
+    if (p[1] == 0.0 && p[2] == 0.0 && p[3] < 0.0) sqp0p3 = 0.0; else sqp0p3 = sqrt(fmax(p[0] + p[3], 0.0)) * nsf;
+    chi[0] = (cx){sqp0p3, 0.0};
+    if (sqp0p3 == 0.0) chi[1] = (cx){-nhel * sqrt(2.0 * p[0]), 0.0};
+    else chi[1] = (cx){nh * p[1] / sqp0p3, p[2] / sqp0p3};
+    if (nh == 1) { fi[2] = cx_r(0); fi[3] = cx_r(0); fi[4] = chi[0]; fi[5] = chi[1]; }
+    else { fi[2] = chi[1]; fi[3] = chi[0]; fi[4] = cx_r(0); fi[5] = cx_r(0); }
+  }
+}
+static void o_oxxxxx(const double p[4], double fmass, int nhel, int nsf, cx fo[6]) {
+  cx chi[2];
+  fo[0] = (cx){p[0] * nsf, p[3] * nsf};
+  fo[1] = (cx){p[1] * nsf, p[2] * nsf};
+  const int nh = nhel * nsf;
+  if (fmass != 0.000) {
+    double pp = fmin(p[0], sqrt((p[1] * p[1]) + (p[2] * p[2]) + (p[3] * p[3])));
+    if (pp == 0.000) {
+      double sqm[2];
+      sqm[0] = sqrt(fabs(fmass)); sqm[1] = o_sgn(sqm[0], fmass);
+      const int ip = -((1 - nh) / 2) * nhel, im = (1 + nh) / 2 * nhel;
+      fo[2] = cx_r(im * sqm[abs(ip)]); fo[3] = cx_r(ip * nsf * sqm[abs(ip)]);
+      fo[4] = cx_r(im * nsf * sqm[abs(im)]); fo[5] = cx_r(ip * sqm[abs(im)]);
+    } else {
+      double sf[2], omega[2], sfomeg[2];
+      sf[0] = (double)(1 + nsf + (1 - nsf) * nh) * 0.5; sf[1] = (double)(1 + nsf - (1 - nsf) * nh) * 0.5;
+      omega[0] = sqrt(p[0] + pp); omega[1] = fmass / omega[0];
+      const int ip = (1 + nh) / 2, im = (1 - nh) / 2;
+      sfomeg[0] = sf[0] * omega[ip]; sfomeg[1] = sf[1] * omega[im];
+      const double pp3 = fmax(pp + p[3], 0.00);
+      chi[0] = (cx){sqrt(pp3 * 0.5 / pp), 0.00};
+      if (pp3 == 0.00) chi[1] = (cx){-nh, 0.00};
+      else { const double dn = sqrt(2.0 * pp * pp3); chi[1] = (cx){nh * p[1] / dn, -p[2] / dn}; }
+      fo[2] = cx_scale(chi[im], sfomeg[1]); fo[3] = cx_scale(chi[ip], sfomeg[1]);
+      fo[4] = cx_scale(chi[im], sfomeg[0]); fo[5] = cx_scale(chi[ip], sfomeg[0]);
+    }
+  } else {
+    double sqp0p3;
+    if ((p[1] == 0.00) && (p[2] == 0.00) && (p[3] < 0.00)) sqp0p3 = 0.00; else sqp0p3 = sqrt(fmax(p[0] + p[3], 0.00)) * nsf;
+    chi[0] = (cx){sqp0p3, 0.00};
+    if (sqp0p3 == 0.000) chi[1] = cx_scale((cx){-nhel, 0.00}, sqrt(2.0 * p[0]));
+    else chi[1] = (cx){nh * p[1] / sqp0p3, -p[2] / sqp0p3};
+    if (nh == 1) { fo[2] = chi[0]; fo[3] = chi[1]; fo[4] = cx_r(0); fo[5] = cx_r(0); }
+    else { fo[2] = cx_r(0); fo[3] = cx_r(0); fo[4] = chi[1]; fo[5] = chi[0]; }
+  }
+}
+typedef struct { cx p, m, c, d; } lc4; /* V+ , V- , V1+iV2 , V1-iV2 */
+static lc4 o_lc(const cx V[6]) {
+  lc4 r;
+  r.p = cx_add(V[2], V[5]); r.m = cx_sub(V[2], V[5]);
+  r.c = cx_add(V[3], cx_i(V[4])); r.d = cx_sub(V[3], cx_i(V[4]));
+  return r;
+}
+/* FFV1_0: COUP * (-i) * [ F1 (gamma.V) F2 ] */
+static cx o_ffv1_0(const cx F1[6], const cx F2[6], const cx V3[6], cx COUP) {
+  const lc4 v = o_lc(V3);
+  cx t = cx_mul(F1[2], cx_add(cx_mul(F2[4], v.p), cx_mul(F2[5], v.c)));
+  t = cx_add(t, cx_mul(F1[3], cx_add(cx_mul(F2[4], v.d), cx_mul(F2[5], v.m))));
+  t = cx_add(t, cx_mul(F1[4], cx_sub(cx_mul(F2[2], v.m), cx_mul(F2[3], v.c))));
+  t = cx_add(t, cx_mul(F1[5], cx_sub(cx_mul(F2[3], v.p), cx_mul(F2[2], v.d))));
+  const cx mi = {0.0, -1.0};
+  return cx_mul(cx_mul(COUP, mi), t);
+}
+/* FFV1_2 with M = W = 0: off-shell incoming-flow spinor F2 from (F1, V3) */
+static void o_ffv1_2(const cx F1[6], const cx V3[6], cx COUP, cx F2[6]) {
+  F2[0] = cx_add(F1[0], V3[0]); F2[1] = cx_add(F1[1], V3[1]);
+  const double P0 = -F2[0].re, P1 = -F2[1].re, P2 = -F2[1].im, P3 = -F2[0].im;
+  const cx denom = cx_div(COUP, cx_r((P0 * P0) - (P1 * P1) - (P2 * P2) - (P3 * P3)));
+  const lc4 v = o_lc(V3);
+  const double Pp = P0 + P3, Pm = P0 - P3;
+  const cx Pc = {P1, P2}, Pd = {P1, -P2};
+  const cx a = cx_add(cx_mul(F1[2], v.p), cx_mul(F1[3], v.d)), b = cx_add(cx_mul(F1[2], v.c), cx_mul(F1[3], v.m));
+  const cx c = cx_sub(cx_mul(F1[4], v.m), cx_mul(F1[5], v.d)), e = cx_sub(cx_mul(F1[4], v.c), cx_mul(F1[5], v.p));
+  const cx id = cx_i(denom);
+  F2[2] = cx_mul(id, cx_sub(cx_scale(a, Pm), cx_mul(Pd, b)));
+  F2[3] = cx_mul(id, cx_sub(cx_scale(b, Pp), cx_mul(Pc, a)));
+  F2[4] = cx_mul(id, cx_sub(cx_scale(c, Pp), cx_mul(Pd, e)));
+  F2[5] = cx_mul(id, cx_sub(cx_mul(Pc, c), cx_scale(e, Pm)));
+}
+/* FFV1_1 with M = W = 0: off-shell outgoing-flow spinor F1 from (F2, V3) */
+static void o_ffv1_1(const cx F2[6], const cx V3[6], cx COUP, cx F1[6]) {
+  F1[0] = cx_add(F2[0], V3[0]); F1[1] = cx_add(F2[1], V3[1]);
+  const double P0 = -F1[0].re, P1 = -F1[1].re, P2 = -F1[1].im, P3 = -F1[0].im;
+  const cx denom = cx_div(COUP, cx_r((P0 * P0) - (P1 * P1) - (P2 * P2) - (P3 * P3)));
+  const lc4 v = o_lc(V3);
+  const double Pp = P0 + P3, Pm = P0 - P3;
+  const cx Pc = {P1, P2}, Pd = {P1, -P2};
+  const cx a = cx_sub(cx_mul(F2[2], v.m), cx_mul(F2[3], v.c)), b = cx_sub(cx_mul(F2[2], v.d), cx_mul(F2[3], v.p));
+  const cx c = cx_add(cx_mul(F2[4], v.p), cx_mul(F2[5], v.c)), e = cx_add(cx_mul(F2[4], v.d), cx_mul(F2[5], v.m));
+  const cx id = cx_i(denom);
+  F1[2] = cx_mul(id, cx_sub(cx_mul(Pc, b), cx_scale(a, Pp)));
+  F1[3] = cx_mul(id, cx_sub(cx_scale(b, Pm), cx_mul(Pd, a)));
+  F1[4] = cx_mul(id, cx_sub(cx_mul(Pc, e), cx_scale(c, Pm)));
+  F1[5] = cx_mul(id, cx_sub(cx_mul(Pd, c), cx_scale(e, Pp)));
+}
+/* reference include/Graniitti/MKinematics.h:799-907 OffShell2LightCone, N = 2 final states */
+static void o_offshell2lightcone(v4 *p1, v4 *p2, v4 p[2]) {
+  const int N = 2;
+  p1->e = v4_p3mod(*p1);
+  p2->e = v4_p3mod(*p2);
+  const v4 q = v4_add(*p1, *p2);
+  double m[2];
+  for (int i = 0; i < N; ++i) m[i] = v4_m(p[i]);
+  int iter = 0;
+  while (1) {
+    double Esum = 0.0;
+    for (int i = 0; i < N; ++i) Esum += p[i].e;
+    const double dE = Esum - q.e;
+    for (int i = 0; i < N; ++i) {
+      const double E = p[i].e - dE / N;
+      const double a = msqrt(E * E - m[i] * m[i]) / v4_p3mod(p[i]);
+      p[i] = (v4){a * p[i].x, a * p[i].y, a * p[i].z, E};
+    }
+    v4 sum = {0, 0, 0, 0};
+    for (int i = 0; i < N; ++i) sum = v4_add(sum, p[i]);
+    const v4 D = v4_sub(sum, q);
+    for (int i = 0; i < N; ++i) {
+      const double dx = D.x * (1.0 / N), dy = D.y * (1.0 / N), dz = D.z * (1.0 / N);
+      p[i].x = p[i].x - dx; p[i].y = p[i].y - dy; p[i].z = p[i].z - dz;
+      p[i].e = msqrt(v4_p3mod2(p[i]) + m[i] * m[i]);
+    }
+    ++iter;
+    sum = (v4){0, 0, 0, 0};
+    for (int i = 0; i < N; ++i) sum = v4_add(sum, p[i]);
+    const double IVM = fabs(v4_m2(v4_sub(q, sum)));
+    if (iter > 15 || IVM < 1e-10) break;
+  }
+}
+/* reference PROC_3: MGamma::yyffbar (lepton pair) -> AMP_MG5_yy_ll::CalcAmp2, then flux::ApplyktEPAfluxes */
+static double yy_con_amp2(ost *S) {
+  static const int HEL[16][4] = {{-1, -1, -1, -1}, {-1, -1, -1, 1}, {-1, -1, 1, -1}, {-1, -1, 1, 1}, {-1, 1, -1, -1},
+                                 {-1, 1, -1, 1},  {-1, 1, 1, -1},  {-1, 1, 1, 1},  {1, -1, -1, -1}, {1, -1, -1, 1},
+                                 {1, -1, 1, -1},  {1, -1, 1, 1},   {1, 1, -1, -1}, {1, 1, -1, 1},   {1, 1, 1, -1}, {1, 1, 1, 1}};
+  v4 pf[2] = {S->node_p4[0], S->node_p4[1]};
+  const double m3 = v4_m(pf[0]), m4 = v4_m(pf[1]);
+  v4 q1 = S->q1, q2 = S->q2;
+  o_offshell2lightcone(&q1, &q2, pf);
+  const double P1[4] = {q1.e, q1.x, q1.y, q1.z}, P2[4] = {q2.e, q2.x, q2.y, q2.z};
+  const double P3[4] = {pf[0].e, pf[0].x, pf[0].y, pf[0].z}, P4[4] = {pf[1].e, pf[1].x, pf[1].y, pf[1].z};
+  /* GC_3 = -(ee * i), ee = 2 sqrt(1/137.03599908) sqrt(pi)  (Parameters_sm.cc:93-101, QED_alpha = ZERO) */
+  const double ee = 2. * sqrt(1.0 / 137.03599908) * sqrt(M_PI);
+  const cx GC3 = {-(ee * 0.0), -(ee * 1.0)};
+  double amp2 = 0.0;
+  for (int ih = 0; ih < 16; ++ih) {
+    cx w0[6], w1[6], w2[6], w3[6], w4[6], w5[6];
+    o_vxxxxx(P1, HEL[ih][0], -1, w0);
+    o_vxxxxx(P2, HEL[ih][1], -1, w1);
+    o_ixxxxx(P3, m3, HEL[ih][2], -1, w2);
+    o_oxxxxx(P4, m4, HEL[ih][3], +1, w3);
+    o_ffv1_2(w2, w0, GC3, w4);
+    o_ffv1_1(w3, w0, GC3, w5);
+    const cx a0 = o_ffv1_0(w4, w3, w1, GC3), a1 = o_ffv1_0(w2, w5, w1, GC3);
+    S->hamp[ih] = cx_add(cx_add((cx){0, 0}, a0), a1);
+  }
+  for (int ih = 0; ih < 16; ++ih) amp2 += cx_abs2(S->hamp[ih]);
+  amp2 /= 4;
+  S->nhamp = 16;
+  /* kt-EPA fluxes, src/MFlux.cc:22-44 */
+  const double f1 = o_coh_flux(S, S->x1, S->t1, S->qt1), f2 = o_coh_flux(S, S->x2, S->t2, S->qt2);
+  const double fluxes = f1 * f2 * (1.0 / (S->x1 * S->x2));
+  const double tot = fluxes * amp2;
+  const double sf = msqrt(fluxes);
+  for (int ih = 0; ih < 16; ++ih) S->hamp[ih] = cx_scale(S->hamp[ih], sf);
+  return tot;
+}
+
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
     case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
+    case GRB_PROC_YY_CON: {
+      const int apdg = abs(S->d->nodes[0].pdg);
+      if (!(apdg == 11 || apdg == 13 || apdg == 15) || S->d->nodes[1].pdg != -S->d->nodes[0].pdg || S->d->qed_alpha != 0) {
+        S->nhamp = 0;
+        return NAN; /* only charged lepton pairs with QED_alpha = ZERO are restated */
+      }
+      return yy_con_amp2(S);
+    }
     case GRB_PROC_PP_RES: return res_amp2(S, 0);
     case GRB_PROC_PP_RES_CON: return res_amp2(S, 1);
     case GRB_PROC_PP_CONTENSOR: {

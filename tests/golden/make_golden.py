@@ -30,6 +30,8 @@ CASES = [
     ("c3_atlas_neg_pipi_rescon_born", "./tests/run_atlas_multi/ATLAS_NEG.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 1024, 8, True),
     ("c3_atlas_kk_res_born", "./tests/run_atlas_multi/ATLAS.json", "PP[RES]<F> -> K+ K-", 0, 1024, 8, True),
     ("c2_alice_pipi_rescon_screened", "./tests/processes/ALICECUTS.json", "PP[RES+CON]<F> -> pi+ pi-", 1, 256, 8, True),
+    ("c4_cms_mumu_yycon_born", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 2048, 8, True),
+    ("c4_cms_ee_yycon_born", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> e+ e-", 0, 1024, 8, True),
     ("c5_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 2048, 24, True),
 ]

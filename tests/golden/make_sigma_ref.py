@@ -17,6 +17,9 @@ CASES = [
     ("c1_test_pipi_con_born", "input/test.json", "PP[CON]<F> -> pi+ pi-", "false", 300000, 0.001),
     ("c1_test_pipi_tensor_born", "input/test.json", "PP[CONTENSOR]<F> -> pi+ pi-", "false", 300000, 0.001),
     ("c2_alice_pipi_tensor_screened", "tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", "true", 20000, 0.01),
+    ("c1_test_pipi_rescon_born", "input/test.json", "PP[RES+CON]<F> -> pi+ pi-", "false", 300000, 0.001),
+    ("c3_atlas_pipi_rescon_born", "tests/run_atlas_multi/ATLAS.json", "PP[RES+CON]<F> -> pi+ pi-", "false", 300000, 0.002),
+    ("c4_cms_mumu_yycon_born", "tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", "false", 300000, 0.001),
     ("c5_cms_rhorho_4pi_con_born", "tests/processes/CMSCUTS.json",
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", "false", 300000, 0.002),
 ]

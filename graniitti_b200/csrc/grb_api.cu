@@ -59,7 +59,7 @@ struct grb_engine {
 static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
 static thread_local std::string g_last_global_error;
 
-#define ITEM_NF 21
+#define ITEM_NF 22
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -519,7 +519,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 2 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
@@ -574,7 +574,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.ev_out = e->d_ev; a.ev_count = e->d_ev_count; a.ev_cap = e->ev_cap; a.npart = npart; a.pay = e->d_pay;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int), e->stream));
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 2 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));

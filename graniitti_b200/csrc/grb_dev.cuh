@@ -193,7 +193,7 @@ __device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4,
 }
 
 // reference MKinematics.h:117-160 SolvePz3_B (unequal forward masses)
-static __device__ __noinline__ double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5,
+__device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5,
                                            double E5, const PzConst &c) {
   const double s   = c.s;
   const double t2  = E5 * E5;

@@ -20,7 +20,7 @@
 namespace grb {
 
 enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY, IT_P3 = 9, IT_P4 = 13,
-       IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_NF };
+       IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_AMP2, IT_NF };
 
 
 // ---- block-level VEGAS accumulation ---------------------------------------------------------------------
@@ -211,20 +211,29 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
         if (isnan(W) || isinf(W)) { W = 0.0; amp_ok = false; }
       }
     }
-    // screened: append to the work list (warp-aggregated slot reservation)
+    // screened: append to the work list (warp-aggregated slot reservation).  Two classes, filled from the two
+    // ends of the buffer: equal-mass points (SolvePz3_A in the loop) from slot 0 up, the others from the top down.
     if (P.screening) {
-      const unsigned m = __ballot_sync(0xffffffffu, valid);
-      if (m) {
-        const int    lane = threadIdx.x & 31;
-        const int    lead = __ffs(m) - 1;
-        unsigned int slot0 = 0;
-        if (lane == lead) slot0 = atomicAdd(a.item_count, (unsigned)__popc(m));
-        slot0 = __shfl_sync(0xffffffffu, slot0, lead);
+      LoopInv L;
+      bool    same = false;
+      if (valid) {
+        make_loop_inv<NN>(S, L);
+        same = L.same_mass;
+      }
+      const unsigned mA = __ballot_sync(0xffffffffu, valid && same), mB = __ballot_sync(0xffffffffu, valid && !same);
+      if (mA | mB) {
+        const int lane = threadIdx.x & 31;
+        unsigned int a0 = 0, b0 = 0;
+        if (lane == 0) {
+          if (mA) a0 = atomicAdd(a.item_count, (unsigned)__popc(mA));
+          if (mB) b0 = atomicAdd(a.item_count + 1, (unsigned)__popc(mB));
+        }
+        a0 = __shfl_sync(0xffffffffu, a0, 0);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
         if (valid) {
-          const int64_t slot = slot0 + __popc(m & ((1u << lane) - 1));
-          if (slot < a.item_cap) {
-            LoopInv L;
-            make_loop_inv<NN>(S, L);
+          const unsigned below = (1u << lane) - 1;
+          const int64_t slot = same ? (int64_t)a0 + __popc(mA & below) : a.item_cap - 1 - ((int64_t)b0 + __popc(mB & below));
+          if (slot >= 0 && slot < a.item_cap) {
             double *it = a.items + slot;
             const int64_t c = a.item_cap;
             it[IT_P1X * c] = L.p1x; it[IT_P1Y * c] = L.p1y; it[IT_P2X * c] = L.p2x; it[IT_P2Y * c] = L.p2y;
@@ -287,33 +296,55 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
   if (VEGAS) hist_flush(nb, dim, a.acc);
 }
 
-template <bool VEGAS, int MINB, int AMP>
+// k_screen is the pure loop integral: it reads one work-list item, writes |A_born + A_loop|^2 back into the item.
+// Weight assembly, NaN handling, outputs and VEGAS accumulation happen in k_finish, which keeps the hot kernel's
+// register budget free of histogram/atomic code.
+template <int AMP, bool SAME>
+__device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
+  const DevProc &P = c_proc;
+  const int64_t  c = a.item_cap;
+  double *       it = a.items + s;
+  LoopInv        L;
+  L.p1x = it[IT_P1X * c]; L.p1y = it[IT_P1Y * c]; L.p2x = it[IT_P2X * c]; L.p2y = it[IT_P2Y * c];
+  L.m1 = it[IT_M1 * c]; L.m2 = it[IT_M2 * c]; L.mXsq = it[IT_MXSQ * c];
+  L.shY = it[IT_SHY * c]; L.chY = it[IT_CHY * c];
+  L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
+  L.emax = P.sqrt_s - (L.m1 + L.m2);
+  L.same_mass = SAME;
+  L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
+  L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
+  cx h0;
+  h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
+  it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
+}
+
+template <int MINB, int AMP>
 __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
-  const DevProc &P   = c_proc;
-  const int      dim = P.lipsdim;
-  const int      nb  = a.bins * dim;
+  const int64_t nA = min((int64_t)a.item_count[0], a.item_cap), nB = min((int64_t)a.item_count[1], a.item_cap - nA);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // class A occupies slots [0, nA), class B slots [cap - nB, cap); each loop is branch-uniform.  The B loop starts
+  // where the A loop's last sweep left idle threads (rotation by nA) to balance the persistent grid.
+  for (int64_t t = t0; t < nA; t += stride) screen_item<AMP, true>(a, t);
+  const int64_t rot = (stride - (nA % stride)) % stride;
+  for (int64_t t = (t0 + rot) % stride; t < nB; t += stride) screen_item<AMP, false>(a, a.item_cap - nB + t);
+}
+
+// weight assembly + outputs + VEGAS accumulation for the screened work list
+template <bool VEGAS>
+__global__ void __launch_bounds__(256) k_finish(const PointArgs a) {
+  const int dim = c_proc.lipsdim;
+  const int nb  = a.bins * dim;
   if (VEGAS) hist_clear(nb);
   ThreadSums    ts;
-  const int64_t n_items = min((int64_t)*a.item_count, a.item_cap);
-  const int64_t stride  = (int64_t)gridDim.x * blockDim.x;
-  const int64_t c       = a.item_cap;
-  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_items; s += stride) {
+  const int64_t c = a.item_cap;
+  const int64_t nA = min((int64_t)a.item_count[0], c), nB = min((int64_t)a.item_count[1], c - nA);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nA + nB; t += stride) {
+    const int64_t s  = t < nA ? t : c - nB + (t - nA);
     const double *it = a.items + s;
-    LoopInv       L;
-    L.p1x = it[IT_P1X * c]; L.p1y = it[IT_P1Y * c]; L.p2x = it[IT_P2X * c]; L.p2y = it[IT_P2Y * c];
-    L.m1 = it[IT_M1 * c]; L.m2 = it[IT_M2 * c]; L.mXsq = it[IT_MXSQ * c];
-    L.shY = it[IT_SHY * c]; L.chY = it[IT_CHY * c];
-    L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
-    L.emax = P.sqrt_s - (L.m1 + L.m2);
-    L.same_mass = fabs(L.m1 - L.m2) < 1e-9;
-    L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
-    L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
-    cx h0;
-    h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
-    const double pref = it[IT_PREF * c], vw = it[IT_VW * c];
-    const double amp2 = screened_amp2_h1<AMP>(L, h0);
-    double       W    = pref * amp2;
-    bool         ok   = true;
+    const double  amp2 = it[IT_AMP2 * c], pref = it[IT_PREF * c], vw = it[IT_VW * c];
+    double        W    = pref * amp2;
+    bool          ok   = true;
     if (isnan(W) || isinf(W)) { W = 0.0; ok = false; }
     const int32_t idx = a.item_idx[s];
     if (a.w) a.w[idx] = W;
@@ -397,11 +428,10 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
 
 template <int MINB, int AMP>
 static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
-  const int    threads = 128;
-  const int    blocks  = sm_count * MINB;  // persistent: exactly the resident CTAs
-  const size_t smem    = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
-  if (a.vegas) k_screen<true, MINB, AMP><<<blocks, threads, smem, st>>>(a);
-  else k_screen<false, MINB, AMP><<<blocks, threads, 0, st>>>(a);
+  k_screen<MINB, AMP><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  if (a.vegas) k_finish<true><<<sm_count * 4, 256, smem, st>>>(a);
+  else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);
 }
 
 int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st) {
@@ -409,15 +439,15 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
   if (amp_kind == AMP_TENSOR_2XS) {
     launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
-    return 1;
+    return 2;
   }
   if (amp_kind == AMP_REGGE_RES) {
     launch_screen_t<2, AMP_REGGE_RES>(a, sm_count, st);
-    return 1;
+    return 2;
   }
   if (amp_kind == AMP_REGGE_RES_CON) {
     launch_screen_t<2, AMP_REGGE_RES_CON>(a, sm_count, st);
-    return 1;
+    return 2;
   }
   switch (minb) {
     case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;
@@ -425,7 +455,7 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
     case 6: launch_screen_t<6, AMP_REGGE>(a, sm_count, st); break;
     default: launch_screen_t<4, AMP_REGGE>(a, sm_count, st); break;
   }
-  return 1;
+  return 2;
 }
 
 cudaError_t run_dfma_peak(int sm_count, double *tflops) {

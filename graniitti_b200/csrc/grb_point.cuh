@@ -530,6 +530,7 @@ __device__ __forceinline__ void make_loop_inv(const PointState<NN> &S, LoopInv &
 // One node of the loop.  The tests that can never fire are not evaluated: px, py, pz are conserved by
 // construction (X = -(n1+n2), p2z = -(Xz+p1z)), and ss[0][1], ss[0][2] >= (m_p + m_X)^2; the energy test of
 // CheckEMC, the direction test, ss13..ss24 >= 0 and t1, t2 <= 0 are kept.
+template <bool SAME>
 __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, double ktx, double kty, NodeKin &o) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
@@ -538,7 +539,10 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   const double mtX = msqrt(L.mXsq + (Xx * Xx + Xy * Xy));
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   if (Xe > L.emax) return false;
-  const double p1z = L.same_mass ? solve_pz3_A(L.m1, pt1, pt2, Xz, Xe, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
+  // SolvePz picks its branch on |m1 - m2| < 1e-9 (MKinematics.h:220-229); m1, m2 are re-derived from the saved
+  // 4-vectors (MFactorized.cc:97-98) whose E^2 - p^2 carries ~3e-9 of rounding noise, so ~2/3 of all points take
+  // the unequal-mass branch.  The work list is partitioned by that flag so that a warp runs one branch only.
+  const double p1z = SAME ? solve_pz3_A(L.m1, pt1, pt2, Xz, Xe, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
   const double p2z = -(Xz + p1z);
   if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
   const double e1 = msqrt(L.m1sq + pow2(pt1) + pow2(p1z));
@@ -565,7 +569,7 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
 // reference src/MProcess.cc:157-288 S3ScreenedAmp2 for a one-amplitude process (H = 1): returns
 // |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order
 // (phi = 2 pi folded onto phi = 0, see grb_set_eikonal).  Rejected nodes contribute 0 but keep their weight.
-template <int AMP>
+template <int AMP, bool SAME>
 __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h0) {
   const DevLoop &Q = c_loop;
   PzConst        pc;
@@ -577,7 +581,7 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
     for (int j = 0; j <= Q.nkt; ++j) {
       const double kt = Q.kt[j];
       NodeKin      in;
-      if (!loop_node(L, pc, kt * cp, kt * sp, in)) continue;
+      if (!loop_node<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
       const cx A = amplitude<AMP>(in, L.p3, L.p4);
       // f = A_eik * A * kt * w_j, with b_j = A_eik(kt_j^2) kt_j w_j tabulated
       Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgrb.so")
-SOURCES = ["grb_kernels.cu", "grb_api.cu", "grb_host.cc"]
+SOURCES = ["grb_kernels.cu", "grb_api.cu", "grb_eikonal.cu", "grb_host.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "grb_dev.cuh"
+#include "grb_eikonal.h"
 #include "grb_host.h"
 
 using namespace grb;
@@ -686,9 +687,21 @@ int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, doubl
   return n;
 }
 
-int grb_build_eikonal(grb_engine *e, int, int, double *, double *, double *, double *) {
-  if (e) e->err = "device eikonal table builder is not implemented yet";
-  return GRB_ERR_UNSUPPORTED;
+int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_out, double *omega_re_out,
+                      double *omega_im_out, double *kt2_out, double *re_out, double *im_out, double *xs_tot_el_inel) {
+  if (!e) return GRB_ERR_ARG;
+  if (number_bt <= 0) number_bt = 10000;    // modeldata/NUMERICS.json NUMERICS_EIKONAL defaults
+  if (number_kt2 <= 0) number_kt2 = 10000;
+  CK(cudaSetDevice(e->device));
+  EikonalTables T;
+  const int rc = build_eikonal_tables(e->desc.soft, e->desc.s, number_bt, number_kt2, e->stream, T, e->err);
+  if (rc > 0) return GRB_ERR_CUDA;
+  if (rc < 0) return rc == -3 ? GRB_ERR_UNSUPPORTED : GRB_ERR_ARG;
+  auto put = [](double *dst, const std::vector<double> &v) { if (dst) memcpy(dst, v.data(), sizeof(double) * v.size()); };
+  put(bt_out, T.bt); put(omega_re_out, T.om_re); put(omega_im_out, T.om_im);
+  put(kt2_out, T.kt2); put(re_out, T.sa_re); put(im_out, T.sa_im);
+  if (xs_tot_el_inel) for (int k = 0; k < 3; ++k) xs_tot_el_inel[k] = T.xs[k] * 1e3;  // barn -> mb
+  return grb_set_eikonal(e, T.kt2.data(), T.sa_re.data(), T.sa_im.data(), (int)T.kt2.size());
 }
 
 int grb_comm_unique_id(char id_out[128]) {

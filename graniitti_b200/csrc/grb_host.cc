@@ -812,3 +812,59 @@ extern "C" int grb_parse_card(const char *card_path, const char *process_overrid
   seterr("");
   return GRB_OK;
 }
+
+// ---- the reference's eikonal table cache: names and file format (src/MEikonal.cc:60-128, 404-487) ----------
+
+extern "C" int grb_eikonal_cache_names(const grb_process_desc *d, int pdg1, int pdg2, int number_bt, int number_kt2,
+                                       char *mbt_name, char *msa_name, int cap) {
+  if (!d || cap <= 0) return GRB_ERR_ARG;
+  if (number_bt <= 0) number_bt = 10000;
+  if (number_kt2 <= 0) number_kt2 = 10000;
+  using std::to_string;
+  const grb_param_soft &S = d->soft;
+  const double GeV2fm = (6.582119514E-25 * 2.99792458E8) * 1E15;
+  // PARAM_SOFT::GetHashString (src/MForm.cc:94-100), MEikonalNumerics::GetHashString (MEikonal.h:60-67)
+  const std::string soft = to_string(S.DELTA_P) + to_string(S.ALPHA_P) + to_string(S.gN_P) + to_string(S.gN_O) + to_string(S.fc1) +
+                           to_string(S.fc2) + to_string(S.fc3) + to_string(S.odderon_on != 0);
+  const std::string num = to_string(1E-6) + to_string(25.0) + to_string((unsigned)number_kt2) + to_string(false) + to_string(1E-6) +
+                          to_string(10.0 / GeV2fm) + to_string((unsigned)number_bt) + to_string(false) + to_string(1E-9) +
+                          to_string(30.0) + to_string(10000u);
+  auto djb2 = [](const std::string &s) {  // gra::aux::djb2hash, src/MAux.cc:281-287
+    unsigned long h = 5381;
+    for (auto c : s) h = (h << 5) + h + c;
+    return h;
+  };
+  char sq[64];
+  snprintf(sq, sizeof sq, "%.0f", std::sqrt(d->s > 0 ? d->s : 0.0));
+  const std::string p1 = to_string(pdg1), p2 = to_string(pdg2), tail = "_" + p1 + "_" + p2 + "_" + sq + "_";
+  const std::string mbt = "MBT" + tail + to_string(djb2(to_string(d->s) + p1 + "_" + p2 + soft + num));
+  const std::string msa = "MSA" + tail + to_string(djb2(to_string(d->s) + p1 + p2 + soft + num));
+  if (mbt_name) snprintf(mbt_name, cap, "%s", mbt.c_str());
+  if (msa_name) snprintf(msa_name, cap, "%s", msa.c_str());
+  return ((int)mbt.size() < cap && (int)msa.size() < cap) ? GRB_OK : GRB_ERR_ARG;
+}
+
+extern "C" int grb_write_eikonal_file(const char *path, const double *x, const double *re, const double *im, int n) {
+  if (!path || !x || !re || !im || n <= 0) return GRB_ERR_ARG;
+  FILE *f = fopen(path, "w");
+  if (!f) return GRB_ERR_PARSE;
+  for (int i = 0; i < n; ++i) fprintf(f, "%.15g,%.15g,%.15g\n", x[i], re[i], im[i]);  // IArray1D::WriteArray
+  return fclose(f) == 0 ? GRB_OK : GRB_ERR_PARSE;
+}
+
+extern "C" int grb_read_eikonal_file(const char *path, double *x, double *re, double *im, int n) {
+  if (!path || !x || !re || !im || n <= 0) return GRB_ERR_ARG;
+  FILE *f = fopen(path, "r");
+  if (!f) return GRB_ERR_PARSE;
+  int got = 0;
+  char line[256];
+  while (got < n && fgets(line, sizeof line, f)) {
+    char *p = line, *q;
+    x[got] = strtod(p, &q);  if (q == p || *q != ',') break;  p = q + 1;
+    re[got] = strtod(p, &q); if (q == p || *q != ',') break;  p = q + 1;
+    im[got] = strtod(p, &q); if (q == p) break;
+    ++got;
+  }
+  fclose(f);
+  return got == n ? GRB_OK : GRB_ERR_PARSE;  // IArray1D::ReadArray: "Corrupted file" unless 3 (N+1) fills
+}

@@ -44,7 +44,14 @@ def lib():
         L.grb_set_eikonal.restype = cint
         L.grb_set_eikonal.argtypes = [vp, vp, vp, vp, cint]
         L.grb_build_eikonal.restype = cint
-        L.grb_build_eikonal.argtypes = [vp, cint, cint, vp, vp, vp, vp]
+        L.grb_build_eikonal.argtypes = [vp, cint, cint, vp, vp, vp, vp, vp, vp, vp]
+        L.grb_eikonal_cache_names.restype = cint
+        L.grb_eikonal_cache_names.argtypes = [C.POINTER(_abi.ProcessDesc), cint, cint, cint, cint, C.c_char_p,
+                                              C.c_char_p, cint]
+        L.grb_write_eikonal_file.restype = cint
+        L.grb_write_eikonal_file.argtypes = [C.c_char_p, vp, vp, vp, cint]
+        L.grb_read_eikonal_file.restype = cint
+        L.grb_read_eikonal_file.argtypes = [C.c_char_p, vp, vp, vp, cint]
         L.grb_eval.restype = cint
         L.grb_eval.argtypes = [vp, i64, vp, cint, vp, cint, vp, vp, vp]
         L.grb_vegas_iterate.restype = cint
@@ -104,6 +111,30 @@ def parse_card(card, process=None, pomloop=-1, base=None):
     if rc != 0:
         raise GrbError(rc, buf.value.decode(errors="replace"))
     return d
+
+
+def eikonal_cache_names(desc, beam_pdg=(2212, 2212), number_bt=0, number_kt2=0):
+    """File names of the reference's eikonal/ table cache for this configuration (MBT_..., MSA_...)."""
+    a, b = C.create_string_buffer(128), C.create_string_buffer(128)
+    rc = lib().grb_eikonal_cache_names(C.byref(desc), beam_pdg[0], beam_pdg[1], number_bt, number_kt2, a, b, 128)
+    if rc != 0:
+        raise GrbError(rc, "grb_eikonal_cache_names")
+    return a.value.decode(), b.value.decode()
+
+
+def write_eikonal_file(path, x, re, im):
+    x, re, im = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, re, im))
+    rc = lib().grb_write_eikonal_file(str(path).encode(), x.ctypes.data, re.ctypes.data, im.ctypes.data, len(x))
+    if rc != 0:
+        raise GrbError(rc, f"grb_write_eikonal_file({path})")
+
+
+def read_eikonal_file(path, n_points=10001):
+    t = np.zeros((3, n_points))
+    rc = lib().grb_read_eikonal_file(str(path).encode(), t[0].ctypes.data, t[1].ctypes.data, t[2].ctypes.data, n_points)
+    if rc != 0:
+        raise GrbError(rc, f"grb_read_eikonal_file({path})")
+    return t
 
 
 def optimize_grid(xmat, f2mat, lam=1.5):
@@ -169,6 +200,17 @@ class Engine:
     def set_eikonal(self, kt2, re, im):
         kt2, re, im = (np.ascontiguousarray(a, dtype=np.float64) for a in (kt2, re, im))
         self._check(lib().grb_set_eikonal(self._h, kt2.ctypes.data, re.ctypes.data, im.ctypes.data, len(kt2)))
+
+    def build_eikonal(self, number_bt=0, number_kt2=0):
+        """Build the opacity (MBT) + screening-amplitude (MSA) tables on the device (reference
+        MEikonal::S3Constructor) and install the MSA. Returns dict(mbt [3][nbt+1], msa [3][nkt2+1], xs_mb [3])."""
+        nb = (number_bt if number_bt > 0 else 10000) + 1
+        nk = (number_kt2 if number_kt2 > 0 else 10000) + 1
+        mbt, msa, xs = np.zeros((3, nb)), np.zeros((3, nk)), np.zeros(3)
+        self._check(lib().grb_build_eikonal(self._h, number_bt, number_kt2, mbt[0].ctypes.data, mbt[1].ctypes.data,
+                                            mbt[2].ctypes.data, msa[0].ctypes.data, msa[1].ctypes.data,
+                                            msa[2].ctypes.data, xs.ctypes.data))
+        return dict(mbt=mbt, msa=msa, xs_mb=xs)
 
     def eval(self, u, tape, want_dump=False):
         """Host numpy convenience: u [dim][n], tape [dtape][n] (SoA). Returns w, flags, dump."""

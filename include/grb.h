@@ -233,11 +233,24 @@ void        grb_destroy(grb_engine *e);
  * (src/MEikonal.cc:46-128).  Host pointers.                                                              */
 int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const double *im, int n_points);
 
-/* Build the density (MBT) and amplitude (MSA) tables on the device from PARAM_SOFT, replacing
- * MEikonal::S3Density/S3Screening/S3CalculateArray (src/MEikonal.cc:177-401). Optionally returns the MSA
- * table (n_points = NumberKT2+1 each) and sigma_tot/el/inel in mb (S3CalcXS, :262-376).                  */
-int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *kt2_out, double *re_out,
-                      double *im_out, double *xs_tot_el_inel /* [3] or NULL */);
+/* Build the density (MBT) and amplitude (MSA) tables on the device from PARAM_SOFT and install the MSA table,
+ * replacing MEikonal::S3Density/S3Screening/S3CalculateArray (src/MEikonal.cc:177-242,379-401; one
+ * Fourier-Bessel integral of 10 001 nodes per table row) and S3CalcXS (:262-376, single-channel part).
+ * number_bt / number_kt2 <= 0 select the NUMERICS.json defaults (10000).  Optional host outputs: the MBT table
+ * (number_bt+1 rows), the MSA table (number_kt2+1 rows), sigma_tot/el/inel in mb.  Values are rounded to the
+ * 15 significant digits of the reference's ASCII table cache (:84-91,404-436), as the reference reads them.  */
+int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_out, double *omega_re_out,
+                      double *omega_im_out, double *kt2_out, double *re_out, double *im_out,
+                      double *xs_tot_el_inel /* [3] or NULL */);
+
+/* The reference's table cache (src/MEikonal.cc:60-128): file names "MBT_<pdg1>_<pdg2>_<sqrts>_<djb2 hash>" /
+ * "MSA_..." (hash over s, beams, PARAM_SOFT, MEikonalNumerics; src/MForm.cc:94-100, MEikonal.h:60-67,
+ * MAux.cc:281-287) and the 3-column "%.15g" CSV rows of IArray1D::WriteArray/ReadArray (:404-487), so that
+ * tables are interchangeable with the reference's eikonal/ directory.  Host-only.                          */
+int grb_eikonal_cache_names(const grb_process_desc *desc, int beam1_pdg, int beam2_pdg, int number_bt,
+                            int number_kt2, char *mbt_name, char *msa_name, int cap);
+int grb_write_eikonal_file(const char *path, const double *x, const double *re, const double *im, int n_points);
+int grb_read_eikonal_file(const char *path, double *x, double *re, double *im, int n_points);
 
 /* ---- seam A x n : batched EventWeight --------------------------------------------------------------- */
 

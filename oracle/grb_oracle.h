@@ -24,6 +24,11 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
                     int32_t *tape_used);
 
+/* CPU restatement of the reference's eikonal table construction (oracle/grb_oracle_eikonal.c): opacity MBT
+ * (n_bt+1 rows) and screening amplitude MSA (n_kt2+1 rows), xs = sigma_tot, sigma_el, sigma_inel in barn */
+int grb_oracle_build_eikonal(const grb_param_soft *S, double s, int n_bt, int n_kt2, double *bt_x, double *bt_re,
+                             double *bt_im, double *kt2_x, double *sa_re, double *sa_im, double *xs);
+
 /* Evaluate the tensor-pomeron amplitude algebra in x87 extended precision from the same double inputs
  * (measures the rounding noise of the reference's double-precision tensor contraction). Born level only. */
 void grb_oracle_set_extended(int on);

@@ -42,6 +42,9 @@ UNIT = "points/s"
 
 # SURVEY.md section 8(d) algorithmic flop model (transcendental = 20 flop, FMA = 2)
 F_KIN, F_BORN, F_NODE = 600.0, 650.0, 700.0
+# DRAM traffic of k_screen per work-list item, from the committed `ncu --set full` capture
+# (profiles/r01_k_screen_summary.txt: dram read 282.6 MB + write 16.7 MB for the 1 866 000 items of one launch)
+SCREEN_DRAM_BYTES_PER_ITEM = (282.602240e6 + 16.744704e6) / 1.866e6
 
 
 def env_int(k, d):
@@ -293,7 +296,10 @@ def run_ours(args):
                         "points_per_step_per_gpu": n_e2e, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
                         "api": "grb_eval (seam A x n) with pinned host buffers, H2D+D2H inside the timed region"},
                 "roofline": {"bound": "fp64", "kernel": "k_screen", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                             "frac": ach / peak if peak else None, "traffic": None,
+                             "frac": ach / peak if peak else None,
+                             "traffic": SCREEN_DRAM_BYTES_PER_ITEM * n_items / max(state["n_screen"], 1),
+                             "traffic_unit": "bytes per launch (ncu dram read+write per work-list item x items per launch; "
+                                             "profiles/r01_k_screen_summary.txt)",
                              "peak_source": "measured live: dependent-free DFMA chains on all SMs (grb_measure_dfma_peak); "
                                             "MEASURED_PEAKS.json has no fp64 figure",
                              "flops_per_node": F_NODE, "nodes_per_accepted_point": n_nodes,

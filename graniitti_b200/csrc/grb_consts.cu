@@ -1,0 +1,84 @@
+// grb_consts.cu -- the __constant__ blocks shared by every kernel translation unit (relocatable device code), their
+// uploads, the k_points dispatch and the fp64 FMA peak microbenchmark.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "grb_point.cuh"
+
+namespace grb {
+
+__constant__ DevProc c_proc;
+__constant__ DevLoop c_loop;
+__constant__ DevRes  c_res;
+
+cudaError_t upload_proc(const DevProc &p, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_proc, &p, sizeof(DevProc), 0, cudaMemcpyHostToDevice, st);
+}
+cudaError_t upload_res(const DevRes &r, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_res, &r, sizeof(DevRes), 0, cudaMemcpyHostToDevice, st);
+}
+cudaError_t upload_loop(const DevLoop &l, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_loop, &l, sizeof(DevLoop), 0, cudaMemcpyHostToDevice, st);
+}
+
+template <int AMP>
+void launch_points_amp(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st);
+
+int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st) {
+  const int     threads = 256;
+  int64_t       blocks  = (a.n + threads - 1) / threads;
+  const int64_t cap     = (int64_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  switch (amp_kind) {
+    case AMP_TENSOR_2XS: launch_points_amp<AMP_TENSOR_2XS>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_REGGE_RES: launch_points_amp<AMP_REGGE_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_REGGE_RES_CON: launch_points_amp<AMP_REGGE_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_YY_LL: launch_points_amp<AMP_YY_LL>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    default: launch_points_amp<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+  }
+  return 1;
+}
+
+// ---- fp64 FMA peak microbenchmark (roofline denominator) -------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+cudaError_t run_dfma_peak(int sm_count, double *tflops) {
+  const int blocks = sm_count * 8, threads = 256, iters = 1 << 16;
+  double *  d      = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double) * blocks * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  k_dfma_peak<<<blocks, threads>>>(d, 1024);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(t0);
+    k_dfma_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(t1);
+    e = cudaEventSynchronize(t1);
+    if (e != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d);
+  *tflops = best;
+  return e;
+}
+
+}  // namespace grb

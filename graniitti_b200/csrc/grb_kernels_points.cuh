@@ -1,0 +1,238 @@
+// grb_kernels_points.cuh -- the two hot kernels of the event-weight path and their launchers.
+//
+//   k_points : one thread per phase-space point. Draws (caller-supplied SoA or Philox through the VEGAS
+//              grid) -> <F> kinematics -> cuts -> Born amplitude -> weight prefactor.  Unscreened
+//              processes finish here (weight + VEGAS accumulation).  Screened processes append the
+//              accepted points to a compact SoA work list (warp-aggregated atomics).
+//   k_screen : one thread per accepted point, the eikonal screening loop integral of
+//              MProcess::S3ScreenedAmp2 (reference src/MProcess.cc:157-288) with every loop invariant in
+//              constant memory; uniform trip count, so no divergence after the compaction.
+//
+// VEGAS accumulators (reference src/MGraniitti.cc:1389-1419, a mutex per point there): per-thread
+// running sums -> warp shuffle -> one global atomic per block; the [bins][dim] histograms live in shared
+// memory per block and are flushed once at block exit.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "grb_accum.cuh"
+
+namespace grb {
+
+template <int NN>
+__device__ __forceinline__ void store_momenta(double *dst, int64_t stride, const PointState<NN> &S, int n_nodes) {
+  const v4 *three[3] = {&S.pX, &S.p1, &S.p2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dst[(4 * k + 0) * stride] = three[k]->x; dst[(4 * k + 1) * stride] = three[k]->y;
+    dst[(4 * k + 2) * stride] = three[k]->z; dst[(4 * k + 3) * stride] = three[k]->e;
+  }
+#pragma unroll
+  for (int i = 0; i < NN; ++i)
+    if (i < n_nodes) {
+      dst[(12 + 4 * i + 0) * stride] = S.np4[i].x; dst[(12 + 4 * i + 1) * stride] = S.np4[i].y;
+      dst[(12 + 4 * i + 2) * stride] = S.np4[i].z; dst[(12 + 4 * i + 3) * stride] = S.np4[i].e;
+    }
+}
+
+// ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
+template <int NN, int AMP>
+__device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
+  NodeKin in;
+  in.ss13 = S.ss13; in.ss24 = S.ss24; in.ss14 = S.ss14; in.ss23 = S.ss23;
+  in.t1 = S.t1; in.t2 = S.t2; in.t_hat = S.t_hat; in.u_hat = S.u_hat;
+  in.p1 = S.p1; in.p2 = S.p2; in.pX = S.pX;
+  return amplitude<AMP>(in, S.np4[0], S.np4[1]);
+}
+
+// weight prefactor: everything of MFactorized.cc:173-174 except |A|^2
+template <int NN>
+__device__ __forceinline__ double weight_prefactor(const PointState<NN> &S) {
+  const double J   = 1.0 / fabs(S.p1.z / S.p1.e - S.p2.z / S.p2.e);                      // :441-443
+  const double pt1 = msqrt(pt2_of(S.p1)), pt2 = msqrt(pt2_of(S.p2));
+  const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J;                               // x 1/2 (2pi)^-5 / 4
+  const double vol = (pow2(S.M_MAX) - pow2(S.M_MIN)) * (pt1 * pt2);                     // x (2pi)^2 dlog^2 dY
+  const double C   = c_proc.ps_active ? S.DW / (2 * GRB_PI) : 1.0;
+  return C * psw * vol * c_proc.w_const;
+}
+
+template <int NN, bool VEGAS, int AMP>
+__global__ void __launch_bounds__(256) k_points(const PointArgs a) {
+  const DevProc &P   = c_proc;
+  const int      dim = P.lipsdim;
+  const int      nb  = a.bins * dim;
+  if (VEGAS) hist_clear(nb);
+  ThreadSums ts;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += stride) {
+    const int64_t idx    = base + threadIdx.x;
+    const bool    active = idx < a.n;
+    double        u[GRB_MAX_DIM > 8 ? 8 : GRB_MAX_DIM];
+    uint64_t      packed = 0;
+    double        vw     = 1.0;
+    PointState<NN> S;
+    bool kin = false, fid = false, veto = false, overrun = false;
+    if (active) {
+      if (VEGAS) {
+        DrawsPhilox dr;
+        const uint64_t gp = (uint64_t)(a.first_call + idx);
+        dr.g.k0 = (uint32_t)a.seed; dr.g.k1 = (uint32_t)(a.seed >> 32);
+        dr.p_lo = (uint32_t)gp; dr.p_hi = (uint32_t)(gp >> 32); dr.iter = a.iter;
+        dr.pos = 0; dr.overrun = false;
+        // reference src/MGraniitti.cc:1357-1375: bin pick + in-bin offset, vegasweight = prod zo*BINS
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < dim) {
+            const double zn  = dr.next() * a.bins + 1.0;
+            unsigned     ind = (unsigned)zn;
+            ind = max(1u, min(ind, (unsigned)a.bins));
+            double zo, ac;
+            if (ind > 1) {
+              const double x1 = a.xmat[(ind - 1) * dim + j], x0 = a.xmat[(ind - 2) * dim + j];
+              zo = x1 - x0;
+              ac = x0 + (zn - ind) * zo;
+            } else {
+              zo = a.xmat[(ind - 1) * dim + j];
+              ac = (zn - ind) * zo;
+            }
+            u[j] = 0.0 + ac * 1.0;
+            vw *= zo * a.bins;
+            packed |= (uint64_t)(ind - 1) << (8 * j);
+          }
+        kin     = point_kinematics<NN>(u, dr, S);
+        overrun = dr.overrun;
+      } else {
+        DrawsSoA dr;
+        dr.u = a.u; dr.tape = a.tape; dr.n = a.ld; dr.idx = idx; dr.dtape = a.dtape; dr.pos = 0; dr.overrun = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < dim) u[j] = dr.coord(j);
+        kin     = point_kinematics<NN>(u, dr, S);
+        overrun = dr.overrun;
+      }
+      if (kin) {  // on failure the reference evaluates the cuts on stale state: flags are don't-care
+        fid  = fiducial_cuts<NN>(S);
+        veto = veto_cuts<NN>(S);
+      }
+    }
+    const bool valid = active && kin && fid && veto && !overrun;
+    double     W = 0.0;
+    bool       amp_ok = true;
+    cx         h0 = {0.0, 0.0};
+    double     pref = 0.0;
+    if (valid) {
+      h0   = born_amplitude<NN, AMP>(S);
+      pref = weight_prefactor<NN>(S);
+      if (!P.screening) {
+        W = pref * (h0.re * h0.re + h0.im * h0.im);
+        if (isnan(W) || isinf(W)) { W = 0.0; amp_ok = false; }
+      }
+    }
+    // screened: append to the work list (warp-aggregated slot reservation).  Two classes, filled from the two
+    // ends of the buffer: equal-mass points (SolvePz3_A in the loop) from slot 0 up, the others from the top down.
+    if (P.screening) {
+      LoopInv L;
+      bool    same = false;
+      if (valid) {
+        make_loop_inv<NN>(S, L);
+        same = L.same_mass;
+      }
+      const unsigned mA = __ballot_sync(0xffffffffu, valid && same), mB = __ballot_sync(0xffffffffu, valid && !same);
+      if (mA | mB) {
+        const int lane = threadIdx.x & 31;
+        unsigned int a0 = 0, b0 = 0;
+        if (lane == 0) {
+          if (mA) a0 = atomicAdd(a.item_count, (unsigned)__popc(mA));
+          if (mB) b0 = atomicAdd(a.item_count + 1, (unsigned)__popc(mB));
+        }
+        a0 = __shfl_sync(0xffffffffu, a0, 0);
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (valid) {
+          const unsigned below = (1u << lane) - 1;
+          const int64_t slot = same ? (int64_t)a0 + __popc(mA & below) : a.item_cap - 1 - ((int64_t)b0 + __popc(mB & below));
+          if (slot >= 0 && slot < a.item_cap) {
+            double *it = a.items + slot;
+            const int64_t c = a.item_cap;
+            it[IT_P1X * c] = L.p1x; it[IT_P1Y * c] = L.p1y; it[IT_P2X * c] = L.p2x; it[IT_P2Y * c] = L.p2y;
+            it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
+            it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
+            it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
+            it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
+            it[IT_H0RE * c] = h0.re; it[IT_H0IM * c] = h0.im;
+            it[IT_PREF * c] = pref; it[IT_VW * c] = vw;
+            a.item_idx[slot]  = (int32_t)idx;
+            a.item_bins[slot] = packed;
+            if (VEGAS && a.mode == GRB_MODE_GENERATE) store_momenta<NN>(a.pay + slot, c, S, P.n_nodes);
+          }
+        }
+      }
+    }
+    if (active) {
+      const uint8_t fl = (uint8_t)((kin ? GRB_FLAG_KIN : 0) | (fid ? GRB_FLAG_FID : 0) | (veto ? GRB_FLAG_VETO : 0) |
+                                   (amp_ok ? GRB_FLAG_AMP : 0));
+      if (a.w) a.w[idx] = W;
+      if (a.flags) a.flags[idx] = fl;
+      if (a.dump) {
+        double *D = a.dump + idx;
+        const int64_t n = a.ld;
+        D[GRB_DUMP_T1 * n] = kin ? S.t1 : 0; D[GRB_DUMP_T2 * n] = kin ? S.t2 : 0;
+        D[GRB_DUMP_S1 * n] = kin ? S.s1 : 0; D[GRB_DUMP_S2 * n] = kin ? S.s2 : 0;
+        D[GRB_DUMP_M2 * n] = kin ? S.m2 : 0; D[GRB_DUMP_Y * n] = kin ? S.Y : 0; D[GRB_DUMP_PT * n] = kin ? S.Pt : 0;
+        D[GRB_DUMP_THAT * n] = kin ? S.t_hat : 0; D[GRB_DUMP_UHAT * n] = kin ? S.u_hat : 0;
+        D[GRB_DUMP_AMP2 * n] = valid ? (h0.re * h0.re + h0.im * h0.im) : 0;
+        D[GRB_DUMP_HAMP0_RE * n] = h0.re; D[GRB_DUMP_HAMP0_IM * n] = h0.im;
+      }
+      // statistics (reference stat.Accumulate(aux)); screened weights are added by k_screen
+      ts.n_eval += 1.0;
+      ts.n_kin += kin ? 1.0 : 0.0;
+      ts.n_fid += (kin && fid) ? 1.0 : 0.0;
+      ts.n_veto += (kin && veto) ? 1.0 : 0.0;
+      if (!P.screening) {
+        ts.n_amp += amp_ok ? 1.0 : 0.0;
+        ts.n_naninf += amp_ok ? 0.0 : 1.0;
+        if (VEGAS && W != 0.0) {
+          const double f = W * vw;
+          ts.fsum += f;
+          ts.f2sum += f * f;
+          ts.maxW = fmax(ts.maxW, W);
+          ts.maxf = fmax(ts.maxf, f);
+          hist_add(nb, dim, packed, f);
+          if (a.mode == GRB_MODE_GENERATE) {
+            const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
+            if (es >= 0) {
+              store_momenta<NN>(a.ev_out + es, a.ev_cap, S, P.n_nodes);
+              a.ev_out[(4 * a.npart + 0) * a.ev_cap + es] = W;
+              a.ev_out[(4 * a.npart + 1) * a.ev_cap + es] = f;
+            }
+          }
+        }
+      }
+    }
+  }
+  flush_sums(ts, a.acc);
+  if (VEGAS) hist_flush(nb, dim, a.acc);
+}
+
+// points that were not Valid() count as amplitude_ok in the reference (aux default true): added on the host.
+
+template <int NN, int AMP>
+inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
+  if (a.vegas) k_points<NN, true, AMP><<<blocks, threads, smem, st>>>(a);
+  else k_points<NN, false, AMP><<<blocks, threads, 0, st>>>(a);
+}
+template <int AMP>
+inline void launch_points_n(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
+  if (n_nodes <= 2) launch_points_t<2, AMP>(a, blocks, threads, smem, st);
+  else if (n_nodes <= 6) launch_points_t<6, AMP>(a, blocks, threads, smem, st);  // config 5: rho rho -> 4 pi
+  else launch_points_t<GRB_MAX_NODES, AMP>(a, blocks, threads, smem, st);
+}
+
+
+// one explicit instantiation per amplitude kind lives in its own translation unit (grb_points_*.cu)
+template <int AMP>
+void launch_points_amp(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
+  launch_points_n<AMP>(a, n_nodes, blocks, threads, smem, st);
+}
+
+}  // namespace grb

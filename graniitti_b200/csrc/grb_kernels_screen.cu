@@ -1,0 +1,124 @@
+// grb_kernels_screen.cu -- the screening loop kernels (their own translation unit: the loop kernel dominates both the
+// run time and the compile time).
+//   k_screen : one thread per accepted point, the eikonal screening loop integral of MProcess::S3ScreenedAmp2
+//              (reference src/MProcess.cc:157-288) with every loop invariant in constant memory; uniform trip
+//              count, so no divergence after the compaction.
+//   k_finish : weight assembly, outputs and VEGAS accumulation for the screened work list.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "grb_accum.cuh"
+
+namespace grb {
+
+// k_screen is the pure loop integral: it reads one work-list item, writes |A_born + A_loop|^2 back into the item.
+// Weight assembly, NaN handling, outputs and VEGAS accumulation happen in k_finish, which keeps the hot kernel's
+// register budget free of histogram/atomic code.
+template <int AMP, bool SAME>
+__device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
+  const DevProc &P = c_proc;
+  const int64_t  c = a.item_cap;
+  double *       it = a.items + s;
+  LoopInv        L;
+  L.p1x = it[IT_P1X * c]; L.p1y = it[IT_P1Y * c]; L.p2x = it[IT_P2X * c]; L.p2y = it[IT_P2Y * c];
+  L.m1 = it[IT_M1 * c]; L.m2 = it[IT_M2 * c]; L.mXsq = it[IT_MXSQ * c];
+  L.shY = it[IT_SHY * c]; L.chY = it[IT_CHY * c];
+  L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
+  L.emax = P.sqrt_s - (L.m1 + L.m2);
+  L.same_mass = SAME;
+  L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
+  L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
+  cx h0;
+  h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
+  it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
+}
+
+template <int MINB, int AMP>
+__global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
+  const int64_t nA = min((int64_t)a.item_count[0], a.item_cap), nB = min((int64_t)a.item_count[1], a.item_cap - nA);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // class A occupies slots [0, nA), class B slots [cap - nB, cap); each loop is branch-uniform.  The B loop starts
+  // where the A loop's last sweep left idle threads (rotation by nA) to balance the persistent grid.
+  for (int64_t t = t0; t < nA; t += stride) screen_item<AMP, true>(a, t);
+  const int64_t rot = (stride - (nA % stride)) % stride;
+  for (int64_t t = (t0 + rot) % stride; t < nB; t += stride) screen_item<AMP, false>(a, a.item_cap - nB + t);
+}
+
+// weight assembly + outputs + VEGAS accumulation for the screened work list
+template <bool VEGAS>
+__global__ void __launch_bounds__(256) k_finish(const PointArgs a) {
+  const int dim = c_proc.lipsdim;
+  const int nb  = a.bins * dim;
+  if (VEGAS) hist_clear(nb);
+  ThreadSums    ts;
+  const int64_t c = a.item_cap;
+  const int64_t nA = min((int64_t)a.item_count[0], c), nB = min((int64_t)a.item_count[1], c - nA);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nA + nB; t += stride) {
+    const int64_t s  = t < nA ? t : c - nB + (t - nA);
+    const double *it = a.items + s;
+    const double  amp2 = it[IT_AMP2 * c], pref = it[IT_PREF * c], vw = it[IT_VW * c];
+    double        W    = pref * amp2;
+    bool          ok   = true;
+    if (isnan(W) || isinf(W)) { W = 0.0; ok = false; }
+    const int32_t idx = a.item_idx[s];
+    if (a.w) a.w[idx] = W;
+    if (a.flags && !ok) a.flags[idx] &= (uint8_t)~GRB_FLAG_AMP;
+    if (a.dump) a.dump[GRB_DUMP_AMP2 * a.ld + idx] = amp2;
+    ts.n_amp += ok ? 1.0 : 0.0;
+    ts.n_naninf += ok ? 0.0 : 1.0;
+    if (VEGAS && W != 0.0) {
+      const double f = W * vw;
+      ts.fsum += f;
+      ts.f2sum += f * f;
+      ts.maxW = fmax(ts.maxW, W);
+      ts.maxf = fmax(ts.maxf, f);
+      hist_add(nb, dim, a.item_bins[s], f);
+      if (a.mode == GRB_MODE_GENERATE) {
+        const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
+        if (es >= 0) {
+          for (int r = 0; r < 4 * a.npart; ++r) a.ev_out[(int64_t)r * a.ev_cap + es] = a.pay[(int64_t)r * c + s];
+          a.ev_out[(4 * a.npart + 0) * a.ev_cap + es] = W;
+          a.ev_out[(4 * a.npart + 1) * a.ev_cap + es] = f;
+        }
+      }
+    }
+  }
+  flush_sums(ts, a.acc);
+  if (VEGAS) hist_flush(nb, dim, a.acc);
+}
+
+template <int MINB, int AMP>
+static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
+  k_screen<MINB, AMP><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  if (a.vegas) k_finish<true><<<sm_count * 4, 256, smem, st>>>(a);
+  else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);
+}
+
+int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st) {
+  // tuning knob for profiling runs; the default is the measured best (profiles/)
+  static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
+  if (amp_kind == AMP_TENSOR_2XS) {
+    launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_REGGE_RES) {
+    launch_screen_t<2, AMP_REGGE_RES>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_REGGE_RES_CON) {
+    launch_screen_t<2, AMP_REGGE_RES_CON>(a, sm_count, st);
+    return 2;
+  }
+  switch (minb) {
+    case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;
+    case 5: launch_screen_t<5, AMP_REGGE>(a, sm_count, st); break;
+    case 6: launch_screen_t<6, AMP_REGGE>(a, sm_count, st); break;
+    default: launch_screen_t<4, AMP_REGGE>(a, sm_count, st); break;
+  }
+  return 2;
+}
+
+}  // namespace grb

@@ -6,8 +6,8 @@
 
 namespace grb {
 
-__constant__ DevProc c_proc;
-__constant__ DevLoop c_loop;
+extern __constant__ DevProc c_proc;  // defined in grb_consts.cu (relocatable device code)
+extern __constant__ DevLoop c_loop;
 
 }  // namespace grb
 

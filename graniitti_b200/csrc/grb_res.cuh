@@ -12,7 +12,7 @@
 
 namespace grb {
 
-__constant__ DevRes c_res;
+extern __constant__ DevRes c_res;  // defined in grb_consts.cu
 
 __device__ __forceinline__ cx cmul(const cx &a, const cx &b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 __device__ __forceinline__ cx cmulc(const cx &a, const cx &b) { return {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im}; }  // a * conj(b)

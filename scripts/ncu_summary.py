@@ -1,0 +1,38 @@
+"""Condense an .ncu-rep (one `ncu --set full` capture) into the few numbers DESIGN.md / bench.py cite.
+usage: python scripts/ncu_summary.py gpurun_out/prof_x.ncu-rep > profiles/rNN_x_summary.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_inst_executed_op_local_ld.sum",
+        "smsp__sass_inst_executed_op_local_st.sum", "smsp__sass_inst_executed_op_global_ld.sum", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__warps_active.avg.per_cycle_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        u = dict(zip(hdr, units))
+        print(f"kernel: {d['Kernel Name']}   grid {d.get('Grid Size')} block {d.get('Block Size')}")
+        for k in KEYS:
+            if k in d:
+                print(f"  {k:75s} {d[k]:>18s} {u[k]}")
+        stalls = sorted(((float(d[k]), k) for k in hdr if k.startswith("smsp__average_warp") and k.endswith("_per_issue_active.ratio")
+                         or (k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio"))), reverse=True)
+        print("  top warp stall reasons (warp-cycles per issued instruction):")
+        for v, k in stalls[:6]:
+            print(f"    {k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):40s} {v:8.3f}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

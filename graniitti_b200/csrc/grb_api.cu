@@ -98,9 +98,18 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     if (d.qed_alpha != 0) { err = "yy[CON]: PARAM_STRUCTURE.QED_alpha must be ZERO on the device path"; return GRB_ERR_UNSUPPORTED; }
     if (d.screening) { err = "yy[CON] with POMLOOP (16 helicity amplitudes in the loop) is not on the device path yet"; return GRB_ERR_UNSUPPORTED; }
   }
-  if (d.proc == GRB_PROC_PP_CONTENSOR && !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0)) {
-    err = "PP[CONTENSOR]: only pseudoscalar pairs (2xS) have a device amplitude yet";
-    return GRB_ERR_UNSUPPORTED;
+  if (d.proc == GRB_PROC_PP_CONTENSOR) {
+    const bool s2 = d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0;
+    const bool v2 = d.nodes[0].spinX2 == 2 && d.nodes[1].spinX2 == 2 && d.nodes[0].pdg == d.nodes[1].pdg &&
+                    (d.nodes[0].pdg == 113 || d.nodes[0].pdg == 333);
+    if (!s2 && !v2) {
+      err = "PP[CONTENSOR]: pseudoscalar pairs (2xS) and rho0 rho0 / phi phi (2xV) have a device amplitude; 2xF not yet";
+      return GRB_ERR_UNSUPPORTED;
+    }
+    if (v2 && d.screening) {
+      err = "PP[CONTENSOR] 2xV with POMLOOP (nine helicity amplitudes in the loop) is not on the device path yet";
+      return GRB_ERR_UNSUPPORTED;
+    }
   }
   if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
@@ -168,6 +177,12 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     P.em_kelly = d.em_ff;
     P.amp_kind = (d.proc == GRB_PROC_PP_CONTENSOR) ? 1 : (d.proc == GRB_PROC_PP_RES ? 2 : (d.proc == GRB_PROC_PP_RES_CON ? 3 : 0));
     if (d.proc == GRB_PROC_YY_CON) P.amp_kind = 4;
+    if (d.proc == GRB_PROC_PP_CONTENSOR && d.nodes[0].spinX2 == 2) {  // 2xV (MTensorPomeron.cc:797-813)
+      P.amp_kind = 5;
+      const double *gv = d.nodes[0].pdg == 113 ? d.tpom.gPrhorho : d.tpom.gPphiphi;
+      P.tp_g1 = gv[0]; P.tp_g2 = gv[1];
+      P.tp_vv_coupling = 9.0 * d.tpom.gPNN * d.tpom.gPNN;
+    }
     P.omega = d.regge.omega;
     const double ee = 2. * std::sqrt(1.0 / 137.03599908) * std::sqrt(M_PI);
     P.yy_ee4 = (ee * ee) * (ee * ee);

@@ -37,6 +37,7 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
     case AMP_REGGE_RES: launch_points_amp<AMP_REGGE_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_RES_CON: launch_points_amp<AMP_REGGE_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_YY_LL: launch_points_amp<AMP_YY_LL>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_TENSOR_2XV: launch_points_amp<AMP_TENSOR_2XV>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     default: launch_points_amp<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;

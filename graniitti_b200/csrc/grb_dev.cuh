@@ -64,6 +64,7 @@ struct DevProc {
   double yy_ee4;                                                      // ee^4, ee = 2 sqrt(pi alpha(0)) (MG5 GC_3)
   // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
   double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
+  double tp_g1, tp_g2, tp_vv_coupling;  // 2xV: Pomeron-V-V couplings (a, b of gPrhorho / gPphiphi), 9 gPNN^2
   int    em_kelly, amp_kind;
   DevNode nodes[GRB_MAX_NODES];
 };

@@ -464,6 +464,145 @@ __device__ __forceinline__ cx tensor_me4_2xS(const NodeKin &in, const v4 &p3, co
   return A;
 }
 
+// ---- tensor pomeron continuum, 2 x vector meson (reference src/MTensorPomeron.cc:797-888) --------------------
+// The reference builds rank-4 vertices iG_Pvv = i F_M [2 g1 Gamma0 - g2 Gamma2] (:2224-2238, 2500-2536) and contracts
+// them with the proton vertex and the pomeron propagator through FTensor.  With X^{kl} = 2 P^k P^l - 1/2 P^2 g^{kl}
+// (proton vertex x propagator, as in the 2xS case) the (k,l) contraction is done analytically:
+//   Gamma0.X = S0 (k1.k2 g_uv - k2_u k1_v),                       S0 = 4 (P.k1)(P.k2) - P^2 (k1.k2)
+//   Gamma2.X = 2 k1.k2 (2 P_u P_v - 1/2 P^2 g_uv) + g_uv S0 - 2 k1_v (2 P_u P.k2 - 1/2 P^2 k2_u)
+//                                                        - 2 k2_u (2 P_v P.k1 - 1/2 P^2 k1_v)
+// which leaves one real 4x4 block per vertex; the two blocks of a channel are joined by the Reggeized vector
+// propagator -g_{r1 r2} (:2353-2368) and the result is contracted with the conjugated massive polarisation vectors
+// (src/MDirac.cc:393-470), helicities (-1,0,1) x (-1,0,1).  Nine complex amplitudes; the four helicity-conserving
+// proton combinations carry the same nine (:658-662), so sum_h |A_h|^2 / 4 = sum_9 |A|^2.
+struct Lv { double c[4]; };  // covariant components [t,x,y,z]
+__device__ __forceinline__ Lv lower(const v4 &a) { Lv r; r.c[0] = a.e; r.c[1] = -a.x; r.c[2] = -a.y; r.c[3] = -a.z; return r; }
+__device__ __forceinline__ void pvv_block(const v4 &Pv, const v4 &k1, const v4 &k2, double g1, double g2, double a[4][4]) {
+  const double Pk1 = mdot(Pv, k1), Pk2 = mdot(Pv, k2), P2 = m2_of(Pv), k12 = mdot(k1, k2);
+  const double S0 = 4.0 * Pk1 * Pk2 - P2 * k12;
+  const Lv     Pl = lower(Pv), k1l = lower(k1), k2l = lower(k2);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const double guv = (u == v) ? (u == 0 ? 1.0 : -1.0) : 0.0;
+      const double A0  = S0 * (k12 * guv - k2l.c[u] * k1l.c[v]);
+      const double A2  = 2.0 * k12 * (2.0 * Pl.c[u] * Pl.c[v] - 0.5 * P2 * guv) + guv * S0 -
+                        2.0 * k1l.c[v] * (2.0 * Pl.c[u] * Pk2 - 0.5 * P2 * k2l.c[u]) -
+                        2.0 * k2l.c[u] * (2.0 * Pl.c[v] * Pk1 - 0.5 * P2 * k1l.c[v]);
+      a[u][v] = 2.0 * g1 * A0 - g2 * A2;
+    }
+}
+// conjugated polarisation vectors, contravariant [t,x,y,z]: e[m+1][mu]
+__device__ __forceinline__ void eps_massive_conj(const v4 &k, cx e[3][4]) {
+  const double pt2 = k.x * k.x + k.y * k.y, pt = msqrt(pt2), pm = msqrt(pt2 + k.z * k.z);
+  const double ct = pm > 0.0 ? k.z / pm : 1.0, st = pm > 0.0 ? pt / pm : 0.0;
+  const double cp = pt > 0.0 ? k.x / pt : 1.0, sp = pt > 0.0 ? k.y / pt : 0.0;
+  const double N = 0.70710678118654752440, M = m_of(k), E = k.e;
+  // m = -1: neg = +1, pos = -1;  m = +1: neg = -1, pos = +1;  conj flips the imaginary parts
+  e[0][0] = {0.0, 0.0}; e[0][1] = {ct * cp * N, -sp * N}; e[0][2] = {ct * sp * N, cp * N}; e[0][3] = {-st * N, 0.0};
+  e[2][0] = {0.0, 0.0}; e[2][1] = {-ct * cp * N, -sp * N}; e[2][2] = {-ct * sp * N, cp * N}; e[2][3] = {st * N, 0.0};
+  e[1][0] = {pm / M, 0.0}; e[1][1] = {E * st * cp / M, 0.0}; e[1][2] = {E * st * sp / M, 0.0}; e[1][3] = {E * ct / M, 0.0};
+}
+__device__ __forceinline__ void tensor_me4_2xV(const NodeKin &in, const v4 &p3, const v4 &p4, cx h[9]) {
+  const DevProc &P = c_proc;
+  v4 pa, pb;
+  pa.x = 0.0; pa.y = 0.0; pa.z = P.pb1z; pa.e = P.pb1e;
+  pb.x = 0.0; pb.y = 0.0; pb.z = P.pb2z; pb.e = P.pb2e;
+  v4 P1, P2, pt, pu, mpt, mpu;
+  P1.x = in.p1.x + pa.x; P1.y = in.p1.y + pa.y; P1.z = in.p1.z + pa.z; P1.e = in.p1.e + pa.e;
+  P2.x = in.p2.x + pb.x; P2.y = in.p2.y + pb.y; P2.z = in.p2.z + pb.z; P2.e = in.p2.e + pb.e;
+  pt.x = (pa.x - in.p1.x) - p3.x; pt.y = (pa.y - in.p1.y) - p3.y; pt.z = (pa.z - in.p1.z) - p3.z; pt.e = (pa.e - in.p1.e) - p3.e;
+  pu.x = (p4.x - pa.x) + in.p1.x; pu.y = (p4.y - pa.y) + in.p1.y; pu.z = (p4.z - pa.z) + in.p1.z; pu.e = (p4.e - pa.e) + in.p1.e;
+  mpt.x = -pt.x; mpt.y = -pt.y; mpt.z = -pt.z; mpt.e = -pt.e;
+  mpu.x = -pu.x; mpu.y = -pu.y; mpu.z = -pu.z; mpu.e = -pu.e;
+  // iG_Pvv(prime, p): Gamma(k1 = prime, k2 = -p).  tA = (pt, -p3), tB = (p4, pt), uA = (p4, pu), uB = (pu, -p3)
+  double atA[4][4], btB[4][4], auA[4][4], buB[4][4];
+  pvv_block(P1, pt, p3, P.tp_g1, P.tp_g2, atA);
+  pvv_block(P2, p4, mpt, P.tp_g1, P.tp_g2, btB);
+  pvv_block(P1, p4, mpu, P.tp_g1, P.tp_g2, auA);
+  pvv_block(P2, pu, p3, P.tp_g1, P.tp_g2, buB);
+  // channel matrices M_t(r3,r4) = sum_r1 A(r1,r3) (-g_r1) B(r4,r1),  M_u(r3,r4) = sum_r1 A(r4,r1) (-g_r1) B(r1,r3)
+  double mt[4][4], mu[4][4];
+#pragma unroll
+  for (int r3 = 0; r3 < 4; ++r3)
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+      mt[r3][r4] = -atA[0][r3] * btB[r4][0] + atA[1][r3] * btB[r4][1] + atA[2][r3] * btB[r4][2] + atA[3][r3] * btB[r4][3];
+      mu[r3][r4] = -auA[r4][0] * buB[0][r3] + auA[r4][1] * buB[1][r3] + auA[r4][2] * buB[2][r3] + auA[r4][3] * buB[3][r3];
+    }
+  // scalar factors: 9 gPNN^2 F1 F1 F_M F_M x pomeron propagators x Reggeized vector propagator x ff^2, then -i
+  const double pt2 = m2_of(pt), pu2 = m2_of(pu);
+  const double a1 = P.tp_delta + P.tp_ap * in.t1, a2 = P.tp_delta + P.tp_ap * in.t2;
+  const double Et = exp(a1 * (log(in.ss13) + P.tp_ln_ap) + a2 * (log(in.ss24) + P.tp_ln_ap)) / (16.0 * in.ss13 * in.ss24);
+  const double Eu = exp(a1 * (log(in.ss14) + P.tp_ln_ap) + a2 * (log(in.ss23) + P.tp_ln_ap)) / (16.0 * in.ss14 * in.ss23);
+  const double qa_t = m2_of(pt.x + p3.x, pt.y + p3.y, pt.z + p3.z, pt.e + p3.e);
+  const double qb_t = m2_of(p4.x - pt.x, p4.y - pt.y, p4.z - pt.z, p4.e - pt.e);
+  const double qa_u = m2_of(p4.x - pu.x, p4.y - pu.y, p4.z - pu.z, p4.e - pu.e);
+  const double qb_u = m2_of(pu.x + p3.x, pu.y + p3.y, pu.z + p3.z, pu.e + p3.e);
+  const double FMt  = (1.0 / (1.0 - qa_t / 0.5)) * (1.0 / (1.0 - qb_t / 0.5));
+  const double FMu  = (1.0 / (1.0 - qa_u / 0.5)) * (1.0 / (1.0 - qb_u / 0.5));
+  const double pre  = P.tp_vv_coupling * proton_F1(in.t1) * proton_F1(in.t2);
+  double       fft, ffu, dum;
+  meson_G_nd(pt2, fft, dum);  // numerator = ff^2 (power law: 1 / dum-part handled below)
+  meson_G_nd(pu2, ffu, dum);
+  if (P.offshellFF == 2) {
+    fft = 1.0 / pow2(fma(-(pt2 - P.M2_leg0), P.inv_b_POW, 1.0));
+    ffu = 1.0 / pow2(fma(-(pu2 - P.M2_leg0), P.inv_b_POW, 1.0));
+  }
+  // iD_V: (e^{i phi} s34 / s_thr)^(alpha_R - 1) / (m2 - M0^2), alpha_R = 0.5 + 0.9 m2, phi = pi/2 (e^{(s_thr-s34)/s_thr} - 1)
+  const double s34 = m2_of(in.pX), sthr = 4.0 * P.M2_leg0;
+  const double phi = GRB_PI / 2.0 * exp((sthr - s34) / sthr) - GRB_PI / 2.0, lnr = log(s34 / sthr);
+  const double bt = (0.5 + 0.9 * pt2) - 1.0, bu = (0.5 + 0.9 * pu2) - 1.0;
+  const double Rt = pre * Et * FMt * fft * exp(bt * lnr) / (pt2 - P.M2_leg0);
+  const double Ru = pre * Eu * FMu * ffu * exp(bu * lnr) / (pu2 - P.M2_leg0);
+  // phases: pomerons e^{-i pi (a1+a2)/2}, vector propagator e^{i b phi}, overall -i
+  double sn, cs;
+  sincos(P.tp_phase * (a1 + a2) + bt * phi - GRB_PI / 2.0, &sn, &cs);
+  const cx Ct = {Rt * cs, Rt * sn};
+  sincos(P.tp_phase * (a1 + a2) + bu * phi - GRB_PI / 2.0, &sn, &cs);
+  const cx Cu = {Ru * cs, Ru * sn};
+  cx e3[3][4], e4[3][4];
+  eps_massive_conj(p3, e3);
+  eps_massive_conj(p4, e4);
+#pragma unroll
+  for (int h3 = 0; h3 < 3; ++h3) {
+    // w_t[r4] = sum_r3 e3[r3] mt[r3][r4]
+    cx wt[4], wu[4];
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+      double tr = 0, ti = 0, ur = 0, ui = 0;
+#pragma unroll
+      for (int r3 = 0; r3 < 4; ++r3) {
+        tr = fma(e3[h3][r3].re, mt[r3][r4], tr); ti = fma(e3[h3][r3].im, mt[r3][r4], ti);
+        ur = fma(e3[h3][r3].re, mu[r3][r4], ur); ui = fma(e3[h3][r3].im, mu[r3][r4], ui);
+      }
+      wt[r4] = {tr, ti}; wu[r4] = {ur, ui};
+    }
+#pragma unroll
+    for (int h4 = 0; h4 < 3; ++h4) {
+      cx st = {0, 0}, su = {0, 0};
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const cx &q = e4[h4][r4];
+        st.re += wt[r4].re * q.re - wt[r4].im * q.im; st.im += wt[r4].re * q.im + wt[r4].im * q.re;
+        su.re += wu[r4].re * q.re - wu[r4].im * q.im; su.im += wu[r4].re * q.im + wu[r4].im * q.re;
+      }
+      h[3 * h3 + h4] = {Ct.re * st.re - Ct.im * st.im + Cu.re * su.re - Cu.im * su.im,
+                        Ct.re * st.im + Ct.im * st.re + Cu.re * su.im + Cu.im * su.re};
+    }
+  }
+}
+__device__ __forceinline__ double tensor_2xV_amp2(const NodeKin &in, const v4 &p3, const v4 &p4, cx &h0) {
+  cx h[9];
+  tensor_me4_2xV(in, p3, p4, h);
+  double a2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) a2 += h[k].re * h[k].re + h[k].im * h[k].im;
+  h0 = h[0];
+  return a2;
+}
+
 // PP[RES] / PP[RES+CON]: ME4 + coherent resonance sum (reference PROC_9, PROC_17)
 __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, const v4 &p4) {
   const DevProc &P = c_proc;
@@ -487,10 +626,14 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
 
 namespace grb {
 
-enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4 };
+enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
+  if (AMP == AMP_TENSOR_2XV) {  // unscreened only: |A|^2 = sum over the nine helicity amplitudes
+    cx h0;
+    return {sqrt(tensor_2xV_amp2(in, p3, p4, h0)), 0.0};
+  }
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {

@@ -17,6 +17,8 @@
 #include "grb_oracle.h"
 
 #define _GNU_SOURCE
+#include <complex.h>
+#undef I /* the screening loop names its integral I */
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -605,12 +607,13 @@ static double o_F1(const ost *S, double Q2) {
   return 1.0 / (tau + 1) * o_GE(S, Q2) + tau / (tau + 1) * o_GM(S, Q2);
 }
 
-/* std::pow(complex z, double a) = exp(a * log z) as libstdc++/glibc evaluate it (polar form) */
+/* std::pow(complex z, double a) as libstdc++ evaluates it: real pow for positive real z, else
+ * polar(exp(a * Re clog z), a * Im clog z) with glibc's clog */
 static cx cx_powr(cx z, double a) {
-  if (z.re == 0.0 && z.im == 0.0) return (cx){0, 0};
-  const double lr = log(hypot(z.re, z.im)), th = atan2(z.im, z.re);
-  const double m = exp(a * lr);
-  return (cx){m * cos(a * th), m * sin(a * th)};
+  if (z.im == 0.0 && z.re > 0.0) return (cx){pow(z.re, a), 0.0};
+  const double complex t = clog(__builtin_complex(z.re, z.im));
+  const double rho = exp(a * creal(t)), th = a * cimag(t);
+  return (cx){rho * cos(th), rho * sin(th)};
 }
 
 /* reference src/MTensorPomeron.cc:2288-2298 iD_P: FACTOR * (g g + g g - 1/2 g g) */
@@ -649,21 +652,24 @@ static void tp_iG_Ppsps(v4 prime, v4 p, double g1, cx T[4][4]) {
 }
 /* A(mu,nu) D(mu,nu,a,b) Ga(a,b) Gb(c,d) D2(c,d,k,l) B(k,l), contracted left to right */
 static cx tp_chain(cx A[4][4], cx D1[4][4][4][4], cx Ga[4][4], cx Gb[4][4], cx D2[4][4][4][4], cx B[4][4]) {
+  /* FTensor: T4*T2 double contractions loop the contracted pair in natural order from result(0)
+   * (Tensor4_times_Tensor2_double.hpp:17-27); T2*T2 double contractions recurse with the FIRST index fastest
+   * (Tensor2_times_Tensor2.hpp:15-46) */
   cx s1 = {0, 0};
-  for (int a = 0; a < 4; ++a)
-    for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < 4; ++b)
+    for (int a = 0; a < 4; ++a) {
       cx X = {0, 0};
       for (int m = 0; m < 4; ++m)
-        for (int n = 0; n < 4; ++n) X = cx_add(X, cx_mul(A[m][n], D1[m][n][a][b]));
-      s1 = cx_add(s1, cx_mul(X, Ga[a][b]));
+        for (int n = 0; n < 4; ++n) X = cx_add(X, cx_mul(D1[m][n][a][b], A[m][n]));
+      s1 = (a == 0 && b == 0) ? cx_mul(X, Ga[a][b]) : cx_add(cx_mul(X, Ga[a][b]), s1);
     }
   cx r = {0, 0};
-  for (int k = 0; k < 4; ++k)
-    for (int l = 0; l < 4; ++l) {
+  for (int l = 0; l < 4; ++l)
+    for (int k = 0; k < 4; ++k) {
       cx Z = {0, 0};
       for (int c = 0; c < 4; ++c)
-        for (int e = 0; e < 4; ++e) Z = cx_add(Z, cx_mul(cx_mul(s1, Gb[c][e]), D2[c][e][k][l]));
-      r = cx_add(r, cx_mul(Z, B[k][l]));
+        for (int e = 0; e < 4; ++e) Z = cx_add(Z, cx_mul(D2[c][e][k][l], cx_mul(s1, Gb[c][e])));
+      r = (k == 0 && l == 0) ? cx_mul(Z, B[k][l]) : cx_add(cx_mul(Z, B[k][l]), r);
     }
   return r;
 }
@@ -789,6 +795,161 @@ static cx cx_div(cx x, cx y) {
 }
 static double v4_theta(v4 a) { return (a.x == 0.0 && a.y == 0.0 && a.z == 0.0) ? 0.0 : atan2(v4_pt(a), a.z); }
 static double v4_phi(v4 a) { return (a.x == 0.0 && a.y == 0.0) ? 0.0 : atan2(a.y, a.x); }
+/* ---- tensor pomeron continuum, 2 x vector meson (reference src/MTensorPomeron.cc:797-888) -------------------- */
+/* :2500-2536 Gamma0 / Gamma2 rank-4 tensor functions (covariant components, M4Vec::operator%) */
+static void tp_gamma0(v4 k1, v4 k2, double T[4][4][4][4]) {
+  const double k1k2 = v4_dot(k1, k2);
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
+      for (int k = 0; k < 4; ++k)
+        for (int l = 0; l < 4; ++l)
+          T[u][v][k][l] = (k1k2 * o_g[u][v] - v4_cov(k2, u) * v4_cov(k1, v)) *
+                          (v4_cov(k1, k) * v4_cov(k2, l) + v4_cov(k2, k) * v4_cov(k1, l) - 0.5 * k1k2 * o_g[k][l]);
+}
+static void tp_gamma2(v4 k1, v4 k2, double T[4][4][4][4]) {
+  const double k1k2 = v4_dot(k1, k2);
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
+      for (int k = 0; k < 4; ++k)
+        for (int l = 0; l < 4; ++l)
+          T[u][v][k][l] = k1k2 * (o_g[u][k] * o_g[v][l] + o_g[u][l] * o_g[v][k]) +
+                          o_g[u][v] * (v4_cov(k1, k) * v4_cov(k2, l) + v4_cov(k2, k) * v4_cov(k1, l)) -
+                          v4_cov(k1, v) * v4_cov(k2, l) * o_g[u][k] - v4_cov(k1, v) * v4_cov(k2, k) * o_g[u][l] -
+                          v4_cov(k2, u) * v4_cov(k1, l) * o_g[v][k] - v4_cov(k2, u) * v4_cov(k1, k) * o_g[v][l] -
+                          (k1k2 * o_g[u][v] - v4_cov(k2, u) * v4_cov(k1, v)) * o_g[k][l];
+}
+/* :2224-2238 iG_Pvv(prime, p, g1, g2) */
+static void tp_iG_Pvv(v4 prime, v4 p, double g1, double g2, cx T[4][4][4][4]) {
+  static double G0[4][4][4][4], G2[4][4][4][4];
+  const v4 mp = {-p.x, -p.y, -p.z, -p.e};
+  tp_gamma0(prime, mp, G0);
+  tp_gamma2(prime, mp, G2);
+  const double fm = 1.0 / (1.0 - v4_m2(v4_sub(prime, p)) / 0.5); /* FM(q2, 0.5), :2486 */
+  const cx FACTOR = {0.0 * fm, 1.0 * fm};
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v)
+      for (int k = 0; k < 4; ++k)
+        for (int l = 0; l < 4; ++l) T[u][v][k][l] = cx_mulr(FACTOR, 2.0 * g1 * G0[u][v][k][l] - g2 * G2[u][v][k][l]);
+}
+/* :2353-2368 iD_V: Reggeized vector propagator, T(u,v) = -g[u][v] / (m2 - M0^2) * (e^{i phi} s34 / s_thresh)^(alpha - 1) */
+static void tp_iD_V(v4 p, double M0, double s34, cx T[4][4]) {
+  const double m2 = v4_m2(p);
+  const double alpha = 0.5 + 0.9 * m2;
+  const double s_thresh = 4 * pow2(M0);
+  const double phi = O_PI / 2.0 * exp((s_thresh - s34) / s_thresh) - O_PI / 2.0;
+  const cx e = {exp(0.0 * phi) * cos(phi), exp(0.0 * phi) * sin(phi)}; /* std::exp(zi * phi) */
+  const cx z = {e.re * s34 / s_thresh, e.im * s34 / s_thresh};
+  const cx R = cx_powr(z, alpha - 1.0);
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v) T[u][v] = cx_mulr(R, -o_g[u][v] / (m2 - pow2(M0)));
+}
+/* src/MDirac.cc:393-470,661-679 massive spin-1 polarisation vectors, complex conjugated, contravariant [t,x,y,z] */
+static void o_eps_massive_conj(v4 k, int m, cx e[4]) {
+  const double theta = v4_theta(k), phi = v4_phi(k);
+  if (m != 0) {
+    const double N = 1.0 / sqrt(2.0), neg = -(double)m, pos = (double)m;
+    e[0] = (cx){0.0, 0.0};
+    e[1] = (cx){(neg * cos(theta) * cos(phi)) * N, -(sin(phi) * N)};
+    e[2] = (cx){(neg * cos(theta) * sin(phi)) * N, (cos(phi) * N)};
+    e[3] = (cx){pos * sin(theta) * N, -0.0};
+    return;
+  }
+  const double E = k.e, M = v4_m(k);
+  e[0] = (cx){v4_p3mod(k) / M, -0.0};
+  e[1] = (cx){E * sin(theta) * cos(phi) / M, -0.0};
+  e[2] = (cx){E * sin(theta) * sin(phi) / M, -0.0};
+  e[3] = (cx){E * cos(theta) / M, -0.0};
+}
+/* Upper/lower block: R(a,b) = G(mu,nu) D(mu,nu,al,be) V(a,b,al,be) */
+static void tp_block(cx G[4][4], cx D[4][4][4][4], cx V[4][4][4][4], cx R[4][4]) {
+  cx X[4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      cx x = {0, 0};
+      for (int m = 0; m < 4; ++m)
+        for (int n = 0; n < 4; ++n) x = cx_add(x, cx_mul(D[m][n][a][b], G[m][n]));
+      X[a][b] = x;
+    }
+  for (int r = 0; r < 4; ++r)
+    for (int q = 0; q < 4; ++q) {
+      cx x = {0, 0};
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) x = cx_add(x, cx_mul(X[a][b], V[r][q][a][b]));
+      R[r][q] = x;
+    }
+}
+static double tensor_me4_2xV(ost *S) {
+  const grb_process_desc *d = S->d;
+  const v4 pa = S->pbeam1, pb = S->pbeam2, p1 = S->pfinal[1], p2 = S->pfinal[2];
+  const v4 p3 = S->node_p4[0], p4 = S->node_p4[1];
+  const double M_ = d->nodes[0].mass;
+  const v4 pt = v4_sub(v4_sub(pa, p1), p3);
+  const v4 pu = v4_add(v4_sub(p4, pa), p1);
+  const v4 mp3 = {-p3.x, -p3.y, -p3.z, -p3.e};
+  double g1 = 0.0, g2 = 0.0;
+  if (d->nodes[0].pdg == 113) { g1 = d->tpom.gPrhorho[0]; g2 = d->tpom.gPrhorho[1]; }
+  else if (d->nodes[0].pdg == 333) { g1 = d->tpom.gPphiphi[0]; g2 = d->tpom.gPphiphi[1]; }
+  static cx D13[4][4][4][4], D24[4][4][4][4], D14[4][4][4][4], D23[4][4][4][4];
+  static cx GtA[4][4][4][4], GtB[4][4][4][4], GuA[4][4][4][4], GuB[4][4][4][4];
+  cx G1a[4][4], G2b[4][4];
+  tp_iDP(S, S->ss[1][3], S->t1, D13);
+  tp_iDP(S, S->ss[2][4], S->t2, D24);
+  tp_iDP(S, S->ss[1][4], S->t1, D14);
+  tp_iDP(S, S->ss[2][3], S->t2, D23);
+  tp_iG_PppHE(S, p1, pa, G1a);
+  tp_iG_PppHE(S, p2, pb, G2b);
+  tp_iG_Pvv(pt, mp3, g1, g2, GtA);
+  tp_iG_Pvv(p4, pt, g1, g2, GtB);
+  tp_iG_Pvv(p4, pu, g1, g2, GuA);
+  tp_iG_Pvv(pu, mp3, g1, g2, GuB);
+  const double s34 = v4_m2(S->pfinal[0]);
+  cx DVt[4][4], DVu[4][4];
+  tp_iD_V(pt, M_, s34, DVt);
+  tp_iD_V(pu, M_, s34, DVu);
+  const double fft = pow2(meson_ff(S, v4_m2(pt), pow2(M_))), ffu = pow2(meson_ff(S, v4_m2(pu), pow2(M_)));
+  cx A[4][4], B[4][4], Y[4][4], Mt[4][4], Mu[4][4], M[4][4];
+  /* single contractions recurse from the top index: t3 + (t2 + (t1 + t0)) (Tensor2_times_Tensor2.hpp:105-290) */
+#define SUM4(expr) ({ cx acc_; { const int q = 0; acc_ = (expr); } for (int q = 1; q < 4; ++q) acc_ = cx_add((expr), acc_); acc_; })
+  /* t-channel: M_t(r3,r4) = [A(r1,r3) iDV(r1,r2)] B(r4,r2) * FF^2 */
+  tp_block(G1a, D13, GtA, A);
+  tp_block(G2b, D24, GtB, B);
+  for (int r3 = 0; r3 < 4; ++r3)
+    for (int r2 = 0; r2 < 4; ++r2) Y[r3][r2] = SUM4(cx_mul(A[q][r3], DVt[q][r2]));
+  for (int r3 = 0; r3 < 4; ++r3)
+    for (int r4 = 0; r4 < 4; ++r4) Mt[r3][r4] = cx_mulr(SUM4(cx_mul(Y[r3][q], B[r4][q])), fft);
+  /* u-channel: M_u(r3,r4) = [A(r4,r1) iDV(r1,r2)] B(r2,r3) * FF^2 */
+  tp_block(G1a, D14, GuA, A);
+  tp_block(G2b, D23, GuB, B);
+  for (int r4 = 0; r4 < 4; ++r4)
+    for (int r2 = 0; r2 < 4; ++r2) Y[r4][r2] = SUM4(cx_mul(A[r4][q], DVu[q][r2]));
+  for (int r3 = 0; r3 < 4; ++r3)
+    for (int r4 = 0; r4 < 4; ++r4) Mu[r3][r4] = cx_mulr(SUM4(cx_mul(Y[r4][q], B[q][r3])), ffu);
+#undef SUM4
+  for (int u = 0; u < 4; ++u)
+    for (int v = 0; v < 4; ++v) M[u][v] = cx_mul((cx){-0.0, -1.0}, cx_add(Mt[u][v], Mu[u][v]));
+  /* MassiveSpin1PolSum (:1227-1247): [eps3*(r3) eps4*(r4)] M(r3,r4), double contraction with r3 fastest */
+  cx e3[3][4], e4[3][4], h[9];
+  for (int m = 0; m < 3; ++m) { o_eps_massive_conj(p3, m - 1, e3[m]); o_eps_massive_conj(p4, m - 1, e4[m]); }
+  for (int h3 = 0; h3 < 3; ++h3)
+    for (int h4 = 0; h4 < 3; ++h4) {
+      cx x = {0, 0};
+      for (int r4 = 0; r4 < 4; ++r4)
+        for (int r3 = 0; r3 < 4; ++r3) {
+          const cx t = cx_mul(cx_mul(e3[h3][r3], e4[h4][r4]), M[r3][r4]);
+          x = (r3 == 0 && r4 == 0) ? t : cx_add(t, x);
+        }
+      h[3 * h3 + h4] = x;
+    }
+  /* the four helicity-conserving proton combinations push the same nine amplitudes */
+  S->nhamp = 36;
+  double SumAmp2 = 0.0;
+  for (int k = 0; k < 36; ++k) {
+    S->hamp[k] = h[k % 9];
+    SumAmp2 += cx_abs2(S->hamp[k]);
+  }
+  return SumAmp2 / 4;
+}
+
 static double o_factorial(int n) {
   double x = 1;
   for (int i = 1; i <= n; ++i) x *= i;
@@ -1255,6 +1416,7 @@ static double bare_amp2(ost *S) {
     case GRB_PROC_PP_RES: return res_amp2(S, 0);
     case GRB_PROC_PP_RES_CON: return res_amp2(S, 1);
     case GRB_PROC_PP_CONTENSOR: {
+      if (S->d->nodes[0].spinX2 == 2 && S->d->nodes[1].spinX2 == 2) return tensor_me4_2xV(S);
       if (g_oracle_extended) {
         double re, im;
         const double a2 = tensor_me4_extended(S, &re, &im);

@@ -34,6 +34,12 @@ CASES = [
     ("c4_cms_ee_yycon_born", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> e+ e-", 0, 1024, 8, True),
     ("c5_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 2048, 24, True),
+    ("c5_cms_rhorho_4pi_tensor_born", "./tests/processes/CMSCUTS.json",
+     "PP[CONTENSOR]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 2048, 24, True),
+    ("c5_cms_phiphi_4k_tensor_born", "./tests/processes/CMSCUTS.json",
+     "PP[CONTENSOR]<F> -> phi(1020)0 > {K+ K-} phi(1020)0 > {K+ K-}", 0, 1024, 24, True),
+    ("c5_cms_rhorho_stable_tensor_born", "./tests/processes/CMSCUTS.json",
+     "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 0, 1024, 8, True),
 ]
 
 

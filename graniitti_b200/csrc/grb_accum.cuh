@@ -6,7 +6,9 @@
 namespace grb {
 
 enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY, IT_P3 = 9, IT_P4 = 13,
-       IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_AMP2, IT_NF };
+       IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_AMP2,
+       // Born-level kinematics for the multi-helicity loop: p1z, p1e, p2z, p2e, pX(x,y,z,e)
+       IT_BK = 22, IT_NF = 30 };
 
 
 // ---- block-level VEGAS accumulation ---------------------------------------------------------------------

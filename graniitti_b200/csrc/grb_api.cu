@@ -60,7 +60,7 @@ struct grb_engine {
 static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
 static thread_local std::string g_last_global_error;
 
-#define ITEM_NF 22
+#define ITEM_NF 30  /* = IT_NF of grb_accum.cuh */
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -96,7 +96,6 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
       return GRB_ERR_UNSUPPORTED;
     }
     if (d.qed_alpha != 0) { err = "yy[CON]: PARAM_STRUCTURE.QED_alpha must be ZERO on the device path"; return GRB_ERR_UNSUPPORTED; }
-    if (d.screening) { err = "yy[CON] with POMLOOP (16 helicity amplitudes in the loop) is not on the device path yet"; return GRB_ERR_UNSUPPORTED; }
   }
   if (d.proc == GRB_PROC_PP_CONTENSOR) {
     const bool s2 = d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0;
@@ -104,10 +103,6 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
                     (d.nodes[0].pdg == 113 || d.nodes[0].pdg == 333);
     if (!s2 && !v2) {
       err = "PP[CONTENSOR]: pseudoscalar pairs (2xS) and rho0 rho0 / phi phi (2xV) have a device amplitude; 2xF not yet";
-      return GRB_ERR_UNSUPPORTED;
-    }
-    if (v2 && d.screening) {
-      err = "PP[CONTENSOR] 2xV with POMLOOP (nine helicity amplitudes in the loop) is not on the device path yet";
       return GRB_ERR_UNSUPPORTED;
     }
   }

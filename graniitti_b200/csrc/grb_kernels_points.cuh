@@ -161,6 +161,10 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
             it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
             it[IT_H0RE * c] = h0.re; it[IT_H0IM * c] = h0.im;
             it[IT_PREF * c] = pref; it[IT_VW * c] = vw;
+            if (AmpHel<AMP>::NH > 1) {
+              it[(IT_BK + 0) * c] = S.p1.z; it[(IT_BK + 1) * c] = S.p1.e; it[(IT_BK + 2) * c] = S.p2.z; it[(IT_BK + 3) * c] = S.p2.e;
+              it[(IT_BK + 4) * c] = S.pX.x; it[(IT_BK + 5) * c] = S.pX.y; it[(IT_BK + 6) * c] = S.pX.z; it[(IT_BK + 7) * c] = S.pX.e;
+            }
             a.item_idx[slot]  = (int32_t)idx;
             a.item_bins[slot] = packed;
             if (VEGAS && a.mode == GRB_MODE_GENERATE) store_momenta<NN>(a.pay + slot, c, S, P.n_nodes);

@@ -29,9 +29,28 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   L.same_mass = SAME;
   L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
   L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
-  cx h0;
-  h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
-  it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
+  if (AmpHel<AMP>::NH > 1) {
+    // Born-level kinematics -> the same scalars lorentz_scalars() formed in k_points (same expressions, same bits)
+    NodeKin B;
+    B.p1.x = L.p1x; B.p1.y = L.p1y; B.p1.z = it[(IT_BK + 0) * c]; B.p1.e = it[(IT_BK + 1) * c];
+    B.p2.x = L.p2x; B.p2.y = L.p2y; B.p2.z = it[(IT_BK + 2) * c]; B.p2.e = it[(IT_BK + 3) * c];
+    B.pX.x = it[(IT_BK + 4) * c]; B.pX.y = it[(IT_BK + 5) * c]; B.pX.z = it[(IT_BK + 6) * c]; B.pX.e = it[(IT_BK + 7) * c];
+    const v4 &p3 = L.p3, &p4 = L.p4;
+    B.ss13 = m2_of(B.p1.x + p3.x, B.p1.y + p3.y, B.p1.z + p3.z, B.p1.e + p3.e);
+    B.ss14 = m2_of(B.p1.x + p4.x, B.p1.y + p4.y, B.p1.z + p4.z, B.p1.e + p4.e);
+    B.ss23 = m2_of(B.p2.x + p3.x, B.p2.y + p3.y, B.p2.z + p3.z, B.p2.e + p3.e);
+    B.ss24 = m2_of(B.p2.x + p4.x, B.p2.y + p4.y, B.p2.z + p4.z, B.p2.e + p4.e);
+    const double q1x = 0.0 - B.p1.x, q1y = 0.0 - B.p1.y, q1z = P.pb1z - B.p1.z, q1e = P.pb1e - B.p1.e;
+    B.t1 = m2_of(q1x, q1y, q1z, q1e);
+    B.t2 = m2_of(0.0 - B.p2.x, 0.0 - B.p2.y, P.pb2z - B.p2.z, P.pb2e - B.p2.e);
+    B.t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+    B.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+    it[IT_AMP2 * c] = screened_amp2_multi<AMP, SAME>(L, B);
+  } else {
+    cx h0;
+    h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
+    it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
+  }
 }
 
 template <int MINB, int AMP>
@@ -106,6 +125,14 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
   }
   if (amp_kind == AMP_REGGE_RES) {
     launch_screen_t<2, AMP_REGGE_RES>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_TENSOR_2XV) {
+    launch_screen_t<2, AMP_TENSOR_2XV>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_YY_LL) {
+    launch_screen_t<2, AMP_YY_LL>(a, sm_count, st);
     return 2;
   }
   if (amp_kind == AMP_REGGE_RES_CON) {

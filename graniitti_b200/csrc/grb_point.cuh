@@ -643,6 +643,21 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
   return regge_me4(in);
 }
 
+// Processes whose helicity amplitudes differ (reference lts.hamp.size() > 1 after dropping identical copies): the
+// screening loop integrates every amplitude separately (MProcess.cc:262-283).  NH = distinct amplitudes,
+// amp2 = SCALE * sum_h |A_h|^2:  yy -> l+ l-: 16 amplitudes, /4;  tensor 2xV: 36 = 4 x 9 amplitudes, /4 -> 9, x1.
+template <int AMP> struct AmpHel { static constexpr int NH = 1; };
+template <> struct AmpHel<AMP_YY_LL> { static constexpr int NH = 16; };
+template <> struct AmpHel<AMP_TENSOR_2XV> { static constexpr int NH = 9; };
+template <int AMP>
+__device__ __forceinline__ double amp_hel_scale() { return AMP == AMP_YY_LL ? 0.25 : 1.0; }
+template <int AMP>
+__device__ __forceinline__ void amplitude_vec(const NodeKin &in, const v4 &p3, const v4 &p4, cx *h) {
+  if (AMP == AMP_YY_LL) yy_ll_core<true>(in, p3, p4, h);
+  else if (AMP == AMP_TENSOR_2XV) tensor_me4_2xV(in, p3, p4, h);
+  else h[0] = amplitude<AMP>(in, p3, p4);
+}
+
 // ---- screening loop: per-point invariants and per-node work -------------------------------------------------
 // reference src/MFactorized.cc:84-139 LoopKinematics: the loop re-derives m1, m2, mX, yX from the saved
 // 4-vectors (pfinal_orig) -- done once per point here -- shifts the proton pT by -/+ kt, rebuilds pX and
@@ -737,6 +752,46 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
   const double lr = -Q.norm * Iim, li = Q.norm * Ire;
   const double ar = h0.re + lr, ai = h0.im + li;
   return ar * ar + ai * ai;
+}
+
+// The same loop for NH > 1 amplitudes.  The Born amplitudes are re-evaluated from the Born-level kinematics carried
+// in the work list (same device function, same inputs as k_points: identical bits), so the list does not grow with NH.
+template <int AMP, bool SAME>
+__device__ __forceinline__ double screened_amp2_multi(const LoopInv &L, const NodeKin &born) {
+  constexpr int  NH = AmpHel<AMP>::NH;
+  const DevLoop &Q  = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  double Ire[NH], Iim[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) { Ire[h] = 0.0; Iim[h] = 0.0; }
+#pragma unroll 1
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+#pragma unroll 1
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      NodeKin      in;
+      if (!loop_node<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
+      cx A[NH];
+      amplitude_vec<AMP>(in, L.p3, L.p4, A);
+      const double br = wi * Q.b_re[j], bi = wi * Q.b_im[j];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        Ire[h] = fma(br, A[h].re, fma(-bi, A[h].im, Ire[h]));
+        Iim[h] = fma(br, A[h].im, fma(bi, A[h].re, Iim[h]));
+      }
+    }
+  }
+  cx h0[NH];
+  amplitude_vec<AMP>(born, L.p3, L.p4, h0);
+  double amp2 = 0.0;
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+    const double ar = h0[h].re - Q.norm * Iim[h], ai = h0[h].im + Q.norm * Ire[h];  // A_0 + i norm I
+    amp2 += ar * ar + ai * ai;
+  }
+  return amp_hel_scale<AMP>() * amp2;
 }
 
 }  // namespace grb

@@ -165,8 +165,11 @@ __device__ __forceinline__ void offshell2lightcone(v4 &q1, v4 &q2, v4 &pa, v4 &p
   }
 }
 
-// |M|^2 (spin averaged) x kt-EPA fluxes for yy[CON] -> l+ l-  (reference PROC_3, MSubProc.h:165-173)
-__device__ __forceinline__ double yy_ll_amp2(const NodeKin &in, const v4 &p3, const v4 &p4) {
+// |M|^2 (spin averaged) x kt-EPA fluxes for yy[CON] -> l+ l-  (reference PROC_3, MSubProc.h:165-173).
+// VEC: also return the 16 helicity amplitudes as the reference leaves them in lts.hamp (MG5 amplitude x GC_3^2 x
+// sqrt(flux_1/x_1) sqrt(flux_2/x_2), src/MFlux.cc:22-44) for the screening loop, where sum |.|^2 / 4 is taken last.
+template <bool VEC>
+__device__ __forceinline__ double yy_ll_core(const NodeKin &in, const v4 &p3, const v4 &p4, cx *hv) {
   const DevProc &P = c_proc;
   v4 q1, q2, pa = p3, pb = p4;
   q1.x = 0.0 - in.p1.x; q1.y = 0.0 - in.p1.y; q1.z = P.pb1z - in.p1.z; q1.e = P.pb1e - in.p1.e;
@@ -204,6 +207,7 @@ __device__ __forceinline__ double yy_ll_amp2(const NodeKin &in, const v4 &p3, co
         for (int h1 = 0; h1 < 2; ++h1) {
           const cx a = cadd(ffv1_0(w4, w3[h3], v1[h1]), ffv1_0(w2[h2], w5, v1[h1]));
           sum += a.re * a.re + a.im * a.im;
+          if (VEC) hv[((h0 * 2 + h2) * 2 + h3) * 2 + h1] = a;
         }
       }
     }
@@ -211,7 +215,15 @@ __device__ __forceinline__ double yy_ll_amp2(const NodeKin &in, const v4 &p3, co
   // GC_3 = -i ee, ee = 2 sqrt(pi/137.03599908) (Parameters_sm.cc:93-101)
   const double amp2 = sum * P.yy_ee4 / 4.0;
   const double f1 = coh_flux_amp(x1, in.t1, qt1), f2 = coh_flux_amp(x2, in.t2, qt2);  // sqrt(flux_i / x_i)
+  if (VEC) {
+    const double sc = sqrt(P.yy_ee4) * (f1 * f2);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { hv[k].re *= sc; hv[k].im *= sc; }
+  }
   return (f1 * f1) * (f2 * f2) * amp2;
+}
+__device__ __forceinline__ double yy_ll_amp2(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  return yy_ll_core<false>(in, p3, p4, nullptr);
 }
 
 }  // namespace grb

@@ -40,6 +40,10 @@ CASES = [
      "PP[CONTENSOR]<F> -> phi(1020)0 > {K+ K-} phi(1020)0 > {K+ K-}", 0, 1024, 24, True),
     ("c5_cms_rhorho_stable_tensor_born", "./tests/processes/CMSCUTS.json",
      "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 0, 1024, 8, True),
+    # multi-helicity screening loops (16 and 36 amplitudes integrated separately)
+    ("c4_cms_mumu_yycon_screened", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 1, 256, 8, True),
+    ("c5_cms_rhorho_stable_tensor_screened", "./tests/processes/CMSCUTS.json",
+     "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 1, 160, 8, True),
 ]
 
 

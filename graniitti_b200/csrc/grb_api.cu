@@ -714,6 +714,12 @@ int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_o
   return grb_set_eikonal(e, T.kt2.data(), T.sa_re.data(), T.sa_im.data(), (int)T.kt2.size());
 }
 
+int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y) {
+  if (!x || !y || n <= 0 || (kind != 0 && kind != 1)) return GRB_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return GRB_ERR_CUDA;
+  return run_fastmath(kind, n, x, y) == cudaSuccess ? GRB_OK : GRB_ERR_CUDA;
+}
+
 int grb_comm_unique_id(char id_out[128]) {
   if (!id_out) return GRB_ERR_ARG;
   NcclApi &n = nccl();

@@ -5,12 +5,16 @@
 #include <cstdlib>
 
 #include "grb_point.cuh"
+#include "grb_fastmath.cuh"
 
 namespace grb {
 
 __constant__ DevProc c_proc;
 __constant__ DevLoop c_loop;
 __constant__ DevRes  c_res;
+// lookup tables of grb_fastmath.cuh (global memory, read through the L1 / read-only path: indices diverge in a warp)
+__device__ const double2 g_logtab[128] = {GRB_LOGTAB_ROWS};
+__device__ const double  g_exptab[64]  = {GRB_EXPTAB_ROWS};
 
 cudaError_t upload_proc(const DevProc &p, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_proc, &p, sizeof(DevProc), 0, cudaMemcpyHostToDevice, st);
@@ -79,6 +83,24 @@ cudaError_t run_dfma_peak(int sm_count, double *tflops) {
   cudaEventDestroy(t1);
   cudaFree(d);
   *tflops = best;
+  return e;
+}
+
+// ---- unit-test hook for grb_fastmath.cuh (grb_test_fastmath) ----------------------------------------------------
+__global__ void k_fastmath(int kind, int64_t n, const double *__restrict__ x, double *__restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = kind == 0 ? fast_log(x[i]) : fast_exp(x[i]);
+}
+cudaError_t run_fastmath(int kind, int64_t n, const double *x_host, double *y_host) {
+  double *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(double) * 2 * (size_t)n);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_fastmath<<<592, 256>>>(kind, n, d, d + n);
+    e = cudaMemcpy(y_host, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
   return e;
 }
 

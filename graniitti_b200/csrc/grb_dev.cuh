@@ -140,6 +140,7 @@ cudaError_t upload_res(const DevRes &r, cudaStream_t st);
 int         launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st);
 int         launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st);
 cudaError_t run_dfma_peak(int sm_count, double *tflops);
+cudaError_t run_fastmath(int kind, int64_t n, const double *x_host, double *y_host);
 
 // ---- small math ----------------------------------------------------------------------------------------
 __device__ __forceinline__ double msqrt(double x) { return sqrt(fmax(0.0, x)); }  // MMath.h:250

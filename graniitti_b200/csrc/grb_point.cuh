@@ -3,6 +3,7 @@
 // See grb_dev.cuh for the arithmetic conventions (-fmad=false, explicit fma()).
 #pragma once
 #include "grb_dev.cuh"
+#include "grb_fastmath.cuh"
 
 namespace grb {
 
@@ -368,23 +369,37 @@ __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
   // S3F(t1) S3F(t2) = 1 / [(1-t1/fc1)(1-t1/fc2)(1-t2/fc1)(1-t2/fc2)], MForm.cc:433
   const double dF = (fma(-in.t1, P.inv_fc1, 1.0) * fma(-in.t1, P.inv_fc2, 1.0)) *
                     (fma(-in.t2, P.inv_fc1, 1.0) * fma(-in.t2, P.inv_fc2, 1.0));
-  double nt, dt, nu, du;
-  meson_G_nd(in.t_hat, nt, dt);
-  meson_G_nd(in.u_hat, nu, du);
-  nu *= P.me4_sign;
-  cx A;
+  double dt = in.t_hat - P.M2_leg0, du = in.u_hat - P.M2_leg0;  // meson propagator denominators, MRegge.cc:1199-1218
+  cx     A;
   if (P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2]) {
-    // single trajectory: one sincos, two exp, four log
+    // single trajectory: one sincos, two exp, four log (table-driven, grb_fastmath.cuh).  The off-shell meson form
+    // factor ff(x)^2 = exp(gx) of the exponential / Orear parametrisations rides in the same exponent.
     const double a1 = fma(P.ap[0], in.t1, P.a0[0]), a2 = fma(P.ap[0], in.t2, P.a0[0]);
-    const double Et = exp(fma(a1, log(in.ss13) + P.ln_inv_s0, a2 * (log(in.ss24) + P.ln_inv_s0)));
-    const double Eu = exp(fma(a1, log(in.ss14) + P.ln_inv_s0, a2 * (log(in.ss23) + P.ln_inv_s0)));
-    // g2 (Et nt/dt + Eu nu/du) / dF
-    const double R = P.g2_const * fma(Et * nt, du, Eu * nu * dt) / (dt * du * dF);
+    double       gt = 0.0, gu = 0.0;
+    if (P.offshellFF == 0) {
+      gt = -2.0 * P.b_EXP * fabs(dt);
+      gu = -2.0 * P.b_EXP * fabs(du);
+    } else if (P.offshellFF == 1) {
+      gt = 2.0 * fma(-P.b_OREAR, msqrt(fabs(dt) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+      gu = 2.0 * fma(-P.b_OREAR, msqrt(fabs(du) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+    } else {
+      const double d1 = fma(-dt, P.inv_b_POW, 1.0), d2 = fma(-du, P.inv_b_POW, 1.0);
+      dt *= d1 * d1;
+      du *= d2 * d2;
+    }
+    const double Et = fast_exp(fma(a1, fast_log(in.ss13) + P.ln_inv_s0, fma(a2, fast_log(in.ss24) + P.ln_inv_s0, gt)));
+    const double Eu = fast_exp(fma(a1, fast_log(in.ss14) + P.ln_inv_s0, fma(a2, fast_log(in.ss23) + P.ln_inv_s0, gu)));
+    // g2 (Et / dt + sign Eu / du) / dF
+    const double R = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt) / (dt * du * dF);
     double       sn, cs;
     sincos(P.phase_c[0] * (in.t1 + in.t2), &sn, &cs);
     A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
     A.im = fma(P.eta0sq_re, sn, P.eta0sq_im * cs) * R;
   } else {
+    double nt, nu;
+    meson_G_nd(in.t_hat, nt, dt);
+    meson_G_nd(in.u_hat, nu, du);
+    nu *= P.me4_sign;
     const cx P13 = regge_prop(in.ss13, in.t1), P24 = regge_prop(in.ss24, in.t2);
     const cx P14 = regge_prop(in.ss14, in.t1), P23 = regge_prop(in.ss23, in.t2);
     const double tr = P13.re * P24.re - P13.im * P24.im, ti = P13.re * P24.im + P13.im * P24.re;

@@ -81,6 +81,8 @@ def lib():
                                     C.POINTER(_abi.VegasResult)]
         L.grb_local_calls.restype = cint
         L.grb_local_calls.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
+        L.grb_test_fastmath.restype = cint
+        L.grb_test_fastmath.argtypes = [cint, cint, i64, vp, vp]
         L.grb_get_stream.restype = vp
         L.grb_get_stream.argtypes = [vp]
         L.grb_last_timing_kernels.restype = cint
@@ -135,6 +137,16 @@ def read_eikonal_file(path, n_points=10001):
     if rc != 0:
         raise GrbError(rc, f"grb_read_eikonal_file({path})")
     return t
+
+
+def test_fastmath(kind, x, device=0):
+    """Device table-driven log (kind 0) / exp (kind 1) of grb_fastmath.cuh on a host array (unit-test hook)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    rc = lib().grb_test_fastmath(device, kind, x.size, x.ctypes.data, y.ctypes.data)
+    if rc != 0:
+        raise GrbError(rc, "grb_test_fastmath")
+    return y
 
 
 def optimize_grid(xmat, f2mat, lam=1.5):

@@ -365,6 +365,10 @@ int grb_allreduce(grb_engine *e);
  * roofline denominator for the path (MEASURED_PEAKS.json has no fp64 figure).                            */
 int grb_measure_dfma_peak(int device, double *tflops_out);
 
+/* Unit-test hook: evaluates the device's table-driven fp64 log (kind 0) or exp (kind 1) used by the amplitude algebra
+ * (graniitti_b200/csrc/grb_fastmath.cuh) on n host values.                                               */
+int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y);
+
 /* Device time in ms of the kernels launched by the last grb_eval / grb_vegas_iterate call (CUDA events on
  * the engine's stream), and how many kernels that call launched.                                         */
 int grb_last_timing(const grb_engine *e, double *kernel_ms, int *n_launches);

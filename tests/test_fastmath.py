@@ -1,0 +1,49 @@
+"""Device table-driven log / exp (graniitti_b200/csrc/grb_fastmath.cuh) against glibc through the C-ABI unit-test hook.
+Budget: the amplitude needs ~1e-15 absolute accuracy on ln(s_ij / s0) (it is multiplied by
+alpha(t) ~ 1) and ~1e-15 relative accuracy on the exponential; both are asserted with margins below that."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fast_log_accuracy(grb):
+    rng = np.random.default_rng(3)
+    x = np.concatenate([10.0 ** rng.uniform(-3, 12, 400000), rng.uniform(0.5, 2.0, 100000),
+                        1.0 + (np.arange(129 * 8) / (128.0 * 8)),            # table interval edges and interiors
+                        np.nextafter(1.0 + np.arange(1, 128) / 128.0, 0)])
+    y = grb.test_fastmath(0, x)
+    ref = np.log(x.astype(np.longdouble))
+    err = np.abs((y - ref).astype(np.float64))
+    bound = 1.2e-16 * (3.0 + np.abs(np.log2(x)))
+    assert np.all(err <= bound), (err / bound).max()
+    big = x > 4.0          # the sub-energies s_ij / s0 of the amplitudes
+    assert np.max(err[big] / np.abs(np.log(x[big]))) < 2.5e-16
+
+
+def test_fast_exp_accuracy(grb):
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(-60, 60, 400000), rng.uniform(-689, 689, 100000), np.linspace(-1e-3, 1e-3, 1001),
+                        np.arange(-640, 641) * (np.log(2.0) / 64)])
+    y = grb.test_fastmath(1, x)
+    ref = np.exp(x.astype(np.longdouble))
+    rel = np.abs(((y - ref) / ref).astype(np.float64))
+    assert rel.max() < 3.4e-16, rel.max()        # <= 1.5 ulp
+
+
+def test_fast_math_out_of_domain_takes_libm_path(grb):
+    x = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310, 2.2250738585072014e-308, 1.7976931348623157e308])
+    y = grb.test_fastmath(0, x)
+    with np.errstate(all="ignore"):
+        ref = np.log(x)
+    assert np.array_equal(np.isnan(y), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.allclose(y[ok], ref[ok], rtol=3e-16, atol=0) or np.array_equal(y[ok], ref[ok])
+    x = np.array([-800.0, -745.2, -690.0, 690.0, 709.7, 710.0, np.inf, -np.inf, np.nan])
+    y = grb.test_fastmath(1, x)
+    with np.errstate(all="ignore"):
+        ref = np.exp(x)
+    assert np.array_equal(np.isnan(y), np.isnan(ref))
+    ok = ~np.isnan(ref) & np.isfinite(ref) & (ref > 1e-300)
+    assert np.allclose(y[ok], ref[ok], rtol=4e-16, atol=0)
+    assert y[0] == 0.0 and np.isinf(y[5]) and np.isinf(y[6]) and y[7] == 0.0

@@ -89,7 +89,14 @@ cudaError_t run_dfma_peak(int sm_count, double *tflops) {
 // ---- unit-test hook for grb_fastmath.cuh (grb_test_fastmath) ----------------------------------------------------
 __global__ void k_fastmath(int kind, int64_t n, const double *__restrict__ x, double *__restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = kind == 0 ? fast_log(x[i]) : fast_exp(x[i]);
+    switch (kind) {
+      case 0: y[i] = fast_log(x[i]); break;
+      case 1: y[i] = fast_exp(x[i]); break;
+      case 2: y[i] = sqrt_fast_ok(x[i]) ? sqrt_fast_core(x[i]) : sqrt(x[i]); break;   // must equal sqrt(x) bit for bit
+      case 3: y[i] = sqrt(x[i]); break;
+      case 4: y[i] = div_checked(x[i], x[(i + 1) % n]); break;                         // must equal x[i] / x[i+1]
+      default: y[i] = x[i] / x[(i + 1) % n]; break;
+    }
 }
 cudaError_t run_fastmath(int kind, int64_t n, const double *x_host, double *y_host) {
   double *d = nullptr;

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "../../include/grb.h"
+#include "grb_fastmath.cuh"
 
 namespace grb {
 
@@ -188,10 +189,10 @@ __device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4,
                      E5 * t9 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 - s * t5 * 2.0 - s * t6 * 4.0 -
                      t2 * t3 * 2.0 - t2 * t4 * 2.0 - t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 4.0 -
                      E5 * t2 * t7 * 4.0;
-  const double t23 = sqrt(t22);
+  const double t23 = sqrt_fast_ok(t22) ? sqrt_fast_core(t22) : sqrt(t22);
   return pz5 * (-1.0 / 2.0) -
-         (E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0))) /
-             (s + t2 - t5 - E5 * t7 * 2.0);
+         div_checked(E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0)),
+                     s + t2 - t5 - E5 * t7 * 2.0);
 }
 
 // reference MKinematics.h:117-160 SolvePz3_B (unequal forward masses)
@@ -230,11 +231,11 @@ __device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, 
                      s * t5 * 2.0 - s * t6 * 2.0 - s * t7 * 2.0 - t2 * t3 * 2.0 - t2 * t4 * 2.0 -
                      t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 2.0 - t2 * t7 * 2.0 - t3 * t6 * 2.0 -
                      t4 * t5 * 2.0 - t5 * t6 * 2.0 - E5 * t2 * t8 * 4.0;
-  const double t30 = sqrt(t29);
+  const double t30 = sqrt_fast_ok(t29) ? sqrt_fast_core(t29) : sqrt(t29);
   return pz5 * (-1.0 / 2.0) -
-         (E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
-          pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0))) /
-             (s + t2 - t7 - E5 * t8 * 2.0);
+         div_checked(E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
+                         pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0)),
+                     s + t2 - t7 - E5 * t8 * 2.0);
 }
 
 __device__ __forceinline__ double solve_pz(double m3, double m4, double pt3, double pt4, double pz5,

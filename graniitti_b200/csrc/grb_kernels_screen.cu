@@ -110,7 +110,14 @@ __global__ void __launch_bounds__(256) k_finish(const PointArgs a) {
 
 template <int MINB, int AMP>
 static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
-  k_screen<MINB, AMP><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
+  // GRB_SCREEN_OCC=n (profiling knob): pad dynamic shared memory so that only n CTAs fit an SM, same code
+  static const int occ = [] { const char *e = getenv("GRB_SCREEN_OCC"); return e ? atoi(e) : 0; }();
+  if (occ > 0 && occ < MINB) {
+    const int pad = (227 * 1024) / (occ + 1) + 2048;
+    cudaFuncSetAttribute(k_screen<MINB, AMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    k_screen<MINB, AMP><<<sm_count * occ, 128, pad, st>>>(a);
+  } else
+    k_screen<MINB, AMP><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
   const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
   if (a.vegas) k_finish<true><<<sm_count * 4, 256, smem, st>>>(a);
   else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);

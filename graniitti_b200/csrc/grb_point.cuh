@@ -387,10 +387,11 @@ __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
       dt *= d1 * d1;
       du *= d2 * d2;
     }
-    const double Et = fast_exp(fma(a1, fast_log(in.ss13) + P.ln_inv_s0, fma(a2, fast_log(in.ss24) + P.ln_inv_s0, gt)));
-    const double Eu = fast_exp(fma(a1, fast_log(in.ss14) + P.ln_inv_s0, fma(a2, fast_log(in.ss23) + P.ln_inv_s0, gu)));
+    double L13, L24, L14, L23, Et, Eu;
+    fast_log4(in.ss13, in.ss24, in.ss14, in.ss23, L13, L24, L14, L23);
+    fast_exp2(fma(a1, L13 + P.ln_inv_s0, fma(a2, L24 + P.ln_inv_s0, gt)), fma(a1, L14 + P.ln_inv_s0, fma(a2, L23 + P.ln_inv_s0, gu)), Et, Eu);
     // g2 (Et / dt + sign Eu / du) / dF
-    const double R = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt) / (dt * du * dF);
+    const double R = div_checked(P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), dt * du * dF);
     double       sn, cs;
     sincos(P.phase_c[0] * (in.t1 + in.t2), &sn, &cs);
     A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
@@ -707,9 +708,10 @@ template <bool SAME>
 __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, double ktx, double kty, NodeKin &o) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
-  const double pt1 = msqrt(n1x * n1x + n1y * n1y), pt2 = msqrt(n2x * n2x + n2y * n2y);
   const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
-  const double mtX = msqrt(L.mXsq + (Xx * Xx + Xy * Xy));
+  // the three independent square roots share one range test (grb_fastmath.cuh sqrt3: same roundings as sqrt())
+  double pt1, pt2, mtX;
+  sqrt3(fmax(0.0, n1x * n1x + n1y * n1y), fmax(0.0, n2x * n2x + n2y * n2y), fmax(0.0, L.mXsq + (Xx * Xx + Xy * Xy)), pt1, pt2, mtX);
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   if (Xe > L.emax) return false;
   // SolvePz picks its branch on |m1 - m2| < 1e-9 (MKinematics.h:220-229); m1, m2 are re-derived from the saved
@@ -718,8 +720,8 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   const double p1z = SAME ? solve_pz3_A(L.m1, pt1, pt2, Xz, Xe, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
   const double p2z = -(Xz + p1z);
   if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
-  const double e1 = msqrt(L.m1sq + pow2(pt1) + pow2(p1z));
-  const double e2 = msqrt(L.m2sq + pow2(pt2) + pow2(p2z));
+  double e1, e2;
+  sqrt2(fmax(0.0, L.m1sq + pow2(pt1) + pow2(p1z)), fmax(0.0, L.m2sq + pow2(pt2) + pow2(p2z)), e1, e2);
   if (P.bsum_e - ((e1 + e2) + Xe) > 1e-6) return false;  // CheckEMC energy component (not abs, MMath.h:191-198)
   const v4 &p3 = L.p3, &p4 = L.p4;
   o.ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);

@@ -76,6 +76,11 @@ static double m_of_beam(double pz, double E) {  // M4Vec::M() of (0,0,pz,E), ref
   return (m2 > 0.0) ? std::sqrt(std::max(0.0, m2)) : -std::sqrt(std::max(0.0, -m2));
 }
 
+// one active Regge trajectory (TUNE0): the screening kernel's one-basic-block node applies (grb_point.cuh)
+static int regge_fast_ff(const DevProc &P) {
+  return (P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
+}
+
 // desc -> DevProc. Host libm (glibc, the reference's) evaluates the loop invariants.
 static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   memset(&P, 0, sizeof(P));
@@ -85,7 +90,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR &&
-      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON && d.proc != GRB_PROC_YY_CON) {
+      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON && d.proc != GRB_PROC_YY_CON && d.proc != GRB_PROC_YY_QED) {
     err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
     return GRB_ERR_UNSUPPORTED;
   }
@@ -97,12 +102,20 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     }
     if (d.qed_alpha != 0) { err = "yy[CON]: PARAM_STRUCTURE.QED_alpha must be ZERO on the device path"; return GRB_ERR_UNSUPPORTED; }
   }
+  if (d.proc == GRB_PROC_YY_QED) {
+    const int a = std::abs(d.nodes[0].pdg);
+    if (!(a == 11 || a == 13 || a == 15) || d.nodes[1].pdg != -d.nodes[0].pdg || d.n_nodes != 2) {
+      err = "yy[QED]: charged lepton pairs have a device amplitude (quark pairs need fragmentation downstream)";
+      return GRB_ERR_UNSUPPORTED;
+    }
+  }
   if (d.proc == GRB_PROC_PP_CONTENSOR) {
     const bool s2 = d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0;
+    const bool f2 = d.nodes[0].spinX2 == 1 && d.nodes[1].spinX2 == 1 && d.n_nodes == 2;
     const bool v2 = d.nodes[0].spinX2 == 2 && d.nodes[1].spinX2 == 2 && d.nodes[0].pdg == d.nodes[1].pdg &&
                     (d.nodes[0].pdg == 113 || d.nodes[0].pdg == 333);
-    if (!s2 && !v2) {
-      err = "PP[CONTENSOR]: pseudoscalar pairs (2xS) and rho0 rho0 / phi phi (2xV) have a device amplitude; 2xF not yet";
+    if (!s2 && !v2 && !f2) {
+      err = "PP[CONTENSOR]: pseudoscalar (2xS), rho0 rho0 / phi phi (2xV) and stable baryon (2xF) pairs have a device amplitude";
       return GRB_ERR_UNSUPPORTED;
     }
   }
@@ -177,6 +190,20 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
       const double *gv = d.nodes[0].pdg == 113 ? d.tpom.gPrhorho : d.tpom.gPphiphi;
       P.tp_g1 = gv[0]; P.tp_g2 = gv[1];
       P.tp_vv_coupling = 9.0 * d.tpom.gPNN * d.tpom.gPNN;
+    }
+    if (d.proc == GRB_PROC_PP_CONTENSOR && d.nodes[0].spinX2 == 1) P.amp_kind = 6;  // 2xF (MTensorPomeron.cc:765-804)
+    if (d.proc == GRB_PROC_YY_QED) P.amp_kind = 7;                                    // QED branch (:664-713)
+    P.tp_ff_coupling = 81.0 * std::pow(d.tpom.gPNN, 4);
+    P.mass_leg0 = d.nodes[0].mass;
+    P.qed_e = std::sqrt(std::max(0.0, 0.0072973525693 * 4.0 * GRB_PI));  // qed::alpha_QED() = alpha_0, MQED.h:19-24,57
+    P.inv_2mp = 1.0 / (2 * 0.938272081);
+    for (int b = 0; b < 2; ++b) {  // MDirac::uHelDirac(pbeam, -1/+1), src/MDirac.cc:224-246 (px = py = 0: phi = 0)
+      const double pz = b == 0 ? d.pbeam1_pz : d.pbeam2_pz, E = b == 0 ? d.pbeam1_E : d.pbeam2_E;
+      const double m = m_of_beam(pz, E), p3 = std::sqrt(std::max(0.0, pz * pz)), N = std::sqrt(std::max(0.0, E + m));
+      const double th2 = ((pz == 0.0) ? 0.0 : std::atan2(0.0, pz)) / 2.0, c = std::cos(th2), s = std::sin(th2);
+      const double r = N * p3 / (E + m);
+      const double um[4] = {-N * s, N * c, r * s, -r * c}, up[4] = {N * c, N * s, r * c, r * s};
+      for (int k = 0; k < 4; ++k) { P.bsp[b][0][k] = um[k]; P.bsp[b][1][k] = up[k]; }
     }
     P.omega = d.regge.omega;
     const double ee = 2. * std::sqrt(1.0 / 137.03599908) * std::sqrt(M_PI);
@@ -534,7 +561,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
-      e->last_launches += launch_screen(a, e->dproc.amp_kind, e->sm_count, e->stream);
+      e->last_launches += launch_screen(a, e->dproc.amp_kind, regge_fast_ff(e->dproc), e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
     }
   }
@@ -589,7 +616,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
-      e->last_launches += launch_screen(a, e->dproc.amp_kind, e->sm_count, e->stream);
+      e->last_launches += launch_screen(a, e->dproc.amp_kind, regge_fast_ff(e->dproc), e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
     }
   }
@@ -715,7 +742,7 @@ int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_o
 }
 
 int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y) {
-  if (!x || !y || n <= 0 || kind < 0 || kind > 5) return GRB_ERR_ARG;
+  if (!x || !y || n <= 0 || kind < 0 || kind > 7) return GRB_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return GRB_ERR_CUDA;
   return run_fastmath(kind, n, x, y) == cudaSuccess ? GRB_OK : GRB_ERR_CUDA;
 }

@@ -15,6 +15,7 @@ __constant__ DevRes  c_res;
 // lookup tables of grb_fastmath.cuh (global memory, read through the L1 / read-only path: indices diverge in a warp)
 __device__ const double2 g_logtab[128] = {GRB_LOGTAB_ROWS};
 __device__ const double  g_exptab[64]  = {GRB_EXPTAB_ROWS};
+__device__ const double2 g_sincostab[128] = {GRB_SINCOSTAB_ROWS};
 
 cudaError_t upload_proc(const DevProc &p, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_proc, &p, sizeof(DevProc), 0, cudaMemcpyHostToDevice, st);
@@ -42,6 +43,8 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
     case AMP_REGGE_RES_CON: launch_points_amp<AMP_REGGE_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_YY_LL: launch_points_amp<AMP_YY_LL>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_TENSOR_2XV: launch_points_amp<AMP_TENSOR_2XV>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_TENSOR_2XF: launch_points_amp<AMP_TENSOR_2XF>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_YY_QED: launch_points_amp<AMP_YY_QED>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     default: launch_points_amp<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;
@@ -95,6 +98,8 @@ __global__ void k_fastmath(int kind, int64_t n, const double *__restrict__ x, do
       case 2: y[i] = sqrt_fast_ok(x[i]) ? sqrt_fast_core(x[i]) : sqrt(x[i]); break;   // must equal sqrt(x) bit for bit
       case 3: y[i] = sqrt(x[i]); break;
       case 4: y[i] = div_checked(x[i], x[(i + 1) % n]); break;                         // must equal x[i] / x[i+1]
+      case 6: { double sn, cs; fast_sincos(x[i], sn, cs); y[i] = sn; break; }
+      case 7: { double sn, cs; fast_sincos(x[i], sn, cs); y[i] = cs; break; }
       default: y[i] = x[i] / x[(i + 1) % n]; break;
     }
 }

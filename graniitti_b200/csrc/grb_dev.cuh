@@ -66,6 +66,10 @@ struct DevProc {
   // tensor pomeron (MTensorPomeron.cc:572-763): 36 gPNN^2 g^2, delta_P, alpha'_P, ln alpha'_P, -pi/2, (2 mp)^2
   double tp_coupling, tp_delta, tp_ap, tp_ln_ap, tp_phase, four_mp2;
   double tp_g1, tp_g2, tp_vv_coupling;  // 2xV: Pomeron-V-V couplings (a, b of gPrhorho / gPphiphi), 9 gPNN^2
+  // 2xF / yy[QED] (grb_ferm.cuh): 81 gPNN^4, PDG mass of the central fermion, e = sqrt(4 pi alpha(0)), 1/(2 m_p),
+  // beam helicity spinors u(p_beam, -1/+1) (real: phi = 0), evaluated by the host libm as MDirac::uHelDirac does
+  double tp_ff_coupling, mass_leg0, qed_e, inv_2mp;
+  double bsp[2][2][4];
   int    em_kelly, amp_kind;
   DevNode nodes[GRB_MAX_NODES];
 };
@@ -139,7 +143,7 @@ cudaError_t upload_proc(const DevProc &p, cudaStream_t st);
 cudaError_t upload_loop(const DevLoop &l, cudaStream_t st);
 cudaError_t upload_res(const DevRes &r, cudaStream_t st);
 int         launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st);
-int         launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st);
+int         launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, cudaStream_t st);
 cudaError_t run_dfma_peak(int sm_count, double *tflops);
 cudaError_t run_fastmath(int kind, int64_t n, const double *x_host, double *y_host);
 
@@ -162,8 +166,12 @@ __device__ __forceinline__ double rap_of(const v4 &a) { return 0.5 * log((a.e + 
 struct PzConst {
   double s, t7, t9, t14;  // s, sqrt(s), s^(3/2), s^2
 };
-__device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4, double pz5, double E5,
-                                              const PzConst &c) {
+// FAST = true: the branch-free form for the one-basic-block loop node -- the MUFU-seeded sqrt / division sequences run
+// unconditionally and `dom` records whether their range guards held (the caller re-evaluates the node on the checked
+// path otherwise); FAST = false: per-call guards with the libm fallback.
+template <bool FAST>
+__device__ __forceinline__ double solve_pz3_A_t(double m3, double pt3, double pt4, double pz5, double E5,
+                                                const PzConst &c, bool &dom) {
   const double s   = c.s;
   const double t2  = E5 * E5;
   const double t3  = pt3 * pt3;
@@ -189,15 +197,25 @@ __device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4,
                      E5 * t9 * 4.0 - s * t3 * 2.0 - s * t4 * 2.0 - s * t5 * 2.0 - s * t6 * 4.0 -
                      t2 * t3 * 2.0 - t2 * t4 * 2.0 - t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 4.0 -
                      E5 * t2 * t7 * 4.0;
-  const double t23 = sqrt_fast_ok(t22) ? sqrt_fast_core(t22) : sqrt(t22);
-  return pz5 * (-1.0 / 2.0) -
-         div_checked(E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0)),
-                     s + t2 - t5 - E5 * t7 * 2.0);
+  double t23;
+  if (FAST) { dom = dom && sqrt_fast_ok(t22); t23 = sqrt_fast_core(t22); }
+  else t23 = sqrt_fast_ok(t22) ? sqrt_fast_core(t22) : sqrt(t22);
+  const double num = E5 * t23 * (1.0 / 2.0) - t7 * t23 * (1.0 / 2.0) + pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0));
+  const double den = s + t2 - t5 - E5 * t7 * 2.0;
+  double       q;
+  if (FAST) { q = div_fast_core(num, den); dom = dom && div_fast_ok(num, q); }
+  else q = div_checked(num, den);
+  return pz5 * (-1.0 / 2.0) - q;
+}
+__device__ __forceinline__ double solve_pz3_A(double m3, double pt3, double pt4, double pz5, double E5, const PzConst &c) {
+  bool dom = true;
+  return solve_pz3_A_t<false>(m3, pt3, pt4, pz5, E5, c, dom);
 }
 
 // reference MKinematics.h:117-160 SolvePz3_B (unequal forward masses)
-__device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5,
-                                           double E5, const PzConst &c) {
+template <bool FAST>
+__device__ __forceinline__ double solve_pz3_B_t(double m3, double m4, double pt3, double pt4, double pz5,
+                                                double E5, const PzConst &c, bool &dom) {
   const double s   = c.s;
   const double t2  = E5 * E5;
   const double t3  = m3 * m3;
@@ -231,11 +249,21 @@ __device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, 
                      s * t5 * 2.0 - s * t6 * 2.0 - s * t7 * 2.0 - t2 * t3 * 2.0 - t2 * t4 * 2.0 -
                      t2 * t5 * 2.0 - t3 * t4 * 2.0 - t2 * t6 * 2.0 - t2 * t7 * 2.0 - t3 * t6 * 2.0 -
                      t4 * t5 * 2.0 - t5 * t6 * 2.0 - E5 * t2 * t8 * 4.0;
-  const double t30 = sqrt_fast_ok(t29) ? sqrt_fast_core(t29) : sqrt(t29);
-  return pz5 * (-1.0 / 2.0) -
-         div_checked(E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
-                         pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0)),
-                     s + t2 - t7 - E5 * t8 * 2.0);
+  double t30;
+  if (FAST) { dom = dom && sqrt_fast_ok(t29); t30 = sqrt_fast_core(t29); }
+  else t30 = sqrt_fast_ok(t29) ? sqrt_fast_core(t29) : sqrt(t29);
+  const double num = E5 * t30 * (1.0 / 2.0) - t8 * t30 * (1.0 / 2.0) +
+                     pz5 * (t3 * (1.0 / 2.0) - t4 * (1.0 / 2.0) + t5 * (1.0 / 2.0) - t6 * (1.0 / 2.0));
+  const double den = s + t2 - t7 - E5 * t8 * 2.0;
+  double       q;
+  if (FAST) { q = div_fast_core(num, den); dom = dom && div_fast_ok(num, q); }
+  else q = div_checked(num, den);
+  return pz5 * (-1.0 / 2.0) - q;
+}
+__device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, double pt4, double pz5, double E5,
+                                              const PzConst &c) {
+  bool dom = true;
+  return solve_pz3_B_t<false>(m3, m4, pt3, pt4, pz5, E5, c, dom);
 }
 
 __device__ __forceinline__ double solve_pz(double m3, double m4, double pt3, double pt4, double pz5,

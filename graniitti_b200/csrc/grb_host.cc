@@ -145,6 +145,12 @@ class ParticleTable {
   const Particle &by_name(const std::string &n) const {
     for (auto &kv : tab)
       if (kv.second.name == n) return kv.second;
+    // PDG number input is allowed too (reference src/MPDG.cc:572-576, aux::IsIntegerDigits)
+    if (!n.empty() && n.find_first_not_of("-0123456789") == std::string::npos) {
+      auto it = tab.find(std::stoi(n));
+      if (it != tab.end()) return it->second;
+      throw std::invalid_argument("MPDG::FindByPDG: Unknown PDG ID: " + n);
+    }
     throw std::invalid_argument("MPDG::FindByPDGName: Unknown particle name: " + n);
   }
   const Particle &by_pdg(int pdg) const {

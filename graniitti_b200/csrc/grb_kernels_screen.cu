@@ -15,7 +15,8 @@ namespace grb {
 // k_screen is the pure loop integral: it reads one work-list item, writes |A_born + A_loop|^2 back into the item.
 // Weight assembly, NaN handling, outputs and VEGAS accumulation happen in k_finish, which keeps the hot kernel's
 // register budget free of histogram/atomic code.
-template <int AMP, bool SAME>
+// FF >= 0: single-trajectory Regge continuum with PARAM_REGGE::offshellFF = FF, the one-basic-block node (grb_point.cuh)
+template <int AMP, bool SAME, int FF>
 __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   const DevProc &P = c_proc;
   const int64_t  c = a.item_cap;
@@ -49,19 +50,20 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   } else {
     cx h0;
     h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
-    it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
+    if (AMP == AMP_REGGE && FF >= 0) it[IT_AMP2 * c] = screened_amp2_regge_fast<SAME, (FF >= 0 ? FF : 0)>(L, h0);
+    else it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
   }
 }
 
-template <int MINB, int AMP>
+template <int MINB, int AMP, int FF>
 __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
   const int64_t nA = min((int64_t)a.item_count[0], a.item_cap), nB = min((int64_t)a.item_count[1], a.item_cap - nA);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // class A occupies slots [0, nA), class B slots [cap - nB, cap); each loop is branch-uniform.  The B loop starts
   // where the A loop's last sweep left idle threads (rotation by nA) to balance the persistent grid.
-  for (int64_t t = t0; t < nA; t += stride) screen_item<AMP, true>(a, t);
+  for (int64_t t = t0; t < nA; t += stride) screen_item<AMP, true, FF>(a, t);
   const int64_t rot = (stride - (nA % stride)) % stride;
-  for (int64_t t = (t0 + rot) % stride; t < nB; t += stride) screen_item<AMP, false>(a, a.item_cap - nB + t);
+  for (int64_t t = (t0 + rot) % stride; t < nB; t += stride) screen_item<AMP, false, FF>(a, a.item_cap - nB + t);
 }
 
 // weight assembly + outputs + VEGAS accumulation for the screened work list
@@ -108,22 +110,23 @@ __global__ void __launch_bounds__(256) k_finish(const PointArgs a) {
   if (VEGAS) hist_flush(nb, dim, a.acc);
 }
 
-template <int MINB, int AMP>
+template <int MINB, int AMP, int FF = -1>
 static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
   // GRB_SCREEN_OCC=n (profiling knob): pad dynamic shared memory so that only n CTAs fit an SM, same code
   static const int occ = [] { const char *e = getenv("GRB_SCREEN_OCC"); return e ? atoi(e) : 0; }();
   if (occ > 0 && occ < MINB) {
     const int pad = (227 * 1024) / (occ + 1) + 2048;
-    cudaFuncSetAttribute(k_screen<MINB, AMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-    k_screen<MINB, AMP><<<sm_count * occ, 128, pad, st>>>(a);
+    cudaFuncSetAttribute(k_screen<MINB, AMP, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+    k_screen<MINB, AMP, FF><<<sm_count * occ, 128, pad, st>>>(a);
   } else
-    k_screen<MINB, AMP><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
+    k_screen<MINB, AMP, FF><<<sm_count * MINB, 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
   const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
   if (a.vegas) k_finish<true><<<sm_count * 4, 256, smem, st>>>(a);
   else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);
 }
 
-int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t st) {
+// regge_ff: PARAM_REGGE::offshellFF when the Regge continuum has one active trajectory (fast node), else -1
+int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, cudaStream_t st) {
   // tuning knob for profiling runs; the default is the measured best (profiles/)
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
   if (amp_kind == AMP_TENSOR_2XS) {
@@ -138,6 +141,14 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
     launch_screen_t<2, AMP_TENSOR_2XV>(a, sm_count, st);
     return 2;
   }
+  if (amp_kind == AMP_TENSOR_2XF) {
+    launch_screen_t<2, AMP_TENSOR_2XF>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_YY_QED) {
+    launch_screen_t<2, AMP_YY_QED>(a, sm_count, st);
+    return 2;
+  }
   if (amp_kind == AMP_YY_LL) {
     launch_screen_t<2, AMP_YY_LL>(a, sm_count, st);
     return 2;
@@ -145,6 +156,12 @@ int launch_screen(const PointArgs &a, int amp_kind, int sm_count, cudaStream_t s
   if (amp_kind == AMP_REGGE_RES_CON) {
     launch_screen_t<2, AMP_REGGE_RES_CON>(a, sm_count, st);
     return 2;
+  }
+  static const bool nofast = getenv("GRB_SCREEN_NOFAST") != nullptr;  // profiling knob: the checked node everywhere
+  if (!nofast && minb == 4) {
+    if (regge_ff == 0) { launch_screen_t<4, AMP_REGGE, 0>(a, sm_count, st); return 2; }
+    if (regge_ff == 1) { launch_screen_t<4, AMP_REGGE, 1>(a, sm_count, st); return 2; }
+    if (regge_ff == 2) { launch_screen_t<4, AMP_REGGE, 2>(a, sm_count, st); return 2; }
   }
   switch (minb) {
     case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;

@@ -393,7 +393,7 @@ __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
     // g2 (Et / dt + sign Eu / du) / dF
     const double R = div_checked(P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), dt * du * dF);
     double       sn, cs;
-    sincos(P.phase_c[0] * (in.t1 + in.t2), &sn, &cs);
+    fast_sincos(P.phase_c[0] * (in.t1 + in.t2), sn, cs);
     A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
     A.im = fma(P.eta0sq_re, sn, P.eta0sq_im * cs) * R;
   } else {
@@ -473,7 +473,7 @@ __device__ __forceinline__ cx tensor_me4_2xS(const NodeKin &in, const v4 &p3, co
   const double pre  = P.tp_coupling * proton_F1(in.t1) * proton_F1(in.t2);
   const double R    = pre * (Et * Rt * FMt * meson_G(pt2) + Eu * Ru * FMu * meson_G(pu2));
   double       sn, cs;
-  sincos(P.tp_phase * (a1 + a2), &sn, &cs);  // tp_phase = -pi/2
+  fast_sincos(P.tp_phase * (a1 + a2), sn, cs);  // tp_phase = -pi/2
   cx A;
   A.re = cs * R;
   A.im = sn * R;
@@ -639,10 +639,12 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
 }  // namespace grb
 
 #include "grb_yy.cuh"
+#include "grb_ferm.cuh"
 
 namespace grb {
 
-enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5 };
+enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5,
+       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
@@ -650,6 +652,8 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
     cx h0;
     return {sqrt(tensor_2xV_amp2(in, p3, p4, h0)), 0.0};
   }
+  if (AMP == AMP_TENSOR_2XF) return {sqrt(tensor_2xF_amp2(in, p3, p4)), 0.0};  // unscreened only
+  if (AMP == AMP_YY_QED) return {sqrt(yy_qed_amp2(in, p3, p4)), 0.0};          // unscreened only
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {
@@ -661,16 +665,21 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
 
 // Processes whose helicity amplitudes differ (reference lts.hamp.size() > 1 after dropping identical copies): the
 // screening loop integrates every amplitude separately (MProcess.cc:262-283).  NH = distinct amplitudes,
-// amp2 = SCALE * sum_h |A_h|^2:  yy -> l+ l-: 16 amplitudes, /4;  tensor 2xV: 36 = 4 x 9 amplitudes, /4 -> 9, x1.
+// amp2 = SCALE * sum_h |A_h|^2:  yy -> l+ l- (HELAS and yy[QED]): 16 amplitudes, /4;  tensor 2xV: 36 = 4 x 9 amplitudes,
+// /4 -> 9, x1;  tensor 2xF: 16 = 4 x 4 -> 4, x1.
 template <int AMP> struct AmpHel { static constexpr int NH = 1; };
 template <> struct AmpHel<AMP_YY_LL> { static constexpr int NH = 16; };
 template <> struct AmpHel<AMP_TENSOR_2XV> { static constexpr int NH = 9; };
+template <> struct AmpHel<AMP_TENSOR_2XF> { static constexpr int NH = 4; };
+template <> struct AmpHel<AMP_YY_QED> { static constexpr int NH = 16; };
 template <int AMP>
-__device__ __forceinline__ double amp_hel_scale() { return AMP == AMP_YY_LL ? 0.25 : 1.0; }
+__device__ __forceinline__ double amp_hel_scale() { return (AMP == AMP_YY_LL || AMP == AMP_YY_QED) ? 0.25 : 1.0; }
 template <int AMP>
 __device__ __forceinline__ void amplitude_vec(const NodeKin &in, const v4 &p3, const v4 &p4, cx *h) {
   if (AMP == AMP_YY_LL) yy_ll_core<true>(in, p3, p4, h);
   else if (AMP == AMP_TENSOR_2XV) tensor_me4_2xV(in, p3, p4, h);
+  else if (AMP == AMP_TENSOR_2XF) tensor_me4_2xF(in, p3, p4, h);
+  else if (AMP == AMP_YY_QED) yy_qed_amp(in, p3, p4, h);
   else h[0] = amplitude<AMP>(in, p3, p4);
 }
 
@@ -766,6 +775,108 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
     Iim = fma(wi, Jim, Iim);
   }
   // hamp_loop = i * norm * I
+  const double lr = -Q.norm * Iim, li = Q.norm * Ire;
+  const double ar = h0.re + lr, ai = h0.im + li;
+  return ar * ar + ai * ai;
+}
+
+// ---- single-trajectory Regge continuum: one loop node as ONE basic block ----------------------------------------------
+// loop_node() + regge_me4() leave a node through ~20 branches (range guards of every sqrt / division / log / exp /
+// sincos, five physics rejections), which costs issue slots and keeps the scheduler from overlapping the independent
+// chains.  Here every MUFU-seeded sequence runs unconditionally: `valid` collects the physics rejections, the return value
+// says whether a range guard failed on a node that was still valid at that point -- then (rare) the caller re-evaluates
+// the node on the checked path.  Same expressions in the same order as the checked path: identical bits when the guards
+// hold.  FF = PARAM_REGGE::offshellFF resolved at compile time.
+template <bool SAME, int FF>
+__device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzConst &pc, double ktx, double kty, bool &valid, cx &A) {
+  const DevProc &P = c_proc;
+  const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
+  const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
+  const double a1s = fmax(0.0, n1x * n1x + n1y * n1y), a2s = fmax(0.0, n2x * n2x + n2y * n2y), aXs = fmax(0.0, L.mXsq + (Xx * Xx + Xy * Xy));
+  bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(aXs));
+  const double pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s), mtX = sqrt_fast_core(aXs);
+  const double Xz = mtX * L.shY, Xe = mtX * L.chY;
+  valid = !(Xe > L.emax);
+  bool         dom = true;
+  const double p1z = SAME ? solve_pz3_A_t<true>(L.m1, pt1, pt2, Xz, Xe, pc, dom) : solve_pz3_B_t<true>(L.m1, L.m2, pt1, pt2, Xz, Xe, pc, dom);
+  redo = redo || (valid && !dom);
+  const double p2z = -(Xz + p1z);
+  valid = valid && !(isnan(p1z) || p1z < 0 || p2z > 0);
+  const double e1s = fmax(0.0, L.m1sq + pow2(pt1) + pow2(p1z)), e2s = fmax(0.0, L.m2sq + pow2(pt2) + pow2(p2z));
+  redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
+  const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
+  valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
+  const v4 &p3 = L.p3, &p4 = L.p4;
+  const double ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
+  const double ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
+  const double ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
+  const double ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
+  valid = valid && !(ss13 < 0 || ss14 < 0 || ss23 < 0 || ss24 < 0);
+  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  const double t1 = m2_of(q1x, q1y, q1z, q1e);
+  const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
+  valid = valid && !(t1 > 0 || t2 > 0);
+  const double t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  const double u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  // amplitude: regge_me4(), single-trajectory branch
+  const double dF = (fma(-t1, P.inv_fc1, 1.0) * fma(-t1, P.inv_fc2, 1.0)) * (fma(-t2, P.inv_fc1, 1.0) * fma(-t2, P.inv_fc2, 1.0));
+  double       dt = t_hat - P.M2_leg0, du = u_hat - P.M2_leg0;
+  const double al1 = fma(P.ap[0], t1, P.a0[0]), al2 = fma(P.ap[0], t2, P.a0[0]);
+  double       gt = 0.0, gu = 0.0;
+  if (FF == 0) {
+    gt = -2.0 * P.b_EXP * fabs(dt);
+    gu = -2.0 * P.b_EXP * fabs(du);
+  } else if (FF == 1) {
+    gt = 2.0 * fma(-P.b_OREAR, msqrt(fabs(dt) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+    gu = 2.0 * fma(-P.b_OREAR, msqrt(fabs(du) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+  } else {
+    const double d1 = fma(-dt, P.inv_b_POW, 1.0), d2 = fma(-du, P.inv_b_POW, 1.0);
+    dt *= d1 * d1;
+    du *= d2 * d2;
+  }
+  redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
+  const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
+  const double xt = fma(al1, L13 + P.ln_inv_s0, fma(al2, L24 + P.ln_inv_s0, gt)), xu = fma(al1, L14 + P.ln_inv_s0, fma(al2, L23 + P.ln_inv_s0, gu));
+  const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
+  const double num = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), den = dt * du * dF;
+  const double R   = div_fast_core(num, den);
+  const double ph  = P.phase_c[0] * (t1 + t2);
+  redo = redo || (valid && !(fabs(xt) < 690.0 && fabs(xu) < 690.0 && div_fast_ok(num, R) && fabs(ph) < 1.0e5));
+  double sn, cs;
+  fast_sincos_core(ph, sn, cs);
+  A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
+  A.im = fma(P.eta0sq_re, sn, P.eta0sq_im * cs) * R;
+  return redo;
+}
+// the checked path of one node (taken when a range guard failed: a handful of nodes per million)
+template <bool SAME>
+__device__ __forceinline__ bool regge_node_checked(const LoopInv &L, const PzConst &pc, double ktx, double kty, cx &A) {
+  NodeKin in;
+  if (!loop_node<SAME>(L, pc, ktx, kty, in)) return false;
+  A = regge_me4(in);
+  return true;
+}
+template <bool SAME, int FF>
+__device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, const cx &h0) {
+  const DevLoop &Q = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  double Ire = 0.0, Iim = 0.0;
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    double       Jre = 0.0, Jim = 0.0;
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      bool         valid;
+      cx           A;
+      if (__builtin_expect(regge_node_fast<SAME, FF>(L, pc, kt * cp, kt * sp, valid, A), 0)) valid = regge_node_checked<SAME>(L, pc, kt * cp, kt * sp, A);
+      const double ar = valid ? A.re : 0.0, ai = valid ? A.im : 0.0;  // rejected nodes contribute 0, keep their weight
+      Jre = fma(Q.b_re[j], ar, fma(-Q.b_im[j], ai, Jre));
+      Jim = fma(Q.b_re[j], ai, fma(Q.b_im[j], ar, Jim));
+    }
+    Ire = fma(wi, Jre, Ire);
+    Iim = fma(wi, Jim, Iim);
+  }
   const double lr = -Q.norm * Iim, li = Q.norm * Ire;
   const double ar = h0.re + lr, ai = h0.im + li;
   return ar * ar + ai * ai;

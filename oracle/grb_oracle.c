@@ -950,6 +950,288 @@ static double tensor_me4_2xV(ost *S) {
   return SumAmp2 / 4;
 }
 
+/* ---- tensor pomeron continuum, 2 x fermion (p pbar, Lambda Lambdabar) and the yy[QED] lepton branch ---------- */
+/* reference src/MTensorPomeron.cc:664-713 (QED), :765-804 (2xF); Dirac algebra of src/MDirac.cc in the DIRAC basis.
+ * Explicit 4x4 complex matrices and rank-4 tensors, as the reference builds them. */
+typedef struct { cx m[4][4]; } m44;
+static m44 og_up[4], og_lo[4], og_sig_lo[4][4];
+static int og_ready = 0;
+static m44 m44_zero(void) { m44 r; memset(&r, 0, sizeof r); return r; }
+static m44 m44_mul(const m44 *a, const m44 *b) { /* MMatrix operator*: C[i][j] += A[i][k] B[k][j] */
+  m44 r = m44_zero();
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < 4; ++k) r.m[i][j] = cx_add(r.m[i][j], cx_mul(a->m[i][k], b->m[k][j]));
+  return r;
+}
+static m44 m44_add(const m44 *a, const m44 *b) {
+  m44 r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[i][j] = cx_add(a->m[i][j], b->m[i][j]);
+  return r;
+}
+static m44 m44_sub(const m44 *a, const m44 *b) {
+  m44 r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[i][j] = (cx){a->m[i][j].re - b->m[i][j].re, a->m[i][j].im - b->m[i][j].im};
+  return r;
+}
+static m44 m44_scale(const m44 *a, cx s) {
+  m44 r;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[i][j] = cx_mul(a->m[i][j], s);
+  return r;
+}
+static m44 m44_scaler(const m44 *a, double s) { return m44_scale(a, (cx){s, 0.0}); }
+static void og_init(void) { /* MDirac::InitGammaMatrices("DIRAC"), src/MDirac.cc:47-140 */
+  if (og_ready) return;
+  static const double y0[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, -1, 0}, {0, 0, 0, -1}};
+  static const double y1[4][4] = {{0, 0, 0, 1}, {0, 0, 1, 0}, {0, -1, 0, 0}, {-1, 0, 0, 0}};
+  static const double y2i[4][4] = {{0, 0, 0, -1}, {0, 0, 1, 0}, {0, 1, 0, 0}, {-1, 0, 0, 0}}; /* times i */
+  static const double y3[4][4] = {{0, 0, 1, 0}, {0, 0, 0, -1}, {-1, 0, 0, 0}, {0, 1, 0, 0}};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      og_up[0].m[i][j] = (cx){y0[i][j], 0}; og_lo[0].m[i][j] = (cx){y0[i][j], 0};
+      og_up[1].m[i][j] = (cx){y1[i][j], 0}; og_lo[1].m[i][j] = (cx){-y1[i][j], 0};
+      og_up[2].m[i][j] = (cx){0, y2i[i][j]}; og_lo[2].m[i][j] = (cx){0, -y2i[i][j]};
+      og_up[3].m[i][j] = (cx){y3[i][j], 0}; og_lo[3].m[i][j] = (cx){-y3[i][j], 0};
+    }
+  for (int mu = 0; mu < 4; ++mu)
+    for (int nu = 0; nu < 4; ++nu) {
+      const m44 ab = m44_mul(&og_lo[mu], &og_lo[nu]), ba = m44_mul(&og_lo[nu], &og_lo[mu]);
+      const m44 c = m44_sub(&ab, &ba);
+      og_sig_lo[mu][nu] = m44_scale(&c, (cx){0.0, 0.5}); /* (zi / 2.0) */
+    }
+  og_ready = 1;
+}
+static inline double v4_con(v4 a, int mu) { return mu == 0 ? a.e : (mu == 1 ? a.x : (mu == 2 ? a.y : a.z)); }
+static m44 o_fslash(v4 a) { /* MDirac::FSlash, :506-510: sum_mu gamma_up[mu] * (a % mu) */
+  m44 r = m44_zero();
+  for (int mu = 0; mu < 4; ++mu) {
+    const m44 t = m44_scaler(&og_up[mu], v4_cov(a, mu));
+    r = m44_add(&r, &t);
+  }
+  return r;
+}
+static m44 o_iD_F(v4 q, double m) { /* MDirac::iD_F, :382-384 */
+  m44 s = o_fslash(q);
+  for (int i = 0; i < 4; ++i) s.m[i][i] = cx_add(s.m[i][i], (cx){m, 0.0});
+  const cx f = cx_div((cx){0.0, 1.0}, (cx){v4_m2(q) - pow2(m), 0.0});
+  return m44_scale(&s, f);
+}
+static void o_uHelDirac(v4 p, int hel, cx u[4]) { /* MDirac::uHelDirac, :224-246 */
+  const double E = p.e, p3 = v4_p3mod(p), m = v4_m(p), N = msqrt(E + m);
+  const double th2 = v4_theta(p) / 2.0, phi = v4_phi(p), c = cos(th2), s = sin(th2);
+  const cx ph = {cos(phi), sin(phi)};
+  if (hel == 1) {
+    u[0] = (cx){N * c, 0}; u[1] = cx_mulr(cx_mulr(ph, N), s);
+    u[2] = (cx){N * p3 / (E + m) * c, 0}; u[3] = cx_mulr(cx_mulr(ph, N * p3 / (E + m)), s);
+  } else {
+    u[0] = (cx){-N * s, 0}; u[1] = cx_mulr(cx_mulr(ph, N), c);
+    u[2] = (cx){N * p3 / (E + m) * s, 0}; u[3] = cx_mulr(cx_mulr(ph, -N * p3 / (E + m)), c);
+  }
+}
+static void o_vHelDirac(v4 p, int hel, cx v[4]) { /* :248-257 */
+  cx u[4];
+  o_uHelDirac(p, -hel, u);
+  v[0] = u[2]; v[1] = u[3]; v[2] = u[0]; v[3] = u[1];
+}
+static void o_bar(const cx s[4], cx b[4]) { /* MDirac::Bar: conj(s) . gamma^0 */
+  b[0] = cx_conj(s[0]); b[1] = cx_conj(s[1]);
+  b[2] = (cx){-s[2].re, s[2].im}; b[3] = (cx){-s[3].re, s[3].im};
+}
+static cx o_vmv(const cx a[4], const m44 *B, const cx c[4]) { /* matoper::VecMatVecMultiply */
+  cx v = {0, 0};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) v = cx_add(v, cx_mul(cx_mul(a[i], B->m[i][j]), c[j]));
+  return v;
+}
+static void o_vm(const cx a[4], const m44 *B, cx c[4]) { /* matoper::VecMatMultiply */
+  for (int j = 0; j < 4; ++j) {
+    c[j] = (cx){0, 0};
+    for (int k = 0; k < 4; ++k) c[j] = cx_add(c[j], cx_mul(a[k], B->m[k][j]));
+  }
+}
+static double o_F2(const ost *S, double Q2) { /* form::F2, src/MForm.cc:550-555 */
+  const double mp = 0.938272081;
+  Q2 = fabs(Q2);
+  const double tau = Q2 / pow2(2 * mp);
+  return -1.0 / (tau + 1) * o_GE(S, Q2) + 1.0 / (tau + 1) * o_GM(S, Q2);
+}
+/* pomeron-fermion vertex matrix of iG_Ppp / iG_PppbarP (:1421-1432,:1465-1481) */
+static m44 o_pff_A(v4 psum, const m44 *slash, int mu, int nu) {
+  const m44 a = m44_scaler(&og_lo[mu], v4_cov(psum, nu)), b = m44_scaler(&og_lo[nu], v4_cov(psum, mu));
+  m44 A = m44_add(&a, &b);
+  A = m44_scaler(&A, 0.5);
+  if (mu == nu) {
+    m44 s = m44_scaler(slash, 0.25);
+    s = m44_scaler(&s, o_g[mu][nu]);
+    A = m44_sub(&A, &s);
+  }
+  return A;
+}
+/* :1441-1488 iG_PppbarP */
+static void tp_iG_PppbarP(const ost *S, v4 prime, const cx ubar[4], v4 pt, const m44 *iSF, const cx v[4], v4 p,
+                          cx T[4][4][4][4]) {
+  const double fl = 3.0 * S->d->tpom.gPNN * o_F1(S, v4_m2(v4_sub(prime, pt)));
+  const double fr = 3.0 * S->d->tpom.gPNN * o_F1(S, v4_m2(v4_sub(pt, p)));
+  const cx lhsF = {-0.0 * fl, -1.0 * fl}, rhsF = {-0.0 * fr, -1.0 * fr};
+  const v4 lsum = v4_add(prime, pt), rsum = v4_add(pt, p);
+  const m44 lsl = o_fslash(lsum), rsl = o_fslash(rsum);
+  m44 RA[4][4];
+  for (int m1 = 0; m1 < 4; ++m1)
+    for (int n1 = 0; n1 < 4; ++n1) RA[m1][n1] = o_pff_A(rsum, &rsl, m1, n1);
+  for (int m2 = 0; m2 < 4; ++m2)
+    for (int n2 = 0; n2 < 4; ++n2) {
+      const m44 lA = o_pff_A(lsum, &lsl, m2, n2);
+      const m44 lAS = m44_mul(&lA, iSF);
+      cx ubarM[4];
+      o_vm(ubar, &lAS, ubarM);
+      for (int m1 = 0; m1 < 4; ++m1)
+        for (int n1 = 0; n1 < 4; ++n1) T[m2][n2][m1][n1] = cx_mul(cx_mul(lhsF, o_vmv(ubarM, &RA[m1][n1], v)), rhsF);
+    }
+}
+static double tensor_me4_2xF(ost *S) {
+  og_init();
+  const grb_process_desc *d = S->d;
+  const v4 pa = S->pbeam1, pb = S->pbeam2, p1 = S->pfinal[1], p2 = S->pfinal[2];
+  const v4 p3 = S->node_p4[0], p4 = S->node_p4[1];
+  const double M_ = d->nodes[0].mass;
+  const v4 pt = v4_sub(v4_sub(pa, p1), p3);
+  const v4 pu = v4_add(v4_sub(p4, pa), p1);
+  const v4 mp3 = {-p3.x, -p3.y, -p3.z, -p3.e};
+  static cx D13[4][4][4][4], D24[4][4][4][4], D14[4][4][4][4], D23[4][4][4][4], Gt[4][4][4][4], Gu[4][4][4][4];
+  cx G1a[4][4], G2b[4][4];
+  tp_iDP(S, S->ss[1][3], S->t1, D13);
+  tp_iDP(S, S->ss[2][4], S->t2, D24);
+  tp_iDP(S, S->ss[1][4], S->t1, D14);
+  tp_iDP(S, S->ss[2][3], S->t2, D23);
+  tp_iG_PppHE(S, p1, pa, G1a);
+  tp_iG_PppHE(S, p2, pb, G2b);
+  const m44 iSFt = o_iD_F(pt, M_), iSFu = o_iD_F(pu, M_);
+  const double fft = pow2(meson_ff(S, v4_m2(pt), pow2(M_))), ffu = pow2(meson_ff(S, v4_m2(pu), pow2(M_))); /* Baryon_FF == Meson_FF */
+  /* pomeron legs: X13(a,b) = G1a(m,n) D13(m,n,a,b) etc. */
+  cx X13[4][4], X24[4][4], X14[4][4], X23[4][4];
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      cx x13 = {0, 0}, x24 = {0, 0}, x14 = {0, 0}, x23 = {0, 0};
+      for (int m = 0; m < 4; ++m)
+        for (int n = 0; n < 4; ++n) {
+          x13 = cx_add(x13, cx_mul(G1a[m][n], D13[m][n][a][b]));
+          x14 = cx_add(x14, cx_mul(G1a[m][n], D14[m][n][a][b]));
+          x24 = cx_add(x24, cx_mul(D24[a][b][m][n], G2b[m][n]));
+          x23 = cx_add(x23, cx_mul(D23[a][b][m][n], G2b[m][n]));
+        }
+      X13[a][b] = x13; X14[a][b] = x14; X24[a][b] = x24; X23[a][b] = x23;
+    }
+  cx h[4];
+  for (int h3 = 0; h3 < 2; ++h3)
+    for (int h4 = 0; h4 < 2; ++h4) {
+      cx v3[4], u4[4], ubar4[4];
+      o_vHelDirac(p3, h3 == 0 ? -1 : 1, v3);
+      o_uHelDirac(p4, h4 == 0 ? -1 : 1, u4);
+      o_bar(u4, ubar4);
+      tp_iG_PppbarP(S, p4, ubar4, pt, &iSFt, v3, mp3, Gt);
+      tp_iG_PppbarP(S, p4, ubar4, pu, &iSFu, v3, mp3, Gu);
+      cx Mt = {0, 0}, Mu = {0, 0};
+      /* t: X13(a1,b1) Gt(a2,b2,a1,b1) X24(a2,b2);  u: X14(a1,b1) Gu(a1,b1,a2,b2) X23(a2,b2) */
+      for (int a1 = 0; a1 < 4; ++a1)
+        for (int b1 = 0; b1 < 4; ++b1)
+          for (int a2 = 0; a2 < 4; ++a2)
+            for (int b2 = 0; b2 < 4; ++b2) {
+              Mt = cx_add(Mt, cx_mul(cx_mul(X13[a1][b1], Gt[a2][b2][a1][b1]), X24[a2][b2]));
+              Mu = cx_add(Mu, cx_mul(cx_mul(X14[a1][b1], Gu[a1][b1][a2][b2]), X23[a2][b2]));
+            }
+      Mt = cx_mulr(Mt, fft);
+      Mu = cx_mulr(Mu, ffu);
+      h[2 * h3 + h4] = cx_mul((cx){-0.0, -1.0}, cx_add(Mt, Mu));
+    }
+  S->nhamp = 16;
+  double SumAmp2 = 0.0;
+  for (int k = 0; k < 16; ++k) {
+    S->hamp[k] = h[k % 4];
+    SumAmp2 += cx_abs2(S->hamp[k]);
+  }
+  return SumAmp2 / 4;
+}
+
+/* :1342-1363 iG_ypp: full proton-photon-proton vertex between spinors */
+static void tp_iG_ypp(const ost *S, v4 prime, v4 p, const cx ubar[4], const cx u[4], cx T[4]) {
+  const double t = v4_m2(v4_sub(prime, p));
+  const double e = msqrt(0.0072973525693 * 4.0 * O_PI);
+  const v4 psum = v4_sub(prime, p);
+  const double F1 = o_F1(S, t), F2 = o_F2(S, t);
+  for (int mu = 0; mu < 4; ++mu) {
+    m44 SUM = m44_zero();
+    for (int nu = 0; nu < 4; ++nu) {
+      const m44 t1 = m44_scaler(&og_sig_lo[mu][nu], v4_con(psum, nu));
+      SUM = m44_add(&SUM, &t1);
+    }
+    const m44 A = m44_scaler(&og_lo[mu], F1);
+    m44 B = m44_scale(&SUM, (cx){0.0, 1.0});
+    B = m44_scaler(&B, 1.0 / (2 * 0.938272081));
+    B = m44_scaler(&B, F2);
+    m44 G = m44_add(&A, &B);
+    G = m44_scale(&G, (cx){-0.0 * e, -1.0 * e});
+    T[mu] = o_vmv(ubar, &G, u);
+  }
+}
+/* :1367-1383 iG_yeebary */
+static void tp_iG_yeebary(const cx ubar[4], const m44 *iSF, const cx v[4], cx T[4][4]) {
+  const double e = msqrt(0.0072973525693 * 4.0 * O_PI);
+  const cx vertex = {0.0, e};
+  for (int mu = 0; mu < 4; ++mu) {
+    const m44 gS = m44_mul(&og_lo[mu], iSF);
+    cx lhs[4];
+    o_vm(ubar, &gS, lhs);
+    for (int nu = 0; nu < 4; ++nu) T[mu][nu] = cx_mul(cx_mul(vertex, o_vmv(lhs, &og_lo[nu], v)), vertex);
+  }
+}
+/* :664-713: lepton pair via two-photon fusion, full QED spinor structure on the proton lines */
+static double tensor_me4_yyQED(ost *S) {
+  og_init();
+  const grb_process_desc *d = S->d;
+  const v4 pa = S->pbeam1, pb = S->pbeam2, p1 = S->pfinal[1], p2 = S->pfinal[2];
+  const v4 p3 = S->node_p4[0], p4 = S->node_p4[1];
+  const double M_ = d->nodes[0].mass;
+  const v4 pt = v4_sub(v4_sub(pa, p1), p3);
+  const v4 pu = v4_add(v4_sub(p4, pa), p1);
+  const m44 iSFt = o_iD_F(pt, M_), iSFu = o_iD_F(pu, M_);
+  int k = 0;
+  for (int ha = 0; ha < 2; ++ha)
+    for (int hb = 0; hb < 2; ++hb) {
+      cx ua[4], ub[4], u1[4], u2[4], ubar1[4], ubar2[4], G1[4], G2[4];
+      o_uHelDirac(pa, ha == 0 ? -1 : 1, ua);
+      o_uHelDirac(pb, hb == 0 ? -1 : 1, ub);
+      o_uHelDirac(p1, ha == 0 ? -1 : 1, u1);
+      o_uHelDirac(p2, hb == 0 ? -1 : 1, u2);
+      o_bar(u1, ubar1);
+      o_bar(u2, ubar2);
+      tp_iG_ypp(S, p1, pa, ubar1, ua, G1);
+      tp_iG_ypp(S, p2, pb, ubar2, ub, G2);
+      /* iD_y(q2)(u,v) = -i g[u][v] / q2, MDirac.cc:372-378 */
+      cx L1[4], L2[4];
+      for (int n = 0; n < 4; ++n) {
+        L1[n] = cx_mul(G1[n], cx_div((cx){-0.0 * o_g[n][n], -1.0 * o_g[n][n]}, (cx){S->t1, 0.0}));
+        L2[n] = cx_mul(cx_div((cx){-0.0 * o_g[n][n], -1.0 * o_g[n][n]}, (cx){S->t2, 0.0}), G2[n]);
+      }
+      for (int h3 = 0; h3 < 2; ++h3)
+        for (int h4 = 0; h4 < 2; ++h4) {
+          cx v3[4], u4[4], ubar4[4], Ft[4][4], Fu[4][4];
+          o_vHelDirac(p3, h3 == 0 ? -1 : 1, v3);
+          o_uHelDirac(p4, h4 == 0 ? -1 : 1, u4);
+          o_bar(u4, ubar4);
+          tp_iG_yeebary(ubar4, &iSFt, v3, Ft);
+          tp_iG_yeebary(ubar4, &iSFu, v3, Fu);
+          cx M = {0, 0};
+          for (int n1 = 0; n1 < 4; ++n1)
+            for (int n2 = 0; n2 < 4; ++n2) M = cx_add(M, cx_mul(cx_mul(L1[n1], cx_add(Ft[n2][n1], Fu[n1][n2])), L2[n2]));
+          S->hamp[k++] = cx_mul((cx){-0.0, -1.0}, M);
+        }
+    }
+  S->nhamp = 16;
+  double SumAmp2 = 0.0;
+  for (int i = 0; i < 16; ++i) SumAmp2 += cx_abs2(S->hamp[i]);
+  return SumAmp2 / 4;
+}
+
 static double o_factorial(int n) {
   double x = 1;
   for (int i = 1; i <= n; ++i) x *= i;
@@ -1415,8 +1697,17 @@ static double bare_amp2(ost *S) {
     }
     case GRB_PROC_PP_RES: return res_amp2(S, 0);
     case GRB_PROC_PP_RES_CON: return res_amp2(S, 1);
+    case GRB_PROC_YY_QED: {
+      const int apdg = abs(S->d->nodes[0].pdg);
+      if (!(apdg == 11 || apdg == 13 || apdg == 15) || S->d->nodes[1].pdg != -S->d->nodes[0].pdg) {
+        S->nhamp = 0;
+        return NAN; /* quark pairs need fragmentation downstream: not restated */
+      }
+      return tensor_me4_yyQED(S);
+    }
     case GRB_PROC_PP_CONTENSOR: {
       if (S->d->nodes[0].spinX2 == 2 && S->d->nodes[1].spinX2 == 2) return tensor_me4_2xV(S);
+      if (S->d->nodes[0].spinX2 == 1 && S->d->nodes[1].spinX2 == 1) return tensor_me4_2xF(S);
       if (g_oracle_extended) {
         double re, im;
         const double a2 = tensor_me4_extended(S, &re, &im);

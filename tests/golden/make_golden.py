@@ -44,6 +44,12 @@ CASES = [
     ("c4_cms_mumu_yycon_screened", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 1, 256, 8, True),
     ("c5_cms_rhorho_stable_tensor_screened", "./tests/processes/CMSCUTS.json",
      "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 1, 160, 8, True),
+    # spin-1/2 central pairs: tensor pomeron 2xF (16 = 4 x 4 helicity amplitudes) and the yy[QED] lepton branch (16)
+    ("c5_cms_ppbar_tensor_born", "./tests/processes/CMSCUTS.json", "PP[CONTENSOR]<F> -> p+ p-", 0, 1536, 8, True),
+    ("c5_cms_lambda_tensor_born", "./tests/processes/CMSCUTS.json", "PP[CONTENSOR]<F> -> Lambda0 Lambda0~", 0, 768, 8, True),
+    ("c2_alice_ppbar_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> p+ p-", 1, 192, 8, True),
+    ("c4_cms_mumu_yyqed_born", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[QED]<F> -> mu+ mu-", 0, 1536, 8, True),
+    ("c4_cms_mumu_yyqed_screened", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[QED]<F> -> mu+ mu-", 1, 160, 8, True),
 ]
 
 

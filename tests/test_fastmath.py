@@ -31,6 +31,27 @@ def test_fast_exp_accuracy(grb):
     assert rel.max() < 3.4e-16, rel.max()        # <= 1.5 ulp
 
 
+def test_fast_sincos_accuracy(grb):
+    """Table-driven sincos of the Regge signature phase: absolute error <= 2e-16 where the amplitudes use it
+    (|x| = pi/2 alpha' |t1 + t2| < ~50), growing only with the argument reduction (|x| ulp-level) beyond."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-50, 50, 400000), rng.uniform(-1e-3, 1e-3, 50000), np.arange(-640, 641) * (np.pi / 64),
+                        np.arange(-640, 641) * (np.pi / 64) + np.pi / 128, rng.uniform(-9e4, 9e4, 100000)])
+    s, c = grb.test_fastmath(6, x), grb.test_fastmath(7, x)
+    xl = x.astype(np.longdouble)
+    es = np.abs((s - np.sin(xl)).astype(np.float64))
+    ec = np.abs((c - np.cos(xl)).astype(np.float64))
+    small = np.abs(x) <= 50
+    assert max(es[small].max(), ec[small].max()) < 2.0e-16, (es[small].max(), ec[small].max())
+    assert max(es.max(), ec.max()) < 1e-15
+    # libm path beyond the table-reduction domain, inf / NaN
+    x = np.array([1.0e5, -3.7e8, 1e22, np.inf, np.nan])
+    s, c = grb.test_fastmath(6, x), grb.test_fastmath(7, x)
+    with np.errstate(all="ignore"):
+        assert np.allclose(s[:3], np.sin(x[:3]), rtol=0, atol=2e-16) and np.allclose(c[:3], np.cos(x[:3]), rtol=0, atol=2e-16)
+    assert np.all(np.isnan(s[3:])) and np.all(np.isnan(c[3:]))
+
+
 def test_fast_math_out_of_domain_takes_libm_path(grb):
     x = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310, 2.2250738585072014e-308, 1.7976931348623157e308])
     y = grb.test_fastmath(0, x)

@@ -742,7 +742,7 @@ int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_o
 }
 
 int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y) {
-  if (!x || !y || n <= 0 || kind < 0 || kind > 7) return GRB_ERR_ARG;
+  if (!x || !y || n <= 0 || kind < 0 || kind > 11) return GRB_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return GRB_ERR_CUDA;
   return run_fastmath(kind, n, x, y) == cudaSuccess ? GRB_OK : GRB_ERR_CUDA;
 }

@@ -98,6 +98,26 @@ __global__ void k_fastmath(int kind, int64_t n, const double *__restrict__ x, do
       case 2: y[i] = sqrt_fast_ok(x[i]) ? sqrt_fast_core(x[i]) : sqrt(x[i]); break;   // must equal sqrt(x) bit for bit
       case 3: y[i] = sqrt(x[i]); break;
       case 4: y[i] = div_checked(x[i], x[(i + 1) % n]); break;                         // must equal x[i] / x[i+1]
+      case 8: case 9: case 10: case 11: {
+        // SolvePz: checked reference-order form (8: A, 10: B) vs the power-of-two-folded fast form (9: A, 11: B) on
+        // arguments derived from six consecutive inputs (loop-node magnitudes at sqrt(s) = 13 TeV); must agree bit for bit
+        const double u0 = x[i], u1 = x[(i + 1) % n], u2 = x[(i + 2) % n], u3 = x[(i + 3) % n], u4 = x[(i + 4) % n], u5 = x[(i + 5) % n];
+        PzConst pc; pc.t7 = 13000.0; pc.s = 13000.0 * 13000.0; pc.t9 = pow(pc.s, 1.5); pc.t14 = pc.s * pc.s;
+        const double m3 = 0.938272081 + 1e-9 * (u0 - 0.5), m4 = (kind < 10) ? m3 : 0.938272081 + 3.0 * u1 * u1;
+        const double pt3 = 3.0 * u2 * u2 + 1e-6, pt4 = 3.0 * u3 * u3 + 1e-6;
+        const double mt = 0.3 + 6.0 * u4, yy = 6.0 * (u5 - 0.5), pz5 = mt * sinh(yy), E5 = mt * cosh(yy);
+        bool dom = true;
+        double r;
+        if (kind == 8) r = solve_pz3_A(m3, pt3, pt4, pz5, E5, pc);
+        else if (kind == 10) r = solve_pz3_B(m3, m4, pt3, pt4, pz5, E5, pc);
+        else {
+          const PzInv I = make_pz_inv(m3, m4, pc, kind == 9);
+          r = (kind == 9) ? solve_pz3_A_fast(I, pt3, pt4, pz5, E5, dom) : solve_pz3_B_fast(I, pt3, pt4, pz5, E5, dom);
+          if (!dom) r = (kind == 9) ? solve_pz3_A(m3, pt3, pt4, pz5, E5, pc) : solve_pz3_B(m3, m4, pt3, pt4, pz5, E5, pc);
+        }
+        y[i] = r;
+        break;
+      }
       case 6: { double sn, cs; fast_sincos(x[i], sn, cs); y[i] = sn; break; }
       case 7: { double sn, cs; fast_sincos(x[i], sn, cs); y[i] = cs; break; }
       default: y[i] = x[i] / x[(i + 1) % n]; break;

@@ -266,6 +266,72 @@ __device__ __forceinline__ double solve_pz3_B(double m3, double m4, double pt3, 
   return solve_pz3_B_t<false>(m3, m4, pt3, pt4, pz5, E5, c, dom);
 }
 
+// ---- SolvePz for the one-basic-block loop node: the same t22 / t29 chains with every power-of-two factor folded --------
+// Multiplying by 2, 4, 8 or 1/2 is exact in binary floating point (no overflow / underflow at these magnitudes), so
+// fl(fl(a b) 2) = fl(a (2 b)): the factors 2.0 / 4.0 / 8.0 / (1/2) of the reference's terms ride on a loop invariant
+// (2 m^2, 2 s, 2 sqrt(s) ...) or on one per-node value shared by several terms (4 E5, 2 E5^2, 2 pz5^2).  Every term and
+// the summation order are unchanged, so p1z comes out bit-identical (pinned by tests/test_fastmath.py on 2^22 argument
+// sets) with ~30 fewer fp64 instructions per node.  PzInv = the per-point invariants.
+struct PzInv {
+  double m3sq, m4sq, m3sq_x2, m4sq_x2, m3q, m4q;  // m^2, 2 m^2, m^4
+  double k_s3, k_s4, k_34;                        // s m3^2 2, s m4^2 2 (A: s m3^2 4), m3^2 m4^2 2
+  double s, s_x2, rs, rs_x2, s15, ssq;            // s, 2 s, sqrt s, 2 sqrt s, s^(3/2), s^2
+};
+__device__ __forceinline__ PzInv make_pz_inv(double m3, double m4, const PzConst &c, bool same) {
+  PzInv I;
+  I.s = c.s; I.s_x2 = 2.0 * c.s; I.rs = c.t7; I.rs_x2 = 2.0 * c.t7; I.s15 = c.t9; I.ssq = c.t14;
+  I.m3sq = m3 * m3; I.m4sq = m4 * m4; I.m3sq_x2 = 2.0 * I.m3sq; I.m4sq_x2 = 2.0 * I.m4sq;
+  I.m3q = I.m3sq * I.m3sq; I.m4q = I.m4sq * I.m4sq;
+  I.k_s3 = same ? c.s * I.m3sq * 4.0 : c.s * I.m3sq * 2.0;
+  I.k_s4 = c.s * I.m4sq * 2.0;
+  I.k_34 = I.m3sq * I.m4sq * 2.0;
+  return I;
+}
+__device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+  const double t2 = E5 * E5, t3 = pt3 * pt3, t4 = pt4 * pt4, t5 = pz5 * pz5, t6 = I.m3sq;
+  const double E4 = 4.0 * E5, t2x2 = 2.0 * t2, t5x2 = 2.0 * t5, t6x4 = 2.0 * I.m3sq_x2;
+  const double t8  = I.s * t2 * 6.0;
+  const double t10 = t2 * t2, t11 = t3 * t3, t12 = t4 * t4, t13 = t5 * t5;
+  const double t15 = t5 * t6x4;                 // t5 t6 4
+  const double t16 = t3 * t5x2, t17 = t4 * t5x2;  // t3 t5 2, t4 t5 2
+  const double t18 = E4 * I.m3sq_x2 * I.rs;     // E5 t6 t7 8
+  const double t19 = E4 * t3 * I.rs, t20 = E4 * t4 * I.rs, t21 = E4 * t5 * I.rs;
+  const double t22 = t8 + t10 + t11 + t12 + t13 + I.ssq + t15 + t16 + t17 + t18 + t19 + t20 + t21 -
+                     E4 * I.s15 - I.s_x2 * t3 - I.s_x2 * t4 - I.s_x2 * t5 - I.k_s3 -
+                     t2x2 * t3 - t2x2 * t4 - t2x2 * t5 - t3 * t4 * 2.0 - t2 * t6x4 -
+                     E4 * t2 * I.rs;
+  dom = dom && sqrt_fast_ok(t22);
+  const double t23h = 0.5 * sqrt_fast_core(t22);
+  const double pz5h = 0.5 * pz5;
+  const double num = E5 * t23h - I.rs * t23h + pz5h * (t3 - t4);
+  const double den = I.s + t2 - t5 - E5 * I.rs_x2;
+  const double q   = div_fast_core(num, den);
+  dom = dom && div_fast_ok(num, q);
+  return -pz5h - q;
+}
+__device__ __forceinline__ double solve_pz3_B_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+  const double t2 = E5 * E5, t3 = I.m3sq, t4 = I.m4sq, t5 = pt3 * pt3, t6 = pt4 * pt4, t7 = pz5 * pz5;
+  const double E4 = 4.0 * E5, t2x2 = 2.0 * t2, t7x2 = 2.0 * t7;
+  const double t9  = I.s * t2 * 6.0;
+  const double t11 = t2 * t2, t14 = t5 * t5, t15 = t6 * t6, t16 = t7 * t7;
+  const double t18 = I.m3sq_x2 * t5, t19 = I.m4sq_x2 * t6, t20 = I.m3sq_x2 * t7, t21 = I.m4sq_x2 * t7;
+  const double t22 = t5 * t7x2, t23 = t6 * t7x2;
+  const double t24 = E4 * t3 * I.rs, t25 = E4 * t4 * I.rs, t26 = E4 * t5 * I.rs, t27 = E4 * t6 * I.rs, t28 = E4 * t7 * I.rs;
+  const double t29 = t9 + t11 + I.m3q + I.m4q + t14 + t15 + t16 + I.ssq + t18 + t19 + t20 + t21 + t22 + t23 +
+                     t24 + t25 + t26 + t27 + t28 - E4 * I.s15 - I.k_s3 - I.k_s4 -
+                     I.s_x2 * t5 - I.s_x2 * t6 - I.s_x2 * t7 - t2 * I.m3sq_x2 - t2 * I.m4sq_x2 -
+                     t2x2 * t5 - I.k_34 - t2x2 * t6 - t2x2 * t7 - I.m3sq_x2 * t6 -
+                     I.m4sq_x2 * t5 - t5 * t6 * 2.0 - E4 * t2 * I.rs;
+  dom = dom && sqrt_fast_ok(t29);
+  const double t30h = 0.5 * sqrt_fast_core(t29);
+  const double pz5h = 0.5 * pz5;
+  const double num = E5 * t30h - I.rs * t30h + pz5h * (t3 - t4 + t5 - t6);
+  const double den = I.s + t2 - t7 - E5 * I.rs_x2;
+  const double q   = div_fast_core(num, den);
+  dom = dom && div_fast_ok(num, q);
+  return -pz5h - q;
+}
+
 __device__ __forceinline__ double solve_pz(double m3, double m4, double pt3, double pt4, double pz5,
                                            double E5, const PzConst &c) {  // MKinematics.h:220-229
   if (fabs(m3 - m4) < 1e-9) return solve_pz3_A(m3, pt3, pt4, pz5, E5, c);

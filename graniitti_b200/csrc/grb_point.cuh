@@ -788,21 +788,23 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
 // the node on the checked path.  Same expressions in the same order as the checked path: identical bits when the guards
 // hold.  FF = PARAM_REGGE::offshellFF resolved at compile time.
 template <bool SAME, int FF>
-__device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzConst &pc, double ktx, double kty, bool &valid, cx &A) {
+__device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
   const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
-  const double a1s = fmax(0.0, n1x * n1x + n1y * n1y), a2s = fmax(0.0, n2x * n2x + n2y * n2y), aXs = fmax(0.0, L.mXsq + (Xx * Xx + Xy * Xy));
+  // msqrt's clamp max(0, .) is dropped on this path: every radicand is a sum of squares (>= 0, or NaN -- and a NaN
+  // fails the range guard, which sends the node to the checked path)
+  const double a1s = n1x * n1x + n1y * n1y, a2s = n2x * n2x + n2y * n2y, aXs = L.mXsq + (Xx * Xx + Xy * Xy);
   bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(aXs));
   const double pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s), mtX = sqrt_fast_core(aXs);
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   valid = !(Xe > L.emax);
   bool         dom = true;
-  const double p1z = SAME ? solve_pz3_A_t<true>(L.m1, pt1, pt2, Xz, Xe, pc, dom) : solve_pz3_B_t<true>(L.m1, L.m2, pt1, pt2, Xz, Xe, pc, dom);
+  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, dom);
   redo = redo || (valid && !dom);
   const double p2z = -(Xz + p1z);
   valid = valid && !(isnan(p1z) || p1z < 0 || p2z > 0);
-  const double e1s = fmax(0.0, L.m1sq + pow2(pt1) + pow2(p1z)), e2s = fmax(0.0, L.m2sq + pow2(pt2) + pow2(p2z));
+  const double e1s = L.m1sq + pow2(pt1) + pow2(p1z), e2s = L.m2sq + pow2(pt2) + pow2(p2z);
   redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
   const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
   valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
@@ -861,6 +863,7 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
   const DevLoop &Q = c_loop;
   PzConst        pc;
   pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  const PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
   double Ire = 0.0, Iim = 0.0;
   for (int i = 0; i < Q.nphi_nodes; ++i) {
     const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
@@ -869,10 +872,11 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
       const double kt = Q.kt[j];
       bool         valid;
       cx           A;
-      if (__builtin_expect(regge_node_fast<SAME, FF>(L, pc, kt * cp, kt * sp, valid, A), 0)) valid = regge_node_checked<SAME>(L, pc, kt * cp, kt * sp, A);
-      const double ar = valid ? A.re : 0.0, ai = valid ? A.im : 0.0;  // rejected nodes contribute 0, keep their weight
-      Jre = fma(Q.b_re[j], ar, fma(-Q.b_im[j], ai, Jre));
-      Jim = fma(Q.b_re[j], ai, fma(Q.b_im[j], ar, Jim));
+      if (__builtin_expect(regge_node_fast<SAME, FF>(L, pzi, kt * cp, kt * sp, valid, A), 0)) valid = regge_node_checked<SAME>(L, pc, kt * cp, kt * sp, A);
+      if (valid) {  // rejected nodes contribute 0 but keep their Simpson weight (predicated, no branch)
+        Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
+        Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
+      }
     }
     Ire = fma(wi, Jre, Ire);
     Iim = fma(wi, Jim, Iim);

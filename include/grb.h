@@ -367,7 +367,8 @@ int grb_measure_dfma_peak(int device, double *tflops_out);
 
 /* Unit-test hook for graniitti_b200/csrc/grb_fastmath.cuh on n host values: kind 0 table-driven log, 1 table-driven
  * exp, 2 branch-free exact sqrt, 3 sqrt(), 4 branch-free exact x[i] / x[i+1], 5 operator/ (3 and 5 are the device's
- * own IEEE results the exact forms must reproduce bit for bit), 6 / 7 table-driven sin / cos.            */
+ * own IEEE results the exact forms must reproduce bit for bit), 6 / 7 table-driven sin / cos,
+ * 8 / 10 SolvePz3_A / _B in the reference's order, 9 / 11 their power-of-two-folded forms (must agree bit for bit). */
 int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y);
 
 /* Device time in ms of the kernels launched by the last grb_eval / grb_vegas_iterate call (CUDA events on

@@ -45,6 +45,10 @@ struct grb_engine {
   // scratch for host-pointer callers
   void * d_scratch     = nullptr;
   size_t scratch_bytes = 0;
+  // grb_eval with host buffers: copy-in / compute / copy-out pipeline over slices of the batch
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;
+  cudaEvent_t  ev_in = nullptr, ev_done = nullptr;
+  int64_t      host_slice = 0;
   // NCCL communicator (optional, loaded at run time)
   void *nccl_comm = nullptr;
   int   comm_rank = 0, comm_size = 1;
@@ -387,8 +391,14 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
   if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", ce);
   cudaEventCreate(&e->ev0);
   cudaEventCreate(&e->ev1);
+  if ((ce = cudaStreamCreateWithFlags(&e->stream_in, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", ce);
+  if ((ce = cudaStreamCreateWithFlags(&e->stream_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", ce);
+  cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming);
   const char *env = getenv("GRB_CHUNK");
   e->chunk        = env ? std::max<int64_t>(1024, atoll(env)) : (int64_t)1 << 23;
+  const char *hs  = getenv("GRB_HOST_SLICE");  // points per pipeline slice of grb_eval with host buffers
+  e->host_slice   = hs ? std::max<int64_t>(1024, atoll(hs)) : (int64_t)1 << 20;
   if (desc->screening) {
     if ((ce = cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk)) != cudaSuccess) return fail("cudaMalloc items", ce);
     if ((ce = cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
@@ -436,6 +446,10 @@ void grb_destroy(grb_engine *e) {
   for (auto ev : e->evk) cudaEventDestroy(ev);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream_in) cudaStreamDestroy(e->stream_in);
+  if (e->stream_out) cudaStreamDestroy(e->stream_out);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_done) cudaEventDestroy(e->ev_done);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -535,8 +549,6 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
   if (!dev_in) {
     du = (double *)sp; sp += b_u;
     dt = dtape ? (double *)sp : nullptr; sp += b_t;
-    CK(cudaMemcpyAsync((void *)du, u, b_u, cudaMemcpyHostToDevice, e->stream));
-    if (dtape) CK(cudaMemcpyAsync((void *)dt, tape, b_t, cudaMemcpyHostToDevice, e->stream));
   }
   if (!dev_out) {
     dw = (double *)sp; sp += b_w;
@@ -547,33 +559,49 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
   if (rc != GRB_OK) return rc;
   e->last_launches = 0;
   e->n_evk = 0;
+  // Host buffers are pipelined: slice k+1 is copied in (stream_in) and slice k-1 copied out (stream_out, the other DMA
+  // engine) while slice k computes.  The SoA rows keep their leading dimension n on the device, so a slice is a 2-D copy
+  // of `len` columns.  Device-resident callers run whole chunks on the compute stream as before.
+  const bool    staged = !dev_in || !dev_out;
+  const int64_t step   = staged ? std::min<int64_t>(e->chunk, e->host_slice) : e->chunk;
+  const size_t  pitch  = sizeof(double) * (size_t)n;
   CK(cudaEventRecord(e->ev0, e->stream));
-  for (int64_t off = 0; off < n; off += e->chunk) {
+  for (int64_t off = 0; off < n; off += step) {
+    const int64_t len = std::min<int64_t>(step, n - off);
+    if (!dev_in) {
+      CK(cudaMemcpy2DAsync((void *)(du + off), pitch, u + off, pitch, sizeof(double) * len, dim, cudaMemcpyHostToDevice, e->stream_in));
+      if (dtape) CK(cudaMemcpy2DAsync((void *)(dt + off), pitch, tape + off, pitch, sizeof(double) * len, dtape, cudaMemcpyHostToDevice, e->stream_in));
+      CK(cudaEventRecord(e->ev_in, e->stream_in));
+      CK(cudaStreamWaitEvent(e->stream, e->ev_in, 0));
+    }
     PointArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = std::min<int64_t>(e->chunk, n - off);
+    a.n = len;
     a.u = du + off; a.tape = dt ? dt + off : nullptr; a.ld = n; a.dim = dim; a.dtape = dtape;
     a.vegas = 0; a.bins = 0;
     a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 2 * sizeof(unsigned int), e->stream));
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
       e->last_launches += launch_screen(a, e->dproc.amp_kind, regge_fast_ff(e->dproc), e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
     }
+    if (!dev_out) {
+      CK(cudaEventRecord(e->ev_done, e->stream));
+      CK(cudaStreamWaitEvent(e->stream_out, e->ev_done, 0));
+      CK(cudaMemcpyAsync(w + off, dw + off, sizeof(double) * len, cudaMemcpyDeviceToHost, e->stream_out));
+      CK(cudaMemcpyAsync(flags + off, df + off, (size_t)len, cudaMemcpyDeviceToHost, e->stream_out));
+      if (dump) CK(cudaMemcpy2DAsync(dump + off, pitch, dd + off, pitch, sizeof(double) * len, GRB_DUMP_LEN, cudaMemcpyDeviceToHost, e->stream_out));
+    }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   e->timed = true;
   CK(cudaGetLastError());
-  if (!dev_out) {
-    CK(cudaMemcpyAsync(w, dw, b_w, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(flags, df, n, cudaMemcpyDeviceToHost, e->stream));
-    if (dump) CK(cudaMemcpyAsync(dump, dd, b_d, cudaMemcpyDeviceToHost, e->stream));
-  }
   CK(cudaStreamSynchronize(e->stream));
+  if (!dev_out) CK(cudaStreamSynchronize(e->stream_out));
   return GRB_OK;
 }
 
@@ -612,7 +640,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.ev_out = e->d_ev; a.ev_count = e->d_ev_count; a.ev_cap = e->ev_cap; a.npart = npart; a.pay = e->d_pay;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 2 * sizeof(unsigned int), e->stream));
+    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));

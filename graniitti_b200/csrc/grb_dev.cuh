@@ -288,7 +288,7 @@ __device__ __forceinline__ PzInv make_pz_inv(double m3, double m4, const PzConst
   return I;
 }
 __device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
-  const double t2 = E5 * E5, t3 = pt3 * pt3, t4 = pt4 * pt4, t5 = pz5 * pz5, t6 = I.m3sq;
+  const double t2 = E5 * E5, t3 = pt3 * pt3, t4 = pt4 * pt4, t5 = pz5 * pz5;  // t6 = m3^2 rides in I.m3sq_x2, I.k_s3
   const double E4 = 4.0 * E5, t2x2 = 2.0 * t2, t5x2 = 2.0 * t5, t6x4 = 2.0 * I.m3sq_x2;
   const double t8  = I.s * t2 * 6.0;
   const double t10 = t2 * t2, t11 = t3 * t3, t12 = t4 * t4, t13 = t5 * t5;

@@ -58,12 +58,25 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
 template <int MINB, int AMP, int FF>
 __global__ void __launch_bounds__(128, MINB) k_screen(const PointArgs a) {
   const int64_t nA = min((int64_t)a.item_count[0], a.item_cap), nB = min((int64_t)a.item_count[1], a.item_cap - nA);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // class A occupies slots [0, nA), class B slots [cap - nB, cap); each loop is branch-uniform.  The B loop starts
-  // where the A loop's last sweep left idle threads (rotation by nA) to balance the persistent grid.
-  for (int64_t t = t0; t < nA; t += stride) screen_item<AMP, true, FF>(a, t);
-  const int64_t rot = (stride - (nA % stride)) % stride;
-  for (int64_t t = (t0 + rot) % stride; t < nB; t += stride) screen_item<AMP, false, FF>(a, a.item_cap - nB + t);
+  // class A occupies slots [0, nA), class B slots [cap - nB, cap).  Work is handed out in tiles of 32 consecutive items
+  // of one class (one warp, branch-uniform, coalesced) from a global tile counter (item_count[2], zeroed with the list):
+  // the persistent grid stays balanced for any list length -- a static stride loop wastes up to one item per thread,
+  // 11 % of a launch at 2^20 points -- and the unequal-mass class (more instructions per node) is started first.
+  const unsigned tilesA = (unsigned)((nA + 31) >> 5), tilesB = (unsigned)((nB + 31) >> 5);
+  const int      lane   = threadIdx.x & 31;
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&a.item_count[2], 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= tilesA + tilesB) break;
+    if (t < tilesB) {
+      const int64_t i = ((int64_t)t << 5) + lane;
+      if (i < nB) screen_item<AMP, false, FF>(a, a.item_cap - nB + i);
+    } else {
+      const int64_t i = ((int64_t)(t - tilesB) << 5) + lane;
+      if (i < nA) screen_item<AMP, true, FF>(a, i);
+    }
+  }
 }
 
 // weight assembly + outputs + VEGAS accumulation for the screened work list

@@ -3,7 +3,7 @@
 The layout is checked against the compiled library by `grb_abi_sizeof` (tests/test_abi.py)."""
 import ctypes as C
 
-GRB_ABI_VERSION = 1
+GRB_ABI_VERSION = 2
 GRB_MAX_NODES = 16
 GRB_MAX_RES = 12
 GRB_MAX_VETO = 8
@@ -37,7 +37,7 @@ class Node(C.Structure):
 
 class GenCut(C.Structure):
     _fields_ = [(k, f64) for k in ("Y_min", "Y_max", "M_min", "M_max", "forward_pt_min", "forward_pt_max",
-                                   "XI_min", "XI_max")]
+                                   "XI_min", "XI_max", "kt_min", "kt_max", "rap_min", "rap_max")]
 
 
 class FidCut(C.Structure):

@@ -549,7 +549,7 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     throw std::invalid_argument("MProcess::SetProcess: Unknown PROCESS: " + ps);
   const std::string istate = ps.substr(0, lb), channel = ps.substr(lb + 1, rb - lb - 1), cls = ps.substr(la + 1, ra - la - 1);
   if (cls == "F") d.ps_class = GRB_CLASS_F;
-  else if (cls == "C") throw Unsupported("phase-space class <C> (MContinuum) is not on the device path yet");
+  else if (cls == "C") d.ps_class = GRB_CLASS_C;
   else throw Unsupported("phase-space class <" + cls + "> is outside the hot-path scope");
   const std::string key = istate + "[" + channel + "]";
   static const std::map<std::string, int> registry = {
@@ -629,6 +629,24 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     grb_gencut &g = d.gcuts;
     g.forward_pt_min = -1.0; g.forward_pt_max = -1.0; g.XI_min = 0.0; g.XI_max = 0.05;
     const Json &gc = card.at("GENCUTS");
+    g.kt_min = 0.0; g.kt_max = -1.0; g.rap_min = 0.0; g.rap_max = 0.0;
+    if (d.ps_class == GRB_CLASS_C) {  // reference src/MGraniitti.cc:688-745 + MContinuum::post_Constructor (src/MContinuum.cc:64-91)
+      if (!gc.has("<C>") || !gc.at("<C>").has("Rap"))
+        throw std::invalid_argument("MGraniitti::ReadGenCuts: <C> phase space class requires from user: \"GENCUTS\" : { \"<C>\" : { \"Rap\" : [min, max] }}");
+      const Json &Cc = gc.at("<C>");
+      range2(Cc.at("Rap"), "GENCUTS::<C>::Rap", g.rap_min, g.rap_max);
+      if (Cc.has("Kt")) range2(Cc.at("Kt"), "GENCUTS::<C>::Kt", g.kt_min, g.kt_max);
+      if (Cc.has("Pt")) range2(Cc.at("Pt"), "GENCUTS::<C>::Pt", g.forward_pt_min, g.forward_pt_max);
+      if (Cc.has("Xi")) range2(Cc.at("Xi"), "GENCUTS::<C>::Xi", g.XI_min, g.XI_max);
+      g.Y_min = g.Y_max = g.M_min = g.M_max = 0.0;
+      if (g.forward_pt_min < 0.0) g.forward_pt_min = 0.0;
+      if (g.forward_pt_max < 0.0) g.forward_pt_max = d.excitation == 0 ? 2.5 : (d.excitation == 1 ? 50.0 : 100.0);
+      if (g.kt_max < 0.0) {
+        g.kt_min = 0.0;
+        g.kt_max = 10.0 / d.n_legs;
+        if (istate != "PP" && istate != "yP" && istate != "OP") g.kt_max = d.sqrt_s / 2.0;
+      }
+    } else {
     if (!gc.has("<F>") || !gc.at("<F>").has("Rap") || !gc.at("<F>").has("M"))
       throw std::invalid_argument("MGraniitti::ReadGenCuts: <F> phase space class requires from user: \"GENCUTS\" : { \"<F>\" : { \"Rap\" : [min, max], \"M\" : [min, max] }}");
     const Json &F = gc.at("<F>");
@@ -638,8 +656,10 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     if (F.has("Xi")) range2(F.at("Xi"), "GENCUTS::<F>::Xi", g.XI_min, g.XI_max);
     if (g.forward_pt_min < 0.0) g.forward_pt_min = 0.0;                                       // MProcess.cc:1369-1386
     if (g.forward_pt_max < 0.0) g.forward_pt_max = d.excitation == 0 ? 2.5 : (d.excitation == 1 ? 50.0 : 100.0);
+    }
   }
-  d.lipsdim = 5 + 1 + d.excitation;  // MFactorized.cc:69-78
+  d.lipsdim = d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 + d.excitation  // MContinuum.cc:86-90
+                                        : 5 + 1 + d.excitation;                 // MFactorized.cc:69-78
 
   // FIDCUTS (reference MGraniitti::ReadFidCuts, src/MGraniitti.cc:826-907); defaults of gra::FIDCUT
   {

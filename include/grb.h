@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GRB_ABI_VERSION 1
+#define GRB_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------------------------- */
 enum {
@@ -62,7 +62,7 @@ enum {
   GRB_PROC_PP_RES_CON   = 17  /* "PP[RES+CON]"   PROC_17 :399            ME4 + sum of ME3/PhotoME3         */
 };
 
-/* phase-space class: "<F>" MFactorized (all BASELINE configs) */
+/* phase-space class: "<F>" MFactorized (all BASELINE configs), "<C>" MContinuum (2 -> 4 direct)  */
 enum { GRB_CLASS_F = 0, GRB_CLASS_C = 1 };
 
 /* flag bits of one evaluated point = AuxIntData of the reference (include/Graniitti/MProcess.h:37-52) */
@@ -94,6 +94,8 @@ typedef struct {
   double M_min, M_max;                   /* GENCUTS.<F>.M                                               */
   double forward_pt_min, forward_pt_max; /* after SetTechnicalBoundaries (MProcess.cc:1369-1386)        */
   double XI_min, XI_max;
+  double kt_min, kt_max;                 /* GENCUTS.<C>.Kt (default [0, 10 / n_legs], MContinuum.cc:70-84)  */
+  double rap_min, rap_max;               /* GENCUTS.<C>.Rap: rapidity of each central leg                   */
 } grb_gencut;
 
 typedef struct {
@@ -152,7 +154,7 @@ typedef struct {
 
 typedef struct {
   int32_t abi_version;
-  int32_t ps_class;   /* GRB_CLASS_F                                                                     */
+  int32_t ps_class;   /* GRB_CLASS_F | GRB_CLASS_C                                                       */
   int32_t proc;       /* GRB_PROC_*                                                                      */
   int32_t screening;  /* POMLOOP                                                                         */
   int32_t excitation; /* NSTARS (0 only on the device path)                                              */

@@ -74,6 +74,7 @@ typedef struct {
   double s1, s2, t1, t2, t_hat, u_hat, m2, Y, Pt, x1, x2, qt1, qt2;
   v4     q1, q2;
   double M_MIN, M_MAX, DW;
+  v4     pkt; /* <C>: intermediate 'difference momentum' q0 (MContinuum::pkt_) */
   cx     hamp[GRB_MAX_HAMP];
   int    nhamp;
   /* tape of internal uniforms (reference: thread-local MRandom, src/MRandom.cc:62-65) */
@@ -404,6 +405,120 @@ static int loop_kinematics(ost *S, double p1px, double p1py, double p2px, double
   S->pfinal[1].e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
   S->pfinal[2].z = p2z;
   S->pfinal[2].e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  if (!check_emc(v4_sub(S->beamsum, v4_add(v4_add(S->pfinal[1], S->pfinal[2]), S->pfinal[0])))) return 0;
+  return lorentz_scalars(S, d->n_legs + 2);
+}
+
+/* ---- <C> phase-space class: MContinuum, 2 -> N direct (restated for N = 4, two central legs) ---------------------- */
+
+/* reference src/MContinuum.cc:438-538 BLinearSystem for Kf = 2: p = A b with A = diag(1/2, 1/2), b0 = q0 - (p1+p2),
+ * b1 = -q0 - (p1+p2); the loop adds b[j] * A[i][j] for both j (the zero entries add signed zeros) */
+static void blinear2(v4 q0, v4 p1f, v4 p2f, v4 p[2]) {
+  const v4 w  = v4_add(p1f, p2f);
+  const v4 b0 = v4_sub(q0, w);
+  const v4 b1 = v4_sub((v4){q0.x * (-1.0), q0.y * (-1.0), q0.z * (-1.0), q0.e * (-1.0)}, w);
+  const double A[2][2] = {{1.0 / 2.0, 0.0}, {0.0, 1.0 / 2.0}};
+  for (int i = 0; i < 2; ++i) {
+    v4 acc = {0, 0, 0, 0};
+    acc = v4_add(acc, (v4){b0.x * A[i][0], b0.y * A[i][0], b0.z * A[i][0], b0.e * A[i][0]});
+    acc = v4_add(acc, (v4){b1.x * A[i][1], b1.y * A[i][1], b1.z * A[i][1], b1.e * A[i][1]});
+    p[i] = acc;
+  }
+}
+
+/* reference src/MContinuum.cc:334-435 BNBuildKin (symmetric beams, no forward excitation, veto cuts inactive) */
+static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2, double kt, double phik,
+                        const double y[2], double m1, double m2) {
+  const grb_process_desc *d = S->d;
+  v4 p1 = {pt1 * cos(phi1), pt1 * sin(phi1), 0, 0};
+  v4 p2 = {pt2 * cos(phi2), pt2 * sin(phi2), 0, 0};
+  S->pkt = (v4){kt * cos(phik), kt * sin(phik), 0, 0};
+  v4 p[2];
+  blinear2(S->pkt, p1, p2, p);
+  v4 sumP = {0, 0, 0, 0};
+  for (int i = 0; i < 2; ++i) {
+    const double m  = S->node_moff[i];
+    const double mt = msqrt(pow2(m) + v4_pt2(p[i]));
+    p[i].z = mt * sinh(y[i]);
+    p[i].e = mt * cosh(y[i]);
+    sumP = v4_add(sumP, p[i]);
+  }
+  if (sumP.e > d->sqrt_s) return 0;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, sumP.z, sumP.e, d->s);
+  const double p2z = -(sumP.z + p1z);
+  if (p1z < 0 || p2z > 0) return 0;
+  if (isnan(p1z)) return 0; /* see b51_build_kin */
+  p1.z = p1z;
+  p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  p2.z = p2z;
+  p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  S->pfinal[1] = p1;
+  S->pfinal[2] = p2;
+  S->pfinal[0] = sumP;
+  double sumM = 0;
+  for (int i = 0; i < 2; ++i) {
+    S->node_p4[i]    = p[i];
+    S->pfinal[i + 3] = p[i];
+    sumM += v4_m(p[i]);
+  }
+  if (v4_m(sumP) < sumM) return 0;
+  if (!check_emc(v4_sub(S->beamsum, v4_add(v4_add(S->pfinal[1], S->pfinal[2]), S->pfinal[0])))) return 0;
+  for (int i = 0; i < d->n_legs; ++i)
+    if (!construct_decay(S, i)) return 0;
+  return lorentz_scalars(S, d->n_legs + 2);
+}
+
+/* reference src/MContinuum.cc:276-331 BNRandomKin, Kf = 2: r = [pt1, pt2, phi1, phi2, kt, phi_k, y3, y4] */
+static int bn_random_kin(ost *S, const double *r) {
+  const grb_process_desc *d  = S->d;
+  const grb_gencut *      gc = &d->gcuts;
+  const double u1 = log(gc->forward_pt_min + O_ZERO_EPS) +
+                    (log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS)) * r[0];
+  const double u2 = log(gc->forward_pt_min + O_ZERO_EPS) +
+                    (log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS)) * r[1];
+  const double pt1 = exp(u1), pt2 = exp(u2);
+  const double phi1 = 2.0 * O_PI * r[2], phi2 = 2.0 * O_PI * r[3];
+  for (int i = 0; i < d->n_legs; ++i) S->node_moff[i] = offshell_mass(S, i);
+  const double kt   = gc->kt_min + (gc->kt_max - gc->kt_min) * r[4];
+  const double phik = 2.0 * O_PI * r[5];
+  const double y[2] = {gc->rap_min + (gc->rap_max - gc->rap_min) * r[6], gc->rap_min + (gc->rap_max - gc->rap_min) * r[7]};
+  return bn_build_kin(S, pt1, pt2, phi1, phi2, kt, phik, y, d->beam1_mass, d->beam2_mass);
+}
+
+/* reference src/MContinuum.cc:94-161 LoopKinematics: the central legs ARE updated here (lts.pfinal[3..]) -- but not
+ * lts.decaytree[i].p4, which t_hat / u_hat and the tensor-pomeron vertices keep reading */
+static int loop_kinematics_C(ost *S, double p1px, double p1py, double p2px, double p2py) {
+  const grb_process_desc *d = S->d;
+  S->pfinal[1].x = p1px;
+  S->pfinal[1].y = p1py;
+  S->pfinal[2].x = p2px;
+  S->pfinal[2].y = p2py;
+  v4 p[2];
+  blinear2(S->pkt, S->pfinal[1], S->pfinal[2], p);
+  v4 sumP = {0, 0, 0, 0};
+  for (int i = 0; i < 2; ++i) {
+    const double y = v4_rap(S->pfinal_orig[i + 3]);
+    const double m = v4_m(S->pfinal_orig[i + 3]);
+    S->pfinal[i + 3].x = p[i].x;
+    S->pfinal[i + 3].y = p[i].y;
+    const double mt = msqrt(pow2(m) + v4_pt2(S->pfinal[i + 3]));
+    S->pfinal[i + 3].z = mt * sinh(y);
+    S->pfinal[i + 3].e = mt * cosh(y);
+    sumP = v4_add(sumP, S->pfinal[i + 3]);
+  }
+  const double pt1 = v4_pt(S->pfinal[1]);
+  const double pt2 = v4_pt(S->pfinal[2]);
+  const double m1  = v4_m(S->pfinal_orig[1]);
+  const double m2  = v4_m(S->pfinal_orig[2]);
+  const double p1z = solve_pz(m1, m2, pt1, pt2, sumP.z, sumP.e, d->s);
+  const double p2z = -(sumP.z + p1z);
+  if (isnan(p1z)) return 0;
+  if (p1z < 0 || p2z > 0) return 0;
+  S->pfinal[1].z = p1z;
+  S->pfinal[1].e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  S->pfinal[2].z = p2z;
+  S->pfinal[2].e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  S->pfinal[0] = sumP;
   if (!check_emc(v4_sub(S->beamsum, v4_add(v4_add(S->pfinal[1], S->pfinal[2]), S->pfinal[0])))) return 0;
   return lorentz_scalars(S, d->n_legs + 2);
 }
@@ -1773,7 +1888,7 @@ static double screened_amp2(ost *S) {
       const cx     A_eik = interpolate1d(S->eik, kt2);
       const double ktx = kt * cos(phi), kty = kt * sin(phi);
       const double Wij = simpson38_w(i, NPHI) * simpson38_w(j, NKT);
-      if (!loop_kinematics(S, p1T[0] - ktx, p1T[1] - kty, p2T[0] + ktx, p2T[1] + kty)) {
+      if (!(d->ps_class == GRB_CLASS_C ? loop_kinematics_C : loop_kinematics)(S, p1T[0] - ktx, p1T[1] - kty, p2T[0] + ktx, p2T[1] + kty)) {
         for (int h = 0; h < nh; ++h) { I[h].re += Wij * 0.0; I[h].im += Wij * 0.0; }
         continue;
       }
@@ -1790,7 +1905,7 @@ static double screened_amp2(ost *S) {
   const cx norm = {0.0 / (8.0 * (O_PI * O_PI) * d->s), 1.0 / (8.0 * (O_PI * O_PI) * d->s)};
   cx       hamp_loop[GRB_MAX_HAMP];
   for (int h = 0; h < nh; ++h) hamp_loop[h] = cx_mul(norm, cx_scale(I[h], scale));
-  loop_kinematics(S, p1T[0], p1T[1], p2T[0], p2T[1]);
+  (d->ps_class == GRB_CLASS_C ? loop_kinematics_C : loop_kinematics)(S, p1T[0], p1T[1], p2T[0], p2T[1]);
   double amp2 = 0.0;
   for (int h = 0; h < nh; ++h) amp2 += cx_abs2(cx_add(hamp_0[h], hamp_loop[h]));
   if (nh != 1) amp2 /= 4;
@@ -1819,14 +1934,40 @@ static double b51_integral_volume(const ost *S) {
   return (pow2(S->M_MAX) - pow2(S->M_MIN)) * (gc->Y_max - gc->Y_min) * fv;
 }
 
-/* reference src/MFactorized.cc:142-184 EventWeight */
+/* reference src/MContinuum.cc:639-658 BNPhaseSpaceWeight, :619-637 BNIntegralVolume (Kf = 2, Nf = 4) */
+static double bn_ps_weight(const ost *S) {
+  const double J = 1.0 / fabs(S->pfinal[1].z / S->pfinal[1].e - S->pfinal[2].z / S->pfinal[2].e);
+  const int    Nf   = S->d->n_legs + 2;
+  double       PROD = 1.0;
+  PROD *= v4_pt(S->pkt);
+  return (1.0 / pow(2, 2 * (Nf - 2))) * (1.0 / pow(2.0 * O_PI, 3 * Nf - 4)) * (v4_pt(S->pfinal[1]) / (2.0 * S->pfinal[1].e)) *
+         (v4_pt(S->pfinal[2]) / (2.0 * S->pfinal[2].e)) * J * PROD;
+}
+static double bn_integral_volume(const ost *S) {
+  const grb_gencut *gc      = &S->d->gcuts;
+  const int         Kf      = S->d->n_legs;
+  const double      PHI_vol = pow2(2.0 * O_PI);
+  const double      J_pt    = v4_pt(S->pfinal[1]) * v4_pt(S->pfinal[2]);
+  const double      PT_vol  = J_pt * pow2(log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS));
+  const double      fv      = PHI_vol * PT_vol;
+  double            KT_vol  = pow(gc->kt_max - gc->kt_min, Kf - 1);
+  KT_vol *= pow(2.0 * O_PI, Kf - 1);
+  KT_vol *= pow(gc->rap_max - gc->rap_min, Kf);
+  return KT_vol * fv;
+}
+
+/* reference src/MFactorized.cc:142-184 EventWeight; src/MContinuum.cc:164-193 for the <C> class */
 static double event_weight(ost *S, const double *u, uint8_t *flags) {
   const grb_process_desc *d = S->d;
   double                  W = 0.0;
-  const int kin  = b51_random_kin(S, u);
+  const int kin  = d->ps_class == GRB_CLASS_C ? bn_random_kin(S, u) : b51_random_kin(S, u);
   const int fid  = common_cuts(S);
   const int veto = veto_cuts(S);
-  if (kin && fid && veto) {
+  if (kin && fid && veto && d->ps_class == GRB_CLASS_C) {
+    const double MatESQ = screened_amp2(S);
+    /* CascadePS() == 1 (no amplitude on the path activates a cascade phase space) */
+    W = 1.0 * (1.0 / d->S_factor) * bn_ps_weight(S) * bn_integral_volume(S) * MatESQ * O_GeV2barn / (2.0 * d->s);
+  } else if (kin && fid && veto) {
     const double MatESQ  = screened_amp2(S);
     double       C_space = 1.0;
     if (d->n_legs != 0 && d->ps_active) {
@@ -1852,7 +1993,8 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
                     int32_t *tape_used) {
   if (!d || !u || !w || !flags) return GRB_ERR_ARG;
-  if (d->ps_class != GRB_CLASS_F || d->excitation != 0 || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
+  if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->excitation != 0 || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
+  if (d->ps_class == GRB_CLASS_C && d->n_legs != 2) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
   if (dim < d->lipsdim) return GRB_ERR_ARG;
   ost *S = (ost *)calloc(1, sizeof(ost));

@@ -23,6 +23,7 @@ GRB_FLAG_KIN, GRB_FLAG_FID, GRB_FLAG_VETO, GRB_FLAG_AMP = 1, 2, 4, 8
 GRB_FLAGS_VALID = 7
 
 GRB_MODE_BURNIN, GRB_MODE_INTEGRATE, GRB_MODE_GENERATE = 0, 1, 2
+GRB_CLASS_F, GRB_CLASS_C = 0, 1
 
 DUMP_NAMES = ["t1", "t2", "s1", "s2", "m2", "Y", "Pt", "t_hat", "u_hat", "amp2", "hamp0_re", "hamp0_im"]
 GRB_DUMP_LEN = len(DUMP_NAMES)

@@ -8,7 +8,9 @@ namespace grb {
 enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY, IT_P3 = 9, IT_P4 = 13,
        IT_H0RE = 17, IT_H0IM, IT_PREF, IT_VW, IT_AMP2,
        // Born-level kinematics for the multi-helicity loop: p1z, p1e, p2z, p2e, pX(x,y,z,e)
-       IT_BK = 22, IT_NF = 30 };
+       IT_BK = 22,
+       // <C> class loop invariants: q0y, sinh / cosh of the two leg rapidities (m3, m4, q0x ride in IT_MXSQ, IT_SHY, IT_CHY)
+       IT_CK = 30, IT_NF = 35 };
 
 
 // ---- block-level VEGAS accumulation ---------------------------------------------------------------------

@@ -64,7 +64,7 @@ struct grb_engine {
 static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
 static thread_local std::string g_last_global_error;
 
-#define ITEM_NF 30  /* = IT_NF of grb_accum.cuh */
+#define ITEM_NF 35  /* = IT_NF of grb_accum.cuh */
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -82,14 +82,15 @@ static double m_of_beam(double pz, double E) {  // M4Vec::M() of (0,0,pz,E), ref
 
 // one active Regge trajectory (TUNE0): the screening kernel's one-basic-block node applies (grb_point.cuh)
 static int regge_fast_ff(const DevProc &P) {
-  return (P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
+  return (P.ps_class == GRB_CLASS_F && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
 }
 
 // desc -> DevProc. Host libm (glibc, the reference's) evaluates the loop invariants.
 static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   memset(&P, 0, sizeof(P));
   if (d.abi_version != GRB_ABI_VERSION) { err = "abi_version mismatch"; return GRB_ERR_ARG; }
-  if (d.ps_class != GRB_CLASS_F) { err = "only the <F> phase-space class is on the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.ps_class != GRB_CLASS_F && d.ps_class != GRB_CLASS_C) { err = "only the <F> and <C> phase-space classes are on the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.ps_class == GRB_CLASS_C && d.veto_active) { err = "<C> with veto cuts needs forward fragmentation (outside the device path)"; return GRB_ERR_UNSUPPORTED; }
   if (d.excitation != 0) { err = "NSTARS != 0 is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
@@ -125,7 +126,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   }
   if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
-  if (d.lipsdim != 6) { err = "lipsdim must be 6 for <F> with NSTARS=0"; return GRB_ERR_ARG; }
+  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 8 : 6)) { err = "lipsdim must be 6 for <F> and 8 for <C> (two central legs) with NSTARS=0"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_veto > GRB_MAX_VETO) { err = "too many veto domains"; return GRB_ERR_ARG; }
   if (d.fcuts.usercuts != 0 && std::abs(d.fcuts.usercuts) != 3 && std::abs(d.fcuts.usercuts) != 111) {
@@ -144,6 +145,9 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.dlog_pt = std::log(d.gcuts.forward_pt_max) - std::log(d.gcuts.forward_pt_min + 1e-12);
   P.Y_min = d.gcuts.Y_min; P.dY = d.gcuts.Y_max - d.gcuts.Y_min;
   P.gM_min = d.gcuts.M_min; P.gM_max = d.gcuts.M_max;
+  P.ps_class = d.ps_class;
+  P.kt_min = d.gcuts.kt_min; P.dkt = d.gcuts.kt_max - d.gcuts.kt_min;
+  P.rap_min = d.gcuts.rap_min; P.drap = d.gcuts.rap_max - d.gcuts.rap_min;
   P.offshell = d.offshell;
   const grb_fidcut &f = d.fcuts;
   P.f_eta_min = f.eta_min; P.f_eta_max = f.eta_max; P.f_rap_min = f.rap_min; P.f_rap_max = f.rap_max;
@@ -157,6 +161,10 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   const double twopi    = 2.0 * PI;
   P.w_const = (1.0 / d.S_factor) * GeV2barn / (2.0 * d.s) * (twopi * twopi) * (P.dlog_pt * P.dlog_pt) * P.dY *
               0.5 / (twopi * twopi * twopi * twopi * twopi) * 0.25;
+  // <C>, Kf = 2 (MContinuum.cc:181-183,619-658): 2^-4 (2pi)^-8 / 4 from the phase-space weight, dkt 2pi drap^2 and the
+  // forward volume (2pi)^2 dlog^2 from the integral volume
+  P.w_const_C = (1.0 / d.S_factor) * GeV2barn / (2.0 * d.s) * (1.0 / 16.0) / std::pow(twopi, 8) * 0.25 *
+                (P.dkt * twopi * (P.drap * P.drap)) * ((twopi * twopi) * (P.dlog_pt * P.dlog_pt));
   // Regge
   const grb_param_regge &R = d.regge;
   for (int k = 0; k < 3; ++k) {

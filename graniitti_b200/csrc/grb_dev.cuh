@@ -50,6 +50,9 @@ struct DevProc {
   double M_MAX0;                   // sqrt_s - (pbeam1.M() + pbeam2.M()), MFactorized.cc:277
   // sampling map (MFactorized.cc:245-258)
   double log_pt0, dlog_pt, Y_min, dY, gM_min, gM_max;
+  // <C> class sampling map (MContinuum.cc:276-331): kt = kt_min + dkt u, y_i = rap_min + drap u; weight constant
+  double kt_min, dkt, rap_min, drap, w_const_C;
+  int    ps_class, pad_c_;
   double offshell;
   // cuts
   double f_eta_min, f_eta_max, f_rap_min, f_rap_max, f_pt_min, f_pt_max, f_Et_min, f_Et_max;

@@ -56,6 +56,14 @@ __device__ __forceinline__ double weight_prefactor(const PointState<NN> &S) {
   const double C   = c_proc.ps_active ? S.DW / (2 * GRB_PI) : 1.0;
   return C * psw * vol * c_proc.w_const;
 }
+// <C> class: MContinuum.cc:181-183 with BNPhaseSpaceWeight (:639-658) and BNIntegralVolume (:619-637), Kf = 2
+template <int NN>
+__device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
+  const double J   = 1.0 / fabs(S.p1.z / S.p1.e - S.p2.z / S.p2.e);
+  const double pt1 = msqrt(pt2_of(S.p1)), pt2 = msqrt(pt2_of(S.p2));
+  const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J * msqrt(S.qx * S.qx + S.qy * S.qy);  // x 2^-4 (2pi)^-8 / 4
+  return psw * (pt1 * pt2) * c_proc.w_const_C;                                               // x dkt 2pi drap^2 (2pi)^2 dlog^2
+}
 
 template <int NN, bool VEGAS, int AMP>
 __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
@@ -100,7 +108,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
             vw *= zo * a.bins;
             packed |= (uint64_t)(ind - 1) << (8 * j);
           }
-        kin     = point_kinematics<NN>(u, dr, S);
+        kin     = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       } else {
         DrawsSoA dr;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < dim) u[j] = dr.coord(j);
-        kin     = point_kinematics<NN>(u, dr, S);
+        kin     = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       }
       if (kin) {  // on failure the reference evaluates the cuts on stale state: flags are don't-care
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
     double     pref = 0.0;
     if (valid) {
       h0   = born_amplitude<NN, AMP>(S);
-      pref = weight_prefactor<NN>(S);
+      pref = P.ps_class == GRB_CLASS_C ? weight_prefactor_C<NN>(S) : weight_prefactor<NN>(S);
       if (!P.screening) {
         W = pref * (h0.re * h0.re + h0.im * h0.im);
         if (isnan(W) || isinf(W)) { W = 0.0; amp_ok = false; }
@@ -157,6 +165,11 @@ __global__ void __launch_bounds__(256) k_points(const PointArgs a) {
             it[IT_P1X * c] = L.p1x; it[IT_P1Y * c] = L.p1y; it[IT_P2X * c] = L.p2x; it[IT_P2Y * c] = L.p2y;
             it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
             it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
+            if (P.ps_class == GRB_CLASS_C) {
+              it[IT_MXSQ * c] = L.m3; it[IT_SHY * c] = L.m4; it[IT_CHY * c] = L.qx;
+              it[(IT_CK + 0) * c] = L.qy; it[(IT_CK + 1) * c] = L.sh3; it[(IT_CK + 2) * c] = L.ch3;
+              it[(IT_CK + 3) * c] = L.sh4; it[(IT_CK + 4) * c] = L.ch4;
+            }
             it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
             it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
             it[IT_H0RE * c] = h0.re; it[IT_H0IM * c] = h0.im;

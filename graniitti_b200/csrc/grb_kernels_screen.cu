@@ -28,6 +28,11 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
   L.emax = P.sqrt_s - (L.m1 + L.m2);
   L.same_mass = SAME;
+  if (FF < 0 && P.ps_class == GRB_CLASS_C) {
+    L.m3 = L.mXsq; L.m4 = L.shY; L.qx = L.chY;
+    L.qy = it[(IT_CK + 0) * c]; L.sh3 = it[(IT_CK + 1) * c]; L.ch3 = it[(IT_CK + 2) * c];
+    L.sh4 = it[(IT_CK + 3) * c]; L.ch4 = it[(IT_CK + 4) * c];
+  }
   L.p3.x = it[(IT_P3 + 0) * c]; L.p3.y = it[(IT_P3 + 1) * c]; L.p3.z = it[(IT_P3 + 2) * c]; L.p3.e = it[(IT_P3 + 3) * c];
   L.p4.x = it[(IT_P4 + 0) * c]; L.p4.y = it[(IT_P4 + 1) * c]; L.p4.z = it[(IT_P4 + 2) * c]; L.p4.e = it[(IT_P4 + 3) * c];
   if (AmpHel<AMP>::NH > 1) {

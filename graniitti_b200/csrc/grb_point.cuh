@@ -89,6 +89,7 @@ struct PointState {
   double M_MIN, M_MAX, DW;
   double t1, t2, s1, s2, t_hat, u_hat, m2, Y, Pt;
   double ss13, ss14, ss23, ss24;
+  double qx, qy;           // <C> class: intermediate difference momentum q0 (MContinuum::pkt_[0])
 };
 
 // reference src/MRandom.cc:82-107 RelativisticBWRandom; node constants are pre-digested on the host with
@@ -162,6 +163,9 @@ __device__ __forceinline__ bool lorentz_scalars(PointState<NN> &S) {
 
 // reference src/MFactorized.cc:245-412 B51RandomKin + B51BuildKin, src/MProcess.cc:1231-1284
 template <int NN, class Draws>
+__device__ __forceinline__ bool cascade_decays(Draws &dr, PointState<NN> &S);
+
+template <int NN, class Draws>
 __device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, PointState<NN> &S) {
   const DevProc &P = c_proc;
   const double   pt1  = exp(P.log_pt0 + P.dlog_pt * u[0]);
@@ -217,7 +221,14 @@ __device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, Poi
     S.DW = two_body(S.pX, msqrt(m2X), S.moff[0], S.moff[1], rc, rp, S.np4[0], S.np4[1]);
     if (S.DW < 0) return false;
   }
-  // cascade decays in the reference's depth-first order
+  if (!cascade_decays<NN>(dr, S)) return false;
+  return lorentz_scalars(S);
+}
+
+// cascade decays in the reference's depth-first order (MProcess::ConstructDecayKinematics)
+template <int NN, class Draws>
+__device__ __forceinline__ bool cascade_decays(Draws &dr, PointState<NN> &S) {
+  const DevProc &P = c_proc;
   if (NN > 2) {
     for (int k = 0; k < P.n_decays; ++k) {
       const int      node = P.decay_order[k];
@@ -242,6 +253,57 @@ __device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, Poi
       if (w < 0) return false;
     }
   }
+  return true;
+}
+
+// ---- <C> phase-space class, two central legs: reference src/MContinuum.cc:276-435 BNRandomKin + BNBuildKin ---------
+// u = [pt1, pt2, phi1, phi2, kt, phi_k, y3, y4]; BLinearSystem for Kf = 2 is p3T = (q0 - w)/2, p4T = (-q0 - w)/2 with
+// w = p1T + p2T (the reference's matrix loop also adds b_j * 0.0, a signed zero).
+template <int NN, class Draws>
+__device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, PointState<NN> &S) {
+  const DevProc &P = c_proc;
+  const double   pt1  = exp(P.log_pt0 + P.dlog_pt * u[0]);
+  const double   pt2  = exp(P.log_pt0 + P.dlog_pt * u[1]);
+  const double   phi1 = 2.0 * GRB_PI * u[2];
+  const double   phi2 = 2.0 * GRB_PI * u[3];
+#pragma unroll
+  for (int i = 0; i < NN; ++i)
+    if (i < P.n_legs) S.moff[i] = offshell_mass(i, dr);
+  const double kt   = P.kt_min + P.dkt * u[4];
+  const double phik = 2.0 * GRB_PI * u[5];
+  const double y3 = P.rap_min + P.drap * u[6], y4 = P.rap_min + P.drap * u[7];
+  const double m1 = P.mb1, m2 = P.mb2;
+  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0;
+  double s1, c1, s2, c2, sk, ck;
+  sincos(phi1, &s1, &c1);
+  sincos(phi2, &s2, &c2);
+  sincos(phik, &sk, &ck);
+  S.p1.x = pt1 * c1; S.p1.y = pt1 * s1;
+  S.p2.x = pt2 * c2; S.p2.y = pt2 * s2;
+  S.qx = kt * ck; S.qy = kt * sk;
+  const double wx = S.p1.x + S.p2.x, wy = S.p1.y + S.p2.y;
+  v4 &p3 = S.np4[0], &p4 = S.np4[1];
+  p3.x = (S.qx - wx) * (1.0 / 2.0); p3.y = (S.qy - wy) * (1.0 / 2.0);
+  p4.x = (S.qx * (-1.0) - wx) * (1.0 / 2.0); p4.y = (S.qy * (-1.0) - wy) * (1.0 / 2.0);
+  const double mt3 = msqrt(pow2(S.moff[0]) + pt2_of(p3)), mt4 = msqrt(pow2(S.moff[1]) + pt2_of(p4));
+  p3.z = mt3 * sinh(y3); p3.e = mt3 * cosh(y3);
+  p4.z = mt4 * sinh(y4); p4.e = mt4 * cosh(y4);
+  S.pX.x = p3.x + p4.x; S.pX.y = p3.y + p4.y; S.pX.z = p3.z + p4.z; S.pX.e = p3.e + p4.e;
+  if (S.pX.e > P.sqrt_s) return false;
+  PzConst pc;
+  pc.s = P.s; pc.t7 = P.sqrt_s; pc.t9 = P.s_pow15; pc.t14 = P.s * P.s;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, S.pX.z, S.pX.e, pc);
+  const double p2z = -(S.pX.z + p1z);
+  if (p1z < 0 || p2z > 0 || isnan(p1z)) return false;
+  S.p1.z = p1z; S.p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  S.p2.z = p2z; S.p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+  if (m_of(S.pX) < m_of(p3) + m_of(p4)) return false;  // mass threshold, :415-416 (sumM = 0 + M3 + M4)
+  {
+    const double dx = 0.0 - ((S.p1.x + S.p2.x) + S.pX.x), dy = 0.0 - ((S.p1.y + S.p2.y) + S.pX.y);
+    const double dz = P.bsum_z - ((S.p1.z + S.p2.z) + S.pX.z), de = P.bsum_e - ((S.p1.e + S.p2.e) + S.pX.e);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  if (!cascade_decays<NN>(dr, S)) return false;
   return lorentz_scalars(S);
 }
 
@@ -692,6 +754,9 @@ struct LoopInv {
   double m1, m2, m1sq, m2sq, mXsq, shY, chY, emax;  // emax = sqrt_s - (m1 + m2)
   v4     p3, p4;
   bool   same_mass;  // |m1 - m2| < 1e-9: SolvePz3_A branch (MKinematics.h:220-229)
+  // <C> class (MContinuum::LoopKinematics): q0 and, per central leg, mass and sinh / cosh of the rapidity re-derived
+  // from the saved 4-vectors (pfinal_orig[3], [4])
+  double qx, qy, m3, m4, sh3, ch3, sh4, ch4;
 };
 
 template <int NN>
@@ -708,6 +773,14 @@ __device__ __forceinline__ void make_loop_inv(const PointState<NN> &S, LoopInv &
   L.same_mass = fabs(L.m1 - L.m2) < 1e-9;
   L.p3 = S.np4[0];
   L.p4 = S.np4[1];
+  if (c_proc.ps_class == GRB_CLASS_C) {
+    L.qx = S.qx; L.qy = S.qy;
+    L.m3 = m_of(S.np4[0]); L.m4 = m_of(S.np4[1]);
+    const double y3 = rap_of(S.np4[0]), y4 = rap_of(S.np4[1]);
+    L.sh3 = sinh(y3); L.ch3 = cosh(y3); L.sh4 = sinh(y4); L.ch4 = cosh(y4);
+  } else {
+    L.qx = L.qy = L.m3 = L.m4 = L.sh3 = L.ch3 = L.sh4 = L.ch4 = 0.0;
+  }
 }
 
 // One node of the loop.  The tests that can never fire are not evaluated: px, py, pz are conserved by
@@ -750,6 +823,54 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   return true;
 }
 
+// One node of the <C> class loop (reference src/MContinuum.cc:94-161): the central legs move with the protons (same
+// masses and rapidities, transverse momenta from the linear system), so ss13..ss24 see the updated legs, while t_hat /
+// u_hat and the amplitudes' vertex algebra keep reading the Born-level lts.decaytree[i].p4 (L.p3, L.p4) -- as the
+// reference does.  No crude energy test here (:128-134 go straight to SolvePz).
+template <bool SAME>
+__device__ __forceinline__ bool loop_node_C(const LoopInv &L, const PzConst &pc, double ktx, double kty, NodeKin &o) {
+  const DevProc &P = c_proc;
+  const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
+  const double wx = n1x + n2x, wy = n1y + n2y;
+  const double p3x = (L.qx - wx) * (1.0 / 2.0), p3y = (L.qy - wy) * (1.0 / 2.0);
+  const double p4x = (L.qx * (-1.0) - wx) * (1.0 / 2.0), p4y = (L.qy * (-1.0) - wy) * (1.0 / 2.0);
+  const double mt3 = msqrt(pow2(L.m3) + (p3x * p3x + p3y * p3y)), mt4 = msqrt(pow2(L.m4) + (p4x * p4x + p4y * p4y));
+  const double p3z = mt3 * L.sh3, p3e = mt3 * L.ch3, p4z = mt4 * L.sh4, p4e = mt4 * L.ch4;
+  const double Xx = p3x + p4x, Xy = p3y + p4y, Xz = p3z + p4z, Xe = p3e + p4e;
+  const double pt1 = msqrt(n1x * n1x + n1y * n1y), pt2 = msqrt(n2x * n2x + n2y * n2y);
+  const double p1z = SAME ? solve_pz3_A(L.m1, pt1, pt2, Xz, Xe, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, Xz, Xe, pc);
+  const double p2z = -(Xz + p1z);
+  if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
+  const double e1 = msqrt(L.m1sq + pow2(pt1) + pow2(p1z)), e2 = msqrt(L.m2sq + pow2(pt2) + pow2(p2z));
+  {
+    const double dx = 0.0 - ((n1x + n2x) + Xx), dy = 0.0 - ((n1y + n2y) + Xy);
+    const double dz = P.bsum_z - ((p1z + p2z) + Xz), de = P.bsum_e - ((e1 + e2) + Xe);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  o.ss13 = m2_of(n1x + p3x, n1y + p3y, p1z + p3z, e1 + p3e);
+  o.ss14 = m2_of(n1x + p4x, n1y + p4y, p1z + p4z, e1 + p4e);
+  o.ss23 = m2_of(n2x + p3x, n2y + p3y, p2z + p3z, e2 + p3e);
+  o.ss24 = m2_of(n2x + p4x, n2y + p4y, p2z + p4z, e2 + p4e);
+  const double s01 = m2_of(Xx + n1x, Xy + n1y, Xz + p1z, Xe + e1), s02 = m2_of(Xx + n2x, Xy + n2y, Xz + p2z, Xe + e2);
+  const double s34 = m2_of(p3x + p4x, p3y + p4y, p3z + p4z, p3e + p4e);
+  if (o.ss13 < 0 || o.ss14 < 0 || o.ss23 < 0 || o.ss24 < 0 || s01 < 0 || s02 < 0 || s34 < 0) return false;
+  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  o.t1 = m2_of(q1x, q1y, q1z, q1e);
+  o.t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
+  if (o.t1 > 0 || o.t2 > 0) return false;
+  const v4 &p3 = L.p3, &p4 = L.p4;
+  o.t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  o.u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  o.p1.x = n1x; o.p1.y = n1y; o.p1.z = p1z; o.p1.e = e1;
+  o.p2.x = n2x; o.p2.y = n2y; o.p2.z = p2z; o.p2.e = e2;
+  o.pX.x = Xx; o.pX.y = Xy; o.pX.z = Xz; o.pX.e = Xe;
+  return true;
+}
+template <bool SAME>
+__device__ __forceinline__ bool loop_node_any(const LoopInv &L, const PzConst &pc, double ktx, double kty, NodeKin &o) {
+  return c_proc.ps_class == GRB_CLASS_C ? loop_node_C<SAME>(L, pc, ktx, kty, o) : loop_node<SAME>(L, pc, ktx, kty, o);
+}
+
 // reference src/MProcess.cc:157-288 S3ScreenedAmp2 for a one-amplitude process (H = 1): returns
 // |A_0 + i/(8 pi^2 s) * Simpson38_2D[ A_eik(kt^2) A(kt) kt ]|^2, nodes in the reference's row-major order
 // (phi = 2 pi folded onto phi = 0, see grb_set_eikonal).  Rejected nodes contribute 0 but keep their weight.
@@ -765,7 +886,7 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
     for (int j = 0; j <= Q.nkt; ++j) {
       const double kt = Q.kt[j];
       NodeKin      in;
-      if (!loop_node<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
+      if (!loop_node_any<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
       const cx A = amplitude<AMP>(in, L.p3, L.p4);
       // f = A_eik * A * kt * w_j, with b_j = A_eik(kt_j^2) kt_j w_j tabulated
       Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
@@ -904,7 +1025,7 @@ __device__ __forceinline__ double screened_amp2_multi(const LoopInv &L, const No
     for (int j = 0; j <= Q.nkt; ++j) {
       const double kt = Q.kt[j];
       NodeKin      in;
-      if (!loop_node<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
+      if (!loop_node_any<SAME>(L, pc, kt * cp, kt * sp, in)) continue;
       cx A[NH];
       amplitude_vec<AMP>(in, L.p3, L.p4, A);
       const double br = wi * Q.b_re[j], bi = wi * Q.b_im[j];

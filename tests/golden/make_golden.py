@@ -50,6 +50,14 @@ CASES = [
     ("c2_alice_ppbar_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> p+ p-", 1, 192, 8, True),
     ("c4_cms_mumu_yyqed_born", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[QED]<F> -> mu+ mu-", 0, 1536, 8, True),
     ("c4_cms_mumu_yyqed_screened", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[QED]<F> -> mu+ mu-", 1, 160, 8, True),
+    # <C> phase-space class (MContinuum, 2 -> 4 direct, 8 integration dimensions)
+    ("cc_alice_pipi_con_born", "./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 0, 2048, 8, True),
+    ("cc_alice_pipi_con_born_flat", "./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 0, 2048, 8, False),
+    ("cc_alice_pipi_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 1, 1024, 8, True),
+    ("cc_alice_pipi_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<C> -> pi+ pi-", 1, 256, 8, True),
+    ("cc_test_pipi_rescon_born", "./input/test.json", "PP[RES+CON]<C> -> pi+ pi-", 0, 1536, 8, True),
+    ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
+     "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
 ]
 
 
@@ -62,7 +70,7 @@ def main():
     for i, (name, card, proc, pom, n, dt, adapted) in enumerate(CASES):
         if only and name not in only:
             continue
-        u, tape = make_points(n, 6, dt, 1000 + i, adapted=adapted)
+        u, tape = make_points(n, 8 if "<C>" in proc else 6, dt, 1000 + i, adapted=adapted)
         r = ref_eval(card, proc, pom, u, tape, kappa=True)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u,
                             tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],

@@ -22,6 +22,8 @@ CASES = [
     ("c4_cms_mumu_yycon_born", "tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", "false", 300000, 0.001),
     ("c5_cms_rhorho_4pi_con_born", "tests/processes/CMSCUTS.json",
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", "false", 300000, 0.002),
+    ("cc_alice_pipi_con_born", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "false", 300000, 0.001),
+    ("cc_alice_pipi_con_screened", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "true", 100000, 0.003),
 ]
 
 

@@ -23,7 +23,7 @@ CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.js
            "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json", "./tests/run_atlas_multi/ATLAS.json": "c3_atlas.json",
            "./tests/run_atlas_multi/ATLAS_NEG.json": "c3_atlas_neg.json",
            "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json": "c4_cms_mumu_lowmass.json"}
-FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))  # c1..c5: <F> class per BASELINE config, cc_*: <C> class
 
 
 def engine_for(grb, msa, card, proc=None, pom=-1):
@@ -76,10 +76,12 @@ def test_device_vs_reference_golden(grb, msa, path):
 
 
 @pytest.mark.parametrize("proc,pom,n", [("PP[CON]<F> -> pi+ pi-", 0, 200000), ("PP[CON]<F> -> pi+ pi-", 1, 40000),
-                                        ("PP[CON-]<F> -> K+ K-", 1, 10000), ("PP[CON]<F> -> p+ p-", 0, 50000)])
+                                        ("PP[CON-]<F> -> K+ K-", 1, 10000), ("PP[CON]<F> -> p+ p-", 0, 50000),
+                                        ("PP[CON]<C> -> pi+ pi-", 0, 200000), ("PP[CON]<C> -> pi+ pi-", 1, 20000),
+                                        ("PP[CON-]<C> -> K+ K-", 1, 5000)])
 def test_device_vs_oracle_seeded(grb, msa, proc, pom, n):
     E = engine_for(grb, msa, "c2_alice.json", proc, pom)
-    u, tape = make_points(n, 6, 8, 99 + n, adapted=True)
+    u, tape = make_points(n, E.desc.lipsdim, 8, 99 + n, adapted=True)
     o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
     w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
     nz = o["w"] != 0
@@ -183,6 +185,8 @@ SIGMA_CASES = [  # name in tests/golden/sigma_ref.json, card, ncall, iters, prec
     ("c1_test_pipi_rescon_born", "c1_test13.json", 1 << 21, 5, 0.0005),
     ("c3_atlas_pipi_rescon_born", "c3_atlas.json", 1 << 21, 5, 0.001),
     ("c4_cms_mumu_yycon_born", "c4_cms_mumu_lowmass.json", 1 << 21, 5, 0.0005),
+    ("cc_alice_pipi_con_born", "c2_alice.json", 1 << 21, 5, 0.0005),
+    ("cc_alice_pipi_con_screened", "c2_alice.json", 1 << 21, 5, 0.001),
 ]
 
 

@@ -34,6 +34,17 @@ def test_overrides_like_gr_cli(grb):
     assert d.ps_active == 0
 
 
+def test_continuum_class_flattening(grb):
+    """<C> (MContinuum): daughters' rapidity range from GENCUTS.<C>.Rap, default kt range [0, 10 / legs],
+    3 Nf - 4 = 8 integration dimensions (reference src/MGraniitti.cc:688-745, src/MContinuum.cc:64-91)."""
+    d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), "PP[CON]<C> -> pi+ pi-", 1)
+    assert d.ps_class == _abi.GRB_CLASS_C and d.lipsdim == 8 and d.n_legs == 2 and d.screening == 1
+    assert (d.gcuts.rap_min, d.gcuts.rap_max) == (-0.9, 0.9) and (d.gcuts.kt_min, d.gcuts.kt_max) == (0.0, 5.0)
+    assert d.gcuts.forward_pt_max == 2.5
+    d = grb.parse_card(os.path.join(CARDS, "c4_cms_mumu_lowmass.json"), "yy[CON]<C> -> mu+ mu-", 0)
+    assert d.gcuts.kt_max == d.sqrt_s / 2.0      # QED / EW processes: kinematic maximum
+
+
 def test_cascade_tree_flattening(grb):
     d = grb.parse_card(os.path.join(CARDS, "c5_cms_4pi.json"))
     assert d.n_legs == 2 and d.n_nodes == 6 and d.n_final == 4 and d.S_factor == 2.0 and d.n_tape == 16

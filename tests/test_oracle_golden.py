@@ -13,7 +13,7 @@ CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.js
            "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json", "./tests/run_atlas_multi/ATLAS.json": "c3_atlas.json",
            "./tests/run_atlas_multi/ATLAS_NEG.json": "c3_atlas_neg.json",
            "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json": "c4_cms_mumu_lowmass.json"}
-FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))  # c1..c5: <F> class per BASELINE config, cc_*: <C> class
 
 
 def load_case(grb, path):
@@ -64,10 +64,11 @@ def test_oracle_reproduces_reference_bit_exactly(grb, msa, path):
 
 @pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
 @pytest.mark.parametrize("proc,pom,n", [("PP[CON]<F> -> pi+ pi-", 0, 20000), ("PP[CON]<F> -> pi+ pi-", 1, 1500),
-                                        ("PP[CON-]<F> -> K+ K-", 0, 5000), ("PP[CON]<F> -> p+ p-", 0, 5000)])
+                                        ("PP[CON-]<F> -> K+ K-", 0, 5000), ("PP[CON]<F> -> p+ p-", 0, 5000),
+                                        ("PP[CON]<C> -> pi+ pi-", 0, 20000), ("PP[CON]<C> -> K+ K-", 1, 300)])
 def test_oracle_vs_live_reference(grb, msa, proc, pom, n):
     d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), proc, pom)
-    u, tape = make_points(n, 6, 8, 4242 + n, adapted=True)
+    u, tape = make_points(n, d.lipsdim, 8, 4242 + n, adapted=True)
     r = ref_eval("./tests/processes/ALICECUTS.json", proc, pom, u, tape)
     o = oracle_eval(d, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
     kin = (r["flags"] & 1) == 1

@@ -105,7 +105,6 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
       err = "yy[CON]: only charged lepton pairs (MG5 yy -> l+ l-) have a device amplitude";
       return GRB_ERR_UNSUPPORTED;
     }
-    if (d.qed_alpha != 0) { err = "yy[CON]: PARAM_STRUCTURE.QED_alpha must be ZERO on the device path"; return GRB_ERR_UNSUPPORTED; }
   }
   if (d.proc == GRB_PROC_YY_QED) {
     const int a = std::abs(d.nodes[0].pdg);
@@ -218,7 +217,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
       for (int k = 0; k < 4; ++k) { P.bsp[b][0][k] = um[k]; P.bsp[b][1][k] = up[k]; }
     }
     P.omega = d.regge.omega;
-    const double ee = 2. * std::sqrt(1.0 / 137.03599908) * std::sqrt(M_PI);
+    // QED_alpha = ZERO: alpha(0); otherwise the MG5 model coupling, aEWM1 = 132.507 (Parameters_sm.cc:31,45-49,93-101)
+    const double ee = d.qed_alpha == 0 ? 2. * std::sqrt(1.0 / 137.03599908) * std::sqrt(M_PI) : 2 * std::sqrt(1. / 1.325070e+02) * std::sqrt(M_PI);
     P.yy_ee4 = (ee * ee) * (ee * ee);
   }
   // nodes

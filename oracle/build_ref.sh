@@ -67,4 +67,7 @@ mkdir -p tests
 for d in processes run_atlas_multi run_cms_mumu_low_high run_rhorho_phiphi LHC_TEVATRON_RHIC; do
   rm -rf "tests/$d"; [ -d "$R/tests/$d" ] && cp -r "$R/tests/$d" "tests/$d"
 done
+# a second tune for the goldens of PARAM_STRUCTURE.QED_alpha != "ZERO" (MG5 param-card coupling): TUNE0 with that one key changed
+rm -rf modeldata/TUNE0_MG; cp -r modeldata/TUNE0 modeldata/TUNE0_MG
+sed -i 's/"QED_alpha"[ ]*:[ ]*"ZERO"/"QED_alpha" : "MG"/' modeldata/TUNE0_MG/GENERAL.json
 echo "build_ref: OK -> $OUT/gra/bin/{gr,ref_eval}"

@@ -1770,8 +1770,11 @@ static double yy_con_amp2(ost *S) {
   o_offshell2lightcone(&q1, &q2, pf);
   const double P1[4] = {q1.e, q1.x, q1.y, q1.z}, P2[4] = {q2.e, q2.x, q2.y, q2.z};
   const double P3[4] = {pf[0].e, pf[0].x, pf[0].y, pf[0].z}, P4[4] = {pf[1].e, pf[1].x, pf[1].y, pf[1].z};
-  /* GC_3 = -(ee * i), ee = 2 sqrt(1/137.03599908) sqrt(pi)  (Parameters_sm.cc:93-101, QED_alpha = ZERO) */
-  const double ee = 2. * sqrt(1.0 / 137.03599908) * sqrt(M_PI);
+  /* GC_3 = -(ee * i), ee = 2 sqrt(1/137.03599908) sqrt(pi)  (Parameters_sm.cc:93-101, QED_alpha = ZERO); otherwise the
+   * MG5 model value mdl_ee = 2 sqrt(aEW) sqrt(pi), aEW = 1 / aEWM1, aEWM1 = 1.325070e+02 (Parameters_sm.cc:31,45-49,
+   * MG5cards/param_card_yy_ll.dat) */
+  const double aEWM1 = 1.325070e+02, aEW = 1. / aEWM1;
+  const double ee = S->d->qed_alpha == 0 ? 2. * sqrt(1.0 / 137.03599908) * sqrt(M_PI) : 2 * sqrt(aEW) * sqrt(M_PI);
   const cx GC3 = {-(ee * 0.0), -(ee * 1.0)};
   double amp2 = 0.0;
   for (int ih = 0; ih < 16; ++ih) {
@@ -1804,9 +1807,9 @@ static double bare_amp2(ost *S) {
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
     case GRB_PROC_YY_CON: {
       const int apdg = abs(S->d->nodes[0].pdg);
-      if (!(apdg == 11 || apdg == 13 || apdg == 15) || S->d->nodes[1].pdg != -S->d->nodes[0].pdg || S->d->qed_alpha != 0) {
+      if (!(apdg == 11 || apdg == 13 || apdg == 15) || S->d->nodes[1].pdg != -S->d->nodes[0].pdg) {
         S->nhamp = 0;
-        return NAN; /* only charged lepton pairs with QED_alpha = ZERO are restated */
+        return NAN; /* only charged lepton pairs are restated */
       }
       return yy_con_amp2(S);
     }

@@ -8,12 +8,13 @@ Per case an .npz with: u [n][dim], tape [n][dtape] (the internal uniforms), and 
 t1, t2, s1, s2, m2, t_hat, u_hat, first helicity amplitudes, and kappa = the reference's own 1-ulp
 conditioning max_k |W(u +- ulp e_k) - W|/|W|."""
 import os
+import re
 import sys
 
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from helpers import GOLDEN, have_ref, make_points, ref_eval, ref_msa  # noqa: E402
+from helpers import GOLDEN, REF_TREE, have_ref, make_points, ref_eval, ref_msa  # noqa: E402
 
 # name, reference card (relative to the reference tree), process override, pomloop, n, dtape, adapted
 CASES = [
@@ -56,6 +57,8 @@ CASES = [
     ("cc_alice_pipi_con_screened", "./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 1, 1024, 8, True),
     ("cc_alice_pipi_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<C> -> pi+ pi-", 1, 256, 8, True),
     ("cc_test_pipi_rescon_born", "./input/test.json", "PP[RES+CON]<C> -> pi+ pi-", 0, 1536, 8, True),
+    # PARAM_STRUCTURE.QED_alpha != ZERO: the MG5 param-card coupling (aEWM1 = 132.507); card copy with MODELPARAM TUNE0_MG
+    ("c4_cms_mumu_yycon_mgalpha_born", "@TUNE0_MG:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1024, 8, True),
     ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
 ]
@@ -71,8 +74,17 @@ def main():
         if only and name not in only:
             continue
         u, tape = make_points(n, 8 if "<C>" in proc else 6, dt, 1000 + i, adapted=adapted)
-        r = ref_eval(card, proc, pom, u, tape, kappa=True)
-        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u,
+        qed_alpha = 0
+        run_card = card
+        if card.startswith("@"):   # "@TUNE:card": run a copy of the card (written under output/) with MODELPARAM replaced
+            tune, card = card[1:].split(":", 1)
+            txt = open(os.path.join(REF_TREE, card)).read()
+            txt = re.sub(r'("MODELPARAM"\s*:\s*)"[^"]*"', r'\g<1>"%s"' % tune, txt)
+            run_card = "./output/golden_%s.json" % name
+            open(os.path.join(REF_TREE, run_card), "w").write(txt)
+            qed_alpha = 1
+        r = ref_eval(run_card, proc, pom, u, tape, kappa=True)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
                             tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
                             s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
                             nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :5])

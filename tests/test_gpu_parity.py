@@ -52,7 +52,12 @@ def compare(w, fl, ref_w, ref_fl, kappa=None, rtol=RTOL):
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
 def test_device_vs_reference_golden(grb, msa, path):
     z = np.load(path, allow_pickle=False)
-    E = engine_for(grb, msa, CARD_OF[str(z["card"])], str(z["process"]), int(z["pomloop"]))
+    if "qed_alpha" in z.files and int(z["qed_alpha"]):   # a tune with PARAM_STRUCTURE.QED_alpha != ZERO: through the POD desc
+        d = grb.parse_card(os.path.join(CARDS, CARD_OF[str(z["card"])]), str(z["process"]), int(z["pomloop"]))
+        d.qed_alpha = int(z["qed_alpha"])
+        E = grb.Engine(desc=d)
+    else:
+        E = engine_for(grb, msa, CARD_OF[str(z["card"])], str(z["process"]), int(z["pomloop"]))
     w, fl, dump = E.eval(z["u"].T.copy(), z["tape"].T.copy(), want_dump=True)
     rel = compare(w, fl, z["W"], z["flags"], kappa=z["kappa"])
     # how many points may need the conditioning term: 1e-3 for the well-conditioned amplitudes; the reference's explicit

@@ -19,6 +19,8 @@ FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))  # c1..c5: <F> class p
 def load_case(grb, path):
     z = np.load(path, allow_pickle=False)
     d = grb.parse_card(os.path.join(CARDS, CARD_OF[str(z["card"])]), str(z["process"]), int(z["pomloop"]))
+    if "qed_alpha" in z.files:   # PARAM_STRUCTURE.QED_alpha of the tune the golden was generated with
+        d.qed_alpha = int(z["qed_alpha"])
     return z, d
 
 

@@ -66,7 +66,9 @@ __device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
 }
 
 template <int NN, bool VEGAS, int AMP>
-__global__ void __launch_bounds__(256) k_points(const PointArgs a) {
+// Regge continuum: two CTAs per SM (<= 128 registers): the kernel is latency-bound (libm calls, divergent cuts), so
+// occupancy pays; the heavier amplitudes keep the full register file
+__global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
   const int      nb  = a.bins * dim;

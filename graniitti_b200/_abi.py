@@ -112,3 +112,8 @@ class VegasResult(C.Structure):
 
 
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+
+class XscanRow(C.Structure):
+    _fields_ = [(k, f64) for k in ("sqrt_s", "xs_tot_mb", "xs_el_mb", "xs_inel_mb", "sigma", "sigma_err", "chi2",
+                                   "evaluations", "seconds")]

@@ -777,6 +777,69 @@ int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_o
   return grb_set_eikonal(e, T.kt2.data(), T.sa_re.data(), T.sa_im.data(), (int)T.kt2.size());
 }
 
+int grb_update_desc(grb_engine *e, const grb_process_desc *desc) {
+  if (!e || !desc) return GRB_ERR_ARG;
+  if (desc->n_nodes != e->desc.n_nodes || desc->n_legs != e->desc.n_legs || desc->ps_class != e->desc.ps_class) {
+    e->err = "grb_update_desc: the decay-tree topology and the phase-space class must stay the same";
+    return GRB_ERR_ARG;
+  }
+  DevProc P;
+  DevRes  R;
+  int rc = digest(*desc, P, e->err);
+  if (rc == GRB_OK) rc = digest_res(*desc, R, e->err);
+  if (rc != GRB_OK) return rc;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  if (desc->screening && !e->d_items) {  // screening switched on: the work list was not allocated at creation
+    CK(cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk));
+    CK(cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk));
+    CK(cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk));
+  }
+  const bool same_loop = desc->s == e->desc.s && desc->loop_nkt == e->desc.loop_nkt && desc->loop_nphi == e->desc.loop_nphi &&
+                         desc->loop_min_kt == e->desc.loop_min_kt && desc->loop_max_kt == e->desc.loop_max_kt;
+  e->desc  = *desc;
+  e->dproc = P;
+  e->dres  = R;
+  if (!same_loop) e->have_loop = false;   // A_eik(kt^2) and the loop norm depend on s and the discretisation
+  if (g_const_owner == e) g_const_owner = nullptr;  // force the constant upload on the next call
+  return GRB_OK;
+}
+
+int grb_set_beam_energies(grb_engine *e, double ebeam1, double ebeam2) {
+  if (!e || !(ebeam1 > 0) || !(ebeam2 > 0)) return GRB_ERR_ARG;
+  grb_process_desc d = e->desc;
+  auto msq = [](double x) { return std::sqrt(std::max(0.0, x)); };
+  const double E1 = std::max(ebeam1, 1.001 * d.beam1_mass), E2 = std::max(ebeam2, 1.001 * d.beam2_mass);
+  d.pbeam1_pz = msq(E1 * E1 - d.beam1_mass * d.beam1_mass); d.pbeam1_E = E1;
+  d.pbeam2_pz = -msq(E2 * E2 - d.beam2_mass * d.beam2_mass); d.pbeam2_E = E2;
+  const double sz = d.pbeam1_pz + d.pbeam2_pz, se = d.pbeam1_E + d.pbeam2_E;
+  d.s      = se * se - (0.0 * 0.0 + 0.0 * 0.0 + sz * sz);   // (pbeam1 + pbeam2).M2()
+  d.sqrt_s = msq(d.s);
+  if (d.sqrt_s < d.beam1_mass + d.beam2_mass) { e->err = "MProcess::SetBeamEnergies: Error with input CMS energy"; return GRB_ERR_ARG; }
+  // <C> class QED / EW processes: the default kt range is the kinematic maximum (MContinuum.cc:80-83)
+  if (d.ps_class == GRB_CLASS_C && d.gcuts.kt_max == e->desc.sqrt_s / 2.0) d.gcuts.kt_max = d.sqrt_s / 2.0;
+  return grb_update_desc(e, &d);
+}
+
+int grb_xscan(grb_engine *e, const double *sqrt_s, int n, const grb_vegas_param *par, grb_xscan_row *rows) {
+  if (!e || !sqrt_s || n < 0 || !par || !rows) return GRB_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    int rc = grb_set_beam_energies(e, sqrt_s[i] / 2, sqrt_s[i] / 2);
+    if (rc != GRB_OK) return rc;
+    double xs[3] = {0, 0, 0};
+    rc = grb_build_eikonal(e, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, xs);
+    if (rc != GRB_OK) return rc;
+    grb_vegas_result r;
+    rc = grb_integrate(e, par, 0, 1, nullptr, nullptr, &r);
+    if (rc != GRB_OK) return rc;
+    rows[i].sqrt_s = e->desc.sqrt_s;
+    rows[i].xs_tot_mb = xs[0]; rows[i].xs_el_mb = xs[1]; rows[i].xs_inel_mb = xs[2];
+    rows[i].sigma = r.sigma; rows[i].sigma_err = r.sigma_err; rows[i].chi2 = r.chi2;
+    rows[i].evaluations = r.evaluations; rows[i].seconds = r.seconds;
+  }
+  return GRB_OK;
+}
+
 int grb_test_fastmath(int device, int kind, int64_t n, const double *x, double *y) {
   if (!x || !y || n <= 0 || kind < 0 || kind > 11) return GRB_ERR_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return GRB_ERR_CUDA;

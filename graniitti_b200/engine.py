@@ -52,6 +52,12 @@ def lib():
         L.grb_write_eikonal_file.argtypes = [C.c_char_p, vp, vp, vp, cint]
         L.grb_read_eikonal_file.restype = cint
         L.grb_read_eikonal_file.argtypes = [C.c_char_p, vp, vp, vp, cint]
+        L.grb_update_desc.restype = cint
+        L.grb_update_desc.argtypes = [vp, C.POINTER(_abi.ProcessDesc)]
+        L.grb_set_beam_energies.restype = cint
+        L.grb_set_beam_energies.argtypes = [vp, dbl, dbl]
+        L.grb_xscan.restype = cint
+        L.grb_xscan.argtypes = [vp, vp, cint, C.POINTER(_abi.VegasParam), C.POINTER(_abi.XscanRow)]
         L.grb_eval.restype = cint
         L.grb_eval.argtypes = [vp, i64, vp, cint, vp, cint, vp, vp, vp]
         L.grb_vegas_iterate.restype = cint
@@ -271,6 +277,24 @@ class Engine:
         cb = _abi.REDUCE_FN(lambda ctx, ptr: int(reduce(ptr) or 0)) if reduce else _abi.REDUCE_FN()
         self._check(lib().grb_integrate(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
         return res
+
+    def update_desc(self, desc):
+        """Re-parameterise without re-creating the engine (same decay-tree topology and phase-space class)."""
+        self._check(lib().grb_update_desc(self._h, C.byref(desc)))
+        lib().grb_get_desc(self._h, C.byref(self.desc))
+
+    def set_beam_energies(self, e1, e2):
+        self._check(lib().grb_set_beam_energies(self._h, float(e1), float(e2)))
+        lib().grb_get_desc(self._h, C.byref(self.desc))
+
+    def xscan(self, sqrt_s, ncall, iters=5, precision=0.01, chi2max=10.0, bins=128, lam=1.5, seed=12345678, burnin=3):
+        """Energy scan (reference src/Program/xscan.cc): rows of (sqrt_s, xs_tot/el/inel [mb], sigma +- err [barn])."""
+        e = np.ascontiguousarray(sqrt_s, dtype=np.float64)
+        par = _abi.VegasParam(bins, iters, burnin, 0, ncall, lam, chi2max, precision, seed, -1, 0)
+        rows = (_abi.XscanRow * len(e))()
+        self._check(lib().grb_xscan(self._h, e.ctypes.data, len(e), C.byref(par), rows))
+        lib().grb_get_desc(self._h, C.byref(self.desc))
+        return list(rows)
 
     def get_events(self, max_events=1 << 22):
         """(momenta [npart][4][n], weights [2][n]) of the events accepted by the last GENERATE iteration."""

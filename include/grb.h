@@ -367,6 +367,32 @@ int grb_allreduce(grb_engine *e);
  * roofline denominator for the path (MEASURED_PEAKS.json has no fp64 figure).                            */
 int grb_measure_dfma_peak(int device, double *tflops_out);
 
+/* ---- callers that loop the integrator ---------------------------------------------------- */
+
+/* Re-parameterise an existing engine instead of re-creating it: the reference's energy scan and parameter fits build a
+ * new MGraniitti per step (src/Program/xscan.cc:111-140, src/Program/Analysis/fitcentral.cc); here the device buffers,
+ * streams and communicator stay, only the POD description is digested again.  The decay-tree topology (n_nodes, n_legs)
+ * and the phase-space class must not change.  A changed s invalidates the installed eikonal table.              */
+int grb_update_desc(grb_engine *e, const grb_process_desc *desc);
+
+/* MProcess::SetInitialState / SetBeamEnergies for the beams of the description (src/MProcess.cc:291-334): new beam
+ * energies (GeV), beam momenta and s.  Invalidates the eikonal table (rebuild with grb_build_eikonal).          */
+int grb_set_beam_energies(grb_engine *e, double ebeam1, double ebeam2);
+
+/* One row of the reference's `xscan` table (scan.csv: sqrts, xstot, xsin, xsel, xs_k): total / elastic / inelastic
+ * cross sections of the eikonal model (mb) and the integrated process cross section (barn).                    */
+typedef struct {
+  double sqrt_s;
+  double xs_tot_mb, xs_el_mb, xs_inel_mb; /* MEikonal::GetTotXS                                                */
+  double sigma, sigma_err, chi2;          /* MGraniitti::GetXS                                                 */
+  double evaluations, seconds;
+} grb_xscan_row;
+
+/* The loop of src/Program/xscan.cc:111-140 for this engine's process: for each sqrt(s) set symmetric beams of
+ * sqrt(s)/2, build the eikonal tables on the device (grb_build_eikonal), integrate (grb_integrate, one rank).
+ * The engine is left at the last energy.                                                                        */
+int grb_xscan(grb_engine *e, const double *sqrt_s, int n, const grb_vegas_param *par, grb_xscan_row *rows);
+
 /* Unit-test hook for graniitti_b200/csrc/grb_fastmath.cuh on n host values: kind 0 table-driven log, 1 table-driven
  * exp, 2 branch-free exact sqrt, 3 sqrt(), 4 branch-free exact x[i] / x[i+1], 5 operator/ (3 and 5 are the device's
  * own IEEE results the exact forms must reproduce bit for bit), 6 / 7 table-driven sin / cos,

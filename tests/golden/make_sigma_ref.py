@@ -24,6 +24,8 @@ CASES = [
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", "false", 300000, 0.002),
     ("cc_alice_pipi_con_born", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "false", 300000, 0.001),
     ("cc_alice_pipi_con_screened", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "true", 100000, 0.003),
+    # another energy (beam energies replaced in the card copy): the energy-scan caller grb_xscan
+    ("c2_alice_pipi_con_screened_7tev", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "true", 100000, 0.003, 3500.0),
 ]
 
 
@@ -31,10 +33,13 @@ def main():
     out_path = os.path.join(GOLDEN, "sigma_ref.json")
     res = json.load(open(out_path)) if os.path.exists(out_path) else {}
     only = sys.argv[1:]
-    for name, card, proc, pom, ncall, prec in CASES:
+    for case in CASES:
+        name, card, proc, pom, ncall, prec = case[:6]
         if only and name not in only:
             continue
         txt = open(os.path.join(REF_TREE, card)).read()
+        if len(case) > 6:
+            txt = re.sub(r'("ENERGY"\s*:\s*)\[[^\]]*\]', r"\g<1>[%g, %g]" % (case[6], case[6]), txt)
         txt = re.sub(r'("NCALL"\s*:\s*)\d+', r"\g<1>%d" % ncall, txt)
         txt = re.sub(r'("VEGAS"\s*:\s*\{[^}]*?"PRECISION"\s*:\s*)[0-9.eE+-]+', r"\g<1>%g" % prec, txt, flags=re.S)
         tmp = os.path.join(REF_TREE, "output", f"sigma_{name}.json")
@@ -52,6 +57,11 @@ def main():
                      "err_barn": float(m.group(2)), "ncall": ncall, "precision": prec,
                      "ref_points_per_s": float(f.group(1)) if f else None, "fid_pass": float(p.group(1)) if p else None,
                      "cores": os.cpu_count()}
+        if len(case) > 6:
+            res[name]["ebeam"] = case[6]
+            mt = re.search(r"Total:\s*([0-9.]+) mb.*?Elastic:\s*([0-9.]+) mb.*?Inelastic:\s*([0-9.]+) mb", clean, re.S)
+            if mt:
+                res[name]["xs_mb"] = [float(mt.group(k)) for k in (1, 2, 3)]
         print(name, res[name], flush=True)
         json.dump(res, open(out_path, "w"), indent=1)
 

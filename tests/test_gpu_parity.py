@@ -255,3 +255,34 @@ def test_event_generation_hit_or_miss(grb, msa, pom):
     assert a1.n_accepted + a2.n_accepted == acc.n_accepted
     assert np.array_equal(np.sort(np.concatenate([w1, w2])), np.sort(wts[1]))
     E.close()
+
+
+def test_energy_scan_and_reparameterisation(grb, msa):
+    """The callers that loop the integrator: grb_xscan = the loop of the reference's xscan program
+    (new beams -> new eikonal tables -> new integration, one engine), against the reference CLI at 7 and 13 TeV and the
+    reference's eikonal-model cross sections; grb_update_desc gives the same bits as a freshly created engine."""
+    import json
+    ref = json.load(open(os.path.join(GOLDEN, "sigma_ref.json")))
+    eik = np.load(os.path.join(GOLDEN, "eikonal_ref.npz"))
+    E = engine_for(grb, msa, "c2_alice.json", None, 1)
+    rows = E.xscan([7000.0, 13000.0], ncall=1 << 21, iters=5, precision=0.001, seed=7)
+    for row, name, key in ((rows[0], "c2_alice_pipi_con_screened_7tev", "xs_mb_7000"), (rows[1], "c2_alice_pipi_con_screened", "xs_mb_13000")):
+        r = ref[name]
+        pull = (row.sigma - r["sigma_barn"]) / np.hypot(row.sigma_err, np.hypot(r["err_barn"], 0.5e-3 * r["sigma_barn"]))
+        assert abs(pull) < 4.0 and row.chi2 < 10, (name, row.sigma, row.sigma_err, r["sigma_barn"], pull)
+        assert np.array_equal(np.round([row.xs_tot_mb, row.xs_el_mb, row.xs_inel_mb], 3), eik[key])
+    assert rows[0].sqrt_s == 7000.0 and E.desc.sqrt_s == 13000.0
+    # re-parameterisation: another Pomeron coupling and K+K- masses through grb_update_desc == a fresh engine
+    d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), "PP[CON]<F> -> K+ K-", 1)
+    u, tape = make_points(20000, 6, 8, 31, adapted=True)
+    E.update_desc(d)
+    E.set_eikonal(msa[0], msa[1], msa[2])
+    w1, f1, _ = E.eval(u.T.copy(), tape.T.copy())
+    E2 = engine_for(grb, msa, "c2_alice.json", "PP[CON]<F> -> K+ K-", 1)
+    w2, f2, _ = E2.eval(u.T.copy(), tape.T.copy())
+    assert np.array_equal(w1, w2) and np.array_equal(f1, f2) and (w1 != 0).sum() > 1000
+    # topology changes are refused
+    d4 = grb.parse_card(os.path.join(CARDS, "c5_cms_4pi.json"))
+    with pytest.raises(grb.GrbError):
+        E.update_desc(d4)
+    E.close(); E2.close()

@@ -10,7 +10,9 @@ enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY
        // Born-level kinematics for the multi-helicity loop: p1z, p1e, p2z, p2e, pX(x,y,z,e)
        IT_BK = 22,
        // <C> class loop invariants: q0y, sinh / cosh of the two leg rapidities (m3, m4, q0x ride in IT_MXSQ, IT_SHY, IT_CHY)
-       IT_CK = 30, IT_NF = 35 };
+       IT_CK = 30,
+       IT_EXC = 35,  // lts.excite1/2 bits of the point (forward N* excitation)
+       IT_NF = 36 };
 
 
 // ---- block-level VEGAS accumulation ---------------------------------------------------------------------

@@ -64,7 +64,7 @@ struct grb_engine {
 static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
 static thread_local std::string g_last_global_error;
 
-#define ITEM_NF 35  /* = IT_NF of grb_accum.cuh */
+#define ITEM_NF 36  /* = IT_NF of grb_accum.cuh */
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -82,7 +82,7 @@ static double m_of_beam(double pz, double E) {  // M4Vec::M() of (0,0,pz,E), ref
 
 // one active Regge trajectory (TUNE0): the screening kernel's one-basic-block node applies (grb_point.cuh)
 static int regge_fast_ff(const DevProc &P) {
-  return (P.ps_class == GRB_CLASS_F && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
+  return (P.ps_class == GRB_CLASS_F && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
 }
 
 // desc -> DevProc. Host libm (glibc, the reference's) evaluates the loop invariants.
@@ -91,7 +91,11 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.abi_version != GRB_ABI_VERSION) { err = "abi_version mismatch"; return GRB_ERR_ARG; }
   if (d.ps_class != GRB_CLASS_F && d.ps_class != GRB_CLASS_C) { err = "only the <F> and <C> phase-space classes are on the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.ps_class == GRB_CLASS_C && d.veto_active) { err = "<C> with veto cuts needs forward fragmentation (outside the device path)"; return GRB_ERR_UNSUPPORTED; }
-  if (d.excitation != 0) { err = "NSTARS != 0 is outside the device path"; return GRB_ERR_UNSUPPORTED; }
+  if (d.excitation != 0 && !(d.ps_class == GRB_CLASS_F && (d.proc == GRB_PROC_PP_CON || d.proc == GRB_PROC_PP_CON_MINUS))) {
+    err = "NSTARS != 0 (forward N* excitation) is on the device path for the <F> class Regge continuum PP[CON], PP[CON-]";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  if (d.excitation < 0 || d.excitation > 2) { err = "MProcess::SetExcitation: Not valid input (0,1,2)"; return GRB_ERR_ARG; }
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR &&
@@ -125,7 +129,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   }
   if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
-  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 8 : 6)) { err = "lipsdim must be 6 for <F> and 8 for <C> (two central legs) with NSTARS=0"; return GRB_ERR_ARG; }
+  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 8 : 6 + d.excitation)) { err = "lipsdim must be 6 + NSTARS for <F> and 8 for <C> (two central legs)"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_veto > GRB_MAX_VETO) { err = "too many veto domains"; return GRB_ERR_ARG; }
   if (d.fcuts.usercuts != 0 && std::abs(d.fcuts.usercuts) != 3 && std::abs(d.fcuts.usercuts) != 111) {
@@ -145,6 +149,12 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.Y_min = d.gcuts.Y_min; P.dY = d.gcuts.Y_max - d.gcuts.Y_min;
   P.gM_min = d.gcuts.M_min; P.gM_max = d.gcuts.M_max;
   P.ps_class = d.ps_class;
+  P.excitation = d.excitation;
+  P.log_M2f_min = std::log(1.09 * 1.09);  // neutron + pi+ threshold, MProcess.cc:1324-1328
+  P.dlog_M2f = std::log(d.gcuts.XI_max * d.s) - P.log_M2f_min;
+  if (d.excitation != 0 && !(d.gcuts.XI_max * d.s > 1.09 * 1.09)) { err = "MProcess::SampleForwardMasses: Forward leg Xi max is below the inelastic threshold"; return GRB_ERR_ARG; }
+  P.exc_vertex = std::sqrt(std::max(0.0, d.soft.g3P * d.soft.gN_P)) / d.soft.gN_P;
+  P.f_fM_min = d.fcuts.forward_M_min; P.f_fM_max = d.fcuts.forward_M_max;
   P.kt_min = d.gcuts.kt_min; P.dkt = d.gcuts.kt_max - d.gcuts.kt_min;
   P.rap_min = d.gcuts.rap_min; P.drap = d.gcuts.rap_max - d.gcuts.rap_min;
   P.offshell = d.offshell;

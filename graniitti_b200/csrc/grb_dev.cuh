@@ -53,6 +53,10 @@ struct DevProc {
   // <C> class sampling map (MContinuum.cc:276-331): kt = kt_min + dkt u, y_i = rap_min + drap u; weight constant
   double kt_min, dkt, rap_min, drap, w_const_C;
   int    ps_class, pad_c_;
+  // forward N* excitation (NSTARS, MProcess.cc:1317-1365,1402-1411; MRegge.cc:637-644): log-flat M^2 sampling range,
+  // sqrt(g3P gN_P) / gN_P (inelastic over elastic proton vertex coupling), forward-mass fiducial cut
+  int    excitation, pad_x_;
+  double log_M2f_min, dlog_M2f, exc_vertex, f_fM_min, f_fM_max;
   double offshell;
   // cuts
   double f_eta_min, f_eta_max, f_rap_min, f_rap_max, f_pt_min, f_pt_max, f_Et_min, f_Et_max;

@@ -627,7 +627,7 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
   // GENCUTS (reference MGraniitti::ReadGenCuts, src/MGraniitti.cc:673-823) + SetTechnicalBoundaries
   {
     grb_gencut &g = d.gcuts;
-    g.forward_pt_min = -1.0; g.forward_pt_max = -1.0; g.XI_min = 0.0; g.XI_max = 0.05;
+    g.forward_pt_min = -1.0; g.forward_pt_max = -1.0; g.XI_min = 0.0; g.XI_max = 1.0;  // gra::GENCUT defaults, MKinematics.h:1554-1576
     const Json &gc = card.at("GENCUTS");
     g.kt_min = 0.0; g.kt_max = -1.0; g.rap_min = 0.0; g.rap_max = 0.0;
     if (d.ps_class == GRB_CLASS_C) {  // reference src/MGraniitti.cc:688-745 + MContinuum::post_Constructor (src/MContinuum.cc:64-91)

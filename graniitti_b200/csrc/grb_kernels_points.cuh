@@ -42,7 +42,7 @@ __device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
   NodeKin in;
   in.ss13 = S.ss13; in.ss24 = S.ss24; in.ss14 = S.ss14; in.ss23 = S.ss23;
   in.t1 = S.t1; in.t2 = S.t2; in.t_hat = S.t_hat; in.u_hat = S.u_hat;
-  in.p1 = S.p1; in.p2 = S.p2; in.pX = S.pX;
+  in.p1 = S.p1; in.p2 = S.p2; in.pX = S.pX; in.exc = S.exc;
   return amplitude<AMP>(in, S.np4[0], S.np4[1]);
 }
 
@@ -54,7 +54,10 @@ __device__ __forceinline__ double weight_prefactor(const PointState<NN> &S) {
   const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J;                               // x 1/2 (2pi)^-5 / 4
   const double vol = (pow2(S.M_MAX) - pow2(S.M_MIN)) * (pt1 * pt2);                     // x (2pi)^2 dlog^2 dY
   const double C   = c_proc.ps_active ? S.DW / (2 * GRB_PI) : 1.0;
-  return C * psw * vol * c_proc.w_const;
+  double       fwd = 1.0;  // ForwardVolume with excitation: log-change of variable jacobian M^2 (ln M2max - ln M2min) per leg
+  if (S.exc & 1) fwd *= m2_of(S.p1) * c_proc.dlog_M2f;
+  if (S.exc & 2) fwd *= m2_of(S.p2) * c_proc.dlog_M2f;
+  return C * psw * vol * fwd * c_proc.w_const;
 }
 // <C> class: MContinuum.cc:181-183 with BNPhaseSpaceWeight (:639-658) and BNIntegralVolume (:619-637), Kf = 2
 template <int NN>
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
             it[IT_P1X * c] = L.p1x; it[IT_P1Y * c] = L.p1y; it[IT_P2X * c] = L.p2x; it[IT_P2Y * c] = L.p2y;
             it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
             it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
+            if (P.excitation) it[IT_EXC * c] = (double)L.exc;
             if (P.ps_class == GRB_CLASS_C) {
               it[IT_MXSQ * c] = L.m3; it[IT_SHY * c] = L.m4; it[IT_CHY * c] = L.qx;
               it[(IT_CK + 0) * c] = L.qy; it[(IT_CK + 1) * c] = L.sh3; it[(IT_CK + 2) * c] = L.ch3;

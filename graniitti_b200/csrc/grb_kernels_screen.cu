@@ -28,6 +28,7 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   L.m1sq = pow2(L.m1); L.m2sq = pow2(L.m2);
   L.emax = P.sqrt_s - (L.m1 + L.m2);
   L.same_mass = SAME;
+  L.exc = P.excitation ? (int)it[IT_EXC * c] : 0;
   if (FF < 0 && P.ps_class == GRB_CLASS_C) {
     L.m3 = L.mXsq; L.m4 = L.shY; L.qx = L.chY;
     L.qy = it[(IT_CK + 0) * c]; L.sh3 = it[(IT_CK + 1) * c]; L.ch3 = it[(IT_CK + 2) * c];
@@ -40,6 +41,7 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
     NodeKin B;
     B.p1.x = L.p1x; B.p1.y = L.p1y; B.p1.z = it[(IT_BK + 0) * c]; B.p1.e = it[(IT_BK + 1) * c];
     B.p2.x = L.p2x; B.p2.y = L.p2y; B.p2.z = it[(IT_BK + 2) * c]; B.p2.e = it[(IT_BK + 3) * c];
+    B.exc = L.exc;
     B.pX.x = it[(IT_BK + 4) * c]; B.pX.y = it[(IT_BK + 5) * c]; B.pX.z = it[(IT_BK + 6) * c]; B.pX.e = it[(IT_BK + 7) * c];
     const v4 &p3 = L.p3, &p4 = L.p4;
     B.ss13 = m2_of(B.p1.x + p3.x, B.p1.y + p3.y, B.p1.z + p3.z, B.p1.e + p3.e);

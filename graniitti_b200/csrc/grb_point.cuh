@@ -90,6 +90,7 @@ struct PointState {
   double t1, t2, s1, s2, t_hat, u_hat, m2, Y, Pt;
   double ss13, ss14, ss23, ss24;
   double qx, qy;           // <C> class: intermediate difference momentum q0 (MContinuum::pkt_[0])
+  int    exc;              // bit 0 / 1: forward leg 1 / 2 is an excited N* system (lts.excite1/2)
 };
 
 // reference src/MRandom.cc:82-107 RelativisticBWRandom; node constants are pre-digested on the host with
@@ -188,7 +189,18 @@ __device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, Poi
     if (trial >= 32) return false;
   }
   const double m2X = pow2(S.M_MIN) + (pow2(S.M_MAX) - pow2(S.M_MIN)) * u[5];
-  const double m1 = P.mb1, m2 = P.mb2;
+  // forward N* system masses (SampleForwardMasses, MProcess.cc:1317-1365): log-flat M^2; single excitation picks the
+  // side with one internal uniform
+  double m1 = P.mb1, m2 = P.mb2;
+  S.exc = 0;
+  if (P.excitation == 1) {
+    const double r = exp(P.log_M2f_min + P.dlog_M2f * u[6]);
+    if (dr.next() < 0.5) { m1 = msqrt(r); S.exc = 1; }
+    else { m2 = msqrt(r); S.exc = 2; }
+  } else if (P.excitation == 2) {
+    const double r1 = exp(P.log_M2f_min + P.dlog_M2f * u[6]), r2 = exp(P.log_M2f_min + P.dlog_M2f * u[7]);
+    m1 = msqrt(r1); m2 = msqrt(r2); S.exc = 3;
+  }
 
   double s1, c1, s2, c2;
   sincos(phi1, &s1, &c1);
@@ -273,7 +285,7 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
   const double phik = 2.0 * GRB_PI * u[5];
   const double y3 = P.rap_min + P.drap * u[6], y4 = P.rap_min + P.drap * u[7];
   const double m1 = P.mb1, m2 = P.mb2;
-  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0;
+  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.exc = 0;
   double s1, c1, s2, c2, sk, ck;
   sincos(phi1, &s1, &c1);
   sincos(phi2, &s2, &c2);
@@ -350,6 +362,10 @@ __device__ __forceinline__ bool fiducial_cuts(const PointState<NN> &S) {
   }
   if (!(fabs(S.t1) >= P.f_t_min && fabs(S.t1) <= P.f_t_max && fabs(S.t2) >= P.f_t_min && fabs(S.t2) <= P.f_t_max))
     return false;
+  if (S.exc) {  // forward system mass of an excited leg, MProcess.cc:1105-1119
+    if ((S.exc & 1) && !(m_of(S.p1) >= P.f_fM_min && m_of(S.p1) <= P.f_fM_max)) return false;
+    if ((S.exc & 2) && !(m_of(S.p2) >= P.f_fM_min && m_of(S.p2) <= P.f_fM_max)) return false;
+  }
   const double M = msqrt(S.m2);
   if (!(M >= P.f_M_min && M <= P.f_M_max && S.Y >= P.f_Y_min && S.Y <= P.f_Y_max && S.Pt >= P.f_Pt_min &&
         S.Pt <= P.f_Pt_max))
@@ -379,6 +395,7 @@ struct NodeKin {
   double ss13, ss24, ss14, ss23, t1, t2, t_hat, u_hat;
   v4     p1, p2;  // outgoing protons lts.pfinal[1], [2] (needed by the tensor-pomeron vertices)
   v4     pX;      // central system lts.pfinal[0] (needed by the resonance amplitudes)
+  int    exc;     // lts.excite1/2 (bits 0, 1)
 };
 typedef NodeKin ReggeIn;
 
@@ -470,6 +487,17 @@ __device__ __forceinline__ cx regge_me4(const ReggeIn &in) {
     const double g2 = P.g2_const / dF, Gt = nt / dt, Gu = nu / du;
     A.re = g2 * (tr * Gt + ur * Gu);
     A.im = g2 * (ti * Gt + ui * Gu);
+  }
+  if (P.excitation) {
+    // PomPomProtonVertex (MRegge.cc:637-644): an excited leg carries sqrt(g3P gN_P) S3FINEL(t, M^2) instead of the
+    // elastic gN_P S3F(t) that sits in g2_const / dF; S3FINEL = [|t| / (M^2 (|t| + a))]^((1 + Delta_P)/2), MForm.cc:443-449
+    double f = 1.0;
+    if (in.exc & 1) f *= P.exc_vertex * pow(fabs(in.t1) / (m2_of(in.p1) * (fabs(in.t1) + 0.5616)), 0.5 * (1 + 0.0808)) *
+                         (fma(-in.t1, P.inv_fc1, 1.0) * fma(-in.t1, P.inv_fc2, 1.0));
+    if (in.exc & 2) f *= P.exc_vertex * pow(fabs(in.t2) / (m2_of(in.p2) * (fabs(in.t2) + 0.5616)), 0.5 * (1 + 0.0808)) *
+                         (fma(-in.t2, P.inv_fc1, 1.0) * fma(-in.t2, P.inv_fc2, 1.0));
+    A.re *= f;
+    A.im *= f;
   }
   return A;
 }
@@ -757,6 +785,7 @@ struct LoopInv {
   // <C> class (MContinuum::LoopKinematics): q0 and, per central leg, mass and sinh / cosh of the rapidity re-derived
   // from the saved 4-vectors (pfinal_orig[3], [4])
   double qx, qy, m3, m4, sh3, ch3, sh4, ch4;
+  int    exc;  // lts.excite1/2 of the point
 };
 
 template <int NN>
@@ -773,6 +802,7 @@ __device__ __forceinline__ void make_loop_inv(const PointState<NN> &S, LoopInv &
   L.same_mass = fabs(L.m1 - L.m2) < 1e-9;
   L.p3 = S.np4[0];
   L.p4 = S.np4[1];
+  L.exc = S.exc;
   if (c_proc.ps_class == GRB_CLASS_C) {
     L.qx = S.qx; L.qy = S.qy;
     L.m3 = m_of(S.np4[0]); L.m4 = m_of(S.np4[1]);
@@ -820,6 +850,7 @@ __device__ __forceinline__ bool loop_node(const LoopInv &L, const PzConst &pc, d
   o.p1.x = n1x; o.p1.y = n1y; o.p1.z = p1z; o.p1.e = e1;
   o.p2.x = n2x; o.p2.y = n2y; o.p2.z = p2z; o.p2.e = e2;
   o.pX.x = Xx; o.pX.y = Xy; o.pX.z = Xz; o.pX.e = Xe;
+  o.exc = L.exc;
   return true;
 }
 
@@ -864,6 +895,7 @@ __device__ __forceinline__ bool loop_node_C(const LoopInv &L, const PzConst &pc,
   o.p1.x = n1x; o.p1.y = n1y; o.p1.z = p1z; o.p1.e = e1;
   o.p2.x = n2x; o.p2.y = n2y; o.p2.z = p2z; o.p2.e = e2;
   o.pX.x = Xx; o.pX.y = Xy; o.pX.z = Xz; o.pX.e = Xe;
+  o.exc = L.exc;
   return true;
 }
 template <bool SAME>

@@ -75,6 +75,8 @@ typedef struct {
   v4     q1, q2;
   double M_MIN, M_MAX, DW;
   v4     pkt; /* <C>: intermediate 'difference momentum' q0 (MContinuum::pkt_) */
+  int    excite1, excite2; /* lts.excite1/2: which forward leg is an excited N* system (MProcess.cc:1317-1365) */
+  double log_M2_f_min, log_M2_f_max;
   cx     hamp[GRB_MAX_HAMP];
   int    nhamp;
   /* tape of internal uniforms (reference: thread-local MRandom, src/MRandom.cc:62-65) */
@@ -309,6 +311,41 @@ static int lorentz_scalars(ost *S, int Nf) {
   return 1;
 }
 
+/* reference src/MProcess.cc:1317-1365 SampleForwardMasses: log-flat M^2 in [1.09^2, XI_max s]; single excitation picks
+ * the side with one internal uniform */
+static void sample_forward_masses(ost *S, const double *rvec, double *m1, double *m2) {
+  const grb_process_desc *d = S->d;
+  *m1 = d->beam1_mass;
+  *m2 = d->beam2_mass;
+  S->excite1 = 0;
+  S->excite2 = 0;
+  if (d->excitation != 0) {
+    const double M2_f_min = pow2(1.09), M2_f_max = d->gcuts.XI_max * d->s;
+    S->log_M2_f_min = log(M2_f_min);
+    S->log_M2_f_max = log(M2_f_max);
+    if (d->excitation == 1) {
+      const double u = S->log_M2_f_min + (S->log_M2_f_max - S->log_M2_f_min) * rvec[0];
+      const double r = exp(u);
+      if (tape_U(S, 0, 1) < 0.5) {
+        *m1 = msqrt(r);
+        S->excite1 = 1;
+      } else {
+        *m2 = msqrt(r);
+        S->excite2 = 1;
+      }
+    } else {
+      const double u1 = S->log_M2_f_min + (S->log_M2_f_max - S->log_M2_f_min) * rvec[0];
+      const double r1 = exp(u1);
+      const double u2 = S->log_M2_f_min + (S->log_M2_f_max - S->log_M2_f_min) * rvec[1];
+      const double r2 = exp(u2);
+      *m1 = msqrt(r1);
+      *m2 = msqrt(r2);
+      S->excite1 = 1;
+      S->excite2 = 1;
+    }
+  }
+}
+
 /* reference src/MFactorized.cc:307-412 B51BuildKin (symmetric beams: the lab boost of :333-340 is the
  * identity; asymmetric beams are rejected at creation) */
 static int b51_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2, double yX, double m2X,
@@ -375,7 +412,9 @@ static int b51_random_kin(ost *S, const double *r) {
     if (trials > 100000 || S->tape_overrun) return 0;
   }
   const double m2X = pow2(S->M_MIN) + (pow2(S->M_MAX) - pow2(S->M_MIN)) * r[5];
-  return b51_build_kin(S, pt1, pt2, phi1, phi2, yX, m2X, d->beam1_mass, d->beam2_mass);
+  double m1, m2;
+  sample_forward_masses(S, r + 6, &m1, &m2);
+  return b51_build_kin(S, pt1, pt2, phi1, phi2, yX, m2X, m1, m2);
 }
 
 /* reference src/MFactorized.cc:84-139 LoopKinematics */
@@ -563,6 +602,8 @@ static int common_cuts(const ost *S) {
     } else {
       return 0;
     }
+    if (S->excite1 && !(v4_m(S->pfinal[1]) >= f->forward_M_min && v4_m(S->pfinal[1]) <= f->forward_M_max)) return 0;
+    if (S->excite2 && !(v4_m(S->pfinal[2]) >= f->forward_M_min && v4_m(S->pfinal[2]) <= f->forward_M_max)) return 0;
     if (msqrt(S->m2) >= f->M_min && msqrt(S->m2) <= f->M_max && S->Y >= f->Y_min && S->Y <= f->Y_max &&
         S->Pt >= f->Pt_min && S->Pt <= f->Pt_max) {
     } else {
@@ -640,11 +681,21 @@ static double meson_ff(const ost *S, double t_hat, double M2) {
 static double meson_prop(double t_hat, double M2) { return 1.0 / (t_hat - M2); }
 
 /* reference src/MRegge.cc:394-438 ME4 (+ :637-644 PomPomProtonVertex, elastic legs) */
+/* reference src/MForm.cc:443-449 S3FINEL, src/MRegge.cc:637-644 PomPomProtonVertex */
+static double s3finel(double t, double M2) {
+  const double DELTA_P = 0.0808, a = 0.5616;
+  return pow(fabs(t) / (M2 * (fabs(t) + a)), 0.5 * (1 + DELTA_P));
+}
+static void pom_pom_proton_vertex(const ost *S, double *FF_A, double *FF_B) {
+  const grb_param_soft *p = &S->d->soft;
+  *FF_A = S->excite1 ? msqrt(p->g3P * p->gN_P) * s3finel(S->t1, v4_m2(S->pfinal[1])) : p->gN_P * s3f(S, S->t1);
+  *FF_B = S->excite2 ? msqrt(p->g3P * p->gN_P) * s3finel(S->t2, v4_m2(S->pfinal[2])) : p->gN_P * s3f(S, S->t2);
+}
 static cx regge_me4(ost *S, double sign) {
   const grb_process_desc *d   = S->d;
   const double            M2_ = pow2(d->nodes[0].mass);
-  const double            FF_A  = d->soft.gN_P * s3f(S, S->t1);
-  const double            FF_B  = d->soft.gN_P * s3f(S, S->t2);
+  double                  FF_A, FF_B;
+  pom_pom_proton_vertex(S, &FF_A, &FF_B);
   const double            gpp_P = d->regge.c[0] / d->soft.gN_P;
   cx A_t = prop_only(S, S->ss[1][3], S->t1);
   A_t    = cx_scale(A_t, FF_A);
@@ -1933,7 +1984,14 @@ static double b51_integral_volume(const ost *S) {
   const double      PHI_vol = pow2(2.0 * O_PI);
   const double      J_pt    = v4_pt(S->pfinal[1]) * v4_pt(S->pfinal[2]);
   const double      PT_vol  = J_pt * pow2(log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS));
-  const double      fv      = PHI_vol * PT_vol;
+  double            fv      = PHI_vol * PT_vol;
+  if (S->d->excitation == 1) { /* MProcess.cc:1402-1411: log-change of variable jacobian */
+    const double J_M2 = S->excite1 ? v4_m2(S->pfinal[1]) : v4_m2(S->pfinal[2]);
+    fv = PHI_vol * PT_vol * J_M2 * (S->log_M2_f_max - S->log_M2_f_min);
+  } else if (S->d->excitation == 2) {
+    const double J_M2 = v4_m2(S->pfinal[1]) * v4_m2(S->pfinal[2]);
+    fv = PHI_vol * PT_vol * J_M2 * pow2(S->log_M2_f_max - S->log_M2_f_min);
+  }
   return (pow2(S->M_MAX) - pow2(S->M_MIN)) * (gc->Y_max - gc->Y_min) * fv;
 }
 
@@ -1996,7 +2054,10 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
                     int32_t *tape_used) {
   if (!d || !u || !w || !flags) return GRB_ERR_ARG;
-  if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->excitation != 0 || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
+  if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
+  /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex) */
+  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS)))
+    return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && d->n_legs != 2) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
   if (dim < d->lipsdim) return GRB_ERR_ARG;

@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import graniitti_b200 as g
-from helpers import CARDS, GOLDEN
+from helpers import CARDS, GOLDEN, card_variant
 from test_oracle_golden import CARD_OF
 msa = np.load(os.path.join(GOLDEN, "msa_pp_13000.npy"))
 for f in sorted(glob.glob(os.path.join(GOLDEN, "c*.npz"))):
@@ -12,7 +12,14 @@ for f in sorted(glob.glob(os.path.join(GOLDEN, "c*.npz"))):
         continue
     z = np.load(f)
     try:
-        E = g.Engine(card=os.path.join(CARDS, CARD_OF[str(z["card"])]), process=str(z["process"]), pomloop=int(z["pomloop"]))
+        nstars = int(z["nstars"]) if "nstars" in z.files else 0          # NSTARS edited in the run card of the golden
+        card = card_variant(os.path.join(CARDS, CARD_OF[str(z["card"])]), nstars)
+        if "qed_alpha" in z.files and int(z["qed_alpha"]):                # a tune with PARAM_STRUCTURE.QED_alpha != ZERO
+            d = g.parse_card(card, str(z["process"]), int(z["pomloop"]))
+            d.qed_alpha = int(z["qed_alpha"])
+            E = g.Engine(desc=d)
+        else:
+            E = g.Engine(card=card, process=str(z["process"]), pomloop=int(z["pomloop"]))
     except g.GrbError as e:
         print(os.path.basename(f), "ENGINE:", e); continue
     if E.desc.screening:

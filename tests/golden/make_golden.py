@@ -58,7 +58,13 @@ CASES = [
     ("cc_alice_pipi_tensor_screened", "./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<C> -> pi+ pi-", 1, 256, 8, True),
     ("cc_test_pipi_rescon_born", "./input/test.json", "PP[RES+CON]<C> -> pi+ pi-", 0, 1536, 8, True),
     # PARAM_STRUCTURE.QED_alpha != ZERO: the MG5 param-card coupling (aEWM1 = 132.507); card copy with MODELPARAM TUNE0_MG
-    ("c4_cms_mumu_yycon_mgalpha_born", "@TUNE0_MG:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1024, 8, True),
+    ("c4_cms_mumu_yycon_mgalpha_born", "@MODELPARAM=TUNE0_MG:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1024, 8, True),
+    # forward N* excitation (NSTARS = 1: one more coordinate + the side pick from the tape; 2: two more coordinates)
+    ("c2_alice_pipi_con_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c2_alice_pipi_con_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 0, 2048, 8, True),
+    ("c2_alice_pipi_con_nstar1_screened", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 512, 8, True),
+    ("c2_alice_kk_con_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 512, 8, True),
+    ("c2_alice_kk_conminus_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON-]<F> -> K+ K-", 0, 1024, 8, True),
     ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
 ]
@@ -73,19 +79,27 @@ def main():
     for i, (name, card, proc, pom, n, dt, adapted) in enumerate(CASES):
         if only and name not in only:
             continue
-        u, tape = make_points(n, 8 if "<C>" in proc else 6, dt, 1000 + i, adapted=adapted)
+        nstars = int(card[1:].split(":", 1)[0].split("=")[1]) if card.startswith("@NSTARS=") else 0
+        u, tape = make_points(n, (8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)
+        if nstars:   # forward pt up to 50 / 100 GeV with excitation: keep the log-pt coordinates where pt is O(0.05 - 3 GeV)
+            u[:, 0] = 0.55 + 0.3 * (u[:, 0] - 0.85) / 0.15
+            u[:, 1] = 0.55 + 0.3 * (u[:, 1] - 0.85) / 0.15
         qed_alpha = 0
         run_card = card
-        if card.startswith("@"):   # "@TUNE:card": run a copy of the card (written under output/) with MODELPARAM replaced
-            tune, card = card[1:].split(":", 1)
+        if card.startswith("@"):   # "@KEY=VALUE:card": run a copy of the card (written under output/) with that key replaced
+            kv, card = card[1:].split(":", 1)
+            key, val = kv.split("=")
             txt = open(os.path.join(REF_TREE, card)).read()
-            txt = re.sub(r'("MODELPARAM"\s*:\s*)"[^"]*"', r'\g<1>"%s"' % tune, txt)
+            if key == "MODELPARAM":
+                txt = re.sub(r'("MODELPARAM"\s*:\s*)"[^"]*"', r'\g<1>"%s"' % val, txt)
+                qed_alpha = 1
+            else:
+                txt = re.sub(r'("%s"\s*:\s*)\d+' % key, r"\g<1>%s" % val, txt)
             run_card = "./output/golden_%s.json" % name
             open(os.path.join(REF_TREE, run_card), "w").write(txt)
-            qed_alpha = 1
         r = ref_eval(run_card, proc, pom, u, tape, kappa=True)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
-                            tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
+                            nstars=nstars, tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
                             s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
                             nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :5])
         nz = r["W"] != 0

@@ -159,3 +159,14 @@ def make_points(n, dim, dtape, seed, adapted=True):
         u[:, 1] = 0.85 + 0.15 * u[:, 1]
     tape = rng.random((n, dtape))
     return u, tape
+
+
+def card_variant(card_path, nstars):
+    """A copy of a test card with PROCESSPARAM.NSTARS replaced (what editing the card does for `gr -i`)."""
+    import re
+    if not nstars:
+        return card_path
+    txt = re.sub(r'("NSTARS"\s*:\s*)\d+', r"\g<1>%d" % nstars, open(card_path).read())
+    out = os.path.join(tempfile.gettempdir(), "grb_%s_nstars%d_%d.json" % (os.path.basename(card_path)[:-5], nstars, os.getpid()))
+    open(out, "w").write(txt)
+    return out

@@ -3,7 +3,7 @@ import os
 
 import pytest
 
-from helpers import CARDS, ROOT, have_ref, ref_info
+from helpers import CARDS, ROOT, card_variant, have_ref, ref_info
 from graniitti_b200 import _abi
 
 REF = "/root/reference"
@@ -43,6 +43,15 @@ def test_continuum_class_flattening(grb):
     assert d.gcuts.forward_pt_max == 2.5
     d = grb.parse_card(os.path.join(CARDS, "c4_cms_mumu_lowmass.json"), "yy[CON]<C> -> mu+ mu-", 0)
     assert d.gcuts.kt_max == d.sqrt_s / 2.0      # QED / EW processes: kinematic maximum
+
+
+def test_forward_excitation_flattening(grb):
+    """NSTARS = 1, 2: one / two more integration dimensions, the technical forward pt bound of SetTechnicalBoundaries
+    (50 / 100 GeV) and gra::GENCUT's default Xi range [0, 1] when the <F> block has no "Xi"."""
+    for ns, ptmax in ((1, 50.0), (2, 100.0)):
+        d = grb.parse_card(card_variant(os.path.join(CARDS, "c2_alice.json"), ns), "PP[CON]<F> -> pi+ pi-", 0)
+        assert d.excitation == ns and d.lipsdim == 6 + ns and d.gcuts.forward_pt_max == ptmax
+        assert (d.gcuts.XI_min, d.gcuts.XI_max) == (0.0, 1.0)
 
 
 def test_cascade_tree_flattening(grb):

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import CARDS, GOLDEN, Eikonal, have_ref, make_points, oracle_eval, ref_eval
+from helpers import CARDS, GOLDEN, Eikonal, card_variant, have_ref, make_points, oracle_eval, ref_eval
 
 CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.json": "c1_test13.json",
            "./tests/processes/CMSCUTS.json": "c5_cms_4pi.json", "./tests/run_atlas_multi/ATLAS.json": "c3_atlas.json",
@@ -18,7 +18,8 @@ FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))  # c1..c5: <F> class p
 
 def load_case(grb, path):
     z = np.load(path, allow_pickle=False)
-    d = grb.parse_card(os.path.join(CARDS, CARD_OF[str(z["card"])]), str(z["process"]), int(z["pomloop"]))
+    nstars = int(z["nstars"]) if "nstars" in z.files else 0
+    d = grb.parse_card(card_variant(os.path.join(CARDS, CARD_OF[str(z["card"])]), nstars), str(z["process"]), int(z["pomloop"]))
     if "qed_alpha" in z.files:   # PARAM_STRUCTURE.QED_alpha of the tune the golden was generated with
         d.qed_alpha = int(z["qed_alpha"])
     return z, d

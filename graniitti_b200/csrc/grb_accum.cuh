@@ -57,11 +57,11 @@ __device__ __forceinline__ void hist_clear(int nb) {
   for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) s_hist[i] = 0.0;
   __syncthreads();
 }
-__device__ __forceinline__ void hist_add(int nb, int dim, uint64_t packed, double f) {
+__device__ __forceinline__ void hist_add(int nb, int dim, uint64_t packed, double f, uint64_t packed_hi = 0) {
   const double f2 = f * f;
 #pragma unroll 1
   for (int j = 0; j < dim; ++j) {
-    const int b = (int)((packed >> (8 * j)) & 0xff);
+    const int b = (int)(((j < 8 ? packed : packed_hi) >> (8 * (j & 7))) & 0xff);
     atomicAdd(&s_hist[b * dim + j], f);
     atomicAdd(&s_hist[nb + b * dim + j], f2);
   }

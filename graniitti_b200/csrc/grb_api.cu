@@ -127,9 +127,14 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
       return GRB_ERR_UNSUPPORTED;
     }
   }
-  if (d.n_legs != 2) { err = "the device path covers 2 first-level central legs"; return GRB_ERR_UNSUPPORTED; }
+  const bool me6 = d.n_legs == 4 && d.ps_class == GRB_CLASS_C && d.proc == GRB_PROC_PP_CON && d.n_nodes == 4;
+  if (d.n_legs != 2 && !me6) {
+    err = "the device path covers 2 first-level central legs, and 4 stable legs for PP[CON]<C> (the MRegge::ME6 ladder)";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  if (me6 && d.screening) { err = "PP[CON]<C> with four central legs: the screening loop is not on the device path yet"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
-  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 8 : 6 + d.excitation)) { err = "lipsdim must be 6 + NSTARS for <F> and 8 for <C> (two central legs)"; return GRB_ERR_ARG; }
+  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 : 6 + d.excitation)) { err = "lipsdim must be 6 + NSTARS for <F> and 3 Nf - 4 for <C>"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_veto > GRB_MAX_VETO) { err = "too many veto domains"; return GRB_ERR_ARG; }
   if (d.fcuts.usercuts != 0 && std::abs(d.fcuts.usercuts) != 3 && std::abs(d.fcuts.usercuts) != 111) {
@@ -172,8 +177,11 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
               0.5 / (twopi * twopi * twopi * twopi * twopi) * 0.25;
   // <C>, Kf = 2 (MContinuum.cc:181-183,619-658): 2^-4 (2pi)^-8 / 4 from the phase-space weight, dkt 2pi drap^2 and the
   // forward volume (2pi)^2 dlog^2 from the integral volume
-  P.w_const_C = (1.0 / d.S_factor) * GeV2barn / (2.0 * d.s) * (1.0 / 16.0) / std::pow(twopi, 8) * 0.25 *
-                (P.dkt * twopi * (P.drap * P.drap)) * ((twopi * twopi) * (P.dlog_pt * P.dlog_pt));
+  {
+    const int Kf = d.n_legs, Nf = Kf + 2;
+    P.w_const_C = (1.0 / d.S_factor) * GeV2barn / (2.0 * d.s) * (1.0 / std::pow(2.0, 2 * (Nf - 2))) / std::pow(twopi, 3 * Nf - 4) * 0.25 *
+                  (std::pow(P.dkt, Kf - 1) * std::pow(twopi, Kf - 1) * std::pow(P.drap, Kf)) * ((twopi * twopi) * (P.dlog_pt * P.dlog_pt));
+  }
   // Regge
   const grb_param_regge &R = d.regge;
   for (int k = 0; k < 3; ++k) {
@@ -190,6 +198,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.gN_P = d.soft.gN_P; P.fc1 = d.soft.fc1; P.fc2 = d.soft.fc2;
   P.gpp_P = R.c[0] / d.soft.gN_P;
   P.M2_leg0 = d.nodes[0].mass * d.nodes[0].mass;
+  P.M2_leg2 = d.n_nodes > 2 ? d.nodes[2].mass * d.nodes[2].mass : P.M2_leg0;
   P.b_EXP = R.b_EXP; P.a_OREAR = R.a_OREAR; P.b_OREAR = R.b_OREAR; P.b_POW = R.b_POW;
   P.me4_sign = (d.proc == GRB_PROC_PP_CON_MINUS) ? -1.0 : 1.0;
   P.inv_fc1 = 1.0 / P.fc1; P.inv_fc2 = 1.0 / P.fc2; P.inv_b_POW = 1.0 / P.b_POW;
@@ -214,6 +223,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     }
     if (d.proc == GRB_PROC_PP_CONTENSOR && d.nodes[0].spinX2 == 1) P.amp_kind = 6;  // 2xF (MTensorPomeron.cc:765-804)
     if (d.proc == GRB_PROC_YY_QED) P.amp_kind = 7;                                    // QED branch (:664-713)
+    if (me6) P.amp_kind = 8;                                                          // MRegge::ME6 ladder
     P.tp_ff_coupling = 81.0 * std::pow(d.tpom.gPNN, 4);
     P.mass_leg0 = d.nodes[0].mass;
     P.qed_e = std::sqrt(std::max(0.0, 0.0072973525693 * 4.0 * GRB_PI));  // qed::alpha_QED() = alpha_0, MQED.h:19-24,57

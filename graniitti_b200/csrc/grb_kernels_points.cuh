@@ -64,8 +64,8 @@ template <int NN>
 __device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
   const double J   = 1.0 / fabs(S.p1.z / S.p1.e - S.p2.z / S.p2.e);
   const double pt1 = msqrt(pt2_of(S.p1)), pt2 = msqrt(pt2_of(S.p2));
-  const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J * msqrt(S.qx * S.qx + S.qy * S.qy);  // x 2^-4 (2pi)^-8 / 4
-  return psw * (pt1 * pt2) * c_proc.w_const_C;                                               // x dkt 2pi drap^2 (2pi)^2 dlog^2
+  const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J * S.qprod;                          // x 2^-2Kf (2pi)^-(3Nf-4) / 4
+  return psw * (pt1 * pt2) * c_proc.w_const_C;                                               // x (dkt 2pi)^(Kf-1) drap^Kf (2pi)^2 dlog^2
 }
 
 template <int NN, bool VEGAS, int AMP>
@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += stride) {
     const int64_t idx    = base + threadIdx.x;
     const bool    active = idx < a.n;
-    double        u[GRB_MAX_DIM > 8 ? 8 : GRB_MAX_DIM];
-    uint64_t      packed = 0;
+    constexpr int UD = (AMP == AMP_REGGE_ME6) ? 14 : 8;   // coordinates: <F> 6 (+2 N*), <C> 8 (two legs), 14 (four legs)
+    double        u[UD];
+    uint64_t      packed = 0, packed_hi = 0;                // VEGAS bin per dimension, 8 bits each
+    Ladder4       X4;                                      // four-leg ladder scalars (AMP_REGGE_ME6 only)
     double        vw     = 1.0;
     PointState<NN> S;
     bool kin = false, fid = false, veto = false, overrun = false;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
         dr.pos = 0; dr.overrun = false;
         // reference src/MGraniitti.cc:1357-1375: bin pick + in-bin offset, vegasweight = prod zo*BINS
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < UD; ++j)
           if (j < dim) {
             const double zn  = dr.next() * a.bins + 1.0;
             unsigned     ind = (unsigned)zn;
@@ -111,17 +113,20 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
             }
             u[j] = 0.0 + ac * 1.0;
             vw *= zo * a.bins;
-            packed |= (uint64_t)(ind - 1) << (8 * j);
+            if (j < 8) packed |= (uint64_t)(ind - 1) << (8 * j);
+            else packed_hi |= (uint64_t)(ind - 1) << (8 * (j - 8));
           }
-        kin     = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
+        if (AMP == AMP_REGGE_ME6) kin = point_kinematics_C4<NN>(u, dr, S, X4);
+        else kin = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       } else {
         DrawsSoA dr;
         dr.u = a.u; dr.tape = a.tape; dr.n = a.ld; dr.idx = idx; dr.dtape = a.dtape; dr.pos = 0; dr.overrun = false;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < UD; ++j)
           if (j < dim) u[j] = dr.coord(j);
-        kin     = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
+        if (AMP == AMP_REGGE_ME6) kin = point_kinematics_C4<NN>(u, dr, S, X4);
+        else kin = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       }
       if (kin) {  // on failure the reference evaluates the cuts on stale state: flags are don't-care
@@ -135,7 +140,8 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
     cx         h0 = {0.0, 0.0};
     double     pref = 0.0;
     if (valid) {
-      h0   = born_amplitude<NN, AMP>(S);
+      if (AMP == AMP_REGGE_ME6) h0 = regge_me6(S.t1, S.t2, X4);
+      else h0 = born_amplitude<NN, AMP>(S);
       pref = P.ps_class == GRB_CLASS_C ? weight_prefactor_C<NN>(S) : weight_prefactor<NN>(S);
       if (!P.screening) {
         W = pref * (h0.re * h0.re + h0.im * h0.im);
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
           ts.f2sum += f * f;
           ts.maxW = fmax(ts.maxW, W);
           ts.maxf = fmax(ts.maxf, f);
-          hist_add(nb, dim, packed, f);
+          hist_add(nb, dim, packed, f, packed_hi);
           if (a.mode == GRB_MODE_GENERATE) {
             const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
             if (es >= 0) {

@@ -183,6 +183,8 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
     if (regge_ff == 1) { launch_screen_t<4, AMP_REGGE, 1>(a, sm_count, st); return 2; }
     if (regge_ff == 2) { launch_screen_t<4, AMP_REGGE, 2>(a, sm_count, st); return 2; }
   }
+  if (!nofast && regge_ff == 2 && minb == 3) { launch_screen_t<3, AMP_REGGE, 2>(a, sm_count, st); return 2; }  // occupancy probes
+  if (!nofast && regge_ff == 2 && minb == 5) { launch_screen_t<5, AMP_REGGE, 2>(a, sm_count, st); return 2; }
   switch (minb) {
     case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;
     case 5: launch_screen_t<5, AMP_REGGE>(a, sm_count, st); break;

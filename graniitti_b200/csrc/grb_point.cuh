@@ -91,6 +91,7 @@ struct PointState {
   double ss13, ss14, ss23, ss24;
   double qx, qy;           // <C> class: intermediate difference momentum q0 (MContinuum::pkt_[0])
   int    exc;              // bit 0 / 1: forward leg 1 / 2 is an excited N* system (lts.excite1/2)
+  double qprod;            // <C> class: prod_i |q_i| of the intermediate difference momenta (BNPhaseSpaceWeight)
 };
 
 // reference src/MRandom.cc:82-107 RelativisticBWRandom; node constants are pre-digested on the host with
@@ -293,6 +294,7 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
   S.p1.x = pt1 * c1; S.p1.y = pt1 * s1;
   S.p2.x = pt2 * c2; S.p2.y = pt2 * s2;
   S.qx = kt * ck; S.qy = kt * sk;
+  S.qprod = 1.0 * msqrt(S.qx * S.qx + S.qy * S.qy);
   const double wx = S.p1.x + S.p2.x, wy = S.p1.y + S.p2.y;
   v4 &p3 = S.np4[0], &p4 = S.np4[1];
   p3.x = (S.qx - wx) * (1.0 / 2.0); p3.y = (S.qy - wy) * (1.0 / 2.0);
@@ -317,6 +319,164 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
   }
   if (!cascade_decays<NN>(dr, S)) return false;
   return lorentz_scalars(S);
+}
+
+// ---- <C> class, four central legs (2 -> 6 direct, 14 coordinates) + the Regge ladder MRegge::ME6 ---------------------
+// u = [pt1, pt2, phi1, phi2, kt_1..3, phi_1..3, y_1..4]; BLinearSystem with the Kf = 4 inverse (MContinuum.cc:485-488).
+// The ladder needs s_1a, s_2a (4 + 4), s_ab (6 pairs), t-type scalars tt_1[a], tt_2[a] (4 + 4) and tt_xy[a][b] (6 pairs).
+struct Ladder4 {
+  double s1a[4], s2a[4], sab[6], tt1[4], tt2[4], txy[6];  // pair index of (a < b): a*(7-a)/2 + b - a - 1 (a, b = 0..3)
+};
+__device__ __forceinline__ int pair4(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * (7 - a) / 2 + b - a - 1; }
+
+template <int NN, class Draws>
+__device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, PointState<NN> &S, Ladder4 &X) {
+  const DevProc &P = c_proc;
+  const double   pt1  = exp(P.log_pt0 + P.dlog_pt * u[0]);
+  const double   pt2  = exp(P.log_pt0 + P.dlog_pt * u[1]);
+  const double   phi1 = 2.0 * GRB_PI * u[2];
+  const double   phi2 = 2.0 * GRB_PI * u[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S.moff[i % NN] = offshell_mass(i, dr);
+  const double m1 = P.mb1, m2 = P.mb2;
+  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.exc = 0; S.qx = 0.0; S.qy = 0.0;
+  double s1, c1, s2, c2;
+  sincos(phi1, &s1, &c1);
+  sincos(phi2, &s2, &c2);
+  S.p1.x = pt1 * c1; S.p1.y = pt1 * s1;
+  S.p2.x = pt2 * c2; S.p2.y = pt2 * s2;
+  const double wx = S.p1.x + S.p2.x, wy = S.p1.y + S.p2.y;
+  double bx[4], by[4];
+  S.qprod = 1.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double kt = P.kt_min + P.dkt * u[4 + i];
+    double       sk, ck;
+    sincos(2.0 * GRB_PI * u[7 + i], &sk, &ck);
+    const double qx = kt * ck, qy = kt * sk;
+    S.qprod *= msqrt(qx * qx + qy * qy);
+    if (i == 0) { bx[0] = qx - wx; by[0] = qy - wy; }
+    bx[i + 1] = qx * (-1.0) - wx; by[i + 1] = qy * (-1.0) - wy;
+  }
+  const double A[4][4] = {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
+                          {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
+                          {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0},
+                          {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}};
+  S.pX.x = 0.0; S.pX.y = 0.0; S.pX.z = 0.0; S.pX.e = 0.0;
+  double sumM = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v4 &p = S.np4[i % NN];
+    p.x = ((((0.0 + bx[0] * A[i][0]) + bx[1] * A[i][1]) + bx[2] * A[i][2]) + bx[3] * A[i][3]);
+    p.y = ((((0.0 + by[0] * A[i][0]) + by[1] * A[i][1]) + by[2] * A[i][2]) + by[3] * A[i][3]);
+    const double y  = P.rap_min + P.drap * u[10 + i];
+    const double mt = msqrt(pow2(S.moff[i % NN]) + pt2_of(p));
+    p.z = mt * sinh(y); p.e = mt * cosh(y);
+    S.pX.x += p.x; S.pX.y += p.y; S.pX.z += p.z; S.pX.e += p.e;
+  }
+  if (S.pX.e > P.sqrt_s) return false;
+  PzConst pc;
+  pc.s = P.s; pc.t7 = P.sqrt_s; pc.t9 = P.s_pow15; pc.t14 = P.s * P.s;
+  const double p1z = solve_pz(m1, m2, pt1, pt2, S.pX.z, S.pX.e, pc);
+  const double p2z = -(S.pX.z + p1z);
+  if (p1z < 0 || p2z > 0 || isnan(p1z)) return false;
+  S.p1.z = p1z; S.p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
+  S.p2.z = p2z; S.p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sumM += m_of(S.np4[i % NN]);
+  if (m_of(S.pX) < sumM) return false;
+  {
+    const double dx = 0.0 - ((S.p1.x + S.p2.x) + S.pX.x), dy = 0.0 - ((S.p1.y + S.p2.y) + S.pX.y);
+    const double dz = P.bsum_z - ((S.p1.z + S.p2.z) + S.pX.z), de = P.bsum_e - ((S.p1.e + S.p2.e) + S.pX.e);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  // Lorentz scalars (MProcess.cc:1499-1584): every pair mass^2 must be >= 0, t1, t2 <= 0
+  S.s1 = m2_of(S.p1.x + S.pX.x, S.p1.y + S.pX.y, S.p1.z + S.pX.z, S.p1.e + S.pX.e);
+  S.s2 = m2_of(S.p2.x + S.pX.x, S.p2.y + S.pX.y, S.p2.z + S.pX.z, S.p2.e + S.pX.e);
+  const double s12 = m2_of(S.p1.x + S.p2.x, S.p1.y + S.p2.y, S.p1.z + S.p2.z, S.p1.e + S.p2.e);
+  bool ok = !(S.s1 < 0 || S.s2 < 0 || s12 < 0);
+  const double q1x = 0.0 - S.p1.x, q1y = 0.0 - S.p1.y, q1z = P.pb1z - S.p1.z, q1e = P.pb1e - S.p1.e;
+  const double q2x = 0.0 - S.p2.x, q2y = 0.0 - S.p2.y, q2z = P.pb2z - S.p2.z, q2e = P.pb2e - S.p2.e;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const v4 &pa = S.np4[a % NN];
+    X.s1a[a] = m2_of(S.p1.x + pa.x, S.p1.y + pa.y, S.p1.z + pa.z, S.p1.e + pa.e);
+    X.s2a[a] = m2_of(S.p2.x + pa.x, S.p2.y + pa.y, S.p2.z + pa.z, S.p2.e + pa.e);
+    const double s0a = m2_of(S.pX.x + pa.x, S.pX.y + pa.y, S.pX.z + pa.z, S.pX.e + pa.e);
+    ok = ok && !(X.s1a[a] < 0 || X.s2a[a] < 0 || s0a < 0);
+    X.tt1[a] = m2_of(q1x - pa.x, q1y - pa.y, q1z - pa.z, q1e - pa.e);
+    X.tt2[a] = m2_of(q2x - pa.x, q2y - pa.y, q2z - pa.z, q2e - pa.e);
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const v4 &pb = S.np4[b % NN];
+      const int k  = a * (7 - a) / 2 + b - a - 1;
+      X.sab[k] = m2_of(pa.x + pb.x, pa.y + pb.y, pa.z + pb.z, pa.e + pb.e);
+      ok = ok && !(X.sab[k] < 0);
+      X.txy[k] = m2_of((q1x - pa.x) - pb.x, (q1y - pa.y) - pb.y, (q1z - pa.z) - pb.z, (q1e - pa.e) - pb.e);
+    }
+  }
+  if (!ok) return false;
+  S.t1 = m2_of(q1x, q1y, q1z, q1e);
+  S.t2 = m2_of(q2x, q2y, q2z, q2e);
+  if (S.t1 > 0 || S.t2 > 0) return false;
+  S.t_hat = 0.0; S.u_hat = 0.0; S.ss13 = X.s1a[0]; S.ss14 = X.s1a[1]; S.ss23 = X.s2a[0]; S.ss24 = X.s2a[1];
+  S.m2 = m2_of(S.pX);
+  S.Y  = rap_of(S.pX);
+  S.Pt = msqrt(pt2_of(S.pX));
+  return true;
+}
+
+// ff(x)^2-type pieces of the ladder: Meson_FF and Meson_prop (MRegge.cc:1155-1218) by run-time form-factor type
+__device__ __forceinline__ double meson_ff1(double x, double M2) {
+  const DevProc &P  = c_proc;
+  const double   tp = x - M2;
+  if (P.offshellFF == 2) return 1.0 / (1.0 - tp / P.b_POW);
+  if (P.offshellFF == 0) return exp(-P.b_EXP * fabs(tp));
+  return exp(-P.b_OREAR * msqrt(fabs(tp) + pow2(P.a_OREAR)) + P.a_OREAR * P.b_OREAR);
+}
+__device__ __forceinline__ cx regge_prop(double s, double t);
+// reference src/MRegge.cc:470-540 ME6: sum over the 24 orderings (a, b, c, d) of the four legs (lexicographic order of
+// math::Permutations) of  Prop(s_1a, t1) F_A ff(tt_a) g / (tt_a - M_A^2) ff_A(tt_ab) g Prop(s_bc, tt_ab) ff_B(tt_ab) g
+// / (tt_d - M_B^2) ff(tt_d) g Prop(s_2d, t2) F_B  with tt_a = (q1 - p_a)^2, tt_ab = (q1 - p_a - p_b)^2, tt_d = (q2 - p_d)^2
+__device__ __forceinline__ cx regge_me6(const double t1, const double t2, const Ladder4 &X) {
+  const DevProc &P = c_proc;
+  const double FA = P.gN_P * (1.0 / (1 - t1 / P.fc1)) * (1.0 / (1 - t1 / P.fc2));
+  const double FB = P.gN_P * (1.0 / (1 - t2 / P.fc1)) * (1.0 / (1 - t2 / P.fc2));
+  const double g  = P.gpp_P;
+  cx P1[4], P2[4];
+  double G1[4], G2[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    P1[a] = regge_prop(X.s1a[a], t1);
+    P2[a] = regge_prop(X.s2a[a], t2);
+    const double fa = meson_ff1(X.tt1[a], P.M2_leg0), fd = meson_ff1(X.tt2[a], P.M2_leg2);
+    G1[a] = fa * g * (1.0 / (X.tt1[a] - P.M2_leg0));
+    G2[a] = g * (1.0 / (X.tt2[a] - P.M2_leg2)) * fd * g;
+  }
+  cx A = {0.0, 0.0};
+#pragma unroll 1
+  for (int a = 0; a < 4; ++a)
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+      if (b == a) continue;
+      const double tab = X.txy[pair4(a, b)];
+      const double Fab = meson_ff1(tab, P.M2_leg0) * g, Fab2 = meson_ff1(tab, P.M2_leg2);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        if (c == a || c == b) continue;
+        const int d  = 6 - a - b - c;
+        const cx  Pm = regge_prop(X.sab[pair4(b, c)], tab);
+        // (((P1 FA G1 ...) Fab) Pm) Fab2 G2) P2 FB
+        cx sub = {P1[a].re * FA * G1[a] * Fab, P1[a].im * FA * G1[a] * Fab};
+        sub = {sub.re * Pm.re - sub.im * Pm.im, sub.re * Pm.im + sub.im * Pm.re};
+        const double r = Fab2 * G2[d];
+        sub = {sub.re * r, sub.im * r};
+        sub = {(sub.re * P2[d].re - sub.im * P2[d].im) * FB, (sub.re * P2[d].im + sub.im * P2[d].re) * FB};
+        A.re += sub.re;
+        A.im += sub.im;
+      }
+    }
+  return A;
 }
 
 // ---- cuts (reference src/MProcess.cc:1069-1175, src/MUserCuts.cc:21-75) ------------------------------------
@@ -734,7 +894,7 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
 namespace grb {
 
 enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5,
-       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7 };
+       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7, AMP_REGGE_ME6 = 8 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
@@ -744,6 +904,7 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
   }
   if (AMP == AMP_TENSOR_2XF) return {sqrt(tensor_2xF_amp2(in, p3, p4)), 0.0};  // unscreened only
   if (AMP == AMP_YY_QED) return {sqrt(yy_qed_amp2(in, p3, p4)), 0.0};          // unscreened only
+  if (AMP == AMP_REGGE_ME6) return {0.0, 0.0};  // four-leg ladder: evaluated in k_points from its own scalars (unscreened only)
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {

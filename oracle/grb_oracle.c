@@ -74,7 +74,8 @@ typedef struct {
   double s1, s2, t1, t2, t_hat, u_hat, m2, Y, Pt, x1, x2, qt1, qt2;
   v4     q1, q2;
   double M_MIN, M_MAX, DW;
-  v4     pkt; /* <C>: intermediate 'difference momentum' q0 (MContinuum::pkt_) */
+  v4     pkt[7]; /* <C>: intermediate 'difference momenta' q_i (MContinuum::pkt_), Kf - 1 of them */
+  double tt_1[10], tt_2[10], tt_xy[10][10]; /* t-type scalars of the ladders (MProcess.cc:1558-1564) */
   int    excite1, excite2; /* lts.excite1/2: which forward leg is an excited N* system (MProcess.cc:1317-1365) */
   double log_M2_f_min, log_M2_f_max;
   cx     hamp[GRB_MAX_HAMP];
@@ -301,6 +302,10 @@ static int lorentz_scalars(ost *S, int Nf) {
     S->t_hat = v4_m2(v4_sub(S->q1, S->node_p4[0]));
     S->u_hat = v4_m2(v4_sub(S->q1, S->node_p4[1]));
   }
+  for (int i = 3; i <= Nf; ++i) S->tt_1[i] = v4_m2(v4_sub(S->q1, S->pfinal[i]));
+  for (int i = 3; i <= Nf; ++i)
+    for (int j = 3; j <= Nf; ++j) S->tt_xy[i][j] = v4_m2(v4_sub(v4_sub(S->q1, S->pfinal[i]), S->pfinal[j]));
+  for (int i = 3; i <= Nf; ++i) S->tt_2[i] = v4_m2(v4_sub(S->q2, S->pfinal[i]));
   S->x1  = (1 - S->pfinal[1].z / S->pbeam1.z);
   S->x2  = (1 - S->pfinal[2].z / S->pbeam2.z);
   S->qt1 = v4_pt(S->q1);
@@ -450,32 +455,41 @@ static int loop_kinematics(ost *S, double p1px, double p1py, double p2px, double
 
 /* ---- <C> phase-space class: MContinuum, 2 -> N direct (restated for N = 4, two central legs) ---------------------- */
 
-/* reference src/MContinuum.cc:438-538 BLinearSystem for Kf = 2: p = A b with A = diag(1/2, 1/2), b0 = q0 - (p1+p2),
- * b1 = -q0 - (p1+p2); the loop adds b[j] * A[i][j] for both j (the zero entries add signed zeros) */
-static void blinear2(v4 q0, v4 p1f, v4 p2f, v4 p[2]) {
-  const v4 w  = v4_add(p1f, p2f);
-  const v4 b0 = v4_sub(q0, w);
-  const v4 b1 = v4_sub((v4){q0.x * (-1.0), q0.y * (-1.0), q0.z * (-1.0), q0.e * (-1.0)}, w);
-  const double A[2][2] = {{1.0 / 2.0, 0.0}, {0.0, 1.0 / 2.0}};
-  for (int i = 0; i < 2; ++i) {
+/* reference src/MContinuum.cc:438-538 BLinearSystem: p = A b with b0 = q0 - (p1+p2), b_i = -q_{i-1} - (p1+p2); A is the
+ * inverse of the ladder's linear system (:480-516, tabulated there for Kf = 2..8; Kf = 2 and 4 restated).  The loop adds
+ * b[j] * A[i][j] for every j (zero entries add signed zeros). */
+static const double o_blin2[2][2] = {{1.0 / 2.0, 0.0}, {0.0, 1.0 / 2.0}};
+static const double o_blin4[4][4] = {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
+                                     {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
+                                     {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0},
+                                     {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}};
+static void blinear(int Kf, const v4 *q, v4 p1f, v4 p2f, v4 *p) {
+  const v4 w = v4_add(p1f, p2f);
+  v4 b[8];
+  for (int i = 0; i < Kf; ++i)
+    b[i] = (i == 0) ? v4_sub(q[0], w) : v4_sub((v4){q[i - 1].x * (-1.0), q[i - 1].y * (-1.0), q[i - 1].z * (-1.0), q[i - 1].e * (-1.0)}, w);
+  for (int i = 0; i < Kf; ++i) {
     v4 acc = {0, 0, 0, 0};
-    acc = v4_add(acc, (v4){b0.x * A[i][0], b0.y * A[i][0], b0.z * A[i][0], b0.e * A[i][0]});
-    acc = v4_add(acc, (v4){b1.x * A[i][1], b1.y * A[i][1], b1.z * A[i][1], b1.e * A[i][1]});
+    for (int j = 0; j < Kf; ++j) {
+      const double a = (Kf == 2) ? o_blin2[i][j] : o_blin4[i][j];
+      acc = v4_add(acc, (v4){b[j].x * a, b[j].y * a, b[j].z * a, b[j].e * a});
+    }
     p[i] = acc;
   }
 }
 
 /* reference src/MContinuum.cc:334-435 BNBuildKin (symmetric beams, no forward excitation, veto cuts inactive) */
-static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2, double kt, double phik,
-                        const double y[2], double m1, double m2) {
+static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2, const double *kt, const double *phik,
+                        const double *y, double m1, double m2) {
   const grb_process_desc *d = S->d;
+  const int Kf = d->n_legs;
   v4 p1 = {pt1 * cos(phi1), pt1 * sin(phi1), 0, 0};
   v4 p2 = {pt2 * cos(phi2), pt2 * sin(phi2), 0, 0};
-  S->pkt = (v4){kt * cos(phik), kt * sin(phik), 0, 0};
-  v4 p[2];
-  blinear2(S->pkt, p1, p2, p);
+  for (int i = 0; i < Kf - 1; ++i) S->pkt[i] = (v4){kt[i] * cos(phik[i]), kt[i] * sin(phik[i]), 0, 0};
+  v4 p[8];
+  blinear(Kf, S->pkt, p1, p2, p);
   v4 sumP = {0, 0, 0, 0};
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < Kf; ++i) {
     const double m  = S->node_moff[i];
     const double mt = msqrt(pow2(m) + v4_pt2(p[i]));
     p[i].z = mt * sinh(y[i]);
@@ -495,7 +509,7 @@ static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2
   S->pfinal[2] = p2;
   S->pfinal[0] = sumP;
   double sumM = 0;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < Kf; ++i) {
     S->node_p4[i]    = p[i];
     S->pfinal[i + 3] = p[i];
     sumM += v4_m(p[i]);
@@ -507,10 +521,11 @@ static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2
   return lorentz_scalars(S, d->n_legs + 2);
 }
 
-/* reference src/MContinuum.cc:276-331 BNRandomKin, Kf = 2: r = [pt1, pt2, phi1, phi2, kt, phi_k, y3, y4] */
+/* reference src/MContinuum.cc:276-331 BNRandomKin: r = [pt1, pt2, phi1, phi2, kt_1..kt_{Kf-1}, phi_1..phi_{Kf-1}, y_1..y_Kf] */
 static int bn_random_kin(ost *S, const double *r) {
   const grb_process_desc *d  = S->d;
   const grb_gencut *      gc = &d->gcuts;
+  const int               Kf = d->n_legs;
   const double u1 = log(gc->forward_pt_min + O_ZERO_EPS) +
                     (log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS)) * r[0];
   const double u2 = log(gc->forward_pt_min + O_ZERO_EPS) +
@@ -518,9 +533,11 @@ static int bn_random_kin(ost *S, const double *r) {
   const double pt1 = exp(u1), pt2 = exp(u2);
   const double phi1 = 2.0 * O_PI * r[2], phi2 = 2.0 * O_PI * r[3];
   for (int i = 0; i < d->n_legs; ++i) S->node_moff[i] = offshell_mass(S, i);
-  const double kt   = gc->kt_min + (gc->kt_max - gc->kt_min) * r[4];
-  const double phik = 2.0 * O_PI * r[5];
-  const double y[2] = {gc->rap_min + (gc->rap_max - gc->rap_min) * r[6], gc->rap_min + (gc->rap_max - gc->rap_min) * r[7]};
+  double kt[7], phik[7], y[8];
+  int    ind = 4;
+  for (int i = 0; i < Kf - 1; ++i) kt[i] = gc->kt_min + (gc->kt_max - gc->kt_min) * r[ind++];
+  for (int i = 0; i < Kf - 1; ++i) phik[i] = 2.0 * O_PI * r[ind++];
+  for (int i = 0; i < Kf; ++i) y[i] = gc->rap_min + (gc->rap_max - gc->rap_min) * r[ind++];
   return bn_build_kin(S, pt1, pt2, phi1, phi2, kt, phik, y, d->beam1_mass, d->beam2_mass);
 }
 
@@ -528,14 +545,15 @@ static int bn_random_kin(ost *S, const double *r) {
  * lts.decaytree[i].p4, which t_hat / u_hat and the tensor-pomeron vertices keep reading */
 static int loop_kinematics_C(ost *S, double p1px, double p1py, double p2px, double p2py) {
   const grb_process_desc *d = S->d;
+  const int Kf = d->n_legs;
   S->pfinal[1].x = p1px;
   S->pfinal[1].y = p1py;
   S->pfinal[2].x = p2px;
   S->pfinal[2].y = p2py;
-  v4 p[2];
-  blinear2(S->pkt, S->pfinal[1], S->pfinal[2], p);
+  v4 p[8];
+  blinear(Kf, S->pkt, S->pfinal[1], S->pfinal[2], p);
   v4 sumP = {0, 0, 0, 0};
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < Kf; ++i) {
     const double y = v4_rap(S->pfinal_orig[i + 3]);
     const double m = v4_m(S->pfinal_orig[i + 3]);
     S->pfinal[i + 3].x = p[i].x;
@@ -1592,6 +1610,50 @@ static cx o_photo_prop(const ost *S, double s, double t, double m2) {
   return cx_scale(cx_scale(eta, pow(s / W02, alpha)), FF);
 }
 /* reference src/MRegge.cc:677-706 ME3 */
+/* reference src/MRegge.cc:470-540 ME6: the 2 -> 6 ladder summed over the 24 orderings (a, b, c, d) of the four central
+ * legs, in the order of math::Permutations (MMath.h:662-720: lexicographic successor) */
+static cx regge_me6(ost *S) {
+  const grb_process_desc *d = S->d;
+  const double M2_A = pow2(d->nodes[0].mass), M2_B = pow2(d->nodes[2].mass);
+  double FF_A, FF_B;
+  pom_pom_proton_vertex(S, &FF_A, &FF_B);
+  const double gpp_P = d->regge.c[0] / d->soft.gN_P;
+  cx  A = {0, 0};
+  int set[4] = {3, 4, 5, 6};
+  for (;;) {
+    const int a = set[0], b = set[1], c = set[2], dd = set[3];
+    const double tt_ab = S->tt_1[a], tt_bc = S->tt_xy[a][b], tt_cd = S->tt_2[dd];
+    cx sub = prop_only(S, S->ss[1][a], S->t1);
+    sub = cx_scale(sub, FF_A);
+    sub = cx_scale(sub, meson_ff(S, tt_ab, M2_A));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_scale(sub, meson_prop(tt_ab, M2_A));
+    sub = cx_scale(sub, meson_ff(S, tt_bc, M2_A));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_mul(sub, prop_only(S, S->ss[b][c], tt_bc));
+    sub = cx_scale(sub, meson_ff(S, tt_bc, M2_B));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_scale(sub, meson_prop(tt_cd, M2_B));
+    sub = cx_scale(sub, meson_ff(S, tt_cd, M2_B));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_mul(sub, prop_only(S, S->ss[2][dd], S->t2));
+    sub = cx_scale(sub, FF_B);
+    A = cx_add(A, sub);
+    /* next permutation in lexicographic order */
+    int j = -1;
+    for (int i = 0; i < 3; ++i)
+      if (set[i] < set[i + 1]) j = i;
+    if (j < 0) break;
+    int l = j + 1;
+    for (int i = j + 1; i < 4; ++i)
+      if (set[j] < set[i]) l = i;
+    int t = set[j]; set[j] = set[l]; set[l] = t;
+    for (int lo = j + 1, hi = 3; lo < hi; ++lo, --hi) { t = set[lo]; set[lo] = set[hi]; set[hi] = t; }
+  }
+  S->hamp[0] = A;
+  S->nhamp   = 1;
+  return A;
+}
 static cx regge_me3(ost *S, const grb_resonance *r) {
   const double FF_A = S->d->soft.gN_P * s3f(S, S->t1), FF_B = S->d->soft.gN_P * s3f(S, S->t2);
   cx A = cx_scale(prop_only(S, S->s1, S->t1), 2.0);
@@ -1854,7 +1916,7 @@ static double yy_con_amp2(ost *S) {
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
-    case GRB_PROC_PP_CON: return cx_abs2(regge_me4(S, 1.0));
+    case GRB_PROC_PP_CON: return S->d->n_legs == 4 ? cx_abs2(regge_me6(S)) : cx_abs2(regge_me4(S, 1.0));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
     case GRB_PROC_YY_CON: {
       const int apdg = abs(S->d->nodes[0].pdg);
@@ -2000,7 +2062,7 @@ static double bn_ps_weight(const ost *S) {
   const double J = 1.0 / fabs(S->pfinal[1].z / S->pfinal[1].e - S->pfinal[2].z / S->pfinal[2].e);
   const int    Nf   = S->d->n_legs + 2;
   double       PROD = 1.0;
-  PROD *= v4_pt(S->pkt);
+  for (int i = 0; i < S->d->n_legs - 1; ++i) PROD *= v4_pt(S->pkt[i]);
   return (1.0 / pow(2, 2 * (Nf - 2))) * (1.0 / pow(2.0 * O_PI, 3 * Nf - 4)) * (v4_pt(S->pfinal[1]) / (2.0 * S->pfinal[1].e)) *
          (v4_pt(S->pfinal[2]) / (2.0 * S->pfinal[2].e)) * J * PROD;
 }
@@ -2058,7 +2120,7 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
   /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex) */
   if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS)))
     return GRB_ERR_UNSUPPORTED;
-  if (d->ps_class == GRB_CLASS_C && d->n_legs != 2) return GRB_ERR_UNSUPPORTED;
+  if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
   if (dim < d->lipsdim) return GRB_ERR_ARG;
   ost *S = (ost *)calloc(1, sizeof(ost));

@@ -65,6 +65,9 @@ CASES = [
     ("c2_alice_pipi_con_nstar1_screened", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 512, 8, True),
     ("c2_alice_kk_con_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 512, 8, True),
     ("c2_alice_kk_conminus_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON-]<F> -> K+ K-", 0, 1024, 8, True),
+    # <C> class with four central legs: the 2 -> 6 ladder MRegge::ME6 (14 integration dimensions)
+    ("cc4_cms_4pi_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 2048, 16, True),
+    ("cc4_cms_2pi2k_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K-", 0, 1536, 16, True),
     ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
 ]
@@ -80,7 +83,9 @@ def main():
         if only and name not in only:
             continue
         nstars = int(card[1:].split(":", 1)[0].split("=")[1]) if card.startswith("@NSTARS=") else 0
-        u, tape = make_points(n, (8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)
+        u, tape = make_points(n, (14 if name.startswith("cc4_") else 8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)
+        if name.startswith("cc4_"):   # keep the three intermediate kt below ~0.75 GeV (flat kt up to 2.5 GeV is mostly cut away)
+            u[:, 4:7] *= 0.3
         if nstars:   # forward pt up to 50 / 100 GeV with excitation: keep the log-pt coordinates where pt is O(0.05 - 3 GeV)
             u[:, 0] = 0.55 + 0.3 * (u[:, 0] - 0.85) / 0.15
             u[:, 1] = 0.55 + 0.3 * (u[:, 1] - 0.85) / 0.15

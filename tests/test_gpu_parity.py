@@ -303,3 +303,37 @@ def test_energy_scan_and_reparameterisation(grb, msa):
     with pytest.raises(grb.GrbError):
         E.update_desc(d4)
     E.close(); E2.close()
+
+
+def test_four_leg_ladder_vegas_path(grb, msa):
+    """PP[CON]<C> -> pi+ pi- pi+ pi- (MRegge::ME6, 14 VEGAS dimensions): the device iteration equals grb_eval on the same
+    Philox points regenerated on the host, the histogram marginals equal the scalar sums in all 14 dimensions (bins of
+    the dimensions 8..13 travel in a second packed word), and a full adaptive integration converges."""
+    from philox_ref import philox_points
+    E = engine_for(grb, msa, "c5_cms_4pi.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 0)
+    bins, dim, N = 128, 14, 8192
+    assert E.desc.lipsdim == dim
+    rng = np.random.default_rng(9)
+    edges = np.sort(rng.random((bins - 1, dim)), axis=0)
+    edges[:, 4:7] *= 0.3                                  # intermediate kt below ~0.75 GeV
+    xmat = np.vstack([edges, np.ones((1, dim))])
+    xmat[-1, 4:7] = 0.3
+    a = E.vegas_iterate(xmat, 500, N, 4711, 1)
+    u, vw, tape = philox_points(xmat, 500, N, 4711, 1, ntape=16)
+    w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
+    f = w * vw
+    assert (w != 0).sum() > 100
+    assert abs(f.sum() - a.fsum) <= 1e-12 * a.fsum and abs((f * f).sum() - a.f2sum) <= 1e-12 * a.f2sum and a.maxf == f.max()
+    fm = np.frombuffer(a.fmat, dtype=np.float64).reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM)
+    for j in range(dim):
+        assert abs(fm[:, j].sum() - a.fsum) <= 1e-11 * a.fsum, j
+    assert np.all(fm[:, dim:] == 0)
+    o = oracle_eval(E.desc, None, u[:512], tape[:512])
+    nz = o["w"] != 0
+    assert np.array_equal(w[:512] != 0, nz) and np.max(np.abs(w[:512][nz] - o["w"][nz]) / o["w"][nz]) < 1e-10
+    # The ladder ansatz has propagator poles 1 / (tt - M^2) inside this phase space (a single flat-grid point carries a weight
+    # of 1e24 b), so the adaptive integration runs into them and stops with the reference's own diagnosis -- the reference
+    # CLI ends the same way on this card ("VEGAS:: Integral inf/nan: FATAL ERROR, cuts or parameters need fixing").
+    with pytest.raises(grb.GrbError):
+        E.integrate(ncall=1 << 20, iters=3, precision=0.05, seed=3)
+    E.close()

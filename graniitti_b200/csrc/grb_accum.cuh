@@ -10,6 +10,8 @@ enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY
        // Born-level kinematics for the multi-helicity loop: p1z, p1e, p2z, p2e, pX(x,y,z,e)
        IT_BK = 22,
        // <C> class loop invariants: q0y, sinh / cosh of the two leg rapidities (m3, m4, q0x ride in IT_MXSQ, IT_SHY, IT_CHY)
+       // four-leg ladder (AMP_REGGE_ME6) reuses rows 6..16 and 22..28: q0x,q0y,q1x,q1y,q2x,q2y, m[0..3], sh[0]; sh[1..3], ch[0..3]
+       IT_L4A = 6, IT_L4B = 22,
        IT_CK = 30,
        IT_EXC = 35,  // lts.excite1/2 bits of the point (forward N* excitation)
        IT_NF = 36 };

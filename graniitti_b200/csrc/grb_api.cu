@@ -33,7 +33,7 @@ struct grb_engine {
   int64_t       chunk      = 0;
   double *      d_items    = nullptr;
   int32_t *     d_item_idx = nullptr;
-  uint64_t *    d_item_bins = nullptr;
+  uint64_t *    d_item_bins = nullptr, *d_item_bins_hi = nullptr;
   unsigned int *d_item_count = nullptr;
   // event generation buffers (allocated on first GRB_MODE_GENERATE call)
   double *      d_ev = nullptr, *d_pay = nullptr;
@@ -132,7 +132,6 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     err = "the device path covers 2 first-level central legs, and 4 stable legs for PP[CON]<C> (the MRegge::ME6 ladder)";
     return GRB_ERR_UNSUPPORTED;
   }
-  if (me6 && d.screening) { err = "PP[CON]<C> with four central legs: the screening loop is not on the device path yet"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
   if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 : 6 + d.excitation)) { err = "lipsdim must be 6 + NSTARS for <F> and 3 Nf - 4 for <C>"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
@@ -431,6 +430,7 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
     if ((ce = cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk)) != cudaSuccess) return fail("cudaMalloc items", ce);
     if ((ce = cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
+    if (desc->lipsdim > 8 && (ce = cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
   }
   if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 4)) != cudaSuccess) return fail("cudaMalloc", ce);
   if ((ce = cudaMalloc(&e->d_acc, sizeof(grb_accum))) != cudaSuccess) return fail("cudaMalloc", ce);
@@ -467,7 +467,7 @@ void grb_destroy(grb_engine *e) {
   if (g_const_owner == e) g_const_owner = nullptr;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_count);
+  cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_bins_hi); cudaFree(e->d_item_count);
   cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch); cudaFree(e->d_max2);
   cudaFree(e->d_ev); cudaFree(e->d_pay); cudaFree(e->d_ev_count);
   if (e->nccl_comm && nccl().ok) nccl().CommDestroy(e->nccl_comm);
@@ -608,7 +608,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     a.u = du + off; a.tape = dt ? dt + off : nullptr; a.ld = n; a.dim = dim; a.dtape = dtape;
     a.vegas = 0; a.bins = 0;
     a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
-    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
+    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
@@ -666,7 +666,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.vegas = 1; a.bins = bins; a.mode = mode; a.xmat = e->d_xmat; a.seed = seed; a.iter = (uint32_t)iteration;
     a.first_call = first_call + off; a.maxf = maxf;
     a.ev_out = e->d_ev; a.ev_count = e->d_ev_count; a.ev_cap = e->ev_cap; a.npart = npart; a.pay = e->d_pay;
-    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_count = e->d_item_count;
+    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
     if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
@@ -815,6 +815,7 @@ int grb_update_desc(grb_engine *e, const grb_process_desc *desc) {
     CK(cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk));
     CK(cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk));
   }
+  if (desc->screening && desc->lipsdim > 8 && !e->d_item_bins_hi) CK(cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk));
   const bool same_loop = desc->s == e->desc.s && desc->loop_nkt == e->desc.loop_nkt && desc->loop_nphi == e->desc.loop_nphi &&
                          desc->loop_min_kt == e->desc.loop_min_kt && desc->loop_max_kt == e->desc.loop_max_kt;
   e->desc  = *desc;

@@ -133,6 +133,7 @@ struct PointArgs {
   double *      items;
   int32_t *     item_idx;
   uint64_t *    item_bins;
+  uint64_t *    item_bins_hi;  // VEGAS bins of dimensions 8..15 (four-leg <C> class: 14 dimensions)
   unsigned int *item_count;
   int64_t       item_cap;
   // accumulators (device)

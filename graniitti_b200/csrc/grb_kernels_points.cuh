@@ -177,13 +177,28 @@ __global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(cons
             it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
             it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
             if (P.excitation) it[IT_EXC * c] = (double)L.exc;
-            if (P.ps_class == GRB_CLASS_C) {
+            if (AMP == AMP_REGGE_ME6) {  // four-leg ladder: leg invariants re-derived from the saved 4-vectors (MContinuum.cc:108-112)
+#pragma unroll
+              for (int k = 0; k < 3; ++k) { it[(IT_L4A + 2 * k) * c] = X4.qx[k]; it[(IT_L4A + 2 * k + 1) * c] = X4.qy[k]; }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const v4    &pk = S.np4[k % NN];
+                const double yk = rap_of(pk), shk = sinh(yk), chk = cosh(yk);
+                it[(IT_L4A + 6 + k) * c] = m_of(pk);
+                if (k == 0) it[(IT_L4A + 10) * c] = shk; else it[(IT_L4B + k - 1) * c] = shk;
+                it[(IT_L4B + 3 + k) * c] = chk;
+              }
+              a.item_bins_hi[slot] = packed_hi;
+            }
+            if (P.ps_class == GRB_CLASS_C && AMP != AMP_REGGE_ME6) {
               it[IT_MXSQ * c] = L.m3; it[IT_SHY * c] = L.m4; it[IT_CHY * c] = L.qx;
               it[(IT_CK + 0) * c] = L.qy; it[(IT_CK + 1) * c] = L.sh3; it[(IT_CK + 2) * c] = L.ch3;
               it[(IT_CK + 3) * c] = L.sh4; it[(IT_CK + 4) * c] = L.ch4;
             }
-            it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
-            it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
+            if (AMP != AMP_REGGE_ME6) {  // (the four-leg ladder keeps its own invariants in these rows)
+              it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
+              it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
+            }
             it[IT_H0RE * c] = h0.re; it[IT_H0IM * c] = h0.im;
             it[IT_PREF * c] = pref; it[IT_VW * c] = vw;
             if (AmpHel<AMP>::NH > 1) {

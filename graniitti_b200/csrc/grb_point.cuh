@@ -324,10 +324,47 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
 // ---- <C> class, four central legs (2 -> 6 direct, 14 coordinates) + the Regge ladder MRegge::ME6 ---------------------
 // u = [pt1, pt2, phi1, phi2, kt_1..3, phi_1..3, y_1..4]; BLinearSystem with the Kf = 4 inverse (MContinuum.cc:485-488).
 // The ladder needs s_1a, s_2a (4 + 4), s_ab (6 pairs), t-type scalars tt_1[a], tt_2[a] (4 + 4) and tt_xy[a][b] (6 pairs).
+#define GRB_BLIN4 {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0}, {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0}, \
+                   {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0}, {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}}
 struct Ladder4 {
   double s1a[4], s2a[4], sab[6], tt1[4], tt2[4], txy[6];  // pair index of (a < b): a*(7-a)/2 + b - a - 1 (a, b = 0..3)
+  double qx[3], qy[3];                                    // intermediate difference momenta (kept for the screening loop)
 };
 __device__ __forceinline__ int pair4(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * (7 - a) / 2 + b - a - 1; }
+
+// Lorentz scalars of the four-leg ladder (MProcess.cc:1499-1584): every pair mass^2 must be >= 0, t1, t2 <= 0
+__device__ __forceinline__ bool ladder4_scalars(const v4 &p1, const v4 &p2, const v4 &pX, const v4 *leg, double &t1, double &t2,
+                                                double &s1, double &s2, Ladder4 &X) {
+  const DevProc &P = c_proc;
+  s1 = m2_of(p1.x + pX.x, p1.y + pX.y, p1.z + pX.z, p1.e + pX.e);
+  s2 = m2_of(p2.x + pX.x, p2.y + pX.y, p2.z + pX.z, p2.e + pX.e);
+  const double s12 = m2_of(p1.x + p2.x, p1.y + p2.y, p1.z + p2.z, p1.e + p2.e);
+  bool ok = !(s1 < 0 || s2 < 0 || s12 < 0);
+  const double q1x = 0.0 - p1.x, q1y = 0.0 - p1.y, q1z = P.pb1z - p1.z, q1e = P.pb1e - p1.e;
+  const double q2x = 0.0 - p2.x, q2y = 0.0 - p2.y, q2z = P.pb2z - p2.z, q2e = P.pb2e - p2.e;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const v4 &pa = leg[a];
+    X.s1a[a] = m2_of(p1.x + pa.x, p1.y + pa.y, p1.z + pa.z, p1.e + pa.e);
+    X.s2a[a] = m2_of(p2.x + pa.x, p2.y + pa.y, p2.z + pa.z, p2.e + pa.e);
+    const double s0a = m2_of(pX.x + pa.x, pX.y + pa.y, pX.z + pa.z, pX.e + pa.e);
+    ok = ok && !(X.s1a[a] < 0 || X.s2a[a] < 0 || s0a < 0);
+    X.tt1[a] = m2_of(q1x - pa.x, q1y - pa.y, q1z - pa.z, q1e - pa.e);
+    X.tt2[a] = m2_of(q2x - pa.x, q2y - pa.y, q2z - pa.z, q2e - pa.e);
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const v4 &pb = leg[b];
+      const int k  = a * (7 - a) / 2 + b - a - 1;
+      X.sab[k] = m2_of(pa.x + pb.x, pa.y + pb.y, pa.z + pb.z, pa.e + pb.e);
+      ok = ok && !(X.sab[k] < 0);
+      X.txy[k] = m2_of((q1x - pa.x) - pb.x, (q1y - pa.y) - pb.y, (q1z - pa.z) - pb.z, (q1e - pa.e) - pb.e);
+    }
+  }
+  if (!ok) return false;
+  t1 = m2_of(q1x, q1y, q1z, q1e);
+  t2 = m2_of(q2x, q2y, q2z, q2e);
+  return !(t1 > 0 || t2 > 0);
+}
 
 template <int NN, class Draws>
 __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, PointState<NN> &S, Ladder4 &X) {
@@ -354,14 +391,12 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
     double       sk, ck;
     sincos(2.0 * GRB_PI * u[7 + i], &sk, &ck);
     const double qx = kt * ck, qy = kt * sk;
+    X.qx[i] = qx; X.qy[i] = qy;
     S.qprod *= msqrt(qx * qx + qy * qy);
     if (i == 0) { bx[0] = qx - wx; by[0] = qy - wy; }
     bx[i + 1] = qx * (-1.0) - wx; by[i + 1] = qy * (-1.0) - wy;
   }
-  const double A[4][4] = {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
-                          {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
-                          {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0},
-                          {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}};
+  const double A[4][4] = GRB_BLIN4;
   S.pX.x = 0.0; S.pX.y = 0.0; S.pX.z = 0.0; S.pX.e = 0.0;
   double sumM = 0.0;
 #pragma unroll
@@ -390,35 +425,12 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
     const double dz = P.bsum_z - ((S.p1.z + S.p2.z) + S.pX.z), de = P.bsum_e - ((S.p1.e + S.p2.e) + S.pX.e);
     if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
   }
-  // Lorentz scalars (MProcess.cc:1499-1584): every pair mass^2 must be >= 0, t1, t2 <= 0
-  S.s1 = m2_of(S.p1.x + S.pX.x, S.p1.y + S.pX.y, S.p1.z + S.pX.z, S.p1.e + S.pX.e);
-  S.s2 = m2_of(S.p2.x + S.pX.x, S.p2.y + S.pX.y, S.p2.z + S.pX.z, S.p2.e + S.pX.e);
-  const double s12 = m2_of(S.p1.x + S.p2.x, S.p1.y + S.p2.y, S.p1.z + S.p2.z, S.p1.e + S.p2.e);
-  bool ok = !(S.s1 < 0 || S.s2 < 0 || s12 < 0);
-  const double q1x = 0.0 - S.p1.x, q1y = 0.0 - S.p1.y, q1z = P.pb1z - S.p1.z, q1e = P.pb1e - S.p1.e;
-  const double q2x = 0.0 - S.p2.x, q2y = 0.0 - S.p2.y, q2z = P.pb2z - S.p2.z, q2e = P.pb2e - S.p2.e;
+  {
+    v4 leg[4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const v4 &pa = S.np4[a % NN];
-    X.s1a[a] = m2_of(S.p1.x + pa.x, S.p1.y + pa.y, S.p1.z + pa.z, S.p1.e + pa.e);
-    X.s2a[a] = m2_of(S.p2.x + pa.x, S.p2.y + pa.y, S.p2.z + pa.z, S.p2.e + pa.e);
-    const double s0a = m2_of(S.pX.x + pa.x, S.pX.y + pa.y, S.pX.z + pa.z, S.pX.e + pa.e);
-    ok = ok && !(X.s1a[a] < 0 || X.s2a[a] < 0 || s0a < 0);
-    X.tt1[a] = m2_of(q1x - pa.x, q1y - pa.y, q1z - pa.z, q1e - pa.e);
-    X.tt2[a] = m2_of(q2x - pa.x, q2y - pa.y, q2z - pa.z, q2e - pa.e);
-#pragma unroll
-    for (int b = a + 1; b < 4; ++b) {
-      const v4 &pb = S.np4[b % NN];
-      const int k  = a * (7 - a) / 2 + b - a - 1;
-      X.sab[k] = m2_of(pa.x + pb.x, pa.y + pb.y, pa.z + pb.z, pa.e + pb.e);
-      ok = ok && !(X.sab[k] < 0);
-      X.txy[k] = m2_of((q1x - pa.x) - pb.x, (q1y - pa.y) - pb.y, (q1z - pa.z) - pb.z, (q1e - pa.e) - pb.e);
-    }
+    for (int i = 0; i < 4; ++i) leg[i] = S.np4[i % NN];
+    if (!ladder4_scalars(S.p1, S.p2, S.pX, leg, S.t1, S.t2, S.s1, S.s2, X)) return false;
   }
-  if (!ok) return false;
-  S.t1 = m2_of(q1x, q1y, q1z, q1e);
-  S.t2 = m2_of(q2x, q2y, q2z, q2e);
-  if (S.t1 > 0 || S.t2 > 0) return false;
   S.t_hat = 0.0; S.u_hat = 0.0; S.ss13 = X.s1a[0]; S.ss14 = X.s1a[1]; S.ss23 = X.s2a[0]; S.ss24 = X.s2a[1];
   S.m2 = m2_of(S.pX);
   S.Y  = rap_of(S.pX);
@@ -478,6 +490,19 @@ __device__ __forceinline__ cx regge_me6(const double t1, const double t2, const 
     }
   return A;
 }
+
+// Screening loop of the four-leg ladder (reference MContinuum::LoopKinematics, src/MContinuum.cc:94-161, with Kf = 4): the
+// legs keep their masses and rapidities (re-derived from the saved 4-vectors), their transverse momenta follow the linear
+// system of the shifted protons; ME6 reads only lts scalars, so every scalar is rebuilt from the updated momenta.
+struct LoopInv4 {
+  double p1x, p1y, p2x, p2y, m1, m2, m1sq, m2sq;
+  double qx[3], qy[3], m[4], sh[4], ch[4];
+};
+struct PzConst;
+template <bool SAME>
+__device__ __forceinline__ bool loop_node_C4(const LoopInv4 &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder4 &X);
+template <bool SAME>
+__device__ __forceinline__ double screened_amp2_me6(const LoopInv4 &L, const cx &h0);
 
 // ---- cuts (reference src/MProcess.cc:1069-1175, src/MUserCuts.cc:21-75) ------------------------------------
 __device__ __forceinline__ bool leaf_fid_ok(const v4 &p) {
@@ -1243,6 +1268,69 @@ __device__ __forceinline__ double screened_amp2_multi(const LoopInv &L, const No
     amp2 += ar * ar + ai * ai;
   }
   return amp_hel_scale<AMP>() * amp2;
+}
+
+// ---- four-leg ladder: loop node and loop integral ---------------------------------------------------------------------
+template <bool SAME>
+__device__ __forceinline__ bool loop_node_C4(const LoopInv4 &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder4 &X) {
+  const DevProc &P = c_proc;
+  v4 p1, p2, pX, leg[4];
+  p1.x = L.p1x - ktx; p1.y = L.p1y - kty; p2.x = L.p2x + ktx; p2.y = L.p2y + kty;
+  const double wx = p1.x + p2.x, wy = p1.y + p2.y;
+  double bx[4], by[4];
+  bx[0] = L.qx[0] - wx; by[0] = L.qy[0] - wy;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { bx[i + 1] = L.qx[i] * (-1.0) - wx; by[i + 1] = L.qy[i] * (-1.0) - wy; }
+  const double A[4][4] = GRB_BLIN4;
+  pX.x = 0.0; pX.y = 0.0; pX.z = 0.0; pX.e = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v4 &p = leg[i];
+    p.x = ((((0.0 + bx[0] * A[i][0]) + bx[1] * A[i][1]) + bx[2] * A[i][2]) + bx[3] * A[i][3]);
+    p.y = ((((0.0 + by[0] * A[i][0]) + by[1] * A[i][1]) + by[2] * A[i][2]) + by[3] * A[i][3]);
+    const double mt = msqrt(pow2(L.m[i]) + (p.x * p.x + p.y * p.y));
+    p.z = mt * L.sh[i]; p.e = mt * L.ch[i];
+    pX.x += p.x; pX.y += p.y; pX.z += p.z; pX.e += p.e;
+  }
+  const double pt1 = msqrt(p1.x * p1.x + p1.y * p1.y), pt2 = msqrt(p2.x * p2.x + p2.y * p2.y);
+  const double p1z = SAME ? solve_pz3_A(L.m1, pt1, pt2, pX.z, pX.e, pc) : solve_pz3_B(L.m1, L.m2, pt1, pt2, pX.z, pX.e, pc);
+  const double p2z = -(pX.z + p1z);
+  if (isnan(p1z) || p1z < 0 || p2z > 0) return false;
+  p1.z = p1z; p1.e = msqrt(L.m1sq + pow2(pt1) + pow2(p1z));
+  p2.z = p2z; p2.e = msqrt(L.m2sq + pow2(pt2) + pow2(p2z));
+  {
+    const double dx = 0.0 - ((p1.x + p2.x) + pX.x), dy = 0.0 - ((p1.y + p2.y) + pX.y);
+    const double dz = P.bsum_z - ((p1.z + p2.z) + pX.z), de = P.bsum_e - ((p1.e + p2.e) + pX.e);
+    if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
+  }
+  double s1, s2;
+  return ladder4_scalars(p1, p2, pX, leg, t1, t2, s1, s2, X);
+}
+template <bool SAME>
+__device__ __forceinline__ double screened_amp2_me6(const LoopInv4 &L, const cx &h0) {
+  const DevLoop &Q = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  double Ire = 0.0, Iim = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    double       Jre = 0.0, Jim = 0.0;
+#pragma unroll 1
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      double       t1, t2;
+      Ladder4      X;
+      if (!loop_node_C4<SAME>(L, pc, kt * cp, kt * sp, t1, t2, X)) continue;
+      const cx A = regge_me6(t1, t2, X);
+      Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
+      Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
+    }
+    Ire = fma(wi, Jre, Ire);
+    Iim = fma(wi, Jim, Iim);
+  }
+  const double ar = h0.re - Q.norm * Iim, ai = h0.im + Q.norm * Ire;
+  return ar * ar + ai * ai;
 }
 
 }  // namespace grb

@@ -68,6 +68,7 @@ CASES = [
     # <C> class with four central legs: the 2 -> 6 ladder MRegge::ME6 (14 integration dimensions)
     ("cc4_cms_4pi_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 2048, 16, True),
     ("cc4_cms_2pi2k_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K-", 0, 1536, 16, True),
+    ("cc4_cms_4pi_con_screened", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 256, 16, True),
     ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
 ]

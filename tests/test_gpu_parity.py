@@ -96,10 +96,13 @@ def test_device_vs_reference_golden(grb, msa, path):
 @pytest.mark.parametrize("proc,pom,n", [("PP[CON]<F> -> pi+ pi-", 0, 200000), ("PP[CON]<F> -> pi+ pi-", 1, 40000),
                                         ("PP[CON-]<F> -> K+ K-", 1, 10000), ("PP[CON]<F> -> p+ p-", 0, 50000),
                                         ("PP[CON]<C> -> pi+ pi-", 0, 200000), ("PP[CON]<C> -> pi+ pi-", 1, 20000),
-                                        ("PP[CON-]<C> -> K+ K-", 1, 5000)])
+                                        ("PP[CON-]<C> -> K+ K-", 1, 5000),
+                                        ("PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 60000), ("PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 6000)])
 def test_device_vs_oracle_seeded(grb, msa, proc, pom, n):
     E = engine_for(grb, msa, "c2_alice.json", proc, pom)
-    u, tape = make_points(n, E.desc.lipsdim, 8, 99 + n, adapted=True)
+    u, tape = make_points(n, E.desc.lipsdim, 16 if E.desc.n_legs == 4 else 8, 99 + n, adapted=True)
+    if E.desc.n_legs == 4:
+        u[:, 4:7] *= 0.3      # intermediate kt of the four-leg ladder below ~0.75 GeV
     o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
     w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
     nz = o["w"] != 0

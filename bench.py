@@ -43,9 +43,9 @@ UNIT = "points/s"
 # SURVEY.md section 8(d) algorithmic flop model (transcendental = 20 flop, FMA = 2)
 F_KIN, F_BORN, F_NODE = 600.0, 650.0, 700.0
 # DRAM traffic of k_screen per work-list item, from the committed `ncu --set full` capture
-# (profiles/r01_k_screen_summary.txt: dram read 280.8 MB + write 14.7 MB for the 1 879 000 items of one launch
+# (profiles/r01_k_screen_summary.txt: dram read 281.3 MB + write 17.1 MB for the 1 879 000 items of one launch
 # = 4 194 304 points x accepted fraction 0.448; algorithmic: 22 doubles + index + bins = 188 B per item)
-SCREEN_DRAM_BYTES_PER_ITEM = (280.763392e6 + 14.745600e6) / (4194304 * 0.4480448544)
+SCREEN_DRAM_BYTES_PER_ITEM = (281.289984e6 + 17.106176e6) / (4194304 * 0.4480448544)
 
 
 def env_int(k, d):

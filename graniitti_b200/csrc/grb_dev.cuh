@@ -285,7 +285,6 @@ struct PzInv {
   double m3sq, m4sq, m3sq_x2, m4sq_x2, m3q, m4q;  // m^2, 2 m^2, m^4
   double k_s3, k_s4, k_34;                        // s m3^2 2, s m4^2 2 (A: s m3^2 4), m3^2 m4^2 2
   double s, s_x2, rs, rs_x2, s15, ssq;            // s, 2 s, sqrt s, 2 sqrt s, s^(3/2), s^2
-  double m3c, m4c;                                // central-leg masses^2 (fast node: t^ = t1 + m3^2 - 2 q1.p3)
 };
 __device__ __forceinline__ PzInv make_pz_inv(double m3, double m4, const PzConst &c, bool same) {
   PzInv I;

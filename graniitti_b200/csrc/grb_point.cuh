@@ -1147,10 +1147,9 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
   redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
   const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
   valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
-  // t^ = (q1 - p3)^2 = t1 + m3^2 - 2 q1.p3 reuses the bit-faithful t1 (6 fp64 instructions instead of 11; all terms are
-  // O(GeV^2), so this differs from the reference's expression at the 1e-16 level).  The sub-energies keep the reference's
-  // (E1 + E3)^2 - |p1 + p3|^2: it carries ~4e-13 of relative rounding noise that a dot-product form would not reproduce
-  // (measured: 2.4 % faster, but screened weights move from a median 4e-15 to 7e-13 against the reference -- not taken).
+  // (Measured and not taken: the sub-energies through dot products, (a + b)^2 = m_a^2 + m_b^2 + 2 a.b -- 2.4 % faster, but
+  // the reference's (E1 + E3)^2 - |p1 + p3|^2 carries ~4e-13 of relative rounding noise that such a form does not
+  // reproduce: screened weights moved from a median 4e-15 to 7e-13 against the reference.)
   const v4 &p3 = L.p3, &p4 = L.p4;
   const double ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
   const double ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
@@ -1161,8 +1160,8 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
   const double t1 = m2_of(q1x, q1y, q1z, q1e);
   const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
   valid = valid && !(t1 > 0 || t2 > 0);
-  const double t_hat = fma(-2.0, fma(-q1z, p3.z, fma(-q1y, p3.y, fma(-q1x, p3.x, q1e * p3.e))), t1 + pzi.m3c);
-  const double u_hat = fma(-2.0, fma(-q1z, p4.z, fma(-q1y, p4.y, fma(-q1x, p4.x, q1e * p4.e))), t1 + pzi.m4c);
+  const double t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  const double u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
   // amplitude: regge_me4(), single-trajectory branch
   const double dF = (fma(-t1, P.inv_fc1, 1.0) * fma(-t1, P.inv_fc2, 1.0)) * (fma(-t2, P.inv_fc1, 1.0) * fma(-t2, P.inv_fc2, 1.0));
   double       dt = t_hat - P.M2_leg0, du = u_hat - P.M2_leg0;
@@ -1206,8 +1205,7 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
   const DevLoop &Q = c_loop;
   PzConst        pc;
   pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
-  PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
-  pzi.m3c = m2_of(L.p3); pzi.m4c = m2_of(L.p4);
+  const PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
   double Ire = 0.0, Iim = 0.0;
   for (int i = 0; i < Q.nphi_nodes; ++i) {
     const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];

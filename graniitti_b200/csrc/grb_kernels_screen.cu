@@ -75,6 +75,7 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
     cx h0;
     h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
     if (AMP == AMP_REGGE && FF >= 0) it[IT_AMP2 * c] = screened_amp2_regge_fast<SAME, (FF >= 0 ? FF : 0)>(L, h0);
+    else if (AMP == AMP_TENSOR_2XS && FF >= 0) it[IT_AMP2 * c] = screened_amp2_tensor_fast<SAME>(L, h0);
     else it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
   }
 }
@@ -162,12 +163,15 @@ static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
   else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);
 }
 
-// regge_ff: PARAM_REGGE::offshellFF when the Regge continuum has one active trajectory (fast node), else -1
+// regge_ff: >= 0 when the one-basic-block node applies -- PARAM_REGGE::offshellFF for the Regge continuum with one active
+// trajectory, 0 for the tensor pomeron 2xS (both: <F> class, no forward excitation) -- else -1
 int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, cudaStream_t st) {
   // tuning knob for profiling runs; the default is the measured best (profiles/)
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
   if (amp_kind == AMP_TENSOR_2XS) {
-    launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
+    static const bool nofast_t = getenv("GRB_SCREEN_NOFAST") != nullptr;
+    if (regge_ff >= 0 && !nofast_t) launch_screen_t<4, AMP_TENSOR_2XS, 0>(a, sm_count, st);  // one-basic-block node (<F> class)
+    else launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
     return 2;
   }
   if (amp_kind == AMP_REGGE_RES) {

@@ -1228,6 +1228,127 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
   return ar * ar + ai * ai;
 }
 
+// ---- tensor pomeron 2xS: the same one-basic-block treatment ------------------------------------------------------------
+// Kinematics as in regge_node_fast (kept as its own copy so that the headline kernel's code generation is untouched);
+// the amplitude of tensor_me4_2xS() with table-driven log / exp / sincos and ALL its quotients -- two 1/(16 s s), four
+// F_M, two meson propagators, ten inside the two Kelly form factors F1(t) -- multiplied up into one division:
+//   R = pre (Nt Du + Nu Dt) / (Dt Du D_F1),  term_x = E'_x R_x num_x / [16 s s (1 - 2 qa)(1 - 2 qb) den_x].
+template <bool SAME>
+__device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
+  const DevProc &P = c_proc;
+  const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
+  const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
+  const double a1s = n1x * n1x + n1y * n1y, a2s = n2x * n2x + n2y * n2y, aXs = L.mXsq + (Xx * Xx + Xy * Xy);
+  bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(aXs));
+  const double pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s), mtX = sqrt_fast_core(aXs);
+  const double Xz = mtX * L.shY, Xe = mtX * L.chY;
+  valid = !(Xe > L.emax);
+  bool         dom = true;
+  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, dom);
+  redo = redo || (valid && !dom);
+  const double p2z = -(Xz + p1z);
+  valid = valid && !(isnan(p1z) || p1z < 0 || p2z > 0);
+  const double e1s = L.m1sq + pow2(pt1) + pow2(p1z), e2s = L.m2sq + pow2(pt2) + pow2(p2z);
+  redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
+  const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
+  valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
+  const v4 &p3 = L.p3, &p4 = L.p4;
+  const double ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
+  const double ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
+  const double ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
+  const double ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
+  valid = valid && !(ss13 < 0 || ss14 < 0 || ss23 < 0 || ss24 < 0);
+  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  const double t1 = m2_of(q1x, q1y, q1z, q1e);
+  const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
+  valid = valid && !(t1 > 0 || t2 > 0);
+  // amplitude (tensor_me4_2xS): vertex vectors
+  v4 P1, P2, pt, pu;
+  P1.x = n1x; P1.y = n1y; P1.z = p1z + P.pb1z; P1.e = e1 + P.pb1e;
+  P2.x = n2x; P2.y = n2y; P2.z = p2z + P.pb2z; P2.e = e2 + P.pb2e;
+  pt.x = (0.0 - n1x) - p3.x; pt.y = (0.0 - n1y) - p3.y; pt.z = (P.pb1z - p1z) - p3.z; pt.e = (P.pb1e - e1) - p3.e;
+  pu.x = (p4.x - 0.0) + n1x; pu.y = (p4.y - 0.0) + n1y; pu.z = (p4.z - P.pb1z) + p1z; pu.e = (p4.e - P.pb1e) + e1;
+  v4 Kta, Ktb, Kua, Kub;
+  Kta.x = pt.x - p3.x; Kta.y = pt.y - p3.y; Kta.z = pt.z - p3.z; Kta.e = pt.e - p3.e;
+  Ktb.x = p4.x + pt.x; Ktb.y = p4.y + pt.y; Ktb.z = p4.z + pt.z; Ktb.e = p4.e + pt.e;
+  Kua.x = p4.x + pu.x; Kua.y = p4.y + pu.y; Kua.z = p4.z + pu.z; Kua.e = p4.e + pu.e;
+  Kub.x = pu.x - p3.x; Kub.y = pu.y - p3.y; Kub.z = pu.z - p3.z; Kub.e = pu.e - p3.e;
+  const double P1sq = m2_of(P1), P2sq = m2_of(P2);
+  const double d1t = mdot(P1, Kta), d2t = mdot(P2, Ktb), d1u = mdot(P1, Kua), d2u = mdot(P2, Kub);
+  const double Rt = (2.0 * d1t * d1t - 0.5 * m2_of(Kta) * P1sq) * (2.0 * d2t * d2t - 0.5 * m2_of(Ktb) * P2sq);
+  const double Ru = (2.0 * d1u * d1u - 0.5 * m2_of(Kua) * P1sq) * (2.0 * d2u * d2u - 0.5 * m2_of(Kub) * P2sq);
+  const double pt2v = m2_of(pt), pu2v = m2_of(pu);
+  const double al1 = P.tp_delta + P.tp_ap * t1, al2 = P.tp_delta + P.tp_ap * t2;
+  redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
+  const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
+  const double xt = al1 * (L13 + P.tp_ln_ap) + al2 * (L24 + P.tp_ln_ap), xu = al1 * (L14 + P.tp_ln_ap) + al2 * (L23 + P.tp_ln_ap);
+  const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
+  const double qa_t = m2_of(pt.x + p3.x, pt.y + p3.y, pt.z + p3.z, pt.e + p3.e);
+  const double qb_t = m2_of(p4.x - pt.x, p4.y - pt.y, p4.z - pt.z, p4.e - pt.e);
+  const double qa_u = m2_of(p4.x - pu.x, p4.y - pu.y, p4.z - pu.z, p4.e - pu.e);
+  const double qb_u = m2_of(pu.x + p3.x, pu.y + p3.y, pu.z + p3.z, pu.e + p3.e);
+  double nt, dt, nu, du;
+  meson_G_nd(pt2v, nt, dt);
+  meson_G_nd(pu2v, nu, du);
+  const double Nt = Et * Rt * nt, Dt = (16.0 * ss13 * ss24) * ((1.0 - 2.0 * qa_t) * (1.0 - 2.0 * qb_t)) * dt;
+  const double Nu = Eu * Ru * nu, Du = (16.0 * ss14 * ss23) * ((1.0 - 2.0 * qa_u) * (1.0 - 2.0 * qb_u)) * du;
+  // F1(t1) F1(t2) as one rational function (Kelly) or dipole (MForm.cc:542-645)
+  const double inv4mp2 = 1.0 / P.four_mp2;
+  const double tau1 = fabs(t1) * inv4mp2, tau2 = fabs(t2) * inv4mp2;
+  double       nF, dF;
+  if (P.em_kelly) {
+    const double nE1 = 1.0 - 0.24 * tau1, dE1 = 1.0 + 10.98 * tau1 + 12.82 * (tau1 * tau1) + 21.97 * (tau1 * (tau1 * tau1));
+    const double nM1 = 2.792847337 * (1.0 + 0.12 * tau1), dM1 = 1.0 + 10.97 * tau1 + 18.86 * (tau1 * tau1) + 6.55 * (tau1 * (tau1 * tau1));
+    const double nE2 = 1.0 - 0.24 * tau2, dE2 = 1.0 + 10.98 * tau2 + 12.82 * (tau2 * tau2) + 21.97 * (tau2 * (tau2 * tau2));
+    const double nM2 = 2.792847337 * (1.0 + 0.12 * tau2), dM2 = 1.0 + 10.97 * tau2 + 18.86 * (tau2 * tau2) + 6.55 * (tau2 * (tau2 * tau2));
+    nF = (nE1 * dM1 + tau1 * nM1 * dE1) * (nE2 * dM2 + tau2 * nM2 * dE2);
+    dF = (dE1 * dM1 * (tau1 + 1.0)) * (dE2 * dM2 * (tau2 + 1.0));
+  } else {
+    const double g1 = pow2(1.0 + fabs(t1) / 0.71), g2 = pow2(1.0 + fabs(t2) / 0.71);   // GM = mu / g, GE = 1 / g
+    nF = (1.0 + tau1 * 2.792847337) * (1.0 + tau2 * 2.792847337);
+    dF = (g1 * (tau1 + 1.0)) * (g2 * (tau2 + 1.0));
+  }
+  const double num = P.tp_coupling * nF * fma(Nt, Du, Nu * Dt), den = (Dt * Du) * dF;
+  const double R   = div_fast_core(num, den);
+  const double ph  = P.tp_phase * (al1 + al2);
+  redo = redo || (valid && !(fabs(xt) < 690.0 && fabs(xu) < 690.0 && div_fast_ok(num, R) && fabs(ph) < 1.0e5));
+  double sn, cs;
+  fast_sincos_core(ph, sn, cs);
+  A.re = cs * R;
+  A.im = sn * R;
+  return redo;
+}
+template <bool SAME>
+__device__ __forceinline__ double screened_amp2_tensor_fast(const LoopInv &L, const cx &h0) {
+  const DevLoop &Q = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  const PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
+  double Ire = 0.0, Iim = 0.0;
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    double       Jre = 0.0, Jim = 0.0;
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      bool         valid;
+      cx           A;
+      if (__builtin_expect(tensor_node_fast<SAME>(L, pzi, kt * cp, kt * sp, valid, A), 0)) {
+        NodeKin in;
+        valid = loop_node<SAME>(L, pc, kt * cp, kt * sp, in);
+        if (valid) A = tensor_me4_2xS(in, L.p3, L.p4);
+      }
+      if (valid) {
+        Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
+        Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
+      }
+    }
+    Ire = fma(wi, Jre, Ire);
+    Iim = fma(wi, Jim, Iim);
+  }
+  const double ar = h0.re - Q.norm * Iim, ai = h0.im + Q.norm * Ire;
+  return ar * ar + ai * ai;
+}
+
 // The same loop for NH > 1 amplitudes.  The Born amplitudes are re-evaluated from the Born-level kinematics carried
 // in the work list (same device function, same inputs as k_points: identical bits), so the list does not grow with NH.
 template <int AMP, bool SAME>

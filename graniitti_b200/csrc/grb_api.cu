@@ -83,6 +83,9 @@ static double m_of_beam(double pz, double E) {  // M4Vec::M() of (0,0,pz,E), ref
 // one active Regge trajectory (TUNE0): the screening kernel's one-basic-block node applies (grb_point.cuh)
 static int regge_fast_ff(const DevProc &P) {
   if (P.ps_class == GRB_CLASS_F && P.excitation == 0 && P.amp_kind == 1) return 0;  // tensor pomeron 2xS
+  if (P.ps_class == GRB_CLASS_C && P.n_legs == 2 && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] &&
+      P.offshellFF >= 0 && P.offshellFF <= 2)
+    return 10 + P.offshellFF;                                                       // <C> class Regge continuum
   return (P.ps_class == GRB_CLASS_F && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
 }
 

@@ -69,9 +69,10 @@ __device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
 }
 
 template <int NN, bool VEGAS, int AMP>
-// Regge continuum: two CTAs per SM (<= 128 registers): the kernel is latency-bound (libm calls, divergent cuts), so
-// occupancy pays; the heavier amplitudes keep the full register file
-__global__ void __launch_bounds__(256, (AMP == AMP_REGGE ? 2 : 1)) k_points(const PointArgs a) {
+// Regge and tensor-pomeron 2xS continuum: two CTAs per SM (<= 128 registers): the kernel is latency-bound (libm calls,
+// divergent cuts), so occupancy pays (2.66 -> 1.96 and 6.15 -> 4.60 ms per 2^23 points); the heavier amplitudes
+// (resonances, HELAS, 2xV / 2xF) keep the full register file -- measured slower with the cap (spills of 4-7 KB)
+__global__ void __launch_bounds__(256, ((AMP == AMP_REGGE || AMP == AMP_TENSOR_2XS) ? 2 : 1)) k_points(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
   const int      nb  = a.bins * dim;

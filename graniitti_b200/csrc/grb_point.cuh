@@ -1228,6 +1228,109 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
   return ar * ar + ai * ai;
 }
 
+// ---- <C> class, single-trajectory Regge continuum: the one-basic-block node with the moving central legs of
+// loop_node_C (two more square roots for the leg transverse masses, no crude energy test, full CheckEMC) ---------------
+template <bool SAME, int FF>
+__device__ __forceinline__ bool regge_node_fast_C(const LoopInv &L, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
+  const DevProc &P = c_proc;
+  const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
+  const double wx = n1x + n2x, wy = n1y + n2y;
+  const double p3x = (L.qx - wx) * (1.0 / 2.0), p3y = (L.qy - wy) * (1.0 / 2.0);
+  const double p4x = (L.qx * (-1.0) - wx) * (1.0 / 2.0), p4y = (L.qy * (-1.0) - wy) * (1.0 / 2.0);
+  const double a3s = pow2(L.m3) + (p3x * p3x + p3y * p3y), a4s = pow2(L.m4) + (p4x * p4x + p4y * p4y);
+  const double a1s = n1x * n1x + n1y * n1y, a2s = n2x * n2x + n2y * n2y;
+  bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(a3s) && sqrt_fast_ok(a4s));
+  const double mt3 = sqrt_fast_core(a3s), mt4 = sqrt_fast_core(a4s), pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s);
+  const double p3z = mt3 * L.sh3, p3e = mt3 * L.ch3, p4z = mt4 * L.sh4, p4e = mt4 * L.ch4;
+  const double Xx = p3x + p4x, Xy = p3y + p4y, Xz = p3z + p4z, Xe = p3e + p4e;
+  bool         dom = true;
+  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, dom);
+  redo = redo || !dom;
+  const double p2z = -(Xz + p1z);
+  valid = !(isnan(p1z) || p1z < 0 || p2z > 0);
+  const double e1s = L.m1sq + pow2(pt1) + pow2(p1z), e2s = L.m2sq + pow2(pt2) + pow2(p2z);
+  redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
+  const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
+  {
+    const double dx = 0.0 - ((n1x + n2x) + Xx), dy = 0.0 - ((n1y + n2y) + Xy);
+    const double dz = P.bsum_z - ((p1z + p2z) + Xz), de = P.bsum_e - ((e1 + e2) + Xe);
+    valid = valid && !(fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6);
+  }
+  const double ss13 = m2_of(n1x + p3x, n1y + p3y, p1z + p3z, e1 + p3e);
+  const double ss14 = m2_of(n1x + p4x, n1y + p4y, p1z + p4z, e1 + p4e);
+  const double ss23 = m2_of(n2x + p3x, n2y + p3y, p2z + p3z, e2 + p3e);
+  const double ss24 = m2_of(n2x + p4x, n2y + p4y, p2z + p4z, e2 + p4e);
+  const double s01 = m2_of(Xx + n1x, Xy + n1y, Xz + p1z, Xe + e1), s02 = m2_of(Xx + n2x, Xy + n2y, Xz + p2z, Xe + e2);
+  const double s34 = m2_of(p3x + p4x, p3y + p4y, p3z + p4z, p3e + p4e);
+  valid = valid && !(ss13 < 0 || ss14 < 0 || ss23 < 0 || ss24 < 0 || s01 < 0 || s02 < 0 || s34 < 0);
+  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  const double t1 = m2_of(q1x, q1y, q1z, q1e);
+  const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
+  valid = valid && !(t1 > 0 || t2 > 0);
+  const v4 &p3 = L.p3, &p4 = L.p4;   // Born-level lts.decaytree[i].p4 (not updated in the reference's loop)
+  const double t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
+  const double u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  // amplitude: regge_me4(), single-trajectory branch (as in regge_node_fast)
+  const double dF = (fma(-t1, P.inv_fc1, 1.0) * fma(-t1, P.inv_fc2, 1.0)) * (fma(-t2, P.inv_fc1, 1.0) * fma(-t2, P.inv_fc2, 1.0));
+  double       dt = t_hat - P.M2_leg0, du = u_hat - P.M2_leg0;
+  const double al1 = fma(P.ap[0], t1, P.a0[0]), al2 = fma(P.ap[0], t2, P.a0[0]);
+  double       gt = 0.0, gu = 0.0;
+  if (FF == 0) {
+    gt = -2.0 * P.b_EXP * fabs(dt);
+    gu = -2.0 * P.b_EXP * fabs(du);
+  } else if (FF == 1) {
+    gt = 2.0 * fma(-P.b_OREAR, msqrt(fabs(dt) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+    gu = 2.0 * fma(-P.b_OREAR, msqrt(fabs(du) + pow2(P.a_OREAR)), P.a_OREAR * P.b_OREAR);
+  } else {
+    const double d1 = fma(-dt, P.inv_b_POW, 1.0), d2 = fma(-du, P.inv_b_POW, 1.0);
+    dt *= d1 * d1;
+    du *= d2 * d2;
+  }
+  redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
+  const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
+  const double xt = fma(al1, L13 + P.ln_inv_s0, fma(al2, L24 + P.ln_inv_s0, gt)), xu = fma(al1, L14 + P.ln_inv_s0, fma(al2, L23 + P.ln_inv_s0, gu));
+  const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
+  const double num = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), den = dt * du * dF;
+  const double R   = div_fast_core(num, den);
+  const double ph  = P.phase_c[0] * (t1 + t2);
+  redo = redo || (valid && !(fabs(xt) < 690.0 && fabs(xu) < 690.0 && div_fast_ok(num, R) && fabs(ph) < 1.0e5));
+  double sn, cs;
+  fast_sincos_core(ph, sn, cs);
+  A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;
+  A.im = fma(P.eta0sq_re, sn, P.eta0sq_im * cs) * R;
+  return redo;
+}
+template <bool SAME, int FF>
+__device__ __forceinline__ double screened_amp2_regge_fast_C(const LoopInv &L, const cx &h0) {
+  const DevLoop &Q = c_loop;
+  PzConst        pc;
+  pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
+  const PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
+  double Ire = 0.0, Iim = 0.0;
+  for (int i = 0; i < Q.nphi_nodes; ++i) {
+    const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
+    double       Jre = 0.0, Jim = 0.0;
+    for (int j = 0; j <= Q.nkt; ++j) {
+      const double kt = Q.kt[j];
+      bool         valid;
+      cx           A;
+      if (__builtin_expect(regge_node_fast_C<SAME, FF>(L, pzi, kt * cp, kt * sp, valid, A), 0)) {
+        NodeKin in;
+        valid = loop_node_C<SAME>(L, pc, kt * cp, kt * sp, in);
+        if (valid) A = regge_me4(in);
+      }
+      if (valid) {
+        Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
+        Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
+      }
+    }
+    Ire = fma(wi, Jre, Ire);
+    Iim = fma(wi, Jim, Iim);
+  }
+  const double ar = h0.re - Q.norm * Iim, ai = h0.im + Q.norm * Ire;
+  return ar * ar + ai * ai;
+}
+
 // ---- tensor pomeron 2xS: the same one-basic-block treatment ------------------------------------------------------------
 // Kinematics as in regge_node_fast (kept as its own copy so that the headline kernel's code generation is untouched);
 // the amplitude of tensor_me4_2xS() with table-driven log / exp / sincos and ALL its quotients -- two 1/(16 s s), four

@@ -36,6 +36,15 @@ __device__ __forceinline__ void store_momenta(double *dst, int64_t stride, const
     }
 }
 
+// launch shape per amplitude kind: CTA size and resident CTAs per SM (register cap = 65536 / (threads x CTAs)).  Measured
+// per 2^23 points (profiles/r01_variants.txt): Regge 2.66 -> 1.96 ms and tensor 2xS 6.15 -> 4.60 ms at 256 x 2 (128
+// registers); resonances 36.8 -> 30.4 ms at 128 x 3 (168 registers; 256 x 2 is slower); HELAS yy -> l+ l- is fastest with
+// the full register file (45.5 ms; 48.8 at 128 x 3, 49.6 at 256 x 2)
+__host__ __device__ constexpr int kp_threads(int amp) { return (amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 128 : 256; }
+__host__ __device__ constexpr int kp_minb(int amp) {
+  return (amp == AMP_REGGE || amp == AMP_TENSOR_2XS) ? 2 : ((amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 3 : 1);
+}
+
 // ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
 template <int NN, int AMP>
 __device__ __forceinline__ cx born_amplitude(const PointState<NN> &S) {
@@ -69,10 +78,7 @@ __device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
 }
 
 template <int NN, bool VEGAS, int AMP>
-// Regge and tensor-pomeron 2xS continuum: two CTAs per SM (<= 128 registers): the kernel is latency-bound (libm calls,
-// divergent cuts), so occupancy pays (2.66 -> 1.96 and 6.15 -> 4.60 ms per 2^23 points); the heavier amplitudes
-// (resonances, HELAS, 2xV / 2xF) keep the full register file -- measured slower with the cap (spills of 4-7 KB)
-__global__ void __launch_bounds__(256, ((AMP == AMP_REGGE || AMP == AMP_TENSOR_2XS) ? 2 : 1)) k_points(const PointArgs a) {
+__global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const PointArgs a) {
   const DevProc &P   = c_proc;
   const int      dim = P.lipsdim;
   const int      nb  = a.bins * dim;
@@ -263,8 +269,10 @@ __global__ void __launch_bounds__(256, ((AMP == AMP_REGGE || AMP == AMP_TENSOR_2
 
 template <int NN, int AMP>
 inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
-  if (a.vegas) k_points<NN, true, AMP><<<blocks, threads, smem, st>>>(a);
-  else k_points<NN, false, AMP><<<blocks, threads, 0, st>>>(a);
+  const int th = kp_threads(AMP);
+  if (th != threads) blocks = blocks * (unsigned)(threads / th);   // same number of resident threads
+  if (a.vegas) k_points<NN, true, AMP><<<blocks, th, smem, st>>>(a);
+  else k_points<NN, false, AMP><<<blocks, th, 0, st>>>(a);
 }
 template <int AMP>
 inline void launch_points_n(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st) {

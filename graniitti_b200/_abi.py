@@ -54,7 +54,7 @@ class VetoDomain(C.Structure):
 
 class ParamSoft(C.Structure):
     _fields_ = [(k, f64) for k in ("DELTA_P", "ALPHA_P", "gN_P", "gN_O", "g3P", "gamma", "fc1", "fc2", "fc3")] + [
-        ("odderon_on", i32), ("pad_", i32)]
+        ("odderon_on", i32), ("f2_model", i32)]
 
 
 class ParamRegge(C.Structure):

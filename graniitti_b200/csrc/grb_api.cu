@@ -95,8 +95,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.abi_version != GRB_ABI_VERSION) { err = "abi_version mismatch"; return GRB_ERR_ARG; }
   if (d.ps_class != GRB_CLASS_F && d.ps_class != GRB_CLASS_C) { err = "only the <F> and <C> phase-space classes are on the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.ps_class == GRB_CLASS_C && d.veto_active) { err = "<C> with veto cuts needs forward fragmentation (outside the device path)"; return GRB_ERR_UNSUPPORTED; }
-  if (d.excitation != 0 && !(d.ps_class == GRB_CLASS_F && (d.proc == GRB_PROC_PP_CON || d.proc == GRB_PROC_PP_CON_MINUS))) {
-    err = "NSTARS != 0 (forward N* excitation) is on the device path for the <F> class Regge continuum PP[CON], PP[CON-]";
+  if (d.excitation != 0 && !(d.ps_class == GRB_CLASS_F && (d.proc == GRB_PROC_PP_CON || d.proc == GRB_PROC_PP_CON_MINUS || d.proc == GRB_PROC_YY_CON))) {
+    err = "NSTARS != 0 (forward N* excitation) is on the device path for PP[CON], PP[CON-] and yy[CON] in the <F> class";
     return GRB_ERR_UNSUPPORTED;
   }
   if (d.excitation < 0 || d.excitation > 2) { err = "MProcess::SetExcitation: Not valid input (0,1,2)"; return GRB_ERR_ARG; }
@@ -158,6 +158,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.gM_min = d.gcuts.M_min; P.gM_max = d.gcuts.M_max;
   P.ps_class = d.ps_class;
   P.excitation = d.excitation;
+  P.f2_model = d.soft.f2_model;
   P.log_M2f_min = std::log(1.09 * 1.09);  // neutron + pi+ threshold, MProcess.cc:1324-1328
   P.dlog_M2f = std::log(d.gcuts.XI_max * d.s) - P.log_M2f_min;
   if (d.excitation != 0 && !(d.gcuts.XI_max * d.s > 1.09 * 1.09)) { err = "MProcess::SampleForwardMasses: Forward leg Xi max is below the inelastic threshold"; return GRB_ERR_ARG; }

@@ -55,7 +55,7 @@ struct DevProc {
   int    ps_class, pad_c_;
   // forward N* excitation (NSTARS, MProcess.cc:1317-1365,1402-1411; MRegge.cc:637-644): log-flat M^2 sampling range,
   // sqrt(g3P gN_P) / gN_P (inelastic over elastic proton vertex coupling), forward-mass fiducial cut
-  int    excitation, pad_x_;
+  int    excitation, f2_model;  // NSTARS; PARAM_STRUCTURE.F2 (0 CKMT, 1 DL)
   double log_M2f_min, dlog_M2f, exc_vertex, f_fM_min, f_fM_max;
   double offshell;
   // cuts

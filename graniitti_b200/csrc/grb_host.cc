@@ -711,6 +711,7 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     const Json &T = tune.at("PARAM_STRUCTURE");
     const std::string em = T.at("EM").as_str(), qa = T.at("QED_alpha").as_str();
     d.em_ff     = (em == "KELLY") ? 1 : 0;
+    d.soft.f2_model = (T.has("F2") && T.at("F2").as_str() == "DL") ? 1 : 0;   // PARAM_STRUCTURE.F2: CKMT (default) or DL
     d.qed_alpha = (qa == "ZERO") ? 0 : 1;
   }
   // PARAM_REGGE + per-particle couplings chosen by the first leg (src/MRegge.cc:984-1033)

@@ -256,6 +256,28 @@ __device__ __forceinline__ double coh_flux_amp(double xi, double t, double pt) {
   return msqrt(f / xi);
 }
 
+// sqrt(IncohFlux(xi,t,pt,M2)/xi): photon flux of a dissociating proton (reference src/MForm.cc:700-719) with the proton
+// structure function F2(x, Q^2) of PARAM_STRUCTURE.F2 (CKMT or Donnachie-Landshoff, :463-508), F1 = F2 / 2x
+__device__ __forceinline__ double f2xq2(double xbj, double Q2) {
+  if (c_proc.f2_model == 1) {
+    return 0.324 * pow(xbj, -0.0808) * pow(Q2 / (Q2 + 0.561991692786383), 1 + 0.0808) +
+           0.098 * pow(xbj, 1 - 0.5475) * pow(Q2 / (Q2 + 0.011133), 0.5475);
+  }
+  const double n_Q2 = (3.0 / 2.0) * (1 + Q2 / (Q2 + 3.5489)), DELTA_Q2 = 0.0800 * (1 + (2 * Q2) / (Q2 + 1.1170));
+  const double C1 = pow(Q2 / (Q2 + 0.2631), 1.0 + DELTA_Q2), C2 = pow(Q2 / (Q2 + 0.6452), 0.4150);
+  return 0.1502 * pow(xbj, -DELTA_Q2) * pow(1 - xbj, n_Q2 + 4.0) * C1 +
+         pow(xbj, 1.0 - 0.4150) * (1.2064 * pow(1 - xbj, n_Q2) + 0.1798 * pow(1 - xbj, n_Q2 + 1.0)) * C2;
+}
+__device__ __forceinline__ double incoh_flux_amp(double xi, double t, double pt, double M2) {
+  const double mp2 = 0.25 * c_proc.four_mp2, pt2 = pt * pt, xi2 = xi * xi, Q2 = fabs(t);
+  const double xbj = Q2 / (Q2 + M2 - mp2), DELTA = pt2 / (pt2 + xi * (M2 - mp2) + xi2 * mp2);
+  const double F2 = f2xq2(xbj, Q2), F1 = F2 / (2.0 * xbj);
+  double f = 0.0072973525693 / GRB_PI * ((1.0 - xi) * (DELTA * DELTA) * F2 / (Q2 + M2 - mp2) +
+                                         (xi2 / (4.0 * (xbj * xbj))) * DELTA * 2.0 * xbj * F1 / (Q2 + M2 - mp2));
+  f = f / xi / pt2 * (16.0 * (GRB_PI * GRB_PI));
+  return msqrt(f / xi);
+}
+
 // Regge single-trajectory propagator pieces shared by all resonances: Prop(s,t) = eta0 cis(pc t) (s/s0)^alpha(t)
 __device__ __forceinline__ cx regge_prop_k(double s, double t, int k, bool with_s0 = true) {
   const DevProc &P = c_proc;

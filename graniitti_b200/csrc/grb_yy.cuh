@@ -214,7 +214,9 @@ __device__ __forceinline__ double yy_ll_core(const NodeKin &in, const v4 &p3, co
   // couplings: each diagram carries GC_3^2 (off-shell line) and the vertex -i GC_3 ... |GC_3|^4 = ee^4 overall;
   // GC_3 = -i ee, ee = 2 sqrt(pi/137.03599908) (Parameters_sm.cc:93-101)
   const double amp2 = sum * P.yy_ee4 / 4.0;
-  const double f1 = coh_flux_amp(x1, in.t1, qt1), f2 = coh_flux_amp(x2, in.t2, qt2);  // sqrt(flux_i / x_i)
+  // sqrt(flux_i / x_i): coherent flux of an intact proton, incoherent flux of an excited N* system (MFlux.cc:22-28)
+  const double f1 = (in.exc & 1) ? incoh_flux_amp(x1, in.t1, qt1, m2_of(in.p1)) : coh_flux_amp(x1, in.t1, qt1);
+  const double f2 = (in.exc & 2) ? incoh_flux_amp(x2, in.t2, qt2, m2_of(in.p2)) : coh_flux_amp(x2, in.t2, qt2);
   if (VEC) {
     const double sc = sqrt(P.yy_ee4) * (f1 * f2);
 #pragma unroll

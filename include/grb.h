@@ -113,7 +113,8 @@ typedef struct {
 /* PARAM_SOFT (src/MForm.cc:71-130), PARAM_REGGE (src/MRegge.cc:924-1033) */
 typedef struct {
   double  DELTA_P, ALPHA_P, gN_P, gN_O, g3P, gamma, fc1, fc2, fc3;
-  int32_t odderon_on, pad_;
+  int32_t odderon_on;
+  int32_t f2_model; /* PARAM_STRUCTURE.F2 (proton structure function of the incoherent photon flux): 0 CKMT, 1 DL */
 } grb_param_soft;
 
 typedef struct {
@@ -157,7 +158,7 @@ typedef struct {
   int32_t ps_class;   /* GRB_CLASS_F | GRB_CLASS_C                                                       */
   int32_t proc;       /* GRB_PROC_*                                                                      */
   int32_t screening;  /* POMLOOP                                                                         */
-  int32_t excitation; /* NSTARS (0 only on the device path)                                              */
+  int32_t excitation; /* NSTARS: 0, or 1 / 2 forward N* systems (PP[CON], PP[CON-], yy[CON] in the <F> class)       */
   int32_t flatamp;    /* @FLATAMP (0 only)                                                               */
   int32_t ps_active;  /* !ISOLATE ("->" true, "&>" false)                                                */
   int32_t flatmass2;

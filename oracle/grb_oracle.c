@@ -1598,6 +1598,36 @@ static double o_coh_flux(const ost *S, double xi, double t, double pt) {
   f *= 16.0 * (O_PI * O_PI);
   return f;
 }
+/* reference src/MForm.cc:463-518 F2xQ2 (Donnachie-Landshoff or CKMT), F1xQ2 (Callan-Gross) */
+static double o_f2xq2(const ost *S, double xbj, double Q2) {
+  if (S->d->soft.f2_model == 1) {
+    const double A = 0.324, B = 0.098, DELTA_P = 0.0808, DELTA_R = 0.5475, a = 0.561991692786383, b = 0.011133;
+    return A * pow(xbj, -DELTA_P) * pow(Q2 / (Q2 + a), 1 + DELTA_P) + B * pow(xbj, 1 - DELTA_R) * pow(Q2 / (Q2 + b), DELTA_R);
+  }
+  const double A = 0.1502, B_u = 1.2064, B_d = 0.1798, alpha_R = 0.4150, DELTA_0 = 0.0800;
+  const double a = 0.2631, b = 0.6452, c = 3.5489, d = 1.1170;
+  const double n_Q2     = (3.0 / 2.0) * (1 + Q2 / (Q2 + c));
+  const double DELTA_Q2 = DELTA_0 * (1 + (2 * Q2) / (Q2 + d));
+  const double C1 = pow(Q2 / (Q2 + a), 1.0 + DELTA_Q2);
+  const double C2 = pow(Q2 / (Q2 + b), alpha_R);
+  return A * pow(xbj, -DELTA_Q2) * pow(1 - xbj, n_Q2 + 4.0) * C1 +
+         pow(xbj, 1.0 - alpha_R) * (B_u * pow(1 - xbj, n_Q2) + B_d * pow(1 - xbj, n_Q2 + 1.0)) * C2;
+}
+static double o_f1xq2(const ost *S, double xbj, double Q2) { return o_f2xq2(S, xbj, Q2) / (2.0 * xbj); }
+/* reference src/MForm.cc:700-719 IncohFlux: kt-unintegrated photon flux of a dissociating proton */
+static double o_incoh_flux(const ost *S, double xi, double t, double pt, double M2) {
+  const double mp = 0.938272081, mp2 = pow2(mp);
+  const double pt2 = pow2(pt), xi2 = pow2(xi), Q2 = fabs(t);
+  const double xbj   = Q2 / (Q2 + M2 - mp2);
+  const double DELTA = pt2 / (pt2 + xi * (M2 - mp2) + xi2 * mp2);
+  double f = 0.0072973525693 / O_PI *
+             ((1.0 - xi) * pow2(DELTA) * o_f2xq2(S, xbj, Q2) / (Q2 + M2 - mp2) +
+              (xi2 / (4.0 * pow2(xbj))) * DELTA * 2.0 * xbj * o_f1xq2(S, xbj, Q2) / (Q2 + M2 - mp2));
+  f /= xi;
+  f /= pt2;
+  f *= 16.0 * (O_PI * O_PI);
+  return f;
+}
 /* reference src/MRegge.cc:852-882 PhotoProp (elastic leg) */
 static cx o_photo_prop(const ost *S, double s, double t, double m2) {
   const grb_param_regge *R = &S->d->regge;
@@ -1905,7 +1935,8 @@ static double yy_con_amp2(ost *S) {
   amp2 /= 4;
   S->nhamp = 16;
   /* kt-EPA fluxes, src/MFlux.cc:22-44 */
-  const double f1 = o_coh_flux(S, S->x1, S->t1, S->qt1), f2 = o_coh_flux(S, S->x2, S->t2, S->qt2);
+  const double f1 = S->excite1 ? o_incoh_flux(S, S->x1, S->t1, S->qt1, v4_m2(S->pfinal[1])) : o_coh_flux(S, S->x1, S->t1, S->qt1);
+  const double f2 = S->excite2 ? o_incoh_flux(S, S->x2, S->t2, S->qt2, v4_m2(S->pfinal[2])) : o_coh_flux(S, S->x2, S->t2, S->qt2);
   const double fluxes = f1 * f2 * (1.0 / (S->x1 * S->x2));
   const double tot = fluxes * amp2;
   const double sf = msqrt(fluxes);
@@ -2117,8 +2148,8 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int32_t *tape_used) {
   if (!d || !u || !w || !flags) return GRB_ERR_ARG;
   if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
-  /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex) */
-  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS)))
+  /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex) and yy[CON] (IncohFlux) */
+  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON)))
     return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;

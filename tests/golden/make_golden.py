@@ -65,6 +65,10 @@ CASES = [
     ("c2_alice_pipi_con_nstar1_screened", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 512, 8, True),
     ("c2_alice_kk_con_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 512, 8, True),
     ("c2_alice_kk_conminus_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON-]<F> -> K+ K-", 0, 1024, 8, True),
+    # semi-exclusive yy -> mu+ mu-: incoherent photon flux (CKMT F2) of the excited leg(s)
+    ("c4_cms_mumu_yycon_nstar1_born", "@NSTARS=1:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
+    ("c4_cms_mumu_yycon_nstar2_born", "@NSTARS=2:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
+    ("c4_cms_mumu_yycon_nstar1_screened", "@NSTARS=1:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 1, 192, 8, True),
     # <C> class with four central legs: the 2 -> 6 ladder MRegge::ME6 (14 integration dimensions)
     ("cc4_cms_4pi_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 2048, 16, True),
     ("cc4_cms_2pi2k_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K-", 0, 1536, 16, True),

@@ -67,7 +67,10 @@ def test_device_vs_reference_golden(grb, msa, path):
     # which feeds S3FINEL(t, M^2) directly.  That noise is a chaotic function of the last bits of the Born-level momenta,
     # and those differ between glibc's and CUDA's exp() in the sampling map (1 ulp): screened N* weights agree with the
     # reference to that noise (measured max 6e-9, median 8e-15), not to 1e-10; Born-level N* weights do (max 5e-13).
-    rtol = 5e-8 if (nstars and int(z["pomloop"])) else RTOL
+    # The same M^2 = E^2 - p^2 of the excited system enters the incoherent photon flux of yy[CON] already at Born level
+    # (x_Bj = Q^2 / (Q^2 + M^2 - m_p^2), MForm.cc:700-719): same noise, same allowance (measured max 5e-9, median 5e-16).
+    noisy = nstars and (int(z["pomloop"]) or "yy[" in str(z["process"]))
+    rtol = 5e-8 if noisy else RTOL
     rel = compare(w, fl, z["W"], z["flags"], kappa=z["kappa"], rtol=rtol)
     # how many points may need the conditioning term: 1e-3 for the well-conditioned amplitudes; the reference's explicit
     # rank-4 tensor algebra of the 2xV continuum is itself ill-conditioned (11-14 % of the golden points have kappa > 1e-11),
@@ -75,7 +78,7 @@ def test_device_vs_reference_golden(grb, msa, path):
     nzk = z["kappa"][z["W"] != 0]
     illcond = any(k in str(z["process"]) for k in ("rho", "phi", "yy[QED]", "p+ p-", "Lambda"))  # + spin-1/2 chains, QED gauge cancellation
     allow = 1e-3 + 2.0 / len(rel) + (0.25 * np.mean(nzk > 1e-11) if illcond else 0.0)
-    if nstars and int(z["pomloop"]):
+    if noisy:
         allow = 0.10
     assert np.mean(rel > RTOL) < allow, "too many points needed the conditioning term"
     # Regge amplitudes reproduce the reference's operation order (median ~1e-15); the tensor-pomeron device

@@ -24,6 +24,10 @@ CASES = [
      "PP[CON]<F> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", "false", 300000, 0.002),
     ("cc_alice_pipi_con_born", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "false", 300000, 0.001),
     ("cc_alice_pipi_con_screened", "tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", "true", 100000, 0.003),
+    # forward N* excitation (NSTARS replaced in the card copy)
+    ("c2_alice_pipi_con_nstar1_born", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "false", 300000, 0.002, "NSTARS=1"),
+    # (the reference needs > 25 min on 8 cores for this one at PRECISION 0.002: not stored yet, the test skips it)
+    ("c4_cms_mumu_yycon_nstar2_born", "tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", "false", 100000, 0.01, "NSTARS=2"),
     # another energy (beam energies replaced in the card copy): the energy-scan caller grb_xscan
     ("c2_alice_pipi_con_screened_7tev", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "true", 100000, 0.003, 3500.0),
 ]
@@ -38,7 +42,10 @@ def main():
         if only and name not in only:
             continue
         txt = open(os.path.join(REF_TREE, card)).read()
-        if len(case) > 6:
+        if len(case) > 6 and isinstance(case[6], str):      # "KEY=int": an integer key of the card replaced
+            key, val = case[6].split("=")
+            txt = re.sub(r'("%s"\s*:\s*)\d+' % key, r"\g<1>%s" % val, txt)
+        elif len(case) > 6:
             txt = re.sub(r'("ENERGY"\s*:\s*)\[[^\]]*\]', r"\g<1>[%g, %g]" % (case[6], case[6]), txt)
         txt = re.sub(r'("NCALL"\s*:\s*)\d+', r"\g<1>%d" % ncall, txt)
         txt = re.sub(r'("VEGAS"\s*:\s*\{[^}]*?"PRECISION"\s*:\s*)[0-9.eE+-]+', r"\g<1>%g" % prec, txt, flags=re.S)
@@ -57,7 +64,9 @@ def main():
                      "err_barn": float(m.group(2)), "ncall": ncall, "precision": prec,
                      "ref_points_per_s": float(f.group(1)) if f else None, "fid_pass": float(p.group(1)) if p else None,
                      "cores": os.cpu_count()}
-        if len(case) > 6:
+        if len(case) > 6 and isinstance(case[6], str):
+            res[name]["nstars"] = int(case[6].split("=")[1])
+        elif len(case) > 6:
             res[name]["ebeam"] = case[6]
             mt = re.search(r"Total:\s*([0-9.]+) mb.*?Elastic:\s*([0-9.]+) mb.*?Inelastic:\s*([0-9.]+) mb", clean, re.S)
             if mt:

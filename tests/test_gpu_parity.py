@@ -212,6 +212,8 @@ SIGMA_CASES = [  # name in tests/golden/sigma_ref.json, card, ncall, iters, prec
     ("cc_alice_pipi_con_born", "c2_alice.json", 1 << 21, 5, 0.0005),
     ("cc_alice_pipi_con_screened", "c2_alice.json", 1 << 21, 5, 0.001),
     ("cc4_cms_4pi_con_born", "c5_cms_4pi.json", 1 << 22, 5, 0.002),
+    ("c2_alice_pipi_con_nstar1_born", "c2_alice.json", 1 << 22, 5, 0.001),
+    ("c4_cms_mumu_yycon_nstar2_born", "c4_cms_mumu_lowmass.json", 1 << 22, 5, 0.001),
 ]
 
 
@@ -225,7 +227,7 @@ def test_cross_section_matches_reference(grb, msa, name, card, ncall, iters, pre
     if name not in allref:
         pytest.skip("no reference cross section stored for " + name)
     ref = allref[name]
-    E = engine_for(grb, msa, card, ref["process"], int(ref["pomloop"]))
+    E = engine_for(grb, msa, card_variant(os.path.join(CARDS, card), ref.get("nstars", 0)), ref["process"], int(ref["pomloop"]))
     r = E.integrate(ncall=ncall, iters=iters, precision=prec, seed=20261017)
     err_ref = np.hypot(ref["err_barn"], 0.5e-3 * ref["sigma_barn"])
     pull = (r.sigma - ref["sigma_barn"]) / np.hypot(r.sigma_err, err_ref)

@@ -261,7 +261,9 @@ int grb_read_eikonal_file(const char *path, double *x, double *re, double *im, i
  * `randvec` of EventWeight); tape is [dtape][n] (the internal uniforms the reference draws from its
  * thread RNG inside EventWeight: BW masses, decay angles; MFactorized.cc:374, MKinematics.h:405-409).
  * w[n] receives the weight W (0 if not Valid()), flags[n] the GRB_FLAG_* bits. dump (optional, [ndump][n],
- * see GRB_DUMP_*) receives intermediate scalars for parity tests. Pointers may be host or device.        */
+ * see GRB_DUMP_*) receives intermediate scalars for parity tests. Pointers may be host or device.
+ * Host buffers are pipelined in slices (GRB_HOST_SLICE points, default 2^20): copy-in, kernels and copy-out of
+ * consecutive slices overlap on three streams; pinned host memory makes the copies asynchronous.          */
 int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
              uint8_t *flags, double *dump);
 

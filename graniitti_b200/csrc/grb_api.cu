@@ -86,7 +86,10 @@ static int regge_fast_ff(const DevProc &P) {
   if (P.ps_class == GRB_CLASS_C && P.n_legs == 2 && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] &&
       P.offshellFF >= 0 && P.offshellFF <= 2)
     return 10 + P.offshellFF;                                                       // <C> class Regge continuum
-  return (P.ps_class == GRB_CLASS_F && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] && P.offshellFF >= 0 && P.offshellFF <= 2) ? P.offshellFF : -1;
+  if (P.ps_class == GRB_CLASS_F && P.excitation == 0 && P.amp_kind == 0 && P.regge_n[0] && !P.regge_n[1] && !P.regge_n[2] &&
+      P.offshellFF >= 0 && P.offshellFF <= 2)
+    return (P.ln_inv_s0 == 0.0 ? 20 : 0) + P.offshellFF;  // s0 = 1 GeV^2: ln(1/s0) = 0 exactly
+  return -1;
 }
 
 // desc -> DevProc. Host libm (glibc, the reference's) evaluates the loop invariants.

@@ -46,7 +46,7 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   L.emax = P.sqrt_s - (L.m1 + L.m2);
   L.same_mass = SAME;
   L.exc = P.excitation ? (int)it[IT_EXC * c] : 0;
-  if ((FF < 0 || FF >= 10) && P.ps_class == GRB_CLASS_C) {
+  if ((FF < 0 || (FF >= 10 && FF < 20)) && P.ps_class == GRB_CLASS_C) {
     L.m3 = L.mXsq; L.m4 = L.shY; L.qx = L.chY;
     L.qy = it[(IT_CK + 0) * c]; L.sh3 = it[(IT_CK + 1) * c]; L.ch3 = it[(IT_CK + 2) * c];
     L.sh4 = it[(IT_CK + 3) * c]; L.ch4 = it[(IT_CK + 4) * c];
@@ -74,8 +74,9 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   } else {
     cx h0;
     h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
-    if (AMP == AMP_REGGE && FF >= 10) it[IT_AMP2 * c] = screened_amp2_regge_fast_C<SAME, (FF >= 10 ? FF - 10 : 0)>(L, h0);
-    else if (AMP == AMP_REGGE && FF >= 0) it[IT_AMP2 * c] = screened_amp2_regge_fast<SAME, (FF >= 0 && FF < 10 ? FF : 0)>(L, h0);
+    if (AMP == AMP_REGGE && FF >= 10 && FF < 20) it[IT_AMP2 * c] = screened_amp2_regge_fast_C<SAME, (FF >= 10 && FF < 20 ? FF - 10 : 0)>(L, h0);
+    else if (AMP == AMP_REGGE && FF >= 20) it[IT_AMP2 * c] = screened_amp2_regge_fast<SAME, (FF >= 20 ? FF - 20 : 0), true>(L, h0);
+    else if (AMP == AMP_REGGE && FF >= 0) it[IT_AMP2 * c] = screened_amp2_regge_fast<SAME, (FF >= 0 && FF < 10 ? FF : 0), false>(L, h0);
     else if (AMP == AMP_TENSOR_2XS && FF >= 0) it[IT_AMP2 * c] = screened_amp2_tensor_fast<SAME>(L, h0);
     else it[IT_AMP2 * c] = screened_amp2_h1<AMP, SAME>(L, h0);
   }
@@ -165,7 +166,8 @@ static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
 }
 
 // regge_ff: >= 0 when the one-basic-block node applies -- PARAM_REGGE::offshellFF for the Regge continuum with one active
-// trajectory (+10 in the <C> class), 0 for the tensor pomeron 2xS (<F> class); no forward excitation -- else -1
+// trajectory (+10 in the <C> class, +20 in the <F> class with s0 = 1 GeV^2), 0 for the tensor pomeron 2xS (<F> class);
+// no forward excitation -- else -1
 int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, cudaStream_t st) {
   // tuning knob for profiling runs; the default is the measured best (profiles/)
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
@@ -208,12 +210,15 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
     if (regge_ff == 0) { launch_screen_t<4, AMP_REGGE, 0>(a, sm_count, st); return 2; }
     if (regge_ff == 1) { launch_screen_t<4, AMP_REGGE, 1>(a, sm_count, st); return 2; }
     if (regge_ff == 2) { launch_screen_t<4, AMP_REGGE, 2>(a, sm_count, st); return 2; }
+    if (regge_ff == 20) { launch_screen_t<4, AMP_REGGE, 20>(a, sm_count, st); return 2; }  // <F> class, s0 = 1 GeV^2
+    if (regge_ff == 21) { launch_screen_t<4, AMP_REGGE, 21>(a, sm_count, st); return 2; }
+    if (regge_ff == 22) { launch_screen_t<4, AMP_REGGE, 22>(a, sm_count, st); return 2; }
     if (regge_ff == 10) { launch_screen_t<4, AMP_REGGE, 10>(a, sm_count, st); return 2; }  // <C> class
     if (regge_ff == 11) { launch_screen_t<4, AMP_REGGE, 11>(a, sm_count, st); return 2; }
     if (regge_ff == 12) { launch_screen_t<4, AMP_REGGE, 12>(a, sm_count, st); return 2; }
   }
-  if (!nofast && regge_ff == 2 && minb == 3) { launch_screen_t<3, AMP_REGGE, 2>(a, sm_count, st); return 2; }  // occupancy probes
-  if (!nofast && regge_ff == 2 && minb == 5) { launch_screen_t<5, AMP_REGGE, 2>(a, sm_count, st); return 2; }
+  if (!nofast && (regge_ff == 2 || regge_ff == 22) && minb == 3) { launch_screen_t<3, AMP_REGGE, 2>(a, sm_count, st); return 2; }  // occupancy probes
+  if (!nofast && (regge_ff == 2 || regge_ff == 22) && minb == 5) { launch_screen_t<5, AMP_REGGE, 2>(a, sm_count, st); return 2; }
   switch (minb) {
     case 3: launch_screen_t<3, AMP_REGGE>(a, sm_count, st); break;
     case 5: launch_screen_t<5, AMP_REGGE>(a, sm_count, st); break;

@@ -1126,7 +1126,8 @@ __device__ __forceinline__ double screened_amp2_h1(const LoopInv &L, const cx &h
 // says whether a range guard failed on a node that was still valid at that point -- then (rare) the caller re-evaluates
 // the node on the checked path.  Same expressions in the same order as the checked path: identical bits when the guards
 // hold.  FF = PARAM_REGGE::offshellFF resolved at compile time.
-template <bool SAME, int FF>
+// S0ONE: PARAM_REGGE::s0 = 1 GeV^2 (TUNE0), ln(1/s0) = 0 exactly: the four additions of it are identities and are skipped
+template <bool SAME, int FF, bool S0ONE>
 __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
@@ -1180,7 +1181,9 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
   }
   redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
   const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
-  const double xt = fma(al1, L13 + P.ln_inv_s0, fma(al2, L24 + P.ln_inv_s0, gt)), xu = fma(al1, L14 + P.ln_inv_s0, fma(al2, L23 + P.ln_inv_s0, gu));
+  const double c0 = S0ONE ? 0.0 : P.ln_inv_s0;
+  const double xt = S0ONE ? fma(al1, L13, fma(al2, L24, gt)) : fma(al1, L13 + c0, fma(al2, L24 + c0, gt));
+  const double xu = S0ONE ? fma(al1, L14, fma(al2, L23, gu)) : fma(al1, L14 + c0, fma(al2, L23 + c0, gu));
   const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
   const double num = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), den = dt * du * dF;
   const double R   = div_fast_core(num, den);
@@ -1200,7 +1203,7 @@ __device__ __forceinline__ bool regge_node_checked(const LoopInv &L, const PzCon
   A = regge_me4(in);
   return true;
 }
-template <bool SAME, int FF>
+template <bool SAME, int FF, bool S0ONE>
 __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, const cx &h0) {
   const DevLoop &Q = c_loop;
   PzConst        pc;
@@ -1214,7 +1217,7 @@ __device__ __forceinline__ double screened_amp2_regge_fast(const LoopInv &L, con
       const double kt = Q.kt[j];
       bool         valid;
       cx           A;
-      if (__builtin_expect(regge_node_fast<SAME, FF>(L, pzi, kt * cp, kt * sp, valid, A), 0)) valid = regge_node_checked<SAME>(L, pc, kt * cp, kt * sp, A);
+      if (__builtin_expect(regge_node_fast<SAME, FF, S0ONE>(L, pzi, kt * cp, kt * sp, valid, A), 0)) valid = regge_node_checked<SAME>(L, pc, kt * cp, kt * sp, A);
       if (valid) {  // rejected nodes contribute 0 but keep their Simpson weight (predicated, no branch)
         Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
         Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,7 @@ struct grb_engine {
   DevLoop          dloop;
   DevRes           dres;
   bool             have_loop = false;
+  bool             const_dirty = true;  // the engine's parameter blocks changed since they were last uploaded
   // screening work list (one chunk)
   int64_t       chunk      = 0;
   double *      d_items    = nullptr;
@@ -39,6 +41,7 @@ struct grb_engine {
   double *      d_ev = nullptr, *d_pay = nullptr;
   unsigned int *d_ev_count = nullptr;
   int64_t       ev_cap = 0;
+  int64_t       ev_dropped = 0;  // accepted events of the last GENERATE iteration that did not fit ev_cap
   // VEGAS
   grb_accum *d_acc  = nullptr;
   double *   d_xmat = nullptr;
@@ -61,7 +64,17 @@ struct grb_engine {
   std::string err;
 };
 
-static const grb_engine *g_const_owner = nullptr;  // whose DevProc/DevLoop sit in constant memory
+// The parameter blocks (DevProc / DevLoop / DevRes) live in __constant__ memory: one copy per device.  Several engines
+// may share a device (and be driven from several host threads), so the copy has an owner per device, guarded by a mutex
+// that is held while a call enqueues its kernels; a new owner first makes its stream wait for the previous owner's last
+// launch (an event recorded after every enqueue), then uploads its own blocks on its own stream.
+struct ConstSlot {
+  std::mutex        mu;
+  const grb_engine *owner    = nullptr;
+  cudaEvent_t       last_use = nullptr;
+};
+static ConstSlot         g_const[64];
+static inline ConstSlot &const_slot(int device) { return g_const[(unsigned)device % 64u]; }
 static thread_local std::string g_last_global_error;
 
 #define ITEM_NF 36  /* = IT_NF of grb_accum.cuh */
@@ -372,13 +385,23 @@ static int digest_res(const grb_process_desc &d, DevRes &R, std::string &err) {
   return GRB_OK;
 }
 
+// call with const_slot(e->device).mu held; release_constants() after the last kernel of the call was enqueued
 static int ensure_constants(grb_engine *e) {
-  if (g_const_owner != e) {
+  ConstSlot &c = const_slot(e->device);
+  if (c.owner != e || e->const_dirty) {
+    if (c.owner != e && c.last_use) CK(cudaStreamWaitEvent(e->stream, c.last_use, 0));
     CK(upload_proc(e->dproc, e->stream));
     CK(upload_res(e->dres, e->stream));
     if (e->have_loop) CK(upload_loop(e->dloop, e->stream));
-    g_const_owner = e;
+    c.owner        = e;
+    e->const_dirty = false;
   }
+  return GRB_OK;
+}
+static int release_constants(grb_engine *e) {
+  ConstSlot &c = const_slot(e->device);
+  if (!c.last_use) CK(cudaEventCreateWithFlags(&c.last_use, cudaEventDisableTiming));
+  CK(cudaEventRecord(c.last_use, e->stream));
   return GRB_OK;
 }
 
@@ -472,9 +495,13 @@ const char *grb_last_error(const grb_engine *e) { return e ? e->err.c_str() : g_
 
 void grb_destroy(grb_engine *e) {
   if (!e) return;
-  if (g_const_owner == e) g_const_owner = nullptr;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  {
+    ConstSlot &c = const_slot(e->device);
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.owner == e) c.owner = nullptr;
+  }
   cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_bins_hi); cudaFree(e->d_item_count);
   cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch); cudaFree(e->d_max2);
   cudaFree(e->d_ev); cudaFree(e->d_pay); cudaFree(e->d_ev_count);
@@ -503,9 +530,17 @@ int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const do
   DevLoop &Q = e->dloop;
   memset(&Q, 0, sizeof(Q));
   Q.nkt = NKT; Q.nphi = NPHI;
+  // IArray1D::Interpolate1D works on the array's own uniform grid (MIN, MAX, STEP = (MAX - MIN) / N; MEikonal.cc:489-512,
+  // defaults MEikonalNumerics::MinKT2 = 1e-6, MaxKT2 = 25, MEikonal.h:27-28): taken from the table, which must be uniform
   const int    N    = n_points - 1;
-  const double MIN = 1e-6, MAX = 25.0;  // MEikonalNumerics::MinKT2/MaxKT2, MEikonal.h:27-28
+  const double MIN = kt2[0], MAX = kt2[N];
   const double STEP = (MAX - MIN) / N;
+  if (!(MAX > MIN) || !(MIN >= 0.0)) { e->err = "eikonal table: kt^2 grid must be increasing and non-negative"; return GRB_ERR_ARG; }
+  for (int i = 0; i <= N; ++i)
+    if (std::fabs(kt2[i] - (MIN + i * STEP)) > 1e-9 * MAX) {
+      e->err = "eikonal table: kt^2 grid is not uniform (log-spaced tables are outside the device path)";
+      return GRB_ERR_ARG;
+    }
   const double StepKT  = (d.loop_max_kt - d.loop_min_kt) / NKT;
   const double StepPhi = (2.0 * GRB_PI - 0.0) / NPHI;
   auto w38 = [](int i, int n) { return (i == 0 || i == n) ? 1.0 : ((i % 3 == 0) ? 2.0 : 3.0); };
@@ -539,8 +574,8 @@ int grb_set_eikonal(grb_engine *e, const double *kt2, const double *re, const do
     Q.wphi[0] += Q.wphi[NPHI];
     Q.nphi_nodes = NPHI;
   }
-  e->have_loop = true;
-  if (g_const_owner == e) g_const_owner = nullptr;  // force re-upload
+  e->have_loop   = true;
+  e->const_dirty = true;  // force re-upload
   return GRB_OK;
 }
 
@@ -554,8 +589,9 @@ static bool is_device_ptr(const void *p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
-             uint8_t *flags, double *dump) {
+// rng: internal draws from the Philox stream (seed, iteration, first_index + i) instead of a caller tape
+static int eval_impl(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, bool rng, uint64_t seed,
+                     uint64_t iteration, int64_t first_index, double *w, uint8_t *flags, double *dump) {
   if (!e || n < 0 || !u || !w || !flags || dim < e->desc.lipsdim || dtape < 0 || (dtape > 0 && !tape)) return GRB_ERR_ARG;
   if (e->desc.screening && !e->have_loop) { e->err = "screening is on but no eikonal table was set"; return GRB_ERR_STATE; }
   if (n == 0) return GRB_OK;
@@ -591,6 +627,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     df = (uint8_t *)sp; sp += b_f;
     dd = dump ? (double *)sp : nullptr;
   }
+  std::unique_lock<std::mutex> const_lock(const_slot(e->device).mu);
   int rc = ensure_constants(e);
   if (rc != GRB_OK) return rc;
   e->last_launches = 0;
@@ -615,6 +652,7 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     a.n = len;
     a.u = du + off; a.tape = dt ? dt + off : nullptr; a.ld = n; a.dim = dim; a.dtape = dtape;
     a.vegas = 0; a.bins = 0;
+    a.tape_rng = rng ? 1 : 0; a.seed = seed; a.iter = (uint32_t)iteration; a.first_call = first_index + off;
     a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
@@ -634,11 +672,24 @@ int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *t
     }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
+  rc = release_constants(e);
+  const_lock.unlock();
+  if (rc != GRB_OK) return rc;
   e->timed = true;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
   if (!dev_out) CK(cudaStreamSynchronize(e->stream_out));
   return GRB_OK;
+}
+
+int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
+             uint8_t *flags, double *dump) {
+  return eval_impl(e, n, u, dim, tape, dtape, false, 0, 0, 0, w, flags, dump);
+}
+
+int grb_eval_rng(grb_engine *e, int64_t n, const double *u, int dim, uint64_t seed, uint64_t iteration, int64_t first_index,
+                 double *w, uint8_t *flags, double *dump) {
+  return eval_impl(e, n, u, dim, nullptr, 0, true, seed, iteration, first_index, w, flags, dump);
 }
 
 int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim, int64_t first_call,
@@ -655,10 +706,12 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
       e->ev_cap = ec ? std::max<int64_t>(1024, atoll(ec)) : (int64_t)1 << 22;
       CK(cudaMalloc(&e->d_ev, sizeof(double) * (4 * npart + 2) * e->ev_cap));
       CK(cudaMalloc(&e->d_ev_count, 2 * sizeof(unsigned int)));
-      if (e->desc.screening) CK(cudaMalloc(&e->d_pay, sizeof(double) * 4 * npart * e->chunk));
     }
+    // (screening may have been switched on by grb_update_desc after the first generation call)
+    if (e->desc.screening && !e->d_pay) CK(cudaMalloc(&e->d_pay, sizeof(double) * 4 * npart * e->chunk));
     CK(cudaMemsetAsync(e->d_ev_count, 0, 2 * sizeof(unsigned int), e->stream));
   }
+  std::unique_lock<std::mutex> const_lock(const_slot(e->device).mu);
   int rc = ensure_constants(e);
   if (rc != GRB_OK) return rc;
   CK(cudaMemcpyAsync(e->d_xmat, xmat, sizeof(double) * bins * dim, cudaMemcpyHostToDevice, e->stream));
@@ -685,6 +738,9 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     }
   }
   CK(cudaEventRecord(e->ev1, e->stream));
+  rc = release_constants(e);
+  const_lock.unlock();
+  if (rc != GRB_OK) return rc;
   e->timed = true;
   CK(cudaGetLastError());
   if (accum_device_ptr) *accum_device_ptr = e->d_acc;
@@ -703,6 +759,7 @@ int grb_vegas_fetch(grb_engine *e, grb_accum *out) {
     CK(cudaMemcpy(c, e->d_ev_count, sizeof(c), cudaMemcpyDeviceToHost));
     out->n_accepted = (double)c[0];
     out->n_overflow = (double)c[1];
+    e->ev_dropped   = std::max<int64_t>(0, (int64_t)c[0] - e->ev_cap);
   }
   return GRB_OK;
 }
@@ -775,8 +832,10 @@ int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, doubl
   if (n_particles) *n_particles = npart;
   if (!e->d_ev) return 0;
   if (cudaSetDevice(e->device) != cudaSuccess) return GRB_ERR_CUDA;
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return GRB_ERR_CUDA;  // the engine's stream is non-blocking
   unsigned int c[2] = {0, 0};
   if (cudaMemcpy(c, e->d_ev_count, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return GRB_ERR_CUDA;
+  e->ev_dropped   = std::max<int64_t>(0, (int64_t)c[0] - e->ev_cap);
   const int64_t n = std::min<int64_t>(std::min<int64_t>((int64_t)c[0], e->ev_cap), max_events);
   if (n == 0) return 0;
   // device rows have stride ev_cap; the caller's arrays are [npart][4][n] and [2][n] (W, f)
@@ -786,6 +845,16 @@ int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, doubl
                               sizeof(double) * e->ev_cap, sizeof(double) * n, 2, cudaMemcpyDeviceToHost) != cudaSuccess)
     return GRB_ERR_CUDA;
   return n;
+}
+
+int64_t grb_events_dropped(const grb_engine *e) { return e ? e->ev_dropped : GRB_ERR_ARG; }
+
+int grb_loop_nodes(const grb_engine *e, int *nkt_nodes, int *nphi_nodes) {
+  if (!e) return GRB_ERR_ARG;
+  if (!e->have_loop) return GRB_ERR_STATE;
+  if (nkt_nodes) *nkt_nodes = e->dloop.nkt + 1;
+  if (nphi_nodes) *nphi_nodes = e->dloop.nphi_nodes;
+  return GRB_OK;
 }
 
 int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_out, double *omega_re_out,
@@ -830,7 +899,7 @@ int grb_update_desc(grb_engine *e, const grb_process_desc *desc) {
   e->dproc = P;
   e->dres  = R;
   if (!same_loop) e->have_loop = false;   // A_eik(kt^2) and the loop norm depend on s and the discretisation
-  if (g_const_owner == e) g_const_owner = nullptr;  // force the constant upload on the next call
+  e->const_dirty = true;  // force the constant upload on the next call
   return GRB_OK;
 }
 

@@ -118,6 +118,7 @@ struct PointArgs {
   const double *u, *tape;
   int64_t       ld;
   int           dim, dtape;
+  int           tape_rng;  // parity mode with internal draws from the point's Philox stream (seed, iter, first_call + idx)
   // VEGAS-mode inputs
   int           vegas, bins, mode;
   const double *xmat;  // [bins][dim] device

@@ -129,6 +129,12 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
       } else {
         DrawsSoA dr;
         dr.u = a.u; dr.tape = a.tape; dr.n = a.ld; dr.idx = idx; dr.dtape = a.dtape; dr.pos = 0; dr.overrun = false;
+        dr.rng = a.tape_rng != 0;
+        if (dr.rng) {
+          const uint64_t gp = (uint64_t)(a.first_call + idx);
+          dr.g.k0 = (uint32_t)a.seed; dr.g.k1 = (uint32_t)(a.seed >> 32);
+          dr.p_lo = (uint32_t)gp; dr.p_hi = (uint32_t)(gp >> 32); dr.iter = a.iter; dr.d0 = dim;
+        }
 #pragma unroll
         for (int j = 0; j < UD; ++j)
           if (j < dim) u[j] = dr.coord(j);

@@ -46,10 +46,23 @@ struct DrawsSoA {
   int64_t       n, idx;
   int           dtape, pos;
   bool          overrun;
+  // rng: the internal draws come from the point's Philox stream instead of a caller tape (grb_eval_rng: seam A as the
+  // reference calls it -- the caller supplies randvec only, EventWeight draws from its own generator).  Draw d0 + pos, the
+  // same stream positions the VEGAS mode uses after its d0 = dim coordinates.
+  bool     rng;
+  Philox   g;
+  uint32_t p_lo, p_hi, iter;
+  int      d0;
   __device__ __forceinline__ double coord(int j) const { return u[(int64_t)j * n + idx]; }
   __device__ __forceinline__ double next() {
     double v = 0.5;
-    if (pos < dtape) v = tape[(int64_t)pos * n + idx]; else overrun = true;
+    if (rng) {
+      const int d = d0 + pos;
+      uint32_t  o[4];
+      g.block(p_lo, p_hi, iter, (uint32_t)(d >> 1), o);
+      v = (d & 1) ? u01_from_bits(o[3], o[2]) : u01_from_bits(o[1], o[0]);
+    } else if (pos < dtape) v = tape[(int64_t)pos * n + idx];
+    else overrun = true;
     ++pos;
     return v;
   }

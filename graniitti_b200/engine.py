@@ -60,6 +60,12 @@ def lib():
         L.grb_xscan.argtypes = [vp, vp, cint, C.POINTER(_abi.VegasParam), C.POINTER(_abi.XscanRow)]
         L.grb_eval.restype = cint
         L.grb_eval.argtypes = [vp, i64, vp, cint, vp, cint, vp, vp, vp]
+        L.grb_eval_rng.restype = cint
+        L.grb_eval_rng.argtypes = [vp, i64, vp, cint, u64, u64, i64, vp, vp, vp]
+        L.grb_loop_nodes.restype = cint
+        L.grb_loop_nodes.argtypes = [vp, C.POINTER(cint), C.POINTER(cint)]
+        L.grb_events_dropped.restype = i64
+        L.grb_events_dropped.argtypes = [vp]
         L.grb_vegas_iterate.restype = cint
         L.grb_vegas_iterate.argtypes = [vp, vp, cint, cint, i64, i64, u64, u64, cint, dbl, C.POINTER(_abi.Accum)]
         L.grb_vegas_iterate_async.restype = cint
@@ -176,6 +182,15 @@ def local_calls(calls, rank, nranks):
     return first.value, n.value
 
 
+def comm_unique_id():
+    """128 opaque bytes (ncclUniqueId) made by rank 0 and shipped to the other ranks by any means."""
+    buf = C.create_string_buffer(128)
+    rc = lib().grb_comm_unique_id(buf)
+    if rc != 0:
+        raise GrbError(rc, lib().grb_last_error(None).decode(errors="replace"))
+    return buf.raw
+
+
 def measure_dfma_peak(device=0):
     v = C.c_double(0)
     rc = lib().grb_measure_dfma_peak(device, C.byref(v))
@@ -247,6 +262,27 @@ class Engine:
         """Pointer-level call (numpy arrays or torch CUDA tensors)."""
         self._check(lib().grb_eval(self._h, n, _ptr(u), dim, _ptr(tape), dtape, _ptr(w), _ptr(flags), _ptr(dump)))
 
+    def eval_rng_raw(self, n, u, dim, seed, iteration, first_index, w, flags, dump=None):
+        """Seam A as the reference calls it: coordinates from the caller, internal draws from the engine's Philox stream."""
+        self._check(lib().grb_eval_rng(self._h, n, _ptr(u), dim, seed, iteration, first_index, _ptr(w), _ptr(flags), _ptr(dump)))
+
+    def eval_rng(self, u, seed, iteration=0, first_index=0):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        dim, n = u.shape
+        w = np.zeros(n)
+        flags = np.zeros(n, dtype=np.uint8)
+        self.eval_rng_raw(n, u, dim, seed, iteration, first_index, w, flags)
+        return w, flags
+
+    def loop_nodes(self):
+        """(kt nodes, phi nodes) of the screening loop as the kernels execute them."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(lib().grb_loop_nodes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def events_dropped(self):
+        return int(lib().grb_events_dropped(self._h))
+
     def vegas_iterate(self, xmat, first_call, ncalls, seed, iteration, mode=_abi.GRB_MODE_INTEGRATE, maxf=0.0):
         xmat = np.ascontiguousarray(xmat, dtype=np.float64)
         bins, dim = xmat.shape
@@ -309,6 +345,14 @@ class Engine:
         mom = mom.reshape(-1)[:npart * 4 * n].reshape(npart, 4, n)
         wts = wts.reshape(-1)[:2 * n].reshape(2, n)
         return mom, wts
+
+    def comm_init(self, rank, nranks, unique_id):
+        """Join the library's own NCCL communicator (torch-free hosts): grb_comm_init."""
+        self._check(lib().grb_comm_init(self._h, rank, nranks, C.create_string_buffer(bytes(unique_id), 128)))
+
+    def allreduce(self):
+        """All-rank sums / maxima of the accumulators of the last vegas_iterate_async, on the engine's stream."""
+        self._check(lib().grb_allreduce(self._h))
 
     def sync(self):
         self._check(lib().grb_sync(self._h))

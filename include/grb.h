@@ -246,6 +246,11 @@ int grb_build_eikonal(grb_engine *e, int number_bt, int number_kt2, double *bt_o
                       double *omega_im_out, double *kt2_out, double *re_out, double *im_out,
                       double *xs_tot_el_inel /* [3] or NULL */);
 
+/* Nodes of the screening loop as the kernels execute them: nkt_nodes = NumberLoopKT + 1, nphi_nodes = NumberLoopPHI
+ * (phi = 2 pi is folded onto phi = 0 with both Simpson end weights) or NumberLoopPHI + 1 with GRB_NO_PHI_FOLD=1.
+ * GRB_ERR_STATE before a table was installed.                                                                          */
+int grb_loop_nodes(const grb_engine *e, int *nkt_nodes, int *nphi_nodes);
+
 /* The reference's table cache (src/MEikonal.cc:60-128): file names "MBT_<pdg1>_<pdg2>_<sqrts>_<djb2 hash>" /
  * "MSA_..." (hash over s, beams, PARAM_SOFT, MEikonalNumerics; src/MForm.cc:94-100, MEikonal.h:60-67,
  * MAux.cc:281-287) and the 3-column "%.15g" CSV rows of IArray1D::WriteArray/ReadArray (:404-487), so that
@@ -266,6 +271,15 @@ int grb_read_eikonal_file(const char *path, double *x, double *re, double *im, i
  * consecutive slices overlap on three streams; pinned host memory makes the copies asynchronous.          */
 int grb_eval(grb_engine *e, int64_t n, const double *u, int dim, const double *tape, int dtape, double *w,
              uint8_t *flags, double *dump);
+
+/* Seam A exactly as the reference calls it: the caller supplies only the VEGAS-visible coordinates (`randvec` of
+ * MProcess::EventWeight, include/Graniitti/MProcess.h:84) and the internal uniforms are drawn by the engine -- the
+ * reference draws them from its per-thread generator inside EventWeight (MFactorized.cc:374, MKinematics.h:405-409), here
+ * point i takes the draws dim, dim+1, ... of the Philox4x32-10 stream (key = seed, counter = (iteration, first_index + i)),
+ * the same stream grb_vegas_iterate uses.  Halves the host-to-device traffic of grb_eval for the BASELINE configurations
+ * (48 instead of 80 bytes per point).  Reproducible on the host with tests/philox_ref.py.                                */
+int grb_eval_rng(grb_engine *e, int64_t n, const double *u, int dim, uint64_t seed, uint64_t iteration,
+                 int64_t first_index, double *w, uint8_t *flags, double *dump);
 
 enum {
   GRB_DUMP_T1 = 0, GRB_DUMP_T2, GRB_DUMP_S1, GRB_DUMP_S2, GRB_DUMP_M2, GRB_DUMP_Y, GRB_DUMP_PT,
@@ -306,6 +320,10 @@ int grb_vegas_optimize_grid(double *xmat, const double *f2mat, int bins, int dim
  * 1657-1668); grb_accum.n_accepted / n_overflow report the totals of the iteration.                        */
 int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, double *weights,
                        int *n_particles);
+
+/* Accepted events of the last GRB_MODE_GENERATE iteration that did not fit the engine's event buffer (GRB_EVENT_CAP
+ * events, default 2^22): grb_accum.n_accepted counts every accepted event, grb_get_events returns at most the capacity. */
+int64_t grb_events_dropped(const grb_engine *e);
 
 /* ---- the integration loop (host C++, device iterations) ----------------------------------------------- */
 

@@ -43,3 +43,53 @@ def philox_points(xmat, first_call, n, seed, it, ntape):
         for t in range(ntape):
             tape[i, t] = draw(seed, p, it, dim + t)
     return u, vw, tape
+
+
+# ---- vectorised restatement (numpy uint64 lanes) for the full-size parity sets -----------------------------------------
+def _philox4x32_np(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on arrays of 32-bit words held in uint64 (so that the 32x32 -> 64 products do not overflow)."""
+    m = np.uint64(MASK)
+    s32 = np.uint64(32)
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        c0, c1, c2, c3 = ((p1 >> s32) ^ c1 ^ k0) & m, p1 & m, ((p0 >> s32) ^ c3 ^ k1) & m, p0 & m
+        k0 = (k0 + np.uint64(W0)) & m
+        k1 = (k1 + np.uint64(W1)) & m
+    return c0, c1, c2, c3
+
+
+def philox_uniforms_np(first_call, n, seed, it, ndraws):
+    """[n][ndraws] uniforms of the points first_call .. first_call + n - 1 (same layout as draw())."""
+    p = np.arange(first_call, first_call + n, dtype=np.uint64)
+    plo, phi = p & np.uint64(MASK), (p >> np.uint64(32)) & np.uint64(MASK)
+    itw = np.full(n, it & MASK, dtype=np.uint64)
+    out = np.empty((n, ndraws))
+    for blk in range((ndraws + 1) // 2):
+        o = _philox4x32_np(plo, phi, itw, np.full(n, blk, dtype=np.uint64), seed & MASK, (seed >> 32) & MASK)
+        for half in range(2):
+            d = 2 * blk + half
+            if d >= ndraws:
+                break
+            lo, hi = (o[2], o[3]) if half else (o[0], o[1])
+            out[:, d] = (((hi << np.uint64(32)) | lo) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    return out
+
+
+def philox_points_np(xmat, first_call, n, seed, it, ntape):
+    """Vectorised philox_points(): (u [n][dim], vegasweight [n], tape [n][ntape]), bit-identical to the scalar loop."""
+    bins, dim = xmat.shape
+    r = philox_uniforms_np(first_call, n, seed, it, dim + ntape)
+    zn = r[:, :dim] * bins + 1.0
+    ind = np.clip(zn.astype(np.int64), 1, bins)
+    cols = np.arange(dim)[None, :]
+    x1 = xmat[ind - 1, cols]
+    x0 = np.where(ind > 1, xmat[np.maximum(ind - 2, 0), cols], 0.0)
+    zo = np.where(ind > 1, x1 - x0, x1)
+    u = np.where(ind > 1, x0 + (zn - ind) * zo, (zn - ind) * zo)
+    vw = np.ones(n)
+    for j in range(dim):      # same left-to-right product as the device loop
+        vw = vw * (zo[:, j] * bins)
+    return u, vw, r[:, dim:].copy()

@@ -345,3 +345,36 @@ def test_four_leg_ladder_vegas_path(grb, msa):
     with pytest.raises(grb.GrbError):
         E.integrate(ncall=1 << 20, iters=3, precision=0.05, seed=3)
     E.close()
+
+
+def test_eval_rng_is_eval_with_the_philox_tape(grb, msa):
+    """grb_eval_rng (seam A as the reference calls it: coordinates from the caller, internal draws from the engine's
+    generator) == grb_eval fed with the same Philox draws regenerated on the host, bit for bit."""
+    from philox_ref import philox_uniforms_np
+    for card, proc, pom, ntape in (("c2_alice.json", None, 1, 8), ("c5_cms_4pi.json", None, 0, 24)):
+        E = engine_for(grb, msa, card, proc, pom)
+        dim, n, seed, it, first = E.desc.lipsdim, 50000, (7 << 32) + 99, 5, (1 << 33) + 12345
+        u, _ = make_points(n, dim, 1, 11, adapted=True)
+        tape = philox_uniforms_np(first, n, seed, it, dim + ntape)[:, dim:]
+        w0, f0, _ = E.eval(u.T.copy(), tape.T.copy())
+        w1, f1 = E.eval_rng(u.T.copy(), seed, it, first)
+        assert np.array_equal(w0, w1) and np.array_equal(f0, f1) and (w0 != 0).sum() > 1000
+        E.close()
+
+
+def test_two_engines_share_a_device(grb, msa):
+    """The __constant__ parameter blocks have one owner per device: engines that alternate on one device (asynchronous
+    iterations in flight on their own streams) must see their own parameters."""
+    bins = 128
+    Ea = engine_for(grb, msa, "c2_alice.json", "PP[CON]<F> -> pi+ pi-", 1)
+    Eb = engine_for(grb, msa, "c2_alice.json", "PP[CON]<F> -> K+ K-", 0)
+    xmat = np.tile(((np.arange(bins) + 1) / bins)[:, None], (1, 6))
+    ra = Ea.vegas_iterate(xmat, 0, 1 << 20, 5, 1)
+    rb = Eb.vegas_iterate(xmat, 0, 1 << 20, 5, 1)
+    for _ in range(3):
+        Ea.vegas_iterate_async(xmat, 0, 1 << 20, 5, 1)
+        Eb.vegas_iterate_async(xmat, 0, 1 << 20, 5, 1)      # uploads its constants while Ea's kernels are in flight
+        a, b = Ea.vegas_fetch(), Eb.vegas_fetch()
+        assert abs(a.fsum - ra.fsum) <= 1e-12 * ra.fsum and a.n_fid_ok == ra.n_fid_ok
+        assert abs(b.fsum - rb.fsum) <= 1e-12 * rb.fsum and b.n_fid_ok == rb.n_fid_ok
+    Ea.close(); Eb.close()

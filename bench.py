@@ -77,8 +77,12 @@ def flop_model(name):
     p = os.path.join(ROOT, "profiles", "r02_opcount.json")
     if os.path.exists(p):
         t = json.load(open(p)).get(name)
-        if t:
+        if t and not t.get("amplitude_as_written_only"):
             return float(t["F_kin"]), float(t["F_born"]), float(t.get("F_node", 0.0)), "op count of the oracle restatement (profiles/r02_opcount.json)"
+        if t:   # kinematics counted; the amplitude is restated as explicit FTensor loops: closed-form estimate of the survey
+            k, b, n = SURVEY_FLOPS[name]
+            return float(t["F_kin"]), float(b), float(n), ("F_kin: op count of the oracle restatement; amplitude: survey's closed-form estimate "
+                                                          "(the oracle restates the reference's explicit rank-4 tensor loops, %.0f flop as written)" % t["F_born"])
     k, b, n = SURVEY_FLOPS[name]
     return float(k), float(b), float(n), "survey estimate (SURVEY.md section 8d)"
 
@@ -89,6 +93,19 @@ def sass_mix(kernel_key):
     if os.path.exists(p):
         return json.load(open(p)).get(kernel_key)
     return None
+
+
+GRIDS = os.path.join(ROOT, "tests", "golden", "bench_grids.npz")
+
+
+def workload_grid(wl, bins=128, dim=6):
+    """The converged VEGAS grid of the workload (scripts/make_bench_grids.py), so that every leg of the bench -- device
+    iterations, end-to-end call, CPU reference arm -- sees points of the distribution the metric is quoted on."""
+    if os.path.exists(GRIDS):
+        z = np.load(GRIDS)
+        if wl in z.files and z[wl].shape == (bins, dim):
+            return z[wl].copy(), "converged VEGAS grid of the workload (tests/golden/bench_grids.npz)"
+    return np.tile(((np.arange(bins) + 1) / bins)[:, None], (1, dim)), "uniform grid (no converged grid committed)"
 
 
 def env_int(k, d):
@@ -149,11 +166,13 @@ class ClockSampler:
 
 
 # ---- CPU reference arm -----------------------------------------------------------------------------------
-def synthetic_points(n, dim, dtape, seed):
-    """Synthetic phase-space points of the workloads: uniform coordinates with the two forward log-pt coordinates
-    concentrated where the proton pt is O(0.05 - 2.5 GeV), as an adapted VEGAS grid does (tests/helpers.make_points)."""
-    import helpers
-    return helpers.make_points(n, dim, dtape, seed, adapted=True)
+def synthetic_points(wl, n, dim, dtape, seed, first=0):
+    """Synthetic phase-space points of the workload: the Philox stream of the device path through the workload's converged
+    VEGAS grid (tests/philox_ref.py restates the device generator on the host)."""
+    from philox_ref import philox_points_np
+    xmat, _ = workload_grid(wl, 128, dim)
+    u, _, tape = philox_points_np(xmat, first, n, seed, 0, dtape)
+    return u, tape
 
 
 def cpu_reference_sample(wl, points_per_proc, nproc, seed):
@@ -161,7 +180,7 @@ def cpu_reference_sample(wl, points_per_proc, nproc, seed):
     Returns (points, seconds = max over processes of the in-loop time, kind)."""
     import helpers
     card, ref_card, process, pom, ntape = WORKLOADS[wl][:5]
-    u_t = [synthetic_points(points_per_proc, 6, ntape, seed + 17 * k) for k in range(nproc)]
+    u_t = [synthetic_points(wl, points_per_proc, 6, ntape, seed, first=k * points_per_proc) for k in range(nproc)]
     if helpers.have_ref():
         td = tempfile.mkdtemp(prefix="grb_ref_")
         procs = []
@@ -270,7 +289,7 @@ def run_ours(args):
     else:
         first, ncalls = rank * args.ncalls, args.ncalls
         total_calls = args.ncalls * world
-    xmat = np.tile(((np.arange(bins) + 1) / bins)[:, None], (1, dim))
+    xmat, grid_source = workload_grid(wl, bins, dim)
     nacc = ctypes.sizeof(_abi.Accum) // 8
     seed = 12345678
     state = {"xmat": xmat, "acc": None, "launches": 0, "ms_kernels": 0.0, "ms_screen": 0.0, "n_screen": 0,
@@ -326,14 +345,14 @@ def run_ours(args):
     # grb_eval_rng = MProcess::EventWeight(randvec) as the reference calls it: the caller supplies the coordinates, the
     # internal uniforms come from the engine's generator.  grb_eval (coordinates + a caller tape) is timed beside it.
     n_e2e = args.e2e_points
-    rng = np.random.default_rng(1234 + rank)
     hu = torch.empty((dim, n_e2e), dtype=torch.float64).pin_memory()
     ht = torch.empty((ntape, n_e2e), dtype=torch.float64).pin_memory()
     hw = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
     hf = torch.empty(n_e2e, dtype=torch.uint8).pin_memory()
-    hu.numpy()[:] = rng.random((dim, n_e2e))
-    hu.numpy()[0:2] = 0.85 + 0.15 * hu.numpy()[0:2]
-    ht.numpy()[:] = rng.random((ntape, n_e2e))
+    pu, ptape = synthetic_points(wl, n_e2e, dim, ntape, 1234, first=rank * n_e2e)
+    hu.numpy()[:] = pu.T
+    ht.numpy()[:] = ptape.T
+    del pu, ptape
     e2e_steps = max(3, min(args.steps, 10))
     e2e = {}
     for api in ("eval_rng", "eval"):
@@ -408,6 +427,7 @@ def run_ours(args):
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": descr, "workload_id": wl,
                            "points_per_step_per_gpu": ncalls, "points_per_step": total_calls, "vegas_bins": bins, "dim": dim,
+                           "grid": grid_source + "; it keeps adapting during the run",
                            "collective": None if world == 1 else ("grb_allreduce (library communicator, NCCL)" if args.comm == "native"
                                                                   else "torch.distributed all_reduce (NCCL) on the engine stream"),
                            "l2": "inputs are generated on the device per step (Philox counters), nothing is re-read "

@@ -351,8 +351,12 @@ static int daughter_parity(const grb_node &n) {
   return -1;  // light pseudoscalar mesons (reference MPDG.cc setPCL table: n0qq1 -> 0-+)
 }
 
+// overrides: the {key: value} blocks of the @R[name]{...} commands that target this resonance, in command order.  The
+// reference applies them to the freshly read resonance BEFORE SetResonances / SetupBranching (src/MGraniitti.cc:481-578),
+// so the decay coupling below is computed from the overridden mass and width (src/MProcess.cc:676-712).
 static void fill_resonance(const Json &R, const Json &tune, const Json &branching, const grb_process_desc &d,
-                           const std::string &name, grb_resonance &o) {
+                           const std::string &name, const std::vector<const std::map<std::string, std::string> *> &overrides,
+                           grb_resonance &o) {
   memset(&o, 0, sizeof(o));
   const Json &sp = tune.at("PARAM_SPIN");
   o.spingen = sp.at("SPINGEN").as_bool(); o.spindec = sp.at("SPINDEC").as_bool();
@@ -384,6 +388,35 @@ static void fill_resonance(const Json &R, const Json &tune, const Json &branchin
         if (a == b) tr += o.rho_re[a * GRB_RHO_DIM + b];
       }
     if (std::abs(tr - 1.0) > 1e-2) throw std::invalid_argument("gra::spin::Positivity: Density matrix is not properly normalized");
+  }
+  // ---- @R[name]{M:, W:, g<n>:, JZ<n>:} on-the-flight overrides (src/MGraniitti.cc:482-566); other keys match nothing ----
+  for (const auto *ov : overrides) {
+    const int N = o.spinX2 != 0 ? n : 1, J = (N - 1) / 2;
+    std::vector<double> newrho((size_t)N * N, 0.0);
+    bool density_touched = false;
+    for (const auto &x : *ov) {
+      if (x.first == "M") o.mass = std::stod(x.second);
+      if (x.first == "W") o.width = std::stod(x.second);
+      for (size_t k = 0; k < gT.size() && k < 8; ++k)
+        if (x.first == "g" + std::to_string(k)) o.g_Tensor[k] = std::stod(x.second);
+      for (int k = 0; k <= (N - 1) / 2; ++k)
+        if (x.first == "JZ" + std::to_string(k)) {
+          const double value = std::stod(x.second);
+          if (value < 0) throw std::invalid_argument("MGraniitti::ReadProcessParam: @R[] JZ value < 0");
+          newrho[(size_t)(N - 1 - J - k) * N + (N - 1 - J - k)] = value;
+          newrho[(size_t)(N - 1 - J + k) * N + (N - 1 - J + k)] = value;
+          density_touched = true;
+        }
+    }
+    if (density_touched) {
+      double trace = 0.0;
+      for (int a = 0; a < N; ++a) trace += newrho[(size_t)a * N + a];
+      if (!(std::abs(trace) > 0)) throw std::invalid_argument("MGraniitti::ReadProcessParam: @R[] Spin density error with <= 0 trace");
+      const double inv = 1.0 / trace;
+      for (int a = 0; a < GRB_RHO_DIM * GRB_RHO_DIM; ++a) { o.rho_re[a] = 0.0; o.rho_im[a] = 0.0; }
+      for (int a = 0; a < N; ++a)
+        for (int b = 0; b < N; ++b) o.rho_re[a * GRB_RHO_DIM + b] = newrho[(size_t)a * N + b] * inv;
+    }
   }
   // ---- decay side: BR, alpha_ls -> T matrix, equivalent coupling g_decay --------------------------------
   if (d.n_legs != 2) throw Unsupported("resonances need a 2-body central final state on the device path");
@@ -764,6 +797,13 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
     Json branching;
     if (base && base[0]) branching = parse_json5(read_file(std::string(base) + "/modeldata/" + modelparam + "/BRANCHING.json"));
     else branching = parse_json5(kBuiltinBranching);
+    for (auto &c : syntax)   // @R target checks, src/MGraniitti.cc:484-497
+      if (c.id == "R") {
+        if (c.target.empty()) throw std::invalid_argument("@Syntax error: invalid R[] without any target []");
+        if (c.target.size() > 1) throw std::invalid_argument("@Syntax error: invalid R[] with multiple targets inside []");
+        if (std::find(names.begin(), names.end(), c.target[0]) == names.end())
+          throw std::invalid_argument("@Syntax error: invalid R[" + c.target[0] + "] not found");
+      }
     for (auto &nm : names) {
       Json R;
       if (base && base[0]) {
@@ -776,14 +816,11 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
         R = parse_json5(txt);
       }
       grb_resonance &o = d.res[d.n_res++];
-      fill_resonance(R.at("PARAM_RES"), tune, branching, d, nm, o);
+      std::vector<const std::map<std::string, std::string> *> overrides;
+      for (auto &c : syntax)
+        if (c.id == "R" && c.target[0] == nm) overrides.push_back(&c.arg);
+      fill_resonance(R.at("PARAM_RES"), tune, branching, d, nm, overrides, o);
       for (auto &c : syntax) {
-        if (c.id == "R" && c.target.size() == 1 && c.target[0] == nm)
-          for (auto &kv : c.arg) {
-            if (kv.first == "M") o.mass = std::stod(kv.second);
-            else if (kv.first == "W") o.width = std::stod(kv.second);
-            else throw Unsupported("@R[]{" + kv.first + "} override is not supported yet");
-          }
         if (c.id == "SPINGEN") o.spingen = c.arg.at("_SINGLET_") == "true";
         if (c.id == "SPINDEC") o.spindec = c.arg.at("_SINGLET_") == "true";
         if (c.id == "FRAME") o.frame = frame_id(c.arg.at("_SINGLET_"));

@@ -23,6 +23,40 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Phase marks for the dynamic op count of this restatement (scripts/oracle_opcount.py builds an instrumented copy with
+ * -DGRB_OPCOUNT and counts executed fp64 operations per phase; SURVEY.md section 8d convention).  No-ops in the normal build. */
+enum { OPC_KIN = 0, OPC_SCAL_KIN, OPC_BORN, OPC_NODE_INV, OPC_NODE_KIN, OPC_NODE_SCAL, OPC_NODE_AMP, OPC_NODE_ACC, OPC_POST, OPC_NPHASE };
+#ifdef GRB_OPCOUNT
+int grb_opc_mark(int phase); /* returns the previous phase */
+#define OPC(k) grb_opc_mark(k)
+#else
+#define OPC(k) (0)
+#endif
+
+/* Conditioning probe (tests/fullsize.py): the result of the k-th libm call of a point can be moved by one ulp.  Two
+ * IEEE-754 platforms differ in exactly these results (glibc vs CUDA libm: <= 1-2 ulp; + - * / sqrt are correctly rounded
+ * on both), so max_k |W(k-th result +- 1 ulp) - W| / |W| is the point's conditioning with respect to everything a
+ * faithful implementation on another platform may legitimately compute differently.  Disabled (g_pert_call < 0) the
+ * wrappers return their argument unchanged: the restatement's results do not depend on them. */
+static int g_pert_call = -1, g_pert_sign = 1, g_call_idx = 0;
+void grb_oracle_perturb_call(int k, int sign) { g_pert_call = k; g_pert_sign = sign; }
+int  grb_oracle_calls_of_last_point(void) { return g_call_idx; }
+static inline double opert(double v) {
+  if (g_call_idx++ == g_pert_call) return nextafter(v, g_pert_sign > 0 ? INFINITY : -INFINITY);
+  return v;
+}
+#ifndef GRB_OPCOUNT /* (the op-counting build lets the compiler merge identical libm calls) */
+#define exp(x) opert(exp(x))
+#define log(x) opert(log(x))
+#define sin(x) opert(sin(x))
+#define cos(x) opert(cos(x))
+#define tan(x) opert(tan(x))
+#define sinh(x) opert(sinh(x))
+#define cosh(x) opert(cosh(x))
+#define atan2(y, x) opert(atan2(y, x))
+#define pow(x, y) opert(pow(x, y))
+#endif
+
 /* reference include/Graniitti/MMath.h:30 (long double literal rounded to double) */
 #define O_PI 3.141592653589793238462643383279502884197169399375105820974944
 /* reference include/Graniitti/MPDG.h:64-78 */
@@ -281,7 +315,19 @@ static int construct_decay(ost *S, int node) {
 }
 
 /* reference src/MProcess.cc:1499-1584 GetLorentzScalars */
+static int lorentz_scalars_impl(ost *S, int Nf);
 static int lorentz_scalars(ost *S, int Nf) {
+#ifdef GRB_OPCOUNT
+  const int prev = OPC(OPC_SCAL_KIN);
+  if (prev == OPC_NODE_KIN) OPC(OPC_NODE_SCAL);
+  const int ok = lorentz_scalars_impl(S, Nf);
+  OPC(prev);
+  return ok;
+#else
+  return lorentz_scalars_impl(S, Nf);
+#endif
+}
+static int lorentz_scalars_impl(ost *S, int Nf) {
   for (int i = 0; i <= Nf; ++i)
     for (int j = 0; j <= Nf; ++j) {
       if (i < j) S->ss[i][j] = v4_m2(v4_add(S->pfinal[i], S->pfinal[j]));
@@ -2009,8 +2055,15 @@ static double simpson38_w(int i, int N) {
 /* reference src/MProcess.cc:157-288 S3ScreenedAmp2 (non-gg initial states) */
 static double screened_amp2(ost *S) {
   const grb_process_desc *d = S->d;
-  if (!d->screening) return bare_amp2(S);
+  if (!d->screening) {
+    OPC(OPC_BORN);
+    const double a2 = bare_amp2(S);
+    OPC(OPC_KIN);
+    return a2;
+  }
+  OPC(OPC_BORN);
   bare_amp2(S);
+  OPC(OPC_KIN);
   if (S->nhamp == 0) return NAN;
   const int nh = S->nhamp;
   cx        hamp_0[GRB_MAX_HAMP];
@@ -2030,16 +2083,20 @@ static double screened_amp2(ost *S) {
   for (int i = 0; i < NPHI + 1; ++i) {
     const double phi = MinPhi + i * StepPhi;
     for (int j = 0; j < NKT + 1; ++j) {
+      OPC(OPC_NODE_INV); /* what depends on (i, j) only: hoisted to table-set time by any batched implementation */
       const double kt    = d->loop_min_kt + j * StepKT;
       const double kt2   = pow2(kt);
       const cx     A_eik = interpolate1d(S->eik, kt2);
       const double ktx = kt * cos(phi), kty = kt * sin(phi);
       const double Wij = simpson38_w(i, NPHI) * simpson38_w(j, NKT);
+      OPC(OPC_NODE_KIN);
       if (!(d->ps_class == GRB_CLASS_C ? loop_kinematics_C : loop_kinematics)(S, p1T[0] - ktx, p1T[1] - kty, p2T[0] + ktx, p2T[1] + kty)) {
         for (int h = 0; h < nh; ++h) { I[h].re += Wij * 0.0; I[h].im += Wij * 0.0; }
         continue;
       }
+      OPC(OPC_NODE_AMP);
       bare_amp2(S);
+      OPC(OPC_NODE_ACC);
       for (int h = 0; h < nh; ++h) {
         const cx f = cx_scale(cx_mul(A_eik, S->hamp[h]), kt);
         I[h].re += Wij * f.re; /* double * complex */
@@ -2047,6 +2104,7 @@ static double screened_amp2(ost *S) {
       }
     }
   }
+  OPC(OPC_POST);
   const double scale = 9 * (StepPhi * StepKT) / 64;
   /* norm = zi / (8 pi^2 s): complex / double */
   const cx norm = {0.0 / (8.0 * (O_PI * O_PI) * d->s), 1.0 / (8.0 * (O_PI * O_PI) * d->s)};
@@ -2057,6 +2115,7 @@ static double screened_amp2(ost *S) {
   for (int h = 0; h < nh; ++h) amp2 += cx_abs2(cx_add(hamp_0[h], hamp_loop[h]));
   if (nh != 1) amp2 /= 4;
   memcpy(S->hamp, hamp_0, sizeof(cx) * nh); /* for the dump: born amplitudes */
+  OPC(OPC_KIN);
   return amp2;
 }
 
@@ -2114,6 +2173,7 @@ static double bn_integral_volume(const ost *S) {
 static double event_weight(ost *S, const double *u, uint8_t *flags) {
   const grb_process_desc *d = S->d;
   double                  W = 0.0;
+  OPC(OPC_KIN);
   const int kin  = d->ps_class == GRB_CLASS_C ? bn_random_kin(S, u) : b51_random_kin(S, u);
   const int fid  = common_cuts(S);
   const int veto = veto_cuts(S);
@@ -2171,6 +2231,7 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
     S->tape_len     = tape ? dtape : 0;
     S->tape_pos     = 0;
     S->tape_overrun = 0;
+    g_call_idx      = 0;
     w[k]            = event_weight(S, u + k * dim, &flags[k]);
     if (tape_used) tape_used[k] = S->tape_overrun ? -S->tape_pos : S->tape_pos;
     if (dump) {

@@ -15,7 +15,7 @@
 // original in MRandom.o, including calls made from inside MRandom.o (RelativisticBWRandom).
 //
 // usage:
-//   ref_eval eval  <card.json> <process|null> <pomloop 0|1|-1(card)> <in.bin> <out.bin> [kappa 0|1]
+//   ref_eval eval  <card.json> <process|null> <pomloop 0|1|-1(card)> <in.bin> <out.bin> [kappa 0|1|2]
 //   ref_eval info  <card.json> <process|null> <pomloop>              (prints flattened process facts)
 //   ref_eval msa   <card.json> <process|null> <out.bin>              (dumps the MSA eikonal table)
 //
@@ -75,10 +75,10 @@ struct Rec {
 constexpr int RECLEN = sizeof(Rec) / sizeof(double);
 
 double eval_point(gra::MGraniitti &g, const double *row, int64_t du, int64_t dt, gra::AuxIntData &aux,
-                  const std::vector<double> *uoverride = nullptr) {
+                  const std::vector<double> *uoverride = nullptr, const std::vector<double> *tapeoverride = nullptr) {
   std::vector<double> u(row, row + du);
   if (uoverride) u = *uoverride;
-  g_tape     = row + du;
+  g_tape     = tapeoverride ? tapeoverride->data() : row + du;
   g_tape_len = dt;
   g_tape_pos = 0;
   aux        = gra::AuxIntData();
@@ -175,7 +175,8 @@ int main(int argc, char **argv) {
       fprintf(stderr, "bad arguments\n");
       return 2;
     }
-    const bool want_kappa = (argc >= 8) ? atoi(argv[7]) != 0 : false;
+    const int  kappa_mode = (argc >= 8) ? atoi(argv[7]) : 0;  // 1: perturb the coordinates, 2: and the consumed tape slots
+    const bool want_kappa = kappa_mode != 0;
     FILE *     fi         = fopen(argv[5], "rb");
     if (!fi) {
       perror("in.bin");
@@ -228,6 +229,30 @@ int main(int argc, char **argv) {
             gra::AuxIntData a2;
             const double    W2 = eval_point(g, row, du, dt, a2, &u);
             if (W2 != 0.0) kap = std::max(kap, std::abs(W2 - W) / std::abs(W));
+          }
+        }
+        // kappa mode 2: one step of the uniform grid (2^-53, what one ulp of 1.0 is -- a relative ulp of a small u is
+        // swallowed by the first affine map, e.g. y = Y_min + dY u) in every coordinate and in every internal uniform the
+        // point consumed (Breit-Wigner masses, decay angles)
+        if (kappa_mode >= 2) {
+          for (int64_t d = 0; d < du; ++d) {
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+              std::vector<double> u(row, row + du);
+              u[d] += sgn * 0x1.0p-53;
+              gra::AuxIntData a2;
+              const double    W2 = eval_point(g, row, du, dt, a2, &u);
+              if (W2 != 0.0) kap = std::max(kap, std::abs(W2 - W) / std::abs(W));
+            }
+          }
+          const int64_t used = std::min<int64_t>((int64_t)r.tape_used, dt);
+          for (int64_t d = 0; d < used; ++d) {
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+              std::vector<double> t(row + du, row + du + dt);
+              t[d] += sgn * 0x1.0p-53;
+              gra::AuxIntData a2;
+              const double    W2 = eval_point(g, row, du, dt, a2, nullptr, &t);
+              if (W2 != 0.0) kap = std::max(kap, std::abs(W2 - W) / std::abs(W));
+            }
           }
         }
         r.kappa = kap;

@@ -41,6 +41,9 @@ CASES = [
      "PP[CONTENSOR]<F> -> phi(1020)0 > {K+ K-} phi(1020)0 > {K+ K-}", 0, 1024, 24, True),
     ("c5_cms_rhorho_stable_tensor_born", "./tests/processes/CMSCUTS.json",
      "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 0, 1024, 8, True),
+    # @R[name]{...} on-the-flight resonance overrides: mass / width (decay coupling recomputed), spin density, coupling
+    ("c1_test_pipi_rescon_override_born", "./input/test.json",
+     "PP[RES+CON]<F> -> pi+ pi- @R[f0_980]{M:1.02,W:0.09} @R[f2_1270]{JZ0:0.2,JZ2:0.8,W:0.2}", 0, 1024, 8, True),
     # multi-helicity screening loops (16 and 36 amplitudes integrated separately)
     ("c4_cms_mumu_yycon_screened", "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 1, 256, 8, True),
     ("c5_cms_rhorho_stable_tensor_screened", "./tests/processes/CMSCUTS.json",

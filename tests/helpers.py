@@ -111,7 +111,7 @@ def ref_eval(card, proc, pomloop, u, tape, kappa=False):
             f.write(struct.pack("<qqq", n, du, dt))
             f.write(np.hstack([u, tape]).tobytes())
         r = subprocess.run([REF_BIN, "eval", card, proc or "null", str(int(pomloop)), fin, fout,
-                            "1" if kappa else "0"], cwd=REF_TREE, capture_output=True, text=True)
+                            str(int(kappa))], cwd=REF_TREE, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("ref_eval failed: " + r.stderr[-2000:])
         raw = open(fout, "rb").read()

@@ -105,3 +105,28 @@ def test_flattening_agrees_with_reference_objects(grb):
     assert float(info["beam_mass"][0]) == d.beam1_mass
     assert int(info["lipsdim"][0]) == d.lipsdim
     assert [int(info["loop"][1]), int(info["loop"][3])] == [d.loop_nkt, d.loop_nphi]
+
+
+def test_resonance_overrides_before_the_decay_coupling(grb):
+    """@R[name]{M, W, g<n>, JZ<n>}: applied to the freshly read resonance before the decay-side computation, so that
+    g_decay = sqrt(BR W / PS(M)) uses the overridden values (reference src/MGraniitti.cc:481-578, MProcess.cc:676-712).
+    Facts of the reference's own objects: tests/golden/res_override_ref.json (make_res_override_ref.py)."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "res_override_ref.json")))
+    d = grb.parse_card(os.path.join(CARDS, "c1_test13.json"), ref["process"], 0)
+    by_pdg = {d.res[i].pdg: d.res[i] for i in range(d.n_res)}
+    assert len(by_pdg) == len(ref["res"]) == 8
+    for name, r in ref["res"].items():
+        o = by_pdg[r["pdg"]]
+        assert o.mass == r["mass"] and o.width == r["width"] and o.BR == r["BR"], name
+        assert abs(o.g_decay - r["gdecay"]) <= 4e-16 * r["gdecay"], (name, o.g_decay, r["gdecay"])
+        n = o.spinX2 + 1
+        if o.spinX2:
+            for a in range(n):
+                for b in range(n):
+                    assert abs(o.rho_re[a * 5 + b] - r["rho_re"][a * n + b]) < 1e-16 and o.rho_im[a * 5 + b] == r["rho_im"][a * n + b], name
+    assert by_pdg[9010221].mass == 1.02 and by_pdg[225].width == 0.2 and by_pdg[113].g_Tensor[0] == 1.5
+    # target errors are the reference's
+    for bad in ("@R[nosuch]{M:1.0}", "@R[]{M:1.0}", "@R[f0_980,f2_1270]{M:1.0}"):
+        with pytest.raises(grb.GrbError):
+            grb.parse_card(os.path.join(CARDS, "c1_test13.json"), "PP[RES+CON]<F> -> pi+ pi- " + bad, 0)

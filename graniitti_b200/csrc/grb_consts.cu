@@ -12,6 +12,9 @@ namespace grb {
 __constant__ DevProc c_proc;
 __constant__ DevLoop c_loop;
 __constant__ DevRes  c_res;
+__constant__ FastConst c_fm = {-1.0 / 6.0, 1.0 / 5.0, 1.0 / 3.0, GRB_LN2,
+                               GRB_64_OVER_LN2, GRB_LN2_64_LO, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
+                               GRB_64_OVER_PI, GRB_PI_64_LO, -1.0 / 5040.0, -1.0 / 720.0};
 // lookup tables of grb_fastmath.cuh (global memory, read through the L1 / read-only path: indices diverge in a warp)
 __device__ const double2 g_logtab[128] = {GRB_LOGTAB_ROWS};
 __device__ const double  g_exptab[64]  = {GRB_EXPTAB_ROWS};

@@ -297,7 +297,9 @@ __device__ __forceinline__ PzInv make_pz_inv(double m3, double m4, const PzConst
   I.k_34 = I.m3sq * I.m4sq * 2.0;
   return I;
 }
-__device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+// key: running minimum of the square-root range keys (fast_key(), grb_fastmath.cuh), so that all range guards of a loop
+// node cost one integer min each and ONE compare at the end; dom: the division's guard
+__device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, unsigned &key, bool &dom) {
   const double t2 = E5 * E5, t3 = pt3 * pt3, t4 = pt4 * pt4, t5 = pz5 * pz5;  // t6 = m3^2 rides in I.m3sq_x2, I.k_s3
   const double E4 = 4.0 * E5, t2x2 = 2.0 * t2, t5x2 = 2.0 * t5, t6x4 = 2.0 * I.m3sq_x2;
   const double t8  = I.s * t2 * 6.0;
@@ -310,16 +312,18 @@ __device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, d
                      E4 * I.s15 - I.s_x2 * t3 - I.s_x2 * t4 - I.s_x2 * t5 - I.k_s3 -
                      t2x2 * t3 - t2x2 * t4 - t2x2 * t5 - t3 * t4 * 2.0 - t2 * t6x4 -
                      E4 * t2 * I.rs;
-  dom = dom && sqrt_fast_ok(t22);
+  key = min(key, fast_key(t22));
   const double t23h = 0.5 * sqrt_fast_core(t22);
   const double pz5h = 0.5 * pz5;
   const double num = E5 * t23h - I.rs * t23h + pz5h * (t3 - t4);
   const double den = I.s + t2 - t5 - E5 * I.rs_x2;
   const double q   = div_fast_core(num, den);
-  dom = dom && div_fast_ok(num, q);
+  dom = dom & div_fast_ok(num, q);
   return -pz5h - q;
 }
-__device__ __forceinline__ double solve_pz3_B_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+// key: running minimum of the square-root range keys (fast_key(), grb_fastmath.cuh), so that all range guards of a loop
+// node cost one integer min each and ONE compare at the end; dom: the division's guard
+__device__ __forceinline__ double solve_pz3_B_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, unsigned &key, bool &dom) {
   const double t2 = E5 * E5, t3 = I.m3sq, t4 = I.m4sq, t5 = pt3 * pt3, t6 = pt4 * pt4, t7 = pz5 * pz5;
   const double E4 = 4.0 * E5, t2x2 = 2.0 * t2, t7x2 = 2.0 * t7;
   const double t9  = I.s * t2 * 6.0;
@@ -332,14 +336,27 @@ __device__ __forceinline__ double solve_pz3_B_fast(const PzInv &I, double pt3, d
                      I.s_x2 * t5 - I.s_x2 * t6 - I.s_x2 * t7 - t2 * I.m3sq_x2 - t2 * I.m4sq_x2 -
                      t2x2 * t5 - I.k_34 - t2x2 * t6 - t2x2 * t7 - I.m3sq_x2 * t6 -
                      I.m4sq_x2 * t5 - t5 * t6 * 2.0 - E4 * t2 * I.rs;
-  dom = dom && sqrt_fast_ok(t29);
+  key = min(key, fast_key(t29));
   const double t30h = 0.5 * sqrt_fast_core(t29);
   const double pz5h = 0.5 * pz5;
   const double num = E5 * t30h - I.rs * t30h + pz5h * (t3 - t4 + t5 - t6);
   const double den = I.s + t2 - t7 - E5 * I.rs_x2;
   const double q   = div_fast_core(num, den);
-  dom = dom && div_fast_ok(num, q);
+  dom = dom & div_fast_ok(num, q);
   return -pz5h - q;
+}
+
+__device__ __forceinline__ double solve_pz3_A_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+  unsigned key = 0xffffffffu;
+  const double r = solve_pz3_A_fast(I, pt3, pt4, pz5, E5, key, dom);
+  dom = dom && fast_key_ok(key);
+  return r;
+}
+__device__ __forceinline__ double solve_pz3_B_fast(const PzInv &I, double pt3, double pt4, double pz5, double E5, bool &dom) {
+  unsigned key = 0xffffffffu;
+  const double r = solve_pz3_B_fast(I, pt3, pt4, pz5, E5, key, dom);
+  dom = dom && fast_key_ok(key);
+  return r;
 }
 
 __device__ __forceinline__ double solve_pz(double m3, double m4, double pt3, double pt4, double pz5,

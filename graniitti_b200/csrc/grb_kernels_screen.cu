@@ -172,7 +172,7 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
   // tuning knob for profiling runs; the default is the measured best (profiles/)
   static const int minb = [] { const char *e = getenv("GRB_SCREEN_MINB"); return e ? atoi(e) : 4; }();
   if (amp_kind == AMP_TENSOR_2XS) {
-    static const bool nofast_t = getenv("GRB_SCREEN_NOFAST") != nullptr;
+    const bool nofast_t = getenv("GRB_SCREEN_NOFAST") != nullptr;
     if (regge_ff >= 0 && !nofast_t) launch_screen_t<4, AMP_TENSOR_2XS, 0>(a, sm_count, st);  // one-basic-block node (<F> class)
     else launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
     return 2;
@@ -205,7 +205,7 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
     launch_screen_t<2, AMP_REGGE_RES_CON>(a, sm_count, st);
     return 2;
   }
-  static const bool nofast = getenv("GRB_SCREEN_NOFAST") != nullptr;  // profiling knob: the checked node everywhere
+  const bool nofast = getenv("GRB_SCREEN_NOFAST") != nullptr;  // profiling / test knob (read per launch): the checked node everywhere
   if (!nofast && minb == 4) {
     if (regge_ff == 0) { launch_screen_t<4, AMP_REGGE, 0>(a, sm_count, st); return 2; }
     if (regge_ff == 1) { launch_screen_t<4, AMP_REGGE, 1>(a, sm_count, st); return 2; }

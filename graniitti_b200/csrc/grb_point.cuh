@@ -1148,34 +1148,48 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
   // msqrt's clamp max(0, .) is dropped on this path: every radicand is a sum of squares (>= 0, or NaN -- and a NaN
   // fails the range guard, which sends the node to the checked path)
   const double a1s = n1x * n1x + n1y * n1y, a2s = n2x * n2x + n2y * n2y, aXs = L.mXsq + (Xx * Xx + Xy * Xy);
-  bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(aXs));
+  // Range guards: every MUFU-seeded square root (and every table-driven log) needs a normal positive argument >= 2^-970;
+  // their keys (fast_key) are min-combined and tested ONCE at the end, the other guards are and-combined without
+  // short-circuit evaluation: no branch, no convergence barrier.  A failed guard sends the node to the checked path
+  // whether or not the node is still valid at that point (identical result either way; guards fail on a handful of nodes
+  // per million, essentially only where the kinematics has no solution).
+  unsigned     key = min(min(fast_key(a1s), fast_key(a2s)), fast_key(aXs));
   const double pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s), mtX = sqrt_fast_core(aXs);
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   valid = !(Xe > L.emax);
   bool         dom = true;
-  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, dom);
-  redo = redo || (valid && !dom);
+  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, key, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, key, dom);
   const double p2z = -(Xz + p1z);
-  valid = valid && !(isnan(p1z) || p1z < 0 || p2z > 0);
+  valid = valid & !(isnan(p1z) | (p1z < 0) | (p2z > 0));
   const double e1s = L.m1sq + pow2(pt1) + pow2(p1z), e2s = L.m2sq + pow2(pt2) + pow2(p2z);
-  redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
+  key = min(key, min(fast_key(e1s), fast_key(e2s)));
   const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
-  valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
+  valid = valid & !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
   // (Measured and not taken: the sub-energies through dot products, (a + b)^2 = m_a^2 + m_b^2 + 2 a.b -- 2.4 % faster, but
   // the reference's (E1 + E3)^2 - |p1 + p3|^2 carries ~4e-13 of relative rounding noise that such a form does not
   // reproduce: screened weights moved from a median 4e-15 to 7e-13 against the reference.)
+  //
+  // M4Vec::M2 is e^2 - ((x^2 + y^2) + z^2).  The transverse parts are shared bit for bit between the scalars:
+  //   t1:  q1 = p_beam1 - p1 has q1x = 0 - n1x, so q1x^2 + q1y^2 = n1x^2 + n1y^2 = a1s (negation is exact); t2 likewise;
+  //   t^:  (q1x - p3x) = -(n1x + p3x) exactly, so its transverse part is the one of ss13 = (p1 + p3)^2; u^ <-> ss14.
+  // Same products, same sums, same order: identical bits, 20 fp64 instructions fewer per node.
   const v4 &p3 = L.p3, &p4 = L.p4;
-  const double ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
-  const double ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
-  const double ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
-  const double ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
-  valid = valid && !(ss13 < 0 || ss14 < 0 || ss23 < 0 || ss24 < 0);
-  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
-  const double t1 = m2_of(q1x, q1y, q1z, q1e);
-  const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
-  valid = valid && !(t1 > 0 || t2 > 0);
-  const double t_hat = m2_of(q1x - p3.x, q1y - p3.y, q1z - p3.z, q1e - p3.e);
-  const double u_hat = m2_of(q1x - p4.x, q1y - p4.y, q1z - p4.z, q1e - p4.e);
+  const double x13 = n1x + p3.x, y13 = n1y + p3.y, x14 = n1x + p4.x, y14 = n1y + p4.y;
+  const double x23 = n2x + p3.x, y23 = n2y + p3.y, x24 = n2x + p4.x, y24 = n2y + p4.y;
+  const double T13 = x13 * x13 + y13 * y13, T14 = x14 * x14 + y14 * y14, T23 = x23 * x23 + y23 * y23, T24 = x24 * x24 + y24 * y24;
+  const double ss13 = pow2(e1 + p3.e) - (T13 + pow2(p1z + p3.z));
+  const double ss14 = pow2(e1 + p4.e) - (T14 + pow2(p1z + p4.z));
+  const double ss23 = pow2(e2 + p3.e) - (T23 + pow2(p2z + p3.z));
+  const double ss24 = pow2(e2 + p4.e) - (T24 + pow2(p2z + p4.z));
+  // ss < 0 for any of the four <=> a sign bit is set (a difference of equal numbers is +0, never -0): one integer test
+  valid = valid & ((__double2hiint(ss13) | __double2hiint(ss14) | __double2hiint(ss23) | __double2hiint(ss24)) >= 0);
+  const double q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  const double t1 = pow2(q1e) - (a1s + pow2(q1z));
+  const double t2 = pow2(P.pb2e - e2) - (a2s + pow2(P.pb2z - p2z));
+  valid = valid & !(t1 > 0);
+  valid = valid & !(t2 > 0);
+  const double t_hat = pow2(q1e - p3.e) - (T13 + pow2(q1z - p3.z));
+  const double u_hat = pow2(q1e - p4.e) - (T14 + pow2(q1z - p4.z));
   // amplitude: regge_me4(), single-trajectory branch
   const double dF = (fma(-t1, P.inv_fc1, 1.0) * fma(-t1, P.inv_fc2, 1.0)) * (fma(-t2, P.inv_fc1, 1.0) * fma(-t2, P.inv_fc2, 1.0));
   double       dt = t_hat - P.M2_leg0, du = u_hat - P.M2_leg0;
@@ -1192,7 +1206,7 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
     dt *= d1 * d1;
     du *= d2 * d2;
   }
-  redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
+  key = min(min(key, fast_key(ss13)), min(min(fast_key(ss24), fast_key(ss14)), fast_key(ss23)));
   const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
   const double c0 = S0ONE ? 0.0 : P.ln_inv_s0;
   const double xt = S0ONE ? fma(al1, L13, fma(al2, L24, gt)) : fma(al1, L13 + c0, fma(al2, L24 + c0, gt));
@@ -1201,7 +1215,7 @@ __device__ __forceinline__ bool regge_node_fast(const LoopInv &L, const PzInv &p
   const double num = P.g2_const * fma(Et, du, P.me4_sign * Eu * dt), den = dt * du * dF;
   const double R   = div_fast_core(num, den);
   const double ph  = P.phase_c[0] * (t1 + t2);
-  redo = redo || (valid && !(fabs(xt) < 690.0 && fabs(xu) < 690.0 && div_fast_ok(num, R) && fabs(ph) < 1.0e5));
+  const bool redo = !(fast_key_ok(key) & dom & (fabs(xt) < 690.0) & (fabs(xu) < 690.0) & div_fast_ok(num, R) & (fabs(ph) < 1.0e5));
   double sn, cs;
   fast_sincos_core(ph, sn, cs);
   A.re = fma(P.eta0sq_re, cs, -P.eta0sq_im * sn) * R;

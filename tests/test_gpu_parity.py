@@ -378,3 +378,22 @@ def test_two_engines_share_a_device(grb, msa):
         assert abs(a.fsum - ra.fsum) <= 1e-12 * ra.fsum and a.n_fid_ok == ra.n_fid_ok
         assert abs(b.fsum - rb.fsum) <= 1e-12 * rb.fsum and b.n_fid_ok == rb.n_fid_ok
     Ea.close(); Eb.close()
+
+
+@pytest.mark.parametrize("proc", ["PP[CON]<F> -> pi+ pi-", "PP[CONTENSOR]<F> -> pi+ pi-", "PP[CON]<C> -> pi+ pi-"])
+def test_fast_node_equals_checked_node(grb, msa, proc, monkeypatch):
+    """The one-basic-block loop nodes evaluate the same expressions in the same order as the checked path (loop_node +
+    amplitude with per-call guards and libm fallbacks): screened weights must agree bit for bit."""
+    u, tape = make_points(60000, 8 if "<C>" in proc else 6, 8, 77, adapted=True)
+    E = engine_for(grb, msa, "c2_alice.json", proc, 1)
+    w1, f1, _ = E.eval(u.T.copy(), tape.T.copy())
+    monkeypatch.setenv("GRB_SCREEN_NOFAST", "1")
+    w2, f2, _ = E.eval(u.T.copy(), tape.T.copy())
+    monkeypatch.delenv("GRB_SCREEN_NOFAST")
+    assert (w1 != 0).sum() > 10000 and np.array_equal(f1, f2)
+    if "TENSOR" in proc:   # the tensor node multiplies all quotients up into one division: not bitwise, 1e-14
+        nz = w2 != 0
+        assert np.max(np.abs(w1[nz] - w2[nz]) / np.abs(w2[nz])) < 1e-13
+    else:
+        assert np.array_equal(w1, w2)
+    E.close()

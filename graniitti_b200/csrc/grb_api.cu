@@ -37,6 +37,14 @@ struct grb_engine {
   int32_t *     d_item_idx = nullptr;
   uint64_t *    d_item_bins = nullptr, *d_item_bins_hi = nullptr;
   unsigned int *d_item_count = nullptr;
+  // second work list + side stream: k_points of chunk c+1 runs beside k_screen of chunk c (grb_vegas_iterate_async)
+  double *      d_items2 = nullptr;
+  int32_t *     d_item_idx2 = nullptr;
+  uint64_t *    d_item_bins2 = nullptr, *d_item_bins_hi2 = nullptr;
+  unsigned int *d_item_count2 = nullptr;
+  cudaStream_t  stream_pts = nullptr;
+  cudaEvent_t   ev_pts[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
+  int           overlap = 0;   // GRB_OVERLAP: 0 off, n > 0: on, k_screen with n CTAs per SM
   // event generation buffers (allocated on first GRB_MODE_GENERATE call)
   double *      d_ev = nullptr, *d_pay = nullptr;
   unsigned int *d_ev_count = nullptr;
@@ -455,6 +463,11 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
   cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming);
   const char *env = getenv("GRB_CHUNK");
   e->chunk        = env ? std::max<int64_t>(1024, atoll(env)) : (int64_t)1 << 23;
+  // k_points / k_screen overlap: GRB_OVERLAP = CTAs per SM left to k_screen; default off -- measured on B200 (profiles/
+  // r02_overlap_sweep.txt): k_screen needs all 16 warps per SM (29.3 instead of 26.7 ms per launch at 3 CTAs per SM), which
+  // costs more than the 2 ms of k_points the overlap hides
+  const char *ov  = getenv("GRB_OVERLAP");
+  e->overlap      = ov ? std::max(0, atoi(ov)) : 0;
   const char *hs  = getenv("GRB_HOST_SLICE");  // points per pipeline slice of grb_eval with host buffers
   e->host_slice   = hs ? std::max<int64_t>(1024, atoll(hs)) : (int64_t)1 << 20;
   if (desc->screening) {
@@ -503,6 +516,10 @@ void grb_destroy(grb_engine *e) {
     if (c.owner == e) c.owner = nullptr;
   }
   cudaFree(e->d_items); cudaFree(e->d_item_idx); cudaFree(e->d_item_bins); cudaFree(e->d_item_bins_hi); cudaFree(e->d_item_count);
+  cudaFree(e->d_items2); cudaFree(e->d_item_idx2); cudaFree(e->d_item_bins2); cudaFree(e->d_item_bins_hi2); cudaFree(e->d_item_count2);
+  for (int k = 0; k < 2; ++k) { if (e->ev_pts[k]) cudaEventDestroy(e->ev_pts[k]); if (e->ev_free[k]) cudaEventDestroy(e->ev_free[k]); }
+  if (e->ev_start) cudaEventDestroy(e->ev_start);
+  if (e->stream_pts) cudaStreamDestroy(e->stream_pts);
   cudaFree(e->d_acc); cudaFree(e->d_xmat); cudaFree(e->d_scratch); cudaFree(e->d_max2);
   cudaFree(e->d_ev); cudaFree(e->d_pay); cudaFree(e->d_ev_count);
   if (e->nccl_comm && nccl().ok) nccl().CommDestroy(e->nccl_comm);
@@ -719,7 +736,29 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
   e->last_launches = 0;
   e->n_evk = 0;
   CK(cudaEventRecord(e->ev0, e->stream));
-  for (int64_t off = 0; off < ncalls; off += e->chunk) {
+  // Optional (GRB_OVERLAP=n): k_points of chunk c+1 on a side stream beside k_screen of chunk c (two work lists), k_screen
+  // keeping n of its 4 resident CTAs per SM and k_points one 128-thread CTA per SM in the freed part of the register file.
+  const bool overlap = e->overlap > 0 && e->desc.screening && mode != GRB_MODE_GENERATE && ncalls > e->chunk;
+  if (overlap && !e->d_items2) {
+    CK(cudaMalloc(&e->d_items2, sizeof(double) * ITEM_NF * e->chunk));
+    CK(cudaMalloc(&e->d_item_idx2, sizeof(int32_t) * e->chunk));
+    CK(cudaMalloc(&e->d_item_bins2, sizeof(uint64_t) * e->chunk));
+    if (e->desc.lipsdim > 8) CK(cudaMalloc(&e->d_item_bins_hi2, sizeof(uint64_t) * e->chunk));
+    CK(cudaMalloc(&e->d_item_count2, sizeof(unsigned int) * 4));
+    CK(cudaStreamCreateWithFlags(&e->stream_pts, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaEventCreateWithFlags(&e->ev_pts[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->ev_free[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
+  }
+  if (overlap) {  // the side stream starts after the constants, the grid and the cleared accumulators are in place
+    CK(cudaEventRecord(e->ev_start, e->stream));
+    CK(cudaStreamWaitEvent(e->stream_pts, e->ev_start, 0));
+  }
+  int64_t chunk_no = 0;
+  for (int64_t off = 0; off < ncalls; off += e->chunk, ++chunk_no) {
+    const int b = overlap ? (int)(chunk_no & 1) : 0;
     PointArgs a;
     memset(&a, 0, sizeof(a));
     a.n = std::min<int64_t>(e->chunk, ncalls - off);
@@ -727,14 +766,26 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     a.vegas = 1; a.bins = bins; a.mode = mode; a.xmat = e->d_xmat; a.seed = seed; a.iter = (uint32_t)iteration;
     a.first_call = first_call + off; a.maxf = maxf;
     a.ev_out = e->d_ev; a.ev_count = e->d_ev_count; a.ev_cap = e->ev_cap; a.npart = npart; a.pay = e->d_pay;
-    a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count;
+    if (b == 0) { a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count; }
+    else { a.items = e->d_items2; a.item_idx = e->d_item_idx2; a.item_bins = e->d_item_bins2; a.item_bins_hi = e->d_item_bins_hi2; a.item_count = e->d_item_count2; }
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
-    e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
+    cudaStream_t sp = overlap ? e->stream_pts : e->stream;
+    if (overlap) {
+      a.side_launch = chunk_no > 0;          // the first chunk has the device to itself
+      a.screen_ctas = e->overlap;
+      if (chunk_no >= 2) CK(cudaStreamWaitEvent(sp, e->ev_free[b], 0));   // k_finish of chunk c-2 has released this list
+    }
+    if (e->desc.screening) CK(cudaMemsetAsync(a.item_count, 0, 4 * sizeof(unsigned int), sp));
+    e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, sp);
+    if (overlap) {
+      CK(cudaEventRecord(e->ev_pts[b], sp));
+      CK(cudaStreamWaitEvent(e->stream, e->ev_pts[b], 0));
+    }
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
       e->last_launches += launch_screen(a, e->dproc.amp_kind, regge_fast_ff(e->dproc), e->sm_count, e->stream);
       CK(cudaEventRecord(next_event(e), e->stream));
+      if (overlap) CK(cudaEventRecord(e->ev_free[b], e->stream));
     }
   }
   CK(cudaEventRecord(e->ev1, e->stream));

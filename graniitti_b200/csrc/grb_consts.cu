@@ -38,6 +38,7 @@ int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, c
   int64_t       blocks  = (a.n + threads - 1) / threads;
   const int64_t cap     = (int64_t)sm_count * 8;
   if (blocks > cap) blocks = cap;
+  if (a.side_launch) blocks = sm_count;
   if (blocks < 1) blocks = 1;
   const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
   switch (amp_kind) {

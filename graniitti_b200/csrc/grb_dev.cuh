@@ -146,6 +146,9 @@ struct PointArgs {
   int64_t       ev_cap;
   int           npart;       // 3 + n_nodes
   double *      pay;         // screened generation: per work-list slot payload [npart*4][item_cap]
+  // launch shaping for the k_points / k_screen overlap (grb_api.cu): k_points beside a running k_screen takes one
+  // 128-thread CTA per SM; k_screen then leaves a quarter of the register file free (3 of its 4 resident CTAs per SM)
+  int side_launch, screen_ctas;
 };
 
 // launchers implemented in grb_kernels.cu

@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
 
 template <int NN, int AMP>
 inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
-  const int th = kp_threads(AMP);
-  if (th != threads) blocks = blocks * (unsigned)(threads / th);   // same number of resident threads
+  int th = kp_threads(AMP);
+  if (a.side_launch) th = 128;                                       // (blocks = one CTA per SM, set by the caller)
+  else if (th != threads) blocks = blocks * (unsigned)(threads / th);   // same number of resident threads
   if (a.vegas) k_points<NN, true, AMP><<<blocks, th, smem, st>>>(a);
   else k_points<NN, false, AMP><<<blocks, th, 0, st>>>(a);
 }

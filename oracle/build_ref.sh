@@ -59,6 +59,14 @@ g++ $CXXF -c "$HERE/ref_harness/ref_eval.cc" -o "$OUT/obj_h/ref_eval.o"
 OBJS=$(ls "$OUT"/obj/*.o | grep -v -e '/gr.o$' -e '/MRandom.o$')
 g++ "$OUT/obj_h/ref_eval.o" $OBJS "$OUT/obj_h/MRandom_weakU.o" -o "$OUT/gra/bin/ref_eval" -L"$OUT" -lLHAPDF -pthread -lrt
 
+# ---- 4b. INTEGRATION.md route A, compiled: the reference's steering + the product's C ABI (needs graniitti_b200/libgrb.so) --
+LIBGRB="$HERE/../graniitti_b200/libgrb.so"
+if [ -f "$LIBGRB" ]; then
+  g++ $CXXF -I"$HERE/../include" -c "$HERE/ref_harness/gr_b200.cc" -o "$OUT/obj_h/gr_b200.o"
+  g++ "$OUT/obj_h/gr_b200.o" $OBJS "$OUT/obj/MRandom.o" -o "$OUT/gra/bin/gr_b200" -L"$OUT" -lLHAPDF -pthread -lrt \
+      "$LIBGRB" -Wl,-rpath,'$ORIGIN/../../../../graniitti_b200'
+fi
+
 # ---- 5. run tree (the program resolves data relative to <binary>/../ ; reference tree is read-only) ----
 cd "$OUT/gra"
 mkdir -p eikonal output sudakov figs

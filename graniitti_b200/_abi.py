@@ -117,3 +117,22 @@ REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 class XscanRow(C.Structure):
     _fields_ = [(k, f64) for k in ("sqrt_s", "xs_tot_mb", "xs_el_mb", "xs_inel_mb", "sigma", "sigma_err", "chi2",
                                    "evaluations", "seconds")]
+
+
+class RecParticle(C.Structure):
+    _fields_ = [("id", i32), ("pid", i32), ("status", i32), ("parent", i32)] + [(k, f64) for k in ("px", "py", "pz", "e", "m")]
+
+
+class RecVertex(C.Structure):
+    _fields_ = [("id", i32), ("status", i32), ("n_in", i32), ("n_out", i32), ("in_", i32 * 4)] + [(k, f64) for k in ("x", "y", "z", "t")]
+
+
+GRB_MAX_REC_PARTICLES = 7 + GRB_MAX_NODES
+GRB_MAX_REC_VERTICES = 4 + GRB_MAX_NODES
+
+
+class WriterOpts(C.Structure):
+    _fields_ = [("format", C.c_char_p), ("generator_name", C.c_char_p), ("generator_version", C.c_char_p), ("card_path", C.c_char_p),
+                ("sigma_pb", f64), ("sigma_err_pb", f64), ("beam1_pdg", i32), ("beam2_pdg", i32), ("weighted", i32), ("nthreads", i32),
+                ("append", i32), ("close_listing", i32), ("number_events", i32), ("lifetimes", i32), ("first_event", C.c_int64),
+                ("lifetime_seed", C.c_uint64)]

@@ -898,6 +898,22 @@ int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, doubl
   return n;
 }
 
+int64_t grb_write_engine_events(grb_engine *e, const char *path, const grb_writer_opts *opts) {
+  if (!e || !path || !opts) return GRB_ERR_ARG;
+  const int npart = 3 + e->desc.n_nodes;
+  if (!e->d_ev) return 0;
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) return GRB_ERR_CUDA;
+  unsigned int c[2] = {0, 0};
+  if (cudaMemcpy(c, e->d_ev_count, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return GRB_ERR_CUDA;
+  const int64_t n = std::min<int64_t>((int64_t)c[0], e->ev_cap);
+  if (n == 0) return grb_write_events(&e->desc, path, opts, 0, nullptr, nullptr);
+  std::vector<double> mom((size_t)4 * npart * n), wts((size_t)2 * n);
+  int np = 0;
+  const int64_t got = grb_get_events(e, n, mom.data(), wts.data(), &np);
+  if (got < 0) return got;
+  return grb_write_events(&e->desc, path, opts, got, mom.data(), wts.data());
+}
+
 int64_t grb_events_dropped(const grb_engine *e) { return e ? e->ev_dropped : GRB_ERR_ARG; }
 
 int grb_loop_nodes(const grb_engine *e, int *nkt_nodes, int *nphi_nodes) {

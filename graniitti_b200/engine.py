@@ -66,6 +66,13 @@ def lib():
         L.grb_loop_nodes.argtypes = [vp, C.POINTER(cint), C.POINTER(cint)]
         L.grb_events_dropped.restype = i64
         L.grb_events_dropped.argtypes = [vp]
+        L.grb_event_record.restype = cint
+        L.grb_event_record.argtypes = [C.POINTER(_abi.ProcessDesc), vp, cint, cint, vp, C.POINTER(_abi.RecParticle), C.POINTER(cint),
+                                       C.POINTER(_abi.RecVertex), C.POINTER(cint)]
+        L.grb_write_events.restype = i64
+        L.grb_write_events.argtypes = [C.POINTER(_abi.ProcessDesc), C.c_char_p, C.POINTER(_abi.WriterOpts), i64, vp, vp]
+        L.grb_write_engine_events.restype = i64
+        L.grb_write_engine_events.argtypes = [vp, C.c_char_p, C.POINTER(_abi.WriterOpts)]
         L.grb_vegas_iterate.restype = cint
         L.grb_vegas_iterate.argtypes = [vp, vp, cint, cint, i64, i64, u64, u64, cint, dbl, C.POINTER(_abi.Accum)]
         L.grb_vegas_iterate_async.restype = cint
@@ -191,6 +198,41 @@ def comm_unique_id():
     return buf.raw
 
 
+def event_record(desc, momenta, beam_pdg=(2212, 2212), lifetime_u=None):
+    """The reference's event record (MProcess::CommonRecord) of one event from momenta [3 + n_nodes][4]: (particles, vertices)
+    as lists of dicts."""
+    mom = np.ascontiguousarray(momenta, dtype=np.float64)
+    P = (_abi.RecParticle * _abi.GRB_MAX_REC_PARTICLES)()
+    V = (_abi.RecVertex * _abi.GRB_MAX_REC_VERTICES)()
+    n_p, n_v = C.c_int(0), C.c_int(0)
+    lu = np.ascontiguousarray(lifetime_u, dtype=np.float64) if lifetime_u is not None else None
+    rc = lib().grb_event_record(C.byref(desc), mom.ctypes.data, beam_pdg[0], beam_pdg[1], lu.ctypes.data if lu is not None else None,
+                                P, C.byref(n_p), V, C.byref(n_v))
+    if rc != 0:
+        raise GrbError(rc, "grb_event_record")
+    parts = [dict(id=p.id, pid=p.pid, status=p.status, parent=p.parent, p=(p.px, p.py, p.pz, p.e), m=p.m) for p in P[:n_p.value]]
+    verts = [dict(id=v.id, n_in=v.n_in, n_out=v.n_out, inc=list(v.in_[:v.n_in]), pos=(v.x, v.y, v.z, v.t)) for v in V[:n_v.value]]
+    return parts, verts
+
+
+def writer_opts(fmt="hepmc3", sigma_pb=0.0, sigma_err_pb=0.0, weighted=False, nthreads=0, append=False, close_listing=True,
+                card_path="", lifetimes=False, number_events=False, first_event=0):
+    return _abi.WriterOpts(fmt.encode(), None, None, card_path.encode(), sigma_pb, sigma_err_pb, 0, 0, int(weighted), nthreads,
+                           int(append), int(close_listing), int(number_events), int(lifetimes), first_event, 12345)
+
+
+def write_events(desc, path, momenta, weights=None, **kw):
+    """n events as SoA momenta [3 + n_nodes][4][n] (+ weights [2][n]) -> file in the reference's output format."""
+    mom = np.ascontiguousarray(momenta, dtype=np.float64)
+    n = mom.shape[2]
+    w = np.ascontiguousarray(weights, dtype=np.float64) if weights is not None else None
+    o = writer_opts(**kw)
+    rc = lib().grb_write_events(C.byref(desc), str(path).encode(), C.byref(o), n, mom.ctypes.data, w.ctypes.data if w is not None else None)
+    if rc < 0:
+        raise GrbError(int(rc), "grb_write_events")
+    return int(rc)
+
+
 def measure_dfma_peak(device=0):
     v = C.c_double(0)
     rc = lib().grb_measure_dfma_peak(device, C.byref(v))
@@ -279,6 +321,14 @@ class Engine:
         a, b = C.c_int(0), C.c_int(0)
         self._check(lib().grb_loop_nodes(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def write_events(self, path, **kw):
+        """The events of the last GENERATE iteration -> file (hepmc3 | hepmc2 | hepevt)."""
+        o = writer_opts(**kw)
+        rc = lib().grb_write_engine_events(self._h, str(path).encode(), C.byref(o))
+        if rc < 0:
+            self._check(int(rc))
+        return int(rc)
 
     def events_dropped(self):
         return int(lib().grb_events_dropped(self._h))

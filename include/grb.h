@@ -325,6 +325,59 @@ int64_t grb_get_events(grb_engine *e, int64_t max_events, double *momenta, doubl
  * events, default 2^22): grb_accum.n_accepted counts every accepted event, grb_get_events returns at most the capacity. */
 int64_t grb_events_dropped(const grb_engine *e);
 
+/* ---- event record + writer ------------------------------------------------------------------ */
+
+/* One particle / vertex of the event record the reference builds in MProcess::CommonRecord (src/MProcess.cc:1588-1706):
+ * ids count from 1 in the order HepMC3::GenEvent assigns them (beam 1, outgoing proton 1, propagator 1, beam 2, outgoing
+ * proton 2, propagator 2, central system, then the decay tree depth first); vertex ids count down from -1.
+ * parent: 0 for the beams, else the (negative) id of the production vertex.                                        */
+typedef struct {
+  int32_t id, pid, status, parent;
+  double  px, py, pz, e, m;
+} grb_rec_particle;
+typedef struct {
+  int32_t id, status, n_in, n_out;
+  int32_t in[4];       /* ids of the incoming particles                                                                */
+  double  x, y, z, t;  /* position [mm]: decay vertices of particles with a width (exponential lifetime), else 0        */
+} grb_rec_vertex;
+#define GRB_MAX_REC_PARTICLES (7 + GRB_MAX_NODES)
+#define GRB_MAX_REC_VERTICES (4 + GRB_MAX_NODES)
+
+/* The record of ONE event from its momenta [3 + n_nodes][4] = (px, py, pz, E) of the central system, the two outgoing
+ * forward systems and every decay-tree node in grb_process_desc.nodes order (the layout of grb_get_events, transposed).
+ * beam pdg 0 = 2212.  lifetime_u: one uniform per node for the decay-vertex positions, or NULL (all vertices at 0).
+ * Status codes and ids: PDG_BEAM 4, PDG_STABLE 1, PDG_DECAY 2, PDG_INTERMEDIATE 81; propagators 99, system 90, excited
+ * forward system 90210 (include/Graniitti/MPDG.h:41-50).  Host-only.                                                */
+int grb_event_record(const grb_process_desc *d, const double *momenta, int beam1_pdg, int beam2_pdg,
+                     const double *lifetime_u, grb_rec_particle *particles, int *n_particles,
+                     grb_rec_vertex *vertices, int *n_vertices);
+
+typedef struct {
+  const char *format;            /* "hepmc3" | "hepmc2" | "hepevt" (OUTPUT FORMAT of the steering card)                 */
+  const char *generator_name;    /* run header tools (src/MGraniitti.cc:190-200); NULL = "GRANIITTI (TUNE0)"           */
+  const char *generator_version; /* NULL = "1.051"                                                                      */
+  const char *card_path;
+  double      sigma_pb, sigma_err_pb; /* per-event GenCrossSection in picobarn (SaveEvent: stat.sigma * 1e12)          */
+  int32_t     beam1_pdg, beam2_pdg;   /* 0 = 2212                                                                       */
+  int32_t     weighted;          /* WEIGHTED: event weight = W, else 1                                                  */
+  int32_t     nthreads;          /* formatting threads, 0 = all host cores                                              */
+  int32_t     append;            /* append to an existing listing (no run header)                                       */
+  int32_t     close_listing;     /* write the END_EVENT_LISTING footer                                                  */
+  int32_t     number_events;     /* 0: event number 0 like the reference (it never sets one); 1: first_event + i       */
+  int32_t     lifetimes;         /* 1: decay-vertex positions from exponential lifetimes (counter-based draws)          */
+  int64_t     first_event;
+  uint64_t    lifetime_seed;
+} grb_writer_opts;
+
+/* Record construction on several host threads + one ordered writer for n events given as SoA momenta [3 + n_nodes][4][n]
+ * and weights [2][n] = (W, f) (the layout of grb_get_events); replaces the per-event CommonRecord + write_event under the
+ * global mutex of MGraniitti::SaveEvent (src/MGraniitti.cc:1651-1726).  Returns the number of events written.  Host-only. */
+int64_t grb_write_events(const grb_process_desc *d, const char *path, const grb_writer_opts *opts, int64_t n,
+                         const double *momenta, const double *weights);
+
+/* The same for the events accepted by the engine's last GRB_MODE_GENERATE iteration (device -> host -> file).        */
+int64_t grb_write_engine_events(grb_engine *e, const char *path, const grb_writer_opts *opts);
+
 /* ---- the integration loop (host C++, device iterations) ----------------------------------------------- */
 
 /* INTEGRALPARAM.VEGAS of the steering card (reference VEGASPARAM, include/Graniitti/MVEGAS.h:18-32) */

@@ -18,6 +18,7 @@
 //   ref_eval eval  <card.json> <process|null> <pomloop 0|1|-1(card)> <in.bin> <out.bin> [kappa 0|1|2]
 //   ref_eval info  <card.json> <process|null> <pomloop>              (prints flattened process facts)
 //   ref_eval msa   <card.json> <process|null> <out.bin>              (dumps the MSA eikonal table)
+//   ref_eval record <card.json> <process|null> <pomloop> <in.bin> <out.txt>   (the reference's event record of every valid point)
 //
 // in.bin : int64 n, int64 du, int64 dt, then n*(du+dt) doubles (point-major: u[du] then tape[dt])
 // out.bin: int64 n, int64 rec, then n*rec doubles, record layout = see `struct Rec` below.
@@ -29,6 +30,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -168,6 +170,64 @@ int main(int argc, char **argv) {
         printf("INFO loop nkt %u nphi %u minkt %.17g maxkt %.17g\n", N.NumberLoopKT, N.NumberLoopPHI,
                N.MinLoopKT, N.MaxLoopKT);
       }
+      return 0;
+    }
+
+    if (mode == "record" && argc >= 7) {
+      // The reference's own event record of every valid point: EventWeight, then MProcess::EventRecord (= CommonRecord,
+      // src/MProcess.cc:1588-1706) into the stub GenEvent, dumped as text: "EVENT k np nv", "P id pid status parent px py pz e"
+      // (ids in the order HepMC3::GenEvent assigns them: incoming then outgoing particles of each vertex as it is attached),
+      // "V id n_in in...".
+      FILE *fi = fopen(argv[5], "rb");
+      if (!fi) return 2;
+      int64_t hdr[3];
+      if (fread(hdr, sizeof(int64_t), 3, fi) != 3) return 2;
+      const int64_t n = hdr[0], du = hdr[1], dt = hdr[2];
+      std::vector<double> in(n * (du + dt));
+      if ((int64_t)fread(in.data(), sizeof(double), in.size(), fi) != (int64_t)in.size()) return 2;
+      fclose(fi);
+      FILE *fo = fopen(argv[6], "w");
+      for (int64_t k = 0; k < n; ++k) {
+        gra::AuxIntData aux;
+        const double    W = eval_point(g, &in[k * (du + dt)], du, dt, aux);
+        if (!(aux.Valid() && W != 0.0)) continue;
+        HepMC3::GenEvent evt(HepMC3::Units::GEV, HepMC3::Units::MM);
+        if (!g.proc->EventRecord(evt)) continue;
+        std::vector<const HepMC3::GenParticle *> order;
+        auto id_of = [&](const HepMC3::GenParticlePtr &p) {
+          for (size_t i = 0; i < order.size(); ++i)
+            if (order[i] == p.get()) return (int)i + 1;
+          order.push_back(p.get());
+          return (int)order.size();
+        };
+        // the stub keeps vertices in add_vertex order; v4 (system -> daughters) is added before its particles are attached,
+        // nested decay vertices are added (with their mother attached) before the next first-level daughter: a depth-first walk
+        // from v4 reproduces the order in which the real GenEvent sees the particles
+        std::vector<int> parent_vertex(64, 0);
+        const auto &     vt = evt.vtx;
+        std::function<void(size_t)> walk = [&](size_t vi) {
+          for (const auto &p : vt[vi]->in) id_of(p);
+          for (const auto &p : vt[vi]->out) {
+            const int id = id_of(p);
+            parent_vertex[id] = -(int)(vi + 1);
+            for (size_t w = vi + 1; w < vt.size(); ++w)
+              if (!vt[w]->in.empty() && vt[w]->in[0].get() == p.get() && vt[w]->in.size() == 1 && w >= 4) walk(w);
+          }
+        };
+        for (size_t vi = 0; vi < vt.size() && vi < 4; ++vi) walk(vi);
+        fprintf(fo, "EVENT %lld %zu %zu %.17g\n", (long long)k, order.size(), vt.size(), W);
+        for (size_t i = 0; i < order.size(); ++i) {
+          const auto &m = order[i]->momentum();
+          fprintf(fo, "P %zu %d %d %d %.17g %.17g %.17g %.17g\n", i + 1, order[i]->pid(), order[i]->status(), parent_vertex[i + 1], m.px(),
+                  m.py(), m.pz(), m.e());
+        }
+        for (size_t vi = 0; vi < vt.size(); ++vi) {
+          fprintf(fo, "V %d %zu", -(int)(vi + 1), vt[vi]->in.size());
+          for (const auto &p : vt[vi]->in) fprintf(fo, " %d", id_of(p));
+          fprintf(fo, " %zu\n", vt[vi]->out.size());
+        }
+      }
+      fclose(fo);
       return 0;
     }
 

@@ -95,6 +95,7 @@ class Accum(C.Structure):
         ("fmat", f64 * (GRB_MAX_BINS * GRB_MAX_DIM)), ("f2mat", f64 * (GRB_MAX_BINS * GRB_MAX_DIM))]
 
 
+ACCUM_LEN = C.sizeof(Accum) // 8   # doubles of one grb_accum; the engine's device buffer has 128 more (per-rank maxima slots)
 ACCUM_NSUM = 10  # leading doubles that are sum-reduced; then maxW, maxf (max-reduced); then fmat, f2mat (sum)
 
 

@@ -394,6 +394,19 @@ static int digest_res(const grb_process_desc &d, DevRes &R, std::string &err) {
 }
 
 // call with const_slot(e->device).mu held; release_constants() after the last kernel of the call was enqueued
+// exchange helpers of grb_allreduce: tail slots [nd + 2 r, nd + 2 r + 1] of the accumulator buffer belong to rank r
+__global__ void k_park_maxima(double *acc, int nd, int imax, int rank, int nranks) {
+  const int t = threadIdx.x;
+  for (int k = t; k < 2 * nranks; k += 32) acc[nd + k] = (k >> 1) == rank ? acc[imax + (k & 1)] : 0.0;
+}
+__global__ void k_fold_maxima(double *acc, int nd, int imax, int nranks) {
+  if (threadIdx.x < 2) {
+    double m = 0.0;
+    for (int r = 0; r < nranks; ++r) m = fmax(m, acc[nd + 2 * r + threadIdx.x]);
+    acc[imax + threadIdx.x] = m;
+  }
+}
+
 static int ensure_constants(grb_engine *e) {
   ConstSlot &c = const_slot(e->device);
   if (c.owner != e || e->const_dirty) {
@@ -477,7 +490,8 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
     if (desc->lipsdim > 8 && (ce = cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
   }
   if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 4)) != cudaSuccess) return fail("cudaMalloc", ce);
-  if ((ce = cudaMalloc(&e->d_acc, sizeof(grb_accum))) != cudaSuccess) return fail("cudaMalloc", ce);
+  // (+ 2 x 64 doubles: the per-rank maxima slots of grb_allreduce)
+  if ((ce = cudaMalloc(&e->d_acc, sizeof(grb_accum) + 128 * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", ce);
   if ((ce = cudaMalloc(&e->d_xmat, sizeof(double) * GRB_MAX_BINS * GRB_MAX_DIM)) != cudaSuccess) return fail("cudaMalloc", ce);
   cudaMemsetAsync(e->d_acc, 0, sizeof(grb_accum), e->stream);
   cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int) * 4, e->stream);
@@ -1019,7 +1033,7 @@ int grb_comm_unique_id(char id_out[128]) {
 }
 
 int grb_comm_init(grb_engine *e, int rank, int nranks, const char id[128]) {
-  if (!e || !id || rank < 0 || nranks < 1 || rank >= nranks) return GRB_ERR_ARG;
+  if (!e || !id || rank < 0 || nranks < 1 || rank >= nranks || nranks > 64) return GRB_ERR_ARG;
   NcclApi &n = nccl();
   if (!n.ok) { e->err = "libnccl.so.2 not found"; return GRB_ERR_NCCL; }
   CK(cudaSetDevice(e->device));
@@ -1033,7 +1047,10 @@ int grb_comm_init(grb_engine *e, int rank, int nranks, const char id[128]) {
   return GRB_OK;
 }
 
-// sum-reduce everything, then restore the max-reduced pair (maxW, maxf)
+// ONE collective per iteration: the accumulator block is followed by 2 x nranks slots; every rank parks its own two maxima
+// in its slots (the others stay zero), a single sum all-reduce then carries the sums AND an all-gather of the maxima, and
+// a one-warp kernel folds the gathered maxima back into (maxW, maxf).  Halves the latency-bound exchange of the iteration
+// turn-around (two dependent NCCL launches before).
 int grb_allreduce(grb_engine *e) {
   if (!e) return GRB_ERR_ARG;
   if (!e->nccl_comm || e->comm_size <= 1) return GRB_OK;
@@ -1041,11 +1058,11 @@ int grb_allreduce(grb_engine *e) {
   CK(cudaSetDevice(e->device));
   double *acc = reinterpret_cast<double *>(e->d_acc);
   const size_t nd = sizeof(grb_accum) / sizeof(double);
-  CK(cudaMemcpyAsync(e->d_max2, acc + kAccSum, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
-  int rc = n.AllReduce(acc, acc, nd, kNcclFloat64, kNcclSum, e->nccl_comm, e->stream);
-  if (rc == 0) rc = n.AllReduce(e->d_max2, e->d_max2, 2, kNcclFloat64, kNcclMax, e->nccl_comm, e->stream);
+  k_park_maxima<<<1, 32, 0, e->stream>>>(acc, (int)nd, kAccSum, e->comm_rank, e->comm_size);
+  const int rc = n.AllReduce(acc, acc, nd + 2 * (size_t)e->comm_size, kNcclFloat64, kNcclSum, e->nccl_comm, e->stream);
   if (rc != 0) { e->err = std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"); return GRB_ERR_NCCL; }
-  CK(cudaMemcpyAsync(acc + kAccSum, e->d_max2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+  k_fold_maxima<<<1, 32, 0, e->stream>>>(acc, (int)nd, kAccSum, e->comm_size);
+  CK(cudaGetLastError());
   return GRB_OK;
 }
 

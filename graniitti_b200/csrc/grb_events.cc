@@ -10,7 +10,7 @@
 // ("hepevt"), which the reference instantiates (src/MGraniitti.cc:180-209).  HepMC3 itself is absent from this image
 // (the reference's tarball is a missing blob), so the layouts follow the library's documented formats and were not
 // byte-compared against it; the RECORD CONTENT (particles, ids, statuses, mothers, momenta, vertices) is pinned against
-// the reference's own CommonRecord (tests/test_events.py through oracle/_ref/gra/bin/ref_eval record).
+// the reference's own CommonRecord on the same events (tests/test_events.py).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

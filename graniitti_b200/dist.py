@@ -13,11 +13,24 @@ class DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
 
-def allreduce_accum(t):
-    """In-place all-reduce of a float64 tensor holding one grb_accum (any device): one SUM over the block, one
-    MAX over the two maxima."""
+def allreduce_accum(t, rank=None, world=None):
+    """In-place all-reduce of a float64 tensor holding one grb_accum (any device).
+
+    If the tensor carries the 2 x world tail slots of the engine's accumulator buffer (grb_vegas_iterate_async returns a
+    pointer to sizeof(grb_accum) / 8 + 128 doubles) ONE sum all-reduce does everything: every rank parks its two maxima in
+    its own slots, zeroes the others, and folds the gathered maxima back afterwards -- the same scheme as the library's
+    grb_allreduce.  A bare accumulator block takes one SUM over the block and one MAX over the two maxima."""
+    import torch
     import torch.distributed as dist
     lo, hi = _abi.ACCUM_NSUM, _abi.ACCUM_NSUM + 2
+    nacc = _abi.ACCUM_LEN
+    if rank is not None and world is not None and t.numel() >= nacc + 2 * world:
+        tail = t[nacc:nacc + 2 * world]
+        tail.zero_()
+        tail[2 * rank:2 * rank + 2] = t[lo:hi]
+        dist.all_reduce(t[:nacc + 2 * world], op=dist.ReduceOp.SUM)
+        t[lo:hi] = torch.amax(tail.view(world, 2), dim=0)
+        return t
     mx = t[lo:hi].clone()
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)

@@ -53,9 +53,14 @@ def worker(rank, world, port, q):
     grids, sums = [], []
     for it in range(2):
         first, n = g.local_calls(NCALLS, rank, world)
-        t = torch.from_numpy(host_accumulate(desc, xmat, first, n, it))
-        g.allreduce_accum(t)
-        a = t.numpy()
+        acc = host_accumulate(desc, xmat, first, n, it)
+        if it == 0:   # the bare block: one SUM + one MAX collective
+            t = torch.from_numpy(acc)
+            g.allreduce_accum(t)
+        else:         # the engine's buffer layout with the per-rank maxima slots: ONE collective
+            t = torch.from_numpy(np.concatenate([acc, np.full(2 * world, 7.0)]))
+            g.allreduce_accum(t, rank, world)
+        a = t.numpy()[:len(acc)]
         nb = _abi.GRB_MAX_BINS * _abi.GRB_MAX_DIM
         g.optimize_grid(xmat, a[12 + nb:].reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM)[:BINS].copy(), 1.5)
         grids.append(xmat.copy()); sums.append(a[:12].copy())

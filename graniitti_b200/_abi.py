@@ -137,3 +137,7 @@ class WriterOpts(C.Structure):
                 ("sigma_pb", f64), ("sigma_err_pb", f64), ("beam1_pdg", i32), ("beam2_pdg", i32), ("weighted", i32), ("nthreads", i32),
                 ("append", i32), ("close_listing", i32), ("number_events", i32), ("lifetimes", i32), ("first_event", C.c_int64),
                 ("lifetime_seed", C.c_uint64)]
+
+
+class FlatParam(C.Structure):
+    _fields_ = [("precision", f64), ("min_events", f64), ("batch", C.c_int64), ("max_events", C.c_int64), ("seed", C.c_uint64)]

@@ -1188,6 +1188,52 @@ int grb_integrate(grb_engine *e, const grb_vegas_param *par, int rank, int nrank
   return GRB_OK;
 }
 
+int grb_sample_flat(grb_engine *e, const grb_flat_param *par, int rank, int nranks, grb_reduce_fn reduce, void *ctx,
+                    grb_vegas_result *out) {
+  if (!e || !par || !out || nranks < 1 || rank < 0 || rank >= nranks) return GRB_ERR_ARG;
+  if (nranks > 1 && !reduce && !e->nccl_comm) { e->err = "multi-rank sampling needs a reduce callback or grb_comm_init"; return GRB_ERR_STATE; }
+  const auto t0 = std::chrono::steady_clock::now();
+  memset(out, 0, sizeof(*out));
+  const int     dim = e->desc.lipsdim, bins = 2;   // a two-bin uniform grid: x = u, vegasweight = 1 exactly
+  const int64_t batch = par->batch > 0 ? par->batch : (int64_t)1 << 22;
+  const double  max_events = par->max_events > 0 ? (double)par->max_events : 1099511627776.0;
+  const double  precision = par->precision > 0 ? par->precision : 0.05, min_events = par->min_events > 0 ? par->min_events : 1e6;
+  std::vector<double> xmat((size_t)bins * dim);
+  for (int i = 0; i < bins; ++i)
+    for (int j = 0; j < dim; ++j) xmat[i * dim + j] = (i + 1.0) / bins;
+  double Wsum = 0, W2sum = 0, evals = 0;
+  int64_t my_first = 0, my_n = 0;
+  grb_local_calls(batch, rank, nranks, &my_first, &my_n);
+  for (uint64_t it = 0;; ++it) {
+    void *dacc = nullptr;
+    int rc = grb_vegas_iterate_async(e, xmat.data(), bins, dim, my_first, my_n, par->seed, it, GRB_MODE_INTEGRATE, 0.0, &dacc);
+    if (rc != GRB_OK) return rc;
+    if (nranks > 1) {
+      rc = reduce ? reduce(ctx, dacc) : grb_allreduce(e);
+      if (rc != GRB_OK) return rc < 0 ? rc : GRB_ERR_NCCL;
+    }
+    grb_accum acc;
+    rc = grb_vegas_fetch(e, &acc);
+    if (rc != GRB_OK) return rc;
+    double ms = 0;
+    grb_last_timing(e, &ms, nullptr);
+    out->device_ms += ms;
+    Wsum += acc.fsum; W2sum += acc.f2sum; evals += acc.evaluations;
+    out->n_kin_ok += acc.n_kin_ok; out->n_fid_ok += acc.n_fid_ok; out->n_veto_ok += acc.n_veto_ok; out->n_amp_ok += acc.n_amp_ok;
+    out->maxW = std::max(out->maxW, acc.maxW); out->maxf = std::max(out->maxf, acc.maxf);
+    out->iterations = (int32_t)(it + 1);
+    // Stats::CalculateCrossSection (include/Graniitti/MGraniitti.h:59-66)
+    out->sigma     = Wsum / evals;
+    out->sigma_err = std::sqrt(std::max(0.0, (W2sum / evals - out->sigma * out->sigma) / evals));
+    if (std::isnan(out->sigma) || std::isinf(out->sigma)) { e->err = "FLAT:: Integral inf/nan"; return GRB_ERR_STATE; }
+    if ((out->sigma > 0 && out->sigma_err / out->sigma < precision && evals > min_events) || evals >= max_events) break;
+  }
+  out->evaluations = evals; out->ncall_final = batch;
+  for (int i = 0; i < bins * dim; ++i) out->xmat[i] = xmat[i];
+  out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return GRB_OK;
+}
+
 int grb_measure_dfma_peak(int device, double *tflops_out) {
   if (!tflops_out) return GRB_ERR_ARG;
   int ndev = 0;

@@ -98,6 +98,8 @@ def lib():
         L.grb_integrate.restype = cint
         L.grb_integrate.argtypes = [vp, C.POINTER(_abi.VegasParam), cint, cint, _abi.REDUCE_FN, vp,
                                     C.POINTER(_abi.VegasResult)]
+        L.grb_sample_flat.restype = cint
+        L.grb_sample_flat.argtypes = [vp, C.POINTER(_abi.FlatParam), cint, cint, _abi.REDUCE_FN, vp, C.POINTER(_abi.VegasResult)]
         L.grb_local_calls.restype = cint
         L.grb_local_calls.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
         L.grb_test_fastmath.restype = cint
@@ -362,6 +364,14 @@ class Engine:
         res = _abi.VegasResult()
         cb = _abi.REDUCE_FN(lambda ctx, ptr: int(reduce(ptr) or 0)) if reduce else _abi.REDUCE_FN()
         self._check(lib().grb_integrate(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
+        return res
+
+    def sample_flat(self, precision=0.05, min_events=1e6, batch=0, seed=12345678, rank=0, nranks=1, reduce=None, max_events=0):
+        """INTEGRATOR "FLAT" (reference MGraniitti::SampleFlat): plain Monte Carlo in device batches."""
+        par = _abi.FlatParam(precision, min_events, batch, max_events, seed)
+        res = _abi.VegasResult()
+        cb = _abi.REDUCE_FN(lambda ctx, ptr: int(reduce(ptr) or 0)) if reduce else _abi.REDUCE_FN()
+        self._check(lib().grb_sample_flat(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
         return res
 
     def update_desc(self, desc):

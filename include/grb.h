@@ -420,6 +420,21 @@ typedef int (*grb_reduce_fn)(void *ctx, void *device_accum);
 int grb_integrate(grb_engine *e, const grb_vegas_param *par, int rank, int nranks, grb_reduce_fn reduce,
                   void *ctx, grb_vegas_result *out);
 
+/* INTEGRATOR "FLAT" (reference MGraniitti::SampleFlat, src/MGraniitti.cc:1446-1523; MCPARAM, MGraniitti.h:40-43): plain
+ * Monte Carlo over the unit hypercube without a grid -- sigma = <W>, err = sqrt((<W^2> - <W>^2) / N) -- in device batches
+ * of `batch` points (per batch all ranks together, sharded like grb_integrate), until the relative error is below
+ * `precision` AND more than `min_events` points were evaluated (the reference tests after every point, here after every
+ * batch).  out: sigma, sigma_err, maxW, the pass counters, evaluations; chi2 = 0, xmat = the uniform grid.            */
+typedef struct {
+  double   precision;  /* MCPARAM::PRECISION, default 0.05                                                             */
+  double   min_events; /* MCPARAM::MIN_EVENTS, default 1e6                                                             */
+  int64_t  batch;      /* points per device batch, 0 = 2^22                                                            */
+  int64_t  max_events; /* safety bound, 0 = 2^40                                                                       */
+  uint64_t seed;
+} grb_flat_param;
+int grb_sample_flat(grb_engine *e, const grb_flat_param *par, int rank, int nranks, grb_reduce_fn reduce, void *ctx,
+                    grb_vegas_result *out);
+
 /* The shard of an iteration's calls that rank `rank` of `nranks` evaluates (reference
  * VEGASData::GetLocalCalls, include/Graniitti/MVEGAS.h:59-69). Host-only.                                   */
 int grb_local_calls(int64_t calls, int rank, int nranks, int64_t *first, int64_t *n);

@@ -59,6 +59,9 @@ g++ $CXXF -c "$HERE/ref_harness/ref_eval.cc" -o "$OUT/obj_h/ref_eval.o"
 OBJS=$(ls "$OUT"/obj/*.o | grep -v -e '/gr.o$' -e '/MRandom.o$')
 g++ "$OUT/obj_h/ref_eval.o" $OBJS "$OUT/obj_h/MRandom_weakU.o" -o "$OUT/gra/bin/ref_eval" -L"$OUT" -lLHAPDF -pthread -lrt
 
+# ---- 4a. the reference's header-only VEGAS grid refinement (MVEGAS.h), for the direct OptimizeGrid goldens -----------
+g++ -std=c++17 -O2 -I$R/include "$HERE/ref_harness/ref_vegas.cc" -o "$OUT/gra/bin/ref_vegas"
+
 # ---- 4b. INTEGRATION.md route A, compiled: the reference's steering + the product's C ABI (needs graniitti_b200/libgrb.so) --
 LIBGRB="$HERE/../graniitti_b200/libgrb.so"
 if [ -f "$LIBGRB" ]; then

@@ -1372,29 +1372,30 @@ __device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
   const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
   const double a1s = n1x * n1x + n1y * n1y, a2s = n2x * n2x + n2y * n2y, aXs = L.mXsq + (Xx * Xx + Xy * Xy);
-  bool         redo = !(sqrt_fast_ok(a1s) && sqrt_fast_ok(a2s) && sqrt_fast_ok(aXs));
+  unsigned     key = min(min(fast_key(a1s), fast_key(a2s)), fast_key(aXs));   // range guards as in regge_node_fast
   const double pt1 = sqrt_fast_core(a1s), pt2 = sqrt_fast_core(a2s), mtX = sqrt_fast_core(aXs);
   const double Xz = mtX * L.shY, Xe = mtX * L.chY;
   valid = !(Xe > L.emax);
   bool         dom = true;
-  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, dom);
-  redo = redo || (valid && !dom);
+  const double p1z = SAME ? solve_pz3_A_fast(pzi, pt1, pt2, Xz, Xe, key, dom) : solve_pz3_B_fast(pzi, pt1, pt2, Xz, Xe, key, dom);
   const double p2z = -(Xz + p1z);
-  valid = valid && !(isnan(p1z) || p1z < 0 || p2z > 0);
+  valid = valid & !(isnan(p1z) | (p1z < 0) | (p2z > 0));
   const double e1s = L.m1sq + pow2(pt1) + pow2(p1z), e2s = L.m2sq + pow2(pt2) + pow2(p2z);
-  redo = redo || (valid && !(sqrt_fast_ok(e1s) && sqrt_fast_ok(e2s)));
+  key = min(key, min(fast_key(e1s), fast_key(e2s)));
   const double e1 = sqrt_fast_core(e1s), e2 = sqrt_fast_core(e2s);
-  valid = valid && !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
+  valid = valid & !(P.bsum_e - ((e1 + e2) + Xe) > 1e-6);
   const v4 &p3 = L.p3, &p4 = L.p4;
   const double ss13 = m2_of(n1x + p3.x, n1y + p3.y, p1z + p3.z, e1 + p3.e);
   const double ss14 = m2_of(n1x + p4.x, n1y + p4.y, p1z + p4.z, e1 + p4.e);
   const double ss23 = m2_of(n2x + p3.x, n2y + p3.y, p2z + p3.z, e2 + p3.e);
   const double ss24 = m2_of(n2x + p4.x, n2y + p4.y, p2z + p4.z, e2 + p4.e);
-  valid = valid && !(ss13 < 0 || ss14 < 0 || ss23 < 0 || ss24 < 0);
-  const double q1x = 0.0 - n1x, q1y = 0.0 - n1y, q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
-  const double t1 = m2_of(q1x, q1y, q1z, q1e);
-  const double t2 = m2_of(0.0 - n2x, 0.0 - n2y, P.pb2z - p2z, P.pb2e - e2);
-  valid = valid && !(t1 > 0 || t2 > 0);
+  valid = valid & ((__double2hiint(ss13) | __double2hiint(ss14) | __double2hiint(ss23) | __double2hiint(ss24)) >= 0);
+  // t1, t2: the transverse part of q = p_beam - p is the one of p (a1s, a2s), see regge_node_fast
+  const double q1z = P.pb1z - p1z, q1e = P.pb1e - e1;
+  const double t1 = pow2(q1e) - (a1s + pow2(q1z));
+  const double t2 = pow2(P.pb2e - e2) - (a2s + pow2(P.pb2z - p2z));
+  valid = valid & !(t1 > 0);
+  valid = valid & !(t2 > 0);
   // amplitude (tensor_me4_2xS): vertex vectors
   v4 P1, P2, pt, pu;
   P1.x = n1x; P1.y = n1y; P1.z = p1z + P.pb1z; P1.e = e1 + P.pb1e;
@@ -1412,7 +1413,7 @@ __device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &
   const double Ru = (2.0 * d1u * d1u - 0.5 * m2_of(Kua) * P1sq) * (2.0 * d2u * d2u - 0.5 * m2_of(Kub) * P2sq);
   const double pt2v = m2_of(pt), pu2v = m2_of(pu);
   const double al1 = P.tp_delta + P.tp_ap * t1, al2 = P.tp_delta + P.tp_ap * t2;
-  redo = redo || (valid && !(fast_log_in_domain(ss13) && fast_log_in_domain(ss24) && fast_log_in_domain(ss14) && fast_log_in_domain(ss23)));
+  key = min(min(key, fast_key(ss13)), min(min(fast_key(ss24), fast_key(ss14)), fast_key(ss23)));
   const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
   const double xt = al1 * (L13 + P.tp_ln_ap) + al2 * (L24 + P.tp_ln_ap), xu = al1 * (L14 + P.tp_ln_ap) + al2 * (L23 + P.tp_ln_ap);
   const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
@@ -1444,7 +1445,7 @@ __device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &
   const double num = P.tp_coupling * nF * fma(Nt, Du, Nu * Dt), den = (Dt * Du) * dF;
   const double R   = div_fast_core(num, den);
   const double ph  = P.tp_phase * (al1 + al2);
-  redo = redo || (valid && !(fabs(xt) < 690.0 && fabs(xu) < 690.0 && div_fast_ok(num, R) && fabs(ph) < 1.0e5));
+  const bool redo = !(fast_key_ok(key) & dom & (fabs(xt) < 690.0) & (fabs(xu) < 690.0) & div_fast_ok(num, R) & (fabs(ph) < 1.0e5));
   double sn, cs;
   fast_sincos_core(ph, sn, cs);
   A.re = cs * R;

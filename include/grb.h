@@ -158,7 +158,7 @@ typedef struct {
   int32_t ps_class;   /* GRB_CLASS_F | GRB_CLASS_C                                                       */
   int32_t proc;       /* GRB_PROC_*                                                                      */
   int32_t screening;  /* POMLOOP                                                                         */
-  int32_t excitation; /* NSTARS: 0, or 1 / 2 forward N* systems (PP[CON], PP[CON-], yy[CON] in the <F> class)       */
+  int32_t excitation; /* NSTARS: 0, or 1 / 2 forward N* systems (PP[CON], PP[CON-], PP[CONTENSOR], yy[CON]; <F> class) */
   int32_t flatamp;    /* @FLATAMP (0 only)                                                               */
   int32_t ps_active;  /* !ISOLATE ("->" true, "&>" false)                                                */
   int32_t flatmass2;

@@ -39,10 +39,15 @@ int grb_opc_mark(int phase); /* returns the previous phase */
  * faithful implementation on another platform may legitimately compute differently.  Disabled (g_pert_call < 0) the
  * wrappers return their argument unchanged: the restatement's results do not depend on them. */
 static int g_pert_call = -1, g_pert_sign = 1, g_call_idx = 0;
+/* k >= 0: the k-th call of a point; k == -2: every call (a coherent shift); sign = +-n moves the result by n ulps (CUDA's
+ * libm documents up to 2 ulp for sin / cos / sinh / tan / atan2, glibc up to 1) */
 void grb_oracle_perturb_call(int k, int sign) { g_pert_call = k; g_pert_sign = sign; }
 int  grb_oracle_calls_of_last_point(void) { return g_call_idx; }
 static inline double opert(double v) {
-  if (g_call_idx++ == g_pert_call) return nextafter(v, g_pert_sign > 0 ? INFINITY : -INFINITY);
+  const int idx = g_call_idx++;
+  if (idx == g_pert_call || g_pert_call == -2) {
+    for (int n = abs(g_pert_sign); n > 0; --n) v = nextafter(v, g_pert_sign > 0 ? INFINITY : -INFINITY);
+  }
   return v;
 }
 #ifndef GRB_OPCOUNT /* (the op-counting build lets the compiler merge identical libm calls) */
@@ -2208,8 +2213,10 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
                     int32_t *tape_used) {
   if (!d || !u || !w || !flags) return GRB_ERR_ARG;
   if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
-  /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex) and yy[CON] (IncohFlux) */
-  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON)))
+  /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex), yy[CON] (IncohFlux) and the
+   * tensor-pomeron continuum (MTensorPomeron::ME4 has no inelastic vertex: the elastic formulas are evaluated on the excited kinematics) */
+  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
+                                                             d->proc == GRB_PROC_PP_CONTENSOR)))
     return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;

@@ -96,14 +96,16 @@ def oracle_kappa(desc, eik, u, tape):
 
 def oracle_kappa_libm(desc, eik, u, tape, max_calls=64):
     """Conditioning with respect to the libm results (oracle/grb_oracle.c opert()): the result of the k-th transcendental
-    call of every point moved by +-1 ulp, k < max_calls (the Born-level sampling map, decays, cuts and amplitude; the
+    call of every point moved by +-2 ulp, k < max_calls (the Born-level sampling map, decays, cuts and amplitude; the
     later calls belong to the screening loop nodes, each of which carries 1/300 of the loop integral)."""
     lib = helpers.load_oracle()
     base = helpers.oracle_eval(desc, eik, u, tape)["w"]
     kap = np.zeros(len(u))
     try:
-        for k in range(max_calls):
-            for sgn in (1, -1):
+        # single calls by +-2 ulp (CUDA's libm documents up to 2 ulp for sin / cos / sinh / tan / atan2), and every call of
+        # the point together by +-1 ulp (differences of several calls can add up coherently)
+        for k, sgn in [(k, sg) for k in range(max_calls) for sg in (2, -2)] + [(-2, 1), (-2, -1)]:
+            if True:
                 lib.grb_oracle_perturb_call(k, sgn)
                 w = helpers.oracle_eval(desc, eik, u, tape)["w"]
                 with np.errstate(divide="ignore", invalid="ignore"):

@@ -68,6 +68,12 @@ CASES = [
     ("c2_alice_pipi_con_nstar1_screened", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 1, 512, 8, True),
     ("c2_alice_kk_con_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<F> -> K+ K-", 1, 512, 8, True),
     ("c2_alice_kk_conminus_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON-]<F> -> K+ K-", 0, 1024, 8, True),
+    # forward N* excitation with the tensor-pomeron continuum (MTensorPomeron::ME4 has no inelastic vertex: the elastic
+    # formulas on the excited kinematics): 2xS born + screened, 2xV, 2xF
+    ("c2_alice_pipi_tensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 0, 1536, 8, True),
+    ("c2_alice_pipi_tensor_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 1, 320, 8, True),
+    ("c2_alice_rhorho_tensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 0, 1024, 8, True),
+    ("c2_alice_ppbar_tensor_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> p+ p-", 0, 1024, 8, True),
     # semi-exclusive yy -> mu+ mu-: incoherent photon flux (CKMT F2) of the excited leg(s)
     ("c4_cms_mumu_yycon_nstar1_born", "@NSTARS=1:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
     ("c4_cms_mumu_yycon_nstar2_born", "@NSTARS=2:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),

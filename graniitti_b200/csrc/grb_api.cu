@@ -120,8 +120,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.ps_class != GRB_CLASS_F && d.ps_class != GRB_CLASS_C) { err = "only the <F> and <C> phase-space classes are on the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.ps_class == GRB_CLASS_C && d.veto_active) { err = "<C> with veto cuts needs forward fragmentation (outside the device path)"; return GRB_ERR_UNSUPPORTED; }
   if (d.excitation != 0 && !(d.ps_class == GRB_CLASS_F && (d.proc == GRB_PROC_PP_CON || d.proc == GRB_PROC_PP_CON_MINUS || d.proc == GRB_PROC_YY_CON ||
-                                                          d.proc == GRB_PROC_PP_CONTENSOR))) {
-    err = "NSTARS != 0 (forward N* excitation) is on the device path for PP[CON], PP[CON-], PP[CONTENSOR] and yy[CON] in the <F> class";
+                                                          d.proc == GRB_PROC_PP_CONTENSOR || d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON))) {
+    err = "NSTARS != 0 (forward N* excitation) is on the device path in the <F> class";
     return GRB_ERR_UNSUPPORTED;
   }
   if (d.excitation < 0 || d.excitation > 2) { err = "MProcess::SetExcitation: Not valid input (0,1,2)"; return GRB_ERR_ARG; }

@@ -912,7 +912,7 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
   const DevProc &P = c_proc;
   ResKin K;
   K.t1 = in.t1; K.t2 = in.t2;
-  K.pX = in.pX; K.p1 = in.p1; K.p2 = in.p2; K.d0 = p3; K.d1 = p4;
+  K.pX = in.pX; K.p1 = in.p1; K.p2 = in.p2; K.d0 = p3; K.d1 = p4; K.exc = in.exc;
   K.s1 = m2_of(in.p1.x + in.pX.x, in.p1.y + in.pX.y, in.p1.z + in.pX.z, in.p1.e + in.pX.e);
   K.s2 = m2_of(in.p2.x + in.pX.x, in.p2.y + in.pX.y, in.p2.z + in.pX.z, in.p2.e + in.pX.e);
   K.m2 = m2_of(in.pX);

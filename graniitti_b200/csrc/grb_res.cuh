@@ -120,6 +120,7 @@ __device__ __forceinline__ double row_weight(const cx rho[N][N], const double d[
 struct ResKin {  // what a resonance needs from the point (current loop node or Born kinematics)
   double s1, s2, t1, t2, m2, x1, x2, qt1, qt2;
   v4     pX, q1, p1, p2, d0, d1;  // central system, upper propagator, protons, daughters (not loop-updated)
+  int    exc;                     // lts.excite1/2 (bits 0, 1): forward N* systems
 };
 
 // rotation angles of the density matrix frame (reference src/MSpin.cc:544-601)
@@ -301,8 +302,12 @@ __device__ __forceinline__ cx resonance_sum(const ResKin &K) {
   const DevRes & R = c_res;
   const double MX = (K.m2 > 0.0) ? msqrt(K.m2) : -msqrt(-K.m2);
   // shared by every ME3 term
-  const double FFA = P.gN_P / (fma(-K.t1, P.inv_fc1, 1.0) * fma(-K.t1, P.inv_fc2, 1.0));
-  const double FFB = P.gN_P / (fma(-K.t2, P.inv_fc1, 1.0) * fma(-K.t2, P.inv_fc2, 1.0));
+  // PomPomProtonVertex (MRegge.cc:637-644): gN_P S3F(t) for an intact proton, sqrt(g3P gN_P) S3FINEL(t, M^2) for an excited system
+  const double M2f1 = (K.exc & 1) ? m2_of(K.p1) : 0.0, M2f2 = (K.exc & 2) ? m2_of(K.p2) : 0.0;
+  const double VX1 = (K.exc & 1) ? P.gN_P * P.exc_vertex * pow(fabs(K.t1) / (M2f1 * (fabs(K.t1) + 0.5616)), 0.5 * (1 + 0.0808)) : 0.0;
+  const double VX2 = (K.exc & 2) ? P.gN_P * P.exc_vertex * pow(fabs(K.t2) / (M2f2 * (fabs(K.t2) + 0.5616)), 0.5 * (1 + 0.0808)) : 0.0;
+  const double FFA = (K.exc & 1) ? VX1 : P.gN_P / (fma(-K.t1, P.inv_fc1, 1.0) * fma(-K.t1, P.inv_fc2, 1.0));
+  const double FFB = (K.exc & 2) ? VX2 : P.gN_P / (fma(-K.t2, P.inv_fc1, 1.0) * fma(-K.t2, P.inv_fc2, 1.0));
   const cx P1 = regge_prop_all(K.s1, K.t1), P2 = regge_prop_all(K.s2, K.t2);
   const cx PP = cscale(cmul(P1, P2), 2.0 * FFA * FFB * exp(-P.omega * log(K.m2)));  // x (1/m2)^omega
   // shared by every PhotoME3 term (pomeron trajectory k = 0)
@@ -311,8 +316,8 @@ __device__ __forceinline__ cx resonance_sum(const ResKin &K) {
   if (R.any_photo) {
     Ph1 = regge_prop_k(K.s1, K.t1, 0, false);  // PhotoProp normalises to W0^2 = 1, not s0 (MRegge.cc:864-866)
     Ph2 = regge_prop_k(K.s2, K.t2, 0, false);
-    gf1 = coh_flux_amp(K.x1, K.t1, K.qt1);
-    gf2 = coh_flux_amp(K.x2, K.t2, K.qt2);
+    gf1 = (K.exc & 1) ? incoh_flux_amp(K.x1, K.t1, K.qt1, M2f1) : coh_flux_amp(K.x1, K.t1, K.qt1);   // MRegge.cc:793-800
+    gf2 = (K.exc & 2) ? incoh_flux_amp(K.x2, K.t2, K.qt2, M2f2) : coh_flux_amp(K.x2, K.t2, K.qt2);
   }
   const double mA = R.bw3 ? m_of(K.d0) : 0.0, mB = R.bw3 ? m_of(K.d1) : 0.0;
   cx A = {0.0, 0.0};
@@ -325,8 +330,9 @@ __device__ __forceinline__ cx resonance_sum(const ResKin &K) {
     cx term;
     if (r.photo) {
       // gammaflux2 * Prop(s1,t1) gN exp(B0 t1 / 2) + gammaflux1 * Prop(s2,t2) gN exp(B0 t2 / 2)
-      const cx a1 = cscale(Ph1, gf2 * P.gN_P * exp(0.5 * r.B0 * K.t1));
-      const cx a2 = cscale(Ph2, gf1 * P.gN_P * exp(0.5 * r.B0 * K.t2));
+      // (PhotoProp's vertex, MRegge.cc:876-880: the inelastic vertex replaces gN exp(B0 t / 2) on an excited leg)
+      const cx a1 = cscale(Ph1, gf2 * ((K.exc & 1) ? VX1 : P.gN_P * exp(0.5 * r.B0 * K.t1)));
+      const cx a2 = cscale(Ph2, gf1 * ((K.exc & 2) ? VX2 : P.gN_P * exp(0.5 * r.B0 * K.t2)));
       term = cmul(core, cadd(a1, a2));
     } else {
       term = cmul(core, PP);

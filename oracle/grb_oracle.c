@@ -41,11 +41,22 @@ int grb_opc_mark(int phase); /* returns the previous phase */
 static int g_pert_call = -1, g_pert_sign = 1, g_call_idx = 0;
 /* k >= 0: the k-th call of a point; k == -2: every call (a coherent shift); sign = +-n moves the result by n ulps (CUDA's
  * libm documents up to 2 ulp for sin / cos / sinh / tan / atan2, glibc up to 1) */
-void grb_oracle_perturb_call(int k, int sign) { g_pert_call = k; g_pert_sign = sign; }
+static int g_pert_start = 0, g_pert_stride = 0, g_pert_off = 0, g_pert_pz = 0;
+static int g_pert_pz2 = 0;
+void grb_oracle_perturb_pz(int n_ulps) { g_pert_pz = n_ulps; g_pert_pz2 = 0; }
+void grb_oracle_perturb_pz2(int n_ulps) { g_pert_pz2 = n_ulps; g_pert_pz = 0; }
+void grb_oracle_perturb_call(int k, int sign) { g_pert_call = k; g_pert_sign = sign; g_pert_stride = 0; }
+/* k == -3: every call with index >= start and (index - start) % stride == off: the same call site in every node of the
+ * screening loop (the loop re-derives y_X, sinh y_X, cosh y_X ... per node; an implementation that hoists them differs
+ * coherently in all nodes) */
+void grb_oracle_perturb_stride(int start, int stride, int off, int sign) {
+  g_pert_call = -3; g_pert_sign = sign; g_pert_start = start; g_pert_stride = stride; g_pert_off = off;
+}
 int  grb_oracle_calls_of_last_point(void) { return g_call_idx; }
 static inline double opert(double v) {
   const int idx = g_call_idx++;
-  if (idx == g_pert_call || g_pert_call == -2) {
+  if (idx == g_pert_call || g_pert_call == -2 ||
+      (g_pert_call == -3 && g_pert_stride > 0 && idx >= g_pert_start && (idx - g_pert_start) % g_pert_stride == g_pert_off)) {
     for (int n = abs(g_pert_sign); n > 0; --n) v = nextafter(v, g_pert_sign > 0 ? INFINITY : -INFINITY);
   }
   return v;
@@ -414,8 +425,14 @@ static int b51_build_kin(ost *S, double pt1, double pt2, double phi1, double phi
   pX.z = mtX * sinh(yX);
   pX.e = mtX * cosh(yX);
   if (pX.e > (d->sqrt_s - (m1 + m2))) return 0;
-  const double p1z = solve_pz(m1, m2, pt1, pt2, pX.z, pX.e, d->s);
-  const double p2z = -(pX.z + p1z);
+  double p1z = solve_pz(m1, m2, pt1, pt2, pX.z, pX.e, d->s);
+  /* conditioning probe: the solved longitudinal momentum moved by n ulps.  A 1-ulp libm difference upstream changes the
+   * exact solution by far less than one ulp of p1z ~ sqrt(s)/2, but flips its ROUNDING with probability ~1e-3; with an
+   * excited forward system that flip moves M^2 = E^2 - p^2 by 2 p ulp(p) = 1.2e-8 GeV^2, which every node of the screening
+   * loop inherits through m1 = pfinal_orig[1].M() (MFactorized.cc:97-98) into S3FINEL(t, M^2). */
+  for (int n = abs(g_pert_pz); n > 0; --n) p1z = nextafter(p1z, g_pert_pz > 0 ? INFINITY : -INFINITY);
+  double p2z = -(pX.z + p1z);
+  for (int n = abs(g_pert_pz2); n > 0; --n) p2z = nextafter(p2z, g_pert_pz2 > 0 ? INFINITY : -INFINITY);
   if (p1z < 0 || p2z > 0) return 0;
   if (isnan(p1z)) return 0; /* NaN compares false above and would be caught by CheckEMC's comparisons? no:
                                NaN passes all '>' tests; the reference then fails GetLorentzScalars
@@ -1680,14 +1697,15 @@ static double o_incoh_flux(const ost *S, double xi, double t, double pt, double 
   return f;
 }
 /* reference src/MRegge.cc:852-882 PhotoProp (elastic leg) */
-static cx o_photo_prop(const ost *S, double s, double t, double m2) {
+static cx o_photo_prop(const ost *S, double s, double t, double m2, int excite, double M2_forward) {
   const grb_param_regge *R = &S->d->regge;
   const double B0 = pow(fmax(pow2(0.7), m2) / 2.0, -O_PI / 2.0) + 3 * O_PI / 2.0;
   const double W02 = pow2(1.0);
   const double alpha = R->a0[0] + R->ap[0] * t;
   const double y = ((-1.0 * O_PI) / 2.0 * R->ap[0]) * t;
   const cx eta = cx_mul(S->regge_eta0[0], (cx){cos(y), sin(y)});
-  const double FF = S->d->soft.gN_P * exp(B0 * t / 2.0);
+  /* proton / dissociative system vertex, MRegge.cc:876-880 */
+  const double FF = excite ? msqrt(S->d->soft.g3P * S->d->soft.gN_P) * s3finel(t, M2_forward) : S->d->soft.gN_P * exp(B0 * t / 2.0);
   return cx_scale(cx_scale(eta, pow(s / W02, alpha)), FF);
 }
 /* reference src/MRegge.cc:677-706 ME3 */
@@ -1736,7 +1754,8 @@ static cx regge_me6(ost *S) {
   return A;
 }
 static cx regge_me3(ost *S, const grb_resonance *r) {
-  const double FF_A = S->d->soft.gN_P * s3f(S, S->t1), FF_B = S->d->soft.gN_P * s3f(S, S->t2);
+  double FF_A, FF_B;
+  pom_pom_proton_vertex(S, &FF_A, &FF_B);
   cx A = cx_scale(prop_only(S, S->s1, S->t1), 2.0);
   A = cx_scale(A, FF_A);
   A = cx_mul(A, o_cbw(S, r));
@@ -1750,10 +1769,12 @@ static cx regge_me3(ost *S, const grb_resonance *r) {
 /* reference src/MRegge.cc:781-828 PhotoME3 (pp initial state, elastic legs) */
 static cx regge_photo_me3(ost *S, const grb_resonance *r) {
   const cx common = cx_scale(o_cbw(S, r), exp(-pow2(S->m2 - pow2(r->mass)) / pow2(pow2(r->g_FF))));
-  const double gf1 = msqrt(o_coh_flux(S, S->x1, S->t1, S->qt1) / S->x1);
-  const double gf2 = msqrt(o_coh_flux(S, S->x2, S->t2, S->qt2) / S->x2);
-  const cx A_1 = cx_mul(cx_scale(common, gf2), o_photo_prop(S, S->s1, S->t1, pow2(r->mass)));
-  const cx A_2 = cx_mul(cx_scale(common, gf1), o_photo_prop(S, S->s2, S->t2, pow2(r->mass)));
+  const double fl1 = S->excite1 ? o_incoh_flux(S, S->x1, S->t1, S->qt1, v4_m2(S->pfinal[1])) : o_coh_flux(S, S->x1, S->t1, S->qt1);
+  const double fl2 = S->excite2 ? o_incoh_flux(S, S->x2, S->t2, S->qt2, v4_m2(S->pfinal[2])) : o_coh_flux(S, S->x2, S->t2, S->qt2);
+  const double gf1 = msqrt(fl1 / S->x1);
+  const double gf2 = msqrt(fl2 / S->x2);
+  const cx A_1 = cx_mul(cx_scale(common, gf2), o_photo_prop(S, S->s1, S->t1, pow2(r->mass), S->excite1, v4_m2(S->pfinal[1])));
+  const cx A_2 = cx_mul(cx_scale(common, gf1), o_photo_prop(S, S->s2, S->t2, pow2(r->mass), S->excite2, v4_m2(S->pfinal[2])));
   const cx A_prod = cx_add(A_1, A_2);
   const cx A_spin = cx_mul(o_prod_amp(S, r), o_decay_amp(S, r));
   return cx_mul(A_prod, A_spin);
@@ -2216,7 +2237,7 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
   /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex), yy[CON] (IncohFlux) and the
    * tensor-pomeron continuum (MTensorPomeron::ME4 has no inelastic vertex: the elastic formulas are evaluated on the excited kinematics) */
   if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
-                                                             d->proc == GRB_PROC_PP_CONTENSOR)))
+                                                             d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON)))
     return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;

@@ -115,6 +115,27 @@ def oracle_kappa_libm(desc, eik, u, tape, max_calls=64):
     return kap
 
 
+def oracle_kappa_pz(desc, eik, u, tape):
+    """Conditioning with respect to the ROUNDING of the solved forward longitudinal momenta (oracle probes
+    grb_oracle_perturb_pz / _pz2: Born-level p1z, p2z moved by one ulp).  A 1-ulp libm difference upstream moves the exact
+    solution by far less than an ulp of p_z ~ sqrt(s)/2, but flips its rounding with probability ~1e-3; with an excited
+    forward system that flip moves M^2 = E^2 - p^2 by 2 p ulp(p) = 1.2e-8 GeV^2, and every node of the screening loop
+    inherits it through the re-derived mass m = pfinal_orig.M() into S3FINEL(t, M^2) / x_Bj."""
+    lib = helpers.load_oracle()
+    base = helpers.oracle_eval(desc, eik, u, tape)["w"]
+    kap = np.zeros(len(u))
+    try:
+        for fn in (lib.grb_oracle_perturb_pz, lib.grb_oracle_perturb_pz2):
+            for sgn in (1, -1, 2, -2, 3, -3):   # (the response is a staircase: E^2 - p^2 re-rounds every few ulps of p_z)
+                fn(sgn)
+                w = helpers.oracle_eval(desc, eik, u, tape)["w"]
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    kap = np.maximum(kap, np.where((base != 0) & (w != 0), np.abs(w - base) / np.abs(base), 0.0))
+    finally:
+        lib.grb_oracle_perturb_pz(0)
+    return kap
+
+
 def _libm_chunk(rng_):
     lo, hi = rng_
     return lo, oracle_kappa_libm(_W["desc"], _W["eik"], _W["u"][lo:hi], _W["tape"][lo:hi], _W["max_calls"])

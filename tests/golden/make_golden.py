@@ -74,6 +74,9 @@ CASES = [
     ("c2_alice_pipi_tensor_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> pi+ pi-", 1, 320, 8, True),
     ("c2_alice_rhorho_tensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> rho(770)0 rho(770)0", 0, 1024, 8, True),
     ("c2_alice_ppbar_tensor_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<F> -> p+ p-", 0, 1024, 8, True),
+    # ... and with the resonances: MRegge::ME3 through PomPomProtonVertex, PhotoME3 with the incoherent flux + inelastic vertex
+    ("c1_test_pipi_rescon_nstar1_born", "@NSTARS=1:./input/test.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 1024, 8, True),
+    ("c3_atlas_kk_res_nstar2_born", "@NSTARS=2:./tests/run_atlas_multi/ATLAS.json", "PP[RES]<F> -> K+ K-", 0, 1536, 8, True),
     # semi-exclusive yy -> mu+ mu-: incoherent photon flux (CKMT F2) of the excited leg(s)
     ("c4_cms_mumu_yycon_nstar1_born", "@NSTARS=1:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
     ("c4_cms_mumu_yycon_nstar2_born", "@NSTARS=2:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),

@@ -35,8 +35,8 @@ def engine_for(grb, msa, card, proc=None, pom=-1):
 
 def compare(w, fl, ref_w, ref_fl, kappa=None, rtol=RTOL, libm=None):
     """libm = (desc, eikonal, u, tape): points beyond max(rtol, 8 kappa) are re-examined with the conditioning with respect to
-    the libm results (the k-th transcendental of the point moved by one ulp in the oracle port, tests/fullsize.py): what
-    two IEEE platforms with different libms legitimately compute differently."""
+    the libm results (the k-th transcendental of the point moved by ulps in the oracle port) and to the rounding of the
+    solved forward p_z (tests/fullsize.py): what two IEEE platforms with different libms legitimately compute differently."""
     kin = (ref_fl & 1) == 1
     assert np.array_equal(fl & 1, ref_fl & 1), "kinematics_ok differs"
     assert np.array_equal(fl[kin], ref_fl[kin]), "cut decisions differ"
@@ -49,10 +49,10 @@ def compare(w, fl, ref_w, ref_fl, kappa=None, rtol=RTOL, libm=None):
         tol = np.maximum(rtol, 8.0 * kappa[nz])
     bad = rel > tol
     if bad.any() and libm is not None:
-        from fullsize import oracle_kappa_libm
+        from fullsize import oracle_kappa_libm, oracle_kappa_pz
         desc, eik, u, tape = libm
         idx = np.flatnonzero(nz)[bad]
-        kl = oracle_kappa_libm(desc, eik, u[idx], tape[idx], max_calls=96)
+        kl = np.maximum(oracle_kappa_libm(desc, eik, u[idx], tape[idx], max_calls=96), oracle_kappa_pz(desc, eik, u[idx], tape[idx]))
         tol[bad] = np.maximum(tol[bad], 8.0 * kl)
         still = rel > tol
         dump = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")

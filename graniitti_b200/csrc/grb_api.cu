@@ -119,11 +119,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.abi_version != GRB_ABI_VERSION) { err = "abi_version mismatch"; return GRB_ERR_ARG; }
   if (d.ps_class != GRB_CLASS_F && d.ps_class != GRB_CLASS_C) { err = "only the <F> and <C> phase-space classes are on the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.ps_class == GRB_CLASS_C && d.veto_active) { err = "<C> with veto cuts needs forward fragmentation (outside the device path)"; return GRB_ERR_UNSUPPORTED; }
-  if (d.excitation != 0 && !(d.ps_class == GRB_CLASS_F && (d.proc == GRB_PROC_PP_CON || d.proc == GRB_PROC_PP_CON_MINUS || d.proc == GRB_PROC_YY_CON ||
-                                                          d.proc == GRB_PROC_PP_CONTENSOR || d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON))) {
-    err = "NSTARS != 0 (forward N* excitation) is on the device path in the <F> class";
-    return GRB_ERR_UNSUPPORTED;
-  }
+  // (forward N* excitation: both phase-space classes, every amplitude on the device path)
   if (d.excitation < 0 || d.excitation > 2) { err = "MProcess::SetExcitation: Not valid input (0,1,2)"; return GRB_ERR_ARG; }
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
@@ -162,7 +158,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     return GRB_ERR_UNSUPPORTED;
   }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
-  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 : 6 + d.excitation)) { err = "lipsdim must be 6 + NSTARS for <F> and 3 Nf - 4 for <C>"; return GRB_ERR_ARG; }
+  if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 : 6) + d.excitation) { err = "lipsdim must be 6 + NSTARS for <F> and 3 Nf - 4 + NSTARS for <C>"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.n_veto > GRB_MAX_VETO) { err = "too many veto domains"; return GRB_ERR_ARG; }
   if (d.fcuts.usercuts != 0 && std::abs(d.fcuts.usercuts) != 3 && std::abs(d.fcuts.usercuts) != 111) {
@@ -1016,6 +1012,19 @@ int grb_xscan(grb_engine *e, const double *sqrt_s, int n, const grb_vegas_param 
     rows[i].xs_tot_mb = xs[0]; rows[i].xs_el_mb = xs[1]; rows[i].xs_inel_mb = xs[2];
     rows[i].sigma = r.sigma; rows[i].sigma_err = r.sigma_err; rows[i].chi2 = r.chi2;
     rows[i].evaluations = r.evaluations; rows[i].seconds = r.seconds;
+  }
+  return GRB_OK;
+}
+
+int grb_integrate_batch(grb_engine *e, const grb_process_desc *descs, int k_sets, const grb_vegas_param *par, int rank, int nranks,
+                        grb_reduce_fn reduce, void *ctx, grb_vegas_result *results) {
+  if (!e || !descs || k_sets < 0 || !par || !results) return GRB_ERR_ARG;
+  for (int k = 0; k < k_sets; ++k) {
+    int rc = grb_update_desc(e, &descs[k]);
+    if (rc != GRB_OK) return rc;
+    if (e->desc.screening && !e->have_loop) { e->err = "grb_integrate_batch: set " + std::to_string(k) + " changes s or the loop discretisation: no eikonal table"; return GRB_ERR_STATE; }
+    rc = grb_integrate(e, par, rank, nranks, reduce, ctx, &results[k]);
+    if (rc != GRB_OK) return rc;
   }
   return GRB_OK;
 }

@@ -74,7 +74,10 @@ __device__ __forceinline__ double weight_prefactor_C(const PointState<NN> &S) {
   const double J   = 1.0 / fabs(S.p1.z / S.p1.e - S.p2.z / S.p2.e);
   const double pt1 = msqrt(pt2_of(S.p1)), pt2 = msqrt(pt2_of(S.p2));
   const double psw = (pt1 / S.p1.e) * (pt2 / S.p2.e) * J * S.qprod;                          // x 2^-2Kf (2pi)^-(3Nf-4) / 4
-  return psw * (pt1 * pt2) * c_proc.w_const_C;                                               // x (dkt 2pi)^(Kf-1) drap^Kf (2pi)^2 dlog^2
+  double       fwd = 1.0;  // ForwardVolume with excitation (as in weight_prefactor)
+  if (S.exc & 1) fwd *= m2_of(S.p1) * c_proc.dlog_M2f;
+  if (S.exc & 2) fwd *= m2_of(S.p2) * c_proc.dlog_M2f;
+  return psw * (pt1 * pt2) * fwd * c_proc.w_const_C;                                         // x (dkt 2pi)^(Kf-1) drap^Kf (2pi)^2 dlog^2
 }
 
 template <int NN, bool VEGAS, int AMP>
@@ -88,8 +91,8 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += stride) {
     const int64_t idx    = base + threadIdx.x;
     const bool    active = idx < a.n;
-    constexpr int UD = (AMP == AMP_REGGE_ME6) ? 14 : 8;   // coordinates: <F> 6 (+2 N*), <C> 8 (two legs), 14 (four legs)
-    double        u[UD];
+    constexpr int UD = (AMP == AMP_REGGE_ME6) ? 16 : 10;  // coordinates: <F> 6 (+2 N*), <C> 8 (two legs) / 14 (four legs) (+2 N*)
+    double        u[UD] = {};
     uint64_t      packed = 0, packed_hi = 0;                // VEGAS bin per dimension, 8 bits each
     Ladder4       X4;                                      // four-leg ladder scalars (AMP_REGGE_ME6 only)
     double        vw     = 1.0;
@@ -201,8 +204,8 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
                 if (k == 0) it[(IT_L4A + 10) * c] = shk; else it[(IT_L4B + k - 1) * c] = shk;
                 it[(IT_L4B + 3 + k) * c] = chk;
               }
-              a.item_bins_hi[slot] = packed_hi;
             }
+            if (dim > 8) a.item_bins_hi[slot] = packed_hi;   // VEGAS bins of the dimensions 8.. (second packed word)
             if (P.ps_class == GRB_CLASS_C && AMP != AMP_REGGE_ME6) {
               it[IT_MXSQ * c] = L.m3; it[IT_SHY * c] = L.m4; it[IT_CHY * c] = L.qx;
               it[(IT_CK + 0) * c] = L.qy; it[(IT_CK + 1) * c] = L.sh3; it[(IT_CK + 2) * c] = L.ch3;

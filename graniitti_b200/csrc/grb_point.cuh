@@ -180,6 +180,26 @@ __device__ __forceinline__ bool lorentz_scalars(PointState<NN> &S) {
 template <int NN, class Draws>
 __device__ __forceinline__ bool cascade_decays(Draws &dr, PointState<NN> &S);
 
+// forward N* system masses (SampleForwardMasses, MProcess.cc:1317-1365): log-flat M^2 from the coordinates ua, ub; single
+// excitation picks the side with one internal uniform.  Returns lts.excite1/2 as bits 0, 1.
+template <class Draws>
+__device__ __forceinline__ int sample_forward_masses(double ua, double ub, Draws &dr, double &m1, double &m2) {
+  const DevProc &P = c_proc;
+  m1 = P.mb1; m2 = P.mb2;
+  if (P.excitation == 1) {
+    const double r = exp(P.log_M2f_min + P.dlog_M2f * ua);
+    if (dr.next() < 0.5) { m1 = msqrt(r); return 1; }
+    m2 = msqrt(r);
+    return 2;
+  }
+  if (P.excitation == 2) {
+    const double r1 = exp(P.log_M2f_min + P.dlog_M2f * ua), r2 = exp(P.log_M2f_min + P.dlog_M2f * ub);
+    m1 = msqrt(r1); m2 = msqrt(r2);
+    return 3;
+  }
+  return 0;
+}
+
 template <int NN, class Draws>
 __device__ __forceinline__ bool point_kinematics(const double *u, Draws &dr, PointState<NN> &S) {
   const DevProc &P = c_proc;
@@ -298,8 +318,9 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
   const double kt   = P.kt_min + P.dkt * u[4];
   const double phik = 2.0 * GRB_PI * u[5];
   const double y3 = P.rap_min + P.drap * u[6], y4 = P.rap_min + P.drap * u[7];
-  const double m1 = P.mb1, m2 = P.mb2;
-  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.exc = 0;
+  double m1, m2;   // forward N* masses from the coordinates after the rapidities (MContinuum.cc:322-328)
+  S.exc = sample_forward_masses(u[8], u[9], dr, m1, m2);
+  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0;
   double s1, c1, s2, c2, sk, ck;
   sincos(phi1, &s1, &c1);
   sincos(phi2, &s2, &c2);
@@ -388,8 +409,9 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
   const double   phi2 = 2.0 * GRB_PI * u[3];
 #pragma unroll
   for (int i = 0; i < 4; ++i) S.moff[i % NN] = offshell_mass(i, dr);
-  const double m1 = P.mb1, m2 = P.mb2;
-  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.exc = 0; S.qx = 0.0; S.qy = 0.0;
+  double m1, m2;
+  S.exc = sample_forward_masses(u[14], u[15], dr, m1, m2);
+  S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.qx = 0.0; S.qy = 0.0;
   double s1, c1, s2, c2;
   sincos(phi1, &s1, &c1);
   sincos(phi2, &s2, &c2);

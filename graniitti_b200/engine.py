@@ -100,6 +100,9 @@ def lib():
                                     C.POINTER(_abi.VegasResult)]
         L.grb_sample_flat.restype = cint
         L.grb_sample_flat.argtypes = [vp, C.POINTER(_abi.FlatParam), cint, cint, _abi.REDUCE_FN, vp, C.POINTER(_abi.VegasResult)]
+        L.grb_integrate_batch.restype = cint
+        L.grb_integrate_batch.argtypes = [vp, C.POINTER(_abi.ProcessDesc), cint, C.POINTER(_abi.VegasParam), cint, cint, _abi.REDUCE_FN, vp,
+                                          C.POINTER(_abi.VegasResult)]
         L.grb_local_calls.restype = cint
         L.grb_local_calls.argtypes = [i64, cint, cint, C.POINTER(i64), C.POINTER(i64)]
         L.grb_test_fastmath.restype = cint
@@ -373,6 +376,15 @@ class Engine:
         cb = _abi.REDUCE_FN(lambda ctx, ptr: int(reduce(ptr) or 0)) if reduce else _abi.REDUCE_FN()
         self._check(lib().grb_sample_flat(self._h, C.byref(par), rank, nranks, cb, None, C.byref(res)))
         return res
+
+    def integrate_batch(self, descs, ncall, iters=5, precision=0.01, chi2max=10.0, bins=128, lam=1.5, seed=12345678, burnin=3):
+        """K parameter sets (same topology) integrated back to back on this engine (fit loops)."""
+        par = _abi.VegasParam(bins, iters, burnin, 0, ncall, lam, chi2max, precision, seed, -1, 0)
+        arr = (_abi.ProcessDesc * len(descs))(*descs)
+        res = (_abi.VegasResult * len(descs))()
+        self._check(lib().grb_integrate_batch(self._h, arr, len(descs), C.byref(par), 0, 1, _abi.REDUCE_FN(), None, res))
+        lib().grb_get_desc(self._h, C.byref(self.desc))
+        return list(res)
 
     def update_desc(self, desc):
         """Re-parameterise without re-creating the engine (same decay-tree topology and phase-space class)."""

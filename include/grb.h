@@ -482,6 +482,15 @@ typedef struct {
  * The engine is left at the last energy.                                                                        */
 int grb_xscan(grb_engine *e, const double *sqrt_s, int n, const grb_vegas_param *par, grb_xscan_row *rows);
 
+/* Parameter fits (reference src/Program/Analysis/fitcentral.cc: every fit step re-creates the generator and re-integrates
+ * for each parameter set): K descriptions of the same topology integrated back to back on ONE engine -- buffers, streams
+ * and the communicator stay, each set costs one description digest and one constant upload (grb_update_desc).  The eikonal
+ * table is kept when s and the loop discretisation do not change.  results[k] = grb_integrate of descs[k]; bit-identical
+ * to K freshly created engines.  (The sets run one after the other: the kernels read their parameters from constant
+ * memory, one set at a time.)                                                                                         */
+int grb_integrate_batch(grb_engine *e, const grb_process_desc *descs, int k_sets, const grb_vegas_param *par, int rank,
+                        int nranks, grb_reduce_fn reduce, void *ctx, grb_vegas_result *results);
+
 /* Unit-test hook for graniitti_b200/csrc/grb_fastmath.cuh on n host values: kind 0 table-driven log, 1 table-driven
  * exp, 2 branch-free exact sqrt, 3 sqrt(), 4 branch-free exact x[i] / x[i+1], 5 operator/ (3 and 5 are the device's
  * own IEEE results the exact forms must reproduce bit for bit), 6 / 7 table-driven sin / cos,

@@ -606,7 +606,9 @@ static int bn_random_kin(ost *S, const double *r) {
   for (int i = 0; i < Kf - 1; ++i) kt[i] = gc->kt_min + (gc->kt_max - gc->kt_min) * r[ind++];
   for (int i = 0; i < Kf - 1; ++i) phik[i] = 2.0 * O_PI * r[ind++];
   for (int i = 0; i < Kf; ++i) y[i] = gc->rap_min + (gc->rap_max - gc->rap_min) * r[ind++];
-  return bn_build_kin(S, pt1, pt2, phi1, phi2, kt, phik, y, d->beam1_mass, d->beam2_mass);
+  double m1, m2; /* forward N* system masses from the coordinates after the rapidities (MContinuum.cc:322-328) */
+  sample_forward_masses(S, r + ind, &m1, &m2);
+  return bn_build_kin(S, pt1, pt2, phi1, phi2, kt, phik, y, m1, m2);
 }
 
 /* reference src/MContinuum.cc:94-161 LoopKinematics: the central legs ARE updated here (lts.pfinal[3..]) -- but not
@@ -2188,7 +2190,14 @@ static double bn_integral_volume(const ost *S) {
   const double      PHI_vol = pow2(2.0 * O_PI);
   const double      J_pt    = v4_pt(S->pfinal[1]) * v4_pt(S->pfinal[2]);
   const double      PT_vol  = J_pt * pow2(log(gc->forward_pt_max) - log(gc->forward_pt_min + O_ZERO_EPS));
-  const double      fv      = PHI_vol * PT_vol;
+  double            fv      = PHI_vol * PT_vol;
+  if (S->d->excitation == 1) { /* ForwardVolume, MProcess.cc:1402-1411 (as in b51_integral_volume) */
+    const double J_M2 = S->excite1 ? v4_m2(S->pfinal[1]) : v4_m2(S->pfinal[2]);
+    fv = PHI_vol * PT_vol * J_M2 * (S->log_M2_f_max - S->log_M2_f_min);
+  } else if (S->d->excitation == 2) {
+    const double J_M2 = v4_m2(S->pfinal[1]) * v4_m2(S->pfinal[2]);
+    fv = PHI_vol * PT_vol * J_M2 * pow2(S->log_M2_f_max - S->log_M2_f_min);
+  }
   double            KT_vol  = pow(gc->kt_max - gc->kt_min, Kf - 1);
   KT_vol *= pow(2.0 * O_PI, Kf - 1);
   KT_vol *= pow(gc->rap_max - gc->rap_min, Kf);
@@ -2236,8 +2245,8 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
   if ((d->ps_class != GRB_CLASS_F && d->ps_class != GRB_CLASS_C) || d->flatamp != 0) return GRB_ERR_UNSUPPORTED;
   /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex), yy[CON] (IncohFlux) and the
    * tensor-pomeron continuum (MTensorPomeron::ME4 has no inelastic vertex: the elastic formulas are evaluated on the excited kinematics) */
-  if (d->excitation != 0 && !(d->ps_class == GRB_CLASS_F && (d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
-                                                             d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON)))
+  if (d->excitation != 0 && !(d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
+                              d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON))
     return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;

@@ -77,6 +77,10 @@ CASES = [
     # ... and with the resonances: MRegge::ME3 through PomPomProtonVertex, PhotoME3 with the incoherent flux + inelastic vertex
     ("c1_test_pipi_rescon_nstar1_born", "@NSTARS=1:./input/test.json", "PP[RES+CON]<F> -> pi+ pi-", 0, 1024, 8, True),
     ("c3_atlas_kk_res_nstar2_born", "@NSTARS=2:./tests/run_atlas_multi/ATLAS.json", "PP[RES]<F> -> K+ K-", 0, 1536, 8, True),
+    # ... and in the <C> phase-space class (MContinuum: the masses come from the coordinates after the leg rapidities)
+    ("cc_alice_pipi_con_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 0, 1536, 8, True),
+    ("cc_alice_pipi_con_nstar2_screened", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 1, 384, 8, True),
+    ("cc_alice_pipi_tensor_nstar2_born", "@NSTARS=2:./tests/processes/ALICECUTS.json", "PP[CONTENSOR]<C> -> pi+ pi-", 0, 1024, 8, True),
     # semi-exclusive yy -> mu+ mu-: incoherent photon flux (CKMT F2) of the excited leg(s)
     ("c4_cms_mumu_yycon_nstar1_born", "@NSTARS=1:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
     ("c4_cms_mumu_yycon_nstar2_born", "@NSTARS=2:./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", 0, 1536, 8, True),
@@ -100,7 +104,7 @@ def main():
         if only and name not in only:
             continue
         nstars = int(card[1:].split(":", 1)[0].split("=")[1]) if card.startswith("@NSTARS=") else 0
-        u, tape = make_points(n, (14 if name.startswith("cc4_") else 8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)
+        u, tape = make_points(n, (14 if name.startswith("cc4_") else 8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)   # (+ NSTARS forward-mass coordinates)
         if name.startswith("cc4_"):   # keep the three intermediate kt below ~0.75 GeV (flat kt up to 2.5 GeV is mostly cut away)
             u[:, 4:7] *= 0.3
         if nstars:   # forward pt up to 50 / 100 GeV with excitation: keep the log-pt coordinates where pt is O(0.05 - 3 GeV)

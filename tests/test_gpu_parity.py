@@ -429,3 +429,27 @@ def test_flat_integrator_mode(grb, msa):
     r1 = E.sample_flat(precision=1.0, min_events=1.0, batch=1 << 21, seed=77)
     assert abs(r1.sigma - a.fsum / (1 << 21)) <= 1e-12 * r1.sigma and r1.iterations == 1 and r1.maxW == a.maxW
     E.close()
+
+
+def test_batched_parameter_sets(grb, msa):
+    """grb_integrate_batch (fit loops, reference fitcentral): K = 8 variations of a resonance coupling / the Pomeron intercept
+    on one engine == 8 freshly created engines, bit for bit (same Philox stream, same grids)."""
+    import copy
+    base = grb.parse_card(os.path.join(CARDS, "c1_test13.json"), None, 0)
+    descs = []
+    for k in range(8):
+        d = copy.deepcopy(base) if False else type(base).from_buffer_copy(bytes(base))
+        d.res[2].g_re *= 1.0 + 0.05 * k          # f0(980) production coupling
+        d.regge.a0[0] += 0.002 * k               # Pomeron intercept
+        descs.append(d)
+    E = grb.Engine(desc=descs[0])
+    rb = E.integrate_batch(descs, ncall=1 << 19, iters=3, precision=0.02, seed=11)
+    E.close()
+    sig = []
+    for k, d in enumerate(descs):
+        F = grb.Engine(desc=d)
+        r = F.integrate(ncall=1 << 19, iters=3, precision=0.02, seed=11)
+        F.close()
+        assert abs(r.sigma - rb[k].sigma) <= 1e-10 * r.sigma and r.iterations == rb[k].iterations, (k, r.sigma, rb[k].sigma)
+        sig.append(r.sigma)
+    assert len(set(sig)) == 8 and sig[7] > sig[0]

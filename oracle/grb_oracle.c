@@ -565,8 +565,10 @@ static int bn_build_kin(ost *S, double pt1, double pt2, double phi1, double phi2
     sumP = v4_add(sumP, p[i]);
   }
   if (sumP.e > d->sqrt_s) return 0;
-  const double p1z = solve_pz(m1, m2, pt1, pt2, sumP.z, sumP.e, d->s);
-  const double p2z = -(sumP.z + p1z);
+  double p1z = solve_pz(m1, m2, pt1, pt2, sumP.z, sumP.e, d->s);
+  for (int n = abs(g_pert_pz); n > 0; --n) p1z = nextafter(p1z, g_pert_pz > 0 ? INFINITY : -INFINITY); /* conditioning probe, see b51_build_kin */
+  double p2z = -(sumP.z + p1z);
+  for (int n = abs(g_pert_pz2); n > 0; --n) p2z = nextafter(p2z, g_pert_pz2 > 0 ? INFINITY : -INFINITY);
   if (p1z < 0 || p2z > 0) return 0;
   if (isnan(p1z)) return 0; /* see b51_build_kin */
   p1.z = p1z;

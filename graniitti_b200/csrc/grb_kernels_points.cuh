@@ -40,9 +40,13 @@ __device__ __forceinline__ void store_momenta(double *dst, int64_t stride, const
 // per 2^23 points (profiles/r01_variants.txt): Regge 2.66 -> 1.96 ms and tensor 2xS 6.15 -> 4.60 ms at 256 x 2 (128
 // registers); resonances 36.8 -> 30.4 ms at 128 x 3 (168 registers; 256 x 2 is slower); HELAS yy -> l+ l- is fastest with
 // the full register file (45.5 ms; 48.8 at 128 x 3, 49.6 at 256 x 2)
-__host__ __device__ constexpr int kp_threads(int amp) { return (amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 128 : 256; }
+// Round 2 (profiles/r02_kp_threads_sweep.txt): HELAS at 64 x 4 (same 255 registers, shorter waits at the final barrier:
+// 2.02e8 -> 2.16e8 points/s), tensor 2xS at 128 x 4 (1.77e9 -> 1.90e9)
+__host__ __device__ constexpr int kp_threads(int amp) {
+  return (amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON || amp == AMP_TENSOR_2XS) ? 128 : (amp == AMP_YY_LL ? 64 : 256);
+}
 __host__ __device__ constexpr int kp_minb(int amp) {
-  return (amp == AMP_REGGE || amp == AMP_TENSOR_2XS) ? 2 : ((amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 3 : 1);
+  return amp == AMP_REGGE ? 2 : ((amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 3 : ((amp == AMP_TENSOR_2XS || amp == AMP_YY_LL) ? 4 : 1));
 }
 
 // ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------
@@ -279,6 +283,10 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
 template <int NN, int AMP>
 inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
   int th = kp_threads(AMP);
+  // GRB_KP_THREADS (tuning knob): CTA size of k_points.  The kernel ends with one __syncthreads() (histogram flush); with
+  // few, long-running warps per CTA the fast warps wait there for the slowest one
+  static const int th_env = [] { const char *e = getenv("GRB_KP_THREADS"); return e ? atoi(e) : 0; }();
+  if (th_env >= 32 && th_env <= th && (th_env & 31) == 0) th = th_env;
   if (a.side_launch) th = 128;                                       // (blocks = one CTA per SM, set by the caller)
   else if (th != threads) blocks = blocks * (unsigned)(threads / th);   // same number of resident threads
   if (a.vegas) k_points<NN, true, AMP><<<blocks, th, smem, st>>>(a);

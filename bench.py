@@ -247,7 +247,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": metric_name(wl), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[wl][7], "points_per_step": ppp * nproc},
+            "config": {"workload": WORKLOADS[wl][7], "workload_id": wl},
+            "run": {"points_per_step": ppp * nproc},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nproc, "kind": kind,
                              "sample": f"{args.steps} x {ppp * nproc} synthetic phase-space points through "
                                        f"MProcess::EventWeight, {nproc} processes, in-loop time"},
@@ -425,8 +426,8 @@ def run_ours(args):
         line = {"metric": metric_name(wl), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": descr, "workload_id": wl,
-                           "points_per_step_per_gpu": ncalls, "points_per_step": total_calls, "vegas_bins": bins, "dim": dim,
+                "config": {"workload": descr, "workload_id": wl},     # (identical in both arms; the run's own facts follow)
+                "run": {"points_per_step_per_gpu": ncalls, "points_per_step": total_calls, "vegas_bins": bins, "dim": dim,
                            "grid": grid_source + "; it keeps adapting during the run",
                            "collective": None if world == 1 else ("grb_allreduce (library communicator, NCCL)" if args.comm == "native"
                                                                   else "torch.distributed all_reduce (NCCL) on the engine stream"),

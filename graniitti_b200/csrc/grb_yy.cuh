@@ -180,37 +180,43 @@ __device__ __forceinline__ double yy_ll_core(const NodeKin &in, const v4 &p3, co
   offshell2lightcone(q1, q2, pa, pb);
   const double k1[4] = {q1.e, q1.x, q1.y, q1.z}, k2[4] = {q2.e, q2.x, q2.y, q2.z};
   const double k3[4] = {pa.e, pa.x, pa.y, pa.z}, k4[4] = {pb.e, pb.x, pb.y, pb.z};
-  wf6 w0[2], w1[2], w2[2], w3[2];
-  lc4 v0[2], v1[2];
+  wf6 w2[2], w3[2];
+  lc4 v1[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int hel = 2 * h - 1;
-    helas_vxxxxx(k1, hel, -1, w0[h]);
-    helas_vxxxxx(k2, hel, -1, w1[h]);
+    wf6 w1;
+    helas_vxxxxx(k2, hel, -1, w1);
     helas_fermion<false>(k3, m3, hel, -1, w2[h]);
     helas_fermion<true>(k4, m4, hel, +1, w3[h]);
-    v0[h] = lightcone(w0[h]);
-    v1[h] = lightcone(w1[h]);
+    v1[h] = lightcone(w1);
   }
   double sum = 0.0;
+  // The helicity of the first photon is a real loop (not unrolled) when only |M|^2 is needed: one polarisation vector and
+  // its four off-shell fermion lines are live at a time instead of both sets (register pressure: the kernel runs at 255
+  // registers with local-memory spills).  Same operations in the same order (h0, h2, h3, h1) as the unrolled form.
+#pragma unroll(VEC ? 2 : 1)
+  for (int h0 = 0; h0 < 2; ++h0) {
+    wf6 w0;
+    helas_vxxxxx(k1, 2 * h0 - 1, -1, w0);
+    const lc4 v0 = lightcone(w0);
+    wf6 w4[2], w5[2];
 #pragma unroll
-  for (int h0 = 0; h0 < 2; ++h0)
+    for (int h = 0; h < 2; ++h) {
+      ffv1_2(w2[h], w0, v0, w4[h]);
+      ffv1_1(w3[h], w0, v0, w5[h]);
+    }
 #pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      wf6 w4;
-      ffv1_2(w2[h2], w0[h0], v0[h0], w4);
+    for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-      for (int h3 = 0; h3 < 2; ++h3) {
-        wf6 w5;
-        ffv1_1(w3[h3], w0[h0], v0[h0], w5);
+      for (int h3 = 0; h3 < 2; ++h3)
 #pragma unroll
         for (int h1 = 0; h1 < 2; ++h1) {
-          const cx a = cadd(ffv1_0(w4, w3[h3], v1[h1]), ffv1_0(w2[h2], w5, v1[h1]));
+          const cx a = cadd(ffv1_0(w4[h2], w3[h3], v1[h1]), ffv1_0(w2[h2], w5[h3], v1[h1]));
           sum += a.re * a.re + a.im * a.im;
           if (VEC) hv[((h0 * 2 + h2) * 2 + h3) * 2 + h1] = a;
         }
-      }
-    }
+  }
   // couplings: each diagram carries GC_3^2 (off-shell line) and the vertex -i GC_3 ... |GC_3|^4 = ee^4 overall;
   // GC_3 = -i ee, ee = 2 sqrt(pi/137.03599908) (Parameters_sm.cc:93-101)
   const double amp2 = sum * P.yy_ee4 / 4.0;

@@ -16,7 +16,7 @@ try:
     d = json.loads(open("gpurun_out/${TAG}_bench_$w.json").read().strip().splitlines()[-1])
     r = json.loads(open("gpurun_out/${TAG}_bench_reference_$w.json").read().strip().splitlines()[-1])
     rf = d["roofline"]
-    print("%-4s %.3e pts/s  e2e %.3e  ref-arm %.3e (%d cores)  e2e/ref %.0f  kernel %s frac %.3f launch %.3f ms  acc %.3f" % ("$w", d["value"], d["e2e"]["value"], r["value"], r["cpu_baseline"]["cores"], d["e2e"]["value"] / r["value"], rf["kernel"], rf["frac"], rf["launch_ms_avg"], d["config"]["accepted_fraction"]))
+    print("%-4s %.3e pts/s  e2e %.3e  ref-arm %.3e (%d cores)  e2e/ref %.0f  kernel %s frac %.3f launch %.3f ms  acc %.3f" % ("$w", d["value"], d["e2e"]["value"], r["value"], r["cpu_baseline"]["cores"], d["e2e"]["value"] / r["value"], rf["kernel"], rf["frac"], rf["launch_ms_avg"], d["run"]["accepted_fraction"]))
 except Exception as e:
     print("$w FAILED", e)
 PY

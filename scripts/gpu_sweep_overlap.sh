@@ -8,7 +8,7 @@ for ov in 0 3 2; do for ch in 8388608 4194304 2097152; do
 import json
 try:
     d = json.loads(open("gpurun_out/bench_ov${ov}_$ch.json").read().strip().splitlines()[-1])
-    print("overlap $ov chunk $ch: %.4e pts/s  ms/step %.3f  screen launch_ms %.3f share %.3f sigma %.5f" % (d["value"], d["ms_per_step"], d["roofline"]["launch_ms_avg"], d["roofline"]["kernel_share_of_step"], d["config"]["sigma_last_iteration_ub"]))
+    print("overlap $ov chunk $ch: %.4e pts/s  ms/step %.3f  screen launch_ms %.3f share %.3f sigma %.5f" % (d["value"], d["ms_per_step"], d["roofline"]["launch_ms_avg"], d["roofline"]["kernel_share_of_step"], d["run"]["sigma_last_iteration_ub"]))
 except Exception as e:
     print("FAILED $ov $ch", e); print(open("gpurun_out/bench_ov.err").read()[-800:])
 PY

@@ -25,10 +25,10 @@ def main(key, src, raw, log):
         wp[op] += int(r[iw])
     line = [ln for ln in open(log) if ln.startswith('{"metric"')][-1]
     d = json.loads(line)
-    pts = d["config"]["points_per_step_per_gpu"]
+    pts = d["run"]["points_per_step_per_gpu"]
     rf = d["roofline"]
     if rf["kernel"] == "k_screen":
-        units = pts * d["config"]["accepted_fraction"] * rf["executed_nodes_per_accepted_point"]
+        units = pts * d["run"]["accepted_fraction"] * rf["executed_nodes_per_accepted_point"]
         per_launch_units = units / max(1, round(pts / 8388608 + 0.499))     # one launch per 2^23-point chunk
         unit = "loop node"
     else:

@@ -426,13 +426,13 @@ def run_ours(args):
         line = {"metric": metric_name(wl), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": descr, "workload_id": wl},     # (identical in both arms; the run's own facts follow)
+                "config": {"workload": descr, "workload_id": wl,
+                           "l2": "inputs are generated on the device per step (Philox counters), nothing is re-read across steps; "
+                                 "the per-chunk work list (151 MB) exceeds L2"},
                 "run": {"points_per_step_per_gpu": ncalls, "points_per_step": total_calls, "vegas_bins": bins, "dim": dim,
                            "grid": grid_source + "; it keeps adapting during the run",
                            "collective": None if world == 1 else ("grb_allreduce (library communicator, NCCL)" if args.comm == "native"
                                                                   else "torch.distributed all_reduce (NCCL) on the engine stream"),
-                           "l2": "inputs are generated on the device per step (Philox counters), nothing is re-read "
-                                 "across steps; the per-chunk work list (151 MB) exceeds L2",
                            "timing": "CUDA events on the engine stream around K steps, max over ranks",
                            "accepted_fraction": p_acc, "sigma_last_iteration_ub": sigma * 1e6},
                 "wall_ms_per_step": wall_ms / args.steps,

@@ -406,7 +406,11 @@ def run_ours(args):
                 "executed_nodes_per_accepted_point": n_nodes, "flops_per_point_model": f_point,
                 "whole_path_tflops": f_point * value / 1e12,
                 "kernel_share_of_step": kernel_ms / state["ms_kernels"] if state["ms_kernels"] else None,
-                "launch_ms_avg": kernel_ms / kernel_n, "traffic": None}
+                "launch_ms_avg": kernel_ms / kernel_n, "traffic": None,
+                "frac_note": "frac = algorithmic flops (SURVEY 8d convention: transcendental = 20 flop, op-counted on the oracle) / "
+                             "self-measured DFMA peak; the device needs fewer executed flops than the convention counts (table-driven "
+                             "log / exp / sincos, merged phases), so read it together with executed_frac (SASS flops / peak) and "
+                             "fp64_slot_frac (fp64 pipe slots in use = what is left for this instruction stream)"}
         if mix:   # executed (not algorithmic) fp64 work of the same kernel from the committed ncu opcode mix
             units = n_items * n_nodes if pom else pts_rank
             ex_flops = units * (2 * mix["dfma"] + mix["dmul"] + mix["dadd"])

@@ -486,12 +486,12 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
     if ((ce = cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
     if (desc->lipsdim > 8 && (ce = cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
   }
-  if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 4)) != cudaSuccess) return fail("cudaMalloc", ce);
+  if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 8)) != cudaSuccess) return fail("cudaMalloc", ce);   // [0..2] work list, [4] k_points tiles
   // (+ 2 x 64 doubles: the per-rank maxima slots of grb_allreduce)
   if ((ce = cudaMalloc(&e->d_acc, sizeof(grb_accum) + 128 * sizeof(double))) != cudaSuccess) return fail("cudaMalloc", ce);
   if ((ce = cudaMalloc(&e->d_xmat, sizeof(double) * GRB_MAX_BINS * GRB_MAX_DIM)) != cudaSuccess) return fail("cudaMalloc", ce);
   cudaMemsetAsync(e->d_acc, 0, sizeof(grb_accum), e->stream);
-  cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int) * 4, e->stream);
+  cudaMemsetAsync(e->d_item_count, 0, sizeof(unsigned int) * 8, e->stream);
   *out = e;
   return GRB_OK;
 }
@@ -684,7 +684,8 @@ static int eval_impl(grb_engine *e, int64_t n, const double *u, int dim, const d
     a.w = dw + off; a.flags = df + off; a.dump = dd ? dd + off : nullptr;
     a.items = e->d_items; a.item_idx = e->d_item_idx; a.item_bins = e->d_item_bins; a.item_bins_hi = e->d_item_bins_hi; a.item_count = e->d_item_count;
     a.item_cap = e->chunk; a.acc = e->d_acc;
-    if (e->desc.screening) CK(cudaMemsetAsync(e->d_item_count, 0, 4 * sizeof(unsigned int), e->stream));
+    a.tile_count = e->d_item_count + 4;
+    CK(cudaMemsetAsync(e->d_item_count, 0, 8 * sizeof(unsigned int), e->stream));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, e->stream);
     if (e->desc.screening) {
       CK(cudaEventRecord(next_event(e), e->stream));
@@ -755,7 +756,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     CK(cudaMalloc(&e->d_item_idx2, sizeof(int32_t) * e->chunk));
     CK(cudaMalloc(&e->d_item_bins2, sizeof(uint64_t) * e->chunk));
     if (e->desc.lipsdim > 8) CK(cudaMalloc(&e->d_item_bins_hi2, sizeof(uint64_t) * e->chunk));
-    CK(cudaMalloc(&e->d_item_count2, sizeof(unsigned int) * 4));
+    CK(cudaMalloc(&e->d_item_count2, sizeof(unsigned int) * 8));
     CK(cudaStreamCreateWithFlags(&e->stream_pts, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
       CK(cudaEventCreateWithFlags(&e->ev_pts[k], cudaEventDisableTiming));
@@ -786,7 +787,8 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
       a.screen_ctas = e->overlap;
       if (chunk_no >= 2) CK(cudaStreamWaitEvent(sp, e->ev_free[b], 0));   // k_finish of chunk c-2 has released this list
     }
-    if (e->desc.screening) CK(cudaMemsetAsync(a.item_count, 0, 4 * sizeof(unsigned int), sp));
+    a.tile_count = a.item_count + 4;
+    CK(cudaMemsetAsync(a.item_count, 0, 8 * sizeof(unsigned int), sp));
     e->last_launches += launch_points(a, e->desc.n_nodes, e->dproc.amp_kind, e->sm_count, sp);
     if (overlap) {
       CK(cudaEventRecord(e->ev_pts[b], sp));

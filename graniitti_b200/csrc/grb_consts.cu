@@ -33,14 +33,16 @@ cudaError_t upload_loop(const DevLoop &l, cudaStream_t st) {
 template <int AMP>
 void launch_points_amp(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st);
 
-int launch_points(const PointArgs &a, int n_nodes, int amp_kind, int sm_count, cudaStream_t st) {
+int launch_points(const PointArgs &a_in, int n_nodes, int amp_kind, int sm_count, cudaStream_t st) {
+  PointArgs a = a_in;
+  a.sm_count  = sm_count;
   const int     threads = 256;
   int64_t       blocks  = (a.n + threads - 1) / threads;
   const int64_t cap     = (int64_t)sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (a.side_launch) blocks = sm_count;
   if (blocks < 1) blocks = 1;
-  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * a.dim : 0;   // fm, f2m [bins][lipsdim] (hist_add indexing)
   switch (amp_kind) {
     case AMP_TENSOR_2XS: launch_points_amp<AMP_TENSOR_2XS>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_RES: launch_points_amp<AMP_REGGE_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;

@@ -136,6 +136,7 @@ struct PointArgs {
   uint64_t *    item_bins;
   uint64_t *    item_bins_hi;  // VEGAS bins of dimensions 8..15 (four-leg <C> class: 14 dimensions)
   unsigned int *item_count;
+  unsigned int *tile_count;    // k_points' tile counter (one unsigned, zeroed per launch)
   int64_t       item_cap;
   // accumulators (device)
   grb_accum *acc;
@@ -149,6 +150,7 @@ struct PointArgs {
   // launch shaping for the k_points / k_screen overlap (grb_api.cu): k_points beside a running k_screen takes one
   // 128-thread CTA per SM; k_screen then leaves a quarter of the register file free (3 of its 4 resident CTAs per SM)
   int side_launch, screen_ctas;
+  int sm_count;   // (host side: launch sizing)
 };
 
 // launchers implemented in grb_kernels.cu

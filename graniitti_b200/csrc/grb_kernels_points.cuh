@@ -91,9 +91,18 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
   const int      nb  = a.bins * dim;
   if (VEGAS) hist_clear(nb);
   ThreadSums ts;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < a.n; base += stride) {
-    const int64_t idx    = base + threadIdx.x;
+  // Warps take tiles of 32 consecutive points from a global counter (a.tile_count, zeroed per launch) instead of a static
+  // stride: the per-point cost varies (rejections, Breit-Wigner retries, light-cone iterations), and with a static split the
+  // fast warps of a CTA wait at the final barrier for the slowest one (18-25 % of all stall samples for the heavy Born
+  // amplitudes, profiles/r02_k_points_c1_opcode_mix.txt); now all warps run out of work within one tile of each other.
+  const int     lane_id = threadIdx.x & 31;
+  const int64_t ntiles  = (a.n + 31) >> 5;
+  for (;;) {
+    unsigned tile = 0;
+    if (lane_id == 0) tile = atomicAdd(a.tile_count, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if ((int64_t)tile >= ntiles) break;
+    const int64_t idx    = ((int64_t)tile << 5) + lane_id;
     const bool    active = idx < a.n;
     constexpr int UD = (AMP == AMP_REGGE_ME6) ? 16 : 10;  // coordinates: <F> 6 (+2 N*), <C> 8 (two legs) / 14 (four legs) (+2 N*)
     double        u[UD] = {};
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
         veto = veto_cuts<NN>(S);
       }
     }
+    __syncwarp();   // (the amplitude starts with the lanes of the warp together, whatever the kinematics and the cuts did)
     const bool valid = active && kin && fid && veto && !overrun;
     double     W = 0.0;
     bool       amp_ok = true;
@@ -273,6 +283,11 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
         }
       }
     }
+    // Reconverge before the next tile.  Without this the lanes that leave the compare-and-swap loops of the shared-memory
+    // histogram one after the other stay split, and the warp walks the next point's kinematics and amplitude in several
+    // partial passes (ncu: 15.7 active threads per instruction for HELAS gamma gamma -> l+ l- where 24 are accepted;
+    // profiles/r02_kp_probe2.txt: 2.6e8 -> 6.2e8 points/s for that workload, 3.8e8 -> 5.8e8 for the resonances).
+    __syncwarp();
   }
   flush_sums(ts, a.acc);
   if (VEGAS) hist_flush(nb, dim, a.acc);
@@ -288,7 +303,16 @@ inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, si
   static const int th_env = [] { const char *e = getenv("GRB_KP_THREADS"); return e ? atoi(e) : 0; }();
   if (th_env >= 32 && th_env <= th && (th_env & 31) == 0) th = th_env;
   if (a.side_launch) th = 128;                                       // (blocks = one CTA per SM, set by the caller)
-  else if (th != threads) blocks = blocks * (unsigned)(threads / th);   // same number of resident threads
+  else {
+    // persistent grid: the CTAs that are resident at once, each taking tiles until the counter runs out
+    int occ = 0;
+    const cudaError_t rc = a.vegas ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_points<NN, true, AMP>, th, smem)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_points<NN, false, AMP>, th, 0);
+    const unsigned sms = a.sm_count > 0 ? (unsigned)a.sm_count : 1u;
+    const int64_t  want = (a.n + th - 1) / th;
+    if (rc == cudaSuccess && occ > 0) blocks = (unsigned)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);
+    else if (th != threads) blocks = blocks * (unsigned)(threads / th);
+  }
   if (a.vegas) k_points<NN, true, AMP><<<blocks, th, smem, st>>>(a);
   else k_points<NN, false, AMP><<<blocks, th, 0, st>>>(a);
 }

@@ -160,7 +160,7 @@ static void launch_screen_t(const PointArgs &a, int sm_count, cudaStream_t st) {
     k_screen<MINB, AMP, FF><<<sm_count * occ, 128, pad, st>>>(a);
   } else
     k_screen<MINB, AMP, FF><<<sm_count * ((a.screen_ctas > 0 && a.screen_ctas < MINB) ? a.screen_ctas : MINB), 128, 0, st>>>(a);  // persistent: exactly the resident CTAs
-  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * GRB_MAX_DIM : 0;
+  const size_t smem = a.vegas ? sizeof(double) * 2 * a.bins * a.dim : 0;
   if (a.vegas) k_finish<true><<<sm_count * 4, 256, smem, st>>>(a);
   else k_finish<false><<<sm_count * 4, 256, 0, st>>>(a);
 }

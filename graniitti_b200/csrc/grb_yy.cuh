@@ -10,6 +10,10 @@
 #pragma once
 #include "grb_res.cuh"
 
+#ifndef GRB_YY_INLINE
+#define GRB_YY_INLINE static __noinline__
+#endif
+
 namespace grb {
 
 struct wf6 {  // HELAS wavefunction: [0..1] momentum, [2..5] components
@@ -104,7 +108,9 @@ __device__ __forceinline__ lc4 lightcone(const wf6 &V) {
   return r;
 }
 // FFV1_0 (HelAmps_sm.cc:678-687) without the coupling: F1 (gamma.V) F2
-__device__ __forceinline__ cx ffv1_0(const wf6 &F1, const wf6 &F2, const lc4 &v) {
+// (GRB_YY_INLINE: 32 inlined copies of this and 8 of FFV1_1 / FFV1_2 made a hot path of 8 900 instructions = 139 KB per point,
+// far beyond the instruction cache: 42 % of the stall samples were instruction fetches; as real functions the hot code shrinks)
+__device__ GRB_YY_INLINE cx ffv1_0(const wf6 &F1, const wf6 &F2, const lc4 &v) {
   cx t = cmul(F1.c[2], cadd(cmul(F2.c[4], v.p), cmul(F2.c[5], v.c)));
   t = cadd(t, cmul(F1.c[3], cadd(cmul(F2.c[4], v.d), cmul(F2.c[5], v.m))));
   t = cadd(t, cmul(F1.c[4], csub(cmul(F2.c[2], v.m), cmul(F2.c[3], v.c))));
@@ -113,7 +119,7 @@ __device__ __forceinline__ cx ffv1_0(const wf6 &F1, const wf6 &F2, const lc4 &v)
 }
 // FFV1_2 / FFV1_1 (HelAmps_sm.cc:435-482, :930-977) with zero propagator mass (AMP_MG5_yy_ll.cc:247-248),
 // without the coupling: i (gamma.P)(gamma.V) F / P^2 in light-cone form
-__device__ __forceinline__ void ffv1_2(const wf6 &F1, const wf6 &V3, const lc4 &v, wf6 &F2) {
+__device__ GRB_YY_INLINE void ffv1_2(const wf6 &F1, const wf6 &V3, const lc4 &v, wf6 &F2) {
   F2.c[0] = cadd(F1.c[0], V3.c[0]); F2.c[1] = cadd(F1.c[1], V3.c[1]);
   const double P0 = -F2.c[0].re, P1 = -F2.c[1].re, P2 = -F2.c[1].im, P3 = -F2.c[0].im;
   const double inv = 1.0 / ((P0 * P0) - (P1 * P1) - (P2 * P2) - (P3 * P3));
@@ -126,7 +132,7 @@ __device__ __forceinline__ void ffv1_2(const wf6 &F1, const wf6 &V3, const lc4 &
   F2.c[4] = cscale(ci(csub(cscale(c, Pp), cmul(Pd, e))), inv);
   F2.c[5] = cscale(ci(csub(cmul(Pc, c), cscale(e, Pm))), inv);
 }
-__device__ __forceinline__ void ffv1_1(const wf6 &F2, const wf6 &V3, const lc4 &v, wf6 &F1) {
+__device__ GRB_YY_INLINE void ffv1_1(const wf6 &F2, const wf6 &V3, const lc4 &v, wf6 &F1) {
   F1.c[0] = cadd(F2.c[0], V3.c[0]); F1.c[1] = cadd(F2.c[1], V3.c[1]);
   const double P0 = -F1.c[0].re, P1 = -F1.c[1].re, P2 = -F1.c[1].im, P3 = -F1.c[0].im;
   const double inv = 1.0 / ((P0 * P0) - (P1 * P1) - (P2 * P2) - (P3 * P3));

@@ -667,8 +667,11 @@ static int eval_impl(grb_engine *e, int64_t n, const double *u, int dim, const d
   const int64_t step   = staged ? std::min<int64_t>(e->chunk, e->host_slice) : e->chunk;
   const size_t  pitch  = sizeof(double) * (size_t)n;
   CK(cudaEventRecord(e->ev0, e->stream));
-  for (int64_t off = 0; off < n; off += step) {
-    const int64_t len = std::min<int64_t>(step, n - off);
+  // The first copy-in cannot overlap anything: the pipeline is started with a quarter and a half slice
+  int64_t len = 0;
+  int     k_slice = 0;
+  for (int64_t off = 0; off < n; off += len, ++k_slice) {
+    len = std::min<int64_t>((!dev_in && k_slice < 2 && step >= 4096) ? step >> (2 - k_slice) : step, n - off);
     if (!dev_in) {
       CK(cudaMemcpy2DAsync((void *)(du + off), pitch, u + off, pitch, sizeof(double) * len, dim, cudaMemcpyHostToDevice, e->stream_in));
       if (dtape) CK(cudaMemcpy2DAsync((void *)(dt + off), pitch, tape + off, pitch, sizeof(double) * len, dtape, cudaMemcpyHostToDevice, e->stream_in));

@@ -1,5 +1,6 @@
 """Probe: k_points in VEGAS mode (Philox + grid map + histogram accumulation) vs parity mode (device-resident coordinates,
-no accumulation) on the same point distribution: what does the accumulation cost?"""
+no accumulation) on the same point distribution.  (Round 2: the gap this probe showed -- 2.2e8 vs 8.8e8 points/s for
+yy -> l+ l- -- was the warp staying split after the histogram's compare-and-swap loops; profiles/r02_kp_probe2.txt.)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,6 +11,9 @@ N = 1 << 23
 for wl in sys.argv[1:] or ["c4", "c1", "c3", "c5", "c1t"]:
     card, _, process, pom, ntape = bench.WORKLOADS[wl][:5]
     E = g.Engine(card=os.path.join(bench.CARDS, card), process=process, pomloop=pom)
+    if E.desc.screening:
+        msa = np.load(bench.MSA)
+        E.set_eikonal(msa[0], msa[1], msa[2])
     xmat, _ = bench.workload_grid(wl, 128, E.desc.lipsdim)
     for _ in range(2):
         a = E.vegas_iterate(xmat, 0, N, 5, 1)

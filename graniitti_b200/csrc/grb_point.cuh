@@ -1388,8 +1388,23 @@ __device__ __forceinline__ double screened_amp2_regge_fast_C(const LoopInv &L, c
 // the amplitude of tensor_me4_2xS() with table-driven log / exp / sincos and ALL its quotients -- two 1/(16 s s), four
 // F_M, two meson propagators, ten inside the two Kelly form factors F1(t) -- multiplied up into one division:
 //   R = pre (Nt Du + Nu Dt) / (Dt Du D_F1),  term_x = E'_x R_x num_x / [16 s s (1 - 2 qa)(1 - 2 qb) den_x].
+// The vertex algebra runs on Lorentz products instead of the reference's component vectors: with q1 = p_a - p_1 (pomeron 1),
+// P1 = p_a + p_1, P2 = p_b + p_2 and the central legs p3, p4 (fixed over the loop in the <F> class)
+//   p_t = q1 - p3, p_u = p4 - q1, K_ta = q1 - 2 p3, K_tb = q1 + p4 - p3, K_ua = 2 p4 - q1, K_ub = p4 - p3 - q1,
+// so every K^2, P.K, p_t^2, p_u^2 is a combination of t1 = q1^2, the ten products q1.p3, q1.p4, P1.p3, P1.p4, P2.p3, P2.p4,
+// P1.q1, P2.q1, P1^2, P2^2 (fused dot products: 4 instructions each instead of 4 + 7 for a component vector and its M2) and
+// the per-point constants m3^2, m4^2, p3.p4.  The F_M arguments are (p_t + p3)^2 = (p4 - p_u)^2 = q1^2 and (p4 - p_t)^2 =
+// (p_u + p3)^2 = (p3 + p4 - q1)^2 (NOT replaced by t2: the solved kinematics conserves momentum only to O(1e-11), see
+// tensor_me4_2xS).  None of these regroupings cancels more than the reference's own forms do (the products are taken with
+// the small components of q1 directly, never as differences of beam-sized products); the result differs from
+// tensor_me4_2xS by ~1e-13 relative (test_fast_node_equals_checked_node), the polynomial form factors are in Horner form.
+// 220 -> 170 fp64 instructions for the vertex algebra.
+struct TensorInv { double m3sq, m4sq, p3p4; };
+__device__ __forceinline__ double fdot(double ae, double ax, double ay, double az, const v4 &b) {  // a.b, fused
+  return fma(ae, b.e, -fma(ax, b.x, fma(ay, b.y, az * b.z)));
+}
 template <bool SAME>
-__device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
+__device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const TensorInv &TI, const PzInv &pzi, double ktx, double kty, bool &valid, cx &A) {
   const DevProc &P = c_proc;
   const double n1x = L.p1x - ktx, n1y = L.p1y - kty, n2x = L.p2x + ktx, n2y = L.p2y + kty;
   const double Xx = -(n1x + n2x), Xy = -(n1y + n2y);
@@ -1418,53 +1433,60 @@ __device__ __forceinline__ bool tensor_node_fast(const LoopInv &L, const PzInv &
   const double t2 = pow2(P.pb2e - e2) - (a2s + pow2(P.pb2z - p2z));
   valid = valid & !(t1 > 0);
   valid = valid & !(t2 > 0);
-  // amplitude (tensor_me4_2xS): vertex vectors
-  v4 P1, P2, pt, pu;
-  P1.x = n1x; P1.y = n1y; P1.z = p1z + P.pb1z; P1.e = e1 + P.pb1e;
-  P2.x = n2x; P2.y = n2y; P2.z = p2z + P.pb2z; P2.e = e2 + P.pb2e;
-  pt.x = (0.0 - n1x) - p3.x; pt.y = (0.0 - n1y) - p3.y; pt.z = (P.pb1z - p1z) - p3.z; pt.e = (P.pb1e - e1) - p3.e;
-  pu.x = (p4.x - 0.0) + n1x; pu.y = (p4.y - 0.0) + n1y; pu.z = (p4.z - P.pb1z) + p1z; pu.e = (p4.e - P.pb1e) + e1;
-  v4 Kta, Ktb, Kua, Kub;
-  Kta.x = pt.x - p3.x; Kta.y = pt.y - p3.y; Kta.z = pt.z - p3.z; Kta.e = pt.e - p3.e;
-  Ktb.x = p4.x + pt.x; Ktb.y = p4.y + pt.y; Ktb.z = p4.z + pt.z; Ktb.e = p4.e + pt.e;
-  Kua.x = p4.x + pu.x; Kua.y = p4.y + pu.y; Kua.z = p4.z + pu.z; Kua.e = p4.e + pu.e;
-  Kub.x = pu.x - p3.x; Kub.y = pu.y - p3.y; Kub.z = pu.z - p3.z; Kub.e = pu.e - p3.e;
-  const double P1sq = m2_of(P1), P2sq = m2_of(P2);
-  const double d1t = mdot(P1, Kta), d2t = mdot(P2, Ktb), d1u = mdot(P1, Kua), d2u = mdot(P2, Kub);
-  const double Rt = (2.0 * d1t * d1t - 0.5 * m2_of(Kta) * P1sq) * (2.0 * d2t * d2t - 0.5 * m2_of(Ktb) * P2sq);
-  const double Ru = (2.0 * d1u * d1u - 0.5 * m2_of(Kua) * P1sq) * (2.0 * d2u * d2u - 0.5 * m2_of(Kub) * P2sq);
-  const double pt2v = m2_of(pt), pu2v = m2_of(pu);
-  const double al1 = P.tp_delta + P.tp_ap * t1, al2 = P.tp_delta + P.tp_ap * t2;
+  // Lorentz products (q1 = (-n1x, -n1y, q1z, q1e); P1 = (n1x, n1y, P1z, P1e); P2 = (n2x, n2y, P2z, P2e)).
+  // u channel: the reference forms p_u = (p4 - p_a) + p_1, whose first difference is rounded at the beam scale (half an ulp
+  // of 6500 GeV = 4.5e-13 GeV in z and E).  Multiplied by beam-sized partners (P.K ~ 1e4 GeV^2, q1e up to 100 GeV) that
+  // deterministic offset reaches 1e-11 ... 5e-10 of the u-channel term: it is part of the reference's result and is kept --
+  // the u channel takes its own pomeron momentum q1u = p4 - p_u built in the reference's order (t channel: p_a - p_1 is exact).
+  const double P1z = p1z + P.pb1z, P1e = e1 + P.pb1e, P2z = p2z + P.pb2z, P2e = e2 + P.pb2e;
+  const double quz = p4.z - ((p4.z - P.pb1z) + p1z), que = p4.e - ((p4.e - P.pb1e) + e1);
+  const double tu  = fma(que, que, -fma(quz, quz, a1s));
+  const double q1p3 = fdot(q1e, -n1x, -n1y, q1z, p3), q1p4 = fdot(q1e, -n1x, -n1y, q1z, p4);
+  const double qup3 = fdot(que, -n1x, -n1y, quz, p3), qup4 = fdot(que, -n1x, -n1y, quz, p4);
+  const double P1p3 = fdot(P1e, n1x, n1y, P1z, p3), P1p4 = fdot(P1e, n1x, n1y, P1z, p4);
+  const double P2p3 = fdot(P2e, n2x, n2y, P2z, p3), P2p4 = fdot(P2e, n2x, n2y, P2z, p4);
+  const double P1q1 = fma(P1e, q1e, -fma(P1z, q1z, -a1s)), P1qu = fma(P1e, que, -fma(P1z, quz, -a1s));
+  const double nn   = fma(n2x, n1x, n2y * n1y);
+  const double P2q1 = fma(P2e, q1e, fma(-P2z, q1z, nn)), P2qu = fma(P2e, que, fma(-P2z, quz, nn));
+  const double hP1 = 0.5 * fma(P1e, P1e, -fma(P1z, P1z, a1s)), hP2 = 0.5 * fma(P2e, P2e, -fma(P2z, P2z, a2s));  // P^2 / 2
+  const double m34 = TI.m3sq + TI.m4sq, t34 = t1 + m34, u34 = tu + m34;
+  const double pt2v = fma(-2.0, q1p3, t1 + TI.m3sq), pu2v = fma(-2.0, qup4, tu + TI.m4sq);                        // t^, u^
+  const double Kta2 = fma(-2.0, q1p3, fma(3.0, TI.m3sq, pt2v)), Kua2 = fma(-2.0, qup4, fma(3.0, TI.m4sq, pu2v));
+  const double Ktb2 = fma(2.0, q1p4 - q1p3, fma(-2.0, TI.p3p4, t34)), Kub2 = fma(-2.0, qup4 - qup3, fma(-2.0, TI.p3p4, u34));
+  // (p3 + p4 - q)^2: pomeron 2 at the meson vertices
+  const double qbt = fma(-2.0, q1p3 + q1p4, fma(2.0, TI.p3p4, t34)), qbu = fma(-2.0, qup3 + qup4, fma(2.0, TI.p3p4, u34));
+  const double d1t = fma(-2.0, P1p3, P1q1), d1u = fma(2.0, P1p4, -P1qu);
+  const double dP2 = P2p4 - P2p3, d2t = dP2 + P2q1, d2u = dP2 - P2qu;
+  const double Rt = fma(2.0 * d1t, d1t, -(Kta2 * hP1)) * fma(2.0 * d2t, d2t, -(Ktb2 * hP2));
+  const double Ru = fma(2.0 * d1u, d1u, -(Kua2 * hP1)) * fma(2.0 * d2u, d2u, -(Kub2 * hP2));
+  const double al1 = fma(P.tp_ap, t1, P.tp_delta), al2 = fma(P.tp_ap, t2, P.tp_delta);
   key = min(min(key, fast_key(ss13)), min(min(fast_key(ss24), fast_key(ss14)), fast_key(ss23)));
   const double L13 = fast_log_core(ss13), L24 = fast_log_core(ss24), L14 = fast_log_core(ss14), L23 = fast_log_core(ss23);
-  const double xt = al1 * (L13 + P.tp_ln_ap) + al2 * (L24 + P.tp_ln_ap), xu = al1 * (L14 + P.tp_ln_ap) + al2 * (L23 + P.tp_ln_ap);
+  const double xt = fma(al1, L13 + P.tp_ln_ap, al2 * (L24 + P.tp_ln_ap)), xu = fma(al1, L14 + P.tp_ln_ap, al2 * (L23 + P.tp_ln_ap));
   const double Et = fast_exp_core(xt), Eu = fast_exp_core(xu);
-  const double qa_t = m2_of(pt.x + p3.x, pt.y + p3.y, pt.z + p3.z, pt.e + p3.e);
-  const double qb_t = m2_of(p4.x - pt.x, p4.y - pt.y, p4.z - pt.z, p4.e - pt.e);
-  const double qa_u = m2_of(p4.x - pu.x, p4.y - pu.y, p4.z - pu.z, p4.e - pu.e);
-  const double qb_u = m2_of(pu.x + p3.x, pu.y + p3.y, pu.z + p3.z, pu.e + p3.e);
   double nt, dt, nu, du;
   meson_G_nd(pt2v, nt, dt);
   meson_G_nd(pu2v, nu, du);
-  const double Nt = Et * Rt * nt, Dt = (16.0 * ss13 * ss24) * ((1.0 - 2.0 * qa_t) * (1.0 - 2.0 * qb_t)) * dt;
-  const double Nu = Eu * Ru * nu, Du = (16.0 * ss14 * ss23) * ((1.0 - 2.0 * qa_u) * (1.0 - 2.0 * qb_u)) * du;
+  // term_x = E_x R_x n_x / (16 s s g_x d_x), g_x = (1 - 2 q^2)(1 - 2 qb_x): F_M with Lambda^2 = 0.5 at both meson vertices
+  const double Nt = Et * Rt * nt, Dt = (ss13 * ss24) * (fma(-2.0, t1, 1.0) * fma(-2.0, qbt, 1.0)) * dt;
+  const double Nu = Eu * Ru * nu, Du = (ss14 * ss23) * (fma(-2.0, tu, 1.0) * fma(-2.0, qbu, 1.0)) * du;
   // F1(t1) F1(t2) as one rational function (Kelly) or dipole (MForm.cc:542-645)
   const double inv4mp2 = 1.0 / P.four_mp2;
   const double tau1 = fabs(t1) * inv4mp2, tau2 = fabs(t2) * inv4mp2;
   double       nF, dF;
   if (P.em_kelly) {
-    const double nE1 = 1.0 - 0.24 * tau1, dE1 = 1.0 + 10.98 * tau1 + 12.82 * (tau1 * tau1) + 21.97 * (tau1 * (tau1 * tau1));
-    const double nM1 = 2.792847337 * (1.0 + 0.12 * tau1), dM1 = 1.0 + 10.97 * tau1 + 18.86 * (tau1 * tau1) + 6.55 * (tau1 * (tau1 * tau1));
-    const double nE2 = 1.0 - 0.24 * tau2, dE2 = 1.0 + 10.98 * tau2 + 12.82 * (tau2 * tau2) + 21.97 * (tau2 * (tau2 * tau2));
-    const double nM2 = 2.792847337 * (1.0 + 0.12 * tau2), dM2 = 1.0 + 10.97 * tau2 + 18.86 * (tau2 * tau2) + 6.55 * (tau2 * (tau2 * tau2));
-    nF = (nE1 * dM1 + tau1 * nM1 * dE1) * (nE2 * dM2 + tau2 * nM2 * dE2);
+    const double dE1 = fma(fma(fma(21.97, tau1, 12.82), tau1, 10.98), tau1, 1.0), dM1 = fma(fma(fma(6.55, tau1, 18.86), tau1, 10.97), tau1, 1.0);
+    const double dE2 = fma(fma(fma(21.97, tau2, 12.82), tau2, 10.98), tau2, 1.0), dM2 = fma(fma(fma(6.55, tau2, 18.86), tau2, 10.97), tau2, 1.0);
+    const double nE1 = fma(-0.24, tau1, 1.0), nM1 = fma(2.792847337 * 0.12, tau1, 2.792847337);
+    const double nE2 = fma(-0.24, tau2, 1.0), nM2 = fma(2.792847337 * 0.12, tau2, 2.792847337);
+    nF = fma(nE1, dM1, (tau1 * nM1) * dE1) * fma(nE2, dM2, (tau2 * nM2) * dE2);
     dF = (dE1 * dM1 * (tau1 + 1.0)) * (dE2 * dM2 * (tau2 + 1.0));
   } else {
     const double g1 = pow2(1.0 + fabs(t1) / 0.71), g2 = pow2(1.0 + fabs(t2) / 0.71);   // GM = mu / g, GE = 1 / g
-    nF = (1.0 + tau1 * 2.792847337) * (1.0 + tau2 * 2.792847337);
+    nF = fma(tau1, 2.792847337, 1.0) * fma(tau2, 2.792847337, 1.0);
     dF = (g1 * (tau1 + 1.0)) * (g2 * (tau2 + 1.0));
   }
-  const double num = P.tp_coupling * nF * fma(Nt, Du, Nu * Dt), den = (Dt * Du) * dF;
+  const double num = (0.0625 * P.tp_coupling) * nF * fma(Nt, Du, Nu * Dt), den = (Dt * Du) * dF;
   const double R   = div_fast_core(num, den);
   const double ph  = P.tp_phase * (al1 + al2);
   const bool redo = !(fast_key_ok(key) & dom & (fabs(xt) < 690.0) & (fabs(xu) < 690.0) & div_fast_ok(num, R) & (fabs(ph) < 1.0e5));
@@ -1480,6 +1502,8 @@ __device__ __forceinline__ double screened_amp2_tensor_fast(const LoopInv &L, co
   PzConst        pc;
   pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
   const PzInv pzi = make_pz_inv(L.m1, L.m2, pc, SAME);
+  TensorInv   TI;
+  TI.m3sq = m2_of(L.p3); TI.m4sq = m2_of(L.p4); TI.p3p4 = mdot(L.p3, L.p4);
   double Ire = 0.0, Iim = 0.0;
   for (int i = 0; i < Q.nphi_nodes; ++i) {
     const double cp = Q.cphi[i], sp = Q.sphi[i], wi = Q.wphi[i];
@@ -1488,7 +1512,7 @@ __device__ __forceinline__ double screened_amp2_tensor_fast(const LoopInv &L, co
       const double kt = Q.kt[j];
       bool         valid;
       cx           A;
-      if (__builtin_expect(tensor_node_fast<SAME>(L, pzi, kt * cp, kt * sp, valid, A), 0)) {
+      if (__builtin_expect(tensor_node_fast<SAME>(L, TI, pzi, kt * cp, kt * sp, valid, A), 0)) {
         NodeKin in;
         valid = loop_node<SAME>(L, pc, kt * cp, kt * sp, in);
         if (valid) A = tensor_me4_2xS(in, L.p3, L.p4);

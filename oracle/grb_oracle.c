@@ -524,13 +524,19 @@ static int loop_kinematics(ost *S, double p1px, double p1py, double p2px, double
 /* ---- <C> phase-space class: MContinuum, 2 -> N direct (restated for N = 4, two central legs) ---------------------- */
 
 /* reference src/MContinuum.cc:438-538 BLinearSystem: p = A b with b0 = q0 - (p1+p2), b_i = -q_{i-1} - (p1+p2); A is the
- * inverse of the ladder's linear system (:480-516, tabulated there for Kf = 2..8; Kf = 2 and 4 restated).  The loop adds
+ * inverse of the ladder's linear system (:480-516, tabulated there for Kf = 2..8; Kf = 2, 4 and 6 restated).  The loop adds
  * b[j] * A[i][j] for every j (zero entries add signed zeros). */
 static const double o_blin2[2][2] = {{1.0 / 2.0, 0.0}, {0.0, 1.0 / 2.0}};
 static const double o_blin4[4][4] = {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
                                      {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0},
                                      {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0},
                                      {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}};
+static const double o_blin6[6][6] = {{4.0 / 3.0, 1.0 / 2.0, -2.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0},
+                                     {5.0 / 6.0, 1.0 / 1.0, -2.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0},
+                                     {1.0 / 3.0, 1.0 / 2.0, 1.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0},
+                                     {-1.0 / 6.0, 0.0, 1.0 / 3.0, 1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0},
+                                     {-2.0 / 3.0, -1.0 / 2.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, -1.0 / 6.0},
+                                     {-7.0 / 6.0, -1.0 / 1.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, 5.0 / 6.0}};
 static void blinear(int Kf, const v4 *q, v4 p1f, v4 p2f, v4 *p) {
   const v4 w = v4_add(p1f, p2f);
   v4 b[8];
@@ -539,7 +545,7 @@ static void blinear(int Kf, const v4 *q, v4 p1f, v4 p2f, v4 *p) {
   for (int i = 0; i < Kf; ++i) {
     v4 acc = {0, 0, 0, 0};
     for (int j = 0; j < Kf; ++j) {
-      const double a = (Kf == 2) ? o_blin2[i][j] : o_blin4[i][j];
+      const double a = (Kf == 2) ? o_blin2[i][j] : (Kf == 4 ? o_blin4[i][j] : o_blin6[i][j]);
       acc = v4_add(acc, (v4){b[j].x * a, b[j].y * a, b[j].z * a, b[j].e * a});
     }
     p[i] = acc;
@@ -1757,6 +1763,56 @@ static cx regge_me6(ost *S) {
   S->nhamp   = 1;
   return A;
 }
+/* reference src/MRegge.cc:560-633 ME8: the 2 -> 8 ladder summed over the 720 orderings (a, b, c, d, e, f) of the six central
+ * legs in the order of math::Permutations; the scalars are the ones the reference reads (tt_cd = tt_xy[b][c] and
+ * tt_de = tt_xy[c][d] are two-leg sums, and there is no form factor on tt_cd: restated as written) */
+static cx regge_me8(ost *S) {
+  const grb_process_desc *d = S->d;
+  const double M2_A = pow2(d->nodes[0].mass), M2_B = pow2(d->nodes[2].mass), M2_C = pow2(d->nodes[4].mass);
+  double FF_A, FF_B;
+  pom_pom_proton_vertex(S, &FF_A, &FF_B);
+  const double gpp_P = d->regge.c[0] / d->soft.gN_P;
+  cx  A = {0, 0};
+  int set[6] = {3, 4, 5, 6, 7, 8};
+  for (;;) {
+    const int a = set[0], b = set[1], c = set[2], dd = set[3], e = set[4], f = set[5];
+    const double tt_ab = S->tt_1[a], tt_bc = S->tt_xy[a][b], tt_cd = S->tt_xy[b][c], tt_de = S->tt_xy[c][dd], tt_ef = S->tt_2[f];
+    cx sub = prop_only(S, S->ss[1][a], S->t1);
+    sub = cx_scale(sub, FF_A);
+    sub = cx_scale(sub, meson_ff(S, tt_ab, M2_A));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_scale(sub, meson_prop(tt_ab, M2_A));
+    sub = cx_scale(sub, meson_ff(S, tt_bc, M2_A));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_mul(sub, prop_only(S, S->ss[b][c], tt_bc));
+    sub = cx_scale(sub, meson_ff(S, tt_bc, M2_B));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_scale(sub, meson_prop(tt_cd, M2_B));
+    sub = cx_scale(sub, meson_ff(S, tt_de, M2_B));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_mul(sub, prop_only(S, S->ss[dd][e], tt_de));
+    sub = cx_scale(sub, meson_ff(S, tt_de, M2_C));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_scale(sub, meson_prop(tt_ef, M2_C));
+    sub = cx_scale(sub, meson_ff(S, tt_ef, M2_C));
+    sub = cx_scale(sub, gpp_P);
+    sub = cx_mul(sub, prop_only(S, S->ss[2][f], S->t2));
+    sub = cx_scale(sub, FF_B);
+    A = cx_add(A, sub);
+    int j = -1;
+    for (int i = 0; i < 5; ++i)
+      if (set[i] < set[i + 1]) j = i;
+    if (j < 0) break;
+    int l = j + 1;
+    for (int i = j + 1; i < 6; ++i)
+      if (set[j] < set[i]) l = i;
+    int t = set[j]; set[j] = set[l]; set[l] = t;
+    for (int lo = j + 1, hi = 5; lo < hi; ++lo, --hi) { t = set[lo]; set[lo] = set[hi]; set[hi] = t; }
+  }
+  S->hamp[0] = A;
+  S->nhamp   = 1;
+  return A;
+}
 static cx regge_me3(ost *S, const grb_resonance *r) {
   double FF_A, FF_B;
   pom_pom_proton_vertex(S, &FF_A, &FF_B);
@@ -2023,7 +2079,7 @@ static double yy_con_amp2(ost *S) {
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
-    case GRB_PROC_PP_CON: return S->d->n_legs == 4 ? cx_abs2(regge_me6(S)) : cx_abs2(regge_me4(S, 1.0));
+    case GRB_PROC_PP_CON: return S->d->n_legs == 6 ? cx_abs2(regge_me8(S)) : (S->d->n_legs == 4 ? cx_abs2(regge_me6(S)) : cx_abs2(regge_me4(S, 1.0)));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
     case GRB_PROC_YY_CON: {
       const int apdg = abs(S->d->nodes[0].pdg);
@@ -2250,7 +2306,7 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
   if (d->excitation != 0 && !(d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
                               d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON))
     return GRB_ERR_UNSUPPORTED;
-  if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || (d->n_legs == 4 && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
+  if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || ((d->n_legs == 4 || d->n_legs == 6) && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
   if (dim < d->lipsdim) return GRB_ERR_ARG;
   ost *S = (ost *)calloc(1, sizeof(ost));

@@ -406,9 +406,10 @@ def test_fast_node_equals_checked_node(grb, msa, proc, monkeypatch):
     w2, f2, _ = E.eval(u.T.copy(), tape.T.copy())
     monkeypatch.delenv("GRB_SCREEN_NOFAST")
     assert (w1 != 0).sum() > 10000 and np.array_equal(f1, f2)
-    if "TENSOR" in proc:   # the tensor node multiplies all quotients up into one division: not bitwise, 1e-14
+    if "TENSOR" in proc:   # the tensor node multiplies all quotients up into one division and runs its vertex algebra on
+        # fused Lorentz products (grb_point.cuh, tensor_node_fast): not bitwise, a few 1e-13
         nz = w2 != 0
-        assert np.max(np.abs(w1[nz] - w2[nz]) / np.abs(w2[nz])) < 1e-13
+        assert np.max(np.abs(w1[nz] - w2[nz]) / np.abs(w2[nz])) < 5e-12
     else:
         assert np.array_equal(w1, w2)
     E.close()

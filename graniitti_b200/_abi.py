@@ -7,7 +7,7 @@ GRB_ABI_VERSION = 2
 GRB_MAX_NODES = 16
 GRB_MAX_RES = 12
 GRB_MAX_VETO = 8
-GRB_MAX_DIM = 16
+GRB_MAX_DIM = 20
 GRB_MAX_TAPE = 32
 GRB_MAX_BINS = 128
 GRB_RHO_DIM = 5

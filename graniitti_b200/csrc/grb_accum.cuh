@@ -10,11 +10,12 @@ enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY
        // Born-level kinematics for the multi-helicity loop: p1z, p1e, p2z, p2e, pX(x,y,z,e)
        IT_BK = 22,
        // <C> class loop invariants: q0y, sinh / cosh of the two leg rapidities (m3, m4, q0x ride in IT_MXSQ, IT_SHY, IT_CHY)
-       // four-leg ladder (AMP_REGGE_ME6) reuses rows 6..16 and 22..28: q0x,q0y,q1x,q1y,q2x,q2y, m[0..3], sh[0]; sh[1..3], ch[0..3]
-       IT_L4A = 6, IT_L4B = 22,
+       // the ladders (AMP_REGGE_ME6 / ME8, K = 4 / 6 legs) keep 5K - 2 invariants -- q_i (x, y; K - 1 of them), m[K], sinh y[K],
+       // cosh y[K] -- in the rows ladder_row(0 .. 5K - 3): rows 6..16, then 22..34, then 36..39
        IT_CK = 30,
        IT_EXC = 35,  // lts.excite1/2 bits of the point (forward N* excitation)
-       IT_NF = 36 };
+       IT_NF = 40 };
+__host__ __device__ constexpr int ladder_row(int r) { return r < 11 ? 6 + r : (r < 24 ? 22 + (r - 11) : 36 + (r - 24)); }
 
 
 // ---- block-level VEGAS accumulation ---------------------------------------------------------------------
@@ -59,11 +60,11 @@ __device__ __forceinline__ void hist_clear(int nb) {
   for (int i = threadIdx.x; i < 2 * nb; i += blockDim.x) s_hist[i] = 0.0;
   __syncthreads();
 }
-__device__ __forceinline__ void hist_add(int nb, int dim, uint64_t packed, double f, uint64_t packed_hi = 0) {
+__device__ __forceinline__ void hist_add(int nb, int dim, uint64_t packed, double f, uint64_t packed_hi = 0, uint64_t packed_x = 0) {
   const double f2 = f * f;
 #pragma unroll 1
   for (int j = 0; j < dim; ++j) {
-    const int b = (int)(((j < 8 ? packed : packed_hi) >> (8 * (j & 7))) & 0xff);
+    const int b = (int)(((j < 8 ? packed : (j < 16 ? packed_hi : packed_x)) >> (8 * (j & 7))) & 0xff);
     atomicAdd(&s_hist[b * dim + j], f);
     atomicAdd(&s_hist[nb + b * dim + j], f2);
   }

@@ -153,10 +153,16 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     }
   }
   const bool me6 = d.n_legs == 4 && d.ps_class == GRB_CLASS_C && d.proc == GRB_PROC_PP_CON && d.n_nodes == 4;
-  if (d.n_legs != 2 && !me6) {
-    err = "the device path covers 2 first-level central legs, and 4 stable legs for PP[CON]<C> (the MRegge::ME6 ladder)";
+  const bool me8 = d.n_legs == 6 && d.ps_class == GRB_CLASS_C && d.proc == GRB_PROC_PP_CON && d.n_nodes == 6;
+  if (d.n_legs != 2 && !me6 && !me8) {
+    err = "the device path covers 2 first-level central legs, and 4 / 6 stable legs for PP[CON]<C> (the MRegge::ME6 / ME8 ladders)";
     return GRB_ERR_UNSUPPORTED;
   }
+  if ((me6 || me8) && d.excitation != 0) {  // (the reference's own ladder integration with N* ends in "Too many NaN weights")
+    err = "forward excitation with the ME6 / ME8 ladders is outside the device path";
+    return GRB_ERR_UNSUPPORTED;
+  }
+  if (d.lipsdim > GRB_MAX_DIM) { err = "lipsdim exceeds GRB_MAX_DIM"; return GRB_ERR_ARG; }
   if (d.n_nodes < 2 || d.n_nodes > GRB_MAX_NODES) { err = "bad n_nodes"; return GRB_ERR_ARG; }
   if (d.lipsdim != (d.ps_class == GRB_CLASS_C ? 3 * (d.n_legs + 2) - 4 : 6) + d.excitation) { err = "lipsdim must be 6 + NSTARS for <F> and 3 Nf - 4 + NSTARS for <C>"; return GRB_ERR_ARG; }
   if (std::fabs(d.pbeam1_pz + d.pbeam2_pz) > 1e-6) { err = "asymmetric beams are outside the device path"; return GRB_ERR_UNSUPPORTED; }
@@ -224,6 +230,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   P.gpp_P = R.c[0] / d.soft.gN_P;
   P.M2_leg0 = d.nodes[0].mass * d.nodes[0].mass;
   P.M2_leg2 = d.n_nodes > 2 ? d.nodes[2].mass * d.nodes[2].mass : P.M2_leg0;
+  P.M2_leg4 = d.n_nodes > 4 ? d.nodes[4].mass * d.nodes[4].mass : P.M2_leg2;
   P.b_EXP = R.b_EXP; P.a_OREAR = R.a_OREAR; P.b_OREAR = R.b_OREAR; P.b_POW = R.b_POW;
   P.me4_sign = (d.proc == GRB_PROC_PP_CON_MINUS) ? -1.0 : 1.0;
   P.inv_fc1 = 1.0 / P.fc1; P.inv_fc2 = 1.0 / P.fc2; P.inv_b_POW = 1.0 / P.b_POW;
@@ -249,6 +256,7 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     if (d.proc == GRB_PROC_PP_CONTENSOR && d.nodes[0].spinX2 == 1) P.amp_kind = 6;  // 2xF (MTensorPomeron.cc:765-804)
     if (d.proc == GRB_PROC_YY_QED) P.amp_kind = 7;                                    // QED branch (:664-713)
     if (me6) P.amp_kind = 8;                                                          // MRegge::ME6 ladder
+    if (me8) P.amp_kind = 9;                                                          // MRegge::ME8 ladder
     P.tp_ff_coupling = 81.0 * std::pow(d.tpom.gPNN, 4);
     P.mass_leg0 = d.nodes[0].mass;
     P.qed_e = std::sqrt(std::max(0.0, 0.0072973525693 * 4.0 * GRB_PI));  // qed::alpha_QED() = alpha_0, MQED.h:19-24,57
@@ -484,7 +492,7 @@ int grb_create(const grb_process_desc *desc, int device, grb_engine **out) {
     if ((ce = cudaMalloc(&e->d_items, sizeof(double) * ITEM_NF * e->chunk)) != cudaSuccess) return fail("cudaMalloc items", ce);
     if ((ce = cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
     if ((ce = cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
-    if (desc->lipsdim > 8 && (ce = cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk)) != cudaSuccess) return fail("cudaMalloc", ce);
+    if (desc->lipsdim > 8 && (ce = cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk * (desc->lipsdim > 16 ? 2 : 1))) != cudaSuccess) return fail("cudaMalloc", ce);
   }
   if ((ce = cudaMalloc(&e->d_item_count, sizeof(unsigned int) * 8)) != cudaSuccess) return fail("cudaMalloc", ce);   // [0..2] work list, [4] k_points tiles
   // (+ 2 x 64 doubles: the per-rank maxima slots of grb_allreduce)
@@ -758,7 +766,7 @@ int grb_vegas_iterate_async(grb_engine *e, const double *xmat, int bins, int dim
     CK(cudaMalloc(&e->d_items2, sizeof(double) * ITEM_NF * e->chunk));
     CK(cudaMalloc(&e->d_item_idx2, sizeof(int32_t) * e->chunk));
     CK(cudaMalloc(&e->d_item_bins2, sizeof(uint64_t) * e->chunk));
-    if (e->desc.lipsdim > 8) CK(cudaMalloc(&e->d_item_bins_hi2, sizeof(uint64_t) * e->chunk));
+    if (e->desc.lipsdim > 8) CK(cudaMalloc(&e->d_item_bins_hi2, sizeof(uint64_t) * e->chunk * (e->desc.lipsdim > 16 ? 2 : 1)));
     CK(cudaMalloc(&e->d_item_count2, sizeof(unsigned int) * 8));
     CK(cudaStreamCreateWithFlags(&e->stream_pts, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
@@ -975,7 +983,7 @@ int grb_update_desc(grb_engine *e, const grb_process_desc *desc) {
     CK(cudaMalloc(&e->d_item_idx, sizeof(int32_t) * e->chunk));
     CK(cudaMalloc(&e->d_item_bins, sizeof(uint64_t) * e->chunk));
   }
-  if (desc->screening && desc->lipsdim > 8 && !e->d_item_bins_hi) CK(cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk));
+  if (desc->screening && desc->lipsdim > 8 && !e->d_item_bins_hi) CK(cudaMalloc(&e->d_item_bins_hi, sizeof(uint64_t) * e->chunk * (desc->lipsdim > 16 ? 2 : 1)));
   const bool same_loop = desc->s == e->desc.s && desc->loop_nkt == e->desc.loop_nkt && desc->loop_nphi == e->desc.loop_nphi &&
                          desc->loop_min_kt == e->desc.loop_min_kt && desc->loop_max_kt == e->desc.loop_max_kt;
   e->desc  = *desc;

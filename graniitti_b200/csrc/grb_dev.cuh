@@ -68,6 +68,7 @@ struct DevProc {
   double a0[3], ap[3], ln_inv_s0, eta0_re[3], eta0_im[3], phase_c[3];  // phase_c = -pi/2 * ap
   double gN_P, fc1, fc2, gpp_P, M2_leg0, b_EXP, a_OREAR, b_OREAR, b_POW, me4_sign;
   double M2_leg2;  // PDG mass^2 of the third central leg (ME6: propagator mass of the lower half of the ladder)
+  double M2_leg4;  // PDG mass^2 of the fifth central leg (ME8: propagator mass of the lowest third of the ladder)
   double inv_fc1, inv_fc2, inv_b_POW, g2_const, eta0sq_re, eta0sq_im;  // g2_const = (gpp_P gN_P)^2
   double omega;                                                       // PARAM_REGGE::omega (ME3 flux power)
   double yy_ee4;                                                      // ee^4, ee = 2 sqrt(pi alpha(0)) (MG5 GC_3)
@@ -134,7 +135,8 @@ struct PointArgs {
   double *      items;
   int32_t *     item_idx;
   uint64_t *    item_bins;
-  uint64_t *    item_bins_hi;  // VEGAS bins of dimensions 8..15 (four-leg <C> class: 14 dimensions)
+  uint64_t *    item_bins_hi;  // VEGAS bins of dimensions 8..15 (four-leg <C> class: 14 dimensions); six legs (20): a third word
+                               // for dimensions 16.. at [item_cap + slot]
   unsigned int *item_count;
   unsigned int *tile_count;    // k_points' tile counter (one unsigned, zeroed per launch)
   int64_t       item_cap;

@@ -104,10 +104,12 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
     if ((int64_t)tile >= ntiles) break;
     const int64_t idx    = ((int64_t)tile << 5) + lane_id;
     const bool    active = idx < a.n;
-    constexpr int UD = (AMP == AMP_REGGE_ME6) ? 16 : 10;  // coordinates: <F> 6 (+2 N*), <C> 8 (two legs) / 14 (four legs) (+2 N*)
+    constexpr int KL = (AMP == AMP_REGGE_ME8) ? 6 : 4;     // legs of the ladder amplitudes
+    constexpr bool LADDER = (AMP == AMP_REGGE_ME6 || AMP == AMP_REGGE_ME8);
+    constexpr int UD = LADDER ? 3 * KL + 4 : 10;           // coordinates: <F> 6 (+2 N*), <C> 8 (two legs) / 14 (four) / 20 (six) (+2 N*)
     double        u[UD] = {};
-    uint64_t      packed = 0, packed_hi = 0;                // VEGAS bin per dimension, 8 bits each
-    Ladder4       X4;                                      // four-leg ladder scalars (AMP_REGGE_ME6 only)
+    uint64_t      packed = 0, packed_hi = 0, packed_x = 0;  // VEGAS bin per dimension, 8 bits each
+    Ladder<KL>    X4;                                      // ladder scalars (AMP_REGGE_ME6 / ME8 only)
     double        vw     = 1.0;
     PointState<NN> S;
     bool kin = false, fid = false, veto = false, overrun = false;
@@ -137,9 +139,10 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
             u[j] = 0.0 + ac * 1.0;
             vw *= zo * a.bins;
             if (j < 8) packed |= (uint64_t)(ind - 1) << (8 * j);
-            else packed_hi |= (uint64_t)(ind - 1) << (8 * (j - 8));
+            else if (j < 16) packed_hi |= (uint64_t)(ind - 1) << (8 * (j - 8));
+            else packed_x |= (uint64_t)(ind - 1) << (8 * (j - 16));
           }
-        if (AMP == AMP_REGGE_ME6) kin = point_kinematics_C4<NN>(u, dr, S, X4);
+        if (LADDER) kin = point_kinematics_CK<NN, KL>(u, dr, S, X4);
         else kin = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       } else {
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
 #pragma unroll
         for (int j = 0; j < UD; ++j)
           if (j < dim) u[j] = dr.coord(j);
-        if (AMP == AMP_REGGE_ME6) kin = point_kinematics_C4<NN>(u, dr, S, X4);
+        if (LADDER) kin = point_kinematics_CK<NN, KL>(u, dr, S, X4);
         else kin = P.ps_class == GRB_CLASS_C ? point_kinematics_C<NN>(u, dr, S) : point_kinematics<NN>(u, dr, S);
         overrun = dr.overrun;
       }
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
     cx         h0 = {0.0, 0.0};
     double     pref = 0.0;
     if (valid) {
-      if (AMP == AMP_REGGE_ME6) h0 = regge_me6(S.t1, S.t2, X4);
+      if (LADDER) h0 = regge_ladder<KL>(S.t1, S.t2, X4);
       else h0 = born_amplitude<NN, AMP>(S);
       pref = P.ps_class == GRB_CLASS_C ? weight_prefactor_C<NN>(S) : weight_prefactor<NN>(S);
       if (!P.screening) {
@@ -207,25 +210,26 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
             it[IT_M1 * c] = L.m1; it[IT_M2 * c] = L.m2; it[IT_MXSQ * c] = L.mXsq;
             it[IT_SHY * c] = L.shY; it[IT_CHY * c] = L.chY;
             if (P.excitation) it[IT_EXC * c] = (double)L.exc;
-            if (AMP == AMP_REGGE_ME6) {  // four-leg ladder: leg invariants re-derived from the saved 4-vectors (MContinuum.cc:108-112)
+            if (LADDER) {  // ladders: leg invariants re-derived from the saved 4-vectors (MContinuum.cc:108-112)
 #pragma unroll
-              for (int k = 0; k < 3; ++k) { it[(IT_L4A + 2 * k) * c] = X4.qx[k]; it[(IT_L4A + 2 * k + 1) * c] = X4.qy[k]; }
+              for (int k = 0; k < KL - 1; ++k) { it[ladder_row(2 * k) * c] = X4.qx[k]; it[ladder_row(2 * k + 1) * c] = X4.qy[k]; }
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < KL; ++k) {
                 const v4    &pk = S.np4[k % NN];
                 const double yk = rap_of(pk), shk = sinh(yk), chk = cosh(yk);
-                it[(IT_L4A + 6 + k) * c] = m_of(pk);
-                if (k == 0) it[(IT_L4A + 10) * c] = shk; else it[(IT_L4B + k - 1) * c] = shk;
-                it[(IT_L4B + 3 + k) * c] = chk;
+                it[ladder_row(2 * (KL - 1) + k) * c] = m_of(pk);
+                it[ladder_row(2 * (KL - 1) + KL + k) * c] = shk;
+                it[ladder_row(2 * (KL - 1) + 2 * KL + k) * c] = chk;
               }
             }
             if (dim > 8) a.item_bins_hi[slot] = packed_hi;   // VEGAS bins of the dimensions 8.. (second packed word)
-            if (P.ps_class == GRB_CLASS_C && AMP != AMP_REGGE_ME6) {
+            if (dim > 16) a.item_bins_hi[c + slot] = packed_x;  // ... and 16.. (third)
+            if (P.ps_class == GRB_CLASS_C && !LADDER) {
               it[IT_MXSQ * c] = L.m3; it[IT_SHY * c] = L.m4; it[IT_CHY * c] = L.qx;
               it[(IT_CK + 0) * c] = L.qy; it[(IT_CK + 1) * c] = L.sh3; it[(IT_CK + 2) * c] = L.ch3;
               it[(IT_CK + 3) * c] = L.sh4; it[(IT_CK + 4) * c] = L.ch4;
             }
-            if (AMP != AMP_REGGE_ME6) {  // (the four-leg ladder keeps its own invariants in these rows)
+            if (!LADDER) {  // (the ladders keep their own invariants in these rows)
               it[(IT_P3 + 0) * c] = L.p3.x; it[(IT_P3 + 1) * c] = L.p3.y; it[(IT_P3 + 2) * c] = L.p3.z; it[(IT_P3 + 3) * c] = L.p3.e;
               it[(IT_P4 + 0) * c] = L.p4.x; it[(IT_P4 + 1) * c] = L.p4.y; it[(IT_P4 + 2) * c] = L.p4.z; it[(IT_P4 + 3) * c] = L.p4.e;
             }
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
           ts.f2sum += f * f;
           ts.maxW = fmax(ts.maxW, W);
           ts.maxf = fmax(ts.maxf, f);
-          hist_add(nb, dim, packed, f, packed_hi);
+          hist_add(nb, dim, packed, f, packed_hi, packed_x);
           if (a.mode == GRB_MODE_GENERATE) {
             const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
             if (es >= 0) {
@@ -319,7 +323,7 @@ inline void launch_points_t(const PointArgs &a, unsigned blocks, int threads, si
 template <int AMP>
 inline void launch_points_n(const PointArgs &a, int n_nodes, unsigned blocks, int threads, size_t smem, cudaStream_t st) {
   if (n_nodes <= 2) launch_points_t<2, AMP>(a, blocks, threads, smem, st);
-  else if (n_nodes <= 6) launch_points_t<6, AMP>(a, blocks, threads, smem, st);  // config 5: rho rho -> 4 pi
+  else if (n_nodes <= 6) launch_points_t<6, AMP>(a, blocks, threads, smem, st);  // config 5: rho rho -> 4 pi; six-leg ladder
   else launch_points_t<GRB_MAX_NODES, AMP>(a, blocks, threads, smem, st);
 }
 

@@ -21,21 +21,22 @@ __device__ __forceinline__ void screen_item(const PointArgs &a, int64_t s) {
   const DevProc &P = c_proc;
   const int64_t  c = a.item_cap;
   double *       it = a.items + s;
-  if (AMP == AMP_REGGE_ME6) {  // four-leg ladder: its own invariants and loop (grb_point.cuh)
-    LoopInv4 L4;
-    L4.p1x = it[IT_P1X * c]; L4.p1y = it[IT_P1Y * c]; L4.p2x = it[IT_P2X * c]; L4.p2y = it[IT_P2Y * c];
-    L4.m1 = it[IT_M1 * c]; L4.m2 = it[IT_M2 * c]; L4.m1sq = pow2(L4.m1); L4.m2sq = pow2(L4.m2);
+  if (AMP == AMP_REGGE_ME6 || AMP == AMP_REGGE_ME8) {  // ladders: their own invariants and loop (grb_point.cuh)
+    constexpr int K = AMP == AMP_REGGE_ME8 ? 6 : 4;
+    LoopInvK<K>   LK;
+    LK.p1x = it[IT_P1X * c]; LK.p1y = it[IT_P1Y * c]; LK.p2x = it[IT_P2X * c]; LK.p2y = it[IT_P2Y * c];
+    LK.m1 = it[IT_M1 * c]; LK.m2 = it[IT_M2 * c]; LK.m1sq = pow2(LK.m1); LK.m2sq = pow2(LK.m2);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { L4.qx[k] = it[(IT_L4A + 2 * k) * c]; L4.qy[k] = it[(IT_L4A + 2 * k + 1) * c]; }
+    for (int k = 0; k < K - 1; ++k) { LK.qx[k] = it[ladder_row(2 * k) * c]; LK.qy[k] = it[ladder_row(2 * k + 1) * c]; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      L4.m[k]  = it[(IT_L4A + 6 + k) * c];
-      L4.sh[k] = (k == 0) ? it[(IT_L4A + 10) * c] : it[(IT_L4B + k - 1) * c];
-      L4.ch[k] = it[(IT_L4B + 3 + k) * c];
+    for (int k = 0; k < K; ++k) {
+      LK.m[k]  = it[ladder_row(2 * (K - 1) + k) * c];
+      LK.sh[k] = it[ladder_row(2 * (K - 1) + K + k) * c];
+      LK.ch[k] = it[ladder_row(2 * (K - 1) + 2 * K + k) * c];
     }
     cx h0;
     h0.re = it[IT_H0RE * c]; h0.im = it[IT_H0IM * c];
-    it[IT_AMP2 * c] = screened_amp2_me6<SAME>(L4, h0);
+    it[IT_AMP2 * c] = screened_amp2_ladder<SAME, K>(LK, h0);
     return;
   }
   LoopInv        L;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) k_finish(const PointArgs a) {
       ts.f2sum += f * f;
       ts.maxW = fmax(ts.maxW, W);
       ts.maxf = fmax(ts.maxf, f);
-      hist_add(nb, dim, a.item_bins[s], f, dim > 8 ? a.item_bins_hi[s] : 0);
+      hist_add(nb, dim, a.item_bins[s], f, dim > 8 ? a.item_bins_hi[s] : 0, dim > 16 ? a.item_bins_hi[c + s] : 0);
       if (a.mode == GRB_MODE_GENERATE) {
         const int64_t es = hitmiss_slot(a, f, (uint64_t)(a.first_call + idx));
         if (es >= 0) {
@@ -195,6 +196,10 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
   }
   if (amp_kind == AMP_REGGE_ME6) {
     launch_screen_t<2, AMP_REGGE_ME6>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_REGGE_ME8) {
+    launch_screen_t<2, AMP_REGGE_ME8>(a, sm_count, st);
     return 2;
   }
   if (amp_kind == AMP_YY_LL) {

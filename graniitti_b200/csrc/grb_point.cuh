@@ -355,20 +355,44 @@ __device__ __forceinline__ bool point_kinematics_C(const double *u, Draws &dr, P
   return lorentz_scalars(S);
 }
 
-// ---- <C> class, four central legs (2 -> 6 direct, 14 coordinates) + the Regge ladder MRegge::ME6 ---------------------
-// u = [pt1, pt2, phi1, phi2, kt_1..3, phi_1..3, y_1..4]; BLinearSystem with the Kf = 4 inverse (MContinuum.cc:485-488).
-// The ladder needs s_1a, s_2a (4 + 4), s_ab (6 pairs), t-type scalars tt_1[a], tt_2[a] (4 + 4) and tt_xy[a][b] (6 pairs).
+// ---- <C> class, K = 4 or 6 central legs (2 -> 6 / 2 -> 8 direct, 14 / 20 coordinates) + the Regge ladders MRegge::ME6, ME8 --
+// u = [pt1, pt2, phi1, phi2, kt_1..K-1, phi_1..K-1, y_1..K]; BLinearSystem with the Kf = K inverse (MContinuum.cc:485-497).
+// The ladders need s_1a, s_2a (K + K), s_ab (pairs), t-type scalars tt_1[a], tt_2[a] (K + K) and tt_xy[a][b] (pairs).
 #define GRB_BLIN4 {{7.0 / 8.0, 1.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0}, {3.0 / 8.0, 5.0 / 8.0, -1.0 / 2.0, -1.0 / 4.0}, \
                    {-1.0 / 8.0, 1.0 / 8.0, 1.0 / 2.0, -1.0 / 4.0}, {-5.0 / 8.0, -3.0 / 8.0, 1.0 / 2.0, 3.0 / 4.0}}
-struct Ladder4 {
-  double s1a[4], s2a[4], sab[6], tt1[4], tt2[4], txy[6];  // pair index of (a < b): a*(7-a)/2 + b - a - 1 (a, b = 0..3)
-  double qx[3], qy[3];                                    // intermediate difference momenta (kept for the screening loop)
+#define GRB_BLIN6 {{4.0 / 3.0, 1.0 / 2.0, -2.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0}, {5.0 / 6.0, 1.0 / 1.0, -2.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0}, \
+                   {1.0 / 3.0, 1.0 / 2.0, 1.0 / 3.0, -1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0}, {-1.0 / 6.0, 0.0, 1.0 / 3.0, 1.0 / 2.0, -1.0 / 3.0, -1.0 / 6.0}, \
+                   {-2.0 / 3.0, -1.0 / 2.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, -1.0 / 6.0}, {-7.0 / 6.0, -1.0 / 1.0, 1.0 / 3.0, 1.0 / 2.0, 2.0 / 3.0, 5.0 / 6.0}}
+template <int K>
+struct Ladder {
+  static constexpr int NP = K * (K - 1) / 2;
+  double s1a[K], s2a[K], sab[NP], tt1[K], tt2[K], txy[NP];  // pair index of (a < b): a*(2K-1-a)/2 + b - a - 1 (a, b = 0..K-1)
+  double qx[K - 1], qy[K - 1];                              // intermediate difference momenta (kept for the screening loop)
 };
-__device__ __forceinline__ int pair4(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * (7 - a) / 2 + b - a - 1; }
+using Ladder4 = Ladder<4>;
+template <int K>
+__device__ __forceinline__ int pairK(int a, int b) { if (a > b) { const int t = a; a = b; b = t; } return a * (2 * K - 1 - a) / 2 + b - a - 1; }
+__device__ __forceinline__ int pair4(int a, int b) { return pairK<4>(a, b); }
+// p = A b for one leg: the reference's loop adds b[j] * A[i][j] for every j, zero entries included (signed zeros)
+template <int K>
+__device__ __forceinline__ double blin_row(int i, const double *b) {
+  double acc = 0.0;
+  if (K == 4) {
+    const double A[4][4] = GRB_BLIN4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc = acc + b[j] * A[i][j];
+  } else {
+    const double A[6][6] = GRB_BLIN6;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc = acc + b[j] * A[i][j];
+  }
+  return acc;
+}
 
-// Lorentz scalars of the four-leg ladder (MProcess.cc:1499-1584): every pair mass^2 must be >= 0, t1, t2 <= 0
-__device__ __forceinline__ bool ladder4_scalars(const v4 &p1, const v4 &p2, const v4 &pX, const v4 *leg, double &t1, double &t2,
-                                                double &s1, double &s2, Ladder4 &X) {
+// Lorentz scalars of the ladder (MProcess.cc:1499-1584): every pair mass^2 must be >= 0, t1, t2 <= 0
+template <int K>
+__device__ __forceinline__ bool ladder_scalars(const v4 &p1, const v4 &p2, const v4 &pX, const v4 *leg, double &t1, double &t2,
+                                               double &s1, double &s2, Ladder<K> &X) {
   const DevProc &P = c_proc;
   s1 = m2_of(p1.x + pX.x, p1.y + pX.y, p1.z + pX.z, p1.e + pX.e);
   s2 = m2_of(p2.x + pX.x, p2.y + pX.y, p2.z + pX.z, p2.e + pX.e);
@@ -377,7 +401,7 @@ __device__ __forceinline__ bool ladder4_scalars(const v4 &p1, const v4 &p2, cons
   const double q1x = 0.0 - p1.x, q1y = 0.0 - p1.y, q1z = P.pb1z - p1.z, q1e = P.pb1e - p1.e;
   const double q2x = 0.0 - p2.x, q2y = 0.0 - p2.y, q2z = P.pb2z - p2.z, q2e = P.pb2e - p2.e;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
+  for (int a = 0; a < K; ++a) {
     const v4 &pa = leg[a];
     X.s1a[a] = m2_of(p1.x + pa.x, p1.y + pa.y, p1.z + pa.z, p1.e + pa.e);
     X.s2a[a] = m2_of(p2.x + pa.x, p2.y + pa.y, p2.z + pa.z, p2.e + pa.e);
@@ -386,9 +410,9 @@ __device__ __forceinline__ bool ladder4_scalars(const v4 &p1, const v4 &p2, cons
     X.tt1[a] = m2_of(q1x - pa.x, q1y - pa.y, q1z - pa.z, q1e - pa.e);
     X.tt2[a] = m2_of(q2x - pa.x, q2y - pa.y, q2z - pa.z, q2e - pa.e);
 #pragma unroll
-    for (int b = a + 1; b < 4; ++b) {
+    for (int b = a + 1; b < K; ++b) {
       const v4 &pb = leg[b];
-      const int k  = a * (7 - a) / 2 + b - a - 1;
+      const int k  = a * (2 * K - 1 - a) / 2 + b - a - 1;
       X.sab[k] = m2_of(pa.x + pb.x, pa.y + pb.y, pa.z + pb.z, pa.e + pb.e);
       ok = ok && !(X.sab[k] < 0);
       X.txy[k] = m2_of((q1x - pa.x) - pb.x, (q1y - pa.y) - pb.y, (q1z - pa.z) - pb.z, (q1e - pa.e) - pb.e);
@@ -400,17 +424,17 @@ __device__ __forceinline__ bool ladder4_scalars(const v4 &p1, const v4 &p2, cons
   return !(t1 > 0 || t2 > 0);
 }
 
-template <int NN, class Draws>
-__device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, PointState<NN> &S, Ladder4 &X) {
+template <int NN, int K, class Draws>
+__device__ __forceinline__ bool point_kinematics_CK(const double *u, Draws &dr, PointState<NN> &S, Ladder<K> &X) {
   const DevProc &P = c_proc;
   const double   pt1  = exp(P.log_pt0 + P.dlog_pt * u[0]);
   const double   pt2  = exp(P.log_pt0 + P.dlog_pt * u[1]);
   const double   phi1 = 2.0 * GRB_PI * u[2];
   const double   phi2 = 2.0 * GRB_PI * u[3];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) S.moff[i % NN] = offshell_mass(i, dr);
+  for (int i = 0; i < K; ++i) S.moff[i % NN] = offshell_mass(i, dr);
   double m1, m2;
-  S.exc = sample_forward_masses(u[14], u[15], dr, m1, m2);
+  S.exc = sample_forward_masses(u[3 * K + 2], u[3 * K + 3], dr, m1, m2);
   S.M_MIN = 0.0; S.M_MAX = 0.0; S.DW = 0.0; S.qx = 0.0; S.qy = 0.0;
   double s1, c1, s2, c2;
   sincos(phi1, &s1, &c1);
@@ -418,28 +442,27 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
   S.p1.x = pt1 * c1; S.p1.y = pt1 * s1;
   S.p2.x = pt2 * c2; S.p2.y = pt2 * s2;
   const double wx = S.p1.x + S.p2.x, wy = S.p1.y + S.p2.y;
-  double bx[4], by[4];
+  double bx[K], by[K];
   S.qprod = 1.0;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < K - 1; ++i) {
     const double kt = P.kt_min + P.dkt * u[4 + i];
     double       sk, ck;
-    sincos(2.0 * GRB_PI * u[7 + i], &sk, &ck);
+    sincos(2.0 * GRB_PI * u[4 + (K - 1) + i], &sk, &ck);
     const double qx = kt * ck, qy = kt * sk;
     X.qx[i] = qx; X.qy[i] = qy;
     S.qprod *= msqrt(qx * qx + qy * qy);
     if (i == 0) { bx[0] = qx - wx; by[0] = qy - wy; }
     bx[i + 1] = qx * (-1.0) - wx; by[i + 1] = qy * (-1.0) - wy;
   }
-  const double A[4][4] = GRB_BLIN4;
   S.pX.x = 0.0; S.pX.y = 0.0; S.pX.z = 0.0; S.pX.e = 0.0;
   double sumM = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < K; ++i) {
     v4 &p = S.np4[i % NN];
-    p.x = ((((0.0 + bx[0] * A[i][0]) + bx[1] * A[i][1]) + bx[2] * A[i][2]) + bx[3] * A[i][3]);
-    p.y = ((((0.0 + by[0] * A[i][0]) + by[1] * A[i][1]) + by[2] * A[i][2]) + by[3] * A[i][3]);
-    const double y  = P.rap_min + P.drap * u[10 + i];
+    p.x = blin_row<K>(i, bx);
+    p.y = blin_row<K>(i, by);
+    const double y  = P.rap_min + P.drap * u[4 + 2 * (K - 1) + i];
     const double mt = msqrt(pow2(S.moff[i % NN]) + pt2_of(p));
     p.z = mt * sinh(y); p.e = mt * cosh(y);
     S.pX.x += p.x; S.pX.y += p.y; S.pX.z += p.z; S.pX.e += p.e;
@@ -453,7 +476,7 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
   S.p1.z = p1z; S.p1.e = msqrt(pow2(m1) + pow2(pt1) + pow2(p1z));
   S.p2.z = p2z; S.p2.e = msqrt(pow2(m2) + pow2(pt2) + pow2(p2z));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) sumM += m_of(S.np4[i % NN]);
+  for (int i = 0; i < K; ++i) sumM += m_of(S.np4[i % NN]);
   if (m_of(S.pX) < sumM) return false;
   {
     const double dx = 0.0 - ((S.p1.x + S.p2.x) + S.pX.x), dy = 0.0 - ((S.p1.y + S.p2.y) + S.pX.y);
@@ -461,10 +484,10 @@ __device__ __forceinline__ bool point_kinematics_C4(const double *u, Draws &dr, 
     if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
   }
   {
-    v4 leg[4];
+    v4 leg[K];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) leg[i] = S.np4[i % NN];
-    if (!ladder4_scalars(S.p1, S.p2, S.pX, leg, S.t1, S.t2, S.s1, S.s2, X)) return false;
+    for (int i = 0; i < K; ++i) leg[i] = S.np4[i % NN];
+    if (!ladder_scalars<K>(S.p1, S.p2, S.pX, leg, S.t1, S.t2, S.s1, S.s2, X)) return false;
   }
   S.t_hat = 0.0; S.u_hat = 0.0; S.ss13 = X.s1a[0]; S.ss14 = X.s1a[1]; S.ss23 = X.s2a[0]; S.ss24 = X.s2a[1];
   S.m2 = m2_of(S.pX);
@@ -526,18 +549,96 @@ __device__ __forceinline__ cx regge_me6(const double t1, const double t2, const 
   return A;
 }
 
-// Screening loop of the four-leg ladder (reference MContinuum::LoopKinematics, src/MContinuum.cc:94-161, with Kf = 4): the
+// reference src/MRegge.cc:560-633 ME8: sum over the 720 orderings (a, b, c, d, e, f) of the six legs of
+//   Prop(s_1a, t1) F_A ff_A(tt_a) g / (tt_a - M_A^2) . ff_A(tt_ab) g Prop(s_bc, tt_ab) ff_B(tt_ab) g . 1 / (tt_bc - M_B^2)
+//   . ff_B(tt_cd) g Prop(s_de, tt_cd) ff_C(tt_cd) g . 1 / (tt_f - M_C^2) ff_C(tt_f) g Prop(s_2f, t2) F_B
+// with the scalars the reference reads: tt_a = tt_1[a], tt_ab = tt_xy[a][b], tt_bc = tt_xy[b][c], tt_cd = tt_xy[c][d] (two-leg
+// sums; no form factor on tt_bc), tt_f = tt_2[f].  The two middle blocks depend on three legs each (120 distinct values): the
+// lower one, M2(c, d, e), is tabulated once (local memory), the upper one is formed in the (a, b, c) loops.
+__device__ __forceinline__ cx regge_me8(const double t1, const double t2, const Ladder<6> &X) {
+  const DevProc &P = c_proc;
+  const double FA = P.gN_P * (1.0 / (1 - t1 / P.fc1)) * (1.0 / (1 - t1 / P.fc2));
+  const double FB = P.gN_P * (1.0 / (1 - t2 / P.fc1)) * (1.0 / (1 - t2 / P.fc2));
+  const double g  = P.gpp_P;
+  cx U[6], V[6];
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a) {
+    const cx     P1 = regge_prop(X.s1a[a], t1), P2 = regge_prop(X.s2a[a], t2);
+    const double ua = FA * meson_ff1(X.tt1[a], P.M2_leg0) * g * (1.0 / (X.tt1[a] - P.M2_leg0));
+    const double vf = (1.0 / (X.tt2[a] - P.M2_leg4)) * meson_ff1(X.tt2[a], P.M2_leg4) * g * FB;
+    U[a] = {P1.re * ua, P1.im * ua};
+    V[a] = {P2.re * vf, P2.im * vf};
+  }
+  cx M2[120];  // index c * 20 + rank(d) * 4 + rank(e)
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c)
+#pragma unroll 1
+    for (int d = 0; d < 6; ++d) {
+      if (d == c) continue;
+      const double tcd = X.txy[pairK<6>(c, d)];
+      const double f   = meson_ff1(tcd, P.M2_leg2) * g * meson_ff1(tcd, P.M2_leg4) * g;
+#pragma unroll 1
+      for (int e = 0; e < 6; ++e) {
+        if (e == c || e == d) continue;
+        const cx Pm = regge_prop(X.sab[pairK<6>(d, e)], tcd);
+        M2[c * 20 + (d - (d > c)) * 4 + (e - (e > c) - (e > d))] = {Pm.re * f, Pm.im * f};
+      }
+    }
+  cx A = {0.0, 0.0};
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a)
+#pragma unroll 1
+    for (int b = 0; b < 6; ++b) {
+      if (b == a) continue;
+      const double tab = X.txy[pairK<6>(a, b)];
+      const double fab = meson_ff1(tab, P.M2_leg0) * g * meson_ff1(tab, P.M2_leg2) * g;
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        if (c == a || c == b) continue;
+        const cx     Pm = regge_prop(X.sab[pairK<6>(b, c)], tab);
+        const double r  = fab * (1.0 / (X.txy[pairK<6>(b, c)] - P.M2_leg2));
+        cx Y = {U[a].re * Pm.re - U[a].im * Pm.im, U[a].re * Pm.im + U[a].im * Pm.re};
+        Y = {Y.re * r, Y.im * r};
+        cx Z = {0.0, 0.0};   // sum over the orderings (d, e, f) of the three remaining legs
+#pragma unroll 1
+        for (int d = 0; d < 6; ++d) {
+          if (d == a || d == b || d == c) continue;
+#pragma unroll 1
+          for (int e = 0; e < 6; ++e) {
+            if (e == a || e == b || e == c || e == d) continue;
+            const int f  = 15 - a - b - c - d - e;
+            const cx  m  = M2[c * 20 + (d - (d > c)) * 4 + (e - (e > c) - (e > d))];
+            Z.re += m.re * V[f].re - m.im * V[f].im;
+            Z.im += m.re * V[f].im + m.im * V[f].re;
+          }
+        }
+        A.re += Y.re * Z.re - Y.im * Z.im;
+        A.im += Y.re * Z.im + Y.im * Z.re;
+      }
+    }
+  return A;
+}
+template <int K>
+__device__ __forceinline__ cx regge_ladder(const double t1, const double t2, const Ladder<K> &X);
+template <>
+__device__ __forceinline__ cx regge_ladder<4>(const double t1, const double t2, const Ladder<4> &X) { return regge_me6(t1, t2, X); }
+template <>
+__device__ __forceinline__ cx regge_ladder<6>(const double t1, const double t2, const Ladder<6> &X) { return regge_me8(t1, t2, X); }
+
+// Screening loop of the ladders (reference MContinuum::LoopKinematics, src/MContinuum.cc:94-161, with Kf = 4, 6): the
 // legs keep their masses and rapidities (re-derived from the saved 4-vectors), their transverse momenta follow the linear
-// system of the shifted protons; ME6 reads only lts scalars, so every scalar is rebuilt from the updated momenta.
-struct LoopInv4 {
+// system of the shifted protons; ME6 / ME8 read only lts scalars, so every scalar is rebuilt from the updated momenta.
+template <int K>
+struct LoopInvK {
   double p1x, p1y, p2x, p2y, m1, m2, m1sq, m2sq;
-  double qx[3], qy[3], m[4], sh[4], ch[4];
+  double qx[K - 1], qy[K - 1], m[K], sh[K], ch[K];
 };
+using LoopInv4 = LoopInvK<4>;
 struct PzConst;
-template <bool SAME>
-__device__ __forceinline__ bool loop_node_C4(const LoopInv4 &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder4 &X);
-template <bool SAME>
-__device__ __forceinline__ double screened_amp2_me6(const LoopInv4 &L, const cx &h0);
+template <bool SAME, int K>
+__device__ __forceinline__ bool loop_node_CK(const LoopInvK<K> &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder<K> &X);
+template <bool SAME, int K>
+__device__ __forceinline__ double screened_amp2_ladder(const LoopInvK<K> &L, const cx &h0);
 
 // ---- cuts (reference src/MProcess.cc:1069-1175, src/MUserCuts.cc:21-75) ------------------------------------
 __device__ __forceinline__ bool leaf_fid_ok(const v4 &p) {
@@ -954,7 +1055,7 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
 namespace grb {
 
 enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5,
-       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7, AMP_REGGE_ME6 = 8 };
+       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7, AMP_REGGE_ME6 = 8, AMP_REGGE_ME8 = 9 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
@@ -964,7 +1065,7 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
   }
   if (AMP == AMP_TENSOR_2XF) return {sqrt(tensor_2xF_amp2(in, p3, p4)), 0.0};  // unscreened only
   if (AMP == AMP_YY_QED) return {sqrt(yy_qed_amp2(in, p3, p4)), 0.0};          // unscreened only
-  if (AMP == AMP_REGGE_ME6) return {0.0, 0.0};  // four-leg ladder: evaluated in k_points from its own scalars (unscreened only)
+  if (AMP == AMP_REGGE_ME6 || AMP == AMP_REGGE_ME8) return {0.0, 0.0};  // ladders: evaluated from their own scalars (regge_ladder)
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {
@@ -1569,24 +1670,23 @@ __device__ __forceinline__ double screened_amp2_multi(const LoopInv &L, const No
   return amp_hel_scale<AMP>() * amp2;
 }
 
-// ---- four-leg ladder: loop node and loop integral ---------------------------------------------------------------------
-template <bool SAME>
-__device__ __forceinline__ bool loop_node_C4(const LoopInv4 &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder4 &X) {
+// ---- four- / six-leg ladder: loop node and loop integral ----------------------------------------------------------------
+template <bool SAME, int K>
+__device__ __forceinline__ bool loop_node_CK(const LoopInvK<K> &L, const PzConst &pc, double ktx, double kty, double &t1, double &t2, Ladder<K> &X) {
   const DevProc &P = c_proc;
-  v4 p1, p2, pX, leg[4];
+  v4 p1, p2, pX, leg[K];
   p1.x = L.p1x - ktx; p1.y = L.p1y - kty; p2.x = L.p2x + ktx; p2.y = L.p2y + kty;
   const double wx = p1.x + p2.x, wy = p1.y + p2.y;
-  double bx[4], by[4];
+  double bx[K], by[K];
   bx[0] = L.qx[0] - wx; by[0] = L.qy[0] - wy;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { bx[i + 1] = L.qx[i] * (-1.0) - wx; by[i + 1] = L.qy[i] * (-1.0) - wy; }
-  const double A[4][4] = GRB_BLIN4;
+  for (int i = 0; i < K - 1; ++i) { bx[i + 1] = L.qx[i] * (-1.0) - wx; by[i + 1] = L.qy[i] * (-1.0) - wy; }
   pX.x = 0.0; pX.y = 0.0; pX.z = 0.0; pX.e = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < K; ++i) {
     v4 &p = leg[i];
-    p.x = ((((0.0 + bx[0] * A[i][0]) + bx[1] * A[i][1]) + bx[2] * A[i][2]) + bx[3] * A[i][3]);
-    p.y = ((((0.0 + by[0] * A[i][0]) + by[1] * A[i][1]) + by[2] * A[i][2]) + by[3] * A[i][3]);
+    p.x = blin_row<K>(i, bx);
+    p.y = blin_row<K>(i, by);
     const double mt = msqrt(pow2(L.m[i]) + (p.x * p.x + p.y * p.y));
     p.z = mt * L.sh[i]; p.e = mt * L.ch[i];
     pX.x += p.x; pX.y += p.y; pX.z += p.z; pX.e += p.e;
@@ -1603,10 +1703,10 @@ __device__ __forceinline__ bool loop_node_C4(const LoopInv4 &L, const PzConst &p
     if (fabs(dx) > 1e-6 || fabs(dy) > 1e-6 || fabs(dz) > 1e-6 || de > 1e-6) return false;
   }
   double s1, s2;
-  return ladder4_scalars(p1, p2, pX, leg, t1, t2, s1, s2, X);
+  return ladder_scalars<K>(p1, p2, pX, leg, t1, t2, s1, s2, X);
 }
-template <bool SAME>
-__device__ __forceinline__ double screened_amp2_me6(const LoopInv4 &L, const cx &h0) {
+template <bool SAME, int K>
+__device__ __forceinline__ double screened_amp2_ladder(const LoopInvK<K> &L, const cx &h0) {
   const DevLoop &Q = c_loop;
   PzConst        pc;
   pc.s = c_proc.s; pc.t7 = c_proc.sqrt_s; pc.t9 = c_proc.s_pow15; pc.t14 = c_proc.s * c_proc.s;
@@ -1619,9 +1719,9 @@ __device__ __forceinline__ double screened_amp2_me6(const LoopInv4 &L, const cx 
     for (int j = 0; j <= Q.nkt; ++j) {
       const double kt = Q.kt[j];
       double       t1, t2;
-      Ladder4      X;
-      if (!loop_node_C4<SAME>(L, pc, kt * cp, kt * sp, t1, t2, X)) continue;
-      const cx A = regge_me6(t1, t2, X);
+      Ladder<K>    X;
+      if (!loop_node_CK<SAME, K>(L, pc, kt * cp, kt * sp, t1, t2, X)) continue;
+      const cx A = regge_ladder<K>(t1, t2, X);
       Jre = fma(Q.b_re[j], A.re, fma(-Q.b_im[j], A.im, Jre));
       Jim = fma(Q.b_re[j], A.im, fma(Q.b_im[j], A.re, Jim));
     }

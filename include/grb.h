@@ -42,7 +42,7 @@ enum {
 #define GRB_MAX_NODES 16   /* flattened central decay tree nodes (config 5: 2 rho + 4 pi = 6)            */
 #define GRB_MAX_RES 12     /* resonances in a coherent sum (cards use <= 8)                              */
 #define GRB_MAX_VETO 8     /* veto domains                                                               */
-#define GRB_MAX_DIM 16     /* VEGAS dimension bound (<F>: 6, +2 with N* excitation)                      */
+#define GRB_MAX_DIM 20     /* VEGAS dimension bound (<F>: 6 + NSTARS; <C>: 3 Nf - 4 + NSTARS, Nf - 2 = 6 legs: 20)  */
 #define GRB_MAX_TAPE 32    /* internal uniforms per point (config 5 uses 12)                             */
 #define GRB_MAX_BINS 128   /* VEGAS bins per dimension (reference MVEGAS.h BINS default 128)             */
 #define GRB_MAX_LOOP_KT 64 /* screening loop kt nodes (Nkt+1 <= 46 for ND<=10)                           */

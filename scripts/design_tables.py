@@ -1,0 +1,74 @@
+"""Regenerates the measured tables of DESIGN.md (between the <!-- MEASURED --> / <!-- SCALE --> marker pairs) from the bench
+lines committed under profiles/ (r02_bench_<workload>.json, r02_bench_reference_<workload>.json, r02_multi/*.json)."""
+import glob, json, os, re, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def last(path):
+    try:
+        return json.loads(open(path).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def measured():
+    rows = ["| workload | process | points/s (device) | e2e points/s (host buffers) | reference, all host cores | e2e / reference | dominant kernel | ms / launch | roofline frac (algorithmic) | executed frac | fp64 slots |",
+            "|---|---|---|---|---|---|---|---|---|---|---|"]
+    for w in ["c1", "c1t", "c2", "c2t", "c3", "c4", "c4q", "c5", "c5t"]:
+        d, r = last(os.path.join(P, "r02_bench_%s.json" % w)), last(os.path.join(P, "r02_bench_reference_%s.json" % w))
+        if not d:
+            continue
+        rf = d["roofline"]
+        proc = d["config"]["workload"].split(":", 1)[1].strip().split(",")[0]
+        ref = "%.3g (%d cores)" % (r["value"], r["cpu_baseline"]["cores"]) if r and "value" in r else "-"
+        ratio = "%.0f" % (d["e2e"]["value"] / r["value"]) if r and "value" in r else "-"
+        ex = ("%.2f" % rf["executed_frac"]) if rf.get("executed_frac") is not None else "-"
+        sl = ("%.2f" % rf["fp64_slot_frac"]) if rf.get("fp64_slot_frac") is not None else "-"
+        rows.append("| %s | %s | %.3g | %.3g | %s | %s | %s | %.2f | %.2f | %s | %s |" % (
+            w, proc, d["value"], d["e2e"]["value"], ref, ratio, rf.get("kernel", "-").replace("|", "/"), rf.get("launch_ms_avg", float("nan")),
+            rf["frac"], ex, sl))
+    return "\n".join(rows)
+
+
+def scale():
+    rows = ["| N | scaling | workload | communicator | points/s | ms / iteration | kernels | exchange + fetch + sync | host grid refinement | e2e points/s |",
+            "|---|---|---|---|---|---|---|---|---|---|"]
+    items = []
+    for f in glob.glob(os.path.join(P, "r02_multi", "*.json")):
+        d = last(f)
+        if not d:
+            continue
+        comm = "library (NCCL)" if "native" in os.path.basename(f) else "torch.distributed (NCCL)"
+        if d["n_gpus"] == 1:
+            comm = "-"
+        t = d["turnaround_ms_per_step"]
+        items.append((d["config"].get("workload_id", ""), d["n_gpus"], d["scaling"], comm,
+                      "| %d | %s | %s | %s | %.4g | %.3f | %.3f | %.3f | %.3f | %.3g |" % (
+                          d["n_gpus"], d["scaling"], d["config"].get("workload_id", ""), comm, d["value"], d["ms_per_step"], t["device_kernels"],
+                          t["exchange_fetch_sync"], t["host_grid_refinement"], d["e2e"]["value"])))
+    seen = set()
+    for it in sorted(items):
+        key = it[:4]
+        if key in seen:
+            continue
+        seen.add(key)
+        rows.append(it[4])
+    return "\n".join(rows)
+
+
+def main():
+    path = os.path.join(ROOT, "DESIGN.md")
+    s = open(path).read()
+    for tag, fn in (("MEASURED", measured), ("SCALE", scale)):
+        body = "<!-- %s -->\n%s\n<!-- /%s -->" % (tag, fn(), tag)
+        if "@@%s@@" % tag in s:
+            s = s.replace("@@%s@@" % tag, body)
+        else:
+            s = re.sub(r"<!-- %s -->.*?<!-- /%s -->" % (tag, tag), lambda m: body, s, flags=re.S)
+    open(path, "w").write(s)
+
+
+if __name__ == "__main__":
+    main()

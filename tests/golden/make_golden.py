@@ -91,6 +91,10 @@ CASES = [
     ("cc4_cms_4pi_con_screened", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 256, 16, True),
     ("cc_cms_rhorho_4pi_con_born", "./tests/processes/CMSCUTS.json",
      "PP[CON]<C> -> rho(770)0 > {pi+ pi-} rho(770)0 > {pi+ pi-}", 0, 1536, 24, True),
+    # <C> class with six central legs: the 2 -> 8 ladder MRegge::ME8 (20 integration dimensions, 720 orderings)
+    ("cc6_cms_6pi_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 0, 3072, 16, True),
+    ("cc6_cms_4pi2k_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K- pi+ pi-", 0, 3072, 16, True),
+    ("cc6_cms_6pi_con_screened", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 1, 512, 16, True),
 ]
 
 
@@ -104,7 +108,9 @@ def main():
         if only and name not in only:
             continue
         nstars = int(card[1:].split(":", 1)[0].split("=")[1]) if card.startswith("@NSTARS=") else 0
-        u, tape = make_points(n, (14 if name.startswith("cc4_") else 8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)   # (+ NSTARS forward-mass coordinates)
+        u, tape = make_points(n, (20 if name.startswith("cc6_") else 14 if name.startswith("cc4_") else 8 if "<C>" in proc else 6) + nstars, dt, 1000 + i, adapted=adapted)   # (+ NSTARS forward-mass coordinates)
+        if name.startswith("cc6_"):   # five intermediate kt, as for the four-leg ladder
+            u[:, 4:9] *= 0.3
         if name.startswith("cc4_"):   # keep the three intermediate kt below ~0.75 GeV (flat kt up to 2.5 GeV is mostly cut away)
             u[:, 4:7] *= 0.3
         if nstars:   # forward pt up to 50 / 100 GeV with excitation: keep the log-pt coordinates where pt is O(0.05 - 3 GeV)

@@ -101,7 +101,8 @@ def test_device_vs_reference_golden(grb, msa, path):
     # Regge amplitudes reproduce the reference's operation order (median ~1e-15); the tensor-pomeron device
     # code is the contracted closed form of the reference's FTensor loops (median ~1e-13)
     # ... and the resonance code replaces the reference's pow()-based Wigner functions by integer powers
-    loose = "TENSOR" in str(z["process"]) or "RES" in str(z["process"]) or "yy[" in str(z["process"])
+    # ... and the six-leg ladder sums its 720 orderings in factorised groups (kappa median 1e-13 in the reference itself)
+    loose = "TENSOR" in str(z["process"]) or "RES" in str(z["process"]) or "yy[" in str(z["process"]) or os.path.basename(path).startswith("cc6_")
     assert np.median(rel) < (2e-12 if loose else 1e-13)
     kin = (z["flags"] & 1) == 1
     # intermediate scalars: absolute 2e-10 on t (t = dE^2 - dpz^2 - pt^2 cancels O(6500 GeV) roundings), relative elsewhere
@@ -117,12 +118,13 @@ def test_device_vs_reference_golden(grb, msa, path):
                                         ("PP[CON-]<F> -> K+ K-", 1, 10000), ("PP[CON]<F> -> p+ p-", 0, 50000),
                                         ("PP[CON]<C> -> pi+ pi-", 0, 200000), ("PP[CON]<C> -> pi+ pi-", 1, 20000),
                                         ("PP[CON-]<C> -> K+ K-", 1, 5000),
-                                        ("PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 60000), ("PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 6000)])
+                                        ("PP[CON]<C> -> pi+ pi- pi+ pi-", 0, 60000), ("PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 6000),
+                                        ("PP[CON]<C> -> pi+ pi- K+ K- pi+ pi-", 0, 20000), ("PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 1, 600)])
 def test_device_vs_oracle_seeded(grb, msa, proc, pom, n):
     E = engine_for(grb, msa, "c2_alice.json", proc, pom)
-    u, tape = make_points(n, E.desc.lipsdim, 16 if E.desc.n_legs == 4 else 8, 99 + n, adapted=True)
-    if E.desc.n_legs == 4:
-        u[:, 4:7] *= 0.3      # intermediate kt of the four-leg ladder below ~0.75 GeV
+    u, tape = make_points(n, E.desc.lipsdim, 16 if E.desc.n_legs >= 4 else 8, 99 + n, adapted=True)
+    if E.desc.n_legs >= 4:
+        u[:, 4:3 + E.desc.n_legs] *= 0.3      # intermediate kt of the four- / six-leg ladder below ~0.75 GeV
     o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
     w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
     nz = o["w"] != 0
@@ -131,7 +133,11 @@ def test_device_vs_oracle_seeded(grb, msa, proc, pom, n):
     assert np.array_equal(w != 0, nz)
     rel = np.abs(w[nz] - o["w"][nz]) / np.abs(o["w"][nz])
     # no per-point kappa here: allow the documented ill-conditioned tail (< 1e-3 of points, < 1e-8)
-    assert np.mean(rel > RTOL) < 1e-3 and rel.max() < 1e-8 and np.median(rel) < 1e-13, (rel.max(), np.mean(rel > RTOL))
+    if E.desc.n_legs == 6:   # 720 orderings with propagator poles inside the phase space: the reference's own 1-ulp conditioning
+        # has a median of 1e-13 and reaches 2e-10 within 122 golden points (tests/golden/cc6_*.npz)
+        assert np.mean(rel > RTOL) < 1e-2 and rel.max() < 1e-6 and np.median(rel) < 2e-12, (rel.max(), np.mean(rel > RTOL), np.median(rel))
+    else:
+        assert np.mean(rel > RTOL) < 1e-3 and rel.max() < 1e-8 and np.median(rel) < 1e-13, (rel.max(), np.mean(rel > RTOL))
     E.close()
 
 
@@ -328,19 +334,21 @@ def test_energy_scan_and_reparameterisation(grb, msa):
     E.close(); E2.close()
 
 
-def test_four_leg_ladder_vegas_path(grb, msa):
-    """PP[CON]<C> -> pi+ pi- pi+ pi- (MRegge::ME6, 14 VEGAS dimensions): the device iteration equals grb_eval on the same
-    Philox points regenerated on the host, the histogram marginals equal the scalar sums in all 14 dimensions (bins of
-    the dimensions 8..13 travel in a second packed word), and a full adaptive integration converges."""
+@pytest.mark.parametrize("legs", [4, 6])
+def test_ladder_vegas_path(grb, msa, legs):
+    """PP[CON]<C> -> 4 pi / 6 pi (MRegge::ME6 / ME8, 14 / 20 VEGAS dimensions): the device iteration equals grb_eval on the
+    same Philox points regenerated on the host, the histogram marginals equal the scalar sums in every dimension (bins of
+    the dimensions 8..15 travel in a second packed word, 16..19 in a third), and a full adaptive integration ends like the
+    reference's."""
     from philox_ref import philox_points
-    E = engine_for(grb, msa, "c5_cms_4pi.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 0)
-    bins, dim, N = 128, 14, 8192
+    E = engine_for(grb, msa, "c5_cms_4pi.json", "PP[CON]<C> ->" + " pi+ pi-" * (legs // 2), 0)
+    bins, dim, N = 128, 3 * legs + 2, 8192 if legs == 4 else 16384
     assert E.desc.lipsdim == dim
     rng = np.random.default_rng(9)
     edges = np.sort(rng.random((bins - 1, dim)), axis=0)
-    edges[:, 4:7] *= 0.3                                  # intermediate kt below ~0.75 GeV
+    edges[:, 4:3 + legs] *= 0.3                                  # intermediate kt below ~0.75 GeV
     xmat = np.vstack([edges, np.ones((1, dim))])
-    xmat[-1, 4:7] = 0.3
+    xmat[-1, 4:3 + legs] = 0.3
     a = E.vegas_iterate(xmat, 500, N, 4711, 1)
     u, vw, tape = philox_points(xmat, 500, N, 4711, 1, ntape=16)
     w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
@@ -353,7 +361,10 @@ def test_four_leg_ladder_vegas_path(grb, msa):
     assert np.all(fm[:, dim:] == 0)
     o = oracle_eval(E.desc, None, u[:512], tape[:512])
     nz = o["w"] != 0
-    assert np.array_equal(w[:512] != 0, nz) and np.max(np.abs(w[:512][nz] - o["w"][nz]) / o["w"][nz]) < 1e-10
+    assert np.array_equal(w[:512] != 0, nz) and np.max(np.abs(w[:512][nz] - o["w"][nz]) / o["w"][nz]) < (1e-10 if legs == 4 else 1e-9)
+    if legs == 6:   # (the 20-dimensional integration needs far more calls than a test should spend)
+        E.close()
+        return
     # The ladder ansatz has propagator poles 1 / (tt - M^2) inside this phase space (a single flat-grid point carries a weight
     # of 1e24 b), so the adaptive integration runs into them and stops with the reference's own diagnosis -- the reference
     # CLI ends the same way on this card ("VEGAS:: Integral inf/nan: FATAL ERROR, cuts or parameters need fixing").

@@ -58,7 +58,28 @@ def scale():
     return "\n".join(rows)
 
 
+def readme():
+    d, r = last(os.path.join(P, "r02_bench_c2.json")), last(os.path.join(P, "r02_bench_reference_c2.json"))
+    rf = d["roofline"]
+    txt = ("headline `configs[1]` (`PP[CON]<F> -> pi+ pi-`, ALICE cuts, screening loop on, fp64): **%.3g screened weights/s** device-timed, "
+           "**%.3g/s end to end** through the C ABI with host buffers" % (d["value"], d["e2e"]["value"]))
+    if r and "value" in r:
+        txt += " = %.0f x the unmodified reference on %d host cores" % (d["e2e"]["value"] / r["value"], r["cpu_baseline"]["cores"])
+    txt += ("; `k_screen` %.2f ms per 2^23-point launch, fp64 pipe slots %.0f %% busy (executed flops %.2f of the DFMA peak, algorithmic "
+            "flops by the survey convention %.2f)." % (rf["launch_ms_avg"], 100 * (rf.get("fp64_slot_frac") or 0), rf.get("executed_frac") or 0, rf["frac"]))
+    m8 = last(os.path.join(P, "r02_multi", "bench_m8_weak_torch.json"))
+    m8s = last(os.path.join(P, "r02_multi", "bench_m8_strong_native.json"))
+    if m8 and m8s:
+        txt += "  8 GPUs: %.3g/s weak-scaled, %.3g/s strong-scaled (2^24 points in total per iteration)." % (m8["value"], m8s["value"])
+    return txt
+
+
 def main():
+    rp = os.path.join(ROOT, "README.md")
+    rs = open(rp).read()
+    body = "<!-- STATE -->%s<!-- /STATE -->" % readme()
+    rs = rs.replace("@@README@@", body) if "@@README@@" in rs else re.sub(r"<!-- STATE -->.*?<!-- /STATE -->", lambda m: body, rs, flags=re.S)
+    open(rp, "w").write(rs)
     path = os.path.join(ROOT, "DESIGN.md")
     s = open(path).read()
     for tag, fn in (("MEASURED", measured), ("SCALE", scale)):

@@ -345,14 +345,19 @@ def run_ours(args):
     # ---- e2e: the same metric through the C ABI with HOST buffers (seam A x n) --------------------------------------
     # grb_eval_rng = MProcess::EventWeight(randvec) as the reference calls it: the caller supplies the coordinates, the
     # internal uniforms come from the engine's generator.  grb_eval (coordinates + a caller tape) is timed beside it.
-    n_e2e = args.e2e_points
+    # One call carries the batch of one step (2^24 points per GPU by default, like the device-timed iteration); the host
+    # restatement of the Philox stream makes 2^22 distinct points through the converged grid, tiled to the batch size.
+    n_e2e = args.e2e_points if args.e2e_points > 0 else max(1 << 20, min(int(ncalls), 1 << 24))
+    n_distinct = min(n_e2e, 1 << 22)
     hu = torch.empty((dim, n_e2e), dtype=torch.float64).pin_memory()
     ht = torch.empty((ntape, n_e2e), dtype=torch.float64).pin_memory()
     hw = torch.empty(n_e2e, dtype=torch.float64).pin_memory()
     hf = torch.empty(n_e2e, dtype=torch.uint8).pin_memory()
-    pu, ptape = synthetic_points(wl, n_e2e, dim, ntape, 1234, first=rank * n_e2e)
-    hu.numpy()[:] = pu.T
-    ht.numpy()[:] = ptape.T
+    pu, ptape = synthetic_points(wl, n_distinct, dim, ntape, 1234, first=rank * n_distinct)
+    for o in range(0, n_e2e, n_distinct):
+        m = min(n_distinct, n_e2e - o)
+        hu.numpy()[:, o:o + m] = pu.T[:, :m]
+        ht.numpy()[:, o:o + m] = ptape.T[:, :m]
     del pu, ptape
     e2e_steps = max(3, min(args.steps, 10))
     e2e = {}
@@ -447,7 +452,7 @@ def run_ours(args):
                 "gpu_launches": int(state["launches"]),
                 "e2e": {"value": n_e2e * world * e2e_steps / e2e_rng_s, "unit": UNIT,
                         "h2d_bytes_per_step": h2d_rng, "d2h_bytes_per_step": int(9 * n_e2e),
-                        "points_per_step_per_gpu": n_e2e, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
+                        "points_per_step_per_gpu": n_e2e, "distinct_points": n_distinct, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
                         "api": "grb_eval_rng (seam A x n: coordinates from pinned host memory, internal draws from the engine's "
                                "Philox stream like the reference's per-thread generator), H2D + D2H inside the timed region",
                         "with_caller_tape": {"value": n_e2e * world * e2e_steps / e2e_tape_s, "api": "grb_eval",
@@ -477,7 +482,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--comm", default="torch", choices=["torch", "native"])
     ap.add_argument("--ncalls", type=int, default=1 << 24, help="VEGAS points per step per GPU (weak) or in total (strong)")
-    ap.add_argument("--e2e-points", type=int, default=1 << 22)
+    ap.add_argument("--e2e-points", type=int, default=0, help="points per e2e call per GPU (0 = the step's own batch, at most 2^24)")
     ap.add_argument("--cpu-points", type=int, default=0, help="cpu_baseline sample: points per host process (0 = per workload)")
     ap.add_argument("--ref-points", type=int, default=0, help="--impl reference: points per host process per step")
     ap.add_argument("--no-cpu", action="store_true")

@@ -15,6 +15,7 @@ enum { IT_P1X = 0, IT_P1Y, IT_P2X, IT_P2Y, IT_M1, IT_M2, IT_MXSQ, IT_SHY, IT_CHY
        IT_CK = 30,
        IT_EXC = 35,  // lts.excite1/2 bits of the point (forward N* excitation)
        IT_NF = 40 };
+static_assert(IT_NF == ITEM_ROWS, "the work-list allocation (grb_api.cu) and the row layout disagree");
 __host__ __device__ constexpr int ladder_row(int r) { return r < 11 ? 6 + r : (r < 24 ? 22 + (r - 11) : 36 + (r - 24)); }
 
 

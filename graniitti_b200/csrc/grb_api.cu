@@ -85,7 +85,7 @@ static ConstSlot         g_const[64];
 static inline ConstSlot &const_slot(int device) { return g_const[(unsigned)device % 64u]; }
 static thread_local std::string g_last_global_error;
 
-#define ITEM_NF 36  /* = IT_NF of grb_accum.cuh */
+#define ITEM_NF grb::ITEM_ROWS  /* rows of the screening work list (grb_dev.cuh; = IT_NF of grb_accum.cuh, asserted there) */
 
 #define CK(call)                                                                                   \
   do {                                                                                             \

@@ -18,6 +18,8 @@
 #include "grb_fastmath.cuh"
 
 namespace grb {
+constexpr int ITEM_ROWS = 40;  // rows of the screening work list (the layout is the IT_* enum of grb_accum.cuh)
+
 
 // reference include/Graniitti/MMath.h:30
 #define GRB_PI 3.141592653589793238462643383279502884197169399375105820974944

@@ -2,11 +2,9 @@
 # round-2 side measurements: variants table, e2e with the step's own batch size, memcheck of small runs of every kernel family
 mkdir -p gpurun_out
 ( timeout 420 python scripts/bench_variants.py > gpurun_out/r02_variants.txt ) 2> gpurun_out/variants.err; cat gpurun_out/r02_variants.txt; tail -3 gpurun_out/variants.err
-for n in 4194304 16777216; do
-python bench.py --steps 5 --warmup 3 --no-cpu --e2e-points $n > gpurun_out/bench_e2e_$n.json 2>/dev/null
+( time python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_e2e_default.json 2>/dev/null ) 2>&1 | grep real
 python -c "
-import json; d=json.loads(open('gpurun_out/bench_e2e_$n.json').read().strip().splitlines()[-1]); print('e2e points $n: value %.4e e2e %.4e tape %.4e' % (d['value'], d['e2e']['value'], d['e2e']['with_caller_tape']['value']))"
-done
+import json; d=json.loads(open('gpurun_out/bench_e2e_default.json').read().strip().splitlines()[-1]); print('default e2e batch %d: value %.4e e2e %.4e tape %.4e' % (d['e2e']['points_per_step_per_gpu'], d['value'], d['e2e']['value'], d['e2e']['with_caller_tape']['value']))"
 cat > /tmp/mc.py <<'PY'
 import os, sys, numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")

@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(kp_threads(AMP), kp_minb(AMP)) k_points(const 
     cx         h0 = {0.0, 0.0};
     double     pref = 0.0;
     if (valid) {
+      pref = P.ps_class == GRB_CLASS_C ? weight_prefactor_C<NN>(S) : weight_prefactor<NN>(S);
       if (LADDER) h0 = regge_ladder<KL>(S.t1, S.t2, X4);
       else h0 = born_amplitude<NN, AMP>(S);
-      pref = P.ps_class == GRB_CLASS_C ? weight_prefactor_C<NN>(S) : weight_prefactor<NN>(S);
       if (!P.screening) {
         W = pref * (h0.re * h0.re + h0.im * h0.im);
         if (isnan(W) || isinf(W)) { W = 0.0; amp_ok = false; }

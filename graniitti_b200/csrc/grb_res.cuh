@@ -64,14 +64,31 @@ __device__ __forceinline__ void wigner_small_d(double theta, double d[N][N]) {
     }
 }
 
+// e_j = exp(i M_j phi), M_j = j - J (N = 2J + 1 = 3, 5): one sincos and the double-angle identities instead of N calls of
+// sincos(M phi) (the reference evaluates each phase on its own; the identities agree with that to 2 ulp, and the kernel is
+// bound by instruction fetch: each inlined double-precision sincos is ~80 instructions of code)
+template <int N>
+__device__ __forceinline__ void azimuthal_phases(double phi, cx e[N]) {
+  constexpr int J = (N - 1) / 2;
+  double s1, c1;
+  sincos(phi, &s1, &c1);
+  e[J] = {1.0, 0.0};
+  e[J + 1] = {c1, s1};
+  e[J - 1] = {c1, -s1};
+  if (N == 5) {
+    const double c2 = (c1 - s1) * (c1 + s1), s2 = 2.0 * s1 * c1;
+    e[J + 2 < N ? J + 2 : 0] = {c2, s2};
+    e[J - 2 >= 0 ? J - 2 : 0] = {c2, -s2};
+  }
+}
+
 // rho_ROT = D^+ rho D with D_{m mp} = d_{m mp}(theta) e^{i mp phi}
 template <int N>
 __device__ __forceinline__ void rotated_rho(const DevResonance &r, double th, double ph, cx out[N][N]) {
   double d[N][N];
   wigner_small_d<N>(th, d);
   cx e[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) sincos((double)(j - (N - 1) / 2) * ph, &e[j].im, &e[j].re);
+  azimuthal_phases<N>(ph, e);
   // t = rho * D : t[k][j] = sum_l rho[k][l] d[l][j] e_j
   cx t[N][N];
 #pragma unroll
@@ -98,13 +115,12 @@ __device__ __forceinline__ void rotated_rho(const DevResonance &r, double th, do
 // Re[ f rho f^+ ] for one row f_j = d_{lambda, M_j}(theta) e^{i M_j phi} * T  (|T|^2 factored out by the caller)
 template <int N>
 __device__ __forceinline__ double row_weight(const cx rho[N][N], const double d[N][N], int row, double phi) {
-  cx f[N];
+  cx f[N], e[N];
+  azimuthal_phases<N>(phi, e);
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    double sn, cs;
-    sincos((double)(j - (N - 1) / 2) * phi, &sn, &cs);
-    f[j].re = d[row][j] * cs;
-    f[j].im = d[row][j] * sn;
+    f[j].re = d[row][j] * e[j].re;
+    f[j].im = d[row][j] * e[j].im;
   }
   double acc = 0.0;
 #pragma unroll

@@ -46,6 +46,30 @@ ncu -i /tmp/prof_generic.ncu-rep --page details > gpurun_out/${TAG}_k_screen_gen
 ncu -i /tmp/prof_generic.ncu-rep --page source --csv > gpurun_out/prof_generic_source.csv 2>/dev/null
 python scripts/ncu_opcode_mix.py gpurun_out/prof_generic_source.csv > gpurun_out/${TAG}_k_screen_generic_opcode_mix.txt 2>/dev/null
 python scripts/parity_stats.py > gpurun_out/${TAG}_parity_stats.txt 2>&1; tail -3 gpurun_out/${TAG}_parity_stats.txt
+( timeout 300 python scripts/bench_variants.py > gpurun_out/${TAG}_variants.txt ) 2> gpurun_out/variants.err; tail -4 gpurun_out/${TAG}_variants.txt
+# compute-sanitizer memcheck over small runs of every kernel family (integration and generation mode)
+cat > /tmp/mc.py <<'PY'
+import os, sys, numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import graniitti_b200 as g
+from helpers import CARDS, GOLDEN
+msa = np.load(os.path.join(GOLDEN, "msa_pp_13000.npy"))
+for card, proc, pom, n in (("c2_alice.json", None, 1, 20000), ("c2_alice.json", "PP[CONTENSOR]<F> -> pi+ pi-", 1, 8000), ("c1_test13.json", None, 0, 20000),
+                           ("c4_cms_mumu_lowmass.json", None, 0, 20000), ("c5_cms_4pi.json", None, 0, 20000),
+                           ("c5_cms_4pi.json", "PP[CON]<C> -> pi+ pi- pi+ pi-", 1, 4000), ("c5_cms_4pi.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 1, 1500),
+                           ("c5_cms_4pi.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 0, 8000)):
+    E = g.Engine(card=os.path.join(CARDS, card), process=proc, pomloop=pom)
+    if E.desc.screening: E.set_eikonal(msa[0], msa[1], msa[2])
+    dim, legs = E.desc.lipsdim, E.desc.n_legs
+    xmat = np.tile(((np.arange(128) + 1) / 128.0)[:, None], (1, dim))
+    if legs >= 4: xmat[:, 4:3 + legs] *= 0.3
+    a = E.vegas_iterate(xmat, 0, n, 7, 1)
+    b = E.vegas_iterate(xmat, 0, n, 7, 1, mode=g._abi.GRB_MODE_GENERATE, maxf=max(a.maxf, 1e-300))
+    print(card, proc, "evaluations", a.evaluations, "fid", a.n_fid_ok, "fsum", a.fsum)
+    E.close()
+PY
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python /tmp/mc.py > gpurun_out/r02_memcheck.txt 2>&1; echo "memcheck rc=$?"; tail -2 gpurun_out/r02_memcheck.txt
+
 # the second bench pass uses the freshly measured SASS mixes (executed flops, fp64 slot fraction)
 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2>> gpurun_out/bench_$TAG.err; tail -c 1800 gpurun_out/${TAG}_bench_n1.json
 du -sh gpurun_out

@@ -74,7 +74,43 @@ def readme():
     return txt
 
 
+def kp_table():
+    mix = {}
+    try:
+        mix = json.load(open(os.path.join(P, "r02_sass_mix.json")))
+    except Exception:
+        pass
+    rows = ["| workload | kernel | points/s per VEGAS iteration | ms per 2^23-point launch | registers | instructions / point (fp64) | fp64 pipe | issue active |",
+            "|---|---|---|---|---|---|---|---|"]
+    for w in ["c1", "c3", "c4", "c4q", "c5", "c5t", "c1t"]:
+        d = last(os.path.join(P, "r02_bench_%s.json" % w))
+        if not d:
+            continue
+        rf = d["roofline"]
+        m = mix.get("%s:k_points" % w, {})
+        ins = "%.0f (%.0f)" % (m["all_instructions"], m["dfma"] + m["dmul"] + m["dadd"] + m.get("dsetp", 0)) if m and m.get("unit") == "point" else "-"
+        rows.append("| %s | `%s` | %.3g | %.2f | %s | %s | %s | %s |" % (
+            w, m.get("kernel", rf.get("kernel", "k_points")).replace("void grb::", "").replace("(grb::PointArgs)", "").replace("(int)", "").replace("(bool)", ""),
+            d["value"], rf.get("launch_ms_avg", float("nan")), ("%.0f" % m["registers"]) if m else "-", ins,
+            ("%.0f %%" % m["fp64_pipe_pct"]) if m else "-", ("%.0f %%" % m["issue_active_pct"]) if m else "-"))
+    return "\n".join(rows)
+
+
+def profiles_readme():
+    rp = os.path.join(P, "README.md")
+    s = open(rp).read()
+    d = last(os.path.join(P, "r02_bench_c2.json"))
+    for tag, val in (("C2V", "%.3g" % d["value"]), ("C2MS", "%.2f" % d["ms_per_step"]), ("C2E", "%.3g" % d["e2e"]["value"])):
+        body = "<!-- %s -->%s<!-- /%s -->" % (tag, val, tag)
+        s = s.replace("@@%s@@" % tag, body) if "@@%s@@" % tag in s else re.sub(r"<!-- %s -->.*?<!-- /%s -->" % (tag, tag), lambda m: body, s, flags=re.S)
+    for tag, fn in (("KP", kp_table), ("MG", scale)):
+        body = "<!-- %s -->\n%s\n<!-- /%s -->" % (tag, fn(), tag)
+        s = s.replace("@@%s@@" % tag, body) if "@@%s@@" % tag in s else re.sub(r"<!-- %s -->.*?<!-- /%s -->" % (tag, tag), lambda m: body, s, flags=re.S)
+    open(rp, "w").write(s)
+
+
 def main():
+    profiles_readme()
     rp = os.path.join(ROOT, "README.md")
     rs = open(rp).read()
     body = "<!-- STATE -->%s<!-- /STATE -->" % readme()

@@ -305,7 +305,7 @@ def run_ours(args):
             else:
                 with torch.cuda.stream(ext):
                     g.allreduce_accum(torch.as_tensor(g.DevArray(ptr, nacc + 2 * world), device=torch.device("cuda", local)), rank, world)
-        acc = E.vegas_fetch()                      # D2H of the accumulators (33 KB) + stream sync
+        acc = E.vegas_fetch()                      # D2H of the accumulators (41 KB) + stream sync
         t_b = time.perf_counter()
         f2 = np.frombuffer(acc.f2mat, dtype=np.float64).reshape(_abi.GRB_MAX_BINS, _abi.GRB_MAX_DIM).copy()
         g.optimize_grid(state["xmat"], f2, 1.5)    # identical on every rank

@@ -9,7 +9,9 @@ import sys
 
 def main(path):
     rows = list(csv.reader(open(path)))
-    kernel, hdr, data = rows[0][1], rows[1], rows[2:]
+    kernel, hdr = rows[0][1], rows[1]
+    kernel = next((r[1] for r in rows if len(r) >= 2 and len(r) < 8 and ("k_points" in r[1] or "k_screen" in r[1])), kernel)
+    data = [r for r in rows[2:] if len(r) == len(hdr) and r != hdr]   # (device functions called from the kernel: own header rows)
     ia, isrc, isamp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
     stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[ia]) for r in data)

@@ -15,7 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def main(key, src, raw, log):
     rows = list(csv.reader(open(src)))
-    kernel, hdr, data = rows[0][1], rows[1], rows[2:]
+    kernel, hdr = rows[0][1], rows[1]
+    kernel = next((r[1] for r in rows if len(r) >= 2 and len(r) < 8 and ("k_points" in r[1] or "k_screen" in r[1])), kernel)
+    data = [r for r in rows[2:] if len(r) == len(hdr) and r != hdr]   # (device functions called from the kernel: own header rows)
     it, isrc = hdr.index("Thread Instructions Executed"), hdr.index("Source")
     iw = hdr.index("Instructions Executed")
     th, wp = collections.Counter(), collections.Counter()

@@ -42,11 +42,17 @@ __device__ __forceinline__ void store_momenta(double *dst, int64_t stride, const
 // the full register file (45.5 ms; 48.8 at 128 x 3, 49.6 at 256 x 2)
 // Round 2 (profiles/r02_kp_threads_sweep.txt): HELAS at 64 x 4 (same 255 registers, shorter waits at the final barrier:
 // 2.02e8 -> 2.16e8 points/s), tensor 2xS at 128 x 4 (1.77e9 -> 1.90e9)
+#ifndef GRB_KP_RES_THREADS   // (build-time knobs of the launch-shape sweeps: -DGRB_KP_RES_THREADS=.. -DGRB_KP_RES_MINB=..)
+#define GRB_KP_RES_THREADS 128
+#endif
+#ifndef GRB_KP_RES_MINB
+#define GRB_KP_RES_MINB 3
+#endif
 __host__ __device__ constexpr int kp_threads(int amp) {
-  return (amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON || amp == AMP_TENSOR_2XS) ? 128 : (amp == AMP_YY_LL ? 64 : 256);
+  return (amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? GRB_KP_RES_THREADS : (amp == AMP_TENSOR_2XS ? 128 : (amp == AMP_YY_LL ? 64 : 256));
 }
 __host__ __device__ constexpr int kp_minb(int amp) {
-  return amp == AMP_REGGE ? 2 : ((amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? 3 : ((amp == AMP_TENSOR_2XS || amp == AMP_YY_LL) ? 4 : 1));
+  return amp == AMP_REGGE ? 2 : ((amp == AMP_REGGE_RES || amp == AMP_REGGE_RES_CON) ? GRB_KP_RES_MINB : ((amp == AMP_TENSOR_2XS || amp == AMP_YY_LL) ? 4 : 1));
 }
 
 // ---- Born amplitude dispatch (reference seam B, MSubProc::GetBareAmplitude2) -----------------------------

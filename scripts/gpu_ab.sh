@@ -1,7 +1,7 @@
 #!/bin/bash
-# A/B of library builds on one box: GRB_LIB=<variant> python bench.py --workload W
+# A/B of library builds on one box: GRB_LIB=<variant> python bench.py --workload W.  usage: bash scripts/gpu_ab.sh "<workloads>" "<variants>"
 mkdir -p gpurun_out
-for w in c1 c4 c5; do for v in head phases work; do
+for w in ${1:-c1}; do for v in ${2:-work}; do
 lib=graniitti_b200/libgrb_$v.so; [ $v = work ] && lib=graniitti_b200/libgrb.so
 GRB_LIB=$PWD/$lib python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_ab_${w}_$v.json 2>/dev/null
 python -c "

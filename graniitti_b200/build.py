@@ -37,6 +37,10 @@ def build_lib(force=False, verbose=False, out=None, extra=()):
     os.makedirs(objdir, exist_ok=True)
     hdrs = _headers()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    lib = out or LIB
+    # a library that is newer than every source and header is up to date even when the object directory did not travel
+    if not force and not extra and not _newer(lib, [os.path.join(CSRC, s) for s in srcs] + hdrs):
+        return lib
     jobs = []
     for s in srcs:
         src, obj = os.path.join(CSRC, s), os.path.join(objdir, s + ".o")
@@ -46,7 +50,6 @@ def build_lib(force=False, verbose=False, out=None, extra=()):
         for rc in ex.map(subprocess.call, jobs):
             if rc != 0:
                 raise subprocess.CalledProcessError(rc, "nvcc -c")
-    lib = out or LIB
     objs = [os.path.join(objdir, s + ".o") for s in srcs]
     if jobs or _newer(lib, objs):
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-rdc=true", "-shared", "-Xcompiler", "-fPIC",

@@ -3,7 +3,7 @@
 The layout is checked against the compiled library by `grb_abi_sizeof` (tests/test_abi.py)."""
 import ctypes as C
 
-GRB_ABI_VERSION = 2
+GRB_ABI_VERSION = 3
 GRB_MAX_NODES = 16
 GRB_MAX_RES = 12
 GRB_MAX_VETO = 8
@@ -18,6 +18,7 @@ GRB_OK, GRB_ERR_ARG, GRB_ERR_CUDA, GRB_ERR_UNSUPPORTED, GRB_ERR_PARSE, GRB_ERR_S
 
 GRB_PROC_YY_CON, GRB_PROC_YY_QED, GRB_PROC_PP_RES = 3, 4, 9
 GRB_PROC_PP_CONTENSOR, GRB_PROC_PP_CON, GRB_PROC_PP_CON_MINUS, GRB_PROC_PP_RES_CON = 12, 15, 16, 17
+GRB_PROC_PP_RESTENSOR, GRB_PROC_PP_RES_CONTENSOR = 11, 14
 
 GRB_FLAG_KIN, GRB_FLAG_FID, GRB_FLAG_VETO, GRB_FLAG_AMP = 1, 2, 4, 8
 GRB_FLAGS_VALID = 7
@@ -72,7 +73,7 @@ class ParamTensorPom(C.Structure):
 class Resonance(C.Structure):
     _fields_ = [("pdg", i32), ("spinX2", i32), ("P", i32), ("BW", i32), ("spingen", i32), ("spindec", i32),
                 ("frame", i32), ("jmax", i32), ("mass", f64), ("width", f64), ("g_re", f64), ("g_im", f64),
-                ("g_FF", f64), ("g_decay", f64), ("BR", f64), ("g_Tensor", f64 * 8),
+                ("g_FF", f64), ("g_decay", f64), ("BR", f64), ("g_Tensor", f64 * 8), ("g_decay_tensor", f64 * 2),
                 ("rho_re", f64 * (GRB_RHO_DIM * GRB_RHO_DIM)), ("rho_im", f64 * (GRB_RHO_DIM * GRB_RHO_DIM)),
                 ("T_re", f64 * 9), ("T_im", f64 * 9), ("T_rows", i32), ("T_cols", i32)]
 

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgrb.so")
 SOURCES = ["grb_consts.cu", "grb_points_regge.cu", "grb_points_tensor.cu", "grb_points_res.cu", "grb_points_rescon.cu",
-           "grb_points_yy.cu", "grb_points_tensorvv.cu", "grb_points_tensorff.cu", "grb_points_yyqed.cu", "grb_points_me6.cu", "grb_points_me8.cu", "grb_kernels_screen.cu", "grb_api.cu", "grb_eikonal.cu", "grb_host.cc", "grb_events.cc"]
+           "grb_points_yy.cu", "grb_points_tensorvv.cu", "grb_points_tensorff.cu", "grb_points_yyqed.cu", "grb_points_me6.cu", "grb_points_me8.cu", "grb_points_tres.cu", "grb_points_trescon.cu", "grb_kernels_screen.cu", "grb_api.cu", "grb_eikonal.cu", "grb_host.cc", "grb_events.cc"]
 # -rdc=true: the __constant__ parameter blocks are defined once (grb_consts.cu) and shared by all kernel TUs
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-rdc=true",
               "-Xcompiler", "-fPIC"]

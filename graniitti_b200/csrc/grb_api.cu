@@ -124,7 +124,8 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
   if (d.flatamp != 0) { err = "@FLATAMP is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.flatmass2 != 0) { err = "FLATMASS2 sampling is outside the device path"; return GRB_ERR_UNSUPPORTED; }
   if (d.proc != GRB_PROC_PP_CON && d.proc != GRB_PROC_PP_CON_MINUS && d.proc != GRB_PROC_PP_CONTENSOR &&
-      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON && d.proc != GRB_PROC_YY_CON && d.proc != GRB_PROC_YY_QED) {
+      d.proc != GRB_PROC_PP_RES && d.proc != GRB_PROC_PP_RES_CON && d.proc != GRB_PROC_YY_CON && d.proc != GRB_PROC_YY_QED &&
+      d.proc != GRB_PROC_PP_RESTENSOR && d.proc != GRB_PROC_PP_RES_CONTENSOR) {
     err = "process id " + std::to_string(d.proc) + " has no device amplitude yet";
     return GRB_ERR_UNSUPPORTED;
   }
@@ -255,6 +256,9 @@ static int digest(const grb_process_desc &d, DevProc &P, std::string &err) {
     }
     if (d.proc == GRB_PROC_PP_CONTENSOR && d.nodes[0].spinX2 == 1) P.amp_kind = 6;  // 2xF (MTensorPomeron.cc:765-804)
     if (d.proc == GRB_PROC_YY_QED) P.amp_kind = 7;                                    // QED branch (:664-713)
+    if (d.proc == GRB_PROC_PP_RESTENSOR) P.amp_kind = 10;       // MTensorPomeron::ME3 (grb_tres.cuh)
+    if (d.proc == GRB_PROC_PP_RES_CONTENSOR) P.amp_kind = 11;   // ME4 (2xS) + ME3, PROC_14
+    if (d.proc == GRB_PROC_PP_RESTENSOR || d.proc == GRB_PROC_PP_RES_CONTENSOR) P.tp_vv_coupling = 9.0 * d.tpom.gPNN * d.tpom.gPNN;
     if (me6) P.amp_kind = 8;                                                          // MRegge::ME6 ladder
     if (me8) P.amp_kind = 9;                                                          // MRegge::ME8 ladder
     P.tp_ff_coupling = 81.0 * std::pow(d.tpom.gPNN, 4);
@@ -360,6 +364,11 @@ static double hfact(int n) {
 static int digest_res(const grb_process_desc &d, DevRes &R, std::string &err) {
   memset(&R, 0, sizeof(R));
   if (d.n_res < 0 || d.n_res > GRB_MAX_RES) { err = "bad n_res"; return GRB_ERR_ARG; }
+  const bool tensor_res = d.proc == GRB_PROC_PP_RESTENSOR || d.proc == GRB_PROC_PP_RES_CONTENSOR;
+  if (tensor_res && !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0 && d.n_nodes == 2 && d.n_legs == 2)) {
+    err = "PP[RESTENSOR] / PP[RES+CONTENSOR]: two pseudoscalar daughters have a device amplitude (vector / photon pairs do not)";
+    return GRB_ERR_UNSUPPORTED;
+  }
   if ((d.proc == GRB_PROC_PP_RES || d.proc == GRB_PROC_PP_RES_CON) && d.n_res > 0 &&
       !(d.nodes[0].spinX2 == 0 && d.nodes[1].spinX2 == 0 && d.n_nodes == 2)) {
     err = "resonances: only two spinless final-state daughters are on the device path";
@@ -371,6 +380,19 @@ static int digest_res(const grb_process_desc &d, DevRes &R, std::string &err) {
     DevResonance &       o = R.r[i];
     if (s.spinX2 < 0 || s.spinX2 > 4 || (s.spinX2 % 2) != 0) { err = "resonance spin must be J = 0, 1 or 2 on the device path"; return GRB_ERR_UNSUPPORTED; }
     if (s.T_rows != 1 || s.T_cols != 1) { err = "resonance decay T matrix must be 1x1 (spinless daughters)"; return GRB_ERR_UNSUPPORTED; }
+    if (tensor_res) {   // MTensorPomeron::ME3: J^P = 0+ and J = 2 (src/MTensorPomeron.cc:232-270,414-560)
+      const int J = (int)(s.spinX2 / 2.0);
+      if (!((J == 0 && s.P == 1) || J == 2)) {
+        err = "MTensorPomeron::ME3: J^P = 0+ and J = 2 resonances have a device amplitude (1- photoproduction and 0- -> gamma gamma do not)";
+        return GRB_ERR_UNSUPPORTED;
+      }
+      tres::ResPar &t = R.tp[i];
+      t.J = J; t.on = 0; t.M0sq = s.mass * s.mass; t.M0G = s.mass * s.width; t.gd = s.g_decay_tensor[0];
+      for (int k = 0; k < 7; ++k) {
+        t.g[k] = s.g_Tensor[k];
+        if (k >= 1 && std::abs(s.g_Tensor[k]) > 1e-6) t.on |= 1 << k;   // EPSILON of iG_PPT_total, :1660-1672
+      }
+    }
     o.spinX2 = s.spinX2; o.P = s.P; o.BW = s.BW; o.spingen = s.spingen; o.spindec = s.spindec; o.frame = s.frame;
     o.photo = ((int)(s.spinX2 / 2.0) == 1 && s.P == -1) ? 1 : 0;
     o.mass = s.mass; o.width = s.width; o.M2 = s.mass * s.mass; o.g_re = s.g_re; o.g_im = s.g_im;

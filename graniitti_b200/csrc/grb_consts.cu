@@ -53,6 +53,8 @@ int launch_points(const PointArgs &a_in, int n_nodes, int amp_kind, int sm_count
     case AMP_YY_QED: launch_points_amp<AMP_YY_QED>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_ME6: launch_points_amp<AMP_REGGE_ME6>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     case AMP_REGGE_ME8: launch_points_amp<AMP_REGGE_ME8>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_TENSOR_RES: launch_points_amp<AMP_TENSOR_RES>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
+    case AMP_TENSOR_RES_CON: launch_points_amp<AMP_TENSOR_RES_CON>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
     default: launch_points_amp<AMP_REGGE>(a, n_nodes, (unsigned)blocks, threads, smem, st); break;
   }
   return 1;

@@ -16,6 +16,7 @@
 
 #include "../../include/grb.h"
 #include "grb_fastmath.cuh"
+#include "grb_tres.cuh"
 
 namespace grb {
 constexpr int ITEM_ROWS = 40;  // rows of the screening work list (the layout is the IT_* enum of grb_accum.cuh)
@@ -95,6 +96,7 @@ struct DevResonance {
 struct DevRes {
   int          n, any_photo, bw3, pad_;
   DevResonance r[GRB_MAX_RES];
+  tres::ResPar tp[GRB_MAX_RES];  // the same resonances as MTensorPomeron::ME3 reads them (PP[RESTENSOR], PP[RES+CONTENSOR])
   // wd[J-1][(i*5+j)*5+k] = sqrt((J+m)!(J-m)!(J+mp)!(J-mp)!) (-1)^(mp-m+k) / [(J-mp-k)!(J+m-k)!(k+mp-m)! k!],
   // m = i-J, mp = j-J (reference src/MSpin.cc:927-950); 0 where a factorial argument is negative
   double wd[2][125];

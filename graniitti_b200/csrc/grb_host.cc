@@ -428,6 +428,7 @@ static void fill_resonance(const Json &R, const Json &tune, const Json &branchin
   std::sort(want.begin(), want.end());
   double BR = 1.0;
   bool   Pcons = true, found = false;
+  std::vector<double> gdt;
   std::map<std::pair<int, int>, std::pair<double, double>> alpha;  // (l,s) -> (re,im), default 1
   std::map<std::pair<int, int>, bool> alpha_set;
   for (auto &kv : tab.obj) {
@@ -438,6 +439,9 @@ static void fill_resonance(const Json &R, const Json &tune, const Json &branchin
     if (have != want) continue;
     BR = kv.second.at("BR").as_num();
     Pcons = kv.second.at("P_conservation").as_bool();
+    if (kv.second.has("g_decay_tensor")) {   // user-set tensor-pomeron decay couplings (src/MProcess.cc:594-600)
+      gdt = kv.second.at("g_decay_tensor").as_vec();
+    }
     if (kv.second.has("alpha_ls"))
       for (auto &a : kv.second.at("alpha_ls").arr) {
         const auto key2 = std::make_pair(a.arr.at(0).as_int(), a.arr.at(1).as_int());
@@ -512,6 +516,29 @@ static void fill_resonance(const Json &R, const Json &tune, const Json &branchin
       PS = pdw2((o.mass + i * o.width) * (o.mass + i * o.width));
       if (PS > 1e-12) break;
     }
+  // tensor-pomeron decay coupling (src/MProcess.cc:683-700, MTensorPomeron::GDecay src/MTensorPomeron.cc:138-156): from
+  // BRANCHING.json when given there, else from J, M, W, BR and the first daughter's mass -- with the same mother-mass
+  // shifts M + i W (i = 1..3) the phase-space loop above takes for a purely off-shell decay
+  if (gdt.empty()) {
+    auto gdecay = [&](double M) {
+      const double pw = o.width * o.BR, PI_ = 3.141592653589793238462643383279502884;
+      const double r = d.nodes[0].mass / M, P = std::sqrt(1 - 4 * (r * r));
+      const int Jr = o.spinX2 / 2;
+      if (Jr == 0) return std::sqrt(pw / (1.0 / (16 * PI_ * M) * (1.0 * 1.0) * P));
+      if (Jr == 1) return std::sqrt(pw / (M / (192 * PI_) * (P * (P * P))));
+      if (Jr == 2) return std::sqrt(pw / (M / (480 * PI_) * ((M / 1.0) * (M / 1.0)) * (P * ((P * P) * (P * P)))));
+      if (Jr == 4) return 1.0;
+      throw std::invalid_argument("MTensorPomeron::GDecay: Unknown input spin J = " + std::to_string(Jr));
+    };
+    gdt = {gdecay(o.mass)};
+    if (std::abs(pdw2(o.mass * o.mass)) < 1e-12)
+      for (int i = 1; i <= 3; ++i) {
+        const double PSi = pdw2((o.mass + i * o.width) * (o.mass + i * o.width));
+        gdt = {gdecay(o.mass + i * o.width)};
+        if (PSi > 1e-12) break;
+      }
+  }
+  for (size_t i = 0; i < gdt.size() && i < 2; ++i) o.g_decay_tensor[i] = gdt[i];
   o.g_decay = std::sqrt(std::max(0.0, o.BR * o.width / PS));
   if (std::isnan(o.g_decay) || std::isinf(o.g_decay))
     throw std::invalid_argument("MProcess::ProcessHelicityDecay: Kinematic coupling problem with resonance " + name + " (daughters too heavy?)");
@@ -588,7 +615,7 @@ static void parse_card_impl(const std::string &card_path, const char *process_ov
   static const std::map<std::string, int> registry = {
       {"yy[CON]", GRB_PROC_YY_CON}, {"yy[QED]", GRB_PROC_YY_QED}, {"PP[RES]", GRB_PROC_PP_RES},
       {"PP[CONTENSOR]", GRB_PROC_PP_CONTENSOR}, {"PP[CON]", GRB_PROC_PP_CON}, {"PP[CON-]", GRB_PROC_PP_CON_MINUS},
-      {"PP[RES+CON]", GRB_PROC_PP_RES_CON}};
+      {"PP[RES+CON]", GRB_PROC_PP_RES_CON}, {"PP[RESTENSOR]", GRB_PROC_PP_RESTENSOR}, {"PP[RES+CONTENSOR]", GRB_PROC_PP_RES_CONTENSOR}};
   auto it = registry.find(key);
   if (it == registry.end()) throw Unsupported("MSubProc: process " + key + "<" + cls + "> is outside the hot-path scope");
   d.proc = it->second;

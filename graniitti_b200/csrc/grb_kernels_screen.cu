@@ -178,6 +178,14 @@ int launch_screen(const PointArgs &a, int amp_kind, int regge_ff, int sm_count, 
     else launch_screen_t<4, AMP_TENSOR_2XS>(a, sm_count, st);
     return 2;
   }
+  if (amp_kind == AMP_TENSOR_RES) {
+    launch_screen_t<2, AMP_TENSOR_RES>(a, sm_count, st);
+    return 2;
+  }
+  if (amp_kind == AMP_TENSOR_RES_CON) {
+    launch_screen_t<2, AMP_TENSOR_RES_CON>(a, sm_count, st);
+    return 2;
+  }
   if (amp_kind == AMP_REGGE_RES) {
     launch_screen_t<2, AMP_REGGE_RES>(a, sm_count, st);
     return 2;

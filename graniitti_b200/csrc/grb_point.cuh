@@ -1030,6 +1030,30 @@ __device__ __forceinline__ double tensor_2xV_amp2(const NodeKin &in, const v4 &p
   return a2;
 }
 
+// ---- tensor pomeron resonances (reference src/MTensorPomeron.cc:164-564 ME3; closed form in grb_tres.cuh) -------------
+// common factor K of grb_tres.cuh: 9 g_PNN^2 F1(t1) F1(t2) F_M(t1) F_M(t2) (s1 a')^a1 (s2 a')^a2 / (16 s1 s2) e^{-i pi (a1+a2)/2}.
+// s1, s2 = (p_1 + p_X)^2, (p_2 + p_X)^2 as lts.s1 / lts.s2 (MKinematics.h GetLorentzScalars); F_M takes q_k^2 = t_k.
+__device__ __forceinline__ cx tensor_me3(const NodeKin &in, const v4 &p3, const v4 &p4) {
+  const DevProc &P = c_proc;
+  typedef tres::V4<double> T4;
+  const T4 pa = {0.0, 0.0, P.pb1z, P.pb1e}, pb = {0.0, 0.0, P.pb2z, P.pb2e};
+  const T4 p1 = {in.p1.x, in.p1.y, in.p1.z, in.p1.e}, p2 = {in.p2.x, in.p2.y, in.p2.z, in.p2.e};
+  const T4 pX = {in.pX.x, in.pX.y, in.pX.z, in.pX.e}, d3 = {p3.x, p3.y, p3.z, p3.e}, d4 = {p4.x, p4.y, p4.z, p4.e};
+  double   re, im;
+  tres::resonance_sum<double>(c_res.tp, c_res.n, pa, pb, p1, p2, pX, d3, d4, re, im);
+  const double s1 = m2_of(in.p1.x + in.pX.x, in.p1.y + in.pX.y, in.p1.z + in.pX.z, in.p1.e + in.pX.e);
+  const double s2 = m2_of(in.p2.x + in.pX.x, in.p2.y + in.pX.y, in.p2.z + in.pX.z, in.p2.e + in.pX.e);
+  const double a1 = P.tp_delta + P.tp_ap * in.t1, a2 = P.tp_delta + P.tp_ap * in.t2;
+  const double E  = exp(a1 * (log(s1) + P.tp_ln_ap) + a2 * (log(s2) + P.tp_ln_ap)) / (16.0 * s1 * s2);
+  const double K  = P.tp_vv_coupling * proton_F1(in.t1) * proton_F1(in.t2) * (1.0 / (1.0 - in.t1 / 1.0)) * (1.0 / (1.0 - in.t2 / 1.0)) * E;
+  double       sn, cs;
+  sincos(P.tp_phase * (a1 + a2), &sn, &cs);  // tp_phase = -pi/2
+  cx A;
+  A.re = K * (cs * re - sn * im);
+  A.im = K * (cs * im + sn * re);
+  return A;
+}
+
 // PP[RES] / PP[RES+CON]: ME4 + coherent resonance sum (reference PROC_9, PROC_17)
 __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, const v4 &p4) {
   const DevProc &P = c_proc;
@@ -1055,7 +1079,7 @@ __device__ __forceinline__ cx regge_resonances(const NodeKin &in, const v4 &p3, 
 namespace grb {
 
 enum { AMP_REGGE = 0, AMP_TENSOR_2XS = 1, AMP_REGGE_RES = 2, AMP_REGGE_RES_CON = 3, AMP_YY_LL = 4, AMP_TENSOR_2XV = 5,
-       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7, AMP_REGGE_ME6 = 8, AMP_REGGE_ME8 = 9 };
+       AMP_TENSOR_2XF = 6, AMP_YY_QED = 7, AMP_REGGE_ME6 = 8, AMP_REGGE_ME8 = 9, AMP_TENSOR_RES = 10, AMP_TENSOR_RES_CON = 11 };
 template <int AMP>
 __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v4 &p4) {
   if (AMP == AMP_YY_LL) return {sqrt(yy_ll_amp2(in, p3, p4)), 0.0};  // unscreened only: |A|^2 is all that is used
@@ -1067,6 +1091,11 @@ __device__ __forceinline__ cx amplitude(const NodeKin &in, const v4 &p3, const v
   if (AMP == AMP_YY_QED) return {sqrt(yy_qed_amp2(in, p3, p4)), 0.0};          // unscreened only
   if (AMP == AMP_REGGE_ME6 || AMP == AMP_REGGE_ME8) return {0.0, 0.0};  // ladders: evaluated from their own scalars (regge_ladder)
   if (AMP == AMP_TENSOR_2XS) return tensor_me4_2xS(in, p3, p4);
+  if (AMP == AMP_TENSOR_RES) return tensor_me3(in, p3, p4);
+  if (AMP == AMP_TENSOR_RES_CON) {  // PROC_14: helicity amplitudes of ME4 and ME3 added index by index (four equal copies each)
+    const cx a = tensor_me4_2xS(in, p3, p4), b = tensor_me3(in, p3, p4);
+    return {a.re + b.re, a.im + b.im};
+  }
   if (AMP == AMP_REGGE_RES) return regge_resonances(in, p3, p4);
   if (AMP == AMP_REGGE_RES_CON) {
     const cx a = regge_me4(in), b = regge_resonances(in, p3, p4);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GRB_ABI_VERSION 2
+#define GRB_ABI_VERSION 3
 
 /* ---- error codes ---------------------------------------------------------------------------------- */
 enum {
@@ -56,7 +56,9 @@ enum {
   GRB_PROC_YY_CON       = 3,  /* "yy[CON]"       PROC_3  MSubProc.h:165  MG5 HELAS yy->l+l- + kt-EPA flux */
   GRB_PROC_YY_QED       = 4,  /* "yy[QED]"       PROC_4  :175            tensor-pomeron code, QED branch   */
   GRB_PROC_PP_RES       = 9,  /* "PP[RES]"       PROC_9                  sum of MRegge::ME3/PhotoME3       */
+  GRB_PROC_PP_RESTENSOR = 11, /* "PP[RESTENSOR]" PROC_11 :278            MTensorPomeron::ME3 (J = 0+, 2+ -> two pseudoscalars) */
   GRB_PROC_PP_CONTENSOR = 12, /* "PP[CONTENSOR]" PROC_12 :288            MTensorPomeron::ME4               */
+  GRB_PROC_PP_RES_CONTENSOR = 14, /* "PP[RES+CONTENSOR]" PROC_14 :321    ME4 (2xS) + ME3, helicity amplitudes added index by index */
   GRB_PROC_PP_CON       = 15, /* "PP[CON]"       PROC_15 :361            MRegge::ME4(+1)                   */
   GRB_PROC_PP_CON_MINUS = 16, /* "PP[CON-]"      PROC_16 :382            MRegge::ME4(-1)                   */
   GRB_PROC_PP_RES_CON   = 17  /* "PP[RES+CON]"   PROC_17 :399            ME4 + sum of ME3/PhotoME3         */
@@ -146,7 +148,9 @@ typedef struct {
   double  g_FF;
   double  g_decay;    /* hel.g_decay                                                                     */
   double  BR;
-  double  g_Tensor[8];
+  double  g_Tensor[8];       /* tensor-pomeron production couplings (2 for J = 0, 1; 7 for J = 2), PARAM_RES.g_Tensor          */
+  double  g_decay_tensor[2]; /* tensor-pomeron decay couplings hel.g_decay_tensor: BRANCHING.json, else MTensorPomeron::GDecay
+                              * from J, M, W, BR and the daughter mass (src/MProcess.cc:594-700, src/MTensorPomeron.cc:138-156) */
   double  rho_re[GRB_RHO_DIM * GRB_RHO_DIM]; /* spin density matrix, row-major, (2J+1)^2 used            */
   double  rho_im[GRB_RHO_DIM * GRB_RHO_DIM];
   double  T_re[9], T_im[9];                  /* decay helicity T matrix (hel.T), row-major n1 x n2       */

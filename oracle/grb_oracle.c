@@ -2077,8 +2077,12 @@ static double yy_con_amp2(ost *S) {
 }
 
 /* reference seam B: MSubProc::GetBareAmplitude2 -> PROC_n::Amp2 (include/Graniitti/MSubProc.h) */
+#include "grb_oracle_tres.inc"
+
 static double bare_amp2(ost *S) {
   switch (S->d->proc) {
+    case GRB_PROC_PP_RESTENSOR: return tensor_me3(S);
+    case GRB_PROC_PP_RES_CONTENSOR: return tensor_res_con(S);
     case GRB_PROC_PP_CON: return S->d->n_legs == 6 ? cx_abs2(regge_me8(S)) : (S->d->n_legs == 4 ? cx_abs2(regge_me6(S)) : cx_abs2(regge_me4(S, 1.0)));
     case GRB_PROC_PP_CON_MINUS: return cx_abs2(regge_me4(S, -1.0));
     case GRB_PROC_YY_CON: {
@@ -2296,6 +2300,13 @@ static double event_weight(ost *S, const double *u, uint8_t *flags) {
 
 /* ---- public entry ----------------------------------------------------------------------------------- */
 
+/* test hook: per evaluated point, the final-state momenta the amplitude saw -- pa, pb, p1, p2, pX, p3, p4 as (x, y, z, e),
+ * then s1, s2, t1, t2, Re / Im of the first helicity amplitude: GRB_ORACLE_CAPTURE_LEN doubles.  Born-level runs only (the
+ * screening loop overwrites the state).  Used by tests/test_tensor_res.py to feed the host-compiled closed form. */
+#define GRB_ORACLE_CAPTURE_LEN 34
+static double *g_capture = NULL;
+void grb_oracle_capture(double *buf) { g_capture = buf; }
+
 int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, int64_t n, const double *u,
                     int dim, const double *tape, int dtape, double *w, uint8_t *flags, double *dump,
                     int32_t *tape_used) {
@@ -2304,7 +2315,8 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
   /* forward N* excitation (NSTARS = 1, 2) is restated for the <F> class Regge continuum (PomPomProtonVertex), yy[CON] (IncohFlux) and the
    * tensor-pomeron continuum (MTensorPomeron::ME4 has no inelastic vertex: the elastic formulas are evaluated on the excited kinematics) */
   if (d->excitation != 0 && !(d->proc == GRB_PROC_PP_CON || d->proc == GRB_PROC_PP_CON_MINUS || d->proc == GRB_PROC_YY_CON ||
-                              d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON))
+                              d->proc == GRB_PROC_PP_CONTENSOR || d->proc == GRB_PROC_PP_RES || d->proc == GRB_PROC_PP_RES_CON ||
+                              d->proc == GRB_PROC_PP_RESTENSOR || d->proc == GRB_PROC_PP_RES_CONTENSOR))
     return GRB_ERR_UNSUPPORTED;
   if (d->ps_class == GRB_CLASS_C && !(d->n_legs == 2 || ((d->n_legs == 4 || d->n_legs == 6) && d->proc == GRB_PROC_PP_CON))) return GRB_ERR_UNSUPPORTED;
   if (d->screening && (!eik || eik->n < 1)) return GRB_ERR_STATE;
@@ -2329,6 +2341,12 @@ int grb_oracle_eval(const grb_process_desc *d, const grb_oracle_eikonal *eik, in
     g_call_idx      = 0;
     w[k]            = event_weight(S, u + k * dim, &flags[k]);
     if (tape_used) tape_used[k] = S->tape_overrun ? -S->tape_pos : S->tape_pos;
+    if (g_capture) {
+      double *c = g_capture + k * GRB_ORACLE_CAPTURE_LEN;
+      const v4 mv[7] = {S->pbeam1, S->pbeam2, S->pfinal[1], S->pfinal[2], S->pfinal[0], S->node_p4[0], S->node_p4[1]};
+      for (int i = 0; i < 7; ++i) { c[4 * i] = mv[i].x; c[4 * i + 1] = mv[i].y; c[4 * i + 2] = mv[i].z; c[4 * i + 3] = mv[i].e; }
+      c[28] = S->s1; c[29] = S->s2; c[30] = S->t1; c[31] = S->t2; c[32] = S->hamp[0].re; c[33] = S->hamp[0].im;
+    }
     if (dump) {
       double *D = dump + k * GRB_DUMP_LEN;
       D[GRB_DUMP_T1] = S->t1; D[GRB_DUMP_T2] = S->t2; D[GRB_DUMP_S1] = S->s1; D[GRB_DUMP_S2] = S->s2;

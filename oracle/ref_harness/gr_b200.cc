@@ -57,6 +57,8 @@ int proc_id(const std::string &istate, const std::string &channel) {  // MSubPro
   if (k == "PP[CON]") return GRB_PROC_PP_CON;
   if (k == "PP[CON-]") return GRB_PROC_PP_CON_MINUS;
   if (k == "PP[RES+CON]") return GRB_PROC_PP_RES_CON;
+  if (k == "PP[RESTENSOR]") return GRB_PROC_PP_RESTENSOR;
+  if (k == "PP[RES+CONTENSOR]") return GRB_PROC_PP_RES_CONTENSOR;
   throw std::invalid_argument("process " + k + " has no device amplitude");
 }
 
@@ -213,6 +215,7 @@ void fill_desc(gra::MGraniitti &g, grb_process_desc &d) {
     o.mass = r.p.mass; o.width = r.p.width; o.g_re = r.g.real(); o.g_im = r.g.imag(); o.g_FF = r.g_FF;
     o.g_decay = r.hel.g_decay; o.BR = r.hel.BR;
     for (size_t k = 0; k < r.g_Tensor.size() && k < 8; ++k) o.g_Tensor[k] = r.g_Tensor[k];
+    for (size_t k = 0; k < r.hel.g_decay_tensor.size() && k < 2; ++k) o.g_decay_tensor[k] = r.hel.g_decay_tensor[k];
     if (r.p.spinX2 != 0) {
       if (r.rho.size_row() > GRB_RHO_DIM) throw std::invalid_argument("resonance spin exceeds GRB_RHO_DIM");
       for (size_t a = 0; a < r.rho.size_row(); ++a)

@@ -95,6 +95,24 @@ CASES = [
     ("cc6_cms_6pi_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 0, 3072, 16, True),
     ("cc6_cms_4pi2k_con_born", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K- pi+ pi-", 0, 3072, 16, True),
     ("cc6_cms_6pi_con_screened", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- pi+ pi- pi+ pi-", 1, 512, 16, True),
+    # tensor-pomeron resonances MTensorPomeron::ME3 (PROC_11 "RESTENSOR", PROC_14 "RES+CONTENSOR"): 0+ and 2+ into two pseudoscalars;
+    # the seven pomeron-pomeron-f2 couplings one at a time (reference tests/run_tensor2_multi/run.sh) and all together
+    ("c5_cms_pipi_restensor_f2_born", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1}", 0, 1536, 8, True),
+    ("c5_cms_pipi_restensor_f0_born", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f0_1500:1}", 0, 1536, 8, True),
+    ("c5_cms_pipi_restensor_f2_allg_born", "./tests/processes/CMSCUTS.json",
+     "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{g0:0.3,g1:1.0,g2:0.7,g3:-0.6,g4:0.5,g5:0.4,g6:-0.2}", 0, 1536, 8, True),
+] + [("c5_cms_pipi_restensor_f2_g%d_born" % m, "./tests/processes/CMSCUTS.json",
+      "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{%s}" % ",".join("g%d:%s" % (k, "1.0" if k == m else "0.0") for k in range(7)),
+      0, 512, 8, True) for m in range(1, 7)] + [
+    ("c5_cms_kk_restensor_born", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> K+ K- @RES{f0_980:1,f2_1525:1,f0_1710:1}", 0, 1536, 8, True),
+    ("c5_cms_pipi_rescontensor_born", "./tests/processes/CMSCUTS.json",
+     "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_500:1,f0_980:1,f2_1270:1,f0_1500:1}", 0, 2048, 8, True),
+    ("c2_alice_pipi_rescontensor_screened", "./tests/processes/ALICECUTS.json",
+     "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 1, 320, 8, True),
+    ("c2_alice_pipi_restensor_f2_screened", "./tests/processes/ALICECUTS.json",
+     "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{g0:1.0,g1:0.5,g2:0.0,g3:0.0,g4:0.3,g5:0.0,g6:0.0}", 1, 320, 8, True),
+    ("c2_alice_pipi_restensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1024, 8, True),
+    ("cc_alice_pipi_rescontensor_born", "./tests/processes/ALICECUTS.json", "PP[RES+CONTENSOR]<C> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1536, 8, True),
 ]
 
 
@@ -116,6 +134,10 @@ def main():
         if nstars:   # forward pt up to 50 / 100 GeV with excitation: keep the log-pt coordinates where pt is O(0.05 - 3 GeV)
             u[:, 0] = 0.55 + 0.3 * (u[:, 0] - 0.85) / 0.15
             u[:, 1] = 0.55 + 0.3 * (u[:, 1] - 0.85) / 0.15
+        if "RESTENSOR]<F>" in proc or "RES+CONTENSOR]<F>" in proc:
+            # the resonance form factors exp(-(m^2 - M0^2)^2 / GeV^4) underflow beyond m ~ 4 GeV (|A|^2 denormal, then 0):
+            # keep the system mass below ~3.1 GeV (m^2 is flat in u5 up to GENCUTS M_max^2 = 81 / 49 GeV^2)
+            u[:, 5] *= 0.12 if "CMSCUTS" in card else 0.2
         qed_alpha = 0
         run_card = card
         if card.startswith("@"):   # "@KEY=VALUE:card": run a copy of the card (written under output/) with that key replaced

@@ -31,7 +31,7 @@ class OracleEikonal(C.Structure):
 def build_oracle(force=False):
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".c")]
-    deps = srcs + [os.path.join(ORACLE_DIR, "grb_oracle.h"), os.path.join(ROOT, "include", "grb.h")]
+    deps = srcs + [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".h", ".inc"))] + [os.path.join(ROOT, "include", "grb.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in deps):
         subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=gnu99", "-o", so]
                               + srcs + ["-lm"])

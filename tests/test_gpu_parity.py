@@ -93,7 +93,9 @@ def test_device_vs_reference_golden(grb, msa, path):
     # rank-4 tensor algebra of the 2xV continuum is itself ill-conditioned (11-14 % of the golden points have kappa > 1e-11),
     # there the allowance is a quarter of that fraction (measured 1.0-2.8 % of points, all inside max(1e-10, 8 kappa))
     nzk = z["kappa"][z["W"] != 0]
-    illcond = any(k in str(z["process"]) for k in ("rho", "phi", "yy[QED]", "p+ p-", "Lambda"))  # + spin-1/2 chains, QED gauge cancellation
+    # (+ spin-1/2 chains, QED gauge cancellation, and the reference's explicit rank-6 pomeron-pomeron-f2 vertex: 8 % of the
+    #  RESTENSOR golden points have kappa > 1e-11, 0.6 % sit beyond 1e-10 -- all inside 8 kappa on the CPU, tests/test_tensor_res.py)
+    illcond = any(k in str(z["process"]) for k in ("rho", "phi", "yy[QED]", "p+ p-", "Lambda", "RESTENSOR", "RES+CONTENSOR"))
     allow = 1e-3 + 2.0 / len(rel) + (0.25 * np.mean(nzk > 1e-11) if illcond else 0.0)
     if noisy:   # (two excited legs double the chance of a staircase flip; the screened N* goldens hold 54-160 points)
         allow = 0.20
@@ -465,3 +467,30 @@ def test_batched_parameter_sets(grb, msa):
         assert abs(r.sigma - rb[k].sigma) <= 1e-10 * r.sigma and r.iterations == rb[k].iterations, (k, r.sigma, rb[k].sigma)
         sig.append(r.sigma)
     assert len(set(sig)) == 8 and sig[7] > sig[0]
+
+
+def test_tensor_resonance_scope(grb):
+    """MTensorPomeron::ME3 classes without a device amplitude (1- photoproduction, vector-pair decays) are refused at create time."""
+    with pytest.raises(grb.GrbError):
+        grb.Engine(card=os.path.join(CARDS, "c5_cms_4pi.json"), process="PP[RESTENSOR]<F> -> pi+ pi- @RES{rho_770:1}", pomloop=0)
+    with pytest.raises(grb.GrbError):
+        grb.Engine(card=os.path.join(CARDS, "c5_cms_4pi.json"), process="PP[RESTENSOR]<F> -> rho(770)0 rho(770)0 @RES{f2_1270:1}", pomloop=0)
+
+
+def test_tensor_resonances_vs_oracle_seeded(grb, msa):
+    """PP[RES+CONTENSOR] on fresh seeded points (Born: 20000, screened: 600) against the oracle's explicit-tensor restatement."""
+    for pom, n in ((0, 20000), (1, 600)):
+        E = engine_for(grb, msa, "c2_alice.json", "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1} @R[f2_1270]{g1:0.5,g4:0.3}", pom)
+        u, tape = make_points(n, E.desc.lipsdim, 8, 4711 + n, adapted=True)
+        u[:, 5] *= 0.2
+        o = oracle_eval(E.desc, Eikonal(msa[0], msa[1], msa[2]) if pom else None, u, tape)
+        w, fl, _ = E.eval(u.T.copy(), tape.T.copy())
+        nz = o["w"] != 0
+        kin = (o["flags"] & 1) == 1
+        assert np.array_equal(fl & 1, o["flags"] & 1) and np.array_equal(fl[kin], o["flags"][kin])
+        assert np.array_equal(w != 0, nz)
+        rel = np.abs(w[nz] - o["w"][nz]) / np.abs(o["w"][nz])
+        # no per-point kappa here: the explicit rank-6 contraction on the oracle side has a tail (0.6 % of points beyond 1e-10,
+        # up to 3e-8 at kappa 3e-7, measured on the CPU against the host-compiled closed form)
+        assert np.mean(rel > RTOL) < 2e-2 and rel.max() < 1e-5 and np.median(rel) < 2e-12, (rel.max(), np.mean(rel > RTOL), np.median(rel))
+        E.close()

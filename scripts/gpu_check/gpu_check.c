@@ -83,6 +83,20 @@ int main(int argc, char **argv) {
       printf("    vegas rc=%d evals %.0f kin %.0f fid %.0f amp_ok %.0f  sigma(flat grid) %.6e +- %.2e  %.3f ms %d launches\n", rc, N, acc->n_kin_ok, acc->n_fid_ok,
              acc->n_amp_ok, mean, sqrt(var > 0 ? var : 0), ms, nl);
       if (rc != GRB_OK || !(acc->fsum > 0)) ++n_fail;
+      /* GRB_CHECK_BENCH=<log2 points>: device-timed VEGAS iterations on the uniform grid (3 warm-up + 5 timed; grb_last_timing =
+       * CUDA events around the kernels of the iteration on the engine's stream) */
+      const char *be = getenv("GRB_CHECK_BENCH");
+      if (be && rc == GRB_OK) {
+        const int64_t nb = (int64_t)1 << atoi(be);
+        double tot = 0, best = 1e30, items = 0;
+        for (int it = 0; it < 8; ++it) {
+          rc = grb_vegas_iterate(E, xmat, bins, D, 0, nb, 777, (uint64_t)it, GRB_MODE_INTEGRATE, 0.0, acc);
+          grb_last_timing(E, &ms, &nl);
+          if (it >= 3) { tot += ms; if (ms < best) best = ms; items = acc->n_fid_ok; }
+        }
+        printf("    bench 2^%s points/iteration: %.3f ms mean, %.3f ms best -> %.4e points/s; %.0f points pass the cuts -> %.4e amplitude%s evaluations/s\n", be, tot / 5,
+               best, nb / (tot / 5 * 1e-3), items, items / (tot / 5 * 1e-3), pom ? " x screening-loop" : "");
+      }
       free(xmat); free(acc);
     }
     grb_destroy(E);

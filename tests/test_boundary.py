@@ -26,6 +26,9 @@ CASES = [  # card of this repo, the reference's card, process, pomloop
     ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[CONTENSOR]<F> -> " + RHO4PI, 0),
     ("c2_alice.json", "./tests/processes/ALICECUTS.json", "PP[CON]<C> -> pi+ pi-", 1),
     ("c1_test13.json", "./input/test.json", "PP[RES+CON]<F> -> pi+ pi- @R[f0_980]{M:1.02,W:0.09} @R[f2_1270]{JZ0:0.2,JZ2:0.8,W:0.2}", 0),
+    # tensor-pomeron resonances: g_Tensor overrides and the decay couplings hel.g_decay_tensor (GDecay; off-shell K+ K- branch for f0(980))
+    ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{g0:0.3,g1:1.0,g2:0.7,g3:-0.6,g4:0.5,g5:0.4,g6:-0.2}", 0),
+    ("c2_alice.json", "./tests/processes/ALICECUTS.json", "PP[RES+CONTENSOR]<F> -> K+ K- @RES{f0_980:1,f2_1525:1,f0_1710:1}", 1),
 ]
 pytestmark = pytest.mark.skipif(not os.path.exists(GR_B200), reason="compiled boundary (oracle/_ref/gra/bin/gr_b200) not present")
 

@@ -12,7 +12,7 @@
 //                                gh = -g + p p / p^2,  kh = gh k,  k = p_3 - p_4,  p = p_X,  Delta = 1/(p^2 - M0^2 + i M0 Gamma)
 //
 // Xh_1, Xh_2, Yh are symmetric and traceless, so the reference's auxiliary tensor R = 1/2 (g g + g g) + 1/4 g g (CalcRTensor,
-// :2538-2575; the +1/4 is the reference's, kept in the oracle) acts on them as the identity and each coupling structure
+// :2538-2575; the +1/4 is the reference's, kept by the CPU checker) acts on them as the identity and each coupling structure
 // collapses to a Lorentz invariant of (Xh_1, Xh_2, Yh, q_1, q_2) -- products of the three linear maps
 //   Xh_k v = 2 P_k (P_k.v) - 1/2 P_k^2 v,      Yh v = kh (kh.v) + 1/3 kh^2 (-v + p (p.v)/p^2)
 // applied to 4-vectors.  With T = Tr(Xh_1 Xh_2 Yh), XX = Xh_1 : Xh_2 = 4 (P_1.P_2)^2 - P_1^2 P_2^2 :
@@ -31,7 +31,7 @@
 // The four helicity-conserving proton combinations carry the same amplitude (:232-252), so one complex number per point.
 //
 // The header is plain C++ under a host compiler (tests/host_tres.cc instantiates it in double and long double to pin the
-// algebra against the CPU oracle and to measure the rounding noise of the reference's explicit contraction) and device
+// algebra against the explicit-tensor CPU restatement and to measure the rounding noise of the reference's explicit contraction) and device
 // code under nvcc; the product only ever calls it from the CUDA kernels.
 #pragma once
 #include <math.h>

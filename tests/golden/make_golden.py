@@ -116,6 +116,11 @@ CASES = [
 ]
 
 
+# written to tests/golden/late/ (run on the device by tests/test_zz_gpu_late.py, sorted after every other GPU test): generated
+# after round 2's GPU budget was spent
+LATE = {"c2_alice_pipi_restensor_f2_screened", "c2_alice_pipi_restensor_nstar1_born", "cc_alice_pipi_rescontensor_born"}
+
+
 def main():
     if not have_ref():
         raise SystemExit("oracle/_ref is not built (needs /root/reference): run oracle/build_ref.sh")
@@ -152,7 +157,7 @@ def main():
             run_card = "./output/golden_%s.json" % name
             open(os.path.join(REF_TREE, run_card), "w").write(txt)
         r = ref_eval(run_card, proc, pom, u, tape, kappa=True)
-        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
+        np.savez_compressed(os.path.join(GOLDEN, "late" if name in LATE else "", name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
                             nstars=nstars, tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
                             s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
                             nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :5])

@@ -39,7 +39,9 @@ def ref_records(card, proc, pom, u, tape, tmp_path):
     ("c2_alice.json", "./tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", 8),
     ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[CON]<F> -> " + RHO4PI, 24),
     ("c1_test13.json", "./input/test.json", "PP[RES+CON]<F> -> pi+ pi-", 8),
-    ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K- pi+ pi-", 16)], ids=["pipi", "rhorho_4pi", "rescon", "ladder_6"])
+    ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[CON]<C> -> pi+ pi- K+ K- pi+ pi-", 16),
+    ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 8)],
+    ids=["pipi", "rhorho_4pi", "rescon", "ladder_6", "rescontensor"])
 def test_record_equals_reference_common_record(grb, tmp_path, card, ref_card, proc, ntape):
     d = grb.parse_card(os.path.join(CARDS, card), proc, 0)
     u, tape = make_points(400 if d.n_legs < 6 else 1500, d.lipsdim, ntape, 5, adapted=True)

@@ -66,6 +66,10 @@ def compare(w, fl, ref_w, ref_fl, kappa=None, rtol=RTOL, libm=None):
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])
 def test_device_vs_reference_golden(grb, msa, path):
+    run_golden(grb, msa, path)
+
+
+def run_golden(grb, msa, path):
     z = np.load(path, allow_pickle=False)
     if "qed_alpha" in z.files and int(z["qed_alpha"]):   # a tune with PARAM_STRUCTURE.QED_alpha != ZERO: through the POD desc
         d = grb.parse_card(os.path.join(CARDS, CARD_OF[str(z["card"])]), str(z["process"]), int(z["pomloop"]))

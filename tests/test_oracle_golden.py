@@ -14,6 +14,7 @@ CARD_OF = {"./tests/processes/ALICECUTS.json": "c2_alice.json", "./input/test.js
            "./tests/run_atlas_multi/ATLAS_NEG.json": "c3_atlas_neg.json",
            "./tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json": "c4_cms_mumu_lowmass.json"}
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*.npz")))  # c1..c5: <F> class per BASELINE config, cc_*: <C> class
+FILES += sorted(glob.glob(os.path.join(GOLDEN, "late", "c*.npz")))  # generated after the round's GPU budget: tests/test_zz_gpu_late.py
 
 
 def load_case(grb, path):

@@ -18,7 +18,7 @@ import pytest
 from helpers import CARDS, GOLDEN, ROOT, load_oracle, oracle_eval
 from test_oracle_golden import load_case
 
-FILES = sorted(f for f in glob.glob(os.path.join(GOLDEN, "c*_restensor_*born.npz")) if "nstar" not in f)
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "c*_restensor_*born.npz")) + glob.glob(os.path.join(GOLDEN, "late", "c*_restensor_*born.npz")))
 
 
 class ResPar(C.Structure):   # grb::tres::ResPar

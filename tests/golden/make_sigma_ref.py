@@ -28,6 +28,9 @@ CASES = [
     ("c2_alice_pipi_con_nstar1_born", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "false", 300000, 0.002, "NSTARS=1"),
     # (the reference needs > 25 min on 8 cores for this one at PRECISION 0.002: not stored yet, the test skips it)
     ("c4_cms_mumu_yycon_nstar2_born", "tests/run_cms_mumu_low_high/CMS_mumu_lowmass.json", "yy[CON]<F> -> mu+ mu-", "false", 100000, 0.01, "NSTARS=2"),
+    # tensor-pomeron resonances (MTensorPomeron::ME3; the reference needs 0.8 ms per amplitude)
+    ("c5_cms_pipi_restensor_f2_born", "tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1}", "false", 200000, 0.005),
+    ("c5_cms_pipi_rescontensor_born", "tests/processes/CMSCUTS.json", "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", "false", 200000, 0.005),
     # another energy (beam energies replaced in the card copy): the energy-scan caller grb_xscan
     ("c2_alice_pipi_con_screened_7tev", "tests/processes/ALICECUTS.json", "PP[CON]<F> -> pi+ pi-", "true", 100000, 0.003, 3500.0),
 ]

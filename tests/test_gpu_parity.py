@@ -249,6 +249,10 @@ def test_cross_section_matches_reference(grb, msa, name, card, ncall, iters, pre
     """Full adaptive integration on the device (grb_integrate: burn-in, grid refinement, chi2 control) against
     sigma +- err of the unmodified reference CLI (tests/golden/make_sigma_ref.py): agreement within the combined
     Monte Carlo error.  The reference prints 4 significant digits, which is added to its error."""
+    run_sigma(grb, msa, name, card, ncall, iters, prec)
+
+
+def run_sigma(grb, msa, name, card, ncall, iters, prec):
     import json
     allref = json.load(open(os.path.join(GOLDEN, "sigma_ref.json")))
     if name not in allref:

@@ -127,3 +127,48 @@ def test_unsupported_resonance_classes_are_refused(grb):
     w = oracle_eval(d, None, u, tape)
     passed = (w["flags"] & 7) == 7
     assert passed.sum() > 20 and np.all(w["w"] == 0) and np.all((w["flags"][passed] & 8) == 0)
+
+
+def _raw_sum(H, rp, n_res, mom, extended=0):
+    out = np.zeros((len(mom), 2))
+    mom = np.ascontiguousarray(mom)
+    H.tres_eval(rp, n_res, C.c_long(len(mom)), mom.ctypes.data_as(C.c_void_p), mom.shape[1], out.ctypes.data_as(C.c_void_p), extended)
+    return out[:, 0] + 1j * out[:, 1]
+
+
+def test_closed_form_properties(grb, msa, host_tres):
+    """Size-independent properties of the contracted vertex: (1) linear in the seven couplings -- the sum of the single-coupling
+    amplitudes is the all-couplings amplitude; (2) a Lorentz scalar -- unchanged by a common boost along the beam axis and a
+    rotation about it applied to every momentum; (3) symmetric under the exchange of the two proton sides (all seven
+    structures are symmetric in pomeron 1 <-> pomeron 2)."""
+    z, d = load_case(grb, os.path.join(GOLDEN, "c5_cms_pipi_restensor_f2_allg_born.npz"))
+    o, cap = captured(d, z["u"], z["tape"])
+    mom = cap[z["W"] != 0][:, :28].copy()
+    rp = respars(d)
+    full = _raw_sum(host_tres, rp, 1, mom, extended=1)
+    # (1) linearity
+    parts, scale = np.zeros_like(full), np.zeros(len(full))
+    for m in range(7):
+        one = respars(d)
+        for k in range(7):
+            one[0].g[k] = rp[0].g[k] if k == m else 0.0
+        one[0].on = (1 << m) if m >= 1 else 0
+        a = _raw_sum(host_tres, one, 1, mom, extended=1)
+        parts += a
+        scale += np.abs(a)
+    assert np.max(np.abs(parts - full) / scale) < 1e-14   # (each part is returned rounded to double; the structures partly cancel)
+    # (2) boost along z (rapidity 0.7) and rotation about z (1.1 rad) of all seven 4-vectors
+    v = mom.reshape(-1, 7, 4).copy()
+    ch, sh, c, s = np.cosh(0.7), np.sinh(0.7), np.cos(1.1), np.sin(1.1)
+    x, y, zz, e = v[..., 0].copy(), v[..., 1].copy(), v[..., 2].copy(), v[..., 3].copy()
+    v[..., 0], v[..., 1] = c * x - s * y, s * x + c * y
+    v[..., 2], v[..., 3] = ch * zz + sh * e, sh * zz + ch * e
+    moved = _raw_sum(host_tres, rp, 1, v.reshape(-1, 28), extended=1)
+    rel = np.abs(moved - full) / np.abs(full)
+    # the transformed momenta are rounded to double again: t_k = (p_beam - p_k)^2 of O(6500 GeV) components moves by ~1e-11
+    # relative per ulp (SURVEY.md section 7), and the exponentials amplify it -- a non-invariant formula would be off by O(1)
+    assert np.median(rel) < 1e-9 and rel.max() < 1e-5, (np.median(rel), rel.max())
+    # (3) side exchange: (pa, p1) <-> (pb, p2)
+    w = mom.reshape(-1, 7, 4)[:, [1, 0, 3, 2, 4, 5, 6], :].reshape(-1, 28)
+    swapped = _raw_sum(host_tres, rp, 1, w, extended=1)
+    assert np.max(np.abs(swapped - full) / np.abs(full)) < 1e-12

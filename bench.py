@@ -4,7 +4,7 @@
 Default workload (BASELINE.json configs[1], the configuration the metric is quoted on): continuum
 pp -> p pi+ pi- p at sqrt(s) = 13 TeV, `PP[CON]<F> -> pi+ pi-` on ALICE-style fiducial cuts with the eikonal
 screening loop on (ND = 1: 19 kt x 15 folded phi nodes = 285 executed loop nodes per accepted point), MODELPARAM TUNE0.
-`--workload c1|c1t|c2|c2t|c3|c4|c4q|c5|c5t` selects the other BASELINE configurations (same JSON line, per-workload roofline).
+`--workload c1|c1t|c2|c2t|c3|c4|c4q|c5|c5t` selects the other BASELINE configurations (`c1r`, `c2r`: the tensor-pomeron resonance processes) (same JSON line, per-workload roofline).
 
 A "step" is one VEGAS iteration over one batch of synthetic phase-space points: Philox-generated points through the VEGAS
 grid -> kinematics -> cuts -> Born amplitude -> (screening loop) -> accumulators, then the per-iteration exchange
@@ -63,6 +63,11 @@ WORKLOADS = {
            "configs[4]: PP[CON]<F> -> rho rho -> 4 pi (decay chains), 13 TeV, CMS cuts, screening off"),
     "c5t": ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[CONTENSOR]<F> -> " + RHO4PI, 0, 16, 60000, 40000,
             "configs[4] variant: PP[CONTENSOR]<F> -> rho rho -> 4 pi (tensor pomeron 2xV), screening off"),
+    # tensor-pomeron resonances (MTensorPomeron::ME3; no converged grid committed yet: uniform grid, see workload_grid)
+    "c1r": ("c5_cms_4pi.json", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1}", 0, 4, 4000, 2000,
+            "tensor-pomeron resonance: PP[RESTENSOR]<F> -> pi+ pi- via f2(1270), 13 TeV, CMS cuts, screening off"),
+    "c2r": ("c2_alice.json", "./tests/processes/ALICECUTS.json", "PP[RES+CONTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 1, 4, 16, 8,
+            "tensor-pomeron resonances + continuum: PP[RES+CONTENSOR]<F> -> pi+ pi- (f0(980), f2(1270)), ALICE cuts, POMLOOP on, ND=1"),
 }
 
 # Algorithmic flop model, SURVEY.md section 8(d) convention (add/sub/mul/div/sqrt/compare = 1, FMA = 2, transcendental
@@ -70,7 +75,8 @@ WORKLOADS = {
 # holds the op counts measured on the oracle restatement (scripts/oracle_opcount.py); the survey's estimates are the
 # fallback and are labelled as such.
 SURVEY_FLOPS = {"c1": (600, 24000, 0), "c1t": (600, 900, 0), "c2": (600, 650, 700), "c2t": (600, 900, 900), "c3": (600, 24000, 0),
-                "c4": (600, 8000, 0), "c4q": (600, 8000, 0), "c5": (1800, 650, 0), "c5t": (1800, 50000, 0)}
+                "c4": (600, 8000, 0), "c4q": (600, 8000, 0), "c5": (1800, 650, 0), "c5t": (1800, 50000, 0),
+                "c1r": (1300, 800, 0), "c2r": (1300, 1700, 1700)}   # (closed-form counts of grb_tres.cuh)
 
 
 def flop_model(name):

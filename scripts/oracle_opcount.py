@@ -163,7 +163,7 @@ def main():
         # the tensor-pomeron amplitudes (and yy[QED], which runs through the same code) are restated as the reference writes
         # them: explicit rank-2 / rank-4 FTensor index loops (2e4 - 3e5 flop per amplitude as written).  That is the
         # reference's redundant evaluation, not a minimal dataflow: for those the survey's closed-form estimates stay.
-        as_written_only = "CONTENSOR" in process or "yy[QED]" in process
+        as_written_only = "TENSOR" in process or "yy[QED]" in process
         res[wl] = {"points": n, "accepted": acc, "amplitude_as_written_only": as_written_only, "F_kin": F_kin, "F_born": F_born + F_post, "F_node": F_node_min,
                    "F_node_as_written": F_node, "node_invariants_hoisted": nd["NODE_INV"],
                    "per_phase_flops": {k: float(v) for k, v in per.items()},

@@ -113,11 +113,16 @@ CASES = [
      "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{g0:1.0,g1:0.5,g2:0.0,g3:0.0,g4:0.3,g5:0.0,g6:0.0}", 1, 320, 8, True),
     ("c2_alice_pipi_restensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1024, 8, True),
     ("cc_alice_pipi_rescontensor_born", "./tests/processes/ALICECUTS.json", "PP[RES+CONTENSOR]<C> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1536, 8, True),
+    # oracle only: the 1- block (gamma-pomeron fusion, full proton spinor vertices), alone and inside the shipped card's own list
+    ("c5_cms_pipi_restensor_rho_born", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{rho_770:1}", 0, 1536, 8, True),
+    ("c1_test_pipi_rescontensor_cardres_born", "./input/test.json", "PP[RES+CONTENSOR]<F> -> pi+ pi-", 0, 1536, 8, True),
 ]
 
 
 # written to tests/golden/late/ (run on the device by tests/test_zz_gpu_late.py, sorted after every other GPU test): generated
 # after round 2's GPU budget was spent
+# the 1- (photoproduction) block of MTensorPomeron::ME3 is restated by the oracle only (no device amplitude: refused at grb_create)
+ORACLE_ONLY = {"c5_cms_pipi_restensor_rho_born", "c1_test_pipi_rescontensor_cardres_born"}
 LATE = {"c2_alice_pipi_restensor_f2_screened", "c2_alice_pipi_restensor_nstar1_born", "cc_alice_pipi_rescontensor_born"}
 
 
@@ -142,7 +147,7 @@ def main():
         if "RESTENSOR]<F>" in proc or "RES+CONTENSOR]<F>" in proc:
             # the resonance form factors exp(-(m^2 - M0^2)^2 / GeV^4) underflow beyond m ~ 4 GeV (|A|^2 denormal, then 0):
             # keep the system mass below ~3.1 GeV (m^2 is flat in u5 up to GENCUTS M_max^2 = 81 / 49 GeV^2)
-            u[:, 5] *= 0.12 if "CMSCUTS" in card else 0.2
+            u[:, 5] *= 0.12 if ("CMSCUTS" in card or "test.json" in card) else 0.2
         qed_alpha = 0
         run_card = card
         if card.startswith("@"):   # "@KEY=VALUE:card": run a copy of the card (written under output/) with that key replaced
@@ -157,7 +162,7 @@ def main():
             run_card = "./output/golden_%s.json" % name
             open(os.path.join(REF_TREE, run_card), "w").write(txt)
         r = ref_eval(run_card, proc, pom, u, tape, kappa=True)
-        np.savez_compressed(os.path.join(GOLDEN, "late" if name in LATE else "", name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
+        np.savez_compressed(os.path.join(GOLDEN, "late" if name in LATE else ("oracle_only" if name in ORACLE_ONLY else ""), name + ".npz"), card=card, process=proc, pomloop=pom, u=u, qed_alpha=qed_alpha,
                             nstars=nstars, tape=tape, W=r["W"], flags=r["flags"], t1=r["t1"], t2=r["t2"], s1=r["s1"],
                             s2=r["s2"], m2=r["m2"], t_hat=r["t_hat"], u_hat=r["u_hat"], hamp=r["hamp"][:, :4],
                             nhamp=r["nhamp"], kappa=r["kappa"], tape_used=r["tape_used"], p=r["p"][:, :5])

@@ -116,18 +116,18 @@ def test_closed_form_is_well_conditioned(grb, msa, host_tres):
     assert rel.max() < 1e-10 and np.median(rel) < 1e-13, (rel.max(), np.median(rel))
 
 
-def test_unsupported_resonance_classes_are_refused(grb):
-    """1- photoproduction (and 0- -> gamma gamma, vector-pair decays) of MTensorPomeron::ME3 have no device amplitude: the oracle
-    reports NaN -> amplitude_ok false, the engine refuses the descriptor at create time (tests/test_gpu_parity.py); nothing is
-    silently evaluated as something else."""
+def test_unsupported_resonance_classes_are_flagged(grb):
+    """0- resonances (-> gamma gamma only in the reference) and unknown gamma-V couplings have no amplitude for two pseudoscalars:
+    the oracle reports NaN -> amplitude_ok false; the engine refuses them (and the 1- block, which only the oracle restates) at
+    create time (tests/test_gpu_parity.py::test_tensor_resonance_scope).  Nothing is silently evaluated as something else."""
     from helpers import make_points
-    d = grb.parse_card(os.path.join(CARDS, "c5_cms_4pi.json"), "PP[RESTENSOR]<F> -> pi+ pi- @RES{rho_770:1}", 0)
+    d = grb.parse_card(os.path.join(CARDS, "c5_cms_4pi.json"), "PP[RESTENSOR]<F> -> pi+ pi- @RES{f0_980:1}", 0)
+    d.res[0].P = -1                                 # a 0- state as MTensorPomeron::ME3 would see it
     u, tape = make_points(512, 6, 8, 7)
     u[:, 5] *= 0.1
     w = oracle_eval(d, None, u, tape)
     passed = (w["flags"] & 7) == 7
     assert passed.sum() > 20 and np.all(w["w"] == 0) and np.all((w["flags"][passed] & 8) == 0)
-
 
 def _raw_sum(H, rp, n_res, mom, extended=0):
     out = np.zeros((len(mom), 2))

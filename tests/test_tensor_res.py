@@ -172,3 +172,18 @@ def test_closed_form_properties(grb, msa, host_tres):
     w = mom.reshape(-1, 7, 4)[:, [1, 0, 3, 2, 4, 5, 6], :].reshape(-1, 28)
     swapped = _raw_sum(host_tres, rp, 1, w, extended=1)
     assert np.max(np.abs(swapped - full) / np.abs(full)) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gra", "bin", "ref_eval")), reason="compiled reference (oracle/_ref) not present")
+def test_oracle_vs_live_reference_screened_C_class(grb, msa):
+    """PP[RES+CONTENSOR] in the <C> phase-space class with the screening loop on: the oracle against the live reference on fresh
+    points (the reference spends ~0.5 s per screened weight here, hence 40 points; measured max 7e-15 on 151)."""
+    from helpers import Eikonal, make_points, ref_eval
+    proc = "PP[RES+CONTENSOR]<C> -> pi+ pi- @RES{f0_980:1,f2_1270:1}"
+    d = grb.parse_card(os.path.join(CARDS, "c2_alice.json"), proc, 1)
+    u, tape = make_points(40, d.lipsdim, 8, 77)
+    r = ref_eval("./tests/processes/ALICECUTS.json", proc, 1, u, tape)
+    o = oracle_eval(d, Eikonal(msa[0], msa[1], msa[2]), u, tape)
+    nz = r["W"] != 0
+    assert nz.sum() > 20 and np.array_equal(o["flags"], r["flags"]) and np.array_equal(o["w"] != 0, nz)
+    assert np.max(np.abs(o["w"][nz] - r["W"][nz]) / np.abs(r["W"][nz])) < 1e-12

@@ -113,6 +113,10 @@ CASES = [
      "PP[RESTENSOR]<F> -> pi+ pi- @RES{f2_1270:1} @R[f2_1270]{g0:1.0,g1:0.5,g2:0.0,g3:0.0,g4:0.3,g5:0.0,g6:0.0}", 1, 320, 8, True),
     ("c2_alice_pipi_restensor_nstar1_born", "@NSTARS=1:./tests/processes/ALICECUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1024, 8, True),
     ("cc_alice_pipi_rescontensor_born", "./tests/processes/ALICECUTS.json", "PP[RES+CONTENSOR]<C> -> pi+ pi- @RES{f0_980:1,f2_1270:1}", 0, 1536, 8, True),
+    # (not kept: "@NSTARS=2:...ALICECUTS.json", "PP[RESTENSOR]<F> -> K+ K- @RES{f0_980:1,f2_1525:1}" -- with two excited forward systems the
+    #  rounding noise of the reference's explicit rank-6 contraction exceeds 8 kappa on single points (1.8e-9 against the closed form,
+    #  which agrees with its own long double evaluation): a golden of the reference's noise, not of the amplitude)
+    ("cc_alice_kk_restensor_born", "./tests/processes/ALICECUTS.json", "PP[RESTENSOR]<C> -> K+ K- @RES{f0_980:1,f2_1525:1,f0_1710:1}", 0, 1536, 8, True),
     # oracle only: the 1- block (gamma-pomeron fusion, full proton spinor vertices), alone and inside the shipped card's own list
     ("c5_cms_pipi_restensor_rho_born", "./tests/processes/CMSCUTS.json", "PP[RESTENSOR]<F> -> pi+ pi- @RES{rho_770:1}", 0, 1536, 8, True),
     ("c1_test_pipi_rescontensor_cardres_born", "./input/test.json", "PP[RES+CONTENSOR]<F> -> pi+ pi-", 0, 1536, 8, True),
@@ -123,7 +127,7 @@ CASES = [
 # after round 2's GPU budget was spent
 # the 1- (photoproduction) block of MTensorPomeron::ME3 is restated by the oracle only (no device amplitude: refused at grb_create)
 ORACLE_ONLY = {"c5_cms_pipi_restensor_rho_born", "c1_test_pipi_rescontensor_cardres_born"}
-LATE = {"c2_alice_pipi_restensor_f2_screened", "c2_alice_pipi_restensor_nstar1_born", "cc_alice_pipi_rescontensor_born"}
+LATE = {"cc_alice_kk_restensor_born", "c2_alice_pipi_restensor_f2_screened", "c2_alice_pipi_restensor_nstar1_born", "cc_alice_pipi_rescontensor_born"}
 
 
 def main():

@@ -1428,7 +1428,8 @@ static void tp_iG_ypp(const ost *S, v4 prime, v4 p, const cx ubar[4], const cx u
     }
     const m44 A = m44_scaler(&og_lo[mu], F1);
     m44 B = m44_scale(&SUM, (cx){0.0, 1.0});
-    B = m44_scaler(&B, 1.0 / (2 * 0.938272081));
+    for (int a = 0; a < 4; ++a) /* MMatrix::operator/(T): element / complex(2 m_p, 0) = component-wise division */
+      for (int b = 0; b < 4; ++b) { B.m[a][b].re /= (2 * 0.938272081); B.m[a][b].im /= (2 * 0.938272081); }
     B = m44_scaler(&B, F2);
     m44 G = m44_add(&A, &B);
     G = m44_scale(&G, (cx){-0.0 * e, -1.0 * e});

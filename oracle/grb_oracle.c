@@ -900,7 +900,7 @@ static void tp_iG_PppHE(const ost *S, v4 prime, v4 p, cx T[4][4]) {
   const double f = 3.0 * S->d->tpom.gPNN * o_F1(S, v4_m2(v4_sub(prime, p)));
   const cx FACTOR = {-0.0 * f, -1.0 * f};
   for (int u = 0; u < 4; ++u)
-    for (int v = 0; v < 4; ++v) T[u][v] = cx_mulr(FACTOR, v4_cov(psum, u) * v4_cov(psum, v));
+    for (int v = 0; v < 4; ++v) T[u][v] = cx_mulr(cx_mulr(FACTOR, v4_cov(psum, u)), v4_cov(psum, v)); /* FACTOR * (psum % u) * (psum % v): left to right */
 }
 /* :2203-2215 iG_Ppsps */
 static void tp_iG_Ppsps(v4 prime, v4 p, double g1, cx T[4][4]) {

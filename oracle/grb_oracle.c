@@ -1350,6 +1350,7 @@ static void tp_iG_PppbarP(const ost *S, v4 prime, const cx ubar[4], v4 pt, const
         for (int n1 = 0; n1 < 4; ++n1) T[m2][n2][m1][n1] = cx_mul(cx_mul(lhsF, o_vmv(ubarM, &RA[m1][n1], v)), rhsF);
     }
 }
+static cx tp_chain3x(cx G1[4][4], cx D1[4][4][4][4], cx C[4][4][4][4], int has_iD, cx iD, cx D2[4][4][4][4], cx G2[4][4], int lead_mzi);
 static double tensor_me4_2xF(ost *S) {
   og_init();
   const grb_process_desc *d = S->d;
@@ -1392,15 +1393,15 @@ static double tensor_me4_2xF(ost *S) {
       o_bar(u4, ubar4);
       tp_iG_PppbarP(S, p4, ubar4, pt, &iSFt, v3, mp3, Gt);
       tp_iG_PppbarP(S, p4, ubar4, pu, &iSFu, v3, mp3, Gu);
-      cx Mt = {0, 0}, Mu = {0, 0};
-      /* t: X13(a1,b1) Gt(a2,b2,a1,b1) X24(a2,b2);  u: X14(a1,b1) Gu(a1,b1,a2,b2) X23(a2,b2) */
+      /* FTensor, left to right: [G1a(m,n) D13(m,n,a1,b1)] Gt(a2,b2,a1,b1) -> (a2,b2); D24(a2,b2,m2,n2) -> (m2,n2); G2b(m2,n2).
+       * u channel: Gu(a1,b1,a2,b2).  (tp_chain3x of grb_oracle_tres.inc with the middle tensor indexed [a1][b1][a2][b2]) */
+      static cx Ct[4][4][4][4];
       for (int a1 = 0; a1 < 4; ++a1)
         for (int b1 = 0; b1 < 4; ++b1)
           for (int a2 = 0; a2 < 4; ++a2)
-            for (int b2 = 0; b2 < 4; ++b2) {
-              Mt = cx_add(Mt, cx_mul(cx_mul(X13[a1][b1], Gt[a2][b2][a1][b1]), X24[a2][b2]));
-              Mu = cx_add(Mu, cx_mul(cx_mul(X14[a1][b1], Gu[a1][b1][a2][b2]), X23[a2][b2]));
-            }
+            for (int b2 = 0; b2 < 4; ++b2) Ct[a1][b1][a2][b2] = Gt[a2][b2][a1][b1];
+      cx Mt = tp_chain3x(G1a, D13, Ct, 0, (cx){0, 0}, D24, G2b, 0);
+      cx Mu = tp_chain3x(G1a, D14, Gu, 0, (cx){0, 0}, D23, G2b, 0);
       Mt = cx_mulr(Mt, fft);
       Mu = cx_mulr(Mu, ffu);
       h[2 * h3 + h4] = cx_mul((cx){-0.0, -1.0}, cx_add(Mt, Mu));
@@ -1469,11 +1470,13 @@ static double tensor_me4_yyQED(ost *S) {
       o_bar(u2, ubar2);
       tp_iG_ypp(S, p1, pa, ubar1, ua, G1);
       tp_iG_ypp(S, p2, pb, ubar2, ub, G2);
-      /* iD_y(q2)(u,v) = -i g[u][v] / q2, MDirac.cc:372-378 */
-      cx L1[4], L2[4];
+      /* FTensor, left to right (:698-700): [(-zi) iG_1(m1)] iD_1(m1,n1) -> E2(n1); [iyFy_t(n2,n1) + iyFy_u(n1,n2)] E2(n1) -> E3(n2);
+       * iD_2(n2,m2) -> E4(m2); iG_2(m2).  iD_y(q2)(u,v) = -zi g[u][v] / q2 (complex / double, MDirac.cc:372-378): diagonal */
+      cx E2[4], D2y[4];
       for (int n = 0; n < 4; ++n) {
-        L1[n] = cx_mul(G1[n], cx_div((cx){-0.0 * o_g[n][n], -1.0 * o_g[n][n]}, (cx){S->t1, 0.0}));
-        L2[n] = cx_mul(cx_div((cx){-0.0 * o_g[n][n], -1.0 * o_g[n][n]}, (cx){S->t2, 0.0}), G2[n]);
+        const cx d1 = {(-0.0 * o_g[n][n]) / S->t1, (-1.0 * o_g[n][n]) / S->t1};
+        D2y[n] = (cx){(-0.0 * o_g[n][n]) / S->t2, (-1.0 * o_g[n][n]) / S->t2};
+        E2[n] = cx_mul(cx_mul(G1[n], (cx){-0.0, -1.0}), d1);
       }
       for (int h3 = 0; h3 < 2; ++h3)
         for (int h4 = 0; h4 < 2; ++h4) {
@@ -1484,9 +1487,12 @@ static double tensor_me4_yyQED(ost *S) {
           tp_iG_yeebary(ubar4, &iSFt, v3, Ft);
           tp_iG_yeebary(ubar4, &iSFu, v3, Fu);
           cx M = {0, 0};
-          for (int n1 = 0; n1 < 4; ++n1)
-            for (int n2 = 0; n2 < 4; ++n2) M = cx_add(M, cx_mul(cx_mul(L1[n1], cx_add(Ft[n2][n1], Fu[n1][n2])), L2[n2]));
-          S->hamp[k++] = cx_mul((cx){-0.0, -1.0}, M);
+          for (int n2 = 0; n2 < 4; ++n2) {
+            cx E3 = {0, 0};
+            for (int n1 = 0; n1 < 4; ++n1) E3 = cx_add(E3, cx_mul(cx_add(Ft[n2][n1], Fu[n1][n2]), E2[n1]));
+            M = cx_add(M, cx_mul(cx_mul(E3, D2y[n2]), G2[n2]));
+          }
+          S->hamp[k++] = M;
         }
     }
   S->nhamp = 16;

@@ -12,7 +12,9 @@
  * tests/golden/ (generator: tests/golden/make_golden.py); see tests/test_oracle_golden.py.
  *
  * Parity status: PINNED by reference-generated golden vectors (the reference's own test-suite holds no
- * vector for this path).
+ * vector for this path): bit-exact weights and flags on 75 golden sets -- Regge amplitudes, resonances,
+ * ladders, the whole tensor-pomeron code incl. the resonance amplitude ME3 (grb_oracle_tres.inc) -- except the HELAS
+ * yy -> l+ l- restatement (light-cone components: <= 1e-13).
  */
 #include "grb_oracle.h"
 

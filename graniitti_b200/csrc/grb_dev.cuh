@@ -184,6 +184,9 @@ __device__ __forceinline__ double rap_of(const v4 &a) { return 0.5 * log((a.e + 
 
 // reference include/Graniitti/MKinematics.h:33-64 SolvePz3_A: the t22 chain is kept in the reference's
 // association (it carries the rounding that decides the last bits of p1z); constants in s are hoisted.
+// Provenance: the reference's formula is itself the output of a computer-algebra system (a closed-form root of the
+// energy-momentum constraint, temporaries t2 .. t30); its term order IS the parity contract of the solved p_z, so the
+// checked variants below restate it term for term -- the folded `FAST` variants next to them are this repo's own.
 struct PzConst {
   double s, t7, t9, t14;  // s, sqrt(s), s^(3/2), s^2
 };
